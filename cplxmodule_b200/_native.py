@@ -1,0 +1,149 @@
+"""ctypes binding of ``csrc/libcplxk.so`` (C ABI declared in ``include/cplxk.h``).
+
+This is the only module that touches the native library.  There is no CPU or
+pure-torch implementation of the hot path behind it: if the library is missing
+or the tensors are not on a CUDA (sm_100) device the calls raise.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcplxk.so")
+
+F32, BF16 = 0, 1
+MATH_AUTO, MATH_TENSOR, MATH_SIMT = 0, 1, 2
+NOISE_INJECT, NOISE_PHILOX_TORCH, NOISE_PHILOX_FAST = 0, 1, 2
+KL_REAL_VD, KL_REAL_ARD, KL_CPLX_VD, KL_CPLX_ARD = 0, 1, 2, 3
+
+EXPORTS = (
+    "cplxk_abi_version", "cplxk_strerror", "cplxk_device_info", "cplxk_linear_fwd",
+    "cplxk_linear_vd_fwd", "cplxk_kl_workspace_bytes", "cplxk_kl", "cplxk_log_alpha",
+    "cplxk_conv2d_fwd", "cplxk_randn_philox_torch",
+)
+
+_lock = threading.Lock()
+_lib = None
+
+_vp, _i64, _u64, _u32, _int = (ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64,
+                               ctypes.c_uint32, ctypes.c_int)
+
+
+def _declare(lib):
+    lib.cplxk_abi_version.restype = _int
+    lib.cplxk_strerror.restype = ctypes.c_char_p
+    lib.cplxk_strerror.argtypes = [_int]
+    lib.cplxk_device_info.argtypes = [ctypes.POINTER(_int)] * 3
+    lib.cplxk_linear_fwd.argtypes = [_vp] * 8 + [_i64] * 3 + [_int, _int, _vp]
+    lib.cplxk_linear_vd_fwd.argtypes = ([_vp] * 9 + [_int, _u64, _u64, _u32] + [_vp] * 2
+                                        + [_i64] * 3 + [_int, _int, _vp])
+    lib.cplxk_kl_workspace_bytes.restype = ctypes.c_size_t
+    lib.cplxk_kl.argtypes = [_int, _vp, _vp, _vp, _i64, _int, _vp, _vp, ctypes.c_double,
+                             _vp, ctypes.c_size_t, _vp]
+    lib.cplxk_log_alpha.argtypes = [_vp, _vp, _vp, _i64, _int, _vp, ctypes.c_float, _vp, _vp]
+    lib.cplxk_conv2d_fwd.argtypes = ([_vp] * 9 + [_int, _u64, _u64, _u32] + [_vp] * 2
+                                     + [_i64] * 13 + [_int, _int, _vp])
+    lib.cplxk_randn_philox_torch.argtypes = [_vp, _i64, _u64, _u64, _u32, ctypes.c_float, _vp]
+    for name in EXPORTS:
+        getattr(lib, name)  # fail at load time, not at first use, if a symbol is missing
+
+
+def lib():
+    """Load (once) the native library; raise loudly when it is not there."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"cplxmodule_b200: native library {LIB_PATH} is missing. Build it with "
+                        "`python -m cplxmodule_b200.build` (needs nvcc). There is no CPU or "
+                        "pure-PyTorch fallback for the hot path."
+                    )
+                handle = ctypes.CDLL(LIB_PATH)
+                _declare(handle)
+                if handle.cplxk_abi_version() != 1:
+                    raise RuntimeError("cplxmodule_b200: libcplxk.so ABI version mismatch; rebuild")
+                _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(lib().cplxk_strerror(rc).decode())
+
+
+def dtype_code(dtype):
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"cplxmodule_b200 kernels take float32 or bfloat16 planes, got {dtype}")
+
+
+def require_cuda(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "cplxmodule_b200 runs its linear/conv/variational-dropout/KL path only as "
+                "sm_100a CUDA kernels: got a CPU tensor and there is no CPU fallback. "
+                "Move the module and its inputs to a B200 (`.cuda()`)."
+            )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def plane(t, dtype=None):
+    """Dense row-major plane (the C ABI wants unit inner stride, 16-byte aligned rows)."""
+    if t is None:
+        return None
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+# --------------------------------------------------------------- philox bookkeeping
+def philox_plan(device, numel):
+    """(seed, offset, threads, increment) replicating torch's CUDA ``normal_`` launch for
+    ``numel`` floats (ATen/native/cuda/DistributionTemplates.h: calc_execution_policy)."""
+    props = torch.cuda.get_device_properties(device)
+    block = 256
+    blocks_per_sm = props.max_threads_per_multi_processor // block
+    grid = min(props.multi_processor_count * blocks_per_sm, (numel + block - 1) // block)
+    grid = max(grid, 1)
+    threads = block * grid
+    increment = ((numel - 1) // (threads * 4) + 1) * 4
+    gen = torch.cuda.default_generators[device.index]
+    offset = gen.get_offset()
+    offset = (offset + 3) // 4 * 4
+    return gen, gen.initial_seed(), offset, threads, increment
+
+
+# -------------------------------------------------------------------- KL workspace
+_kl_ws = {}
+
+
+def kl_workspace(device):
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _kl_ws.get(key)
+    if ws is None:
+        nbytes = lib().cplxk_kl_workspace_bytes()
+        ws = torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=device)
+        _kl_ws[key] = ws
+    return ws

@@ -1,0 +1,167 @@
+// C-ABI entry points (include/cplxk.h): argument validation, path selection,
+// error reporting.  No torch types, no allocation, asynchronous on `stream`.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "epilogue.cuh"
+
+namespace cplxk {
+
+static thread_local cudaError_t g_last_cuda = cudaSuccess;
+void set_last_cuda_error(cudaError_t e) { g_last_cuda = e; }
+
+int fwd_simt_dispatch(int dtype, bool cplx, bool vd, const void* x_re, const void* x_im,
+                      const void* w_re, const void* w_im, const void* ls2, int64_t M, int64_t N,
+                      int64_t K, const EpiParams& ep, cudaStream_t st);
+bool fwd_tc_supported(int dtype, bool cplx, const void* x_re, const void* x_im, const void* w_re,
+                      const void* w_im, const void* ls2, int64_t M, int64_t N, int64_t K);
+int fwd_tc_dispatch(int dtype, bool cplx, bool vd, int swz, const void* x_re, const void* x_im,
+                    const void* w_re, const void* w_im, const void* ls2, int64_t M, int64_t N,
+                    int64_t K, const EpiParams& ep, cudaStream_t st);
+
+static int check_arch() {
+  static int ok = -1;  // per process; one process per GPU
+  if (ok < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+      set_last_cuda_error(cudaGetLastError());
+      return CPLXK_ERR_CUDA;
+    }
+    ok = (major == 10) ? 1 : 0;
+  }
+  return ok ? CPLXK_OK : CPLXK_ERR_ARCH;
+}
+
+static int env_swizzle() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("CPLXK_TC_SWIZZLE");
+    v = e ? std::atoi(e) : 0;
+    if (v != 64 && v != 128) v = 0;
+  }
+  return v;
+}
+
+static NoiseParams make_noise(int mode, uint64_t seed, uint64_t offset, uint32_t threads, bool cplx) {
+  NoiseParams np;
+  np.mode = mode;
+  np.seed_lo = static_cast<uint32_t>(seed);
+  np.seed_hi = static_cast<uint32_t>(seed >> 32);
+  np.ctr_base = offset >> 2;
+  np.threads = threads ? threads : 1u;
+  // torch: randn(...) / sqrt(2) on CUDA multiplies by the fp32 reciprocal of fp32(sqrt 2)
+  np.scale = cplx ? (1.0f / static_cast<float>(1.4142135623730951)) : 1.0f;
+  return np;
+}
+
+static int forward_common(bool vd, const void* x_re, const void* x_im, const void* w_re,
+                          const void* w_im, const void* b_re, const void* b_im, const void* ls2,
+                          const void* eps_re, const void* eps_im, int noise, uint64_t seed,
+                          uint64_t offset, uint32_t threads, void* y_re, void* y_im, int64_t M,
+                          int64_t N, int64_t K, int dtype, int math, void* stream) {
+  if (!x_re || !w_re || !y_re || M < 0 || N < 0 || K < 0) return CPLXK_ERR_BADARG;
+  const bool cplx = (x_im != nullptr);
+  if (cplx != (w_im != nullptr) || cplx != (y_im != nullptr)) return CPLXK_ERR_BADARG;
+  if ((b_re != nullptr) && cplx && !b_im) return CPLXK_ERR_BADARG;
+  if (dtype != CPLXK_F32 && dtype != CPLXK_BF16) return CPLXK_ERR_BADARG;
+  if (math < CPLXK_MATH_AUTO || math > CPLXK_MATH_SIMT) return CPLXK_ERR_BADARG;
+  if (vd) {
+    if (!ls2) return CPLXK_ERR_BADARG;
+    if (noise < CPLXK_NOISE_INJECT || noise > CPLXK_NOISE_PHILOX_FAST) return CPLXK_ERR_BADARG;
+    if (noise == CPLXK_NOISE_INJECT && (!eps_re || (cplx && !eps_im))) return CPLXK_ERR_BADARG;
+    if (noise == CPLXK_NOISE_PHILOX_TORCH && (threads == 0 || (offset & 3u))) return CPLXK_ERR_BADARG;
+  }
+  int rc = check_arch();
+  if (rc) return rc;
+  if (M == 0 || N == 0) return CPLXK_OK;
+
+  EpiParams ep;
+  ep.b_re = b_re, ep.b_im = b_im, ep.eps_re = eps_re, ep.eps_im = eps_im;
+  ep.y_re = y_re, ep.y_im = y_im;
+  ep.M = M, ep.N = N, ep.plane_elems = M * N;
+  ep.noise = make_noise(vd ? noise : CPLXK_NOISE_INJECT, seed, offset, threads, cplx);
+
+  auto st = static_cast<cudaStream_t>(stream);
+  const bool tc_ok = fwd_tc_supported(dtype, cplx, x_re, x_im, w_re, w_im, vd ? ls2 : nullptr, M, N, K);
+  if (math == CPLXK_MATH_TENSOR && !tc_ok) return CPLXK_ERR_ALIGN;
+  if (math != CPLXK_MATH_SIMT && tc_ok) {
+    int swz = env_swizzle();
+    if (!swz) swz = (cplx && vd) ? 64 : 128;
+    return fwd_tc_dispatch(dtype, cplx, vd, swz, x_re, x_im, w_re, w_im, ls2, M, N, K, ep, st);
+  }
+  return fwd_simt_dispatch(dtype, cplx, vd, x_re, x_im, w_re, w_im, ls2, M, N, K, ep, st);
+}
+
+__global__ void randn_philox_torch_kernel(float* out, int64_t n, NoiseParams np) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 16;
+  for (int64_t i0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 16; i0 < n;
+       i0 += stride) {
+    TorchNoiseCursor cur;
+    cur.seek(static_cast<uint64_t>(i0), np.threads);
+    for (int j = 0; j < 16 && i0 + j < n; ++j) out[i0 + j] = cur.next(np) * np.scale;
+  }
+}
+
+}  // namespace cplxk
+
+using namespace cplxk;
+
+extern "C" int cplxk_abi_version(void) { return CPLXK_ABI_VERSION; }
+
+extern "C" const char* cplxk_strerror(int status) {
+  static thread_local char buf[256];
+  switch (status) {
+    case CPLXK_OK: return "ok";
+    case CPLXK_ERR_BADARG: return "cplxk: bad argument (null pointer, bad enum or negative size)";
+    case CPLXK_ERR_ALIGN: return "cplxk: pointer/pitch violates the 16-byte alignment contract of the tensor-core path";
+    case CPLXK_ERR_ARCH: return "cplxk: current device is not compute capability 10.x (sm_100a kernels only; there is no CPU or other-arch path)";
+    case CPLXK_ERR_CUDA:
+      std::snprintf(buf, sizeof(buf), "cplxk: CUDA error: %s", cudaGetErrorString(g_last_cuda));
+      return buf;
+    case CPLXK_ERR_UNSUPPORTED: return "cplxk: unsupported configuration";
+    case CPLXK_ERR_WORKSPACE: return "cplxk: workspace missing or too small";
+  }
+  return "cplxk: unknown status";
+}
+
+extern "C" int cplxk_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  CPLXK_CUDA_TRY(cudaGetDevice(&dev));
+  if (sm_count) CPLXK_CUDA_TRY(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+  if (cc_major) CPLXK_CUDA_TRY(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_minor) CPLXK_CUDA_TRY(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return CPLXK_OK;
+}
+
+extern "C" int cplxk_linear_fwd(const void* x_re, const void* x_im, const void* w_re,
+                                const void* w_im, const void* b_re, const void* b_im, void* y_re,
+                                void* y_im, int64_t M, int64_t N, int64_t K, int dtype, int math,
+                                void* stream) {
+  return forward_common(false, x_re, x_im, w_re, w_im, b_re, b_im, nullptr, nullptr, nullptr, 0, 0,
+                        0, 0, y_re, y_im, M, N, K, dtype, math, stream);
+}
+
+extern "C" int cplxk_linear_vd_fwd(const void* x_re, const void* x_im, const void* w_re,
+                                   const void* w_im, const void* b_re, const void* b_im,
+                                   const void* log_sigma2, const void* eps_re, const void* eps_im,
+                                   int noise, uint64_t seed, uint64_t offset,
+                                   uint32_t philox_threads, void* y_re, void* y_im, int64_t M,
+                                   int64_t N, int64_t K, int dtype, int math, void* stream) {
+  return forward_common(true, x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise,
+                        seed, offset, philox_threads, y_re, y_im, M, N, K, dtype, math, stream);
+}
+
+extern "C" int cplxk_randn_philox_torch(float* out, int64_t n, uint64_t seed, uint64_t offset,
+                                        uint32_t philox_threads, float scale, void* stream) {
+  if (!out || n < 0 || philox_threads == 0 || (offset & 3u)) return CPLXK_ERR_BADARG;
+  if (n == 0) return CPLXK_OK;
+  NoiseParams np = make_noise(CPLXK_NOISE_PHILOX_TORCH, seed, offset, philox_threads, false);
+  np.scale = scale;
+  int64_t want = (n + 16 * 256 - 1) / (16 * 256);
+  int grid = static_cast<int>(want > 4096 ? 4096 : want);
+  randn_philox_torch_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, np);
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
+}

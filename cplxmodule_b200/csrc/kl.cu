@@ -1,0 +1,328 @@
+// kl_reduce: one HBM pass over (weight planes, log_sigma2) -> per-element KL
+// penalty and/or its sum.  HBM-bandwidth bound: 128-bit coalesced loads, a
+// few dozen flops per element, warp-shuffle + block reduction, one double
+// partial per CTA and a deterministic last-CTA finish (no float atomics).
+//
+// Reference formulas (cplxmodule/nn/relevance/...):
+//   log_alpha           real/base.py:23-26, complex/base.py:27-31 (|w| = sqrt(re^2+im^2), cplx.py:183-192)
+//   REAL_VD  penalty    real/vd.py:74-76     0.5 softplus(-la) + 0.63576 sigmoid(-1.48695 la - 1.87320)
+//   REAL_ARD penalty    real/ard.py:39       0.5 softplus(-la)
+//   CPLX_VD  penalty    complex/vd.py:95-99  gamma - la - Ei(-exp(-la))      (host scipy in the reference)
+//   CPLX_ARD penalty    complex/ard.py:39    softplus(-la)
+#include "common.cuh"
+
+namespace cplxk {
+
+constexpr int kKlThreads = 256;
+constexpr int kKlMaxBlocks = 2048;
+
+struct KlWorkspace {
+  unsigned int ticket;
+  unsigned int pad[3];
+  double partial[kKlMaxBlocks];
+};
+
+__device__ __forceinline__ float softplus_f(float x) {
+  // log(1 + e^x), stable for both signs (torch switches to identity above 20:
+  // same value in fp32)
+  return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x)));
+}
+
+// Ein(t) = gamma + ln t + E1(t) = gamma - la - Ei(-exp(-la)),  t = exp(-la) > 0.
+// t <= 1: t * P8(t)  (minimax fit of the entire series sum (-1)^(k+1) t^k / (k k!),
+//         rel. err 1e-9, tools/fit_ein.py) -- cancellation free, unlike the
+//         reference's fp32 "gamma + n - Ei" which returns 0 for la >= 15.
+// t >  1: gamma + n + exp(-t)/t * R44(t), Abramowitz & Stegun 5.1.56 (|eps| < 2e-8).
+__device__ __forceinline__ float ein_from_neg_log_alpha(float n) {
+  const float t = __expf(n);
+  if (t <= 1.0f) {
+    float p = 2.055084504e-07f;  // deg-8 fit, highest power first
+    p = fmaf(p, t, -2.924913139e-06f);
+    p = fmaf(p, t, 2.817395093e-05f);
+    p = fmaf(p, t, -2.313831111e-04f);
+    p = fmaf(p, t, 1.666633120e-03f);
+    p = fmaf(p, t, -1.041666021e-02f);
+    p = fmaf(p, t, 5.555555493e-02f);
+    p = fmaf(p, t, -2.500000000e-01f);
+    p = fmaf(p, t, 1.0f);
+    return t * p;
+  }
+  const float kGamma = 0.57721566490153286f;
+  float e1 = 0.f;
+  if (t < 60.f) {
+    float num = (((t + 8.5733287401f) * t + 18.0590169730f) * t + 8.6347608925f) * t + 0.2677737343f;
+    float den = (((t + 9.5733223454f) * t + 25.6329561486f) * t + 21.0996530827f) * t + 3.9584969228f;
+    e1 = __expf(-t) * __fdividef(num, den * t);
+  }
+  return kGamma + n + e1;
+}
+
+template <int kKind>
+__device__ __forceinline__ float log_alpha_of(float wr, float wi, float ls2) {
+  float aw;
+  if constexpr (kKind == CPLXK_KL_CPLX_VD || kKind == CPLXK_KL_CPLX_ARD) {
+    aw = sqrtf(fmaf(wr, wr, wi * wi));
+  } else {
+    aw = fabsf(wr);
+  }
+  return ls2 - 2.0f * logf(aw + 1e-12f);
+}
+
+template <int kKind>
+__device__ __forceinline__ float penalty_of(float la) {
+  const float n = -la;
+  if constexpr (kKind == CPLXK_KL_REAL_VD) {
+    float z = fmaf(1.48695f, n, -1.87320f);
+    float sig = __fdividef(1.0f, 1.0f + __expf(-z));
+    return fmaf(0.63576f, sig, 0.5f * softplus_f(n));
+  } else if constexpr (kKind == CPLXK_KL_REAL_ARD) {
+    return 0.5f * softplus_f(n);
+  } else if constexpr (kKind == CPLXK_KL_CPLX_VD) {
+    return ein_from_neg_log_alpha(n);
+  } else {
+    return softplus_f(n);
+  }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = (l < kKlThreads / 32) ? sh[l] : 0.0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  return r;  // valid in thread 0
+}
+
+template <typename T, int kKind, bool kVecOK>
+__global__ void __launch_bounds__(kKlThreads)
+kl_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T* __restrict__ ls2,
+          int64_t n, T* __restrict__ out_elem, float* __restrict__ out_sum, double scale,
+          KlWorkspace* __restrict__ ws) {
+  constexpr bool kCplx = (kKind == CPLXK_KL_CPLX_VD || kKind == CPLXK_KL_CPLX_ARD);
+  constexpr int V = Elem<T>::kVec;
+  __shared__ double sh[kKlThreads / 32];
+  __shared__ bool is_last;
+
+  float acc = 0.f;
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * kKlThreads + threadIdx.x;
+  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * kKlThreads;
+
+  int64_t done = 0;
+  if constexpr (kVecOK) {
+    const int64_t nvec = n / V;
+    // two independent 16-byte streams per plane in flight per thread
+    for (int64_t i = tid; i < nvec; i += 2 * nthreads) {
+      const int64_t i2 = i + nthreads;
+      const bool has2 = i2 < nvec;
+      Vec16<T> a0, b0, c0, a1, b1, c1;
+      a0.load(w_re + i * V);
+      if constexpr (kCplx) b0.load(w_im + i * V);
+      c0.load(ls2 + i * V);
+      if (has2) {
+        a1.load(w_re + i2 * V);
+        if constexpr (kCplx) b1.load(w_im + i2 * V);
+        c1.load(ls2 + i2 * V);
+      }
+      Vec16<T> o;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float p = penalty_of<kKind>(log_alpha_of<kKind>(a0.v[j], kCplx ? b0.v[j] : 0.f, c0.v[j]));
+        acc += p;
+        o.v[j] = p;
+      }
+      if (out_elem) o.store(out_elem + i * V);
+      if (has2) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          float p = penalty_of<kKind>(log_alpha_of<kKind>(a1.v[j], kCplx ? b1.v[j] : 0.f, c1.v[j]));
+          acc += p;
+          o.v[j] = p;
+        }
+        if (out_elem) o.store(out_elem + i2 * V);
+      }
+    }
+    done = nvec * V;
+  }
+  for (int64_t i = done + tid; i < n; i += nthreads) {
+    float wr = Elem<T>::to_f(w_re[i]);
+    float wi = kCplx ? Elem<T>::to_f(w_im[i]) : 0.f;
+    float p = penalty_of<kKind>(log_alpha_of<kKind>(wr, wi, Elem<T>::to_f(ls2[i])));
+    acc += p;
+    if (out_elem) out_elem[i] = Elem<T>::from_f(p);
+  }
+
+  if (out_sum == nullptr) return;
+
+  double bsum = block_sum(static_cast<double>(acc), sh);
+  if (threadIdx.x == 0) {
+    ws->partial[blockIdx.x] = bsum;
+    __threadfence();
+    unsigned int t = atomicAdd(&ws->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double v = 0.0;
+  for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += kKlThreads)
+    v += *(volatile double*)&ws->partial[i];
+  __syncthreads();  // sh reuse
+  double total = block_sum(v, sh);
+  if (threadIdx.x == 0) {
+    *out_sum = static_cast<float>(total * scale);
+    ws->ticket = 0;  // restore the workspace for the next call on this stream
+  }
+}
+
+template <typename T, bool kCplx, bool kVecOK>
+__global__ void __launch_bounds__(256)
+log_alpha_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im,
+                 const T* __restrict__ ls2, int64_t n, T* __restrict__ out_la, float threshold,
+                 T* __restrict__ out_mask) {
+  constexpr int V = Elem<T>::kVec;
+  constexpr int kKind = kCplx ? CPLXK_KL_CPLX_ARD : CPLXK_KL_REAL_ARD;
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int64_t done = 0;
+  if constexpr (kVecOK) {
+    const int64_t nvec = n / V;
+    for (int64_t i = tid; i < nvec; i += nthreads) {
+      Vec16<T> a, b, c, la, mk;
+      a.load(w_re + i * V);
+      if constexpr (kCplx) b.load(w_im + i * V);
+      c.load(ls2 + i * V);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        la.v[j] = log_alpha_of<kKind>(a.v[j], kCplx ? b.v[j] : 0.f, c.v[j]);
+        mk.v[j] = la.v[j] <= threshold ? 1.f : 0.f;
+      }
+      if (out_la) la.store(out_la + i * V);
+      if (out_mask) mk.store(out_mask + i * V);
+    }
+    done = nvec * V;
+  }
+  for (int64_t i = done + tid; i < n; i += nthreads) {
+    float la = log_alpha_of<kKind>(Elem<T>::to_f(w_re[i]), kCplx ? Elem<T>::to_f(w_im[i]) : 0.f,
+                                   Elem<T>::to_f(ls2[i]));
+    if (out_la) out_la[i] = Elem<T>::from_f(la);
+    if (out_mask) out_mask[i] = Elem<T>::from_f(la <= threshold ? 1.f : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+static int sm_count_cached() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  }
+  return sms;
+}
+
+template <typename T, int kKind>
+static int launch_kl(const void* w_re, const void* w_im, const void* ls2, int64_t n, void* out_elem,
+                     float* out_sum, double scale, KlWorkspace* ws, cudaStream_t st) {
+  constexpr int V = Elem<T>::kVec;
+  const bool vec_ok = aligned16(w_re) && aligned16(ls2) && (w_im == nullptr || aligned16(w_im)) &&
+                      (out_elem == nullptr || aligned16(out_elem));
+  int64_t work = (n + V - 1) / V;
+  int64_t want = (work + 2 * kKlThreads - 1) / (2 * kKlThreads);
+  int grid = static_cast<int>(want < 1 ? 1 : (want > 8 * sm_count_cached() ? 8 * sm_count_cached() : want));
+  if (grid > kKlMaxBlocks) grid = kKlMaxBlocks;
+  auto a = static_cast<const T*>(w_re);
+  auto b = static_cast<const T*>(w_im);
+  auto c = static_cast<const T*>(ls2);
+  auto o = static_cast<T*>(out_elem);
+  if (vec_ok)
+    kl_kernel<T, kKind, true><<<grid, kKlThreads, 0, st>>>(a, b, c, n, o, out_sum, scale, ws);
+  else
+    kl_kernel<T, kKind, false><<<grid, kKlThreads, 0, st>>>(a, b, c, n, o, out_sum, scale, ws);
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
+}
+
+template <typename T>
+static int dispatch_kl(int kind, const void* w_re, const void* w_im, const void* ls2, int64_t n,
+                       void* out_elem, float* out_sum, double scale, KlWorkspace* ws,
+                       cudaStream_t st) {
+  switch (kind) {
+    case CPLXK_KL_REAL_VD:
+      return launch_kl<T, CPLXK_KL_REAL_VD>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st);
+    case CPLXK_KL_REAL_ARD:
+      return launch_kl<T, CPLXK_KL_REAL_ARD>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st);
+    case CPLXK_KL_CPLX_VD:
+      return launch_kl<T, CPLXK_KL_CPLX_VD>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st);
+    case CPLXK_KL_CPLX_ARD:
+      return launch_kl<T, CPLXK_KL_CPLX_ARD>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st);
+  }
+  return CPLXK_ERR_BADARG;
+}
+
+}  // namespace cplxk
+
+using namespace cplxk;
+
+extern "C" size_t cplxk_kl_workspace_bytes(void) { return sizeof(KlWorkspace); }
+
+extern "C" int cplxk_kl(int kind, const void* w_re, const void* w_im, const void* log_sigma2,
+                        int64_t n, int dtype, void* out_elem, float* out_sum, double scale,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (!w_re || !log_sigma2 || n < 0 || (!out_elem && !out_sum)) return CPLXK_ERR_BADARG;
+  const bool cplx = (kind == CPLXK_KL_CPLX_VD || kind == CPLXK_KL_CPLX_ARD);
+  if (kind < 0 || kind > 3 || cplx != (w_im != nullptr)) return CPLXK_ERR_BADARG;
+  if (out_sum) {
+    if (!workspace || workspace_bytes < sizeof(KlWorkspace)) return CPLXK_ERR_WORKSPACE;
+    if (!aligned16(workspace)) return CPLXK_ERR_ALIGN;
+  }
+  auto st = static_cast<cudaStream_t>(stream);
+  auto ws = static_cast<KlWorkspace*>(workspace);
+  if (dtype == CPLXK_F32)
+    return dispatch_kl<float>(kind, w_re, w_im, log_sigma2, n, out_elem, out_sum, scale, ws, st);
+  if (dtype == CPLXK_BF16)
+    return dispatch_kl<__nv_bfloat16>(kind, w_re, w_im, log_sigma2, n, out_elem, out_sum, scale, ws, st);
+  return CPLXK_ERR_BADARG;
+}
+
+template <typename T>
+static int launch_log_alpha(const void* w_re, const void* w_im, const void* ls2, int64_t n,
+                            void* out_la, float thr, void* out_mask, cudaStream_t st) {
+  constexpr int V = Elem<T>::kVec;
+  const bool vec_ok = aligned16(w_re) && aligned16(ls2) && (!w_im || aligned16(w_im)) &&
+                      (!out_la || aligned16(out_la)) && (!out_mask || aligned16(out_mask));
+  int64_t work = (n + V - 1) / V;
+  int64_t want = (work + 255) / 256;
+  int grid = static_cast<int>(want < 1 ? 1 : (want > 16 * 148 ? 16 * 148 : want));
+  auto a = static_cast<const T*>(w_re);
+  auto b = static_cast<const T*>(w_im);
+  auto c = static_cast<const T*>(ls2);
+  auto o = static_cast<T*>(out_la);
+  auto m = static_cast<T*>(out_mask);
+  if (w_im) {
+    if (vec_ok) log_alpha_kernel<T, true, true><<<grid, 256, 0, st>>>(a, b, c, n, o, thr, m);
+    else log_alpha_kernel<T, true, false><<<grid, 256, 0, st>>>(a, b, c, n, o, thr, m);
+  } else {
+    if (vec_ok) log_alpha_kernel<T, false, true><<<grid, 256, 0, st>>>(a, b, c, n, o, thr, m);
+    else log_alpha_kernel<T, false, false><<<grid, 256, 0, st>>>(a, b, c, n, o, thr, m);
+  }
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
+}
+
+extern "C" int cplxk_log_alpha(const void* w_re, const void* w_im, const void* log_sigma2,
+                               int64_t n, int dtype, void* out_log_alpha, float threshold,
+                               void* out_mask, void* stream) {
+  if (!w_re || !log_sigma2 || n < 0 || (!out_log_alpha && !out_mask)) return CPLXK_ERR_BADARG;
+  auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == CPLXK_F32)
+    return launch_log_alpha<float>(w_re, w_im, log_sigma2, n, out_log_alpha, threshold, out_mask, st);
+  if (dtype == CPLXK_BF16)
+    return launch_log_alpha<__nv_bfloat16>(w_re, w_im, log_sigma2, n, out_log_alpha, threshold, out_mask, st);
+  return CPLXK_ERR_BADARG;
+}

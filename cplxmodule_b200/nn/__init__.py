@@ -1,0 +1,4 @@
+from .modules import *
+from .modules.base import CplxParameter
+from . import init
+from . import relevance

@@ -1,0 +1,110 @@
+"""Complex-valued variational dropout / ARD layers.
+
+Reference: ``cplxmodule/nn/relevance/complex/{base,vd,ard}.py``.  State-dict keys:
+``weight.real, weight.imag, bias.real, bias.imag, log_sigma2``.
+The exact complex-VD KL ``gamma - log_alpha - Ei(-1/alpha)`` is evaluated on the device
+(the reference round-trips through host ``scipy.special.expi``, ``complex/vd.py:31-36``).
+"""
+import torch
+
+from ... import _native as nv
+from ... import cplx, ops
+from ..modules.conv import CplxConv1d, CplxConv2d
+from ..modules.linear import CplxLinear
+from .base import BaseARD
+
+
+class _CplxGaussianMixin:
+    _kl_kind = None
+    __sparsity_ignore__ = ("log_sigma2",)
+
+    def reset_variational_parameters(self):
+        self.log_sigma2.data.fill_(-10.0)
+
+    @property
+    def log_alpha(self):
+        w = self.weight
+        return ops.log_alpha(w.real, w.imag, self.log_sigma2)
+
+    @property
+    def penalty(self):
+        w = self.weight
+        return ops.kl(self._kl_kind, w.real, w.imag, self.log_sigma2, None)
+
+    def _penalty_reduced(self, reduction):
+        w = self.weight
+        return ops.kl(self._kl_kind, w.real, w.imag, self.log_sigma2, reduction)
+
+    def relevance(self, *, threshold, **kwargs):
+        w = self.weight
+        with torch.no_grad():
+            return ops.log_alpha(w.real, w.imag, self.log_sigma2, threshold=threshold)
+
+    def sparsity(self, *, threshold, **kwargs):
+        w = self.weight
+        n_dropped = float(w.real.numel()) - float(self.relevance(threshold=threshold).sum().item())
+        return [(id(w.real), n_dropped), (id(w.imag), n_dropped)]
+
+
+class CplxLinearGaussian(_CplxGaussianMixin, CplxLinear):
+    """Complex linear layer with the fused local-reparameterisation forward."""
+
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__(in_features, out_features, bias=bias)
+        self.log_sigma2 = torch.nn.Parameter(torch.empty(out_features, in_features))
+        self.reset_variational_parameters()
+
+    def forward(self, input, eps=None):
+        if not self.training:
+            return super().forward(input)
+        w, b = self.weight, self.bias
+        b_re, b_im = (None, None) if b is None else (b.real, b.imag)
+        eps = None if eps is None else (eps.real, eps.imag)
+        re, im = ops.cplx_linear_vd(input.real, input.imag, w.real, w.imag, b_re, b_im,
+                                    self.log_sigma2, eps=eps)
+        return cplx.Cplx(re, im)
+
+
+class CplxLinearVD(CplxLinearGaussian, BaseARD):
+    """Complex variational dropout with the exact KL divergence."""
+    _kl_kind = nv.KL_CPLX_VD
+
+
+class CplxLinearARD(CplxLinearGaussian, BaseARD):
+    """Complex ARD: ``softplus(-log_alpha)``."""
+    _kl_kind = nv.KL_CPLX_ARD
+
+
+class _CplxConvGaussianMixin(_CplxGaussianMixin):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                 groups=1, bias=True, padding_mode="zeros"):
+        super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=padding,
+                         dilation=dilation, groups=groups, bias=bias, padding_mode=padding_mode)
+        if self.padding_mode != "zeros":
+            raise ValueError(f"Only `zeros` padding mode is supported. Got `{self.padding_mode}`.")
+        self.log_sigma2 = torch.nn.Parameter(torch.empty(*self.weight.shape))
+        self.reset_variational_parameters()
+
+    def forward(self, input, eps=None):
+        if not self.training:
+            return super().forward(input)
+        from ... import conv_ops
+        return conv_ops.cplx_convnd(len(self.kernel_size), input, self.weight, self.bias,
+                                    self.stride, self.padding, self.dilation, self.groups,
+                                    self.padding_mode, log_sigma2=self.log_sigma2, eps=eps)
+
+
+class CplxConv1dVD(_CplxConvGaussianMixin, CplxConv1d, BaseARD):
+    _kl_kind = nv.KL_CPLX_VD
+
+
+class CplxConv2dVD(_CplxConvGaussianMixin, CplxConv2d, BaseARD):
+    _kl_kind = nv.KL_CPLX_VD
+
+
+class CplxConv1dARD(_CplxConvGaussianMixin, CplxConv1d, BaseARD):
+    _kl_kind = nv.KL_CPLX_ARD
+
+
+class CplxConv2dARD(_CplxConvGaussianMixin, CplxConv2d, BaseARD):
+    _kl_kind = nv.KL_CPLX_ARD

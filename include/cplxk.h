@@ -1,0 +1,185 @@
+/*
+ * cplxk.h -- C ABI of the B200-native (sm_100a) kernels behind cplxmodule's
+ * complex linear / variational-dropout forward / KL `penalties()` hot path.
+ *
+ * The reference (ivannz/cplxmodule, pure Python) has no FFI of its own; the
+ * seam a maintainer binds is its functional layer.  Each entry point below
+ * names the reference function it replaces (paths relative to the reference
+ * tree).  See INTEGRATION.md for the ctypes stub that goes into the
+ * reference's `cplx.py` / `nn/relevance/*`.
+ *
+ * Conventions
+ * -----------
+ *  - plain pointers + sizes, no torch types; all pointers are DEVICE pointers
+ *    on the device that is current on the calling thread, unless noted;
+ *  - planes are row-major with unit inner stride ("split" complex: separate
+ *    real and imaginary planes, as `Cplx.real` / `Cplx.imag`);
+ *  - the library allocates nothing and keeps no state besides per-process
+ *    function attributes; the caller owns every buffer (incl. workspace);
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *    no implicit synchronisation;
+ *  - return value: 0 on success, negative cplxk_status otherwise -- never
+ *    throws, never aborts.  `cplxk_strerror` maps a status to text;
+ *  - there is NO CPU path: a machine without an sm_100 device gets
+ *    CPLXK_ERR_ARCH / CPLXK_ERR_CUDA.
+ */
+#ifndef CPLXK_H_
+#define CPLXK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPLXK_ABI_VERSION 1
+
+typedef enum {
+  CPLXK_OK = 0,
+  CPLXK_ERR_BADARG = -1,   /* null pointer / bad enum / negative size          */
+  CPLXK_ERR_ALIGN = -2,    /* pointer or pitch violates the alignment contract */
+  CPLXK_ERR_ARCH = -3,     /* device is not compute capability 10.x            */
+  CPLXK_ERR_CUDA = -4,     /* a CUDA runtime/driver call failed                */
+  CPLXK_ERR_UNSUPPORTED = -5,
+  CPLXK_ERR_WORKSPACE = -6 /* workspace too small                              */
+} cplxk_status;
+
+/* storage type of every plane in a call (inputs, parameters and outputs) */
+typedef enum { CPLXK_F32 = 0, CPLXK_BF16 = 1 } cplxk_dtype;
+
+/* arithmetic used by the GEMM-shaped part of a forward call */
+typedef enum {
+  CPLXK_MATH_AUTO = 0,   /* tensor cores when the shape/alignment allows, else SIMT */
+  CPLXK_MATH_TENSOR = 1, /* tcgen05: tf32 operands for F32 planes, bf16 for BF16;
+                            fp32 accumulation in TMEM.  Needs 16-byte aligned
+                            planes and K*sizeof(elem) % 16 == 0.              */
+  CPLXK_MATH_SIMT = 2    /* exact fp32 FMA on CUDA cores (any shape)          */
+} cplxk_math;
+
+/* source of the local-reparameterisation noise */
+typedef enum {
+  CPLXK_NOISE_INJECT = 0,       /* read eps_re/eps_im planes [M,N] supplied by the caller */
+  CPLXK_NOISE_PHILOX_TORCH = 1, /* regenerate, inside the epilogue, exactly the
+                                   Philox4x32-10 stream `torch.randn(2,M,N,device='cuda')/sqrt(2)`
+                                   (complex) or `torch.randn(M,N,device='cuda')` (real)
+                                   would produce for (seed, offset, philox_threads)       */
+  CPLXK_NOISE_PHILOX_FAST = 2   /* library-private counter layout: one Philox call
+                                   feeds 4 normals of one thread (4x cheaper)             */
+} cplxk_noise;
+
+typedef enum {
+  CPLXK_KL_REAL_VD = 0,  /* nn/relevance/real/vd.py:74-76     */
+  CPLXK_KL_REAL_ARD = 1, /* nn/relevance/real/ard.py:39       */
+  CPLXK_KL_CPLX_VD = 2,  /* nn/relevance/complex/vd.py:95-99  */
+  CPLXK_KL_CPLX_ARD = 3  /* nn/relevance/complex/ard.py:39    */
+} cplxk_kl_kind;
+
+int cplxk_abi_version(void);
+const char* cplxk_strerror(int status);
+
+/* Number of SMs / compute capability of the current device (host ints). */
+int cplxk_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/*
+ * Complex (or real) affine map  y = x W^T + b.
+ * Replaces cplx.linear == linear_naive (cplxmodule/cplx.py:634-648,698) and,
+ * with x_im == w_im == NULL, torch.nn.functional.linear as used by
+ * nn/relevance/real/base.py:44.
+ *   x_re,x_im : [M,K]   w_re,w_im : [N,K]   b_re,b_im : [N] or NULL
+ *   y_re,y_im : [M,N]   (y_im NULL for the real map)
+ */
+int cplxk_linear_fwd(const void* x_re, const void* x_im,
+                     const void* w_re, const void* w_im,
+                     const void* b_re, const void* b_im,
+                     void* y_re, void* y_im,
+                     int64_t M, int64_t N, int64_t K,
+                     int dtype, int math, void* stream);
+
+/*
+ * Local-reparameterisation forward of a Gaussian (variational dropout) linear
+ * layer, fused: mean GEMM(s), variance GEMM |x|^2 . exp(log_sigma2)^T, noise,
+ * and  y = mu + eps * sqrt(max(s2, 1e-8)).
+ * Replaces CplxLinearGaussian.forward (nn/relevance/complex/base.py:43-56)
+ * and, with x_im == w_im == NULL, LinearGaussian.forward
+ * (nn/relevance/real/base.py:43-49).
+ *   log_sigma2 : [N,K]
+ *   noise == INJECT        : eps_re (,eps_im) are [M,N] planes of dtype
+ *   noise == PHILOX_*      : eps_* ignored; (seed, offset) as in torch's CUDA
+ *                            generator state (offset % 4 == 0);
+ *                            philox_threads = 256 * grid of torch's randn kernel
+ *                            (only used by PHILOX_TORCH).
+ */
+int cplxk_linear_vd_fwd(const void* x_re, const void* x_im,
+                        const void* w_re, const void* w_im,
+                        const void* b_re, const void* b_im,
+                        const void* log_sigma2,
+                        const void* eps_re, const void* eps_im,
+                        int noise, uint64_t seed, uint64_t offset,
+                        uint32_t philox_threads,
+                        void* y_re, void* y_im,
+                        int64_t M, int64_t N, int64_t K,
+                        int dtype, int math, void* stream);
+
+/*
+ * KL penalty of a variational layer over n parameters, one HBM pass:
+ *   log_alpha = log_sigma2 - 2 log(|w| + 1e-12)
+ *     (nn/relevance/real/base.py:23-26, complex/base.py:27-31)
+ *   penalty(kind, log_alpha)            (see cplxk_kl_kind)
+ * out_elem (nullable): per-element penalty, dtype planes  (reduction=None)
+ * out_sum  (nullable): one float, scale * sum(penalty)    (reduction="sum"/"mean",
+ *                      nn/relevance/base.py:135-139)
+ * w_im must be NULL for the REAL kinds.
+ * workspace: cplxk_kl_workspace_bytes() bytes, 16-byte aligned, zero-filled
+ *            once by the caller before first use (the kernel restores it).
+ */
+size_t cplxk_kl_workspace_bytes(void);
+int cplxk_kl(int kind, const void* w_re, const void* w_im,
+             const void* log_sigma2, int64_t n, int dtype,
+             void* out_elem, float* out_sum, double scale,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * log_alpha itself and the relevance mask  (log_alpha <= threshold)
+ * (complex/vd.py:47-60, real/vd.py:13-24).  Either output may be NULL.
+ */
+int cplxk_log_alpha(const void* w_re, const void* w_im, const void* log_sigma2,
+                    int64_t n, int dtype, void* out_log_alpha,
+                    float threshold, void* out_mask, void* stream);
+
+/*
+ * Complex (or real) 2-d cross-correlation, NCHW, groups == 1, zero padding.
+ * Replaces cplx.conv2d -> convnd_quick (cplxmodule/cplx.py:729-742,822-838);
+ * with log_sigma2 != NULL also the variational forward
+ * CplxConvNdGaussianMixin._forward_impl (nn/relevance/complex/base.py:120-135).
+ * conv1d is the H == kh == 1 case.
+ *   x : [B,C,H,W]  w,log_sigma2 : [O,C,kh,kw]  b : [O]  y,eps : [B,O,Ho,Wo]
+ */
+int cplxk_conv2d_fwd(const void* x_re, const void* x_im,
+                     const void* w_re, const void* w_im,
+                     const void* b_re, const void* b_im,
+                     const void* log_sigma2,
+                     const void* eps_re, const void* eps_im,
+                     int noise, uint64_t seed, uint64_t offset,
+                     uint32_t philox_threads,
+                     void* y_re, void* y_im,
+                     int64_t B, int64_t C, int64_t H, int64_t W,
+                     int64_t O, int64_t kh, int64_t kw,
+                     int64_t stride_h, int64_t stride_w,
+                     int64_t pad_h, int64_t pad_w,
+                     int64_t dil_h, int64_t dil_w,
+                     int dtype, int math, void* stream);
+
+/*
+ * Test hook: fill out[n] (float) with scale * N(0,1) using the very device
+ * function the VD epilogue uses for CPLXK_NOISE_PHILOX_TORCH, i.e. element i
+ * equals torch.randn(n, device='cuda')[i] * scale for the same generator state.
+ */
+int cplxk_randn_philox_torch(float* out, int64_t n, uint64_t seed,
+                             uint64_t offset, uint32_t philox_threads,
+                             float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPLXK_H_ */

@@ -1,0 +1,160 @@
+"""CPU-side checks: API surface / state-dict format / init parity with the reference,
+penalty collection logic, loud failure without CUDA, C-ABI export list."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import cplxmodule_b200 as cb
+from cplxmodule_b200 import _native, cplx
+from cplxmodule_b200.nn import CplxConv1d, CplxConv2d, CplxLinear, CplxParameter, RealToCplx
+from cplxmodule_b200.nn.relevance import (BaseARD, CplxConv2dVD, CplxLinearARD, CplxLinearVD,
+                                          LinearARD, LinearVD, compute_ard_masks, named_penalties,
+                                          penalties)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAVE_REF = os.path.isdir("/root/reference/cplxmodule")
+
+
+def test_cabi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "cplxk.h")).read()
+    declared = set(re.findall(r"\b(cplxk_[a-z0-9_]+)\s*\(", header))
+    declared -= {"cplxk_status", "cplxk_dtype", "cplxk_math", "cplxk_noise", "cplxk_kl_kind"}
+    assert declared == set(_native.EXPORTS)
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.cplxk_abi_version() == 1
+
+
+def test_library_reports_errors_not_aborts_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _native.lib()
+    rc = lib.cplxk_device_info(None, None, None)
+    assert rc == -4 and b"CUDA error" in lib.cplxk_strerror(rc)
+    assert lib.cplxk_kl(0, None, None, None, 0, 0, None, None, 1.0, None, 0, None) == -1
+
+
+def test_cpu_tensors_fail_loudly():
+    layer = CplxLinearVD(8, 4)
+    z = cplx.Cplx(torch.randn(3, 8), torch.randn(3, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        layer(z)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sum(penalties(layer))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        LinearVD(8, 4)(torch.randn(3, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        CplxConv2d(2, 3, 3)(cplx.Cplx(torch.randn(1, 2, 5, 5), torch.randn(1, 2, 5, 5)))
+
+
+def test_state_dict_format():
+    assert sorted(CplxLinearVD(5, 3).state_dict()) == [
+        "bias.imag", "bias.real", "log_sigma2", "weight.imag", "weight.real"]
+    assert sorted(LinearARD(5, 3).state_dict()) == ["bias", "log_sigma2", "weight"]
+    assert sorted(CplxConv2dVD(2, 3, 3, bias=False).state_dict()) == [
+        "log_sigma2", "weight.imag", "weight.real"]
+    m = CplxLinearARD(5, 3)
+    assert isinstance(m.weight, cplx.Cplx) and m.weight.shape == (3, 5)
+    assert isinstance(m._modules["weight"], CplxParameter)
+    assert float(m.log_sigma2.min()) == -10.0 == float(m.log_sigma2.max())
+
+
+def test_real_to_complex_promotion_on_load():
+    dense = torch.nn.Linear(6, 4)
+    vd = CplxLinearVD(6, 4)
+    missing, unexpected = vd.load_state_dict(dense.state_dict(), strict=False)
+    assert missing == ["log_sigma2"] and unexpected == []
+    assert torch.equal(vd.weight.real, dense.weight) and float(vd.weight.imag.abs().max()) == 0.0
+    src = CplxLinear(6, 4)
+    vd.load_state_dict(src.state_dict(), strict=False)
+    assert torch.equal(vd.weight.imag, src.weight.imag)
+    bad = {k: v for k, v in src.state_dict().items() if k != "weight.imag"}
+    with pytest.raises(RuntimeError, match="requires both"):
+        CplxLinear(6, 4).load_state_dict(bad)
+
+
+def test_cplx_container_semantics():
+    a = cplx.Cplx(torch.randn(3, 4), torch.randn(3, 4))
+    b = cplx.Cplx(torch.randn(3, 4), torch.randn(3, 4))
+    p = a * b
+    ref = torch.complex(a.real, a.imag) * torch.complex(b.real, b.imag)
+    assert torch.allclose(p.real, ref.real) and torch.allclose(p.imag, ref.imag)
+    q = a / b
+    ref = torch.complex(a.real, a.imag) / torch.complex(b.real, b.imag)
+    assert torch.allclose(q.real, ref.real, atol=1e-5) and torch.allclose(q.imag, ref.imag, atol=1e-5)
+    assert torch.allclose(abs(a), torch.complex(a.real, a.imag).abs())
+    assert cplx.Cplx(a) is a
+    with pytest.raises(TypeError):
+        cplx.Cplx([1.0])
+    with pytest.raises(ValueError):
+        cplx.Cplx(torch.zeros(2), torch.zeros(3))
+    with pytest.raises(AttributeError):
+        a.real = torch.zeros(3, 4)
+    r = torch.randn(2, 10)
+    z = cplx.from_interleaved_real(r)
+    assert torch.equal(z.real, r[:, 0::2]) and torch.equal(cplx.to_interleaved_real(z), r)
+    z = cplx.from_concatenated_real(r)
+    assert torch.equal(z.imag, r[:, 5:]) and torch.equal(cplx.to_concatenated_real(z), r)
+    assert RealToCplx()(r).shape == (2, 5)
+    assert cplx.cat([a, b], dim=0).shape == (6, 4) and cplx.stack([a, b], dim=0).shape == (2, 3, 4)
+    torch.manual_seed(3)
+    n = cplx.randn(1000, 50)
+    assert abs(float((n.real ** 2 + n.imag ** 2).mean()) - 1.0) < 0.02
+
+
+class _Toy(BaseARD):
+    def __init__(self, value):
+        super().__init__()
+        self.value = torch.nn.Parameter(torch.tensor(value))
+
+    @property
+    def penalty(self):
+        return self.value * torch.ones(2, 3)
+
+    def relevance(self, **kw):
+        return torch.ones(2, 3)
+
+
+def test_penalty_collection_walk():
+    shared = _Toy(2.0)
+    net = torch.nn.Sequential(shared, torch.nn.ReLU(), _Toy(1.0), shared)
+    got = dict(named_penalties(net, reduction="sum"))
+    assert list(got) == ["0", "2"]            # shared module visited once
+    assert float(got["0"]) == 12.0 and float(got["2"]) == 6.0
+    assert float(sum(penalties(net, reduction="mean"))) == 3.0
+    assert [p.shape for p in penalties(net, reduction=None)] == [(2, 3), (2, 3)]
+    with pytest.raises(ValueError):
+        list(penalties(net, reduction="max"))
+    assert sorted(compute_ard_masks(net)) == ["0.mask", "2.mask"]
+    assert sorted(compute_ard_masks(net, prefix="enc")) == ["enc.0.mask", "enc.2.mask"]
+
+
+def test_conv_module_ctor_matches_torch():
+    m = CplxConv2d(4, 6, (3, 2), stride=2, padding=(1, 0), dilation=(1, 2), bias=False)
+    assert m.weight.shape == (6, 4, 3, 2) and m.bias is None and m.stride == (2, 2)
+    assert CplxConv1d(4, 6, 5).weight.shape == (6, 4, 5)
+    with pytest.raises(ValueError):
+        CplxConv2d(3, 6, 3, groups=2)
+    with pytest.raises(ValueError):
+        CplxConv2dVD(2, 2, 3, padding_mode="circular")
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference not present")
+def test_default_init_bit_parity_with_reference():
+    from oracle.make_golden import import_reference
+    import_reference()
+    from cplxmodule.nn import CplxLinear as RefLinear, CplxConv2d as RefConv2d
+    from cplxmodule.nn.relevance import CplxLinearVD as RefVD, LinearVD as RefRealVD
+    for ours, ref, args in ((CplxLinear, RefLinear, (31, 17)), (CplxLinearVD, RefVD, (31, 17)),
+                            (LinearVD, RefRealVD, (31, 17)), (CplxConv2d, RefConv2d, (3, 5, 3))):
+        torch.manual_seed(99)
+        a = ours(*args).state_dict()
+        torch.manual_seed(99)
+        b = ref(*args).state_dict()
+        assert list(a) == list(b)
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
