@@ -34,14 +34,10 @@ static int check_arch() {
   return ok ? CPLXK_OK : CPLXK_ERR_ARCH;
 }
 
-static int env_swizzle() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = std::getenv("CPLXK_TC_SWIZZLE");
-    v = e ? std::atoi(e) : 0;
-    if (v != 64 && v != 128) v = 0;
-  }
-  return v;
+static int env_swizzle() {  // tuning knob, read per call (cheap) so one process can sweep it
+  const char* e = std::getenv("CPLXK_TC_SWIZZLE");
+  int v = e ? std::atoi(e) : 0;
+  return (v == 64 || v == 128) ? v : 0;
 }
 
 static NoiseParams make_noise(int mode, uint64_t seed, uint64_t offset, uint32_t threads, bool cplx) {

@@ -14,6 +14,7 @@
 //
 // Warp roles (192 threads): 0 = TMA producer, 1 = MMA issuer (+TMEM alloc),
 // 2..5 = transform + epilogue (TMEM lane quarter = warp % 4).
+#include <cstdlib>
 #include <type_traits>
 
 #include "epilogue.cuh"
@@ -49,6 +50,19 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;
   static_assert(STAGES >= 2, "need a double-buffered ring at least");
 };
+
+// derived operands are rounded to the MMA operand precision with round-to-nearest (the
+// bf16 store already does; fp32 tiles are consumed as tf32, which would otherwise truncate)
+template <typename T>
+__device__ __forceinline__ float round_operand(float v) {
+  if constexpr (std::is_same<T, float>::value) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+  } else {
+    return v;
+  }
+}
 
 constexpr int kTcThreads = 192;
 constexpr int kRasterGroup = 12;  // m-tiles per raster group: a wave covers ~12x12 tiles (L2 reuse)
@@ -204,16 +218,16 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__
             Vec16<T> b;
             b.load_smem(reinterpret_cast<const T*>(st + C::OFF_A1 + 16 * i));
 #pragma unroll
-            for (int j = 0; j < Vec16<T>::N; ++j) q.v[j] = fmaf(a.v[j], a.v[j], b.v[j] * b.v[j]);
+            for (int j = 0; j < Vec16<T>::N; ++j) q.v[j] = round_operand<T>(fmaf(a.v[j], a.v[j], b.v[j] * b.v[j]));
           } else {
 #pragma unroll
-            for (int j = 0; j < Vec16<T>::N; ++j) q.v[j] = a.v[j] * a.v[j];
+            for (int j = 0; j < Vec16<T>::N; ++j) q.v[j] = round_operand<T>(a.v[j] * a.v[j]);
           }
           q.store(reinterpret_cast<T*>(st + C::OFF_Q + 16 * i));
           Vec16<T> e;
           e.load_smem(reinterpret_cast<const T*>(st + C::OFF_E + 16 * i));
 #pragma unroll
-          for (int j = 0; j < Vec16<T>::N; ++j) e.v[j] = __expf(e.v[j]);
+          for (int j = 0; j < Vec16<T>::N; ++j) e.v[j] = round_operand<T>(__expf(e.v[j]));
           e.store(reinterpret_cast<T*>(st + C::OFF_E + 16 * i));
         }
         ptx::fence_proxy_async_smem();
@@ -274,15 +288,23 @@ static PFN_encodeTiled get_encode_fn() {
 
 // plane [rows, K] row-major -> box {kSwz bytes of K, 128 rows}
 template <typename T, int kSwz>
-static int make_plane_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K) {
+static int make_plane_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K,
+                          bool mma_operand = true) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return CPLXK_ERR_CUDA;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(K) * sizeof(T)};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(kSwz / sizeof(T)), 128u};
   cuuint32_t estr[2] = {1u, 1u};
-  CUtensorMapDataType dt = std::is_same<T, float>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-                                                         : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  // fp32 planes feed kind::tf32 MMAs: the TFLOAT32 tensor-map type makes TMA deliver tf32
+  // values (round-to-nearest) instead of leaving the truncation to the tensor core, which
+  // would bias every product by about -2^-10 relative.
+  const char* raw_env = std::getenv("CPLXK_TMA_RAW_F32");
+  const bool raw_f32 = raw_env && raw_env[0] == '1';
+  CUtensorMapDataType dt = std::is_same<T, float>::value
+                               ? ((raw_f32 || !mma_operand) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                            : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32)
+                               : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMapSwizzle sw = kSwz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                       : (kSwz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
@@ -305,7 +327,8 @@ static int launch_tc(const void* x_re, const void* x_im, const void* w_re, const
     if ((rc = make_plane_map<T, kSwz>(&tm_xi, x_im, M, K))) return rc;
     if ((rc = make_plane_map<T, kSwz>(&tm_wi, w_im, N, K))) return rc;
   }
-  if (kVD && (rc = make_plane_map<T, kSwz>(&tm_ls, ls2, N, K))) return rc;
+  // log_sigma2 is exponentiated first: it must arrive with all its fp32 bits
+  if (kVD && (rc = make_plane_map<T, kSwz>(&tm_ls, ls2, N, K, false))) return rc;
 
   TcParams p;
   p.M = M, p.N = N, p.K = K;

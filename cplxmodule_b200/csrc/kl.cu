@@ -274,6 +274,10 @@ extern "C" size_t cplxk_kl_workspace_bytes(void) { return sizeof(KlWorkspace); }
 extern "C" int cplxk_kl(int kind, const void* w_re, const void* w_im, const void* log_sigma2,
                         int64_t n, int dtype, void* out_elem, float* out_sum, double scale,
                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (n == 0) {  // empty layer: the sum of nothing
+    if (out_sum) CPLXK_CUDA_TRY(cudaMemsetAsync(out_sum, 0, sizeof(float), static_cast<cudaStream_t>(stream)));
+    return (kind < 0 || kind > 3) ? CPLXK_ERR_BADARG : CPLXK_OK;
+  }
   if (!w_re || !log_sigma2 || n < 0 || (!out_elem && !out_sum)) return CPLXK_ERR_BADARG;
   const bool cplx = (kind == CPLXK_KL_CPLX_VD || kind == CPLXK_KL_CPLX_ARD);
   if (kind < 0 || kind > 3 || cplx != (w_im != nullptr)) return CPLXK_ERR_BADARG;
@@ -318,6 +322,7 @@ static int launch_log_alpha(const void* w_re, const void* w_im, const void* ls2,
 extern "C" int cplxk_log_alpha(const void* w_re, const void* w_im, const void* log_sigma2,
                                int64_t n, int dtype, void* out_log_alpha, float threshold,
                                void* out_mask, void* stream) {
+  if (n == 0) return CPLXK_OK;
   if (!w_re || !log_sigma2 || n < 0 || (!out_log_alpha && !out_mask)) return CPLXK_ERR_BADARG;
   auto st = static_cast<cudaStream_t>(stream);
   if (dtype == CPLXK_F32)
