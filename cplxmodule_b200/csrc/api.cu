@@ -17,8 +17,9 @@ int fwd_simt_dispatch(int dtype, bool cplx, bool vd, const void* x_re, const voi
 bool fwd_tc_supported(int dtype, bool cplx, const void* x_re, const void* x_im, const void* w_re,
                       const void* w_im, const void* ls2, int64_t M, int64_t N, int64_t K);
 int fwd_tc_dispatch(int dtype, bool cplx, bool vd, int swz, const void* x_re, const void* x_im,
-                    const void* w_re, const void* w_im, const void* ls2, int64_t M, int64_t N,
-                    int64_t K, const EpiParams& ep, cudaStream_t st);
+                    const void* w_re, const void* w_im, const void* ls2, void* workspace,
+                    int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st);
+size_t fwd_tc_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K);
 
 static int check_arch() {
   static int ok = -1;  // per process; one process per GPU
@@ -56,7 +57,8 @@ static int forward_common(bool vd, const void* x_re, const void* x_im, const voi
                           const void* w_im, const void* b_re, const void* b_im, const void* ls2,
                           const void* eps_re, const void* eps_im, int noise, uint64_t seed,
                           uint64_t offset, uint32_t threads, void* y_re, void* y_im, int64_t M,
-                          int64_t N, int64_t K, int dtype, int math, void* stream) {
+                          int64_t N, int64_t K, int dtype, int math, void* workspace,
+                          size_t workspace_bytes, void* stream) {
   if (!x_re || !w_re || !y_re || M < 0 || N < 0 || K < 0) return CPLXK_ERR_BADARG;
   const bool cplx = (x_im != nullptr);
   if (cplx != (w_im != nullptr) || cplx != (y_im != nullptr)) return CPLXK_ERR_BADARG;
@@ -85,7 +87,12 @@ static int forward_common(bool vd, const void* x_re, const void* x_im, const voi
   if (math != CPLXK_MATH_SIMT && tc_ok) {
     int swz = env_swizzle();
     if (!swz) swz = (cplx && vd) ? 64 : 128;
-    return fwd_tc_dispatch(dtype, cplx, vd, swz, x_re, x_im, w_re, w_im, ls2, M, N, K, ep, st);
+    if (workspace) {
+      if (!aligned16(workspace)) return CPLXK_ERR_ALIGN;
+      if (workspace_bytes < fwd_tc_workspace_bytes(dtype, M, N, K)) return CPLXK_ERR_WORKSPACE;
+    }
+    return fwd_tc_dispatch(dtype, cplx, vd, swz, x_re, x_im, w_re, w_im, ls2, vd ? workspace : nullptr,
+                           M, N, K, ep, st);
   }
   return fwd_simt_dispatch(dtype, cplx, vd, x_re, x_im, w_re, w_im, ls2, M, N, K, ep, st);
 }
@@ -136,7 +143,7 @@ extern "C" int cplxk_linear_fwd(const void* x_re, const void* x_im, const void* 
                                 void* y_im, int64_t M, int64_t N, int64_t K, int dtype, int math,
                                 void* stream) {
   return forward_common(false, x_re, x_im, w_re, w_im, b_re, b_im, nullptr, nullptr, nullptr, 0, 0,
-                        0, 0, y_re, y_im, M, N, K, dtype, math, stream);
+                        0, 0, y_re, y_im, M, N, K, dtype, math, nullptr, 0, stream);
 }
 
 extern "C" int cplxk_linear_vd_fwd(const void* x_re, const void* x_im, const void* w_re,
@@ -144,9 +151,16 @@ extern "C" int cplxk_linear_vd_fwd(const void* x_re, const void* x_im, const voi
                                    const void* log_sigma2, const void* eps_re, const void* eps_im,
                                    int noise, uint64_t seed, uint64_t offset,
                                    uint32_t philox_threads, void* y_re, void* y_im, int64_t M,
-                                   int64_t N, int64_t K, int dtype, int math, void* stream) {
+                                   int64_t N, int64_t K, int dtype, int math, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
   return forward_common(true, x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise,
-                        seed, offset, philox_threads, y_re, y_im, M, N, K, dtype, math, stream);
+                        seed, offset, philox_threads, y_re, y_im, M, N, K, dtype, math, workspace,
+                        workspace_bytes, stream);
+}
+
+extern "C" size_t cplxk_linear_vd_workspace_bytes(int64_t M, int64_t N, int64_t K, int dtype) {
+  if (M < 0 || N < 0 || K < 0) return 0;
+  return fwd_tc_workspace_bytes(dtype, M, N, K);
 }
 
 extern "C" int cplxk_randn_philox_torch(float* out, int64_t n, uint64_t seed, uint64_t offset,

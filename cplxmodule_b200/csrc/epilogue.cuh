@@ -117,4 +117,169 @@ __device__ __forceinline__ void epilogue_run(const EpiParams& p, int64_t m, int6
   }
 }
 
+
+// ---- two-phase epilogue: the noise of a thread's run is produced (or fetched) BEFORE the
+// accumulators are ready -- i.e. while the tensor pipe is still busy -- and kept in
+// registers; the second phase only needs bias, sqrt, one FMA per plane and the stores.
+template <typename T, bool kCplx, int R>
+__device__ __forceinline__ void noise_prefetch(const EpiParams& p, int64_t m, int64_t n0,
+                                               float (&nre)[R], float (&nim)[kCplx ? R : 1]) {
+  static_assert(R % 4 == 0, "runs are whole noise quads");
+#pragma unroll
+  for (int j = 0; j < R; ++j) nre[j] = 0.f;
+  if constexpr (kCplx) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) nim[j] = 0.f;
+  }
+  if (m >= p.M || n0 >= p.N) return;
+  const int64_t row_off = m * p.N;
+  const int nvalid = (p.N - n0) < R ? static_cast<int>(p.N - n0) : R;
+  if (p.noise.mode == CPLXK_NOISE_INJECT) {
+    constexpr int V = Elem<T>::kVec;
+    const T* er = static_cast<const T*>(p.eps_re) + row_off + n0;
+    const T* ei = kCplx ? static_cast<const T*>(p.eps_im) + row_off + n0 : nullptr;
+    const bool vec = (nvalid == R) && ((reinterpret_cast<uintptr_t>(er) & 15u) == 0) &&
+                     (!kCplx || (reinterpret_cast<uintptr_t>(ei) & 15u) == 0) && (R % V == 0);
+    if (vec) {
+#pragma unroll
+      for (int c = 0; c < R / V; ++c) {
+        Vec16<T> a;
+        a.load(er + c * V);
+#pragma unroll
+        for (int j = 0; j < V; ++j) nre[c * V + j] = a.v[j];
+        if constexpr (kCplx) {
+          a.load(ei + c * V);
+#pragma unroll
+          for (int j = 0; j < V; ++j) nim[c * V + j] = a.v[j];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        if (j < nvalid) {
+          nre[j] = Elem<T>::to_f(__ldg(er + j));
+          if constexpr (kCplx) nim[j] = Elem<T>::to_f(__ldg(ei + j));
+        }
+    }
+  } else if (p.noise.mode == CPLXK_NOISE_PHILOX_TORCH) {
+    // A ROLLED loop (8 normals per plane per trip) that shifts the register-resident run
+    // down by 8 and appends the new values: straight-line code for all R values would be
+    // ~200 KB of SASS executed once per tile, i.e. instruction-fetch bound.  The 8 Philox
+    // chains of a trip are independent (branch-free cursor arithmetic) so they interleave.
+    static_assert(R % 8 == 0, "trip size");
+    const uint32_t T = p.noise.threads;
+    uint64_t slot_re = static_cast<uint64_t>(row_off + n0) / T;
+    uint32_t idx_re = static_cast<uint32_t>(static_cast<uint64_t>(row_off + n0) - slot_re * T);
+    uint64_t slot_im = 0;
+    uint32_t idx_im = 0;
+    if constexpr (kCplx) {
+      slot_im = static_cast<uint64_t>(p.plane_elems + row_off + n0) / T;
+      idx_im = static_cast<uint32_t>(static_cast<uint64_t>(p.plane_elems + row_off + n0) - slot_im * T);
+    }
+#pragma unroll 1
+    for (int trip = 0; trip < R / 8; ++trip) {
+#pragma unroll
+      for (int j = 0; j < R - 8; ++j) nre[j] = nre[j + 8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t i = idx_re + j;
+        const bool wrap = i >= T;
+        i = wrap ? i - T : i;
+        nre[R - 8 + j] = philox_torch_normal(i, slot_re + (wrap ? 1u : 0u), p.noise) * p.noise.scale;
+      }
+      idx_re += 8;
+      if (idx_re >= T) idx_re -= T, ++slot_re;
+      if constexpr (kCplx) {
+#pragma unroll
+        for (int j = 0; j < R - 8; ++j) nim[j] = nim[j + 8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t i = idx_im + j;
+          const bool wrap = i >= T;
+          i = wrap ? i - T : i;
+          nim[R - 8 + j] = philox_torch_normal(i, slot_im + (wrap ? 1u : 0u), p.noise) * p.noise.scale;
+        }
+        idx_im += 8;
+        if (idx_im >= T) idx_im -= T, ++slot_im;
+      }
+    }
+  } else {
+    const uint64_t quads_per_row = static_cast<uint64_t>((p.N + 3) >> 2);
+    const uint64_t q0 = static_cast<uint64_t>(m) * quads_per_row + static_cast<uint64_t>(n0 >> 2);
+#pragma unroll 1
+    for (int trip = 0; trip < R / 8; ++trip) {
+#pragma unroll
+      for (int j = 0; j < R - 8; ++j) nre[j] = nre[j + 8];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float4 g = philox_fast_normal4(q0 + 2 * trip + q, 0u, p.noise);
+        nre[R - 8 + 4 * q + 0] = g.x * p.noise.scale, nre[R - 8 + 4 * q + 1] = g.y * p.noise.scale;
+        nre[R - 8 + 4 * q + 2] = g.z * p.noise.scale, nre[R - 8 + 4 * q + 3] = g.w * p.noise.scale;
+      }
+      if constexpr (kCplx) {
+#pragma unroll
+        for (int j = 0; j < R - 8; ++j) nim[j] = nim[j + 8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float4 h = philox_fast_normal4(q0 + 2 * trip + q, 1u, p.noise);
+          nim[R - 8 + 4 * q + 0] = h.x * p.noise.scale, nim[R - 8 + 4 * q + 1] = h.y * p.noise.scale;
+          nim[R - 8 + 4 * q + 2] = h.z * p.noise.scale, nim[R - 8 + 4 * q + 3] = h.w * p.noise.scale;
+        }
+      }
+    }
+  }
+}
+
+// second phase for C consecutive columns starting at n0 (noise pointers already offset)
+template <typename T, bool kCplx, int C>
+__device__ __forceinline__ void epilogue_finish(const EpiParams& p, int64_t m, int64_t n0,
+                                                float (&re)[C], float (&im)[C], float (&s2)[C],
+                                                const float* nre, const float* nim) {
+  if (m >= p.M || n0 >= p.N) return;
+  const int64_t row_off = m * p.N;
+  const int nvalid = (p.N - n0) < C ? static_cast<int>(p.N - n0) : C;
+  if (p.b_re) {
+    const T* br = static_cast<const T*>(p.b_re);
+    const T* bi = static_cast<const T*>(p.b_im);
+#pragma unroll
+    for (int j = 0; j < C; ++j)
+      if (j < nvalid) {
+        re[j] += Elem<T>::to_f(__ldg(br + n0 + j));
+        if constexpr (kCplx) im[j] += Elem<T>::to_f(__ldg(bi + n0 + j));
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    const float sd = sqrtf(fmaxf(s2[j], 1e-8f));
+    re[j] = fmaf(nre[j], sd, re[j]);
+    if constexpr (kCplx) im[j] = fmaf(nim[j], sd, im[j]);
+  }
+  constexpr int V = Elem<T>::kVec;
+  T* yr = static_cast<T*>(p.y_re) + row_off + n0;
+  T* yi = kCplx ? static_cast<T*>(p.y_im) + row_off + n0 : nullptr;
+  const bool vec = (nvalid == C) && ((reinterpret_cast<uintptr_t>(yr) & 15u) == 0) &&
+                   (!kCplx || (reinterpret_cast<uintptr_t>(yi) & 15u) == 0) && (C % V == 0);
+  if (vec) {
+#pragma unroll
+    for (int c = 0; c < C / V; ++c) {
+      Vec16<T> o;
+#pragma unroll
+      for (int j = 0; j < V; ++j) o.v[j] = re[c * V + j];
+      o.store(yr + c * V);
+      if constexpr (kCplx) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.v[j] = im[c * V + j];
+        o.store(yi + c * V);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < C; ++j)
+      if (j < nvalid) {
+        yr[j] = Elem<T>::from_f(re[j]);
+        if constexpr (kCplx) yi[j] = Elem<T>::from_f(im[j]);
+      }
+  }
+}
+
 }  // namespace cplxk

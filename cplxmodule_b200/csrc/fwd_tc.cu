@@ -22,7 +22,7 @@
 
 namespace cplxk {
 
-template <typename T, bool kCplx, bool kVD, int kSwz>
+template <typename T, bool kCplx, bool kVD, bool kXform, int kSwz>
 struct TcCfg {
   static constexpr bool kBF16 = std::is_same<T, __nv_bfloat16>::value;
   static constexpr int BM = 128, BN = 128;
@@ -40,7 +40,10 @@ struct TcCfg {
   static constexpr int OFF_B1 = OFF_B0 + TILE_BYTES;
   static constexpr int OFF_E = OFF_B0 + NB * TILE_BYTES;
   static constexpr int STAGE_BYTES = NTILES * TILE_BYTES;
-  static constexpr int LOAD_BYTES = (NA + NB + (kVD ? 1 : 0)) * TILE_BYTES;
+  // kXform: |x|^2 and exp(log_sigma2) are made in smem by the transform warps (TMA brings
+  // log_sigma2 into the E slot); otherwise both arrive precomputed through TMA.
+  static constexpr int LOAD_BYTES = (kVD && !kXform) ? NTILES * TILE_BYTES
+                                                     : (NA + NB + (kVD ? 1 : 0)) * TILE_BYTES;
   static constexpr int NACC = NA + (kVD ? 1 : 0);
   static constexpr int TMEM_COLS = NACC * BN <= 128 ? 128 : (NACC * BN <= 256 ? 256 : 512);
   static constexpr int AUX_BYTES = 1024;  // barriers + tmem slot
@@ -49,6 +52,12 @@ struct TcCfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;
   static_assert(STAGES >= 2, "need a double-buffered ring at least");
+  // With precomputed operands no warp has mainloop duties besides TMA / MMA issue, so the
+  // epilogue is spread over EIGHT warps (two per TMEM lane quarter, 64 columns each) that
+  // spend the mainloop generating their noise into registers.
+  static constexpr bool kPrefetchNoise = kVD && !kXform;
+  static constexpr int EPI_WARPS = kPrefetchNoise ? 8 : 4;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
 
 // derived operands are rounded to the MMA operand precision with round-to-nearest (the
@@ -73,12 +82,13 @@ struct TcParams {
   EpiParams ep;
 };
 
-template <typename T, bool kCplx, bool kVD, int kSwz>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <typename T, bool kCplx, bool kVD, bool kXform, int kSwz>
+__global__ void __launch_bounds__((TcCfg<T, kCplx, kVD, kXform, kSwz>::THREADS), 1)
 fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__ CUtensorMap tm_xi,
               const __grid_constant__ CUtensorMap tm_wr, const __grid_constant__ CUtensorMap tm_wi,
-              const __grid_constant__ CUtensorMap tm_ls, const TcParams p) {
-  using C = TcCfg<T, kCplx, kVD, kSwz>;
+              const __grid_constant__ CUtensorMap tm_ls, const __grid_constant__ CUtensorMap tm_q,
+              const TcParams p) {
+  using C = TcCfg<T, kCplx, kVD, kXform, kSwz>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms need 1024-B alignment
@@ -120,6 +130,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__
       ptx::prefetch_tensormap(&tm_wi);
     }
     if constexpr (kVD) ptx::prefetch_tensormap(&tm_ls);
+    if constexpr (kVD && !kXform) ptx::prefetch_tensormap(&tm_q);
     for (int s = 0; s < C::STAGES; ++s) {
       ptx::mbar_init(bar_full + 8 * s, 1);
       ptx::mbar_init(bar_xf + 8 * s, 4);  // one arrive per transform warp
@@ -152,7 +163,8 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__
         if constexpr (kCplx) ptx::tma_load_2d(st + C::OFF_A1, &tm_xi, fb, k0, m0);
         ptx::tma_load_2d(st + C::OFF_B0, &tm_wr, fb, k0, n0);
         if constexpr (kCplx) ptx::tma_load_2d(st + C::OFF_B1, &tm_wi, fb, k0, n0);
-        if constexpr (kVD) ptx::tma_load_2d(st + C::OFF_E, &tm_ls, fb, k0, n0);
+        if constexpr (kVD) ptx::tma_load_2d(st + C::OFF_E, &tm_ls, fb, k0, n0);  // log_sigma2 or exp() of it
+        if constexpr (kVD && !kXform) ptx::tma_load_2d(st + C::OFF_Q, &tm_q, fb, k0, m0);
       }
     }
   } else if (warp == 1) {
@@ -163,6 +175,27 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__
       const uint32_t t_re = tmem_base;
       const uint32_t t_im = tmem_base + C::BN;
       const uint32_t t_s2 = tmem_base + C::NA * C::BN;
+      // The variance MMAs of k-block kb-1 are issued AFTER the mean MMAs of k-block kb: the
+      // transform warps get a whole stage time to produce |x|^2 / exp(log_sigma2) and the
+      // tensor pipe never waits for them.
+      auto issue_var = [&](int kb) {
+        const int s = kb % C::STAGES;
+        const uint32_t ph = (kb / C::STAGES) & 1;
+        const uint32_t st = base + s * C::STAGE_BYTES;
+        if constexpr (kXform) {
+          ptx::mbar_wait(bar_xf + 8 * s, ph);
+          ptx::tcgen05_fence_after();
+        }
+        const uint64_t aq = ptx::make_kmajor_desc<kSwz>(st + C::OFF_Q);
+        const uint64_t be = ptx::make_kmajor_desc<kSwz>(st + C::OFF_E);
+#pragma unroll
+        for (int k = 0; k < C::KSTEPS; ++k) {
+          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+          const uint32_t off = k * 32;
+          ptx::umma_ss<C::kBF16>(t_s2, ptx::desc_advance(aq, off), ptx::desc_advance(be, off), idesc, acc);
+        }
+        ptx::umma_commit(bar_empty + 8 * s);  // stage reusable once everything issued so far retires
+      };
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % C::STAGES;
         const uint32_t ph = (kb / C::STAGES) & 1;
@@ -184,26 +217,21 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__
             ptx::umma_ss<C::kBF16>(t_im, ptx::desc_advance(a1, off), ptx::desc_advance(b0, off), idesc, 1u);
           }
         }
-        if constexpr (kVD) {
-          ptx::mbar_wait(bar_xf + 8 * s, ph);
-          ptx::tcgen05_fence_after();
-          const uint64_t aq = ptx::make_kmajor_desc<kSwz>(st + C::OFF_Q);
-          const uint64_t be = ptx::make_kmajor_desc<kSwz>(st + C::OFF_E);
-#pragma unroll
-          for (int k = 0; k < C::KSTEPS; ++k) {
-            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            const uint32_t off = k * 32;
-            ptx::umma_ss<C::kBF16>(t_s2, ptx::desc_advance(aq, off), ptx::desc_advance(be, off), idesc, acc);
-          }
+        if constexpr (kVD && kXform) {
+          if (kb > 0) issue_var(kb - 1);
+        } else if constexpr (kVD) {
+          issue_var(kb);  // operands landed with the same TMA transaction group
+        } else {
+          ptx::umma_commit(bar_empty + 8 * s);
         }
-        ptx::umma_commit(bar_empty + 8 * s);  // stage reusable once these MMAs retire
       }
+      if constexpr (kVD && kXform) issue_var(num_kb - 1);
       ptx::umma_commit(bar_accum);  // accumulators complete
     }
   } else {
     // -------------------------------------------------- transform, then epilogue
-    const int tt = threadIdx.x - 64;  // 0..127
-    if constexpr (kVD) {
+    [[maybe_unused]] const int tt = threadIdx.x - 64;  // 0..127
+    if constexpr (kVD && kXform) {
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % C::STAGES;
         const uint32_t ph = (kb / C::STAGES) & 1;
@@ -236,6 +264,35 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__
       }
     }
 
+    if constexpr (C::kPrefetchNoise) {
+      const int quarter = warp & 3;          // TMEM lanes this warp may touch
+      const int half = (warp - 2) >> 2;      // which 64 columns of the tile
+      const int64_t m = static_cast<int64_t>(m0) + quarter * 32 + lane;
+      const int64_t nb = static_cast<int64_t>(n0) + half * 64;
+      float nre[64], nim[kCplx ? 64 : 1];
+      noise_prefetch<T, kCplx, 64>(p.ep, m, nb, nre, nim);  // overlaps the MMA mainloop
+      ptx::mbar_wait(bar_accum, 0);
+      ptx::tcgen05_fence_after();
+      const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 64;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {  // 8 columns at a time keeps the live set under 168 registers
+        uint32_t r_re[8], r_im[8], r_s2[8];
+        ptx::tmem_ld_32x32b_x8(lane_base + c * 8, r_re);
+        if constexpr (kCplx) ptx::tmem_ld_32x32b_x8(lane_base + C::BN + c * 8, r_im);
+        ptx::tmem_ld_32x32b_x8(lane_base + C::NA * C::BN + c * 8, r_s2);
+        ptx::tmem_ld_wait();
+        float f_re[8], f_im[8], f_s2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f_re[j] = __uint_as_float(r_re[j]);
+          f_im[j] = kCplx ? __uint_as_float(r_im[j]) : 0.f;
+          f_s2[j] = __uint_as_float(r_s2[j]);
+        }
+        epilogue_finish<T, kCplx, 8>(p.ep, m, nb + c * 8, f_re, f_im, f_s2, &nre[c * 8],
+                                     &nim[kCplx ? c * 8 : 0]);
+      }
+      ptx::tcgen05_fence_before();
+    } else {
     ptx::mbar_wait(bar_accum, 0);
     ptx::tcgen05_fence_after();
     const int quarter = warp & 3;
@@ -258,6 +315,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__
       epilogue_run<T, kCplx, kVD, 16>(p.ep, m, static_cast<int64_t>(n0) + c * 16, f_re, f_im, f_s2);
     }
     ptx::tcgen05_fence_before();
+    }
   }
 
   __syncthreads();
@@ -313,22 +371,81 @@ static int make_plane_map(CUtensorMap* out, const void* ptr, int64_t rows, int64
   return r == CUDA_SUCCESS ? CPLXK_OK : CPLXK_ERR_CUDA;
 }
 
-template <typename T, bool kCplx, bool kVD, int kSwz>
+// ---- operand preparation for the variational forward (workspace variant) ----------------
+// q = |x|^2 (per input row) and E = exp(log_sigma2) (per weight row), rounded to the MMA
+// operand precision, written once to a caller-provided workspace.  HBM-bound elementwise pass;
+// it takes the square/exp work (and its shared-memory traffic) out of the GEMM mainloop.
+template <typename T, bool kCplx>
+__global__ void __launch_bounds__(256)
+vd_prepare_kernel(const T* __restrict__ x_re, const T* __restrict__ x_im, int64_t nx,
+                  T* __restrict__ q, const T* __restrict__ ls2, int64_t nw, T* __restrict__ e) {
+  constexpr int V = Elem<T>::kVec;
+  const int64_t vx = nx / V, vw = nw / V;  // K * sizeof(T) % 16 == 0 => both exact
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < vx + vw;
+       i += stride) {
+    Vec16<T> o;
+    if (i < vx) {
+      Vec16<T> a;
+      a.load(x_re + i * V);
+      if constexpr (kCplx) {
+        Vec16<T> b;
+        b.load(x_im + i * V);
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.v[j] = round_operand<T>(fmaf(a.v[j], a.v[j], b.v[j] * b.v[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.v[j] = round_operand<T>(a.v[j] * a.v[j]);
+      }
+      o.store(q + i * V);
+    } else {
+      const int64_t k = i - vx;
+      Vec16<T> a;
+      a.load(ls2 + k * V);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o.v[j] = round_operand<T>(__expf(a.v[j]));
+      o.store(e + k * V);
+    }
+  }
+}
+
+size_t fwd_tc_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K) {
+  const size_t es = dtype == CPLXK_F32 ? 4 : 2;
+  const size_t qb = (static_cast<size_t>(M) * K * es + 255) & ~static_cast<size_t>(255);
+  const size_t eb = (static_cast<size_t>(N) * K * es + 255) & ~static_cast<size_t>(255);
+  return qb + eb;
+}
+
+template <typename T, bool kCplx, bool kVD, bool kXform, int kSwz>
 static int launch_tc(const void* x_re, const void* x_im, const void* w_re, const void* w_im,
-                     const void* ls2, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
-                     cudaStream_t st) {
-  using C = TcCfg<T, kCplx, kVD, kSwz>;
-  CUtensorMap tm_xr, tm_xi, tm_wr, tm_wi, tm_ls;
+                     const void* ls2, void* workspace, int64_t M, int64_t N, int64_t K,
+                     const EpiParams& ep, cudaStream_t st) {
+  using C = TcCfg<T, kCplx, kVD, kXform, kSwz>;
+  CUtensorMap tm_xr, tm_xi, tm_wr, tm_wi, tm_ls, tm_q;
   int rc;
   if ((rc = make_plane_map<T, kSwz>(&tm_xr, x_re, M, K))) return rc;
   if ((rc = make_plane_map<T, kSwz>(&tm_wr, w_re, N, K))) return rc;
-  tm_xi = tm_xr, tm_wi = tm_wr, tm_ls = tm_wr;
+  tm_xi = tm_xr, tm_wi = tm_wr, tm_ls = tm_wr, tm_q = tm_xr;
   if (kCplx) {
     if ((rc = make_plane_map<T, kSwz>(&tm_xi, x_im, M, K))) return rc;
     if ((rc = make_plane_map<T, kSwz>(&tm_wi, w_im, N, K))) return rc;
   }
-  // log_sigma2 is exponentiated first: it must arrive with all its fp32 bits
-  if (kVD && (rc = make_plane_map<T, kSwz>(&tm_ls, ls2, N, K, false))) return rc;
+  if (kVD && kXform) {
+    // log_sigma2 is exponentiated in the kernel: it must arrive with all its fp32 bits
+    if ((rc = make_plane_map<T, kSwz>(&tm_ls, ls2, N, K, false))) return rc;
+  } else if (kVD) {
+    T* q = static_cast<T*>(workspace);
+    const size_t qb = (static_cast<size_t>(M) * K * sizeof(T) + 255) & ~static_cast<size_t>(255);
+    T* e = reinterpret_cast<T*>(static_cast<uint8_t*>(workspace) + qb);
+    const int64_t work = (M * K + N * K) / Elem<T>::kVec;
+    const int grid = static_cast<int>(work / 256 + 1 > 148 * 16 ? 148 * 16 : work / 256 + 1);
+    vd_prepare_kernel<T, kCplx><<<grid, 256, 0, st>>>(static_cast<const T*>(x_re),
+                                                    static_cast<const T*>(x_im), M * K, q,
+                                                    static_cast<const T*>(ls2), N * K, e);
+    CPLXK_CUDA_TRY(cudaGetLastError());
+    if ((rc = make_plane_map<T, kSwz>(&tm_q, q, M, K, false))) return rc;   // already rounded
+    if ((rc = make_plane_map<T, kSwz>(&tm_ls, e, N, K, false))) return rc;
+  }
 
   TcParams p;
   p.M = M, p.N = N, p.K = K;
@@ -338,9 +455,9 @@ static int launch_tc(const void* x_re, const void* x_im, const void* w_re, const
   const int64_t tiles = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
   if (tiles > 0x7fffffff) return CPLXK_ERR_UNSUPPORTED;
 
-  auto kern = fwd_tc_kernel<T, kCplx, kVD, kSwz>;
+  auto kern = fwd_tc_kernel<T, kCplx, kVD, kXform, kSwz>;
   CPLXK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  kern<<<static_cast<unsigned>(tiles), kTcThreads, C::SMEM_BYTES, st>>>(tm_xr, tm_xi, tm_wr, tm_wi, tm_ls, p);
+  kern<<<static_cast<unsigned>(tiles), C::THREADS, C::SMEM_BYTES, st>>>(tm_xr, tm_xi, tm_wr, tm_wi, tm_ls, tm_q, p);
   CPLXK_CUDA_TRY(cudaGetLastError());
   return CPLXK_OK;
 }
@@ -358,13 +475,17 @@ bool fwd_tc_supported(int dtype, bool cplx, const void* x_re, const void* x_im, 
 }
 
 int fwd_tc_dispatch(int dtype, bool cplx, bool vd, int swz, const void* x_re, const void* x_im,
-                    const void* w_re, const void* w_im, const void* ls2, int64_t M, int64_t N,
-                    int64_t K, const EpiParams& ep, cudaStream_t st) {
-#define CPLXK_TC_CASE(T, SW)                                                                          \
-  if (cplx && vd) return launch_tc<T, true, true, SW>(x_re, x_im, w_re, w_im, ls2, M, N, K, ep, st);   \
-  if (cplx && !vd) return launch_tc<T, true, false, SW>(x_re, x_im, w_re, w_im, ls2, M, N, K, ep, st); \
-  if (!cplx && vd) return launch_tc<T, false, true, SW>(x_re, x_im, w_re, w_im, ls2, M, N, K, ep, st); \
-  return launch_tc<T, false, false, SW>(x_re, x_im, w_re, w_im, ls2, M, N, K, ep, st);
+                    const void* w_re, const void* w_im, const void* ls2, void* workspace,
+                    int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st) {
+  const bool xform = vd && workspace == nullptr;
+#define CPLXK_TC_ARGS x_re, x_im, w_re, w_im, ls2, workspace, M, N, K, ep, st
+#define CPLXK_TC_CASE(T, SW)                                                                   \
+  if (cplx && vd && xform) return launch_tc<T, true, true, true, SW>(CPLXK_TC_ARGS);           \
+  if (cplx && vd) return launch_tc<T, true, true, false, SW>(CPLXK_TC_ARGS);                   \
+  if (cplx) return launch_tc<T, true, false, false, SW>(CPLXK_TC_ARGS);                        \
+  if (vd && xform) return launch_tc<T, false, true, true, SW>(CPLXK_TC_ARGS);                  \
+  if (vd) return launch_tc<T, false, true, false, SW>(CPLXK_TC_ARGS);                          \
+  return launch_tc<T, false, false, false, SW>(CPLXK_TC_ARGS);
   if (dtype == CPLXK_F32) {
     if (swz == 64) { CPLXK_TC_CASE(float, 64) }
     CPLXK_TC_CASE(float, 128)
@@ -374,6 +495,7 @@ int fwd_tc_dispatch(int dtype, bool cplx, bool vd, int swz, const void* x_re, co
     CPLXK_TC_CASE(__nv_bfloat16, 128)
   }
 #undef CPLXK_TC_CASE
+#undef CPLXK_TC_ARGS
   return CPLXK_ERR_BADARG;
 }
 

@@ -12,7 +12,7 @@ import torch
 
 from . import _native as nv
 
-_state = {"noise": "torch", "math": "auto"}
+_state = {"noise": "torch", "math": "auto", "prepare": True}
 _MATH = {"auto": nv.MATH_AUTO, "tensor": nv.MATH_TENSOR, "simt": nv.MATH_SIMT}
 _NOISE = {"torch": nv.NOISE_PHILOX_TORCH, "fast": nv.NOISE_PHILOX_FAST}
 
@@ -32,6 +32,13 @@ def set_math_mode(mode):
     if mode not in _MATH:
         raise ValueError(f"math mode must be one of {sorted(_MATH)}")
     _state["math"] = mode
+
+
+def set_operand_prepass(enabled):
+    """True (default): |x|^2 and exp(log_sigma2) are written once to a scratch workspace by an
+    elementwise launch and streamed by TMA; False: produced inside the GEMM kernel's smem
+    pipeline (single launch)."""
+    _state["prepare"] = bool(enabled)
 
 
 def get_noise_mode():
@@ -87,10 +94,15 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
                 er = ei = None
                 numel = (2 if cplx else 1) * M * N
                 gen, seed, offset, threads, inc = nv.philox_plan(dev, max(numel, 1))
+            ws, ws_bytes = None, 0
+            if _state["prepare"] and math != nv.MATH_SIMT:
+                ws_bytes = lib.cplxk_linear_vd_workspace_bytes(M, N, K, code)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             nv.check(lib.cplxk_linear_vd_fwd(nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi),
                                              nv.ptr(br), nv.ptr(bi), nv.ptr(ls2), nv.ptr(er),
                                              nv.ptr(ei), noise, seed, offset, threads,
-                                             nv.ptr(y_re), nv.ptr(y_im), M, N, K, code, math, st))
+                                             nv.ptr(y_re), nv.ptr(y_im), M, N, K, code, math,
+                                             nv.ptr(ws), ws_bytes, st))
             if noise != nv.NOISE_INJECT:
                 gen.set_offset(offset + inc)
     y_re = y_re.reshape(*lead, N)

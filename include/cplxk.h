@@ -109,7 +109,14 @@ int cplxk_linear_fwd(const void* x_re, const void* x_im,
  *                            generator state (offset % 4 == 0);
  *                            philox_threads = 256 * grid of torch's randn kernel
  *                            (only used by PHILOX_TORCH).
+ *   workspace (nullable)   : cplxk_linear_vd_workspace_bytes() bytes, 16-byte aligned,
+ *                            uninitialised scratch.  With it the call first writes the two
+ *                            derived GEMM operands |x|^2 [M,K] and exp(log_sigma2) [N,K]
+ *                            there (one elementwise launch) and the GEMM kernel streams them
+ *                            by TMA; without it they are produced inside the GEMM kernel's
+ *                            shared-memory pipeline (one launch, slower mainloop).
  */
+size_t cplxk_linear_vd_workspace_bytes(int64_t M, int64_t N, int64_t K, int dtype);
 int cplxk_linear_vd_fwd(const void* x_re, const void* x_im,
                         const void* w_re, const void* w_im,
                         const void* b_re, const void* b_im,
@@ -119,7 +126,8 @@ int cplxk_linear_vd_fwd(const void* x_re, const void* x_im,
                         uint32_t philox_threads,
                         void* y_re, void* y_im,
                         int64_t M, int64_t N, int64_t K,
-                        int dtype, int math, void* stream);
+                        int dtype, int math,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * KL penalty of a variational layer over n parameters, one HBM pass:

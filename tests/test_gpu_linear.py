@@ -235,3 +235,28 @@ def test_full_size_rows_sampled_against_oracle():
         f2 = lin(cplx.Cplx(2 * x.real, 2 * x.imag))
     b2 = cplx.Cplx(b.real.detach(), b.imag.detach())
     assert rel_err(f2.real - b2.real, 2 * (f1.real - b2.real)) < 1e-5
+
+
+@pytest.mark.parametrize("prepass", [True, False])
+def test_prepass_and_inkernel_transform_agree(prepass):
+    """Workspace variant (|x|^2, exp(log_sigma2) via an elementwise pre-pass + TMA) and the
+    single-launch variant (made in the GEMM's smem pipeline) against the float64 oracle."""
+    torch.manual_seed(31)
+    M, N, K = 300, 260, 520
+    x_re, x_im = torch.randn(M, K), torch.randn(M, K)
+    w_re, w_im = torch.randn(N, K) / K ** 0.5, torch.randn(N, K) / K ** 0.5
+    ls2 = torch.empty(N, K).uniform_(-8, 1)
+    eps = (torch.randn(M, N), torch.randn(M, N))
+    want = orc.cplx_linear_vd(x_re.double(), x_im.double(), w_re.double(), w_im.double(), None,
+                              None, ls2.double(), eps[0].double(), eps[1].double())
+    d = lambda t: t.to(DEV)
+    cb.set_operand_prepass(prepass)
+    try:
+        got = ops.cplx_linear_vd(d(x_re), d(x_im), d(w_re), d(w_im), None, None, d(ls2),
+                                 eps=(d(eps[0]), d(eps[1])))
+        real = ops.real_linear_vd(d(x_re), d(w_re), None, d(ls2), eps=d(eps[0]))
+    finally:
+        cb.set_operand_prepass(True)
+    assert rel_err(got[0], want[0]) < 1e-3 and rel_err(got[1], want[1]) < 1e-3
+    assert rel_err(real, orc.real_linear_vd(x_re.double(), w_re.double(), None, ls2.double(),
+                                            eps[0].double())) < 1e-3

@@ -53,6 +53,16 @@ def main():
                 "real_lin": lambda: ops.real_linear(x.real, w_re, b_re),
                 "real_vd_torch": lambda: ops.real_linear_vd(x.real, w_re, b_re, ls2),
             }
+            if os.environ.get("KB_QUICK"):
+                cases = {k: v for k, v in cases.items() if k in ("cplx_lin", "cplx_vd_inject", "cplx_vd_torch")}
+            for name, fn in list(cases.items()):
+                if "vd" in name:
+                    cb.set_operand_prepass(False)
+                    ms = timeit(fn)
+                    cb.set_operand_prepass(True)
+                    rows.append(dict(dtype=dt_name, swz=swz, case=name + "_xform", ms=ms,
+                                     tflops=(10 if "cplx" in name else 4) * M * N * K / ms / 1e9))
+                    print(json.dumps(rows[-1]), flush=True)
             for name, fn in cases.items():
                 cb.set_noise_mode("torch")
                 ms = timeit(fn)
@@ -68,6 +78,9 @@ def main():
             print(json.dumps(rows[-1]), flush=True)
         os.environ.pop("CPLXK_TC_SWIZZLE", None)
 
+    if os.environ.get("KB_QUICK"):
+        json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "kbench_quick.json"), "w"), indent=1)
+        return
     # ---- tf32 rounding experiment: TFLOAT32 tensor maps vs raw FLOAT32 (tensor-core truncation)
     torch.manual_seed(1)
     for (m, n, k) in ((5, 3, 8), (256, 256, 64), (512, 512, 4096)):
