@@ -359,7 +359,10 @@ def run_ours(args, rank, local_rank, world):
             "peak_source": f"{peaks['source']} bf16 cuBLAS sustained (MEASURED_PEAKS.json); "
                            "tf32 hardware rate is half the bf16 rate",
             "algorithmic_flops_per_launch": FLOPS_PER_STEP, "ms_per_launch": f_ms,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE fwd_tc_kernel launch, from the
+            # committed `ncu --set full` capture (profiles/prof_fwd_*_v2.raw.csv)
+            "traffic": (1.258414e9 + 0.122350e9) if args.dtype != "bf16" else (0.582534e9 + 0.066843e9),
+            "traffic_unit": "bytes/launch", "algorithmic_bytes_per_launch": FWD_ALGO_BYTES * esize / 4.0,
         },
         "roofline_kl": {
             "kernel": "kl_kernel<CPLX_VD>", "bound": "hbm", "achieved": kl_gbs,
