@@ -21,7 +21,7 @@ KL_REAL_VD, KL_REAL_ARD, KL_CPLX_VD, KL_CPLX_ARD = 0, 1, 2, 3
 EXPORTS = (
     "cplxk_abi_version", "cplxk_strerror", "cplxk_device_info", "cplxk_linear_fwd",
     "cplxk_linear_vd_fwd", "cplxk_linear_vd_workspace_bytes", "cplxk_kl_workspace_bytes", "cplxk_kl", "cplxk_log_alpha",
-    "cplxk_conv2d_fwd", "cplxk_randn_philox_torch",
+    "cplxk_conv2d_fwd", "cplxk_conv2d_workspace_bytes", "cplxk_randn_philox_torch",
 )
 
 _lock = threading.Lock()
@@ -46,7 +46,9 @@ def _declare(lib):
                              _vp, ctypes.c_size_t, _vp]
     lib.cplxk_log_alpha.argtypes = [_vp, _vp, _vp, _i64, _int, _vp, ctypes.c_float, _vp, _vp]
     lib.cplxk_conv2d_fwd.argtypes = ([_vp] * 9 + [_int, _u64, _u64, _u32] + [_vp] * 2
-                                     + [_i64] * 13 + [_int, _int, _vp])
+                                     + [_i64] * 13 + [_int, _int, _vp, ctypes.c_size_t, _vp])
+    lib.cplxk_conv2d_workspace_bytes.restype = ctypes.c_size_t
+    lib.cplxk_conv2d_workspace_bytes.argtypes = [_i64] * 7 + [_int, _int]
     lib.cplxk_randn_philox_torch.argtypes = [_vp, _i64, _u64, _u64, _u32, ctypes.c_float, _vp]
     for name in EXPORTS:
         getattr(lib, name)  # fail at load time, not at first use, if a symbol is missing

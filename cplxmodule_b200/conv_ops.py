@@ -68,13 +68,19 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
         else:
             numel = (2 if cplx else 1) * y_re.numel()
             gen, seed, offset, threads, inc = nv.philox_plan(dev, max(numel, 1))
+    math = nv.MATH_SIMT if ops.get_math_mode() == "simt" else (
+        nv.MATH_TENSOR if ops.get_math_mode() == "tensor" else nv.MATH_AUTO)
+    ws, ws_bytes = None, 0
+    if cplx and math != nv.MATH_SIMT:
+        ws_bytes = nv.lib().cplxk_conv2d_workspace_bytes(B, C, H, W, O, kh, kw, code,
+                                                         1 if ls2 is not None else 0)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         nv.check(nv.lib().cplxk_conv2d_fwd(
             nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi), nv.ptr(br), nv.ptr(bi), nv.ptr(l2),
             nv.ptr(er), nv.ptr(ei), mode, seed, offset, threads, nv.ptr(y_re), nv.ptr(y_im),
             B, C, H, W, O, kh, kw, stride[0], stride[1], padding[0], padding[1],
-            dilation[0], dilation[1], code,
-            nv.MATH_SIMT if ops.get_math_mode() == "simt" else nv.MATH_AUTO, nv.stream_ptr(dev)))
+            dilation[0], dilation[1], code, math, nv.ptr(ws), ws_bytes, nv.stream_ptr(dev)))
     if gen is not None:
         gen.set_offset(offset + inc)
     return y_re, y_im

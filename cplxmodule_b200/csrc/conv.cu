@@ -8,6 +8,7 @@
 // dilation / padding); conv1d is the H == kh == 1 case.
 #include "common.cuh"
 #include "noise.cuh"
+#include "conv_tc.cuh"
 
 namespace cplxk {
 
@@ -208,7 +209,8 @@ extern "C" int cplxk_conv2d_fwd(const void* x_re, const void* x_im, const void* 
                                 void* y_re, void* y_im, int64_t B, int64_t C, int64_t H, int64_t W,
                                 int64_t O, int64_t kh, int64_t kw, int64_t stride_h,
                                 int64_t stride_w, int64_t pad_h, int64_t pad_w, int64_t dil_h,
-                                int64_t dil_w, int dtype, int math, void* stream) {
+                                int64_t dil_w, int dtype, int math, void* workspace,
+                                size_t workspace_bytes, void* stream) {
   if (!x_re || !w_re || !y_re) return CPLXK_ERR_BADARG;
   if (B < 0 || C < 1 || H < 1 || W < 1 || O < 0 || kh < 1 || kw < 1 || stride_h < 1 ||
       stride_w < 1 || pad_h < 0 || pad_w < 0 || dil_h < 1 || dil_w < 1)
@@ -223,7 +225,6 @@ extern "C" int cplxk_conv2d_fwd(const void* x_re, const void* x_im, const void* 
     if (noise == CPLXK_NOISE_PHILOX_TORCH && (philox_threads == 0 || (offset & 3u)))
       return CPLXK_ERR_BADARG;
   }
-  if (math == CPLXK_MATH_TENSOR) return CPLXK_ERR_UNSUPPORTED;  // tcgen05 implicit GEMM: next
   ConvGeom g;
   g.B = B, g.C = C, g.H = H, g.W = W, g.O = O;
   g.kh = static_cast<int>(kh), g.kw = static_cast<int>(kw);
@@ -248,6 +249,18 @@ extern "C" int cplxk_conv2d_fwd(const void* x_re, const void* x_im, const void* 
   ep.noise.scale = cplx ? (1.0f / static_cast<float>(1.4142135623730951)) : 1.0f;
 
   auto st = static_cast<cudaStream_t>(stream);
+  // tensor-core implicit GEMM: complex, workspace supplied, geometry within the TMA box limits
+  const bool tc_ok = cplx && workspace != nullptr && aligned16(workspace) && aligned16(x_re) &&
+                     conv_tc_supported(dtype, B, C, H, W, O, g.Ho, g.Wo, g.kh, g.kw, g.sh, g.sw) &&
+                     workspace_bytes >= conv_tc_workspace_bytes(dtype, vd, B, C, H, W, O, kh, kw);
+  if (math == CPLXK_MATH_TENSOR && !tc_ok) return workspace ? CPLXK_ERR_UNSUPPORTED : CPLXK_ERR_WORKSPACE;
+  if (math != CPLXK_MATH_SIMT && tc_ok) {
+    ConvTcEpi te;
+    te.b_re = b_re, te.b_im = b_im, te.eps_re = eps_re, te.eps_im = eps_im;
+    te.y_re = y_re, te.y_im = y_im, te.plane_elems = ep.plane_elems, te.noise = ep.noise;
+    return conv_tc_dispatch(dtype, vd, x_re, x_im, w_re, w_im, log_sigma2, workspace, B, C, H, W, O,
+                            g.Ho, g.Wo, g.kh, g.kw, g.sh, g.sw, g.ph, g.pw, g.dh, g.dw, te, st);
+  }
 #define CPLXK_CONV_CASE(T)                                                                  \
   if (cplx && vd) return launch_conv<T, true, true>(x_re, x_im, w_re, w_im, log_sigma2, g, ep, st);   \
   if (cplx && !vd) return launch_conv<T, true, false>(x_re, x_im, w_re, w_im, log_sigma2, g, ep, st); \
@@ -257,4 +270,10 @@ extern "C" int cplxk_conv2d_fwd(const void* x_re, const void* x_im, const void* 
   if (dtype == CPLXK_BF16) { CPLXK_CONV_CASE(__nv_bfloat16) }
 #undef CPLXK_CONV_CASE
   return CPLXK_ERR_BADARG;
+}
+
+extern "C" size_t cplxk_conv2d_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t O,
+                                               int64_t kh, int64_t kw, int dtype, int variational) {
+  if (B < 0 || C < 1 || H < 1 || W < 1 || O < 0 || kh < 1 || kw < 1) return 0;
+  return conv_tc_workspace_bytes(dtype, variational != 0, B, C, H, W, O, kh, kw);
 }

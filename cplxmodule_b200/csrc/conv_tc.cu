@@ -1,0 +1,517 @@
+// tcgen05 + TMA implicit-GEMM complex convolution (NCHW in / NCHW out, groups == 1).
+//
+//   re = x_re * U - x_im * V ,  im = x_re * V + x_im * U      (cplx.py:729-742, convnd_quick)
+//   s2 = |x|^2 * exp(log_sigma2) ,  y = mu + b + eps sqrt(max(s2, 1e-8))   (complex/base.py:120-135)
+//
+// Like the reference's convnd_quick, the real and imaginary kernels are STACKED along the
+// output-channel axis: one 128-wide B operand [U(64 rows); V(64 rows)] per k-block, so a
+// 128-pixel x 64-channel complex output tile costs two N=128 MMAs per k-step
+//   D1 += x_re . [U;V]^T   ->  [ x_re*U | x_re*V ]
+//   D2 += x_im . [U;V]^T   ->  [ x_im*U | x_im*V ]
+// and the epilogue combines  re = D1[:, :64] - D2[:, 64:],  im = D1[:, 64:] + D2[:, :64].
+//
+// GEMM view: M = output pixels (a Ht x Wt patch of one image, Ht*Wt = 128), N = channels,
+// K = (r, s, c): for each kernel tap (r, s) and 128-byte channel chunk one 4-d TMA box
+// {channels, Wt, Ht, 1} of the channels-last copy of the input lands as a K-major 128B-swizzled
+// [128 pixels x 128 B] tile -- zero padding is TMA's out-of-bounds fill, stride is the tensor
+// map's element stride, dilation an offset of the box origin.  The channels-last copies (and
+// |x|^2, exp(log_sigma2), and the tap-major weight planes) are written once per call by
+// elementwise pre-pass kernels into a caller-provided workspace.
+#include <type_traits>
+
+#include "common.cuh"
+#include "noise.cuh"
+#include "ptx.cuh"
+#include "conv_tc.cuh"
+
+namespace cplxk {
+
+template <typename T>
+__device__ __forceinline__ float round_mma_operand(float v) {
+  if constexpr (std::is_same<T, float>::value) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+  } else {
+    return v;
+  }
+}
+
+// ------------------------------------------------------------------ pre-pass kernels
+// NCHW -> channels-last (NHWC, channels padded to Cp) for x_re, x_im and (VD) |x|^2.
+// 32 x 32 smem transpose: reads coalesced along W, writes coalesced along C.
+template <typename T, bool kVD>
+__global__ void __launch_bounds__(256)
+conv_nhwc_kernel(const T* __restrict__ x_re, const T* __restrict__ x_im, T* __restrict__ o_re,
+                 T* __restrict__ o_im, T* __restrict__ o_q, int C, int Cp, int H, int W) {
+  __shared__ float s_re[32][33], s_im[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int w0 = blockIdx.z * 32, c0 = blockIdx.y * 32;
+  const int64_t bh = blockIdx.x;  // b * H + h
+  const int64_t b = bh / H, h = bh - b * H;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, w = w0 + tx;
+    float vr = 0.f, vi = 0.f;
+    if (c < C && w < W) {
+      const int64_t off = ((b * C + c) * H + h) * W + w;
+      vr = Elem<T>::to_f(x_re[off]);
+      vi = Elem<T>::to_f(x_im[off]);
+    }
+    s_re[ty + 8 * i][tx] = vr;
+    s_im[ty + 8 * i][tx] = vi;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int w = w0 + ty + 8 * i, c = c0 + tx;
+    if (w < W && c < Cp) {
+      const float vr = s_re[tx][ty + 8 * i], vi = s_im[tx][ty + 8 * i];
+      const int64_t off = ((b * H + h) * W + w) * Cp + c;
+      o_re[off] = Elem<T>::from_f(round_mma_operand<T>(vr));
+      o_im[off] = Elem<T>::from_f(round_mma_operand<T>(vi));
+      if constexpr (kVD) o_q[off] = Elem<T>::from_f(round_mma_operand<T>(fmaf(vr, vr, vi * vi)));
+    }
+  }
+}
+
+// weights [O, C, kh, kw] -> tap-major planes [(r*kw+s) * Op + o][Cp]; E = exp(log_sigma2)
+template <typename T, bool kVD>
+__global__ void __launch_bounds__(256)
+conv_wprep_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T* __restrict__ ls2,
+                  T* __restrict__ u, T* __restrict__ v, T* __restrict__ e, int O, int Op, int C,
+                  int Cp, int khw) {
+  const int64_t total = static_cast<int64_t>(khw) * Op * Cp;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cp);
+    const int64_t t = i / Cp;
+    const int o = static_cast<int>(t % Op);
+    const int rs = static_cast<int>(t / Op);
+    float fu = 0.f, fv = 0.f, fe = 0.f;
+    if (o < O && c < C) {
+      const int64_t src = (static_cast<int64_t>(o) * C + c) * khw + rs;
+      fu = Elem<T>::to_f(w_re[src]);
+      fv = Elem<T>::to_f(w_im[src]);
+      if constexpr (kVD) fe = __expf(Elem<T>::to_f(ls2[src]));
+    }
+    u[i] = Elem<T>::from_f(round_mma_operand<T>(fu));
+    v[i] = Elem<T>::from_f(round_mma_operand<T>(fv));
+    if constexpr (kVD) e[i] = Elem<T>::from_f(round_mma_operand<T>(fe));
+  }
+}
+
+// ------------------------------------------------------------------------ main kernel
+template <typename T, bool kVD>
+struct ConvCfg {
+  static constexpr bool kBF16 = std::is_same<T, __nv_bfloat16>::value;
+  static constexpr int BM = 128, BNO = 64;                 // pixels x complex output channels
+  static constexpr int BKC = 128 / static_cast<int>(sizeof(T));  // channels per k-block
+  static constexpr int KSTEPS = 4;
+  static constexpr int A_TILE = 128 * 128;                 // 16 KB
+  static constexpr int OFF_XR = 0, OFF_XI = A_TILE, OFF_Q = 2 * A_TILE;
+  static constexpr int OFF_UV = (kVD ? 3 : 2) * A_TILE;    // [U(64 rows); V(64 rows)] = 16 KB
+  static constexpr int OFF_E = OFF_UV + A_TILE;            // 64 rows = 8 KB
+  static constexpr int STAGE_BYTES = OFF_UV + A_TILE + (kVD ? A_TILE / 2 : 0);
+  static constexpr int STAGES = kVD ? 3 : 2;               // VD: 1 CTA/SM, plain: 2 CTAs/SM
+  static constexpr int TMEM_COLS = kVD ? 512 : 256;        // D1 128 | D2 128 | (s2 64)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 1024;
+  static constexpr int THREADS = 192;
+};
+
+template <typename T, bool kVD>
+__global__ void __launch_bounds__(192, (kVD ? 1 : 2))
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__ CUtensorMap tm_xi,
+               const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_u,
+               const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_e,
+               const ConvTcGeom g, const ConvTcEpi ep) {
+  using C = ConvCfg<T, kVD>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t aux = base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bar_full = aux, bar_empty = aux + 8 * C::STAGES, bar_accum = aux + 16 * C::STAGES;
+  const uint32_t tmem_slot = bar_accum + 8;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + C::STAGES * C::STAGE_BYTES + 16 * C::STAGES + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile -> (n block, w block, h block, image)
+  int t = blockIdx.x;
+  const int n_blk = t % g.tiles_n;
+  t /= g.tiles_n;
+  const int w_blk = t % g.tiles_w;
+  t /= g.tiles_w;
+  const int h_blk = t % g.tiles_h;
+  const int b = t / g.tiles_h;
+  const int ow0 = w_blk * g.Wt, oh0 = h_blk * g.Ht, n0 = n_blk * C::BNO;
+  const int cchunks = (g.Cp + C::BKC - 1) / C::BKC;
+  const int num_kb = g.kh * g.kw * cchunks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_xr);
+    ptx::prefetch_tensormap(&tm_xi);
+    ptx::prefetch_tensormap(&tm_u);
+    ptx::prefetch_tensormap(&tm_v);
+    if constexpr (kVD) {
+      ptx::prefetch_tensormap(&tm_q);
+      ptx::prefetch_tensormap(&tm_e);
+    }
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, 1);
+    }
+    ptx::mbar_init(bar_accum, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % C::STAGES;
+        const uint32_t ph = (kb / C::STAGES) & 1;
+        ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        const uint32_t fb = bar_full + 8 * s;
+        const uint32_t st = base + s * C::STAGE_BYTES;
+        ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
+        const int rs = kb / cchunks, cc = kb - rs * cchunks;
+        const int r = rs / g.kw, sx = rs - r * g.kw;
+        const int32_t c0 = cc * C::BKC;
+        // box origin in INPUT coordinates (may be negative: zero padding = OOB fill)
+        const int32_t iw = ow0 * g.sw - g.pw + sx * g.dw;
+        const int32_t ih = oh0 * g.sh - g.ph + r * g.dh;
+        ptx::tma_load_4d(st + C::OFF_XR, &tm_xr, fb, c0, iw, ih, b);
+        ptx::tma_load_4d(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
+        if constexpr (kVD) ptx::tma_load_4d(st + C::OFF_Q, &tm_q, fb, c0, iw, ih, b);
+        const int32_t wrow = rs * g.Op + n0;
+        ptx::tma_load_2d(st + C::OFF_UV, &tm_u, fb, c0, wrow);
+        ptx::tma_load_2d(st + C::OFF_UV + C::A_TILE / 2, &tm_v, fb, c0, wrow);
+        if constexpr (kVD) ptx::tma_load_2d(st + C::OFF_E, &tm_e, fb, c0, wrow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc128 = ptx::make_idesc<C::kBF16>(128, 128, false, false);
+      constexpr uint32_t idesc64 = ptx::make_idesc<C::kBF16>(128, 64, false, false);
+      const uint32_t t_d1 = tmem_base, t_d2 = tmem_base + 128, t_s2 = tmem_base + 256;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % C::STAGES;
+        const uint32_t ph = (kb / C::STAGES) & 1;
+        const uint32_t st = base + s * C::STAGE_BYTES;
+        ptx::mbar_wait(bar_full + 8 * s, ph);
+        ptx::tcgen05_fence_after();
+        const uint64_t a_r = ptx::make_kmajor_desc<128>(st + C::OFF_XR);
+        const uint64_t a_i = ptx::make_kmajor_desc<128>(st + C::OFF_XI);
+        const uint64_t a_q = ptx::make_kmajor_desc<128>(st + C::OFF_Q);
+        const uint64_t b_uv = ptx::make_kmajor_desc<128>(st + C::OFF_UV);
+        const uint64_t b_e = ptx::make_kmajor_desc<128>(st + C::OFF_E);
+#pragma unroll
+        for (int k = 0; k < C::KSTEPS; ++k) {
+          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+          const uint32_t off = k * 32;
+          ptx::umma_ss<C::kBF16>(t_d1, ptx::desc_advance(a_r, off), ptx::desc_advance(b_uv, off), idesc128, acc);
+          ptx::umma_ss<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc128, acc);
+          if constexpr (kVD)
+            ptx::umma_ss<C::kBF16>(t_s2, ptx::desc_advance(a_q, off), ptx::desc_advance(b_e, off), idesc64, acc);
+        }
+        ptx::umma_commit(bar_empty + 8 * s);
+      }
+      ptx::umma_commit(bar_accum);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int quarter = warp & 3;
+    const int p = quarter * 32 + lane;            // pixel of the tile = TMEM lane
+    const int hh = p / g.Wt, ww = p - hh * g.Wt;
+    const int64_t oh = oh0 + hh, ow = ow0 + ww;
+    const bool pix_ok = oh < g.Ho && ow < g.Wo;
+    const int64_t hw = g.Ho * g.Wo;
+    const int64_t pix_off = static_cast<int64_t>(b) * g.O * hw + oh * g.Wo + ow;  // + o * hw
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+
+    // VD: the 2 x 64 normals of this pixel (one per output channel and plane) are generated /
+    // fetched while the MMAs run and stay in registers.  Consecutive channels are `hw` apart in
+    // torch's linear element order, so (subsequence, slot) advance by a constant -- no division.
+    float nre[kVD ? 64 : 1], nim[kVD ? 64 : 1];
+    if constexpr (kVD) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) nre[j] = 0.f, nim[j] = 0.f;
+      if (pix_ok) {
+        if (ep.noise.mode == CPLXK_NOISE_INJECT) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (n0 + j < g.O) {
+              const int64_t off = pix_off + static_cast<int64_t>(n0 + j) * hw;
+              nre[j] = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.eps_re) + off));
+              nim[j] = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.eps_im) + off));
+            }
+        } else if (ep.noise.mode == CPLXK_NOISE_PHILOX_TORCH) {
+          const uint32_t T_ = ep.noise.threads;
+          const uint64_t li0 = static_cast<uint64_t>(pix_off + static_cast<int64_t>(n0) * hw);
+          uint64_t slot_re = li0 / T_;
+          uint32_t idx_re = static_cast<uint32_t>(li0 - slot_re * T_);
+          const uint64_t li1 = li0 + static_cast<uint64_t>(ep.plane_elems);
+          uint64_t slot_im = li1 / T_;
+          uint32_t idx_im = static_cast<uint32_t>(li1 - slot_im * T_);
+          const uint64_t dq = static_cast<uint64_t>(hw) / T_;
+          const uint32_t dr = static_cast<uint32_t>(static_cast<uint64_t>(hw) - dq * T_);
+#pragma unroll 1
+          for (int trip = 0; trip < 8; ++trip) {
+#pragma unroll
+            for (int j = 0; j < 56; ++j) nre[j] = nre[j + 8], nim[j] = nim[j + 8];
+            uint32_t ir[8], ii[8];
+            uint64_t sr[8], si[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              ir[j] = idx_re, sr[j] = slot_re, ii[j] = idx_im, si[j] = slot_im;
+              idx_re += dr, slot_re += dq;
+              if (idx_re >= T_) idx_re -= T_, ++slot_re;
+              idx_im += dr, slot_im += dq;
+              if (idx_im >= T_) idx_im -= T_, ++slot_im;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              nre[56 + j] = philox_torch_normal(ir[j], sr[j], ep.noise) * ep.noise.scale;
+              nim[56 + j] = philox_torch_normal(ii[j], si[j], ep.noise) * ep.noise.scale;
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int trip = 0; trip < 8; ++trip) {
+#pragma unroll
+            for (int j = 0; j < 56; ++j) nre[j] = nre[j + 8], nim[j] = nim[j + 8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int64_t off = pix_off + static_cast<int64_t>(n0 + trip * 8 + j) * hw;
+              const uint64_t q = static_cast<uint64_t>(off) >> 2;
+              const int comp = static_cast<int>(off & 3);
+              float4 a = philox_fast_normal4(q, 0u, ep.noise);
+              float4 bb = philox_fast_normal4(q, 1u, ep.noise);
+              nre[56 + j] = (comp == 0 ? a.x : comp == 1 ? a.y : comp == 2 ? a.z : a.w) * ep.noise.scale;
+              nim[56 + j] = (comp == 0 ? bb.x : comp == 1 ? bb.y : comp == 2 ? bb.z : bb.w) * ep.noise.scale;
+            }
+          }
+        }
+      }
+    }
+
+    ptx::mbar_wait(bar_accum, 0);
+    ptx::tcgen05_fence_after();
+#pragma unroll
+    for (int c = 0; c < C::BNO / 8; ++c) {
+      uint32_t d1a[8], d1b[8], d2a[8], d2b[8], s2r[8];
+      ptx::tmem_ld_32x32b_x8(lane_base + c * 8, d1a);          // x_re * U
+      ptx::tmem_ld_32x32b_x8(lane_base + 64 + c * 8, d1b);     // x_re * V
+      ptx::tmem_ld_32x32b_x8(lane_base + 128 + c * 8, d2a);    // x_im * U
+      ptx::tmem_ld_32x32b_x8(lane_base + 192 + c * 8, d2b);    // x_im * V
+      if constexpr (kVD) ptx::tmem_ld_32x32b_x8(lane_base + 256 + c * 8, s2r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int o = n0 + c * 8 + j;
+        if (!pix_ok || o >= g.O) continue;
+        float re = __uint_as_float(d1a[j]) - __uint_as_float(d2b[j]);
+        float im = __uint_as_float(d1b[j]) + __uint_as_float(d2a[j]);
+        if (ep.b_re) {
+          re += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_re) + o));
+          im += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_im) + o));
+        }
+        const int64_t off = pix_off + static_cast<int64_t>(o) * hw;
+        if constexpr (kVD) {
+          const float sd = sqrtf(fmaxf(__uint_as_float(s2r[j]), 1e-8f));
+          re = fmaf(nre[c * 8 + j], sd, re);
+          im = fmaf(nim[c * 8 + j], sd, im);
+        }
+        static_cast<T*>(ep.y_re)[off] = Elem<T>::from_f(re);   // 32 lanes -> 32 consecutive pixels
+        static_cast<T*>(ep.y_im)[off] = Elem<T>::from_f(im);
+      }
+    }
+    ptx::tcgen05_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// -------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiledC)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiledC conv_encode_fn() {
+  static PFN_encodeTiledC fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiledC>(p);
+  }
+  return fn;
+}
+
+template <typename T>
+static CUtensorMapDataType conv_dt() {
+  return std::is_same<T, float>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                       : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+}
+
+// channels-last activation plane [B, H, W, Cp]: box {BKC channels, Wt px (stride sw), Ht rows (stride sh), 1}
+template <typename T>
+static int make_act_map(CUtensorMap* out, const void* ptr, const ConvTcGeom& g) {
+  auto enc = conv_encode_fn();
+  if (!enc) return CPLXK_ERR_CUDA;
+  const cuuint64_t es = sizeof(T);
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(g.Cp), static_cast<cuuint64_t>(g.W),
+                        static_cast<cuuint64_t>(g.H), static_cast<cuuint64_t>(g.B)};
+  cuuint64_t gstr[3] = {g.Cp * es, static_cast<cuuint64_t>(g.W) * g.Cp * es,
+                        static_cast<cuuint64_t>(g.H) * g.W * g.Cp * es};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(128 / sizeof(T)),
+                       static_cast<cuuint32_t>((g.Wt - 1) * g.sw + 1),
+                       static_cast<cuuint32_t>((g.Ht - 1) * g.sh + 1), 1u};
+  cuuint32_t estr[4] = {1u, static_cast<cuuint32_t>(g.sw), static_cast<cuuint32_t>(g.sh), 1u};
+  CUresult r = enc(out, conv_dt<T>(), 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CPLXK_OK : CPLXK_ERR_CUDA;
+}
+
+// tap-major weight plane [khw * Op, Cp]: box {BKC channels, 64 rows}
+template <typename T>
+static int make_w_map(CUtensorMap* out, const void* ptr, const ConvTcGeom& g) {
+  auto enc = conv_encode_fn();
+  if (!enc) return CPLXK_ERR_CUDA;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(g.Cp),
+                        static_cast<cuuint64_t>(g.kh) * g.kw * g.Op};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(g.Cp) * sizeof(T)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / sizeof(T)), 64u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, conv_dt<T>(), 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CPLXK_OK : CPLXK_ERR_CUDA;
+}
+
+static inline size_t up256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+static void conv_tc_plan(ConvTcGeom& g, int dtype) {
+  const int gran = dtype == CPLXK_F32 ? 8 : 16;   // pitch % 32 B, whole k-steps
+  g.Cp = static_cast<int>((g.C + gran - 1) / gran * gran);
+  g.Op = static_cast<int>((g.O + 63) / 64 * 64);
+  int wt = 128;
+  while (wt > 8 && wt / 2 >= g.Wo) wt /= 2;       // smallest power of two covering Wo (>= 8)
+  g.Wt = wt;
+  g.Ht = 128 / wt;
+  g.tiles_w = static_cast<int>((g.Wo + g.Wt - 1) / g.Wt);
+  g.tiles_h = static_cast<int>((g.Ho + g.Ht - 1) / g.Ht);
+  g.tiles_n = g.Op / 64;
+}
+
+size_t conv_tc_workspace_bytes(int dtype, bool vd, int64_t B, int64_t C, int64_t H, int64_t W,
+                               int64_t O, int64_t kh, int64_t kw) {
+  ConvTcGeom g{};
+  g.B = B, g.C = C, g.H = H, g.W = W, g.O = O, g.kh = static_cast<int>(kh), g.kw = static_cast<int>(kw);
+  g.Wo = g.Ho = 128;
+  conv_tc_plan(g, dtype);
+  const size_t es = dtype == CPLXK_F32 ? 4 : 2;
+  const size_t act = up256(static_cast<size_t>(B) * H * W * g.Cp * es);
+  const size_t wgt = up256(static_cast<size_t>(kh) * kw * g.Op * g.Cp * es);
+  return (vd ? 3 : 2) * act + (vd ? 3 : 2) * wgt;
+}
+
+bool conv_tc_supported(int dtype, int64_t B, int64_t C, int64_t H, int64_t W, int64_t O, int64_t Ho,
+                       int64_t Wo, int kh, int kw, int sh, int sw) {
+  if (B < 1 || B > 0x7fffffff || H > 0x7fffffff || W > 0x7fffffff) return false;
+  ConvTcGeom g{};
+  g.C = C, g.O = O, g.Ho = Ho, g.Wo = Wo;
+  conv_tc_plan(g, dtype);
+  if ((g.Wt - 1) * sw + 1 > 256 || (g.Ht - 1) * sh + 1 > 256) return false;  // TMA box limit
+  const int64_t tiles = B * g.tiles_h * g.tiles_w * g.tiles_n;
+  return tiles > 0 && tiles <= 0x7fffffff && kh * kw <= 4096;
+}
+
+template <typename T, bool kVD>
+static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, const void* w_im,
+                          const void* ls2, void* workspace, ConvTcGeom g, const ConvTcEpi& ep,
+                          cudaStream_t st) {
+  using C = ConvCfg<T, kVD>;
+  const size_t es = sizeof(T);
+  const size_t act = up256(static_cast<size_t>(g.B) * g.H * g.W * g.Cp * es);
+  const size_t wgt = up256(static_cast<size_t>(g.kh) * g.kw * g.Op * g.Cp * es);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  T* a_re = reinterpret_cast<T*>(ws);
+  T* a_im = reinterpret_cast<T*>(ws + act);
+  T* a_q = kVD ? reinterpret_cast<T*>(ws + 2 * act) : nullptr;
+  uint8_t* wbase = ws + (kVD ? 3 : 2) * act;
+  T* u = reinterpret_cast<T*>(wbase);
+  T* v = reinterpret_cast<T*>(wbase + wgt);
+  T* e = kVD ? reinterpret_cast<T*>(wbase + 2 * wgt) : nullptr;
+
+  dim3 tg(static_cast<unsigned>(g.B * g.H), static_cast<unsigned>((g.Cp + 31) / 32),
+          static_cast<unsigned>((g.W + 31) / 32));
+  if (tg.y > 65535u || tg.z > 65535u || g.B * g.H > 0x7fffffff) return CPLXK_ERR_UNSUPPORTED;
+  conv_nhwc_kernel<T, kVD><<<tg, 256, 0, st>>>(static_cast<const T*>(x_re), static_cast<const T*>(x_im),
+                                               a_re, a_im, a_q, static_cast<int>(g.C), g.Cp,
+                                               static_cast<int>(g.H), static_cast<int>(g.W));
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  const int64_t wtotal = static_cast<int64_t>(g.kh) * g.kw * g.Op * g.Cp;
+  conv_wprep_kernel<T, kVD><<<static_cast<unsigned>(wtotal / 256 + 1 > 1184 ? 1184 : wtotal / 256 + 1), 256, 0, st>>>(
+      static_cast<const T*>(w_re), static_cast<const T*>(w_im), static_cast<const T*>(ls2), u, v, e,
+      static_cast<int>(g.O), g.Op, static_cast<int>(g.C), g.Cp, g.kh * g.kw);
+  CPLXK_CUDA_TRY(cudaGetLastError());
+
+  CUtensorMap tm_xr, tm_xi, tm_q, tm_u, tm_v, tm_e;
+  int rc;
+  if ((rc = make_act_map<T>(&tm_xr, a_re, g))) return rc;
+  if ((rc = make_act_map<T>(&tm_xi, a_im, g))) return rc;
+  if ((rc = make_w_map<T>(&tm_u, u, g))) return rc;
+  if ((rc = make_w_map<T>(&tm_v, v, g))) return rc;
+  tm_q = tm_xr, tm_e = tm_u;
+  if (kVD) {
+    if ((rc = make_act_map<T>(&tm_q, a_q, g))) return rc;
+    if ((rc = make_w_map<T>(&tm_e, e, g))) return rc;
+  }
+  const int64_t tiles = g.B * g.tiles_h * g.tiles_w * g.tiles_n;
+  auto kern = conv_tc_kernel<T, kVD>;
+  CPLXK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  kern<<<static_cast<unsigned>(tiles), C::THREADS, C::SMEM_BYTES, st>>>(tm_xr, tm_xi, tm_q, tm_u, tm_v,
+                                                                      tm_e, g, ep);
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
+}
+
+int conv_tc_dispatch(int dtype, bool vd, const void* x_re, const void* x_im, const void* w_re,
+                     const void* w_im, const void* ls2, void* workspace, int64_t B, int64_t C,
+                     int64_t H, int64_t W, int64_t O, int64_t Ho, int64_t Wo, int kh, int kw, int sh,
+                     int sw, int ph, int pw, int dh, int dw, const ConvTcEpi& ep, cudaStream_t st) {
+  ConvTcGeom g{};
+  g.B = B, g.C = C, g.H = H, g.W = W, g.O = O, g.Ho = Ho, g.Wo = Wo;
+  g.kh = kh, g.kw = kw, g.sh = sh, g.sw = sw, g.ph = ph, g.pw = pw, g.dh = dh, g.dw = dw;
+  conv_tc_plan(g, dtype);
+  if (dtype == CPLXK_F32) {
+    if (vd) return launch_conv_tc<float, true>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st);
+    return launch_conv_tc<float, false>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st);
+  }
+  if (dtype == CPLXK_BF16) {
+    if (vd) return launch_conv_tc<__nv_bfloat16, true>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st);
+    return launch_conv_tc<__nv_bfloat16, false>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st);
+  }
+  return CPLXK_ERR_BADARG;
+}
+
+}  // namespace cplxk

@@ -1,0 +1,36 @@
+// Interface between the conv C-ABI entry point (conv.cu) and the tcgen05 implicit GEMM (conv_tc.cu).
+#pragma once
+#include "common.cuh"
+#include "noise.cuh"
+
+namespace cplxk {
+
+struct ConvTcGeom {
+  int64_t B, C, H, W, O, Ho, Wo;
+  int Cp, Op;            // padded channel counts of the workspace planes
+  int kh, kw, sh, sw, ph, pw, dh, dw;
+  int Wt, Ht;            // output patch of one tile (Wt * Ht == 128)
+  int tiles_w, tiles_h, tiles_n;
+};
+
+struct ConvTcEpi {
+  const void* b_re;
+  const void* b_im;
+  const void* eps_re;
+  const void* eps_im;
+  void* y_re;
+  void* y_im;
+  int64_t plane_elems;
+  NoiseParams noise;
+};
+
+size_t conv_tc_workspace_bytes(int dtype, bool vd, int64_t B, int64_t C, int64_t H, int64_t W,
+                               int64_t O, int64_t kh, int64_t kw);
+bool conv_tc_supported(int dtype, int64_t B, int64_t C, int64_t H, int64_t W, int64_t O, int64_t Ho,
+                       int64_t Wo, int kh, int kw, int sh, int sw);
+int conv_tc_dispatch(int dtype, bool vd, const void* x_re, const void* x_im, const void* w_re,
+                     const void* w_im, const void* ls2, void* workspace, int64_t B, int64_t C,
+                     int64_t H, int64_t W, int64_t O, int64_t Ho, int64_t Wo, int kh, int kw, int sh,
+                     int sw, int ph, int pw, int dh, int dw, const ConvTcEpi& ep, cudaStream_t st);
+
+}  // namespace cplxk

@@ -162,7 +162,14 @@ int cplxk_log_alpha(const void* w_re, const void* w_im, const void* log_sigma2,
  * CplxConvNdGaussianMixin._forward_impl (nn/relevance/complex/base.py:120-135).
  * conv1d is the H == kh == 1 case.
  *   x : [B,C,H,W]  w,log_sigma2 : [O,C,kh,kw]  b : [O]  y,eps : [B,O,Ho,Wo]
+ *   workspace (nullable): cplxk_conv2d_workspace_bytes() bytes of scratch, 16-byte aligned.
+ *     With it (complex planes only) the call runs the tcgen05 implicit GEMM: two elementwise
+ *     launches write channels-last copies of the input (and |x|^2, exp(log_sigma2), tap-major
+ *     weights) to the workspace, one kernel does the MMAs + epilogue.  Without it, or for
+ *     geometries outside the TMA box limits, the exact-fp32 CUDA-core kernel runs.
  */
+size_t cplxk_conv2d_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t O,
+                                    int64_t kh, int64_t kw, int dtype, int variational);
 int cplxk_conv2d_fwd(const void* x_re, const void* x_im,
                      const void* w_re, const void* w_im,
                      const void* b_re, const void* b_im,
@@ -176,7 +183,8 @@ int cplxk_conv2d_fwd(const void* x_re, const void* x_im,
                      int64_t stride_h, int64_t stride_w,
                      int64_t pad_h, int64_t pad_w,
                      int64_t dil_h, int64_t dil_w,
-                     int dtype, int math, void* stream);
+                     int dtype, int math,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Test hook: fill out[n] (float) with scale * N(0,1) using the very device

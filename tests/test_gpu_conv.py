@@ -12,6 +12,15 @@ from tests.conftest import load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+TOL = {"simt": 2e-5, "tensor": 1e-3}
+
+
+@pytest.fixture(params=["simt", "tensor"])
+def math(request):
+    from cplxmodule_b200 import ops
+    ops.set_math_mode(request.param)
+    yield request.param
+    ops.set_math_mode("auto")
 
 
 def _mod(cls, g, suffix="", **kw):
@@ -25,26 +34,88 @@ def _mod(cls, g, suffix="", **kw):
     return m.to(DEV)
 
 
-def test_golden_conv2d():
+def test_golden_conv2d(math):
     g = load_golden("cplx_conv2d")
     z = cplx.Cplx(g["x_re"].to(DEV), g["x_im"].to(DEV))
     out = _mod(CplxConv2d, g)(z)
     assert out.shape == g["y_re"].shape
-    assert rel_err(out.real, g["y_re"]) < 2e-5 and rel_err(out.imag, g["y_im"]) < 2e-5
+    assert rel_err(out.real, g["y_re"]) < TOL[math] and rel_err(out.imag, g["y_im"]) < TOL[math]
     out = _mod(CplxConv2d, g, "2", stride=(2, 1), padding=(1, 2), dilation=(1, 2))(z)
     assert out.shape == g["y2_re"].shape
-    assert rel_err(out.real, g["y2_re"]) < 2e-5 and rel_err(out.imag, g["y2_im"]) < 2e-5
+    assert rel_err(out.real, g["y2_re"]) < TOL[math] and rel_err(out.imag, g["y2_im"]) < TOL[math]
 
 
-def test_golden_conv2d_vd():
+def test_golden_conv2d_vd(math):
     g = load_golden("cplx_conv2d_vd")
     layer = _mod(CplxConv2dVD, g, padding=1).train()
     z = cplx.Cplx(g["x_re"].to(DEV), g["x_im"].to(DEV))
     with torch.no_grad():
         out = layer(z, eps=cplx.Cplx(g["eps_re"].to(DEV), g["eps_im"].to(DEV)))
         kl = sum(penalties(layer))
-    assert rel_err(out.real, g["y_re"]) < 2e-5 and rel_err(out.imag, g["y_im"]) < 2e-5
+    assert rel_err(out.real, g["y_re"]) < TOL[math] and rel_err(out.imag, g["y_im"]) < TOL[math]
     assert abs(kl.item() - g["penalty_sum"].item()) / g["penalty_sum"].item() < 1e-3
+
+
+@pytest.mark.parametrize("shape", [
+    # (B, C, H, W, O, k, stride, padding, dilation)
+    (3, 64, 20, 140, 64, 3, 1, 0, 1),       # Wt = 128 with a ragged second w-tile
+    (2, 40, 17, 19, 72, (3, 5), 1, (1, 2), 1),   # Cp/Op padding, Wt = 32, two n-blocks
+    (2, 16, 30, 33, 8, 3, 2, 1, 1),         # stride 2 through the tensor map's element strides
+    (1, 24, 12, 9, 5, 2, 1, 0, (2, 3)),     # dilation, Wt = 16
+    (2, 8, 6, 40, 4, (1, 7), (1, 3), (0, 3), 1),  # conv1d-like row kernel, stride 3
+])
+@pytest.mark.parametrize("vd", [False, True])
+def test_tensor_core_conv_shapes(shape, vd):
+    """tcgen05 implicit GEMM (channels-last pre-pass + 4-d TMA boxes) vs the float64 oracle."""
+    from cplxmodule_b200 import ops
+    B, C, H, W, O, k, stride, padding, dilation = shape
+    torch.manual_seed(hash(shape) % 1000)
+    cls = CplxConv2dVD if vd else CplxConv2d
+    m = cls(C, O, k, stride=stride, padding=padding, dilation=dilation).to(DEV).train()
+    z = cplx.randn(B, C, H, W, device=DEV)
+    c = lambda t: t.detach().cpu().double()
+    args = [c(z.real), c(z.imag), c(m.weight.real), c(m.weight.imag), c(m.bias.real), c(m.bias.imag)]
+    if vd:
+        with torch.no_grad():
+            m.log_sigma2.uniform_(-8, 0)
+        want_mu = orc.cplx_conv2d(*args, m.stride, m.padding, m.dilation)
+        eps = cplx.randn(*want_mu[0].shape, device=DEV)
+        want = orc.cplx_conv2d_vd(*args, c(m.log_sigma2), c(eps.real), c(eps.imag), m.stride,
+                                  m.padding, m.dilation)
+    else:
+        eps = None
+        want = orc.cplx_conv2d(*args, m.stride, m.padding, m.dilation)
+    ops.set_math_mode("tensor")
+    try:
+        with torch.no_grad():
+            out = m(z, eps=eps) if vd else m(z)
+    finally:
+        ops.set_math_mode("auto")
+    assert out.shape == want[0].shape
+    assert rel_err(out.real, want[0]) < 1e-3 and rel_err(out.imag, want[1]) < 1e-3
+
+
+def test_full_size_conv_config4_one_image():
+    """BASELINE config 4 (256 x 64 x 128 x 128, 3x3, 64 -> 64): images 0 and 255 of the
+    tensor-core result against the oracle on CPU; bf16 planes within 1e-2."""
+    torch.manual_seed(12)
+    m = CplxConv2d(64, 64, 3).to(DEV)
+    z = cplx.randn(256, 64, 128, 128, device=DEV)
+    with torch.no_grad():
+        out = m(z)
+    assert out.shape == (256, 64, 126, 126)
+    c = lambda t: t.detach().cpu()
+    for b in (0, 255):
+        want = orc.cplx_conv2d(c(z.real[b:b + 1]), c(z.imag[b:b + 1]), c(m.weight.real),
+                               c(m.weight.imag), c(m.bias.real), c(m.bias.imag))
+        assert rel_err(out.real[b:b + 1], want[0]) < 1e-3
+        assert rel_err(out.imag[b:b + 1], want[1]) < 1e-3
+    m16, z16 = m.bfloat16(), z.to(torch.bfloat16)
+    with torch.no_grad():
+        out16 = m16(z16)
+    want = orc.cplx_conv2d(c(z16.real[:1]).float(), c(z16.imag[:1]).float(), c(m16.weight.real).float(),
+                           c(m16.weight.imag).float(), c(m16.bias.real).float(), c(m16.bias.imag).float())
+    assert rel_err(out16.real[:1].float(), want[0]) < 1e-2
 
 
 def test_conv2d_vd_fused_noise_matches_device_draw():
@@ -76,7 +147,7 @@ def test_conv1d_groups_circular_vs_torch_formula():
     re = wr[:, :6] - wi[:, 6:] + c(m.bias.real)[None, :, None]
     im = wr[:, 6:] + wi[:, :6] + c(m.bias.imag)[None, :, None]
     assert out.shape == re.shape
-    assert rel_err(out.real, re) < 2e-5 and rel_err(out.imag, im) < 2e-5
+    assert rel_err(out.real, re) < 1e-3 and rel_err(out.imag, im) < 1e-3
     # groups = 2 (convnd_naive, cplx.py:717-726)
     m = CplxConv2d(4, 6, 3, groups=2, bias=False).to(DEV)
     z = cplx.randn(2, 4, 7, 7, device=DEV)
@@ -84,7 +155,7 @@ def test_conv1d_groups_circular_vs_torch_formula():
     f = lambda a, w: F.conv2d(c(a), c(w), None, 1, 0, 1, 2)
     re = f(z.real, m.weight.real) - f(z.imag, m.weight.imag)
     im = f(z.real, m.weight.imag) + f(z.imag, m.weight.real)
-    assert rel_err(out.real, re) < 2e-5 and rel_err(out.imag, im) < 2e-5
+    assert rel_err(out.real, re) < 1e-3 and rel_err(out.imag, im) < 1e-3
     # circular padding (cplx.py:701-714, 784-786)
     m = CplxConv2d(2, 3, 3, padding=2, padding_mode="circular").to(DEV)
     z = cplx.randn(1, 2, 6, 5, device=DEV)
@@ -92,6 +163,6 @@ def test_conv1d_groups_circular_vs_torch_formula():
     pad = lambda a: F.pad(c(a), (1, 1, 1, 1), mode="circular")
     want = orc.cplx_conv2d(pad(z.real), pad(z.imag), c(m.weight.real), c(m.weight.imag),
                            c(m.bias.real), c(m.bias.imag))
-    assert rel_err(out.real, want[0]) < 2e-5 and rel_err(out.imag, want[1]) < 2e-5
+    assert rel_err(out.real, want[0]) < 1e-3 and rel_err(out.imag, want[1]) < 1e-3
     with pytest.raises(ValueError):
         cplx.conv2d(z, m.weight, None, padding_mode="reflect")

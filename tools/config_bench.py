@@ -78,12 +78,20 @@ def main():
         for cls, name, nconv in ((CplxConv2d, "CplxConv2d", 4), (CplxConv2dVD, "CplxConv2dVD", 5)):
             conv = cls(64, 64, 3).to(DEV).train()
             z = cplx.randn(256, 64, 128, 128, device=DEV)
-            ms = timeit(lambda: conv(z), 3, 1)
             flops = nconv * 2 * 256 * 64 * 126 * 126 * 64 * 9
-            nbytes = 4 * (2 * 256 * 64 * 128 * 128 + 2 * 256 * 64 * 126 * 126)
-            out.append(row(f"4 {name} 64->64 3x3 128x128 B=256 fp32", ms, flops, nbytes,
-                           "conv_simt_kernel: exact-fp32 CUDA-core implicit GEMM (tensor-core conv = next)"))
-            del conv, z
+            for dt, es, tag in ((torch.float32, 4, "fp32/tf32"), (torch.bfloat16, 2, "bf16")):
+                convd, zd = conv.to(dt), z.to(dt)
+                ms = timeit(lambda: convd(zd), 5, 2)
+                nbytes = es * (2 * 256 * 64 * 128 * 128 + 2 * 256 * 64 * 126 * 126)
+                out.append(row(f"4 {name} 64->64 3x3 128x128 B=256 {tag}", ms, flops, nbytes,
+                               "channels-last pre-pass + conv_tc_kernel (tcgen05 implicit GEMM)"))
+            ops.set_math_mode("simt")
+            conv32, z32 = conv.float(), z
+            ms = timeit(lambda: conv32(z32), 2, 1)
+            ops.set_math_mode("auto")
+            out.append(row(f"4 {name} fp32 exact (conv_simt_kernel)", ms, flops,
+                           4 * (2 * 256 * 64 * 128 * 128 + 2 * 256 * 64 * 126 * 126), "CUDA-core path"))
+            del conv, z, convd, zd
         # 5. CplxLinearARD 8192^2, per-GPU shard of the 8-GPU config: 8192 rows, 1/8 of the KL
         ard = CplxLinearARD(8192, 8192).to(DEV).train()
         z = cplx.randn(8192, 8192, device=DEV)
