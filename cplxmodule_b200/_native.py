@@ -22,6 +22,8 @@ EXPORTS = (
     "cplxk_abi_version", "cplxk_strerror", "cplxk_device_info", "cplxk_linear_fwd",
     "cplxk_linear_vd_fwd", "cplxk_linear_vd_workspace_bytes", "cplxk_kl_workspace_bytes", "cplxk_kl", "cplxk_log_alpha",
     "cplxk_conv2d_fwd", "cplxk_conv2d_workspace_bytes", "cplxk_randn_philox_torch",
+    "cplxk_transpose2d", "cplxk_colsum", "cplxk_vd_grad_s2", "cplxk_vd_grad_input",
+    "cplxk_mul_exp", "cplxk_kl_bwd",
 )
 
 _lock = threading.Lock()
@@ -38,7 +40,7 @@ def _declare(lib):
     lib.cplxk_device_info.argtypes = [ctypes.POINTER(_int)] * 3
     lib.cplxk_linear_fwd.argtypes = [_vp] * 8 + [_i64] * 3 + [_int, _int, _vp]
     lib.cplxk_linear_vd_fwd.argtypes = ([_vp] * 9 + [_int, _u64, _u64, _u32] + [_vp] * 2
-                                        + [_i64] * 3 + [_int, _int, _vp, ctypes.c_size_t, _vp])
+                                        + [_i64] * 3 + [_int, _int, _vp, _vp, ctypes.c_size_t, _vp])
     lib.cplxk_linear_vd_workspace_bytes.restype = ctypes.c_size_t
     lib.cplxk_linear_vd_workspace_bytes.argtypes = [_i64, _i64, _i64, _int]
     lib.cplxk_kl_workspace_bytes.restype = ctypes.c_size_t
@@ -50,6 +52,13 @@ def _declare(lib):
     lib.cplxk_conv2d_workspace_bytes.restype = ctypes.c_size_t
     lib.cplxk_conv2d_workspace_bytes.argtypes = [_i64] * 7 + [_int, _int]
     lib.cplxk_randn_philox_torch.argtypes = [_vp, _i64, _u64, _u64, _u32, ctypes.c_float, _vp]
+    lib.cplxk_transpose2d.argtypes = [_vp, _vp, _vp, _i64, _i64, _int, _int, _vp]
+    lib.cplxk_colsum.argtypes = [_vp, _vp, _i64, _i64, _int, _vp]
+    lib.cplxk_vd_grad_s2.argtypes = [_vp] * 5 + [_int, _u64, _u64, _u32, _vp, _i64, _i64, _int, _vp]
+    lib.cplxk_vd_grad_input.argtypes = [_vp] * 5 + [_i64, _int, _vp]
+    lib.cplxk_mul_exp.argtypes = [_vp, _vp, _vp, _i64, _int, _int, _vp]
+    lib.cplxk_kl_bwd.argtypes = [_int, _vp, _vp, _vp, _i64, _int, _vp, _int, _int, ctypes.c_double,
+                                 _vp, _vp, _vp, _vp]
     for name in EXPORTS:
         getattr(lib, name)  # fail at load time, not at first use, if a symbol is missing
 

@@ -57,7 +57,7 @@ static int forward_common(bool vd, const void* x_re, const void* x_im, const voi
                           const void* w_im, const void* b_re, const void* b_im, const void* ls2,
                           const void* eps_re, const void* eps_im, int noise, uint64_t seed,
                           uint64_t offset, uint32_t threads, void* y_re, void* y_im, int64_t M,
-                          int64_t N, int64_t K, int dtype, int math, void* workspace,
+                          int64_t N, int64_t K, int dtype, int math, void* s2_out, void* workspace,
                           size_t workspace_bytes, void* stream) {
   if (!x_re || !w_re || !y_re || M < 0 || N < 0 || K < 0) return CPLXK_ERR_BADARG;
   const bool cplx = (x_im != nullptr);
@@ -77,7 +77,7 @@ static int forward_common(bool vd, const void* x_re, const void* x_im, const voi
 
   EpiParams ep;
   ep.b_re = b_re, ep.b_im = b_im, ep.eps_re = eps_re, ep.eps_im = eps_im;
-  ep.y_re = y_re, ep.y_im = y_im;
+  ep.y_re = y_re, ep.y_im = y_im, ep.s2_out = vd ? s2_out : nullptr;
   ep.M = M, ep.N = N, ep.plane_elems = M * N;
   ep.noise = make_noise(vd ? noise : CPLXK_NOISE_INJECT, seed, offset, threads, cplx);
 
@@ -143,7 +143,7 @@ extern "C" int cplxk_linear_fwd(const void* x_re, const void* x_im, const void* 
                                 void* y_im, int64_t M, int64_t N, int64_t K, int dtype, int math,
                                 void* stream) {
   return forward_common(false, x_re, x_im, w_re, w_im, b_re, b_im, nullptr, nullptr, nullptr, 0, 0,
-                        0, 0, y_re, y_im, M, N, K, dtype, math, nullptr, 0, stream);
+                        0, 0, y_re, y_im, M, N, K, dtype, math, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int cplxk_linear_vd_fwd(const void* x_re, const void* x_im, const void* w_re,
@@ -151,11 +151,11 @@ extern "C" int cplxk_linear_vd_fwd(const void* x_re, const void* x_im, const voi
                                    const void* log_sigma2, const void* eps_re, const void* eps_im,
                                    int noise, uint64_t seed, uint64_t offset,
                                    uint32_t philox_threads, void* y_re, void* y_im, int64_t M,
-                                   int64_t N, int64_t K, int dtype, int math, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+                                   int64_t N, int64_t K, int dtype, int math, void* s2_out,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
   return forward_common(true, x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise,
-                        seed, offset, philox_threads, y_re, y_im, M, N, K, dtype, math, workspace,
-                        workspace_bytes, stream);
+                        seed, offset, philox_threads, y_re, y_im, M, N, K, dtype, math, s2_out,
+                        workspace, workspace_bytes, stream);
 }
 
 extern "C" size_t cplxk_linear_vd_workspace_bytes(int64_t M, int64_t N, int64_t K, int dtype) {

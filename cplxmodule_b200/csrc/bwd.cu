@@ -1,0 +1,325 @@
+// Backward-pass support kernels.  The heavy lifting of every gradient is a GEMM that runs
+// through the SAME tcgen05 forward kernels (cplxk_linear_fwd):
+//   dx = g . conj(W)           ->  linear(g, (U^T, -V^T))          [M,K]
+//   dW = g^T . conj(x)         ->  linear((g_re^T, g_im^T), (x_re^T, -x_im^T))   [N,K]
+//   variational part:  g_s2 = (g_re eps_re + g_im eps_im) / (2 sqrt(s2)) [s2 > 1e-8]
+//                      dq = g_s2 . E,  dE = g_s2^T . q,  d log_sigma2 = dE * E,
+//                      dx += 2 x * dq
+// (derivatives of cplxmodule/nn/relevance/complex/base.py:43-56; the reference gets them
+// from torch autograd).  Both GEMM operands must be K-major for the TMA path, so the
+// kernels here produce the transposed / derived operand planes, plus the small elementwise
+// pieces and the closed-form KL gradients (complex/vd.py:38-41: dEi(x)/dx = e^x / x).
+#include "common.cuh"
+#include "noise.cuh"
+
+namespace cplxk {
+
+enum { TR_COPY = 0, TR_NEG = 1, TR_EXP = 2, TR_ABS2 = 3, TR_SQR = 4 };
+
+// out[c, r] = op(in[r, c])  (TR_ABS2: in^2 + in2^2), 32 x 32 smem tiles, coalesced both ways
+template <typename T, int kOp>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const T* __restrict__ in, const T* __restrict__ in2, T* __restrict__ out,
+                 int64_t rows, int64_t cols) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 32, r0 = static_cast<int64_t>(blockIdx.y) * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty + 8 * i, c = c0 + tx;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = Elem<T>::to_f(in[r * cols + c]);
+      if constexpr (kOp == TR_NEG) v = -v;
+      if constexpr (kOp == TR_EXP) v = __expf(v);
+      if constexpr (kOp == TR_SQR) v = v * v;
+      if constexpr (kOp == TR_ABS2) {
+        const float w = Elem<T>::to_f(in2[r * cols + c]);
+        v = fmaf(v, v, w * w);
+      }
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t c = c0 + ty + 8 * i, r = r0 + tx;
+    if (c < cols && r < rows) out[c * rows + r] = Elem<T>::from_f(tile[tx][ty + 8 * i]);
+  }
+}
+
+// out[n] = sum_m g[m, n]  (bias gradient); one block per 32 columns, deterministic order
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ g, T* __restrict__ out, int64_t M, int64_t N) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t n = static_cast<int64_t>(blockIdx.x) * 32 + tx;
+  float acc = 0.f;
+  if (n < N)
+    for (int64_t m = ty; m < M; m += 8) acc += Elem<T>::to_f(g[m * N + n]);
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += part[i][tx];
+    out[n] = Elem<T>::from_f(s);
+  }
+}
+
+// g_s2 = (g_re eps_re + g_im eps_im) * 0.5 / sqrt(s2) where s2 > 1e-8, else 0
+template <typename T, bool kCplx>
+__global__ void __launch_bounds__(256)
+vd_grad_s2_kernel(const T* __restrict__ g_re, const T* __restrict__ g_im, const T* __restrict__ s2,
+                  const T* __restrict__ eps_re, const T* __restrict__ eps_im, T* __restrict__ out,
+                  int64_t M, int64_t N, NoiseParams np) {
+  // one thread = 8 consecutive columns of one row (noise quads / cursor stay cheap)
+  const int64_t runs_per_row = (N + 7) / 8;
+  const int64_t total = M * runs_per_row;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t m = t / runs_per_row;
+    const int64_t n0 = (t - m * runs_per_row) * 8;
+    const int64_t off = m * N + n0;
+    const int nv = (N - n0) < 8 ? static_cast<int>(N - n0) : 8;
+    float er[8], ei[8];
+    if (np.mode == CPLXK_NOISE_INJECT) {
+      for (int j = 0; j < nv; ++j) {
+        er[j] = Elem<T>::to_f(eps_re[off + j]);
+        ei[j] = kCplx ? Elem<T>::to_f(eps_im[off + j]) : 0.f;
+      }
+    } else if (np.mode == CPLXK_NOISE_PHILOX_TORCH) {
+      TorchNoiseCursor cur;
+      cur.seek(static_cast<uint64_t>(off), np.threads);
+      for (int j = 0; j < nv; ++j) er[j] = cur.next(np) * np.scale;
+      if constexpr (kCplx) {
+        cur.seek(static_cast<uint64_t>(M * N + off), np.threads);
+        for (int j = 0; j < nv; ++j) ei[j] = cur.next(np) * np.scale;
+      }
+    } else {
+      const uint64_t q0 = static_cast<uint64_t>(m) * static_cast<uint64_t>((N + 3) >> 2) +
+                          static_cast<uint64_t>(n0 >> 2);
+      for (int q = 0; q < 2; ++q) {
+        float4 a = philox_fast_normal4(q0 + q, 0u, np);
+        er[4 * q] = a.x * np.scale, er[4 * q + 1] = a.y * np.scale;
+        er[4 * q + 2] = a.z * np.scale, er[4 * q + 3] = a.w * np.scale;
+        if constexpr (kCplx) {
+          float4 b = philox_fast_normal4(q0 + q, 1u, np);
+          ei[4 * q] = b.x * np.scale, ei[4 * q + 1] = b.y * np.scale;
+          ei[4 * q + 2] = b.z * np.scale, ei[4 * q + 3] = b.w * np.scale;
+        }
+      }
+    }
+    for (int j = 0; j < nv; ++j) {
+      const float v = Elem<T>::to_f(s2[off + j]);
+      float acc = Elem<T>::to_f(g_re[off + j]) * er[j];
+      if constexpr (kCplx) acc = fmaf(Elem<T>::to_f(g_im[off + j]), ei[j], acc);
+      out[off + j] = Elem<T>::from_f(v > 1e-8f ? acc * 0.5f * rsqrtf(v) : 0.f);
+    }
+  }
+}
+
+// dx_re += 2 x_re dq ; dx_im += 2 x_im dq
+template <typename T, bool kCplx>
+__global__ void __launch_bounds__(256)
+vd_grad_input_kernel(T* __restrict__ dx_re, T* __restrict__ dx_im, const T* __restrict__ x_re,
+                     const T* __restrict__ x_im, const T* __restrict__ dq, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float d = 2.f * Elem<T>::to_f(dq[i]);
+    dx_re[i] = Elem<T>::from_f(fmaf(Elem<T>::to_f(x_re[i]), d, Elem<T>::to_f(dx_re[i])));
+    if constexpr (kCplx)
+      dx_im[i] = Elem<T>::from_f(fmaf(Elem<T>::to_f(x_im[i]), d, Elem<T>::to_f(dx_im[i])));
+  }
+}
+
+// out = a * exp(b) (+ out if accumulate)
+template <typename T>
+__global__ void __launch_bounds__(256)
+mul_exp_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n,
+               int accumulate) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float v = Elem<T>::to_f(a[i]) * __expf(Elem<T>::to_f(b[i]));
+    if (accumulate) v += Elem<T>::to_f(out[i]);
+    out[i] = Elem<T>::from_f(v);
+  }
+}
+
+// d penalty / d (w_re, w_im, log_sigma2), times the upstream gradient (scalar or per element)
+template <typename T, int kKind>
+__global__ void __launch_bounds__(256)
+kl_bwd_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T* __restrict__ ls2,
+              int64_t n, const void* __restrict__ grad, int grad_is_tensor, int grad_is_f32,
+              float scale, T* __restrict__ d_w_re, T* __restrict__ d_w_im, T* __restrict__ d_ls2) {
+  constexpr bool kCplx = (kKind == CPLXK_KL_CPLX_VD || kKind == CPLXK_KL_CPLX_ARD);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float wr = Elem<T>::to_f(w_re[i]);
+    const float wi = kCplx ? Elem<T>::to_f(w_im[i]) : 0.f;
+    const float r2 = fmaf(wr, wr, wi * wi) + 1e-24f;
+    const float nla = __logf(r2) - Elem<T>::to_f(ls2[i]);  // -log_alpha
+    float dn;                                             // d penalty / d (-log_alpha)
+    if constexpr (kKind == CPLXK_KL_REAL_VD) {
+      const float s = __fdividef(1.f, 1.f + __expf(-fmaf(1.48695f, nla, -1.87320f)));
+      dn = 0.5f * __fdividef(1.f, 1.f + __expf(-nla)) + 0.63576f * 1.48695f * s * (1.f - s);
+    } else if constexpr (kKind == CPLXK_KL_REAL_ARD) {
+      dn = 0.5f * __fdividef(1.f, 1.f + __expf(-nla));
+    } else if constexpr (kKind == CPLXK_KL_CPLX_VD) {
+      dn = -expm1f(-__expf(nla));                          // 1 - exp(-1/alpha)
+    } else {
+      dn = __fdividef(1.f, 1.f + __expf(-nla));
+    }
+    float g;
+    if (grad_is_tensor)
+      g = grad_is_f32 ? static_cast<const float*>(grad)[i] : Elem<T>::to_f(static_cast<const T*>(grad)[i]);
+    else
+      g = grad_is_f32 ? static_cast<const float*>(grad)[0] : Elem<T>::to_f(static_cast<const T*>(grad)[0]);
+    g *= scale * dn;
+    // -log_alpha = log(r2) - ls2  =>  d/dw = 2 w / r2 ,  d/dls2 = -1
+    const float k = 2.f * __fdividef(g, r2);
+    d_w_re[i] = Elem<T>::from_f(k * wr);
+    if constexpr (kCplx) d_w_im[i] = Elem<T>::from_f(k * wi);
+    d_ls2[i] = Elem<T>::from_f(-g);
+  }
+}
+
+static inline int ew_grid(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  return static_cast<int>(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
+}
+
+}  // namespace cplxk
+
+using namespace cplxk;
+
+#define CPLXK_BY_DTYPE(dtype, ...)                                    \
+  if ((dtype) == CPLXK_F32) { using T = float; __VA_ARGS__; }         \
+  else if ((dtype) == CPLXK_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+  else return CPLXK_ERR_BADARG;
+
+extern "C" int cplxk_transpose2d(const void* in, const void* in2, void* out, int64_t rows,
+                                 int64_t cols, int dtype, int op, void* stream) {
+  if (!in || !out || rows < 0 || cols < 0 || op < TR_COPY || op > TR_SQR) return CPLXK_ERR_BADARG;
+  if (op == TR_ABS2 && !in2) return CPLXK_ERR_BADARG;
+  if (rows == 0 || cols == 0) return CPLXK_OK;
+  dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32));
+  if (grid.y > 65535u) return CPLXK_ERR_UNSUPPORTED;
+  auto st = static_cast<cudaStream_t>(stream);
+  CPLXK_BY_DTYPE(dtype, {
+    auto a = static_cast<const T*>(in);
+    auto b = static_cast<const T*>(in2);
+    auto o = static_cast<T*>(out);
+    switch (op) {
+      case TR_COPY: transpose_kernel<T, TR_COPY><<<grid, 256, 0, st>>>(a, b, o, rows, cols); break;
+      case TR_NEG: transpose_kernel<T, TR_NEG><<<grid, 256, 0, st>>>(a, b, o, rows, cols); break;
+      case TR_EXP: transpose_kernel<T, TR_EXP><<<grid, 256, 0, st>>>(a, b, o, rows, cols); break;
+      case TR_SQR: transpose_kernel<T, TR_SQR><<<grid, 256, 0, st>>>(a, b, o, rows, cols); break;
+      default: transpose_kernel<T, TR_ABS2><<<grid, 256, 0, st>>>(a, b, o, rows, cols); break;
+    }
+  })
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
+}
+
+extern "C" int cplxk_colsum(const void* g, void* out, int64_t M, int64_t N, int dtype, void* stream) {
+  if (!g || !out || M < 0 || N < 0) return CPLXK_ERR_BADARG;
+  if (N == 0) return CPLXK_OK;
+  auto st = static_cast<cudaStream_t>(stream);
+  CPLXK_BY_DTYPE(dtype, {
+    colsum_kernel<T><<<static_cast<unsigned>((N + 31) / 32), 256, 0, st>>>(
+        static_cast<const T*>(g), static_cast<T*>(out), M, N);
+  })
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
+}
+
+extern "C" int cplxk_vd_grad_s2(const void* g_re, const void* g_im, const void* s2,
+                                const void* eps_re, const void* eps_im, int noise, uint64_t seed,
+                                uint64_t offset, uint32_t philox_threads, void* out, int64_t M,
+                                int64_t N, int dtype, void* stream) {
+  if (!g_re || !s2 || !out || M < 0 || N < 0) return CPLXK_ERR_BADARG;
+  if (noise < CPLXK_NOISE_INJECT || noise > CPLXK_NOISE_PHILOX_FAST) return CPLXK_ERR_BADARG;
+  const bool cplx = g_im != nullptr;
+  if (noise == CPLXK_NOISE_INJECT && (!eps_re || (cplx && !eps_im))) return CPLXK_ERR_BADARG;
+  if (noise == CPLXK_NOISE_PHILOX_TORCH && (philox_threads == 0 || (offset & 3u))) return CPLXK_ERR_BADARG;
+  if (M == 0 || N == 0) return CPLXK_OK;
+  NoiseParams np;
+  np.mode = noise, np.seed_lo = static_cast<uint32_t>(seed), np.seed_hi = static_cast<uint32_t>(seed >> 32);
+  np.ctr_base = offset >> 2, np.threads = philox_threads ? philox_threads : 1u;
+  np.scale = cplx ? (1.0f / static_cast<float>(1.4142135623730951)) : 1.0f;
+  auto st = static_cast<cudaStream_t>(stream);
+  const int grid = ew_grid(M * ((N + 7) / 8));
+  CPLXK_BY_DTYPE(dtype, {
+    auto a = static_cast<const T*>(g_re); auto b = static_cast<const T*>(g_im);
+    auto c = static_cast<const T*>(s2); auto e1 = static_cast<const T*>(eps_re);
+    auto e2 = static_cast<const T*>(eps_im); auto o = static_cast<T*>(out);
+    if (cplx) vd_grad_s2_kernel<T, true><<<grid, 256, 0, st>>>(a, b, c, e1, e2, o, M, N, np);
+    else vd_grad_s2_kernel<T, false><<<grid, 256, 0, st>>>(a, b, c, e1, e2, o, M, N, np);
+  })
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
+}
+
+extern "C" int cplxk_vd_grad_input(void* dx_re, void* dx_im, const void* x_re, const void* x_im,
+                                   const void* dq, int64_t n, int dtype, void* stream) {
+  if (!dx_re || !x_re || !dq || n < 0) return CPLXK_ERR_BADARG;
+  if ((dx_im != nullptr) != (x_im != nullptr)) return CPLXK_ERR_BADARG;
+  if (n == 0) return CPLXK_OK;
+  auto st = static_cast<cudaStream_t>(stream);
+  CPLXK_BY_DTYPE(dtype, {
+    if (dx_im)
+      vd_grad_input_kernel<T, true><<<ew_grid(n), 256, 0, st>>>(
+          static_cast<T*>(dx_re), static_cast<T*>(dx_im), static_cast<const T*>(x_re),
+          static_cast<const T*>(x_im), static_cast<const T*>(dq), n);
+    else
+      vd_grad_input_kernel<T, false><<<ew_grid(n), 256, 0, st>>>(
+          static_cast<T*>(dx_re), nullptr, static_cast<const T*>(x_re), nullptr,
+          static_cast<const T*>(dq), n);
+  })
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
+}
+
+extern "C" int cplxk_mul_exp(const void* a, const void* b, void* out, int64_t n, int dtype,
+                             int accumulate, void* stream) {
+  if (!a || !b || !out || n < 0) return CPLXK_ERR_BADARG;
+  if (n == 0) return CPLXK_OK;
+  auto st = static_cast<cudaStream_t>(stream);
+  CPLXK_BY_DTYPE(dtype, {
+    mul_exp_kernel<T><<<ew_grid(n), 256, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(b),
+                                                  static_cast<T*>(out), n, accumulate);
+  })
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
+}
+
+extern "C" int cplxk_kl_bwd(int kind, const void* w_re, const void* w_im, const void* log_sigma2,
+                            int64_t n, int dtype, const void* grad, int grad_is_tensor,
+                            int grad_is_f32, double scale, void* d_w_re, void* d_w_im,
+                            void* d_log_sigma2, void* stream) {
+  if (kind < 0 || kind > 3 || n < 0) return CPLXK_ERR_BADARG;
+  if (n == 0) return CPLXK_OK;
+  const bool cplx = (kind == CPLXK_KL_CPLX_VD || kind == CPLXK_KL_CPLX_ARD);
+  if (!w_re || !log_sigma2 || !grad || !d_w_re || !d_log_sigma2) return CPLXK_ERR_BADARG;
+  if (cplx != (w_im != nullptr) || cplx != (d_w_im != nullptr)) return CPLXK_ERR_BADARG;
+  auto st = static_cast<cudaStream_t>(stream);
+  const float sc = static_cast<float>(scale);
+#define CPLXK_KLB(K)                                                                              \
+  kl_bwd_kernel<T, K><<<ew_grid(n), 256, 0, st>>>(                                                \
+      static_cast<const T*>(w_re), static_cast<const T*>(w_im), static_cast<const T*>(log_sigma2), \
+      n, grad, grad_is_tensor, grad_is_f32, sc, static_cast<T*>(d_w_re), static_cast<T*>(d_w_im), \
+      static_cast<T*>(d_log_sigma2))
+  CPLXK_BY_DTYPE(dtype, {
+    switch (kind) {
+      case CPLXK_KL_REAL_VD: CPLXK_KLB(CPLXK_KL_REAL_VD); break;
+      case CPLXK_KL_REAL_ARD: CPLXK_KLB(CPLXK_KL_REAL_ARD); break;
+      case CPLXK_KL_CPLX_VD: CPLXK_KLB(CPLXK_KL_CPLX_VD); break;
+      default: CPLXK_KLB(CPLXK_KL_CPLX_ARD); break;
+    }
+  })
+#undef CPLXK_KLB
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
+}

@@ -16,10 +16,32 @@ struct EpiParams {
   const void* eps_im;
   void* y_re;
   void* y_im;
+  void* s2_out;        // nullable: the variance accumulator, saved for the backward pass
   int64_t M, N;        // logical output matrix [M, N] (rows = samples / output pixels)
   int64_t plane_elems; // elements of one noise plane in torch's randn call (= M*N)
   NoiseParams noise;
 };
+
+template <typename T, int C>
+__device__ __forceinline__ void store_s2_run(const EpiParams& p, int64_t row_off, int64_t n0,
+                                             int nvalid, const float (&s2)[C]) {
+  if (!p.s2_out) return;
+  T* dst = static_cast<T*>(p.s2_out) + row_off + n0;
+  constexpr int V = Elem<T>::kVec;
+  if (nvalid == C && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && C % V == 0) {
+#pragma unroll
+    for (int c = 0; c < C / V; ++c) {
+      Vec16<T> o;
+#pragma unroll
+      for (int j = 0; j < V; ++j) o.v[j] = s2[c * V + j];
+      o.store(dst + c * V);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < C; ++j)
+      if (j < nvalid) dst[j] = Elem<T>::from_f(s2[j]);
+  }
+}
 
 // `row_off` = linear offset of (m, 0) inside a plane; consecutive n are contiguous.
 template <typename T, bool kCplx, bool kVD, int C>
@@ -42,6 +64,7 @@ __device__ __forceinline__ void epilogue_run(const EpiParams& p, int64_t m, int6
   }
 
   if constexpr (kVD) {
+    store_s2_run<T, C>(p, row_off, n0, nvalid, s2);
     float sd[C];
 #pragma unroll
     for (int j = 0; j < C; ++j) sd[j] = sqrtf(fmaxf(s2[j], 1e-8f));
@@ -248,6 +271,7 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams& p, int64_t m, i
         if constexpr (kCplx) im[j] += Elem<T>::to_f(__ldg(bi + n0 + j));
       }
   }
+  store_s2_run<T, C>(p, row_off, n0, nvalid, s2);
 #pragma unroll
   for (int j = 0; j < C; ++j) {
     const float sd = sqrtf(fmaxf(s2[j], 1e-8f));

@@ -49,18 +49,14 @@ def get_math_mode():
     return _state["math"]
 
 
-_BACKWARD_MSG = (
-    "cplxmodule_b200: backward of the fused {} kernel is not implemented yet "
-    "(forward + KL are the accelerated path; there is deliberately no silent torch fallback)."
-)
-
-
 def _flat2d(t, K):
     return None if t is None else nv.plane(t.reshape(-1, K))
 
 
-def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise):
-    """Shared launcher. Returns (y_re, y_im|None). ``noise`` is None for the plain map."""
+def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise,
+                 want_s2=False, math=None):
+    """Shared launcher. Returns (y_re, y_im|None, aux). ``noise`` is None for the plain map;
+    ``aux`` = dict(s2=..., philox=(seed, offset, threads)) for the variational forward."""
     dev = nv.require_cuda(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im)
     cplx = x_im is not None
     dt = w_re.dtype
@@ -77,8 +73,9 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
     br, bi = nv.plane(b_re, dt), nv.plane(b_im, dt)
     y_re = torch.empty((M, N), dtype=dt, device=dev)
     y_im = torch.empty((M, N), dtype=dt, device=dev) if cplx else None
+    aux = {}
     lib = nv.lib()
-    math = _MATH[_state["math"]]
+    math = _MATH[_state["math"]] if math is None else math
     with torch.cuda.device(dev):
         st = nv.stream_ptr(dev)
         if log_sigma2 is None:
@@ -98,57 +95,225 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
             if _state["prepare"] and math != nv.MATH_SIMT:
                 ws_bytes = lib.cplxk_linear_vd_workspace_bytes(M, N, K, code)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            s2 = torch.empty((M, N), dtype=dt, device=dev) if want_s2 else None
             nv.check(lib.cplxk_linear_vd_fwd(nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi),
                                              nv.ptr(br), nv.ptr(bi), nv.ptr(ls2), nv.ptr(er),
                                              nv.ptr(ei), noise, seed, offset, threads,
                                              nv.ptr(y_re), nv.ptr(y_im), M, N, K, code, math,
-                                             nv.ptr(ws), ws_bytes, st))
+                                             nv.ptr(s2), nv.ptr(ws), ws_bytes, st))
             if noise != nv.NOISE_INJECT:
                 gen.set_offset(offset + inc)
+            aux = {"s2": s2, "philox": (seed, offset, threads), "eps": (er, ei), "x": (xr, xi)}
     y_re = y_re.reshape(*lead, N)
     if cplx:
         y_im = y_im.reshape(*lead, N)
-    return y_re, y_im
+    return y_re, y_im, aux
+
+
+# ------------------------------------------------------------------ backward helpers
+TR_COPY, TR_NEG, TR_EXP, TR_ABS2, TR_SQR = 0, 1, 2, 3, 4
+
+
+def _transpose(t, op=TR_COPY, t2=None):
+    """out[cols, rows] = op(t[rows, cols]) through the C ABI (makes a K-major GEMM operand)."""
+    rows, cols = t.shape
+    out = torch.empty((cols, rows), dtype=t.dtype, device=t.device)
+    with torch.cuda.device(t.device):
+        nv.check(nv.lib().cplxk_transpose2d(nv.ptr(t), nv.ptr(t2), nv.ptr(out), rows, cols,
+                                            nv.dtype_code(t.dtype), op, nv.stream_ptr(t.device)))
+    return out
+
+
+def _colsum(g):
+    M, N = g.shape
+    out = torch.empty(N, dtype=g.dtype, device=g.device)
+    with torch.cuda.device(g.device):
+        nv.check(nv.lib().cplxk_colsum(nv.ptr(g), nv.ptr(out), M, N, nv.dtype_code(g.dtype),
+                                       nv.stream_ptr(g.device)))
+    return out
+
+
+def _gemm(a_re, a_im, p_re, p_im):
+    """(a_re + i a_im) . (p_re + i p_im)^T  (or the real product) on the tensor cores; gradient
+    GEMMs contract over whatever the batch size is, so shapes the TMA path cannot take fall
+    through to the exact-fp32 kernel even when the user forced ``"tensor"`` for the forward."""
+    math = nv.MATH_SIMT if _state["math"] == "simt" else nv.MATH_AUTO
+    re, im, _ = _forward_raw(a_re, a_im, p_re, p_im, None, None, None, None, None, None, math=math)
+    return re, im
+
+
+def _grad2d(g, like_lead, N, dt, dev):
+    if g is None:
+        M = 1
+        for s_ in like_lead:
+            M *= s_
+        return torch.zeros((M, N), dtype=dt, device=dev)
+    return nv.plane(g.reshape(-1, N).to(dt))
+
+
+def _linear_backward(ctx, g_re, g_im, need_x, need_w, need_b):
+    """Gradients of y = x W^T + b for split-complex (or real) planes."""
+    xr, xi, wr, wi = ctx.saved_planes
+    cplx = xi is not None
+    dx_re = dx_im = dw_re = dw_im = db_re = db_im = None
+    if need_x:
+        if cplx:  # dx = g . conj(W): P = (U^T, -V^T)
+            dx_re, dx_im = _gemm(g_re, g_im, _transpose(wr), _transpose(wi, TR_NEG))
+        else:
+            dx_re, _ = _gemm(g_re, None, _transpose(wr), None)
+    if need_w:
+        if cplx:  # dW = g^T . conj(x)
+            dw_re, dw_im = _gemm(_transpose(g_re), _transpose(g_im), _transpose(xr),
+                                 _transpose(xi, TR_NEG))
+        else:
+            dw_re, _ = _gemm(_transpose(g_re), None, _transpose(xr), None)
+    if need_b:
+        db_re = _colsum(g_re)
+        db_im = _colsum(g_im) if cplx else None
+    return dx_re, dx_im, dw_re, dw_im, db_re, db_im
+
+
+def _vd_backward_extra(ctx, g_re, g_im, dx_re, dx_im, need_x, need_ls2):
+    """Variational part: through s2 = |x|^2 . exp(log_sigma2)^T and y = mu + eps sqrt(max(s2, 1e-8))."""
+    xr, xi, wr, wi = ctx.saved_planes
+    cplx = xi is not None
+    s2, ls2 = ctx.s2, ctx.ls2
+    M, N = s2.shape
+    dev, dt = s2.device, s2.dtype
+    gs2 = torch.empty_like(s2)
+    seed, offset, threads = ctx.philox
+    er, ei = ctx.eps
+    with torch.cuda.device(dev):
+        nv.check(nv.lib().cplxk_vd_grad_s2(nv.ptr(g_re), nv.ptr(g_im), nv.ptr(s2), nv.ptr(er),
+                                           nv.ptr(ei), ctx.noise, seed, offset, threads,
+                                           nv.ptr(gs2), M, N, nv.dtype_code(dt), nv.stream_ptr(dev)))
+    dls2 = None
+    if need_x:   # dq = g_s2 . E ; dx += 2 x dq
+        dq, _ = _gemm(gs2, None, _transpose(ls2, TR_EXP), None)
+        with torch.cuda.device(dev):
+            nv.check(nv.lib().cplxk_vd_grad_input(nv.ptr(dx_re), nv.ptr(dx_im), nv.ptr(xr),
+                                                  nv.ptr(xi), nv.ptr(dq), dq.numel(),
+                                                  nv.dtype_code(dt), nv.stream_ptr(dev)))
+    if need_ls2:  # dE = g_s2^T . |x|^2 ; d log_sigma2 = dE * E
+        qT = _transpose(xr, TR_ABS2, xi) if cplx else _transpose(xr, TR_SQR)
+        dE, _ = _gemm(_transpose(gs2), None, qT, None)
+        dls2 = torch.empty_like(dE)
+        with torch.cuda.device(dev):
+            nv.check(nv.lib().cplxk_mul_exp(nv.ptr(dE), nv.ptr(ls2), nv.ptr(dls2), dE.numel(),
+                                            nv.dtype_code(dt), 0, nv.stream_ptr(dev)))
+    return dls2
+
+
+def _save_linear(ctx, x_re, x_im, w_re, w_im):
+    dt = w_re.dtype
+    K = w_re.shape[1]
+    ctx.saved_planes = (_flat2d(x_re.to(dt), K), None if x_im is None else _flat2d(x_im.to(dt), K),
+                        nv.plane(w_re), nv.plane(w_im))
+    ctx.lead = tuple(x_re.shape[:-1])
+    ctx.x_dtype = x_re.dtype
+
+
+def _shape_back(t, lead, last, dtype=None):
+    if t is None:
+        return None
+    t = t.reshape(*lead, last)
+    return t if dtype is None or t.dtype == dtype else t.to(dtype)
 
 
 class _CplxLinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_re, x_im, w_re, w_im, b_re, b_im):
-        return _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, None, None, None, None)
+        if any(ctx.needs_input_grad):
+            _save_linear(ctx, x_re, x_im, w_re, w_im)
+        re, im, _ = _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, None, None, None, None)
+        return re, im
 
     @staticmethod
-    def backward(ctx, *grads):
-        raise NotImplementedError(_BACKWARD_MSG.format("complex linear"))
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_re, g_im):
+        xr, xi, wr, wi = ctx.saved_planes
+        N, K = wr.shape
+        g_re, g_im = (_grad2d(g, ctx.lead, N, wr.dtype, wr.device) for g in (g_re, g_im))
+        n = ctx.needs_input_grad
+        dx_re, dx_im, dw_re, dw_im, db_re, db_im = _linear_backward(
+            ctx, g_re, g_im, n[0] or n[1], n[2] or n[3], n[4] or n[5])
+        return (_shape_back(dx_re, ctx.lead, K, ctx.x_dtype), _shape_back(dx_im, ctx.lead, K, ctx.x_dtype),
+                dw_re, dw_im, db_re, db_im)
 
 
 class _RealLinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b):
+        if any(ctx.needs_input_grad):
+            _save_linear(ctx, x, None, w, None)
         return _forward_raw(x, None, w, None, b, None, None, None, None, None)[0]
 
     @staticmethod
-    def backward(ctx, *grads):
-        raise NotImplementedError(_BACKWARD_MSG.format("linear"))
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        xr, _, wr, _ = ctx.saved_planes
+        N, K = wr.shape
+        g = _grad2d(g, ctx.lead, N, wr.dtype, wr.device)
+        n = ctx.needs_input_grad
+        dx, _, dw, _, db, _ = _linear_backward(ctx, g, None, n[0], n[1], n[2])
+        return _shape_back(dx, ctx.lead, K, ctx.x_dtype), dw, db
+
+
+def _save_vd(ctx, aux, log_sigma2, noise):
+    ctx.s2, ctx.philox, ctx.eps = aux["s2"], aux["philox"], aux["eps"]
+    ctx.ls2 = nv.plane(log_sigma2, aux["s2"].dtype)
+    ctx.noise = noise
 
 
 class _CplxLinearVDFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise):
-        return _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise)
+        need = any(ctx.needs_input_grad)
+        if need:
+            _save_linear(ctx, x_re, x_im, w_re, w_im)
+        re, im, aux = _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
+                                   noise, want_s2=need)
+        if need:
+            _save_vd(ctx, aux, log_sigma2, noise)
+        return re, im
 
     @staticmethod
-    def backward(ctx, *grads):
-        raise NotImplementedError(_BACKWARD_MSG.format("complex variational linear"))
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_re, g_im):
+        xr, xi, wr, wi = ctx.saved_planes
+        N, K = wr.shape
+        g_re, g_im = (_grad2d(g, ctx.lead, N, wr.dtype, wr.device) for g in (g_re, g_im))
+        n = ctx.needs_input_grad
+        need_x = n[0] or n[1]
+        dx_re, dx_im, dw_re, dw_im, db_re, db_im = _linear_backward(
+            ctx, g_re, g_im, need_x, n[2] or n[3], n[4] or n[5])
+        dls2 = _vd_backward_extra(ctx, g_re, g_im, dx_re, dx_im, need_x, n[6])
+        return (_shape_back(dx_re, ctx.lead, K, ctx.x_dtype), _shape_back(dx_im, ctx.lead, K, ctx.x_dtype),
+                dw_re, dw_im, db_re, db_im, dls2, None, None, None)
 
 
 class _RealLinearVDFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, log_sigma2, eps, noise):
-        return _forward_raw(x, None, w, None, b, None, log_sigma2, eps, None, noise)[0]
+        need = any(ctx.needs_input_grad)
+        if need:
+            _save_linear(ctx, x, None, w, None)
+        y, _, aux = _forward_raw(x, None, w, None, b, None, log_sigma2, eps, None, noise,
+                                 want_s2=need)
+        if need:
+            _save_vd(ctx, aux, log_sigma2, noise)
+        return y
 
     @staticmethod
-    def backward(ctx, *grads):
-        raise NotImplementedError(_BACKWARD_MSG.format("variational linear"))
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        xr, _, wr, _ = ctx.saved_planes
+        N, K = wr.shape
+        g = _grad2d(g, ctx.lead, N, wr.dtype, wr.device)
+        n = ctx.needs_input_grad
+        dx, _, dw, _, db, _ = _linear_backward(ctx, g, None, n[0], n[1], n[2])
+        dls2 = _vd_backward_extra(ctx, g, None, dx, None, n[0], n[3])
+        return _shape_back(dx, ctx.lead, K, ctx.x_dtype), dw, db, dls2, None, None
 
 
 def cplx_linear(x_re, x_im, w_re, w_im, b_re=None, b_im=None):
@@ -211,11 +376,33 @@ def kl_penalty(kind, w_re, w_im, log_sigma2, reduction="sum"):
 class _KLFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, kind, reduction, w_re, w_im, log_sigma2):
+        if any(ctx.needs_input_grad):
+            dt = w_re.dtype
+            ctx.kind, ctx.reduction = kind, reduction
+            ctx.planes = (nv.plane(w_re), nv.plane(w_im), nv.plane(log_sigma2, dt))
+            ctx.shape = tuple(w_re.shape)
         return kl_penalty(kind, w_re, w_im, log_sigma2, reduction)
 
     @staticmethod
-    def backward(ctx, *grads):
-        raise NotImplementedError(_BACKWARD_MSG.format("KL"))
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        wr, wi, ls2 = ctx.planes
+        dev, dt = wr.device, wr.dtype
+        n = wr.numel()
+        grad = grad.contiguous()
+        if grad.dtype not in (torch.float32, dt):
+            grad = grad.float()
+        per_elem = ctx.reduction is None
+        scale = 1.0 / max(n, 1) if ctx.reduction == "mean" else 1.0
+        d_wr, d_ls2 = torch.empty_like(wr), torch.empty_like(ls2)
+        d_wi = torch.empty_like(wi) if wi is not None else None
+        with torch.cuda.device(dev):
+            nv.check(nv.lib().cplxk_kl_bwd(ctx.kind, nv.ptr(wr), nv.ptr(wi), nv.ptr(ls2), n,
+                                           nv.dtype_code(dt), nv.ptr(grad), 1 if per_elem else 0,
+                                           1 if grad.dtype == torch.float32 else 0, scale,
+                                           nv.ptr(d_wr), nv.ptr(d_wi), nv.ptr(d_ls2),
+                                           nv.stream_ptr(dev)))
+        return None, None, d_wr, d_wi, d_ls2
 
 
 def kl(kind, w_re, w_im, log_sigma2, reduction="sum"):

@@ -126,7 +126,7 @@ int cplxk_linear_vd_fwd(const void* x_re, const void* x_im,
                         uint32_t philox_threads,
                         void* y_re, void* y_im,
                         int64_t M, int64_t N, int64_t K,
-                        int dtype, int math,
+                        int dtype, int math, void* s2_out /* nullable [M,N]: saved variance */,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /*
@@ -185,6 +185,36 @@ int cplxk_conv2d_fwd(const void* x_re, const void* x_im,
                      int64_t dil_h, int64_t dil_w,
                      int dtype, int math,
                      void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * ---- backward pass ---------------------------------------------------------------------
+ * Every gradient GEMM runs through cplxk_linear_fwd on transposed / conjugated operands
+ * (dx = g . conj(W), dW = g^T . conj(x), dq = g_s2 . E, dE = g_s2^T . q); the entry points
+ * below produce those operands and the elementwise pieces.  The reference obtains all of
+ * this from torch autograd over cplx.py:634-648 and nn/relevance/complex/base.py:43-56; its
+ * one hand-written derivative is ExpiFunction.backward (complex/vd.py:38-41).
+ */
+/* out[cols, rows] = op(in[rows, cols]); op: 0 copy, 1 negate, 2 exp, 3 in^2 + in2^2, 4 in^2 */
+int cplxk_transpose2d(const void* in, const void* in2, void* out, int64_t rows, int64_t cols,
+                      int dtype, int op, void* stream);
+/* out[N] = sum over rows of g[M, N]  (bias gradient) */
+int cplxk_colsum(const void* g, void* out, int64_t M, int64_t N, int dtype, void* stream);
+/* g_s2 = (g_re eps_re + g_im eps_im) / (2 sqrt(s2)) where s2 > 1e-8 (eps as in the forward) */
+int cplxk_vd_grad_s2(const void* g_re, const void* g_im, const void* s2, const void* eps_re,
+                     const void* eps_im, int noise, uint64_t seed, uint64_t offset,
+                     uint32_t philox_threads, void* out, int64_t M, int64_t N, int dtype,
+                     void* stream);
+/* dx_re += 2 x_re dq, dx_im += 2 x_im dq  (in place) */
+int cplxk_vd_grad_input(void* dx_re, void* dx_im, const void* x_re, const void* x_im,
+                        const void* dq, int64_t n, int dtype, void* stream);
+/* out (+)= a * exp(b) */
+int cplxk_mul_exp(const void* a, const void* b, void* out, int64_t n, int dtype, int accumulate,
+                  void* stream);
+/* gradient of scale * sum(grad * penalty) w.r.t. (w_re, w_im, log_sigma2); `grad` is a device
+ * scalar (grad_is_tensor == 0) or an [n] plane, fp32 (grad_is_f32) or of `dtype` */
+int cplxk_kl_bwd(int kind, const void* w_re, const void* w_im, const void* log_sigma2, int64_t n,
+                 int dtype, const void* grad, int grad_is_tensor, int grad_is_f32, double scale,
+                 void* d_w_re, void* d_w_im, void* d_log_sigma2, void* stream);
 
 /*
  * Test hook: fill out[n] (float) with scale * N(0,1) using the very device
