@@ -17,6 +17,7 @@
 // map's element stride, dilation an offset of the box origin.  The channels-last copies (and
 // |x|^2, exp(log_sigma2), and the tap-major weight planes) are written once per call by
 // elementwise pre-pass kernels into a caller-provided workspace.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -346,6 +347,186 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
   }
 }
 
+// ---------------------------------------------------------------- persistent variant
+// Plain (non-variational) convolution: one CTA per SM walks its share of the tiles.  The TMA
+// producer and the MMA issuer run ahead across tile boundaries (the smem ring never drains)
+// and the two 256-column halves of TMEM are used alternately, so the epilogue of tile i
+// (TMEM -> registers -> NCHW stores) overlaps the MMAs of tile i+1.
+template <typename T>
+struct ConvPCfg {
+  static constexpr bool kBF16 = std::is_same<T, __nv_bfloat16>::value;
+  static constexpr int BNO = 64;
+  static constexpr int BKC = 128 / static_cast<int>(sizeof(T));
+  static constexpr int A_TILE = 128 * 128;
+  static constexpr int OFF_XR = 0, OFF_XI = A_TILE, OFF_UV = 2 * A_TILE;
+  static constexpr int STAGE_BYTES = 3 * A_TILE;   // 48 KB
+  static constexpr int STAGES = 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 1024;
+};
+
+__device__ __forceinline__ void conv_tile_coords(const ConvTcGeom& g, int tile, int& b, int& oh0,
+                                                 int& ow0, int& n0) {
+  const int n_blk = tile % g.tiles_n;
+  tile /= g.tiles_n;
+  const int w_blk = tile % g.tiles_w;
+  tile /= g.tiles_w;
+  const int h_blk = tile % g.tiles_h;
+  b = tile / g.tiles_h;
+  ow0 = w_blk * g.Wt, oh0 = h_blk * g.Ht, n0 = n_blk * 64;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_xr,
+                          const __grid_constant__ CUtensorMap tm_xi,
+                          const __grid_constant__ CUtensorMap tm_u,
+                          const __grid_constant__ CUtensorMap tm_v, const ConvTcGeom g,
+                          const ConvTcEpi ep, const int total_tiles) {
+  using C = ConvPCfg<T>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t aux = base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bar_full = aux, bar_empty = aux + 8 * C::STAGES;
+  const uint32_t bar_tfull = aux + 16 * C::STAGES, bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_slot = bar_tempty + 16;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      smem + C::STAGES * C::STAGE_BYTES + 16 * C::STAGES + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cchunks = (g.Cp + C::BKC - 1) / C::BKC;
+  const int num_kb = g.kh * g.kw * cchunks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_xr);
+    ptx::prefetch_tensormap(&tm_xi);
+    ptx::prefetch_tensormap(&tm_u);
+    ptx::prefetch_tensormap(&tm_v);
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar_tfull + 8 * i, 1);
+      ptx::mbar_init(bar_tempty + 8 * i, 4);   // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t kbg = 0;  // k-blocks issued so far, across tiles
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int b, oh0, ow0, n0;
+        conv_tile_coords(g, tile, b, oh0, ow0, n0);
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const uint32_t s = kbg % C::STAGES, ph = (kbg / C::STAGES) & 1u;
+          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          const uint32_t fb = bar_full + 8 * s, st = base + s * C::STAGE_BYTES;
+          ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
+          const int rs = kb / cchunks, cc = kb - rs * cchunks;
+          const int r = rs / g.kw, sx = rs - r * g.kw;
+          const int32_t c0 = cc * C::BKC;
+          const int32_t iw = ow0 * g.sw - g.pw + sx * g.dw;
+          const int32_t ih = oh0 * g.sh - g.ph + r * g.dh;
+          ptx::tma_load_4d(st + C::OFF_XR, &tm_xr, fb, c0, iw, ih, b);
+          ptx::tma_load_4d(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
+          const int32_t wrow = rs * g.Op + n0;
+          ptx::tma_load_2d(st + C::OFF_UV, &tm_u, fb, c0, wrow);
+          ptx::tma_load_2d(st + C::OFF_UV + C::A_TILE / 2, &tm_v, fb, c0, wrow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc<C::kBF16>(128, 128, false, false);
+      uint32_t kbg = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1u, tph = (it >> 1) & 1u;
+        ptx::mbar_wait(bar_tempty + 8 * buf, tph ^ 1u);   // epilogue drained this half
+        ptx::tcgen05_fence_after();
+        const uint32_t t_d1 = tmem_base + buf * 256, t_d2 = t_d1 + 128;
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const uint32_t s = kbg % C::STAGES, ph = (kbg / C::STAGES) & 1u;
+          const uint32_t st = base + s * C::STAGE_BYTES;
+          ptx::mbar_wait(bar_full + 8 * s, ph);
+          ptx::tcgen05_fence_after();
+          const uint64_t a_r = ptx::make_kmajor_desc<128>(st + C::OFF_XR);
+          const uint64_t a_i = ptx::make_kmajor_desc<128>(st + C::OFF_XI);
+          const uint64_t b_uv = ptx::make_kmajor_desc<128>(st + C::OFF_UV);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            const uint32_t off = k * 32;
+            ptx::umma_ss<C::kBF16>(t_d1, ptx::desc_advance(a_r, off), ptx::desc_advance(b_uv, off), idesc, acc);
+            ptx::umma_ss<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc, acc);
+          }
+          ptx::umma_commit(bar_empty + 8 * s);
+        }
+        ptx::umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int p = quarter * 32 + lane;
+    const int hh = p / g.Wt, ww = p - hh * g.Wt;
+    const int64_t hw = g.Ho * g.Wo;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int b, oh0, ow0, n0;
+      conv_tile_coords(g, tile, b, oh0, ow0, n0);
+      const uint32_t buf = it & 1u, tph = (it >> 1) & 1u;
+      const int64_t oh = oh0 + hh, ow = ow0 + ww;
+      const bool pix_ok = oh < g.Ho && ow < g.Wo;
+      const int64_t pix_off = static_cast<int64_t>(b) * g.O * hw + oh * g.Wo + ow;
+      ptx::mbar_wait(bar_tfull + 8 * buf, tph);
+      ptx::tcgen05_fence_after();
+      const uint32_t lane_base = tmem_base + buf * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 2
+      for (int c = 0; c < 8; ++c) {
+        uint32_t d1a[8], d1b[8], d2a[8], d2b[8];
+        ptx::tmem_ld_32x32b_x8(lane_base + c * 8, d1a);
+        ptx::tmem_ld_32x32b_x8(lane_base + 64 + c * 8, d1b);
+        ptx::tmem_ld_32x32b_x8(lane_base + 128 + c * 8, d2a);
+        ptx::tmem_ld_32x32b_x8(lane_base + 192 + c * 8, d2b);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int o = n0 + c * 8 + j;
+          if (!pix_ok || o >= g.O) continue;
+          float re = __uint_as_float(d1a[j]) - __uint_as_float(d2b[j]);
+          float im = __uint_as_float(d1b[j]) + __uint_as_float(d2a[j]);
+          if (ep.b_re) {
+            re += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_re) + o));
+            im += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_im) + o));
+          }
+          const int64_t off = pix_off + static_cast<int64_t>(o) * hw;
+          static_cast<T*>(ep.y_re)[off] = Elem<T>::from_f(re);
+          static_cast<T*>(ep.y_im)[off] = Elem<T>::from_f(im);
+        }
+      }
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);   // this half may be overwritten
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // -------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiledC)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                      const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -487,6 +668,22 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
     if ((rc = make_w_map<T>(&tm_e, e, g))) return rc;
   }
   const int64_t tiles = g.B * g.tiles_h * g.tiles_w * g.tiles_n;
+  if constexpr (!kVD) {
+    const char* np = std::getenv("CPLXK_CONV_NONPERSISTENT");
+    if (!(np && np[0] == '1')) {
+      int dev = 0, sms = 148;
+      CPLXK_CUDA_TRY(cudaGetDevice(&dev));
+      CPLXK_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      auto pk = conv_tc_persistent_kernel<T>;
+      CPLXK_CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          ConvPCfg<T>::SMEM_BYTES));
+      const unsigned grid = static_cast<unsigned>(tiles < sms ? tiles : sms);
+      pk<<<grid, 192, ConvPCfg<T>::SMEM_BYTES, st>>>(tm_xr, tm_xi, tm_u, tm_v, g, ep,
+                                                     static_cast<int>(tiles));
+      CPLXK_CUDA_TRY(cudaGetLastError());
+      return CPLXK_OK;
+    }
+  }
   auto kern = conv_tc_kernel<T, kVD>;
   CPLXK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   kern<<<static_cast<unsigned>(tiles), C::THREADS, C::SMEM_BYTES, st>>>(tm_xr, tm_xi, tm_q, tm_u, tm_v,
