@@ -409,6 +409,10 @@ vd_prepare_kernel(const T* __restrict__ x_re, const T* __restrict__ x_im, int64_
   }
 }
 
+int fwd_tc2_dispatch(int dtype, bool cplx, const void* x_re, const void* x_im, const void* w_re,
+                     const void* w_im, const void* q, const void* e, int64_t M, int64_t N, int64_t K,
+                     const EpiParams& ep, cudaStream_t st);
+
 size_t fwd_tc_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K) {
   const size_t es = dtype == CPLXK_F32 ? 4 : 2;
   const size_t qb = (static_cast<size_t>(M) * K * es + 255) & ~static_cast<size_t>(255);
@@ -443,6 +447,14 @@ static int launch_tc(const void* x_re, const void* x_im, const void* w_re, const
                                                     static_cast<const T*>(x_im), M * K, q,
                                                     static_cast<const T*>(ls2), N * K, e);
     CPLXK_CUDA_TRY(cudaGetLastError());
+    {
+      // CTA-pair kernel (cta_group::2): default for tiles that fill a pair, CPLXK_PAIR=0 disables
+      const char* pe = std::getenv("CPLXK_PAIR");
+      const bool want_pair = pe ? (pe[0] == '1') : true;
+      if (want_pair && M > 128)
+        return fwd_tc2_dispatch(std::is_same<T, float>::value ? CPLXK_F32 : CPLXK_BF16, kCplx, x_re,
+                                x_im, w_re, w_im, q, e, M, N, K, ep, st);
+    }
     if ((rc = make_plane_map<T, kSwz>(&tm_q, q, M, K, false))) return rc;   // already rounded
     if ((rc = make_plane_map<T, kSwz>(&tm_ls, e, N, K, false))) return rc;
   }

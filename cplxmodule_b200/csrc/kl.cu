@@ -22,17 +22,37 @@ struct KlWorkspace {
   double partial[kKlMaxBlocks];
 };
 
+// MUFU approximations without the denormal/range fix-up code of __logf/__expf/__fdividef:
+// every argument in this kernel is a normal number well inside the fast range.
+__device__ __forceinline__ float f_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float f_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float f_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float f_log(float x) { return 0.69314718056f * f_lg2(x); }
+__device__ __forceinline__ float f_exp(float x) { return f_ex2(1.44269504089f * x); }
+
 // log(1 + e) for e in (0, 1]: 4-term series below 0.03 (rel. err < 2e-7), fast log above
 // (abs. err ~2^-22 on a result >= 0.0296).  log1pf() costs ~4x as many instructions and this
 // kernel has to stay under ~40 instructions per element to remain HBM bound.
 __device__ __forceinline__ float log1p_unit(float e) {
   if (e < 0.03f) return e * fmaf(e, fmaf(e, fmaf(e, -0.25f, 0.33333334f), -0.5f), 1.0f);
-  return __logf(1.0f + e);
+  return f_log(1.0f + e);
 }
 
 __device__ __forceinline__ float softplus_f(float x) {
   // log(1 + e^x), stable for both signs (torch switches to identity above 20: same fp32 value)
-  return fmaxf(x, 0.f) + log1p_unit(__expf(-fabsf(x)));
+  return fmaxf(x, 0.f) + log1p_unit(f_exp(-fabsf(x)));
 }
 
 // Ein(t) = gamma + ln t + E1(t) = gamma - la - Ei(-exp(-la)),  t = exp(-la) = 1/alpha > 0.
@@ -58,7 +78,7 @@ __device__ __forceinline__ float ein_of(float t, float n) {
   if (t < 60.f) {
     float num = (((t + 8.5733287401f) * t + 18.0590169730f) * t + 8.6347608925f) * t + 0.2677737343f;
     float den = (((t + 9.5733223454f) * t + 25.6329561486f) * t + 21.0996530827f) * t + 3.9584969228f;
-    e1 = __expf(-t) * __fdividef(num, den * t);
+    e1 = f_exp(-t) * num * f_rcp(den * t);
   }
   return kGamma + n + e1;
 }
@@ -78,20 +98,20 @@ __device__ __forceinline__ float modulus2_of(float wr, float wi) {
 
 template <int kKind>
 __device__ __forceinline__ float log_alpha_of(float wr, float wi, float ls2) {
-  return ls2 - __logf(modulus2_of<kKind>(wr, wi));
+  return ls2 - f_log(modulus2_of<kKind>(wr, wi));
 }
 
 template <int kKind>
 __device__ __forceinline__ float penalty_of(float wr, float wi, float ls2) {
-  const float n = __logf(modulus2_of<kKind>(wr, wi)) - ls2;  // -log_alpha
+  const float n = f_log(modulus2_of<kKind>(wr, wi)) - ls2;  // -log_alpha
   if constexpr (kKind == CPLXK_KL_REAL_VD) {
     float z = fmaf(1.48695f, n, -1.87320f);
-    float sig = __fdividef(1.0f, 1.0f + __expf(-z));
+    float sig = f_rcp(1.0f + f_exp(-z));
     return fmaf(0.63576f, sig, 0.5f * softplus_f(n));
   } else if constexpr (kKind == CPLXK_KL_REAL_ARD) {
     return 0.5f * softplus_f(n);
   } else if constexpr (kKind == CPLXK_KL_CPLX_VD) {
-    return ein_of(__expf(n), n);
+    return ein_of(f_exp(n), n);
   } else {
     return softplus_f(n);
   }
