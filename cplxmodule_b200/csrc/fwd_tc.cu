@@ -375,6 +375,44 @@ static int make_plane_map(CUtensorMap* out, const void* ptr, int64_t rows, int64
 // q = |x|^2 (per input row) and E = exp(log_sigma2) (per weight row), rounded to the MMA
 // operand precision, written once to a caller-provided workspace.  HBM-bound elementwise pass;
 // it takes the square/exp work (and its shared-memory traffic) out of the GEMM mainloop.
+// fp32 planes -> bf16 derived operands (mixed-precision variance GEMM of the CTA-pair kernel)
+template <bool kCplx>
+__global__ void __launch_bounds__(256)
+vd_prepare_bf16_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im, int64_t nx,
+                       __nv_bfloat16* __restrict__ q, const float* __restrict__ ls2, int64_t nw,
+                       __nv_bfloat16* __restrict__ e) {
+  const int64_t vx = nx / 8, vw = nw / 8;   // 8 elements per thread: 2 x 16 B in, 16 B out
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < vx + vw;
+       i += stride) {
+    Vec16<__nv_bfloat16> o;
+    if (i < vx) {
+      Vec16<float> a0, a1;
+      a0.load(x_re + i * 8), a1.load(x_re + i * 8 + 4);
+      if constexpr (kCplx) {
+        Vec16<float> b0, b1;
+        b0.load(x_im + i * 8), b1.load(x_im + i * 8 + 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o.v[j] = fmaf(a0.v[j], a0.v[j], b0.v[j] * b0.v[j]);
+          o.v[4 + j] = fmaf(a1.v[j], a1.v[j], b1.v[j] * b1.v[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o.v[j] = a0.v[j] * a0.v[j], o.v[4 + j] = a1.v[j] * a1.v[j];
+      }
+      o.store(q + i * 8);
+    } else {
+      const int64_t k = i - vx;
+      Vec16<float> a0, a1;
+      a0.load(ls2 + k * 8), a1.load(ls2 + k * 8 + 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o.v[j] = __expf(a0.v[j]), o.v[4 + j] = __expf(a1.v[j]);
+      o.store(e + k * 8);
+    }
+  }
+}
+
 template <typename T, bool kCplx>
 __global__ void __launch_bounds__(256)
 vd_prepare_kernel(const T* __restrict__ x_re, const T* __restrict__ x_im, int64_t nx,
@@ -409,9 +447,9 @@ vd_prepare_kernel(const T* __restrict__ x_re, const T* __restrict__ x_im, int64_
   }
 }
 
-int fwd_tc2_dispatch(int dtype, bool cplx, const void* x_re, const void* x_im, const void* w_re,
-                     const void* w_im, const void* q, const void* e, int64_t M, int64_t N, int64_t K,
-                     const EpiParams& ep, cudaStream_t st);
+int fwd_tc2_dispatch(int dtype, bool cplx, bool mix_var, const void* x_re, const void* x_im,
+                     const void* w_re, const void* w_im, const void* q, const void* e, int64_t M,
+                     int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st);
 
 size_t fwd_tc_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K) {
   const size_t es = dtype == CPLXK_F32 ? 4 : 2;
@@ -441,20 +479,32 @@ static int launch_tc(const void* x_re, const void* x_im, const void* w_re, const
     T* q = static_cast<T*>(workspace);
     const size_t qb = (static_cast<size_t>(M) * K * sizeof(T) + 255) & ~static_cast<size_t>(255);
     T* e = reinterpret_cast<T*>(static_cast<uint8_t*>(workspace) + qb);
-    const int64_t work = (M * K + N * K) / Elem<T>::kVec;
+    // CTA-pair kernel (cta_group::2): default for problems that fill a pair, CPLXK_PAIR=0 disables;
+    // with fp32 planes its variance operands travel as bf16 (CPLXK_MIXVAR=0 keeps them tf32)
+    const char* pe = std::getenv("CPLXK_PAIR");
+    const bool use_pair = (pe ? (pe[0] == '1') : true) && M > 128;
+    const char* me = std::getenv("CPLXK_MIXVAR");
+    const bool mix_var = use_pair && std::is_same<T, float>::value && (K % 8 == 0) &&
+                         (me ? (me[0] == '1') : true);
+    const int64_t work = (M * K + N * K) / (mix_var ? 8 : Elem<T>::kVec);
     const int grid = static_cast<int>(work / 256 + 1 > 148 * 16 ? 148 * 16 : work / 256 + 1);
-    vd_prepare_kernel<T, kCplx><<<grid, 256, 0, st>>>(static_cast<const T*>(x_re),
-                                                    static_cast<const T*>(x_im), M * K, q,
-                                                    static_cast<const T*>(ls2), N * K, e);
-    CPLXK_CUDA_TRY(cudaGetLastError());
-    {
-      // CTA-pair kernel (cta_group::2): default for tiles that fill a pair, CPLXK_PAIR=0 disables
-      const char* pe = std::getenv("CPLXK_PAIR");
-      const bool want_pair = pe ? (pe[0] == '1') : true;
-      if (want_pair && M > 128)
-        return fwd_tc2_dispatch(std::is_same<T, float>::value ? CPLXK_F32 : CPLXK_BF16, kCplx, x_re,
-                                x_im, w_re, w_im, q, e, M, N, K, ep, st);
+    if constexpr (std::is_same<T, float>::value) {
+      if (mix_var) {
+        auto qb = reinterpret_cast<__nv_bfloat16*>(q);
+        auto eb = reinterpret_cast<__nv_bfloat16*>(e);
+        vd_prepare_bf16_kernel<kCplx><<<grid, 256, 0, st>>>(
+            static_cast<const float*>(x_re), static_cast<const float*>(x_im), M * K, qb,
+            static_cast<const float*>(ls2), N * K, eb);
+      }
     }
+    if (!mix_var)
+      vd_prepare_kernel<T, kCplx><<<grid, 256, 0, st>>>(static_cast<const T*>(x_re),
+                                                      static_cast<const T*>(x_im), M * K, q,
+                                                      static_cast<const T*>(ls2), N * K, e);
+    CPLXK_CUDA_TRY(cudaGetLastError());
+    if (use_pair)
+      return fwd_tc2_dispatch(std::is_same<T, float>::value ? CPLXK_F32 : CPLXK_BF16, kCplx, mix_var,
+                              x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
     if ((rc = make_plane_map<T, kSwz>(&tm_q, q, M, K, false))) return rc;   // already rounded
     if ((rc = make_plane_map<T, kSwz>(&tm_ls, e, N, K, false))) return rc;
   }

@@ -14,18 +14,27 @@
 
 namespace cplxk {
 
-template <typename T, bool kCplx>
+// kMixVar (fp32 planes only): the two operands of the variance GEMM, |x|^2 and exp(log_sigma2),
+// are all-positive and only feed sqrt(s2) * eps, so they travel as bf16 (round-to-nearest in
+// the pre-pass; the rounding errors average out over K) and that GEMM runs as kind::f16 at
+// twice the tf32 rate: 4.5 instead of 5 tf32-MMA-equivalents per k-step, smaller stages.
+template <typename T, bool kCplx, bool kMixVar>
 struct Tc2Cfg {
+  static_assert(!kMixVar || std::is_same<T, float>::value, "mixed variance operands: fp32 planes");
   static constexpr bool kBF16 = std::is_same<T, __nv_bfloat16>::value;
   static constexpr int BM = 128, BN = 128;            // per-CTA rows; N of the pair tile
   static constexpr int BK = 128 / static_cast<int>(sizeof(T));
   static constexpr int KSTEPS = 4;
   static constexpr int A_TILE = 128 * 128, B_HALF = 64 * 128;
   static constexpr int NA = kCplx ? 2 : 1;
+  static constexpr int Q_TILE = kMixVar ? A_TILE / 2 : A_TILE;     // bf16: 128 rows x 64 B (SW64)
+  static constexpr int E_HALF = kMixVar ? B_HALF / 2 : B_HALF;
+  static constexpr int VAR_SWZ = kMixVar ? 64 : 128;
+  static constexpr int VAR_KSTEPS = kMixVar ? 2 : 4;               // K = 16 bf16 per MMA
   static constexpr int OFF_A0 = 0, OFF_A1 = A_TILE, OFF_Q = NA * A_TILE;
-  static constexpr int OFF_B0 = (NA + 1) * A_TILE, OFF_B1 = OFF_B0 + B_HALF;
+  static constexpr int OFF_B0 = OFF_Q + Q_TILE, OFF_B1 = OFF_B0 + B_HALF;
   static constexpr int OFF_E = OFF_B0 + NA * B_HALF;
-  static constexpr int STAGE_BYTES = (NA + 1) * (A_TILE + B_HALF);   // 72 KB complex, 48 KB real
+  static constexpr int STAGE_BYTES = OFF_E + E_HALF;               // 72 KB complex (60 KB mixed)
   static constexpr int STAGES = (227 * 1024 - 2048) / STAGE_BYTES > 6 ? 6 : (227 * 1024 - 2048) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;
   static constexpr int NACC = NA + 1;
@@ -39,13 +48,13 @@ struct Tc2Params {
   EpiParams ep;
 };
 
-template <typename T, bool kCplx>
+template <typename T, bool kCplx, bool kMixVar>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__ CUtensorMap tm_xi,
                const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_wr,
                const __grid_constant__ CUtensorMap tm_wi, const __grid_constant__ CUtensorMap tm_e,
                const Tc2Params p) {
-  using C = Tc2Cfg<T, kCplx>;
+  using C = Tc2Cfg<T, kCplx, kMixVar>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -136,10 +145,10 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
         ptx::tcgen05_fence_after();
         const uint64_t a0 = ptx::make_kmajor_desc<128>(st + C::OFF_A0);
         const uint64_t a1 = ptx::make_kmajor_desc<128>(st + C::OFF_A1);
-        const uint64_t aq = ptx::make_kmajor_desc<128>(st + C::OFF_Q);
+        const uint64_t aq = ptx::make_kmajor_desc<C::VAR_SWZ>(st + C::OFF_Q);
         const uint64_t b0 = ptx::make_kmajor_desc<128>(st + C::OFF_B0);
         const uint64_t b1 = ptx::make_kmajor_desc<128>(st + C::OFF_B1);
-        const uint64_t be = ptx::make_kmajor_desc<128>(st + C::OFF_E);
+        const uint64_t be = ptx::make_kmajor_desc<C::VAR_SWZ>(st + C::OFF_E);
 #pragma unroll
         for (int k = 0; k < C::KSTEPS; ++k) {
           const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
@@ -150,7 +159,17 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
             ptx::umma_ss_pair<C::kBF16>(t_im, ptx::desc_advance(a0, off), ptx::desc_advance(b1, off), idesc, acc);
             ptx::umma_ss_pair<C::kBF16>(t_im, ptx::desc_advance(a1, off), ptx::desc_advance(b0, off), idesc, 1u);
           }
-          ptx::umma_ss_pair<C::kBF16>(t_s2, ptx::desc_advance(aq, off), ptx::desc_advance(be, off), idesc, acc);
+          if constexpr (!kMixVar)
+            ptx::umma_ss_pair<C::kBF16>(t_s2, ptx::desc_advance(aq, off), ptx::desc_advance(be, off), idesc, acc);
+        }
+        if constexpr (kMixVar) {
+          constexpr uint32_t idesc_bf = ptx::make_idesc<true>(256, C::BN, false, false);
+#pragma unroll
+          for (int k = 0; k < C::VAR_KSTEPS; ++k) {
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            ptx::umma_ss_pair<true>(t_s2, ptx::desc_advance(aq, k * 32), ptx::desc_advance(be, k * 32),
+                                    idesc_bf, acc);
+          }
         }
         ptx::umma_commit_pair(bar_empty + 8 * s);   // frees the stage in BOTH CTAs
       }
@@ -213,36 +232,43 @@ static PFN_encodeTiled2 encode_fn2() {
   return fn;
 }
 
-// plane [rows, K] row-major -> box {128 bytes of K, box_rows}
+// plane [rows, K] row-major of T -> box {box_k elements of K, box_rows}, swizzle = box bytes
 template <typename T>
 static int plane_map2(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K, int box_rows,
-                      bool round_tf32) {
+                      bool round_tf32, int box_k = 128 / static_cast<int>(sizeof(T))) {
   auto enc = encode_fn2();
   if (!enc) return CPLXK_ERR_CUDA;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(K) * sizeof(T)};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / sizeof(T)), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_k), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1u, 1u};
   CUtensorMapDataType dt = std::is_same<T, float>::value
                                ? (round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)
                                : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = box_k * sizeof(T) == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                         : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? CPLXK_OK : CPLXK_ERR_CUDA;
 }
 
-template <typename T, bool kCplx>
+template <typename T, bool kCplx, bool kMixVar>
 static int launch_tc2(const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                       const void* q, const void* e, int64_t M, int64_t N, int64_t K,
                       const EpiParams& ep, cudaStream_t st) {
-  using C = Tc2Cfg<T, kCplx>;
+  using C = Tc2Cfg<T, kCplx, kMixVar>;
   CUtensorMap tm_xr, tm_xi, tm_q, tm_wr, tm_wi, tm_e;
   int rc;
   if ((rc = plane_map2<T>(&tm_xr, x_re, M, K, 128, true))) return rc;
-  if ((rc = plane_map2<T>(&tm_q, q, M, K, 128, false))) return rc;
   if ((rc = plane_map2<T>(&tm_wr, w_re, N, K, 64, true))) return rc;
-  if ((rc = plane_map2<T>(&tm_e, e, N, K, 64, false))) return rc;
+  if (kMixVar) {   // q / E were written as bf16 by the pre-pass: 32 K-elements = 64-byte rows
+    if ((rc = plane_map2<__nv_bfloat16>(&tm_q, q, M, K, 128, false, 32))) return rc;
+    if ((rc = plane_map2<__nv_bfloat16>(&tm_e, e, N, K, 64, false, 32))) return rc;
+  } else {
+    if ((rc = plane_map2<T>(&tm_q, q, M, K, 128, false))) return rc;
+    if ((rc = plane_map2<T>(&tm_e, e, N, K, 64, false))) return rc;
+  }
   tm_xi = tm_xr, tm_wi = tm_wr;
   if (kCplx) {
     if ((rc = plane_map2<T>(&tm_xi, x_im, M, K, 128, true))) return rc;
@@ -255,7 +281,7 @@ static int launch_tc2(const void* x_re, const void* x_im, const void* w_re, cons
   p.ep = ep;
   const int64_t pairs = static_cast<int64_t>(p.tiles_m2) * p.tiles_n;
   if (2 * pairs > 0x7fffffff) return CPLXK_ERR_UNSUPPORTED;
-  auto kern = fwd_tc2_kernel<T, kCplx>;
+  auto kern = fwd_tc2_kernel<T, kCplx, kMixVar>;
   CPLXK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   kern<<<static_cast<unsigned>(2 * pairs), C::THREADS, C::SMEM_BYTES, st>>>(tm_xr, tm_xi, tm_q, tm_wr,
                                                                           tm_wi, tm_e, p);
@@ -263,16 +289,20 @@ static int launch_tc2(const void* x_re, const void* x_im, const void* w_re, cons
   return CPLXK_OK;
 }
 
-int fwd_tc2_dispatch(int dtype, bool cplx, const void* x_re, const void* x_im, const void* w_re,
-                     const void* w_im, const void* q, const void* e, int64_t M, int64_t N, int64_t K,
-                     const EpiParams& ep, cudaStream_t st) {
+int fwd_tc2_dispatch(int dtype, bool cplx, bool mix_var, const void* x_re, const void* x_im,
+                     const void* w_re, const void* w_im, const void* q, const void* e, int64_t M,
+                     int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st) {
   if (dtype == CPLXK_F32) {
-    if (cplx) return launch_tc2<float, true>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
-    return launch_tc2<float, false>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
+    if (mix_var) {
+      if (cplx) return launch_tc2<float, true, true>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
+      return launch_tc2<float, false, true>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
+    }
+    if (cplx) return launch_tc2<float, true, false>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
+    return launch_tc2<float, false, false>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
   }
   if (dtype == CPLXK_BF16) {
-    if (cplx) return launch_tc2<__nv_bfloat16, true>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
-    return launch_tc2<__nv_bfloat16, false>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
+    if (cplx) return launch_tc2<__nv_bfloat16, true, false>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
+    return launch_tc2<__nv_bfloat16, false, false>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
   }
   return CPLXK_ERR_BADARG;
 }
