@@ -11,7 +11,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcplxk.so")
+LIB_PATH = os.environ.get("CPLXK_LIB") or os.path.join(_HERE, "csrc", "libcplxk.so")  # CPLXK_LIB: A/B builds
 
 F32, BF16 = 0, 1
 MATH_AUTO, MATH_TENSOR, MATH_SIMT = 0, 1, 2

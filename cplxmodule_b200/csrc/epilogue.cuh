@@ -190,14 +190,14 @@ __device__ __forceinline__ void noise_prefetch(const EpiParams& p, int64_t m, in
     // ~200 KB of SASS executed once per tile, i.e. instruction-fetch bound.  The 8 Philox
     // chains of a trip are independent (branch-free cursor arithmetic) so they interleave.
     static_assert(R % 8 == 0, "trip size");
-    const uint32_t T = p.noise.threads;
-    uint64_t slot_re = static_cast<uint64_t>(row_off + n0) / T;
-    uint32_t idx_re = static_cast<uint32_t>(static_cast<uint64_t>(row_off + n0) - slot_re * T);
+    const uint32_t Tn = p.noise.threads;
+    uint64_t slot_re = static_cast<uint64_t>(row_off + n0) / Tn;
+    uint32_t idx_re = static_cast<uint32_t>(static_cast<uint64_t>(row_off + n0) - slot_re * Tn);
     uint64_t slot_im = 0;
     uint32_t idx_im = 0;
     if constexpr (kCplx) {
-      slot_im = static_cast<uint64_t>(p.plane_elems + row_off + n0) / T;
-      idx_im = static_cast<uint32_t>(static_cast<uint64_t>(p.plane_elems + row_off + n0) - slot_im * T);
+      slot_im = static_cast<uint64_t>(p.plane_elems + row_off + n0) / Tn;
+      idx_im = static_cast<uint32_t>(static_cast<uint64_t>(p.plane_elems + row_off + n0) - slot_im * Tn);
     }
 #pragma unroll 1
     for (int trip = 0; trip < R / 8; ++trip) {
@@ -206,24 +206,24 @@ __device__ __forceinline__ void noise_prefetch(const EpiParams& p, int64_t m, in
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         uint32_t i = idx_re + j;
-        const bool wrap = i >= T;
-        i = wrap ? i - T : i;
+        const bool wrap = i >= Tn;
+        i = wrap ? i - Tn : i;
         nre[R - 8 + j] = philox_torch_normal(i, slot_re + (wrap ? 1u : 0u), p.noise) * p.noise.scale;
       }
       idx_re += 8;
-      if (idx_re >= T) idx_re -= T, ++slot_re;
+      if (idx_re >= Tn) idx_re -= Tn, ++slot_re;
       if constexpr (kCplx) {
 #pragma unroll
         for (int j = 0; j < R - 8; ++j) nim[j] = nim[j + 8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           uint32_t i = idx_im + j;
-          const bool wrap = i >= T;
-          i = wrap ? i - T : i;
+          const bool wrap = i >= Tn;
+          i = wrap ? i - Tn : i;
           nim[R - 8 + j] = philox_torch_normal(i, slot_im + (wrap ? 1u : 0u), p.noise) * p.noise.scale;
         }
         idx_im += 8;
-        if (idx_im >= T) idx_im -= T, ++slot_im;
+        if (idx_im >= Tn) idx_im -= Tn, ++slot_im;
       }
     }
   } else {

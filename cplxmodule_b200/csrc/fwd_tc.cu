@@ -73,7 +73,6 @@ __device__ __forceinline__ float round_operand(float v) {
   }
 }
 
-constexpr int kTcThreads = 192;
 constexpr int kRasterGroup = 12;  // m-tiles per raster group: a wave covers ~12x12 tiles (L2 reuse)
 
 struct TcParams {
