@@ -135,6 +135,12 @@ def plane(t, dtype=None):
 def philox_plan(device, numel):
     """(seed, offset, threads, increment) replicating torch's CUDA ``normal_`` launch for
     ``numel`` floats (ATen/native/cuda/DistributionTemplates.h: calc_execution_policy)."""
+    if numel >= 2 ** 31:
+        # torch splits such tensors into 32-bit-indexable pieces with one generator advance each;
+        # that stream is not reproduced -- ask for the private layout instead
+        raise NotImplementedError(
+            "torch-exact noise is limited to outputs below 2**31 elements; "
+            "use cplxmodule_b200.set_noise_mode('fast') for this size")
     props = torch.cuda.get_device_properties(device)
     block = 256
     blocks_per_sm = props.max_threads_per_multi_processor // block

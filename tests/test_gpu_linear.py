@@ -260,3 +260,31 @@ def test_prepass_and_inkernel_transform_agree(prepass):
     assert rel_err(got[0], want[0]) < 1e-3 and rel_err(got[1], want[1]) < 1e-3
     assert rel_err(real, orc.real_linear_vd(x_re.double(), w_re.double(), None, ls2.double(),
                                             eps[0].double())) < 1e-3
+
+
+def test_dense_to_vd_to_masked_pipeline_on_gpu():
+    """compute_ard_masks -> binarize_masks -> deploy_masks; the masked layer's forward is the
+    accelerated kernel on weight * mask (reference: tests/test_relevance.py:206-242)."""
+    from cplxmodule_b200.nn.masked import CplxLinearMasked, binarize_masks, deploy_masks
+    from cplxmodule_b200.nn.relevance import compute_ard_masks
+    from cplxmodule_b200.nn.utils import sparsity
+    torch.manual_seed(17)
+    vd = CplxLinearVD(64, 48).to(DEV)
+    with torch.no_grad():
+        vd.log_sigma2.uniform_(-12, 4)
+    masks = compute_ard_masks(vd, threshold=0.0)
+    assert set(masks) == {"mask"} and 0 < masks["mask"].mean().item() < 1
+    state, masks = binarize_masks(vd.state_dict(), masks)
+    masked = CplxLinearMasked(64, 48).to(DEV)
+    masked.load_state_dict(state, strict=False)
+    deploy_masks(masked, state_dict=masks)
+    z = cplx.randn(10, 64, device=DEV)
+    out = masked(z)
+    c = lambda t: t.detach().cpu()
+    mk = c(masks["mask"])
+    want = orc.cplx_linear(c(z.real), c(z.imag), c(vd.weight.real) * mk, c(vd.weight.imag) * mk,
+                           c(vd.bias.real), c(vd.bias.imag))
+    assert rel_err(out.real, want[0]) < 1e-3 and rel_err(out.imag, want[1]) < 1e-3
+    frac = sparsity(masked)
+    assert abs(frac - (1 - mk.mean().item()) * (2 * 64 * 48) / (2 * 64 * 48 + 2 * 48)) < 1e-6
+    assert abs(sparsity(vd, threshold=0.0) - frac) < 1e-6

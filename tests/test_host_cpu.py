@@ -159,3 +159,38 @@ def test_default_init_bit_parity_with_reference():
         assert list(a) == list(b)
         for k in a:
             assert torch.equal(a[k], b[k]), k
+
+
+def test_masked_layer_mask_semantics_and_state_dict():
+    from cplxmodule_b200.nn.masked import (CplxLinearMasked, LinearMasked, binarize_masks,
+                                           deploy_masks, named_masks)
+    m = CplxLinearMasked(6, 4)
+    assert not m.is_sparse and "mask" not in m.state_dict()
+    with pytest.raises(RuntimeError, match="no sparsity mask"):
+        m.weight_masked
+    m.mask = torch.ones(6)                      # broadcast to the weight's shape
+    assert m.is_sparse and m.mask.shape == (4, 6) and "mask" in m.state_dict()
+    wm = m.weight_masked
+    assert isinstance(wm, cplx.Cplx) and torch.equal(wm.real, m.weight.real)
+    m.mask = None
+    assert not m.is_sparse
+    with pytest.raises(TypeError):
+        m.mask = [1, 0]
+    # dense -> VD -> masked transfer through state dicts (nn/relevance/README.md:77-89)
+    vd = CplxLinearVD(6, 4)
+    masks = {"mask": (torch.rand(4, 6) > 0.5).float()}
+    state, masks = binarize_masks(vd.state_dict(), masks)
+    missing, unexpected = m.load_state_dict(state, strict=False)
+    assert "log_sigma2" in unexpected and not m.is_sparse
+    deploy_masks(m, state_dict=masks)
+    assert m.is_sparse and torch.equal(m.mask, masks["mask"])
+    assert dict(named_masks(m))[""] is m.mask
+    net = torch.nn.Sequential(LinearMasked(5, 3), torch.nn.ReLU(), LinearMasked(3, 2))
+    deploy_masks(net, state_dict={"0.mask": torch.zeros(3, 5)})
+    assert net[0].is_sparse and not net[2].is_sparse
+    deploy_masks(net, state_dict={}, reset=True)
+    assert not net[0].is_sparse
+    sd = net.state_dict()
+    sd["2.mask"] = torch.ones(2, 3)
+    net.load_state_dict(sd, strict=False)
+    assert net[2].is_sparse
