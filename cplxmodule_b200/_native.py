@@ -132,10 +132,10 @@ def plane(t, dtype=None):
 
 
 # --------------------------------------------------------------- philox bookkeeping
-def philox_plan(device, numel):
+def philox_plan(device, numel, torch_exact=True):
     """(seed, offset, threads, increment) replicating torch's CUDA ``normal_`` launch for
     ``numel`` floats (ATen/native/cuda/DistributionTemplates.h: calc_execution_policy)."""
-    if numel >= 2 ** 31:
+    if torch_exact and numel >= 2 ** 31:
         # torch splits such tensors into 32-bit-indexable pieces with one generator advance each;
         # that stream is not reproduced -- ask for the private layout instead
         raise NotImplementedError(

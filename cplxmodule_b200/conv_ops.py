@@ -67,7 +67,7 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
             er, ei = nv.plane(eps_re, dt), nv.plane(eps_im, dt)
         else:
             numel = (2 if cplx else 1) * y_re.numel()
-            gen, seed, offset, threads, inc = nv.philox_plan(dev, max(numel, 1))
+            gen, seed, offset, threads, inc = nv.philox_plan(dev, max(numel, 1), noise == nv.NOISE_PHILOX_TORCH)
     math = nv.MATH_SIMT if ops.get_math_mode() == "simt" else (
         nv.MATH_TENSOR if ops.get_math_mode() == "tensor" else nv.MATH_AUTO)
     ws, ws_bytes = None, 0

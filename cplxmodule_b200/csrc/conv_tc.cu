@@ -117,11 +117,14 @@ struct ConvCfg {
   static constexpr int STAGES = kVD ? 3 : 2;               // VD: 1 CTA/SM, plain: 2 CTAs/SM
   static constexpr int TMEM_COLS = kVD ? 512 : 256;        // D1 128 | D2 128 | (s2 64)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 1024;
-  static constexpr int THREADS = 192;
+  // VD: eight epilogue warps (two per TMEM lane quarter, 32 channels each) so that twice as
+  // many warps generate the torch-exact noise in the shadow of the MMAs
+  static constexpr int THREADS = kVD ? 320 : 192;
+  static constexpr int CH_PER_WARP = kVD ? 32 : 64;
 };
 
 template <typename T, bool kVD>
-__global__ void __launch_bounds__(192, (kVD ? 1 : 2))
+__global__ void __launch_bounds__((kVD ? 320 : 192), (kVD ? 1 : 2))
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__ CUtensorMap tm_xi,
                const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_u,
                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_e,
@@ -240,25 +243,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
     const int64_t pix_off = static_cast<int64_t>(b) * g.O * hw + oh * g.Wo + ow;  // + o * hw
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
 
-    // VD: the 2 x 64 normals of this pixel (one per output channel and plane) are generated /
+    // VD: the 2 x 32 normals (this warp's half of the tile's channels) of this pixel (one per output channel and plane) are generated /
     // fetched while the MMAs run and stay in registers.  Consecutive channels are `hw` apart in
     // torch's linear element order, so (subsequence, slot) advance by a constant -- no division.
-    float nre[kVD ? 64 : 1], nim[kVD ? 64 : 1];
+    constexpr int NCH = C::CH_PER_WARP;            // channels this thread owns
+    const int cbase = kVD ? ((warp - 2) >> 2) * NCH : 0;   // first of them inside the tile
+    float nre[kVD ? NCH : 1], nim[kVD ? NCH : 1];
     if constexpr (kVD) {
 #pragma unroll
-      for (int j = 0; j < 64; ++j) nre[j] = 0.f, nim[j] = 0.f;
+      for (int j = 0; j < NCH; ++j) nre[j] = 0.f, nim[j] = 0.f;
       if (pix_ok) {
         if (ep.noise.mode == CPLXK_NOISE_INJECT) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j)
-            if (n0 + j < g.O) {
-              const int64_t off = pix_off + static_cast<int64_t>(n0 + j) * hw;
+          for (int j = 0; j < NCH; ++j)
+            if (n0 + cbase + j < g.O) {
+              const int64_t off = pix_off + static_cast<int64_t>(n0 + cbase + j) * hw;
               nre[j] = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.eps_re) + off));
               nim[j] = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.eps_im) + off));
             }
         } else if (ep.noise.mode == CPLXK_NOISE_PHILOX_TORCH) {
           const uint32_t T_ = ep.noise.threads;
-          const uint64_t li0 = static_cast<uint64_t>(pix_off + static_cast<int64_t>(n0) * hw);
+          const uint64_t li0 = static_cast<uint64_t>(pix_off + static_cast<int64_t>(n0 + cbase) * hw);
           uint64_t slot_re = li0 / T_;
           uint32_t idx_re = static_cast<uint32_t>(li0 - slot_re * T_);
           const uint64_t li1 = li0 + static_cast<uint64_t>(ep.plane_elems);
@@ -267,9 +272,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
           const uint64_t dq = static_cast<uint64_t>(hw) / T_;
           const uint32_t dr = static_cast<uint32_t>(static_cast<uint64_t>(hw) - dq * T_);
 #pragma unroll 1
-          for (int trip = 0; trip < 8; ++trip) {
+          for (int trip = 0; trip < NCH / 8; ++trip) {
 #pragma unroll
-            for (int j = 0; j < 56; ++j) nre[j] = nre[j + 8], nim[j] = nim[j + 8];
+            for (int j = 0; j < NCH - 8; ++j) nre[j] = nre[j + 8], nim[j] = nim[j + 8];
             uint32_t ir[8], ii[8];
             uint64_t sr[8], si[8];
 #pragma unroll
@@ -282,24 +287,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              nre[56 + j] = philox_torch_normal(ir[j], sr[j], ep.noise) * ep.noise.scale;
-              nim[56 + j] = philox_torch_normal(ii[j], si[j], ep.noise) * ep.noise.scale;
+              nre[NCH - 8 + j] = philox_torch_normal(ir[j], sr[j], ep.noise) * ep.noise.scale;
+              nim[NCH - 8 + j] = philox_torch_normal(ii[j], si[j], ep.noise) * ep.noise.scale;
             }
           }
         } else {
 #pragma unroll 1
-          for (int trip = 0; trip < 8; ++trip) {
+          for (int trip = 0; trip < NCH / 8; ++trip) {
 #pragma unroll
-            for (int j = 0; j < 56; ++j) nre[j] = nre[j + 8], nim[j] = nim[j + 8];
+            for (int j = 0; j < NCH - 8; ++j) nre[j] = nre[j + 8], nim[j] = nim[j + 8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int64_t off = pix_off + static_cast<int64_t>(n0 + trip * 8 + j) * hw;
+              const int64_t off = pix_off + static_cast<int64_t>(n0 + cbase + trip * 8 + j) * hw;
               const uint64_t q = static_cast<uint64_t>(off) >> 2;
               const int comp = static_cast<int>(off & 3);
               float4 a = philox_fast_normal4(q, 0u, ep.noise);
               float4 bb = philox_fast_normal4(q, 1u, ep.noise);
-              nre[56 + j] = (comp == 0 ? a.x : comp == 1 ? a.y : comp == 2 ? a.z : a.w) * ep.noise.scale;
-              nim[56 + j] = (comp == 0 ? bb.x : comp == 1 ? bb.y : comp == 2 ? bb.z : bb.w) * ep.noise.scale;
+              nre[NCH - 8 + j] = (comp == 0 ? a.x : comp == 1 ? a.y : comp == 2 ? a.z : a.w) * ep.noise.scale;
+              nim[NCH - 8 + j] = (comp == 0 ? bb.x : comp == 1 ? bb.y : comp == 2 ? bb.z : bb.w) * ep.noise.scale;
             }
           }
         }
@@ -309,7 +314,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
     ptx::mbar_wait(bar_accum, 0);
     ptx::tcgen05_fence_after();
 #pragma unroll
-    for (int c = 0; c < C::BNO / 8; ++c) {
+    for (int cc = 0; cc < NCH / 8; ++cc) {
+      const int c = cbase / 8 + cc;                             // 8-channel chunk inside the tile
       uint32_t d1a[8], d1b[8], d2a[8], d2b[8], s2r[8];
       ptx::tmem_ld_32x32b_x8(lane_base + c * 8, d1a);          // x_re * U
       ptx::tmem_ld_32x32b_x8(lane_base + 64 + c * 8, d1b);     // x_re * V
@@ -330,8 +336,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
         const int64_t off = pix_off + static_cast<int64_t>(o) * hw;
         if constexpr (kVD) {
           const float sd = sqrtf(fmaxf(__uint_as_float(s2r[j]), 1e-8f));
-          re = fmaf(nre[c * 8 + j], sd, re);
-          im = fmaf(nim[c * 8 + j], sd, im);
+          re = fmaf(nre[cc * 8 + j], sd, re);
+          im = fmaf(nim[cc * 8 + j], sd, im);
         }
         static_cast<T*>(ep.y_re)[off] = Elem<T>::from_f(re);   // 32 lanes -> 32 consecutive pixels
         static_cast<T*>(ep.y_im)[off] = Elem<T>::from_f(im);

@@ -90,7 +90,7 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
             else:
                 er = ei = None
                 numel = (2 if cplx else 1) * M * N
-                gen, seed, offset, threads, inc = nv.philox_plan(dev, max(numel, 1))
+                gen, seed, offset, threads, inc = nv.philox_plan(dev, max(numel, 1), noise == nv.NOISE_PHILOX_TORCH)
             ws, ws_bytes = None, 0
             if _state["prepare"] and math != nv.MATH_SIMT:
                 ws_bytes = lib.cplxk_linear_vd_workspace_bytes(M, N, K, code)
