@@ -1,13 +1,13 @@
 """First-contact diagnostics for the tcgen05 kernel on a real B200: every kernel variant
 (real/complex x plain/VD x fp32/bf16 x swizzle 64/128) in its OWN subprocess under a timeout,
 so a hang or a sticky CUDA error in one variant cannot take the others (or the box) down.
-Writes gpurun_out/tc_diag.json.   usage: python tools/tc_diag.py [--one cfg-json]"""
+Writes gpurun_out/tc_diag.json.   usage: python tests/tools/tc_diag.py [--one cfg-json]"""
 import json
 import os
 import subprocess
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

@@ -1,6 +1,5 @@
 """Kernel-level timing sweep of the fused forward on one GPU (CUDA events, L2-exceeding
-operands): swizzle/stage count, noise mode, dtype, plain vs variational, and the tf32
-rounding experiment.  Writes gpurun_out/kbench.json."""
+operands): swizzle/stage count, noise mode, dtype, plain vs variational, pre-pass vs in-kernel transform.  Writes gpurun_out/kbench.json."""
 import json
 import os
 import sys
@@ -11,7 +10,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import cplxmodule_b200 as cb                      # noqa: E402
 from cplxmodule_b200 import cplx, ops             # noqa: E402
-from oracle import cplx_oracle as orc             # noqa: E402
 
 DEV = "cuda"
 M = N = K = int(os.environ.get("KB_SIZE", "4096"))
@@ -81,23 +79,6 @@ def main():
     if os.environ.get("KB_QUICK"):
         json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "kbench_quick.json"), "w"), indent=1)
         return
-    # ---- tf32 rounding experiment: TFLOAT32 tensor maps vs raw FLOAT32 (tensor-core truncation)
-    torch.manual_seed(1)
-    for (m, n, k) in ((5, 3, 8), (256, 256, 64), (512, 512, 4096)):
-        xr, xi = torch.randn(m, k), torch.randn(m, k)
-        wr, wi = torch.randn(n, k) / k ** 0.5, torch.randn(n, k) / k ** 0.5
-        want = orc.cplx_linear(xr.double(), xi.double(), wr.double(), wi.double())
-        for raw in ("1", "0"):
-            os.environ["CPLXK_TMA_RAW_F32"] = raw
-            got = ops.cplx_linear(xr.to(DEV), xi.to(DEV), wr.to(DEV), wi.to(DEV))
-            err = max(float((g.double().cpu() - w).abs().max() / w.abs().max())
-                      for g, w in zip(got, want))
-            bias = float(((got[0].double().cpu() - want[0]) * want[0].sign()).mean() /
-                         want[0].abs().mean())
-            rows.append(dict(case="tf32_rounding", raw_f32=raw, shape=[m, n, k], rel_err=err,
-                             signed_bias=bias))
-            print(json.dumps(rows[-1]), flush=True)
-    os.environ.pop("CPLXK_TMA_RAW_F32", None)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "kbench.json"), "w") as f:
         json.dump(rows, f, indent=1)
