@@ -258,11 +258,11 @@ def run_ours(args, rank, local_rank, world):
         ms = timed(lambda: step(record=True), args.steps)
         # the timed loop may be shorter than nvidia-smi's sampling period: keep the identical
         # loop running (untimed) until ~0.4 s of load has been sampled
-        t_end = time.perf_counter() + max(0.0, 0.4 - ms / 1e3)
-        while time.perf_counter() < t_end:
-            for _ in range(10):
-                step()
-            torch.cuda.synchronize(dev)
+        # (`ms` is the all-reduced maximum, so every rank runs the same number of extra steps)
+        extra = int(max(0.0, 400.0 - ms) / max(ms / args.steps, 1e-3)) + 1
+        for _ in range(min(extra, 5000)):
+            step()
+        torch.cuda.synchronize(dev)
         clocks = sampler.stop() if rank == 0 else None
         if clocks is not None:
             clocks["window"] = "timed loop + identical untimed continuation, >= 0.4 s under load"
