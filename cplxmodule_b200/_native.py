@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("CPLXK_LIB") or os.path.join(_HERE, "csrc", "libcplxk.
 F32, BF16 = 0, 1
 MATH_AUTO, MATH_TENSOR, MATH_SIMT = 0, 1, 2
 NOISE_INJECT, NOISE_PHILOX_TORCH, NOISE_PHILOX_FAST = 0, 1, 2
+ERR_UNSUPPORTED = -5
 KL_REAL_VD, KL_REAL_ARD, KL_CPLX_VD, KL_CPLX_ARD = 0, 1, 2, 3
 
 EXPORTS = (
@@ -48,7 +49,7 @@ def _declare(lib):
                              _vp, ctypes.c_size_t, _vp]
     lib.cplxk_log_alpha.argtypes = [_vp, _vp, _vp, _i64, _int, _vp, ctypes.c_float, _vp, _vp]
     lib.cplxk_conv2d_fwd.argtypes = ([_vp] * 9 + [_int, _u64, _u64, _u32] + [_vp] * 2
-                                     + [_i64] * 13 + [_int, _int, _vp, ctypes.c_size_t, _vp])
+                                     + [_i64] * 13 + [_int, _int, _int, _vp, ctypes.c_size_t, _vp])
     lib.cplxk_conv2d_workspace_bytes.restype = ctypes.c_size_t
     lib.cplxk_conv2d_workspace_bytes.argtypes = [_i64] * 7 + [_int, _int]
     lib.cplxk_randn_philox_torch.argtypes = [_vp, _i64, _u64, _u64, _u32, ctypes.c_float, _vp]

@@ -51,11 +51,24 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
     Wo = (W + 2 * padding[1] - dilation[1] * (kw - 1) - 1) // stride[1] + 1
     if Ho <= 0 or Wo <= 0:
         raise RuntimeError("kernel size can't be greater than actual input size")
-    xr, xi = nv.plane(x_re, dt), nv.plane(x_im, dt)
+    math = nv.MATH_SIMT if ops.get_math_mode() == "simt" else (
+        nv.MATH_TENSOR if ops.get_math_mode() == "tensor" else nv.MATH_AUTO)
+    # torch.channels_last activations (NCHW shape, NHWC strides) are consumed in place by the
+    # tensor-core path and the output keeps that memory format, as F.conv2d would
+    gran = 8 if dt == torch.float32 else 16
+    cl = (cplx and math != nv.MATH_SIMT and C % gran == 0 and C > 1
+          and x_re.dtype == dt and x_im.dtype == dt
+          and x_re.is_contiguous(memory_format=torch.channels_last) and not x_re.is_contiguous()
+          and x_im.is_contiguous(memory_format=torch.channels_last))
+    if cl:
+        xr, xi = x_re, x_im
+    else:
+        xr, xi = nv.plane(x_re, dt), nv.plane(x_im, dt)
     wr, wi = nv.plane(w_re), nv.plane(w_im)
     br, bi = nv.plane(b_re, dt), nv.plane(b_im, dt)
     l2 = nv.plane(ls2, dt)
-    y_re = torch.empty((B, O, Ho, Wo), dtype=dt, device=dev)
+    fmt = torch.channels_last if cl else torch.contiguous_format
+    y_re = torch.empty((B, O, Ho, Wo), dtype=dt, device=dev, memory_format=fmt)
     y_im = torch.empty_like(y_re) if cplx else None
     er = ei = None
     seed = offset = threads = 0
@@ -68,19 +81,29 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
         else:
             numel = (2 if cplx else 1) * y_re.numel()
             gen, seed, offset, threads, inc = nv.philox_plan(dev, max(numel, 1), noise == nv.NOISE_PHILOX_TORCH)
-    math = nv.MATH_SIMT if ops.get_math_mode() == "simt" else (
-        nv.MATH_TENSOR if ops.get_math_mode() == "tensor" else nv.MATH_AUTO)
     ws, ws_bytes = None, 0
     if cplx and math != nv.MATH_SIMT:
         ws_bytes = nv.lib().cplxk_conv2d_workspace_bytes(B, C, H, W, O, kh, kw, code,
                                                          1 if ls2 is not None else 0)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
-        nv.check(nv.lib().cplxk_conv2d_fwd(
-            nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi), nv.ptr(br), nv.ptr(bi), nv.ptr(l2),
-            nv.ptr(er), nv.ptr(ei), mode, seed, offset, threads, nv.ptr(y_re), nv.ptr(y_im),
-            B, C, H, W, O, kh, kw, stride[0], stride[1], padding[0], padding[1],
-            dilation[0], dilation[1], code, math, nv.ptr(ws), ws_bytes, nv.stream_ptr(dev)))
+    def call(xr, xi, y_re, y_im, cl):
+        with torch.cuda.device(dev):
+            return nv.lib().cplxk_conv2d_fwd(
+                nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi), nv.ptr(br), nv.ptr(bi), nv.ptr(l2),
+                nv.ptr(er), nv.ptr(ei), mode, seed, offset, threads, nv.ptr(y_re), nv.ptr(y_im),
+                B, C, H, W, O, kh, kw, stride[0], stride[1], padding[0], padding[1],
+                dilation[0], dilation[1], code, math, 1 if cl else 0, nv.ptr(ws), ws_bytes,
+                nv.stream_ptr(dev))
+
+    rc = call(xr, xi, y_re, y_im, cl)
+    if cl and rc == nv.ERR_UNSUPPORTED:
+        # geometry outside the implicit-GEMM kernel's TMA box limits: the other CUDA kernels
+        # take NCHW planes, so re-lay the activations once (still no CPU path)
+        xr, xi = nv.plane(x_re, dt), nv.plane(x_im, dt)
+        y_re = torch.empty((B, O, Ho, Wo), dtype=dt, device=dev)
+        y_im = torch.empty_like(y_re)
+        rc = call(xr, xi, y_re, y_im, False)
+    nv.check(rc)
     if gen is not None:
         gen.set_offset(offset + inc)
     return y_re, y_im

@@ -209,8 +209,8 @@ extern "C" int cplxk_conv2d_fwd(const void* x_re, const void* x_im, const void* 
                                 void* y_re, void* y_im, int64_t B, int64_t C, int64_t H, int64_t W,
                                 int64_t O, int64_t kh, int64_t kw, int64_t stride_h,
                                 int64_t stride_w, int64_t pad_h, int64_t pad_w, int64_t dil_h,
-                                int64_t dil_w, int dtype, int math, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+                                int64_t dil_w, int dtype, int math, int channels_last,
+                                void* workspace, size_t workspace_bytes, void* stream) {
   if (!x_re || !w_re || !y_re) return CPLXK_ERR_BADARG;
   if (B < 0 || C < 1 || H < 1 || W < 1 || O < 0 || kh < 1 || kw < 1 || stride_h < 1 ||
       stride_w < 1 || pad_h < 0 || pad_w < 0 || dil_h < 1 || dil_w < 1)
@@ -254,11 +254,13 @@ extern "C" int cplxk_conv2d_fwd(const void* x_re, const void* x_im, const void* 
                      conv_tc_supported(dtype, B, C, H, W, O, g.Ho, g.Wo, g.kh, g.kw, g.sh, g.sw) &&
                      workspace_bytes >= conv_tc_workspace_bytes(dtype, vd, B, C, H, W, O, kh, kw);
   if (math == CPLXK_MATH_TENSOR && !tc_ok) return workspace ? CPLXK_ERR_UNSUPPORTED : CPLXK_ERR_WORKSPACE;
+  if (channels_last && !(tc_ok && math != CPLXK_MATH_SIMT)) return CPLXK_ERR_UNSUPPORTED;  // NHWC: TC path only
   if (math != CPLXK_MATH_SIMT && tc_ok) {
     ConvTcEpi te;
     te.b_re = b_re, te.b_im = b_im, te.eps_re = eps_re, te.eps_im = eps_im;
     te.y_re = y_re, te.y_im = y_im, te.plane_elems = ep.plane_elems, te.noise = ep.noise;
-    return conv_tc_dispatch(dtype, vd, x_re, x_im, w_re, w_im, log_sigma2, workspace, B, C, H, W, O,
+    te.nhwc = channels_last ? 1 : 0;
+    return conv_tc_dispatch(dtype, vd, channels_last != 0, x_re, x_im, w_re, w_im, log_sigma2, workspace, B, C, H, W, O,
                             g.Ho, g.Wo, g.kh, g.kw, g.sh, g.sw, g.ph, g.pw, g.dh, g.dw, te, st);
   }
 #define CPLXK_CONV_CASE(T)                                                                  \

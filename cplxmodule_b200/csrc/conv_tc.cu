@@ -102,6 +102,62 @@ conv_wprep_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const 
   }
 }
 
+// Output address of (image b, channel o, pixel oh,ow).  The noise / eps planes always follow
+// torch's logical NCHW element order; only y follows the activations' memory format.
+__device__ __forceinline__ int64_t conv_y_offset(const ConvTcGeom& g, bool nhwc, int64_t b,
+                                                 int64_t o, int64_t oh, int64_t ow) {
+  return nhwc ? ((b * g.Ho + oh) * g.Wo + ow) * g.O + o : ((b * g.O + o) * g.Ho + oh) * g.Wo + ow;
+}
+
+// Eight consecutive output channels of one pixel.  NCHW: one scalar store per channel (the 32
+// lanes of a warp hold 32 consecutive pixels, so each store instruction is one 128 B line).
+// NHWC: the eight values are contiguous, written as one 32 B (fp32) / 16 B (bf16) vector.
+template <typename T>
+__device__ __forceinline__ void conv_store8(T* __restrict__ y, const ConvTcGeom& g, bool nhwc,
+                                            int64_t nchw_off, int64_t hw, int64_t nhwc_off, int o0,
+                                            const float (&v)[8]) {
+  if (!nhwc) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (o0 + j < g.O) y[nchw_off + static_cast<int64_t>(o0 + j) * hw] = Elem<T>::from_f(v[j]);
+    return;
+  }
+  T* dst = y + nhwc_off + o0;
+  if (o0 + 8 <= g.O && (g.O & 7) == 0) {
+    if constexpr (std::is_same<T, float>::value) {
+      asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(v[0]),
+                   "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                   : "memory");
+    } else {
+      uint4 pk;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+      pk.x = *reinterpret_cast<uint32_t*>(&h0), pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2), pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(dst) = pk;
+    }
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (o0 + j < g.O) dst[j] = Elem<T>::from_f(v[j]);
+}
+
+// channels-last |x|^2 for the variational forward when the input needs no transposition
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_abs2_kernel(const T* __restrict__ x_re, const T* __restrict__ x_im, T* __restrict__ q, int64_t n) {
+  constexpr int V = Elem<T>::kVec;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n / V;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    Vec16<T> a, b, o;
+    a.load(x_re + i * V), b.load(x_im + i * V);
+#pragma unroll
+    for (int j = 0; j < V; ++j) o.v[j] = round_mma_operand<T>(fmaf(a.v[j], a.v[j], b.v[j] * b.v[j]));
+    o.store(q + i * V);
+  }
+}
+
 // ------------------------------------------------------------------------ main kernel
 template <typename T, bool kVD>
 struct ConvCfg {
@@ -323,24 +379,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
       ptx::tmem_ld_32x32b_x8(lane_base + 192 + c * 8, d2b);    // x_im * V
       if constexpr (kVD) ptx::tmem_ld_32x32b_x8(lane_base + 256 + c * 8, s2r);
       ptx::tmem_ld_wait();
+      float re8[8], im8[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int o = n0 + c * 8 + j;
-        if (!pix_ok || o >= g.O) continue;
         float re = __uint_as_float(d1a[j]) - __uint_as_float(d2b[j]);
         float im = __uint_as_float(d1b[j]) + __uint_as_float(d2a[j]);
-        if (ep.b_re) {
+        if (ep.b_re && o < g.O) {
           re += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_re) + o));
           im += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_im) + o));
         }
-        const int64_t off = pix_off + static_cast<int64_t>(o) * hw;
         if constexpr (kVD) {
           const float sd = sqrtf(fmaxf(__uint_as_float(s2r[j]), 1e-8f));
           re = fmaf(nre[cc * 8 + j], sd, re);
           im = fmaf(nim[cc * 8 + j], sd, im);
         }
-        static_cast<T*>(ep.y_re)[off] = Elem<T>::from_f(re);   // 32 lanes -> 32 consecutive pixels
-        static_cast<T*>(ep.y_im)[off] = Elem<T>::from_f(im);
+        re8[j] = re, im8[j] = im;
+      }
+      if (pix_ok) {
+        const int64_t cl_off = ((static_cast<int64_t>(b) * g.Ho + oh) * g.Wo + ow) * g.O;
+        conv_store8<T>(static_cast<T*>(ep.y_re), g, ep.nhwc != 0, pix_off, hw, cl_off, n0 + c * 8, re8);
+        conv_store8<T>(static_cast<T*>(ep.y_im), g, ep.nhwc != 0, pix_off, hw, cl_off, n0 + c * 8, im8);
       }
     }
     ptx::tcgen05_fence_before();
@@ -505,19 +564,22 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_xr,
         ptx::tmem_ld_32x32b_x8(lane_base + 128 + c * 8, d2a);
         ptx::tmem_ld_32x32b_x8(lane_base + 192 + c * 8, d2b);
         ptx::tmem_ld_wait();
+        float re8[8], im8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int o = n0 + c * 8 + j;
-          if (!pix_ok || o >= g.O) continue;
           float re = __uint_as_float(d1a[j]) - __uint_as_float(d2b[j]);
           float im = __uint_as_float(d1b[j]) + __uint_as_float(d2a[j]);
-          if (ep.b_re) {
+          if (ep.b_re && o < g.O) {
             re += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_re) + o));
             im += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_im) + o));
           }
-          const int64_t off = pix_off + static_cast<int64_t>(o) * hw;
-          static_cast<T*>(ep.y_re)[off] = Elem<T>::from_f(re);
-          static_cast<T*>(ep.y_im)[off] = Elem<T>::from_f(im);
+          re8[j] = re, im8[j] = im;
+        }
+        if (pix_ok) {
+          const int64_t cl_off = ((static_cast<int64_t>(b) * g.Ho + oh) * g.Wo + ow) * g.O;
+          conv_store8<T>(static_cast<T*>(ep.y_re), g, ep.nhwc != 0, pix_off, hw, cl_off, n0 + c * 8, re8);
+          conv_store8<T>(static_cast<T*>(ep.y_im), g, ep.nhwc != 0, pix_off, hw, cl_off, n0 + c * 8, im8);
         }
       }
       ptx::tcgen05_fence_before();
@@ -560,7 +622,7 @@ static CUtensorMapDataType conv_dt() {
 
 // channels-last activation plane [B, H, W, Cp]: box {BKC channels, Wt px (stride sw), Ht rows (stride sh), 1}
 template <typename T>
-static int make_act_map(CUtensorMap* out, const void* ptr, const ConvTcGeom& g) {
+static int make_act_map(CUtensorMap* out, const void* ptr, const ConvTcGeom& g, bool round_tf32 = false) {
   auto enc = conv_encode_fn();
   if (!enc) return CPLXK_ERR_CUDA;
   const cuuint64_t es = sizeof(T);
@@ -572,7 +634,9 @@ static int make_act_map(CUtensorMap* out, const void* ptr, const ConvTcGeom& g) 
                        static_cast<cuuint32_t>((g.Wt - 1) * g.sw + 1),
                        static_cast<cuuint32_t>((g.Ht - 1) * g.sh + 1), 1u};
   cuuint32_t estr[4] = {1u, static_cast<cuuint32_t>(g.sw), static_cast<cuuint32_t>(g.sh), 1u};
-  CUresult r = enc(out, conv_dt<T>(), 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+  const CUtensorMapDataType dt = (round_tf32 && std::is_same<T, float>::value)
+                                     ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : conv_dt<T>();
+  CUresult r = enc(out, dt, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? CPLXK_OK : CPLXK_ERR_CUDA;
@@ -649,13 +713,28 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
   T* v = reinterpret_cast<T*>(wbase + wgt);
   T* e = kVD ? reinterpret_cast<T*>(wbase + 2 * wgt) : nullptr;
 
-  dim3 tg(static_cast<unsigned>(g.B * g.H), static_cast<unsigned>((g.Cp + 31) / 32),
-          static_cast<unsigned>((g.W + 31) / 32));
-  if (tg.y > 65535u || tg.z > 65535u || g.B * g.H > 0x7fffffff) return CPLXK_ERR_UNSUPPORTED;
-  conv_nhwc_kernel<T, kVD><<<tg, 256, 0, st>>>(static_cast<const T*>(x_re), static_cast<const T*>(x_im),
-                                               a_re, a_im, a_q, static_cast<int>(g.C), g.Cp,
-                                               static_cast<int>(g.H), static_cast<int>(g.W));
-  CPLXK_CUDA_TRY(cudaGetLastError());
+  const bool nhwc = ep.nhwc != 0;
+  if (nhwc) {
+    // activations already channels-last: TMA reads them in place (rounding to tf32 on load)
+    if (g.Cp != g.C || ((reinterpret_cast<uintptr_t>(x_re) | reinterpret_cast<uintptr_t>(x_im)) & 15u))
+      return CPLXK_ERR_UNSUPPORTED;
+    a_re = const_cast<T*>(static_cast<const T*>(x_re));
+    a_im = const_cast<T*>(static_cast<const T*>(x_im));
+    if (kVD) {
+      const int64_t n = g.B * g.H * g.W * g.C;
+      conv_abs2_kernel<T><<<static_cast<unsigned>(n / (256 * Elem<T>::kVec) + 1 > 148 * 16 ? 148 * 16 : n / (256 * Elem<T>::kVec) + 1), 256, 0, st>>>(
+          a_re, a_im, a_q, n);
+      CPLXK_CUDA_TRY(cudaGetLastError());
+    }
+  } else {
+    dim3 tg(static_cast<unsigned>(g.B * g.H), static_cast<unsigned>((g.Cp + 31) / 32),
+            static_cast<unsigned>((g.W + 31) / 32));
+    if (tg.y > 65535u || tg.z > 65535u || g.B * g.H > 0x7fffffff) return CPLXK_ERR_UNSUPPORTED;
+    conv_nhwc_kernel<T, kVD><<<tg, 256, 0, st>>>(static_cast<const T*>(x_re), static_cast<const T*>(x_im),
+                                                 a_re, a_im, a_q, static_cast<int>(g.C), g.Cp,
+                                                 static_cast<int>(g.H), static_cast<int>(g.W));
+    CPLXK_CUDA_TRY(cudaGetLastError());
+  }
   const int64_t wtotal = static_cast<int64_t>(g.kh) * g.kw * g.Op * g.Cp;
   conv_wprep_kernel<T, kVD><<<static_cast<unsigned>(wtotal / 256 + 1 > 1184 ? 1184 : wtotal / 256 + 1), 256, 0, st>>>(
       static_cast<const T*>(w_re), static_cast<const T*>(w_im), static_cast<const T*>(ls2), u, v, e,
@@ -664,8 +743,8 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
 
   CUtensorMap tm_xr, tm_xi, tm_q, tm_u, tm_v, tm_e;
   int rc;
-  if ((rc = make_act_map<T>(&tm_xr, a_re, g))) return rc;
-  if ((rc = make_act_map<T>(&tm_xi, a_im, g))) return rc;
+  if ((rc = make_act_map<T>(&tm_xr, a_re, g, nhwc))) return rc;
+  if ((rc = make_act_map<T>(&tm_xi, a_im, g, nhwc))) return rc;
   if ((rc = make_w_map<T>(&tm_u, u, g))) return rc;
   if ((rc = make_w_map<T>(&tm_v, v, g))) return rc;
   tm_q = tm_xr, tm_e = tm_u;
@@ -698,10 +777,12 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
   return CPLXK_OK;
 }
 
-int conv_tc_dispatch(int dtype, bool vd, const void* x_re, const void* x_im, const void* w_re,
+int conv_tc_dispatch(int dtype, bool vd, bool nhwc, const void* x_re, const void* x_im, const void* w_re,
                      const void* w_im, const void* ls2, void* workspace, int64_t B, int64_t C,
                      int64_t H, int64_t W, int64_t O, int64_t Ho, int64_t Wo, int kh, int kw, int sh,
-                     int sw, int ph, int pw, int dh, int dw, const ConvTcEpi& ep, cudaStream_t st) {
+                     int sw, int ph, int pw, int dh, int dw, const ConvTcEpi& ep_in, cudaStream_t st) {
+  ConvTcEpi ep = ep_in;
+  ep.nhwc = nhwc ? 1 : 0;
   ConvTcGeom g{};
   g.B = B, g.C = C, g.H = H, g.W = W, g.O = O, g.Ho = Ho, g.Wo = Wo;
   g.kh = kh, g.kw = kw, g.sh = sh, g.sw = sw, g.ph = ph, g.pw = pw, g.dh = dh, g.dw = dw;

@@ -21,6 +21,7 @@ struct ConvTcEpi {
   void* y_re;
   void* y_im;
   int64_t plane_elems;
+  int nhwc;              // 1: x / y planes are channels-last (torch.channels_last): no transposing pre-pass
   NoiseParams noise;
 };
 
@@ -28,7 +29,7 @@ size_t conv_tc_workspace_bytes(int dtype, bool vd, int64_t B, int64_t C, int64_t
                                int64_t O, int64_t kh, int64_t kw);
 bool conv_tc_supported(int dtype, int64_t B, int64_t C, int64_t H, int64_t W, int64_t O, int64_t Ho,
                        int64_t Wo, int kh, int kw, int sh, int sw);
-int conv_tc_dispatch(int dtype, bool vd, const void* x_re, const void* x_im, const void* w_re,
+int conv_tc_dispatch(int dtype, bool vd, bool nhwc, const void* x_re, const void* x_im, const void* w_re,
                      const void* w_im, const void* ls2, void* workspace, int64_t B, int64_t C,
                      int64_t H, int64_t W, int64_t O, int64_t Ho, int64_t Wo, int kh, int kw, int sh,
                      int sw, int ph, int pw, int dh, int dw, const ConvTcEpi& ep, cudaStream_t st);

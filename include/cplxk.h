@@ -184,6 +184,9 @@ int cplxk_conv2d_fwd(const void* x_re, const void* x_im,
                      int64_t pad_h, int64_t pad_w,
                      int64_t dil_h, int64_t dil_w,
                      int dtype, int math,
+                     int channels_last /* 1: x and y planes are NHWC in memory (torch.channels_last);
+                                          tensor-core path only, C % 8 == 0 (fp32) / 16 (bf16); skips
+                                          the transposing pre-pass.  eps stays NCHW. */,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /*

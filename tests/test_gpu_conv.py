@@ -118,6 +118,72 @@ def test_full_size_conv_config4_one_image():
     assert rel_err(out16.real[:1].float(), want[0]) < 1e-2
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("vd", [False, True])
+def test_channels_last_conv_matches_nchw_and_oracle(vd, dtype):
+    """torch.channels_last activations are read in place by the implicit-GEMM kernel (no
+    transposing pre-pass); the output keeps the memory format and equals the NCHW result."""
+    torch.manual_seed(31)
+    B, C, H, W, O = 3, 32, 18, 37, 24
+    cls = CplxConv2dVD if vd else CplxConv2d
+    m = cls(C, O, 3, padding=1, stride=(1, 2)).to(DEV).train()
+    if vd:
+        with torch.no_grad():
+            m.log_sigma2.uniform_(-8, 0)
+    m = m.to(dtype)
+    z = cplx.randn(B, C, H, W, device=DEV).to(dtype)
+    zcl = cplx.Cplx(z.real.contiguous(memory_format=torch.channels_last),
+                    z.imag.contiguous(memory_format=torch.channels_last))
+    eps = cplx.randn(B, O, 18, 19, device=DEV).to(dtype) if vd else None
+    with torch.no_grad():
+        ref = m(z, eps=eps) if vd else m(z)
+        out = m(zcl, eps=eps) if vd else m(zcl)
+    assert out.shape == ref.shape == (B, O, 18, 19)
+    assert out.real.is_contiguous(memory_format=torch.channels_last)
+    assert out.imag.is_contiguous(memory_format=torch.channels_last)
+    tol = 1e-3 if dtype == torch.float32 else 1e-2
+    assert rel_err(out.real.float(), ref.real.float().cpu()) < tol
+    assert rel_err(out.imag.float(), ref.imag.float().cpu()) < tol
+    c = lambda t: t.detach().cpu().double()
+    args = [c(z.real), c(z.imag), c(m.weight.real), c(m.weight.imag), c(m.bias.real), c(m.bias.imag)]
+    if vd:
+        want = orc.cplx_conv2d_vd(*args, c(m.log_sigma2), c(eps.real), c(eps.imag), m.stride,
+                                  m.padding, m.dilation)
+    else:
+        want = orc.cplx_conv2d(*args, m.stride, m.padding, m.dilation)
+    assert rel_err(out.real.float(), want[0]) < tol and rel_err(out.imag.float(), want[1]) < tol
+
+
+def test_channels_last_conv_fused_noise_and_layout_fallback():
+    """Fused torch-exact noise is indexed in logical NCHW order (cplx.randn draws a contiguous
+    tensor, cplx.py:544-550) whatever the activation layout; channel counts the in-place path
+    cannot take (C % 8 != 0) go through the NCHW kernels."""
+    torch.manual_seed(6)
+    layer = CplxConv2dVD(16, 8, 3, padding=1).to(DEV).train()
+    with torch.no_grad():
+        layer.log_sigma2.uniform_(-6, 1)
+    z = cplx.randn(2, 16, 9, 12, device=DEV)
+    zcl = cplx.Cplx(z.real.contiguous(memory_format=torch.channels_last),
+                    z.imag.contiguous(memory_format=torch.channels_last))
+    torch.manual_seed(42)
+    with torch.no_grad():
+        fused = layer(zcl)
+    torch.manual_seed(42)
+    eps = cplx.randn(2, 8, 9, 12, device=DEV)
+    with torch.no_grad():
+        inject = layer(zcl, eps=eps)
+        nchw = layer(z, eps=eps)
+    assert fused.real.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(fused.real, inject.real) and torch.equal(fused.imag, inject.imag)
+    assert rel_err(inject.real, nchw.real.cpu()) < 1e-3
+    m = CplxConv2d(6, 4, 3).to(DEV)
+    z6 = cplx.randn(2, 6, 8, 8, device=DEV)
+    z6cl = cplx.Cplx(z6.real.contiguous(memory_format=torch.channels_last),
+                     z6.imag.contiguous(memory_format=torch.channels_last))
+    with torch.no_grad():
+        assert torch.equal(m(z6cl).real, m(z6).real)
+
+
 def test_conv2d_vd_fused_noise_matches_device_draw():
     torch.manual_seed(5)
     layer = CplxConv2dVD(3, 4, 3, padding=1).to(DEV).train()

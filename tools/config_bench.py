@@ -85,6 +85,12 @@ def main():
                 nbytes = es * (2 * 256 * 64 * 128 * 128 + 2 * 256 * 64 * 126 * 126)
                 out.append(row(f"4 {name} 64->64 3x3 128x128 B=256 {tag}", ms, flops, nbytes,
                                "channels-last pre-pass + conv_tc_kernel (tcgen05 implicit GEMM)"))
+                zcl = cplx.Cplx(zd.real.contiguous(memory_format=torch.channels_last),
+                                zd.imag.contiguous(memory_format=torch.channels_last))
+                ms = timeit(lambda: convd(zcl), 5, 2)
+                out.append(row(f"4 {name} 64->64 3x3 128x128 B=256 {tag} channels_last in/out", ms,
+                               flops, nbytes, "conv_tc_kernel reads NHWC planes in place"))
+                del zcl
             ops.set_math_mode("simt")
             conv32, z32 = conv.float(), z
             ms = timeit(lambda: conv32(z32), 2, 1)
