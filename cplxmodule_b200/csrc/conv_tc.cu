@@ -426,7 +426,9 @@ struct ConvPCfg {
   static constexpr int OFF_XR = 0, OFF_XI = A_TILE, OFF_UV = 2 * A_TILE;
   static constexpr int STAGE_BYTES = 3 * A_TILE;   // 48 KB
   static constexpr int STAGES = 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 1024;
+  static constexpr int OFF_BIAS = 256;             // after the barriers: 8 warps x 64 floats
+  static constexpr int THREADS = 320;              // TMA warp, MMA warp, 8 epilogue warps
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + OFF_BIAS + 8 * 64 * 4;
 };
 
 __device__ __forceinline__ void conv_tile_coords(const ConvTcGeom& g, int tile, int& b, int& oh0,
@@ -441,7 +443,7 @@ __device__ __forceinline__ void conv_tile_coords(const ConvTcGeom& g, int tile, 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_xr,
                           const __grid_constant__ CUtensorMap tm_xi,
                           const __grid_constant__ CUtensorMap tm_u,
@@ -474,7 +476,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_xr,
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(bar_tfull + 8 * i, 1);
-      ptx::mbar_init(bar_tempty + 8 * i, 4);   // one arrive per epilogue warp
+      ptx::mbar_init(bar_tempty + 8 * i, 8);   // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -541,45 +543,67 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_xr,
       }
     }
   } else {
-    const int quarter = warp & 3;
+    // 8 epilogue warps: TMEM lane quarter = warp % 4, channel half = (warp - 2) / 4
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int p = quarter * 32 + lane;
     const int hh = p / g.Wt, ww = p - hh * g.Wt;
     const int64_t hw = g.Ho * g.Wo;
+    // this warp's 32 + 32 bias values, staged once per n-block and read back as broadcasts
+    float* sbias = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::OFF_BIAS) +
+                   (warp - 2) * 64;
+    int bias_n0 = -1;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int b, oh0, ow0, n0;
       conv_tile_coords(g, tile, b, oh0, ow0, n0);
+      if (n0 != bias_n0) {
+        __syncwarp();
+        const int o = n0 + half * 32 + lane;
+        float br = 0.f, bi = 0.f;
+        if (ep.b_re && o < g.O) {
+          br = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_re) + o));
+          bi = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_im) + o));
+        }
+        sbias[lane] = br, sbias[32 + lane] = bi;
+        __syncwarp();
+        bias_n0 = n0;
+      }
       const uint32_t buf = it & 1u, tph = (it >> 1) & 1u;
       const int64_t oh = oh0 + hh, ow = ow0 + ww;
       const bool pix_ok = oh < g.Ho && ow < g.Wo;
       const int64_t pix_off = static_cast<int64_t>(b) * g.O * hw + oh * g.Wo + ow;
+      const int64_t cl_off = ((static_cast<int64_t>(b) * g.Ho + oh) * g.Wo + ow) * g.O;
       ptx::mbar_wait(bar_tfull + 8 * buf, tph);
       ptx::tcgen05_fence_after();
       const uint32_t lane_base = tmem_base + buf * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 2
-      for (int c = 0; c < 8; ++c) {
-        uint32_t d1a[8], d1b[8], d2a[8], d2b[8];
-        ptx::tmem_ld_32x32b_x8(lane_base + c * 8, d1a);
-        ptx::tmem_ld_32x32b_x8(lane_base + 64 + c * 8, d1b);
-        ptx::tmem_ld_32x32b_x8(lane_base + 128 + c * 8, d2a);
-        ptx::tmem_ld_32x32b_x8(lane_base + 192 + c * 8, d2b);
-        ptx::tmem_ld_wait();
-        float re8[8], im8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int o = n0 + c * 8 + j;
-          float re = __uint_as_float(d1a[j]) - __uint_as_float(d2b[j]);
-          float im = __uint_as_float(d1b[j]) + __uint_as_float(d2a[j]);
-          if (ep.b_re && o < g.O) {
-            re += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_re) + o));
-            im += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_im) + o));
+      for (int c = 0; c < 2; ++c) {
+        const int col = half * 32 + c * 16;
+        uint32_t d1a[16], d1b[16], d2a[16], d2b[16];
+        ptx::tmem_ld_32x32b_x16(lane_base + col, d1a);          // x_re * U
+        ptx::tmem_ld_32x32b_x16(lane_base + 64 + col, d1b);     // x_re * V
+        ptx::tmem_ld_32x32b_x16(lane_base + 128 + col, d2a);    // x_im * U
+        ptx::tmem_ld_32x32b_x16(lane_base + 192 + col, d2b);    // x_im * V
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          float re8[8], im8[8];
+          const float4* br4 = reinterpret_cast<const float4*>(sbias + c * 16 + h8 * 8);
+          const float4* bi4 = reinterpret_cast<const float4*>(sbias + 32 + c * 16 + h8 * 8);
+          const float4 r0 = br4[0], r1 = br4[1], i0 = bi4[0], i1 = bi4[1];
+          const float brv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          const float biv[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = h8 * 8 + j;
+            re8[j] = __uint_as_float(d1a[k]) - __uint_as_float(d2b[k]) + brv[j];
+            im8[j] = __uint_as_float(d1b[k]) + __uint_as_float(d2a[k]) + biv[j];
           }
-          re8[j] = re, im8[j] = im;
-        }
-        if (pix_ok) {
-          const int64_t cl_off = ((static_cast<int64_t>(b) * g.Ho + oh) * g.Wo + ow) * g.O;
-          conv_store8<T>(static_cast<T*>(ep.y_re), g, ep.nhwc != 0, pix_off, hw, cl_off, n0 + c * 8, re8);
-          conv_store8<T>(static_cast<T*>(ep.y_im), g, ep.nhwc != 0, pix_off, hw, cl_off, n0 + c * 8, im8);
+          if (pix_ok) {
+            const int o0 = n0 + col + h8 * 8;
+            conv_store8<T>(static_cast<T*>(ep.y_re), g, ep.nhwc != 0, pix_off, hw, cl_off, o0, re8);
+            conv_store8<T>(static_cast<T*>(ep.y_im), g, ep.nhwc != 0, pix_off, hw, cl_off, o0, im8);
+          }
         }
       }
       ptx::tcgen05_fence_before();
@@ -763,7 +787,7 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
       CPLXK_CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ConvPCfg<T>::SMEM_BYTES));
       const unsigned grid = static_cast<unsigned>(tiles < sms ? tiles : sms);
-      pk<<<grid, 192, ConvPCfg<T>::SMEM_BYTES, st>>>(tm_xr, tm_xi, tm_u, tm_v, g, ep,
+      pk<<<grid, ConvPCfg<T>::THREADS, ConvPCfg<T>::SMEM_BYTES, st>>>(tm_xr, tm_xi, tm_u, tm_v, g, ep,
                                                      static_cast<int>(tiles));
       CPLXK_CUDA_TRY(cudaGetLastError());
       return CPLXK_OK;
