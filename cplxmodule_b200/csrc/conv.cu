@@ -167,13 +167,14 @@ conv_simt_kernel(const T* __restrict__ x_re, const T* __restrict__ x_im,
             ei = cur.next(ep.noise) * ep.noise.scale;
           }
         } else {
-          const uint64_t q = static_cast<uint64_t>(off) >> 2;
-          const int comp = static_cast<int>(off & 3);
-          float4 a = philox_fast_normal4(q, 0u, ep.noise);
-          er = (comp == 0 ? a.x : comp == 1 ? a.y : comp == 2 ? a.z : a.w) * ep.noise.scale;
           if constexpr (kCplx) {
-            float4 c = philox_fast_normal4(q, 1u, ep.noise);
-            ei = (comp == 0 ? c.x : comp == 1 ? c.y : comp == 2 ? c.z : c.w) * ep.noise.scale;
+            const float2 z = philox_fast_pair(static_cast<uint64_t>(off), ep.noise);
+            er = z.x * ep.noise.scale, ei = z.y * ep.noise.scale;
+          } else {
+            const uint64_t q = static_cast<uint64_t>(off) >> 2;
+            const int comp = static_cast<int>(off & 3);
+            float4 a = philox_fast_normal4(q, 0u, ep.noise);
+            er = (comp == 0 ? a.x : comp == 1 ? a.y : comp == 2 ? a.z : a.w) * ep.noise.scale;
           }
         }
         re = fmaf(er, sd, re);

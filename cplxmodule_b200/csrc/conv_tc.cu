@@ -173,14 +173,15 @@ struct ConvCfg {
   static constexpr int STAGES = kVD ? 3 : 2;               // VD: 1 CTA/SM, plain: 2 CTAs/SM
   static constexpr int TMEM_COLS = kVD ? 512 : 256;        // D1 128 | D2 128 | (s2 64)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 1024;
-  // VD: eight epilogue warps (two per TMEM lane quarter, 32 channels each) so that twice as
-  // many warps generate the torch-exact noise in the shadow of the MMAs
-  static constexpr int THREADS = kVD ? 320 : 192;
-  static constexpr int CH_PER_WARP = kVD ? 32 : 64;
+  // VD: sixteen epilogue warps (four per TMEM lane quarter, 16 channels each).  The kernel is
+  // bound by the torch-exact noise (one Philox-10 + Box-Muller per normal, branchy libm inside),
+  // and only more resident warps hide its fixed-latency dependency stalls.
+  static constexpr int THREADS = kVD ? 576 : 192;
+  static constexpr int CH_PER_WARP = kVD ? 16 : 64;
 };
 
 template <typename T, bool kVD>
-__global__ void __launch_bounds__((kVD ? 320 : 192), (kVD ? 1 : 2))
+__global__ void __launch_bounds__((kVD ? 576 : 192), (kVD ? 1 : 2))
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__ CUtensorMap tm_xi,
                const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_u,
                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_e,
@@ -355,12 +356,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int64_t off = pix_off + static_cast<int64_t>(n0 + cbase + trip * 8 + j) * hw;
-              const uint64_t q = static_cast<uint64_t>(off) >> 2;
-              const int comp = static_cast<int>(off & 3);
-              float4 a = philox_fast_normal4(q, 0u, ep.noise);
-              float4 bb = philox_fast_normal4(q, 1u, ep.noise);
-              nre[NCH - 8 + j] = (comp == 0 ? a.x : comp == 1 ? a.y : comp == 2 ? a.z : a.w) * ep.noise.scale;
-              nim[NCH - 8 + j] = (comp == 0 ? bb.x : comp == 1 ? bb.y : comp == 2 ? bb.z : bb.w) * ep.noise.scale;
+              const float2 z = philox_fast_pair(static_cast<uint64_t>(off), ep.noise);
+              nre[NCH - 8 + j] = z.x * ep.noise.scale;
+              nim[NCH - 8 + j] = z.y * ep.noise.scale;
             }
           }
         }

@@ -86,4 +86,15 @@ __device__ __forceinline__ float4 philox_fast_normal4(uint64_t quad, uint32_t pl
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// PHILOX_FAST, complex conv outputs: neighbouring elements of one output plane belong to
+// different threads there (a thread walks channels), so the unit is one complex element:
+// counter = (ctr_base + element, 0, 0x80000001) and ONE Box-Muller gives its (re, im) pair.
+__device__ __forceinline__ float2 philox_fast_pair(uint64_t elem, const NoiseParams& np) {
+  uint64_t ctr = np.ctr_base + elem;
+  uint4 c = make_uint4(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0u,
+                       0x80000001u);
+  uint4 r = philox4x32_10(c, PhiloxKey{np.seed_lo, np.seed_hi});
+  return _curand_box_muller(r.x, r.y);
+}
+
 }  // namespace cplxk

@@ -184,6 +184,40 @@ def test_channels_last_conv_fused_noise_and_layout_fallback():
         assert torch.equal(m(z6cl).real, m(z6).real)
 
 
+def test_conv_fast_noise_same_stream_on_both_kernels_and_unit_variance():
+    """'fast' noise for complex conv: one Philox call + one Box-Muller per complex output element,
+    indexed by the logical NCHW element -> the CUDA-core and tensor-core kernels draw the same
+    stream, and the standardised draw is CN(0, 1)."""
+    from cplxmodule_b200 import ops
+    torch.manual_seed(3)
+    layer = CplxConv2dVD(16, 24, 3, padding=1, bias=False).to(DEV).train()
+    with torch.no_grad():
+        layer.weight.real.zero_(); layer.weight.imag.zero_(); layer.log_sigma2.zero_()
+    z = cplx.Cplx(torch.ones(4, 16, 20, 33, device=DEV), torch.zeros(4, 16, 20, 33, device=DEV))
+    cb.set_noise_mode("fast")
+    try:
+        outs = {}
+        for mode in ("simt", "tensor"):
+            ops.set_math_mode(mode)
+            torch.manual_seed(77)
+            with torch.no_grad():
+                outs[mode] = layer(z)
+        ops.set_math_mode("auto")
+        with torch.no_grad():
+            again = layer(z)
+    finally:
+        ops.set_math_mode("auto")
+        cb.set_noise_mode("torch")
+    a, b = outs["simt"], outs["tensor"]
+    assert rel_err(b.real, a.real.cpu()) < 1e-3 and rel_err(b.imag, a.imag.cpu()) < 1e-3
+    assert not torch.equal(again.real, b.real)      # generator advanced
+    # interior pixels see all 9 taps x 16 channels of |x|^2 = 1, sigma2 = 1  ->  s2 = 144
+    zr, zi = b.real[:, :, 1:-1, 1:-1] / 12.0, b.imag[:, :, 1:-1, 1:-1] / 12.0
+    for plane in (zr, zi):
+        assert abs(plane.mean().item()) < 0.01 and abs(plane.var().item() - 0.5) < 0.01
+    assert abs((zr * zi).mean().item()) < 0.01
+
+
 def test_conv2d_vd_fused_noise_matches_device_draw():
     torch.manual_seed(5)
     layer = CplxConv2dVD(3, 4, 3, padding=1).to(DEV).train()

@@ -90,6 +90,12 @@ def main():
                 ms = timeit(lambda: convd(zcl), 5, 2)
                 out.append(row(f"4 {name} 64->64 3x3 128x128 B=256 {tag} channels_last in/out", ms,
                                flops, nbytes, "conv_tc_kernel reads NHWC planes in place"))
+                if cls is CplxConv2dVD:
+                    cb.set_noise_mode("fast")
+                    ms = timeit(lambda: convd(zcl), 5, 2)
+                    cb.set_noise_mode("torch")
+                    out.append(row(f"4 {name} 64->64 3x3 128x128 B=256 {tag} channels_last, fast noise",
+                                   ms, flops, nbytes, "one Philox + Box-Muller per complex element"))
                 del zcl
             ops.set_math_mode("simt")
             conv32, z32 = conv.float(), z
