@@ -450,11 +450,22 @@ int fwd_tc2_dispatch(int dtype, bool cplx, bool mix_var, const void* x_re, const
                      const void* w_re, const void* w_im, const void* q, const void* e, int64_t M,
                      int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st);
 
+// persistent CTA-pair kernel on 16-bit operands (fwd_tc3.cu)
+size_t fwd_tc3_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K);
+bool fwd_tc3_supported(int dtype, int64_t M, int64_t N, int64_t K);
+int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
+                const void* ls2, void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
+                cudaStream_t st);
+int fwd_tc3_bf16(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
+                 const void* q, const void* e, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
+                 cudaStream_t st);
+
 size_t fwd_tc_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K) {
   const size_t es = dtype == CPLXK_F32 ? 4 : 2;
   const size_t qb = (static_cast<size_t>(M) * K * es + 255) & ~static_cast<size_t>(255);
   const size_t eb = (static_cast<size_t>(N) * K * es + 255) & ~static_cast<size_t>(255);
-  return qb + eb;
+  const size_t v3 = fwd_tc3_workspace_bytes(dtype, M, N, K);
+  return qb + eb > v3 ? qb + eb : v3;
 }
 
 template <typename T, bool kCplx, bool kVD, bool kXform, int kSwz>
@@ -478,6 +489,25 @@ static int launch_tc(const void* x_re, const void* x_im, const void* w_re, const
     T* q = static_cast<T*>(workspace);
     const size_t qb = (static_cast<size_t>(M) * K * sizeof(T) + 255) & ~static_cast<size_t>(255);
     T* e = reinterpret_cast<T*>(static_cast<uint8_t*>(workspace) + qb);
+    // fp32 planes: per-row-scaled fp16 operands on kind::f16 (CPLXK_F16=0: tf32 operands as
+    // below); CPLXK_PERSIST=1 selects the persistent kernel of fwd_tc3.cu for either dtype
+    const char* f16e = std::getenv("CPLXK_F16");
+    const char* pers = std::getenv("CPLXK_PERSIST");
+    const bool persist = pers && pers[0] == '1';
+    if (fwd_tc3_supported(std::is_same<T, float>::value ? CPLXK_F32 : CPLXK_BF16, M, N, K)) {
+      if constexpr (std::is_same<T, float>::value) {
+        if (!(f16e && f16e[0] == '0'))
+          return fwd_tc3_f32(kCplx, x_re, x_im, w_re, w_im, ls2, workspace, M, N, K, ep, st);
+      } else if (persist) {
+        const int64_t work3 = (M * K + N * K) / Elem<T>::kVec;
+        const int grid3 = static_cast<int>(work3 / 256 + 1 > 148 * 16 ? 148 * 16 : work3 / 256 + 1);
+        vd_prepare_kernel<T, kCplx><<<grid3, 256, 0, st>>>(static_cast<const T*>(x_re),
+                                                         static_cast<const T*>(x_im), M * K, q,
+                                                         static_cast<const T*>(ls2), N * K, e);
+        CPLXK_CUDA_TRY(cudaGetLastError());
+        return fwd_tc3_bf16(kCplx, x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
+      }
+    }
     // CTA-pair kernel (cta_group::2): default for problems that fill a pair, CPLXK_PAIR=0 disables;
     // with fp32 planes its variance operands travel as bf16 (CPLXK_MIXVAR=0 keeps them tf32)
     const char* pe = std::getenv("CPLXK_PAIR");

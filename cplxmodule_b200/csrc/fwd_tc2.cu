@@ -7,6 +7,7 @@
 // Per CTA a pipeline stage is 3 x 16 KB + 3 x 8 KB = 72 KB instead of 96 KB, which lets the
 // 128-byte-swizzle / 3-stage schedule of the plain complex GEMM fit, and the B operands
 // cross L2 -> SM once per pair instead of once per CTA.
+#include <cstdlib>
 #include <type_traits>
 
 #include "epilogue.cuh"
@@ -18,12 +19,17 @@ namespace cplxk {
 // are all-positive and only feed sqrt(s2) * eps, so they travel as bf16 (round-to-nearest in
 // the pre-pass; the rounding errors average out over K) and that GEMM runs as kind::f16 at
 // twice the tf32 rate: 4.5 instead of 5 tf32-MMA-equivalents per k-step, smaller stages.
-template <typename T, bool kCplx, bool kMixVar>
+// kOp: 0 = operands are the planes themselves (tf32 / bf16), 1 = kMixVar, 2 = fp32 planes whose
+// mean operands arrive as per-row-scaled fp16 and variance operands as bf16 (pre-pass
+// vd_prepare_f16_kernel, fwd_tc3.cu): everything runs as kind::f16, the epilogue undoes the scales.
+template <typename T, bool kCplx, int kOp>
 struct Tc2Cfg {
-  static_assert(!kMixVar || std::is_same<T, float>::value, "mixed variance operands: fp32 planes");
-  static constexpr bool kBF16 = std::is_same<T, __nv_bfloat16>::value;
+  static constexpr bool kMixVar = kOp == 1;
+  static constexpr bool kHalfOps = kOp == 2;
+  static_assert(kOp == 0 || std::is_same<T, float>::value, "derived 16-bit operands: fp32 planes");
+  static constexpr bool kBF16 = std::is_same<T, __nv_bfloat16>::value || kHalfOps;   // kind::f16 MMAs
   static constexpr int BM = 128, BN = 128;            // per-CTA rows; N of the pair tile
-  static constexpr int BK = 128 / static_cast<int>(sizeof(T));
+  static constexpr int BK = kHalfOps ? 64 : 128 / static_cast<int>(sizeof(T));
   static constexpr int KSTEPS = 4;
   static constexpr int A_TILE = 128 * 128, B_HALF = 64 * 128;
   static constexpr int NA = kCplx ? 2 : 1;
@@ -45,16 +51,20 @@ struct Tc2Cfg {
 struct Tc2Params {
   int64_t M, N, K;
   int tiles_m2, tiles_n;   // tiles of 256 rows, 128 columns
+  int dbg;                 // CPLXK_DBG: 1 = MMAs without operand loads, 2 = loads without MMAs, 3 = no mainloop
+  const float* sx;         // kOp == 2: inverse row scales of x [M] and of W [N]
+  const float* sw;
   EpiParams ep;
 };
 
-template <typename T, bool kCplx, bool kMixVar>
+template <typename T, bool kCplx, int kOp>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__ CUtensorMap tm_xi,
                const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_wr,
                const __grid_constant__ CUtensorMap tm_wi, const __grid_constant__ CUtensorMap tm_e,
                const Tc2Params p) {
-  using C = Tc2Cfg<T, kCplx, kMixVar>;
+  using C = Tc2Cfg<T, kCplx, kOp>;
+  constexpr bool kMixVar = C::kMixVar;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -85,7 +95,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
   const int32_t m0 = tile_m * 256 + static_cast<int32_t>(rank) * 128;   // this CTA's rows
   const int32_t n0 = tile_n * C::BN;
   const int32_t nb0 = n0 + static_cast<int32_t>(rank) * 64;             // this CTA's half of B
-  const int num_kb = static_cast<int>((p.K + C::BK - 1) / C::BK);
+  const int num_kb = p.dbg == 3 ? 0 : static_cast<int>((p.K + C::BK - 1) / C::BK);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_xr);
@@ -114,7 +124,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
 
   if (warp == 0) {
     // ---------------------------------------------- TMA producer (one per CTA of the pair)
-    if (lane == 0) {
+    if (lane == 0 && p.dbg != 1) {
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % C::STAGES;
         const uint32_t ph = (kb / C::STAGES) & 1;
@@ -134,15 +144,22 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer: leader only
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc<C::kBF16>(256, C::BN, false, false);
-      constexpr uint32_t idesc_na = ptx::make_idesc<C::kBF16>(256, C::BN, true, false);
+      // a/b format field: 0 = fp16 (scaled operands), 1 = bf16, 2 = tf32
+      constexpr uint32_t fmt_fix = C::kHalfOps ? (1u << 7) | (1u << 10) : 0u;   // clears bf16 -> fp16
+      constexpr uint32_t idesc = ptx::make_idesc<C::kBF16>(256, C::BN, false, false) ^ fmt_fix;
+      constexpr uint32_t idesc_na = ptx::make_idesc<C::kBF16>(256, C::BN, true, false) ^ fmt_fix;
+      constexpr uint32_t idesc_v = ptx::make_idesc<C::kBF16>(256, C::BN, false, false);
       const uint32_t t_re = tmem_base, t_im = tmem_base + C::BN, t_s2 = tmem_base + C::NA * C::BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % C::STAGES;
         const uint32_t ph = (kb / C::STAGES) & 1;
         const uint32_t st = base + s * C::STAGE_BYTES;
-        ptx::mbar_wait(bar_full + 8 * s, ph);
+        if (p.dbg != 1) ptx::mbar_wait(bar_full + 8 * s, ph);
         ptx::tcgen05_fence_after();
+        if (p.dbg == 2) {
+          ptx::umma_commit_pair(bar_empty + 8 * s);
+          continue;
+        }
         const uint64_t a0 = ptx::make_kmajor_desc<128>(st + C::OFF_A0);
         const uint64_t a1 = ptx::make_kmajor_desc<128>(st + C::OFF_A1);
         const uint64_t aq = ptx::make_kmajor_desc<C::VAR_SWZ>(st + C::OFF_Q);
@@ -160,7 +177,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
             ptx::umma_ss_pair<C::kBF16>(t_im, ptx::desc_advance(a1, off), ptx::desc_advance(b0, off), idesc, 1u);
           }
           if constexpr (!kMixVar)
-            ptx::umma_ss_pair<C::kBF16>(t_s2, ptx::desc_advance(aq, off), ptx::desc_advance(be, off), idesc, acc);
+            ptx::umma_ss_pair<C::kBF16>(t_s2, ptx::desc_advance(aq, off), ptx::desc_advance(be, off), idesc_v, acc);
         }
         if constexpr (kMixVar) {
           constexpr uint32_t idesc_bf = ptx::make_idesc<true>(256, C::BN, false, false);
@@ -183,6 +200,8 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
     const int64_t nb = static_cast<int64_t>(n0) + half * 64;
     float nre[64], nim[kCplx ? 64 : 1];
     noise_prefetch<T, kCplx, 64>(p.ep, m, nb, nre, nim);
+    [[maybe_unused]] float sxm = 1.f;
+    if constexpr (C::kHalfOps) sxm = m < p.M ? __ldg(p.sx + m) : 1.f;
     ptx::mbar_wait(bar_accum, 0);
     ptx::tcgen05_fence_after();
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 64;
@@ -199,6 +218,12 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
         f_re[j] = __uint_as_float(r_re[j]);
         f_im[j] = kCplx ? __uint_as_float(r_im[j]) : 0.f;
         f_s2[j] = __uint_as_float(r_s2[j]);
+        if constexpr (C::kHalfOps) {   // undo the power-of-two row scales of x and W (exact)
+          const int64_t n = nb + c * 8 + j;
+          const float sc = sxm * (n < p.N ? __ldg(p.sw + n) : 1.f);
+          f_re[j] *= sc;
+          f_im[j] *= sc;
+        }
       }
       epilogue_finish<T, kCplx, 8>(p.ep, m, nb + c * 8, f_re, f_im, f_s2, &nre[c * 8],
                                    &nim[kCplx ? c * 8 : 0]);
@@ -253,13 +278,40 @@ static int plane_map2(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K
   return r == CUDA_SUCCESS ? CPLXK_OK : CPLXK_ERR_CUDA;
 }
 
-template <typename T, bool kCplx, bool kMixVar>
+// fp16 planes written by the pre-pass: box {64 elements of K, rows}, 128B swizzle
+static int half_map2(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K, int box_rows) {
+  auto enc = encode_fn2();
+  if (!enc) return CPLXK_ERR_CUDA;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(K) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CPLXK_OK : CPLXK_ERR_CUDA;
+}
+
+template <typename T, bool kCplx, int kOp>
 static int launch_tc2(const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                       const void* q, const void* e, int64_t M, int64_t N, int64_t K,
-                      const EpiParams& ep, cudaStream_t st) {
-  using C = Tc2Cfg<T, kCplx, kMixVar>;
+                      const EpiParams& ep, cudaStream_t st, const float* sx = nullptr,
+                      const float* sw = nullptr) {
+  using C = Tc2Cfg<T, kCplx, kOp>;
+  constexpr bool kMixVar = kOp == 1;
   CUtensorMap tm_xr, tm_xi, tm_q, tm_wr, tm_wi, tm_e;
   int rc;
+  if (kOp == 2) {
+    if ((rc = half_map2(&tm_xr, x_re, M, K, 128))) return rc;
+    if ((rc = half_map2(&tm_wr, w_re, N, K, 64))) return rc;
+    if ((rc = plane_map2<__nv_bfloat16>(&tm_q, q, M, K, 128, false))) return rc;
+    if ((rc = plane_map2<__nv_bfloat16>(&tm_e, e, N, K, 64, false))) return rc;
+    tm_xi = tm_xr, tm_wi = tm_wr;
+    if (kCplx) {
+      if ((rc = half_map2(&tm_xi, x_im, M, K, 128))) return rc;
+      if ((rc = half_map2(&tm_wi, w_im, N, K, 64))) return rc;
+    }
+  } else {
   if ((rc = plane_map2<T>(&tm_xr, x_re, M, K, 128, true))) return rc;
   if ((rc = plane_map2<T>(&tm_wr, w_re, N, K, 64, true))) return rc;
   if (kMixVar) {   // q / E were written as bf16 by the pre-pass: 32 K-elements = 64-byte rows
@@ -274,14 +326,18 @@ static int launch_tc2(const void* x_re, const void* x_im, const void* w_re, cons
     if ((rc = plane_map2<T>(&tm_xi, x_im, M, K, 128, true))) return rc;
     if ((rc = plane_map2<T>(&tm_wi, w_im, N, K, 64, true))) return rc;
   }
+  }
   Tc2Params p;
+  p.sx = sx, p.sw = sw;
   p.M = M, p.N = N, p.K = K;
   p.tiles_m2 = static_cast<int>((M + 255) / 256);
   p.tiles_n = static_cast<int>((N + C::BN - 1) / C::BN);
   p.ep = ep;
+  const char* dbg_env = std::getenv("CPLXK_DBG");
+  p.dbg = dbg_env ? std::atoi(dbg_env) : 0;
   const int64_t pairs = static_cast<int64_t>(p.tiles_m2) * p.tiles_n;
   if (2 * pairs > 0x7fffffff) return CPLXK_ERR_UNSUPPORTED;
-  auto kern = fwd_tc2_kernel<T, kCplx, kMixVar>;
+  auto kern = fwd_tc2_kernel<T, kCplx, kOp>;
   CPLXK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   kern<<<static_cast<unsigned>(2 * pairs), C::THREADS, C::SMEM_BYTES, st>>>(tm_xr, tm_xi, tm_q, tm_wr,
                                                                           tm_wi, tm_e, p);
@@ -294,17 +350,26 @@ int fwd_tc2_dispatch(int dtype, bool cplx, bool mix_var, const void* x_re, const
                      int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st) {
   if (dtype == CPLXK_F32) {
     if (mix_var) {
-      if (cplx) return launch_tc2<float, true, true>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
-      return launch_tc2<float, false, true>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
+      if (cplx) return launch_tc2<float, true, 1>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
+      return launch_tc2<float, false, 1>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
     }
-    if (cplx) return launch_tc2<float, true, false>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
-    return launch_tc2<float, false, false>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
+    if (cplx) return launch_tc2<float, true, 0>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
+    return launch_tc2<float, false, 0>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
   }
   if (dtype == CPLXK_BF16) {
-    if (cplx) return launch_tc2<__nv_bfloat16, true, false>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
-    return launch_tc2<__nv_bfloat16, false, false>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
+    if (cplx) return launch_tc2<__nv_bfloat16, true, 0>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
+    return launch_tc2<__nv_bfloat16, false, 0>(x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
   }
   return CPLXK_ERR_BADARG;
+}
+
+// fp32 planes, operands already converted to per-row-scaled fp16 (+ bf16 variance operands)
+int fwd_tc2_half_dispatch(bool cplx, const void* xh_re, const void* xh_im, const void* wh_re,
+                          const void* wh_im, const void* q, const void* e, const float* sx,
+                          const float* sw, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
+                          cudaStream_t st) {
+  if (cplx) return launch_tc2<float, true, 2>(xh_re, xh_im, wh_re, wh_im, q, e, M, N, K, ep, st, sx, sw);
+  return launch_tc2<float, false, 2>(xh_re, xh_im, wh_re, wh_im, q, e, M, N, K, ep, st, sx, sw);
 }
 
 }  // namespace cplxk

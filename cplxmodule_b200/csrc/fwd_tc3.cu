@@ -1,0 +1,664 @@
+// Persistent CTA-pair (cta_group::2) fused variational forward on 16-bit operands.
+//
+//   re += a_re U^T - a_im V^T ,  im += a_re V^T + a_im U^T      (cplxmodule/cplx.py:641-642)
+//   s2 += |x|^2 exp(log_sigma2)^T                               (nn/relevance/complex/base.py:50-54)
+//   y   = mu * (sx[m] sw[n]) + b + eps sqrt(max(s2, 1e-8))      (complex/base.py:56, cplx.py:644-646)
+//
+// Differences to fwd_tc2.cu (one tile pair per cluster, direct global stores):
+//  * fp32 planes do NOT run as kind::tf32.  A pre-pass (vd_prepare_f16_kernel below) rescales
+//    every row of x and of W by a power of two so its largest entry sits at 2^13 and writes it
+//    as fp16: same 11-bit significand as tf32 (round-to-nearest), no range problem because the
+//    scale is per row, and kind::f16 runs at twice the tf32 rate.  The epilogue undoes the two
+//    scales (exact: powers of two).  bf16 planes are consumed as they are.
+//  * One cluster per SM pair loops over output tiles (static round-robin).  The TMA producers run
+//    ahead into the ring while the epilogue warps drain TMEM, so the next tile's MMAs start the
+//    moment the accumulators are released (tmem_empty barrier) -- no prologue / pipeline refill
+//    per tile.
+//  * The epilogue writes through a 64B/32B-swizzled shared-memory slab and TMA stores: full-line
+//    asynchronous writes that overlap the next tile's mainloop, instead of one 16-byte store per
+//    lane per row.
+//
+// Warps (320 threads / CTA): 0 = TMA producer, 1 = MMA issuer (leader CTA), 2..9 = noise
+// prefetch (during the mainloop, registers) + drain.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <type_traits>
+
+#include "epilogue.cuh"
+#include "ptx.cuh"
+
+namespace cplxk {
+
+template <typename OutT, bool kCplx>
+struct Tc3Cfg {
+  static constexpr int BN = 128;
+  static constexpr int BK = 32;                       // 16-bit elements: 64-byte rows (SW64)
+  static constexpr int KSTEPS = 2;                    // K = 16 per MMA
+  static constexpr int A_TILE = 128 * 64, B_HALF = 64 * 64;
+  static constexpr int NA = kCplx ? 2 : 1;
+  static constexpr int OFF_A0 = 0, OFF_A1 = A_TILE, OFF_Q = NA * A_TILE;
+  static constexpr int OFF_B0 = OFF_Q + A_TILE, OFF_B1 = OFF_B0 + B_HALF;
+  static constexpr int OFF_E = OFF_B0 + NA * B_HALF;
+  static constexpr int STAGE_BYTES = OFF_E + B_HALF;  // 36 KB complex, 24 KB real
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int CH = 16;                       // columns per drain chunk
+  static constexpr int ROW_BYTES = CH * static_cast<int>(sizeof(OutT));   // 64 (f32) / 32 (bf16)
+  static constexpr int SLAB_PLANE = 32 * ROW_BYTES;
+  static constexpr int SLAB_BYTES = NA * SLAB_PLANE;
+  static constexpr int STG_BYTES = EPI_WARPS * SLAB_BYTES;
+  static constexpr int AUX_BYTES = 4096;              // barriers, tmem slot, per-tile column vectors
+  static constexpr int AVAIL = 227 * 1024 - 1024 - AUX_BYTES - STG_BYTES;
+  static constexpr int STAGES = AVAIL / STAGE_BYTES > 8 ? 8 : AVAIL / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + AUX_BYTES + 1024;
+  static constexpr int NACC = NA + 1;
+  static constexpr int TMEM_COLS = NACC * BN <= 256 ? 256 : 512;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static_assert(STAGES >= 3, "ring too shallow");
+};
+
+struct Tc3Params {
+  int64_t M, N, K;
+  int tiles_m2, tiles_n;   // tiles of 256 rows, 128 columns
+  int f16;                 // mean operands are fp16 (else bf16)
+  int dbg;                 // CPLXK_DBG: 1 = MMAs without loads, 2 = loads without MMAs, 3 = no mainloop
+  const float* sx;         // [M] inverse row scales of x (nullable)
+  const float* sw;         // [N] inverse row scales of W (nullable)
+  EpiParams ep;
+};
+
+namespace ptx {
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int32_t c0,
+                                             int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+// kind::f16 instruction descriptor with explicit operand format (0 = fp16, 1 = bf16)
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t fmt, int M, int N, bool neg_a) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (neg_a ? (1u << 13) : 0u) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+}  // namespace ptx
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <typename OutT, bool kCplx>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__ CUtensorMap tm_xi,
+               const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_wr,
+               const __grid_constant__ CUtensorMap tm_wi, const __grid_constant__ CUtensorMap tm_e,
+               const __grid_constant__ CUtensorMap tm_yr, const __grid_constant__ CUtensorMap tm_yi,
+               const Tc3Params p) {
+  using C = Tc3Cfg<OutT, kCplx>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t stg = base + C::STAGES * C::STAGE_BYTES;          // 1024-aligned
+  const uint32_t aux = stg + C::STG_BYTES;
+  // aux: full[8] empty[8] accum_full tmem_empty tmem_slot | colvec[2][3][128] floats at +1024
+  const uint32_t bar_full = aux, bar_empty = aux + 64, bar_accum = aux + 128, bar_tfree = aux + 136;
+  const uint32_t tmem_slot = aux + 144;
+  uint8_t* aux_ptr = smem + C::STAGES * C::STAGE_BYTES + C::STG_BYTES;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(aux_ptr + 144);
+  float* colvec = reinterpret_cast<float*>(aux_ptr + 1024);         // [2][3][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_tiles = p.tiles_m2 * p.tiles_n;
+  const int num_kb = p.dbg == 3 ? 0 : static_cast<int>((p.K + C::BK - 1) / C::BK);
+
+  auto decode_tile = [&](int t, int& tile_m, int& tile_n) {
+    constexpr int kGroup = 6;   // 256-row tiles per raster group
+    const int per_group = kGroup * p.tiles_n;
+    const int g = t / per_group;
+    const int first_m = g * kGroup;
+    const int gsize = (p.tiles_m2 - first_m) < kGroup ? (p.tiles_m2 - first_m) : kGroup;
+    const int r = t - g * per_group;
+    tile_m = first_m + r % gsize;
+    tile_n = r / gsize;
+  };
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_xr);
+    ptx::prefetch_tensormap(&tm_wr);
+    ptx::prefetch_tensormap(&tm_q);
+    ptx::prefetch_tensormap(&tm_e);
+    ptx::prefetch_tensormap(&tm_yr);
+    if constexpr (kCplx) {
+      ptx::prefetch_tensormap(&tm_xi);
+      ptx::prefetch_tensormap(&tm_wi);
+      ptx::prefetch_tensormap(&tm_yi);
+    }
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);    // only the leader's is used
+      ptx::mbar_init(bar_empty + 8 * s, 1);
+    }
+    ptx::mbar_init(bar_accum, 1);
+    ptx::mbar_init(bar_tfree, 2 * C::EPI_WARPS);   // only the leader's is used
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------- TMA producer
+    if (lane == 0 && p.dbg != 1) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        int tile_m, tile_n;
+        decode_tile(t, tile_m, tile_n);
+        const int32_t m0 = tile_m * 256 + static_cast<int32_t>(rank) * 128;
+        const int32_t nb0 = tile_n * C::BN + static_cast<int32_t>(rank) * 64;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          const uint32_t fb = bar_full + 8 * s;
+          const uint32_t st = base + s * C::STAGE_BYTES;
+          if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * C::STAGE_BYTES);
+          const int32_t k0 = kb * C::BK;
+          ptx::tma_load_2d_pair(st + C::OFF_A0, &tm_xr, fb, k0, m0);
+          if constexpr (kCplx) ptx::tma_load_2d_pair(st + C::OFF_A1, &tm_xi, fb, k0, m0);
+          ptx::tma_load_2d_pair(st + C::OFF_Q, &tm_q, fb, k0, m0);
+          ptx::tma_load_2d_pair(st + C::OFF_B0, &tm_wr, fb, k0, nb0);
+          if constexpr (kCplx) ptx::tma_load_2d_pair(st + C::OFF_B1, &tm_wi, fb, k0, nb0);
+          ptx::tma_load_2d_pair(st + C::OFF_E, &tm_e, fb, k0, nb0);
+          if (++s == C::STAGES) s = 0, ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // --------------------------------------------------------- MMA issuer: leader CTA only
+    if (leader && lane == 0) {
+      const uint32_t fmt = p.f16 ? 0u : 1u;
+      const uint32_t idesc = ptx::make_idesc_f16(fmt, 256, C::BN, false);
+      const uint32_t idesc_na = ptx::make_idesc_f16(fmt, 256, C::BN, true);
+      constexpr uint32_t idesc_var = ptx::make_idesc_f16(1u, 256, C::BN, false);
+      const uint32_t t_re = tmem_base, t_im = tmem_base + C::BN, t_s2 = tmem_base + C::NA * C::BN;
+      int s = 0;
+      uint32_t ph = 0, tile_par = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, tile_par ^= 1u) {
+        ptx::mbar_wait_cluster(bar_tfree, tile_par ^ 1u);   // previous tile drained by both CTAs
+        ptx::tcgen05_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const uint32_t st = base + s * C::STAGE_BYTES;
+          if (p.dbg != 1) ptx::mbar_wait(bar_full + 8 * s, ph);
+          ptx::tcgen05_fence_after();
+          if (p.dbg != 2) {
+            const uint64_t a0 = ptx::make_kmajor_desc<64>(st + C::OFF_A0);
+            const uint64_t a1 = ptx::make_kmajor_desc<64>(st + C::OFF_A1);
+            const uint64_t aq = ptx::make_kmajor_desc<64>(st + C::OFF_Q);
+            const uint64_t b0 = ptx::make_kmajor_desc<64>(st + C::OFF_B0);
+            const uint64_t b1 = ptx::make_kmajor_desc<64>(st + C::OFF_B1);
+            const uint64_t be = ptx::make_kmajor_desc<64>(st + C::OFF_E);
+#pragma unroll
+            for (int k = 0; k < C::KSTEPS; ++k) {
+              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+              const uint32_t off = k * 32;
+              ptx::umma_ss_pair<true>(t_re, ptx::desc_advance(a0, off), ptx::desc_advance(b0, off), idesc, acc);
+              if constexpr (kCplx) {
+                ptx::umma_ss_pair<true>(t_re, ptx::desc_advance(a1, off), ptx::desc_advance(b1, off), idesc_na, 1u);
+                ptx::umma_ss_pair<true>(t_im, ptx::desc_advance(a0, off), ptx::desc_advance(b1, off), idesc, acc);
+                ptx::umma_ss_pair<true>(t_im, ptx::desc_advance(a1, off), ptx::desc_advance(b0, off), idesc, 1u);
+              }
+              ptx::umma_ss_pair<true>(t_s2, ptx::desc_advance(aq, off), ptx::desc_advance(be, off), idesc_var, acc);
+            }
+          }
+          ptx::umma_commit_pair(bar_empty + 8 * s);   // frees the stage in BOTH CTAs
+          if (++s == C::STAGES) s = 0, ph ^= 1u;
+        }
+        ptx::umma_commit_pair(bar_accum);             // accumulators complete, both CTAs
+      }
+    }
+  } else {
+    // ------------------------------------ 8 epilogue warps: noise prefetch, then drain + TMA store
+    // (little is kept live across noise_prefetch: it needs ~all of the 168 registers)
+    uint32_t tile_par = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, tile_par ^= 1u) {
+      float nre[64], nim[kCplx ? 64 : 1];
+      {
+        int tile_m, tile_n;
+        decode_tile(t, tile_m, tile_n);
+        const int64_t m = static_cast<int64_t>(tile_m) * 256 + rank * 128 + (warp & 3) * 32 + lane;
+        const int64_t nb = static_cast<int64_t>(tile_n) * C::BN + ((warp - 2) >> 2) * 64;
+        noise_prefetch<OutT, kCplx, 64>(p.ep, m, nb, nre, nim);
+      }
+      const int quarter = warp & 3;
+      const int half = (warp - 2) >> 2;
+      const int te = threadIdx.x - 64;                       // 0..255
+      const uint32_t slab = stg + (warp - 2) * C::SLAB_BYTES;
+      const uint32_t tfree_remote = ptx::mapa_u32(bar_tfree, 0);
+      constexpr uint32_t kSwzMask = sizeof(OutT) == 4 ? 3u : 1u;
+      int tile_m, tile_n;
+      decode_tile(t, tile_m, tile_n);
+      const int32_t m0 = tile_m * 256 + static_cast<int32_t>(rank) * 128;
+      const int32_t n0 = tile_n * C::BN;
+      const int64_t m = static_cast<int64_t>(m0) + quarter * 32 + lane;
+      const int64_t nb = static_cast<int64_t>(n0) + half * 64;
+
+      // per-tile column vectors (bias, inverse weight-row scale) -> smem, double buffered
+      float* cv = colvec + tile_par * 3 * 128;
+      if (te < 128) {
+        const int64_t n = static_cast<int64_t>(n0) + te;
+        const bool ok = n < p.N;
+        const OutT* br = static_cast<const OutT*>(p.ep.b_re);
+        const OutT* bi = static_cast<const OutT*>(p.ep.b_im);
+        cv[te] = (ok && br) ? Elem<OutT>::to_f(__ldg(br + n)) : 0.f;
+        cv[128 + te] = (kCplx && ok && bi) ? Elem<OutT>::to_f(__ldg(bi + n)) : 0.f;
+        cv[256 + te] = (ok && p.sw) ? __ldg(p.sw + n) : 1.f;
+      }
+      const float sxm = (p.sx && m < p.M) ? __ldg(p.sx + m) : 1.f;
+      ptx::named_bar_sync(1, 32 * C::EPI_WARPS);            // column vectors visible
+
+      ptx::mbar_wait(bar_accum, tile_par);
+      ptx::tcgen05_fence_after();
+      const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 64;
+      const float* cvb = cv + half * 64;
+#pragma unroll
+      for (int c = 0; c < 64 / C::CH; ++c) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {       // two 8-column halves of the chunk (register budget)
+          const int col = c * 16 + h * 8;
+          uint32_t r_re[8], r_im[8], r_s2[8];
+          ptx::tmem_ld_32x32b_x8(lane_base + col, r_re);
+          if constexpr (kCplx) ptx::tmem_ld_32x32b_x8(lane_base + C::BN + col, r_im);
+          ptx::tmem_ld_32x32b_x8(lane_base + C::NA * C::BN + col, r_s2);
+          ptx::tmem_ld_wait();
+          if (c == 64 / C::CH - 1 && h == 1) {   // last TMEM read of this warp: hand the accumulators back
+            ptx::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(tfree_remote);
+          }
+          float f_re[8], f_im[8], f_s2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float sc = sxm * cvb[256 + col + j];
+            f_s2[j] = __uint_as_float(r_s2[j]);
+            const float sd = sqrtf(fmaxf(f_s2[j], 1e-8f));
+            f_re[j] = fmaf(nre[col + j], sd, fmaf(__uint_as_float(r_re[j]), sc, cvb[col + j]));
+            if constexpr (kCplx)
+              f_im[j] = fmaf(nim[col + j], sd, fmaf(__uint_as_float(r_im[j]), sc, cvb[128 + col + j]));
+          }
+          if (p.ep.s2_out && m < p.M && nb + col < p.N) {
+            const int64_t ncol = nb + col;
+            const int nvalid = (p.N - ncol) < 8 ? static_cast<int>(p.N - ncol) : 8;
+            store_s2_run<OutT, 8>(p.ep, m * p.N, ncol, nvalid, f_s2);
+          }
+          if (h == 0) {   // the slab is free once the previous chunk's TMA store has read it
+            if (lane == 0) ptx::bulk_wait_read0();
+            __syncwarp();
+          }
+          if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const uint32_t off = lane * C::ROW_BYTES + (2 * h + q) * 16;
+              const uint32_t a = slab + (off ^ (((off >> 7) & kSwzMask) << 4));
+              ptx::st_shared_v4(a, __float_as_uint(f_re[4 * q]), __float_as_uint(f_re[4 * q + 1]),
+                                __float_as_uint(f_re[4 * q + 2]), __float_as_uint(f_re[4 * q + 3]));
+              if constexpr (kCplx)
+                ptx::st_shared_v4(a + C::SLAB_PLANE, __float_as_uint(f_im[4 * q]),
+                                  __float_as_uint(f_im[4 * q + 1]), __float_as_uint(f_im[4 * q + 2]),
+                                  __float_as_uint(f_im[4 * q + 3]));
+            }
+          } else {
+            const uint32_t off = lane * C::ROW_BYTES + h * 16;
+            const uint32_t a = slab + (off ^ (((off >> 7) & kSwzMask) << 4));
+            ptx::st_shared_v4(a, pack_bf16x2(f_re[0], f_re[1]), pack_bf16x2(f_re[2], f_re[3]),
+                              pack_bf16x2(f_re[4], f_re[5]), pack_bf16x2(f_re[6], f_re[7]));
+            if constexpr (kCplx)
+              ptx::st_shared_v4(a + C::SLAB_PLANE, pack_bf16x2(f_im[0], f_im[1]),
+                                pack_bf16x2(f_im[2], f_im[3]), pack_bf16x2(f_im[4], f_im[5]),
+                                pack_bf16x2(f_im[6], f_im[7]));
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int32_t c0 = static_cast<int32_t>(nb) + c * 16;
+          const int32_t c1 = m0 + quarter * 32;
+          ptx::tma_store_2d(&tm_yr, slab, c0, c1);
+          if constexpr (kCplx) ptx::tma_store_2d(&tm_yi, slab + C::SLAB_PLANE, c0, c1);
+          ptx::bulk_commit();
+        }
+      }
+    }
+    if (lane == 0) ptx::bulk_wait0();
+    ptx::tcgen05_fence_before();
+  }
+
+  ptx::cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer may still use it
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ fp32 -> fp16 operand pre-pass
+// One block per row of x ([0, M)) or of W ([M, M + N)).  Row maximum -> power-of-two scale that
+// puts it in [2^13, 2^14) -> fp16 planes; the row's inverse scale goes to isx / isw.  The same
+// pass writes the variance-GEMM operands |x|^2 and exp(log_sigma2) as bf16 (unscaled: bf16 has
+// fp32's range).  K % 8 == 0.
+template <bool kCplx>
+__global__ void __launch_bounds__(256)
+vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im, int64_t M,
+                      const float* __restrict__ w_re, const float* __restrict__ w_im,
+                      const float* __restrict__ ls2, int64_t N, int64_t K,
+                      __half* __restrict__ xh_re, __half* __restrict__ xh_im,
+                      __nv_bfloat16* __restrict__ q, __half* __restrict__ wh_re,
+                      __half* __restrict__ wh_im, __nv_bfloat16* __restrict__ e,
+                      float* __restrict__ isx, float* __restrict__ isw) {
+  constexpr int kCache = 4;                  // 8-element groups per thread kept in registers (K <= 8192)
+  __shared__ float red[8];
+  const int tid = threadIdx.x;
+  for (int64_t row = blockIdx.x; row < M + N; row += gridDim.x) {
+    const bool is_x = row < M;
+    const int64_t r = is_x ? row : row - M;
+    const float* pr = (is_x ? x_re : w_re) + r * K;
+    const float* pi = kCplx ? (is_x ? x_im : w_im) + r * K : nullptr;
+    __half* hr = (is_x ? xh_re : wh_re) + r * K;
+    __half* hi = kCplx ? (is_x ? xh_im : wh_im) + r * K : nullptr;
+    __nv_bfloat16* dv = (is_x ? q : e) + r * K;
+    const float* pl = is_x ? nullptr : ls2 + r * K;
+
+    float cr[kCache][8], ci[kCache][8];
+    float amax = 0.f;
+#pragma unroll
+    for (int it = 0; it < kCache; ++it) {
+      const int64_t k = (static_cast<int64_t>(it) * 256 + tid) * 8;
+      if (k < K) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(pr + k));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(pr + k + 4));
+        cr[it][0] = a0.x, cr[it][1] = a0.y, cr[it][2] = a0.z, cr[it][3] = a0.w;
+        cr[it][4] = a1.x, cr[it][5] = a1.y, cr[it][6] = a1.z, cr[it][7] = a1.w;
+        if constexpr (kCplx) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(pi + k));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(pi + k + 4));
+          ci[it][0] = b0.x, ci[it][1] = b0.y, ci[it][2] = b0.z, ci[it][3] = b0.w;
+          ci[it][4] = b1.x, ci[it][5] = b1.y, ci[it][6] = b1.z, ci[it][7] = b1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          amax = fmaxf(amax, fabsf(cr[it][j]));
+          if constexpr (kCplx) amax = fmaxf(amax, fabsf(ci[it][j]));
+        }
+      }
+    }
+    for (int64_t k = (static_cast<int64_t>(kCache) * 256 + tid) * 8; k < K; k += 2048) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(pr + k + 4 * h));
+        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(a.x), fabsf(a.y))), fmaxf(fabsf(a.z), fabsf(a.w)));
+        if constexpr (kCplx) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(pi + k + 4 * h));
+          amax = fmaxf(fmaxf(amax, fmaxf(fabsf(b.x), fabsf(b.y))), fmaxf(fabsf(b.z), fabsf(b.w)));
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    __syncthreads();                          // red[] of the previous row fully consumed
+    if ((tid & 31) == 0) red[tid >> 5] = amax;
+    __syncthreads();
+    amax = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) amax = fmaxf(amax, red[w]);
+    // scale = 2^s with amax * 2^s in [2^13, 2^14); s clamped so that 2^s and 2^-s are normal
+    const int ex = static_cast<int>((__float_as_uint(amax) >> 23) & 0xffu) - 127;
+    int s = 13 - ex;
+    if (amax == 0.f || ex == 128) s = 0;      // empty row, or inf / nan: leave as is
+    s = s > 126 ? 126 : s;
+    const float scale = __uint_as_float(static_cast<uint32_t>(s + 127) << 23);
+    if (tid == 0) (is_x ? isx : isw)[r] = __uint_as_float(static_cast<uint32_t>(127 - s) << 23);
+
+    auto emit = [&](int64_t k, const float (&vr)[8], const float (&vi)[8]) {
+      uint4 o;
+      __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(vr[2 * j] * scale, vr[2 * j + 1] * scale);
+      *reinterpret_cast<uint4*>(hr + k) = o;
+      if constexpr (kCplx) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(vi[2 * j] * scale, vi[2 * j + 1] * scale);
+        *reinterpret_cast<uint4*>(hi + k) = o;
+      }
+      __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&o);
+      if (is_x) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float q0 = vr[2 * j] * vr[2 * j], q1 = vr[2 * j + 1] * vr[2 * j + 1];
+          if constexpr (kCplx) q0 = fmaf(vi[2 * j], vi[2 * j], q0), q1 = fmaf(vi[2 * j + 1], vi[2 * j + 1], q1);
+          b[j] = __floats2bfloat162_rn(q0, q1);
+        }
+      } else {
+        const float4 l0 = __ldg(reinterpret_cast<const float4*>(pl + k));
+        const float4 l1 = __ldg(reinterpret_cast<const float4*>(pl + k + 4));
+        b[0] = __floats2bfloat162_rn(__expf(l0.x), __expf(l0.y));
+        b[1] = __floats2bfloat162_rn(__expf(l0.z), __expf(l0.w));
+        b[2] = __floats2bfloat162_rn(__expf(l1.x), __expf(l1.y));
+        b[3] = __floats2bfloat162_rn(__expf(l1.z), __expf(l1.w));
+      }
+      *reinterpret_cast<uint4*>(dv + k) = o;
+    };
+#pragma unroll
+    for (int it = 0; it < kCache; ++it) {
+      const int64_t k = (static_cast<int64_t>(it) * 256 + tid) * 8;
+      if (k < K) emit(k, cr[it], ci[it]);
+    }
+    for (int64_t k = (static_cast<int64_t>(kCache) * 256 + tid) * 8; k < K; k += 2048) {
+      float vr[8], vi[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(pr + k + 4 * h));
+        vr[4 * h] = a.x, vr[4 * h + 1] = a.y, vr[4 * h + 2] = a.z, vr[4 * h + 3] = a.w;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (kCplx) b = __ldg(reinterpret_cast<const float4*>(pi + k + 4 * h));
+        vi[4 * h] = b.x, vi[4 * h + 1] = b.y, vi[4 * h + 2] = b.z, vi[4 * h + 3] = b.w;
+      }
+      emit(k, vr, vi);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled3 encode_fn3() {
+  static PFN_encodeTiled3 fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult r;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) != cudaSuccess ||
+        r != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled3>(q);
+  }
+  return fn;
+}
+
+// plane [rows, cols] row-major, element size es -> box {box_c, box_r}; swizzle = box_c * es bytes
+static int map2d(CUtensorMap* out, CUtensorMapDataType dt, size_t es, const void* ptr, int64_t rows,
+                 int64_t cols, int box_c, int box_r) {
+  auto enc = encode_fn3();
+  if (!enc) return CPLXK_ERR_CUDA;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(cols) * es};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_r)};
+  cuuint32_t estr[2] = {1u, 1u};
+  const size_t inner = box_c * es;
+  const CUtensorMapSwizzle sw = inner == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : inner == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                              : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CPLXK_OK : CPLXK_ERR_CUDA;
+}
+
+struct Tc3Operands {
+  const void *a_re, *a_im, *q, *b_re, *b_im, *e;   // 16-bit planes [M,K] / [N,K]
+  const float *sx, *sw;
+  bool f16;
+};
+
+template <typename OutT, bool kCplx>
+static int launch_tc3(const Tc3Operands& o, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
+                      cudaStream_t st) {
+  using C = Tc3Cfg<OutT, kCplx>;
+  CUtensorMap tm_xr, tm_xi, tm_q, tm_wr, tm_wi, tm_e, tm_yr, tm_yi;
+  const CUtensorMapDataType dt_op = o.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt_bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt_out = std::is_same<OutT, float>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                                      : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  int rc;
+  if ((rc = map2d(&tm_xr, dt_op, 2, o.a_re, M, K, C::BK, 128))) return rc;
+  if ((rc = map2d(&tm_wr, dt_op, 2, o.b_re, N, K, C::BK, 64))) return rc;
+  if ((rc = map2d(&tm_q, dt_bf, 2, o.q, M, K, C::BK, 128))) return rc;
+  if ((rc = map2d(&tm_e, dt_bf, 2, o.e, N, K, C::BK, 64))) return rc;
+  if ((rc = map2d(&tm_yr, dt_out, sizeof(OutT), ep.y_re, M, N, C::CH, 32))) return rc;
+  tm_xi = tm_xr, tm_wi = tm_wr, tm_yi = tm_yr;
+  if (kCplx) {
+    if ((rc = map2d(&tm_xi, dt_op, 2, o.a_im, M, K, C::BK, 128))) return rc;
+    if ((rc = map2d(&tm_wi, dt_op, 2, o.b_im, N, K, C::BK, 64))) return rc;
+    if ((rc = map2d(&tm_yi, dt_out, sizeof(OutT), ep.y_im, M, N, C::CH, 32))) return rc;
+  }
+  Tc3Params p;
+  p.M = M, p.N = N, p.K = K;
+  p.tiles_m2 = static_cast<int>((M + 255) / 256);
+  p.tiles_n = static_cast<int>((N + C::BN - 1) / C::BN);
+  p.f16 = o.f16 ? 1 : 0;
+  const char* dbg_env = std::getenv("CPLXK_DBG");
+  p.dbg = dbg_env ? std::atoi(dbg_env) : 0;
+  p.sx = o.sx, p.sw = o.sw;
+  p.ep = ep;
+  const int64_t pairs = static_cast<int64_t>(p.tiles_m2) * p.tiles_n;
+  if (pairs > 0x3fffffff) return CPLXK_ERR_UNSUPPORTED;
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    CPLXK_CUDA_TRY(cudaGetDevice(&dev));
+    CPLXK_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int64_t clusters = sm_count / 2;
+  if (clusters < 1) clusters = 1;
+  if (clusters > pairs) clusters = pairs;
+  auto kern = fwd_tc3_kernel<OutT, kCplx>;
+  CPLXK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  kern<<<static_cast<unsigned>(2 * clusters), C::THREADS, C::SMEM_BYTES, st>>>(
+      tm_xr, tm_xi, tm_q, tm_wr, tm_wi, tm_e, tm_yr, tm_yi, p);
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+// workspace of the fp32-plane path: xh_re, xh_im, q [M,K]; wh_re, wh_im, E [N,K] (2 bytes each),
+// isx [M], isw [N] floats
+size_t fwd_tc3_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K) {
+  if (dtype != CPLXK_F32) return 0;
+  return 3 * align256(static_cast<size_t>(M) * K * 2) + 3 * align256(static_cast<size_t>(N) * K * 2) +
+         align256(static_cast<size_t>(M) * 4) + align256(static_cast<size_t>(N) * 4);
+}
+
+bool fwd_tc3_supported(int dtype, int64_t M, int64_t N, int64_t K) {
+  const int64_t es = dtype == CPLXK_F32 ? 4 : 2;
+  return M > 128 && K % 8 == 0 && (N * es) % 16 == 0;
+}
+
+int fwd_tc2_half_dispatch(bool cplx, const void* xh_re, const void* xh_im, const void* wh_re,
+                          const void* wh_im, const void* q, const void* e, const float* sx,
+                          const float* sw, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
+                          cudaStream_t st);
+
+// fp32 planes: pre-pass to scaled fp16, then the CTA-pair kernel of fwd_tc2.cu on kind::f16
+// (CPLXK_PERSIST=1: the persistent kernel above).
+int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
+                const void* ls2, void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
+                cudaStream_t st) {
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const size_t xb = align256(static_cast<size_t>(M) * K * 2), wb = align256(static_cast<size_t>(N) * K * 2);
+  __half* xh_re = reinterpret_cast<__half*>(ws);
+  __half* xh_im = reinterpret_cast<__half*>(ws + xb);
+  __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(ws + 2 * xb);
+  __half* wh_re = reinterpret_cast<__half*>(ws + 3 * xb);
+  __half* wh_im = reinterpret_cast<__half*>(ws + 3 * xb + wb);
+  __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(ws + 3 * xb + 2 * wb);
+  float* isx = reinterpret_cast<float*>(ws + 3 * xb + 3 * wb);
+  float* isw = reinterpret_cast<float*>(ws + 3 * xb + 3 * wb + align256(static_cast<size_t>(M) * 4));
+  const int64_t rows = M + N;
+  const int grid = static_cast<int>(rows > 148 * 8 ? 148 * 8 : rows);
+  if (cplx)
+    vd_prepare_f16_kernel<true><<<grid, 256, 0, st>>>(
+        static_cast<const float*>(x_re), static_cast<const float*>(x_im), M,
+        static_cast<const float*>(w_re), static_cast<const float*>(w_im),
+        static_cast<const float*>(ls2), N, K, xh_re, xh_im, q, wh_re, wh_im, e, isx, isw);
+  else
+    vd_prepare_f16_kernel<false><<<grid, 256, 0, st>>>(
+        static_cast<const float*>(x_re), nullptr, M, static_cast<const float*>(w_re), nullptr,
+        static_cast<const float*>(ls2), N, K, xh_re, nullptr, q, wh_re, nullptr, e, isx, isw);
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  const char* pe = std::getenv("CPLXK_PERSIST");
+  if (!(pe && pe[0] == '1'))
+    return fwd_tc2_half_dispatch(cplx, xh_re, xh_im, wh_re, wh_im, q, e, isx, isw, M, N, K, ep, st);
+  Tc3Operands o{xh_re, xh_im, q, wh_re, wh_im, e, isx, isw, true};
+  return cplx ? launch_tc3<float, true>(o, M, N, K, ep, st) : launch_tc3<float, false>(o, M, N, K, ep, st);
+}
+
+// bf16 planes: operands as they are; q / E (bf16) were written by the caller's pre-pass.
+int fwd_tc3_bf16(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
+                 const void* q, const void* e, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
+                 cudaStream_t st) {
+  Tc3Operands o{x_re, x_im, q, w_re, w_im, e, nullptr, nullptr, false};
+  return cplx ? launch_tc3<__nv_bfloat16, true>(o, M, N, K, ep, st)
+              : launch_tc3<__nv_bfloat16, false>(o, M, N, K, ep, st);
+}
+
+}  // namespace cplxk
