@@ -18,7 +18,9 @@ bool fwd_tc_supported(int dtype, bool cplx, const void* x_re, const void* x_im, 
                       const void* w_im, const void* ls2, int64_t M, int64_t N, int64_t K);
 int fwd_tc_dispatch(int dtype, bool cplx, bool vd, int swz, const void* x_re, const void* x_im,
                     const void* w_re, const void* w_im, const void* ls2, void* workspace,
-                    int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st);
+                    int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st,
+                    const KlFuse& kl);
+bool fwd_tc_fuses_kl(int dtype, int64_t M, int64_t N, int64_t K);
 size_t fwd_tc_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K);
 
 static int check_arch() {
@@ -58,7 +60,9 @@ static int forward_common(bool vd, const void* x_re, const void* x_im, const voi
                           const void* eps_re, const void* eps_im, int noise, uint64_t seed,
                           uint64_t offset, uint32_t threads, void* y_re, void* y_im, int64_t M,
                           int64_t N, int64_t K, int dtype, int math, void* s2_out, void* workspace,
-                          size_t workspace_bytes, void* stream) {
+                          size_t workspace_bytes, void* stream, KlFuse kl = KlFuse{-1, nullptr, nullptr},
+                          int* kl_done = nullptr) {
+  if (kl_done) *kl_done = 0;
   if (!x_re || !w_re || !y_re || M < 0 || N < 0 || K < 0) return CPLXK_ERR_BADARG;
   const bool cplx = (x_im != nullptr);
   if (cplx != (w_im != nullptr) || cplx != (y_im != nullptr)) return CPLXK_ERR_BADARG;
@@ -91,8 +95,12 @@ static int forward_common(bool vd, const void* x_re, const void* x_im, const voi
       if (!aligned16(workspace)) return CPLXK_ERR_ALIGN;
       if (workspace_bytes < fwd_tc_workspace_bytes(dtype, M, N, K)) return CPLXK_ERR_WORKSPACE;
     }
-    return fwd_tc_dispatch(dtype, cplx, vd, swz, x_re, x_im, w_re, w_im, ls2, vd ? workspace : nullptr,
-                           M, N, K, ep, st);
+    const bool fuse = vd && workspace && kl.kind >= 0 && kl.sum && kl.ws && fwd_tc_fuses_kl(dtype, M, N, K);
+    if (!fuse) kl.kind = -1;
+    rc = fwd_tc_dispatch(dtype, cplx, vd, swz, x_re, x_im, w_re, w_im, ls2, vd ? workspace : nullptr,
+                         M, N, K, ep, st, kl);
+    if (rc == CPLXK_OK && fuse && kl_done) *kl_done = 1;
+    return rc;
   }
   return fwd_simt_dispatch(dtype, cplx, vd, x_re, x_im, w_re, w_im, ls2, M, N, K, ep, st);
 }
@@ -156,6 +164,30 @@ extern "C" int cplxk_linear_vd_fwd(const void* x_re, const void* x_im, const voi
   return forward_common(true, x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise,
                         seed, offset, philox_threads, y_re, y_im, M, N, K, dtype, math, s2_out,
                         workspace, workspace_bytes, stream);
+}
+
+extern "C" int cplxk_linear_vd_fwd_kl(const void* x_re, const void* x_im, const void* w_re,
+                                      const void* w_im, const void* b_re, const void* b_im,
+                                      const void* log_sigma2, const void* eps_re, const void* eps_im,
+                                      int noise, uint64_t seed, uint64_t offset,
+                                      uint32_t philox_threads, void* y_re, void* y_im, int64_t M,
+                                      int64_t N, int64_t K, int dtype, int math, void* s2_out,
+                                      void* workspace, size_t workspace_bytes, int kl_kind,
+                                      float* kl_sum, void* kl_workspace, size_t kl_workspace_bytes,
+                                      int* kl_done, void* stream) {
+  if (kl_done) *kl_done = 0;
+  KlFuse kl{-1, nullptr, nullptr};
+  if (kl_kind >= 0) {
+    const bool cplx_kind = kl_kind == CPLXK_KL_CPLX_VD || kl_kind == CPLXK_KL_CPLX_ARD;
+    if (kl_kind > CPLXK_KL_CPLX_ARD || cplx_kind != (w_im != nullptr) || !kl_sum || !kl_done)
+      return CPLXK_ERR_BADARG;
+    if (!kl_workspace || kl_workspace_bytes < cplxk_kl_workspace_bytes()) return CPLXK_ERR_WORKSPACE;
+    if (!aligned16(kl_workspace)) return CPLXK_ERR_ALIGN;
+    kl = KlFuse{kl_kind, kl_sum, kl_workspace};
+  }
+  return forward_common(true, x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise,
+                        seed, offset, philox_threads, y_re, y_im, M, N, K, dtype, math, s2_out,
+                        workspace, workspace_bytes, stream, kl, kl_done);
 }
 
 extern "C" size_t cplxk_linear_vd_workspace_bytes(int64_t M, int64_t N, int64_t K, int dtype) {

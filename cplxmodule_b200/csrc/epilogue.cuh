@@ -22,6 +22,14 @@ struct EpiParams {
   NoiseParams noise;
 };
 
+// optional by-product of the variational forward: the layer's KL sum, evaluated by the operand
+// pre-pass on the weight rows it reads anyway (kind < 0: not requested)
+struct KlFuse {
+  int kind;
+  float* sum;   // device float
+  void* ws;     // KlWorkspace
+};
+
 template <typename T, int C>
 __device__ __forceinline__ void store_s2_run(const EpiParams& p, int64_t row_off, int64_t n0,
                                              int nvalid, const float (&s2)[C]) {

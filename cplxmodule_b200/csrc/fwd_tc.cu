@@ -455,7 +455,7 @@ size_t fwd_tc3_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K);
 bool fwd_tc3_supported(int dtype, int64_t M, int64_t N, int64_t K);
 int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                 const void* ls2, void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
-                cudaStream_t st);
+                cudaStream_t st, int kl_kind, float* kl_sum, void* kl_ws);
 int fwd_tc3_bf16(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                  const void* q, const void* e, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
                  cudaStream_t st);
@@ -471,7 +471,7 @@ size_t fwd_tc_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K) {
 template <typename T, bool kCplx, bool kVD, bool kXform, int kSwz>
 static int launch_tc(const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                      const void* ls2, void* workspace, int64_t M, int64_t N, int64_t K,
-                     const EpiParams& ep, cudaStream_t st) {
+                     const EpiParams& ep, cudaStream_t st, const KlFuse& kl) {
   using C = TcCfg<T, kCplx, kVD, kXform, kSwz>;
   CUtensorMap tm_xr, tm_xi, tm_wr, tm_wi, tm_ls, tm_q;
   int rc;
@@ -490,14 +490,19 @@ static int launch_tc(const void* x_re, const void* x_im, const void* w_re, const
     const size_t qb = (static_cast<size_t>(M) * K * sizeof(T) + 255) & ~static_cast<size_t>(255);
     T* e = reinterpret_cast<T*>(static_cast<uint8_t*>(workspace) + qb);
     // fp32 planes: per-row-scaled fp16 operands on kind::f16 (CPLXK_F16=0: tf32 operands as
-    // below); CPLXK_PERSIST=1 selects the persistent kernel of fwd_tc3.cu for either dtype
+    // below); the persistent kernel of fwd_tc3.cu is the default for either dtype
+    // (CPLXK_PERSIST=0: one tile pair per cluster, fwd_tc2.cu)
     const char* f16e = std::getenv("CPLXK_F16");
     const char* pers = std::getenv("CPLXK_PERSIST");
-    const bool persist = pers && pers[0] == '1';
-    if (fwd_tc3_supported(std::is_same<T, float>::value ? CPLXK_F32 : CPLXK_BF16, M, N, K)) {
+    const bool persist = !(pers && pers[0] == '0');
+    // bf16 variance operands: their rounding errors (2^-9 each) average out over K; for a
+    // handful of terms they do not, so short reductions keep tf32 everywhere
+    const bool short_k = K < 64;
+    if (!short_k && fwd_tc3_supported(std::is_same<T, float>::value ? CPLXK_F32 : CPLXK_BF16, M, N, K)) {
       if constexpr (std::is_same<T, float>::value) {
         if (!(f16e && f16e[0] == '0'))
-          return fwd_tc3_f32(kCplx, x_re, x_im, w_re, w_im, ls2, workspace, M, N, K, ep, st);
+          return fwd_tc3_f32(kCplx, x_re, x_im, w_re, w_im, ls2, workspace, M, N, K, ep, st,
+                             kl.kind, kl.sum, kl.ws);
       } else if (persist) {
         const int64_t work3 = (M * K + N * K) / Elem<T>::kVec;
         const int grid3 = static_cast<int>(work3 / 256 + 1 > 148 * 16 ? 148 * 16 : work3 / 256 + 1);
@@ -513,7 +518,7 @@ static int launch_tc(const void* x_re, const void* x_im, const void* w_re, const
     const char* pe = std::getenv("CPLXK_PAIR");
     const bool use_pair = (pe ? (pe[0] == '1') : true) && M > 128;
     const char* me = std::getenv("CPLXK_MIXVAR");
-    const bool mix_var = use_pair && std::is_same<T, float>::value && (K % 8 == 0) &&
+    const bool mix_var = use_pair && std::is_same<T, float>::value && (K % 8 == 0) && !short_k &&
                          (me ? (me[0] == '1') : true);
     const int64_t work = (M * K + N * K) / (mix_var ? 8 : Elem<T>::kVec);
     const int grid = static_cast<int>(work / 256 + 1 > 148 * 16 ? 148 * 16 : work / 256 + 1);
@@ -553,6 +558,12 @@ static int launch_tc(const void* x_re, const void* x_im, const void* w_re, const
   return CPLXK_OK;
 }
 
+// true when fwd_tc_dispatch(vd, workspace) will also produce the layer's KL sum (pre-pass fusion)
+bool fwd_tc_fuses_kl(int dtype, int64_t M, int64_t N, int64_t K) {
+  const char* f16e = std::getenv("CPLXK_F16");
+  return dtype == CPLXK_F32 && !(f16e && f16e[0] == '0') && K >= 64 && fwd_tc3_supported(dtype, M, N, K);
+}
+
 bool fwd_tc_supported(int dtype, bool cplx, const void* x_re, const void* x_im, const void* w_re,
                       const void* w_im, const void* ls2, int64_t M, int64_t N, int64_t K) {
   const int64_t es = dtype == CPLXK_F32 ? 4 : 2;
@@ -567,9 +578,10 @@ bool fwd_tc_supported(int dtype, bool cplx, const void* x_re, const void* x_im, 
 
 int fwd_tc_dispatch(int dtype, bool cplx, bool vd, int swz, const void* x_re, const void* x_im,
                     const void* w_re, const void* w_im, const void* ls2, void* workspace,
-                    int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st) {
+                    int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st,
+                    const KlFuse& kl) {
   const bool xform = vd && workspace == nullptr;
-#define CPLXK_TC_ARGS x_re, x_im, w_re, w_im, ls2, workspace, M, N, K, ep, st
+#define CPLXK_TC_ARGS x_re, x_im, w_re, w_im, ls2, workspace, M, N, K, ep, st, kl
 #define CPLXK_TC_CASE(T, SW)                                                                   \
   if (cplx && vd && xform) return launch_tc<T, true, true, true, SW>(CPLXK_TC_ARGS);           \
   if (cplx && vd) return launch_tc<T, true, true, false, SW>(CPLXK_TC_ARGS);                   \

@@ -4,7 +4,7 @@
 //   s2 += |x|^2 exp(log_sigma2)^T                               (nn/relevance/complex/base.py:50-54)
 //   y   = mu * (sx[m] sw[n]) + b + eps sqrt(max(s2, 1e-8))      (complex/base.py:56, cplx.py:644-646)
 //
-// Differences to fwd_tc2.cu (one tile pair per cluster, direct global stores):
+// Differences to fwd_tc2.cu (one tile pair per cluster):
 //  * fp32 planes do NOT run as kind::tf32.  A pre-pass (vd_prepare_f16_kernel below) rescales
 //    every row of x and of W by a power of two so its largest entry sits at 2^13 and writes it
 //    as fp16: same 11-bit significand as tf32 (round-to-nearest), no range problem because the
@@ -12,11 +12,11 @@
 //    scales (exact: powers of two).  bf16 planes are consumed as they are.
 //  * One cluster per SM pair loops over output tiles (static round-robin).  The TMA producers run
 //    ahead into the ring while the epilogue warps drain TMEM, so the next tile's MMAs start the
-//    moment the accumulators are released (tmem_empty barrier) -- no prologue / pipeline refill
-//    per tile.
-//  * The epilogue writes through a 64B/32B-swizzled shared-memory slab and TMA stores: full-line
-//    asynchronous writes that overlap the next tile's mainloop, instead of one 16-byte store per
-//    lane per row.
+//    moment the accumulators are released (tmem_empty barrier): no prologue, TMEM allocation or
+//    pipeline refill per tile.
+//  * The drain is short: each epilogue thread folds accumulator, scales, bias and its prefetched
+//    noise IN PLACE into the registers that held the noise, releases TMEM after its last
+//    tcgen05.ld, and only then issues the global stores, which trail into the next mainloop.
 //
 // Warps (320 threads / CTA): 0 = TMA producer, 1 = MMA issuer (leader CTA), 2..9 = noise
 // prefetch (during the mainloop, registers) + drain.
@@ -26,6 +26,7 @@
 #include <type_traits>
 
 #include "epilogue.cuh"
+#include "kl_math.cuh"
 #include "ptx.cuh"
 
 namespace cplxk {
@@ -33,24 +34,19 @@ namespace cplxk {
 template <typename OutT, bool kCplx>
 struct Tc3Cfg {
   static constexpr int BN = 128;
-  static constexpr int BK = 32;                       // 16-bit elements: 64-byte rows (SW64)
-  static constexpr int KSTEPS = 2;                    // K = 16 per MMA
-  static constexpr int A_TILE = 128 * 64, B_HALF = 64 * 64;
+  static constexpr int BK = 64;                       // 16-bit elements: 128-byte rows (SW128)
+  static constexpr int KSTEPS = 4;                    // K = 16 per MMA
+  static constexpr int A_TILE = 128 * 128, B_HALF = 64 * 128;
   static constexpr int NA = kCplx ? 2 : 1;
   static constexpr int OFF_A0 = 0, OFF_A1 = A_TILE, OFF_Q = NA * A_TILE;
   static constexpr int OFF_B0 = OFF_Q + A_TILE, OFF_B1 = OFF_B0 + B_HALF;
   static constexpr int OFF_E = OFF_B0 + NA * B_HALF;
-  static constexpr int STAGE_BYTES = OFF_E + B_HALF;  // 36 KB complex, 24 KB real
+  static constexpr int STAGE_BYTES = OFF_E + B_HALF;  // 72 KB complex, 48 KB real
   static constexpr int EPI_WARPS = 8;
-  static constexpr int CH = 16;                       // columns per drain chunk
-  static constexpr int ROW_BYTES = CH * static_cast<int>(sizeof(OutT));   // 64 (f32) / 32 (bf16)
-  static constexpr int SLAB_PLANE = 32 * ROW_BYTES;
-  static constexpr int SLAB_BYTES = NA * SLAB_PLANE;
-  static constexpr int STG_BYTES = EPI_WARPS * SLAB_BYTES;
   static constexpr int AUX_BYTES = 4096;              // barriers, tmem slot, per-tile column vectors
-  static constexpr int AVAIL = 227 * 1024 - 1024 - AUX_BYTES - STG_BYTES;
+  static constexpr int AVAIL = 227 * 1024 - 1024 - AUX_BYTES;
   static constexpr int STAGES = AVAIL / STAGE_BYTES > 8 ? 8 : AVAIL / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + AUX_BYTES + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;
   static constexpr int NACC = NA + 1;
   static constexpr int TMEM_COLS = NACC * BN <= 256 ? 256 : 512;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
@@ -120,24 +116,41 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// 64 consecutive outputs of one row, 16-byte vector stores when the row segment allows
+template <typename T>
+__device__ __forceinline__ void store_run64(T* dst, const float (&v)[64], int nvalid) {
+  constexpr int V = Elem<T>::kVec;
+  if (nvalid == 64 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+#pragma unroll
+    for (int c = 0; c < 64 / V; ++c) {
+      Vec16<T> o;
+#pragma unroll
+      for (int j = 0; j < V; ++j) o.v[j] = v[c * V + j];
+      o.store(dst + c * V);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 64; ++j)
+      if (j < nvalid) dst[j] = Elem<T>::from_f(v[j]);
+  }
+}
+
 template <typename OutT, bool kCplx>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__ CUtensorMap tm_xi,
                const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_wr,
                const __grid_constant__ CUtensorMap tm_wi, const __grid_constant__ CUtensorMap tm_e,
-               const __grid_constant__ CUtensorMap tm_yr, const __grid_constant__ CUtensorMap tm_yi,
                const Tc3Params p) {
   using C = Tc3Cfg<OutT, kCplx>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t stg = base + C::STAGES * C::STAGE_BYTES;          // 1024-aligned
-  const uint32_t aux = stg + C::STG_BYTES;
+  const uint32_t aux = base + C::STAGES * C::STAGE_BYTES;
   // aux: full[8] empty[8] accum_full tmem_empty tmem_slot | colvec[2][3][128] floats at +1024
   const uint32_t bar_full = aux, bar_empty = aux + 64, bar_accum = aux + 128, bar_tfree = aux + 136;
   const uint32_t tmem_slot = aux + 144;
-  uint8_t* aux_ptr = smem + C::STAGES * C::STAGE_BYTES + C::STG_BYTES;
+  uint8_t* aux_ptr = smem + C::STAGES * C::STAGE_BYTES;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(aux_ptr + 144);
   float* colvec = reinterpret_cast<float*>(aux_ptr + 1024);         // [2][3][128]
 
@@ -164,11 +177,9 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
     ptx::prefetch_tensormap(&tm_wr);
     ptx::prefetch_tensormap(&tm_q);
     ptx::prefetch_tensormap(&tm_e);
-    ptx::prefetch_tensormap(&tm_yr);
     if constexpr (kCplx) {
       ptx::prefetch_tensormap(&tm_xi);
       ptx::prefetch_tensormap(&tm_wi);
-      ptx::prefetch_tensormap(&tm_yi);
     }
     for (int s = 0; s < C::STAGES; ++s) {
       ptx::mbar_init(bar_full + 8 * s, 1);    // only the leader's is used
@@ -231,12 +242,12 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
           if (p.dbg != 1) ptx::mbar_wait(bar_full + 8 * s, ph);
           ptx::tcgen05_fence_after();
           if (p.dbg != 2) {
-            const uint64_t a0 = ptx::make_kmajor_desc<64>(st + C::OFF_A0);
-            const uint64_t a1 = ptx::make_kmajor_desc<64>(st + C::OFF_A1);
-            const uint64_t aq = ptx::make_kmajor_desc<64>(st + C::OFF_Q);
-            const uint64_t b0 = ptx::make_kmajor_desc<64>(st + C::OFF_B0);
-            const uint64_t b1 = ptx::make_kmajor_desc<64>(st + C::OFF_B1);
-            const uint64_t be = ptx::make_kmajor_desc<64>(st + C::OFF_E);
+            const uint64_t a0 = ptx::make_kmajor_desc<128>(st + C::OFF_A0);
+            const uint64_t a1 = ptx::make_kmajor_desc<128>(st + C::OFF_A1);
+            const uint64_t aq = ptx::make_kmajor_desc<128>(st + C::OFF_Q);
+            const uint64_t b0 = ptx::make_kmajor_desc<128>(st + C::OFF_B0);
+            const uint64_t b1 = ptx::make_kmajor_desc<128>(st + C::OFF_B1);
+            const uint64_t be = ptx::make_kmajor_desc<128>(st + C::OFF_E);
 #pragma unroll
             for (int k = 0; k < C::KSTEPS; ++k) {
               const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
@@ -272,9 +283,7 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
       const int quarter = warp & 3;
       const int half = (warp - 2) >> 2;
       const int te = threadIdx.x - 64;                       // 0..255
-      const uint32_t slab = stg + (warp - 2) * C::SLAB_BYTES;
       const uint32_t tfree_remote = ptx::mapa_u32(bar_tfree, 0);
-      constexpr uint32_t kSwzMask = sizeof(OutT) == 4 ? 3u : 1u;
       int tile_m, tile_n;
       decode_tile(t, tile_m, tile_n);
       const int32_t m0 = tile_m * 256 + static_cast<int32_t>(rank) * 128;
@@ -301,74 +310,41 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
       const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 64;
       const float* cvb = cv + half * 64;
 #pragma unroll
-      for (int c = 0; c < 64 / C::CH; ++c) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {       // two 8-column halves of the chunk (register budget)
-          const int col = c * 16 + h * 8;
-          uint32_t r_re[8], r_im[8], r_s2[8];
-          ptx::tmem_ld_32x32b_x8(lane_base + col, r_re);
-          if constexpr (kCplx) ptx::tmem_ld_32x32b_x8(lane_base + C::BN + col, r_im);
-          ptx::tmem_ld_32x32b_x8(lane_base + C::NA * C::BN + col, r_s2);
-          ptx::tmem_ld_wait();
-          if (c == 64 / C::CH - 1 && h == 1) {   // last TMEM read of this warp: hand the accumulators back
-            ptx::tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_cluster(tfree_remote);
-          }
-          float f_re[8], f_im[8], f_s2[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float sc = sxm * cvb[256 + col + j];
-            f_s2[j] = __uint_as_float(r_s2[j]);
-            const float sd = sqrtf(fmaxf(f_s2[j], 1e-8f));
-            f_re[j] = fmaf(nre[col + j], sd, fmaf(__uint_as_float(r_re[j]), sc, cvb[col + j]));
-            if constexpr (kCplx)
-              f_im[j] = fmaf(nim[col + j], sd, fmaf(__uint_as_float(r_im[j]), sc, cvb[128 + col + j]));
-          }
-          if (p.ep.s2_out && m < p.M && nb + col < p.N) {
-            const int64_t ncol = nb + col;
-            const int nvalid = (p.N - ncol) < 8 ? static_cast<int>(p.N - ncol) : 8;
-            store_s2_run<OutT, 8>(p.ep, m * p.N, ncol, nvalid, f_s2);
-          }
-          if (h == 0) {   // the slab is free once the previous chunk's TMA store has read it
-            if (lane == 0) ptx::bulk_wait_read0();
-            __syncwarp();
-          }
-          if constexpr (sizeof(OutT) == 4) {
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const uint32_t off = lane * C::ROW_BYTES + (2 * h + q) * 16;
-              const uint32_t a = slab + (off ^ (((off >> 7) & kSwzMask) << 4));
-              ptx::st_shared_v4(a, __float_as_uint(f_re[4 * q]), __float_as_uint(f_re[4 * q + 1]),
-                                __float_as_uint(f_re[4 * q + 2]), __float_as_uint(f_re[4 * q + 3]));
-              if constexpr (kCplx)
-                ptx::st_shared_v4(a + C::SLAB_PLANE, __float_as_uint(f_im[4 * q]),
-                                  __float_as_uint(f_im[4 * q + 1]), __float_as_uint(f_im[4 * q + 2]),
-                                  __float_as_uint(f_im[4 * q + 3]));
-            }
-          } else {
-            const uint32_t off = lane * C::ROW_BYTES + h * 16;
-            const uint32_t a = slab + (off ^ (((off >> 7) & kSwzMask) << 4));
-            ptx::st_shared_v4(a, pack_bf16x2(f_re[0], f_re[1]), pack_bf16x2(f_re[2], f_re[3]),
-                              pack_bf16x2(f_re[4], f_re[5]), pack_bf16x2(f_re[6], f_re[7]));
-            if constexpr (kCplx)
-              ptx::st_shared_v4(a + C::SLAB_PLANE, pack_bf16x2(f_im[0], f_im[1]),
-                                pack_bf16x2(f_im[2], f_im[3]), pack_bf16x2(f_im[4], f_im[5]),
-                                pack_bf16x2(f_im[6], f_im[7]));
-          }
+      for (int c = 0; c < 8; ++c) {
+        const int col = c * 8;
+        uint32_t r_re[8], r_im[8], r_s2[8];
+        ptx::tmem_ld_32x32b_x8(lane_base + col, r_re);
+        if constexpr (kCplx) ptx::tmem_ld_32x32b_x8(lane_base + C::BN + col, r_im);
+        ptx::tmem_ld_32x32b_x8(lane_base + C::NA * C::BN + col, r_s2);
+        ptx::tmem_ld_wait();
+        if (c == 7) {   // last TMEM read of this warp: hand the accumulators back to the MMA issuer
+          ptx::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(tfree_remote);
         }
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          const int32_t c0 = static_cast<int32_t>(nb) + c * 16;
-          const int32_t c1 = m0 + quarter * 32;
-          ptx::tma_store_2d(&tm_yr, slab, c0, c1);
-          if constexpr (kCplx) ptx::tma_store_2d(&tm_yi, slab + C::SLAB_PLANE, c0, c1);
-          ptx::bulk_commit();
+        float f_s2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float sc = sxm * cvb[256 + col + j];
+          f_s2[j] = __uint_as_float(r_s2[j]);
+          const float sd = sqrtf(fmaxf(f_s2[j], 1e-8f));
+          nre[col + j] = fmaf(nre[col + j], sd, fmaf(__uint_as_float(r_re[j]), sc, cvb[col + j]));
+          if constexpr (kCplx)
+            nim[col + j] = fmaf(nim[col + j], sd, fmaf(__uint_as_float(r_im[j]), sc, cvb[128 + col + j]));
+        }
+        if (p.ep.s2_out && m < p.M && nb + col < p.N) {
+          const int64_t ncol = nb + col;
+          const int nvalid = (p.N - ncol) < 8 ? static_cast<int>(p.N - ncol) : 8;
+          store_s2_run<OutT, 8>(p.ep, m * p.N, ncol, nvalid, f_s2);
         }
       }
+      // TMEM is released; the stores trail into the next tile's mainloop
+      if (m < p.M && nb < p.N) {
+        const int nvalid = (p.N - nb) < 64 ? static_cast<int>(p.N - nb) : 64;
+        store_run64<OutT>(static_cast<OutT*>(p.ep.y_re) + m * p.N + nb, nre, nvalid);
+        if constexpr (kCplx) store_run64<OutT>(static_cast<OutT*>(p.ep.y_im) + m * p.N + nb, nim, nvalid);
+      }
     }
-    if (lane == 0) ptx::bulk_wait0();
     ptx::tcgen05_fence_before();
   }
 
@@ -392,9 +368,13 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
                       __half* __restrict__ xh_re, __half* __restrict__ xh_im,
                       __nv_bfloat16* __restrict__ q, __half* __restrict__ wh_re,
                       __half* __restrict__ wh_im, __nv_bfloat16* __restrict__ e,
-                      float* __restrict__ isx, float* __restrict__ isw) {
+                      float* __restrict__ isx, float* __restrict__ isw, int kl_kind,
+                      float* __restrict__ kl_sum, KlWorkspace* __restrict__ kl_ws) {
   constexpr int kCache = 4;                  // 8-element groups per thread kept in registers (K <= 8192)
   __shared__ float red[8];
+  __shared__ double kl_sh[kKlThreads / 32];
+  __shared__ bool kl_last;
+  float kl_acc = 0.f;                        // KL penalty of the weight rows this thread converts
   const int tid = threadIdx.x;
   for (int64_t row = blockIdx.x; row < M + N; row += gridDim.x) {
     const bool is_x = row < M;
@@ -478,6 +458,11 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
       } else {
         const float4 l0 = __ldg(reinterpret_cast<const float4*>(pl + k));
         const float4 l1 = __ldg(reinterpret_cast<const float4*>(pl + k + 4));
+        if (kl_kind >= 0) {   // the weights and log_sigma2 are in registers anyway: KL for free
+          const float l[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) kl_acc += penalty_any(kl_kind, vr[j], kCplx ? vi[j] : 0.f, l[j]);
+        }
         b[0] = __floats2bfloat162_rn(__expf(l0.x), __expf(l0.y));
         b[1] = __floats2bfloat162_rn(__expf(l0.z), __expf(l0.w));
         b[2] = __floats2bfloat162_rn(__expf(l1.x), __expf(l1.y));
@@ -502,6 +487,11 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
       }
       emit(k, vr, vi);
     }
+  }
+  if (kl_kind >= 0) {
+    __syncthreads();
+    const double bsum = block_sum(static_cast<double>(kl_acc), kl_sh);
+    grid_sum_finish(bsum, kl_ws, kl_sum, 1.0, kl_sh, &kl_last);
   }
 }
 
@@ -553,22 +543,18 @@ template <typename OutT, bool kCplx>
 static int launch_tc3(const Tc3Operands& o, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
                       cudaStream_t st) {
   using C = Tc3Cfg<OutT, kCplx>;
-  CUtensorMap tm_xr, tm_xi, tm_q, tm_wr, tm_wi, tm_e, tm_yr, tm_yi;
+  CUtensorMap tm_xr, tm_xi, tm_q, tm_wr, tm_wi, tm_e;
   const CUtensorMapDataType dt_op = o.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const CUtensorMapDataType dt_bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  const CUtensorMapDataType dt_out = std::is_same<OutT, float>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-                                                                      : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   int rc;
   if ((rc = map2d(&tm_xr, dt_op, 2, o.a_re, M, K, C::BK, 128))) return rc;
   if ((rc = map2d(&tm_wr, dt_op, 2, o.b_re, N, K, C::BK, 64))) return rc;
   if ((rc = map2d(&tm_q, dt_bf, 2, o.q, M, K, C::BK, 128))) return rc;
   if ((rc = map2d(&tm_e, dt_bf, 2, o.e, N, K, C::BK, 64))) return rc;
-  if ((rc = map2d(&tm_yr, dt_out, sizeof(OutT), ep.y_re, M, N, C::CH, 32))) return rc;
-  tm_xi = tm_xr, tm_wi = tm_wr, tm_yi = tm_yr;
+  tm_xi = tm_xr, tm_wi = tm_wr;
   if (kCplx) {
     if ((rc = map2d(&tm_xi, dt_op, 2, o.a_im, M, K, C::BK, 128))) return rc;
     if ((rc = map2d(&tm_wi, dt_op, 2, o.b_im, N, K, C::BK, 64))) return rc;
-    if ((rc = map2d(&tm_yi, dt_out, sizeof(OutT), ep.y_im, M, N, C::CH, 32))) return rc;
   }
   Tc3Params p;
   p.M = M, p.N = N, p.K = K;
@@ -593,7 +579,7 @@ static int launch_tc3(const Tc3Operands& o, int64_t M, int64_t N, int64_t K, con
   auto kern = fwd_tc3_kernel<OutT, kCplx>;
   CPLXK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   kern<<<static_cast<unsigned>(2 * clusters), C::THREADS, C::SMEM_BYTES, st>>>(
-      tm_xr, tm_xi, tm_q, tm_wr, tm_wi, tm_e, tm_yr, tm_yi, p);
+      tm_xr, tm_xi, tm_q, tm_wr, tm_wi, tm_e, p);
   CPLXK_CUDA_TRY(cudaGetLastError());
   return CPLXK_OK;
 }
@@ -610,7 +596,8 @@ size_t fwd_tc3_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K) {
 
 bool fwd_tc3_supported(int dtype, int64_t M, int64_t N, int64_t K) {
   const int64_t es = dtype == CPLXK_F32 ? 4 : 2;
-  return M > 128 && K % 8 == 0 && (N * es) % 16 == 0;
+  (void)es;
+  return M > 128 && K % 8 == 0;
 }
 
 int fwd_tc2_half_dispatch(bool cplx, const void* xh_re, const void* xh_im, const void* wh_re,
@@ -619,10 +606,10 @@ int fwd_tc2_half_dispatch(bool cplx, const void* xh_re, const void* xh_im, const
                           cudaStream_t st);
 
 // fp32 planes: pre-pass to scaled fp16, then the CTA-pair kernel of fwd_tc2.cu on kind::f16
-// (CPLXK_PERSIST=1: the persistent kernel above).
+// (CPLXK_PERSIST=0) or, by default, the persistent kernel above.
 int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                 const void* ls2, void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
-                cudaStream_t st) {
+                cudaStream_t st, int kl_kind, float* kl_sum, void* kl_ws) {
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const size_t xb = align256(static_cast<size_t>(M) * K * 2), wb = align256(static_cast<size_t>(N) * K * 2);
   __half* xh_re = reinterpret_cast<__half*>(ws);
@@ -634,19 +621,23 @@ int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re,
   float* isx = reinterpret_cast<float*>(ws + 3 * xb + 3 * wb);
   float* isw = reinterpret_cast<float*>(ws + 3 * xb + 3 * wb + align256(static_cast<size_t>(M) * 4));
   const int64_t rows = M + N;
-  const int grid = static_cast<int>(rows > 148 * 8 ? 148 * 8 : rows);
+  const int grid = static_cast<int>(rows > 148 * 8 ? 148 * 8 : rows);   // <= kKlMaxBlocks partials
+  if (!kl_sum || !kl_ws) kl_kind = -1;
+  auto kws = static_cast<KlWorkspace*>(kl_ws);
   if (cplx)
     vd_prepare_f16_kernel<true><<<grid, 256, 0, st>>>(
         static_cast<const float*>(x_re), static_cast<const float*>(x_im), M,
         static_cast<const float*>(w_re), static_cast<const float*>(w_im),
-        static_cast<const float*>(ls2), N, K, xh_re, xh_im, q, wh_re, wh_im, e, isx, isw);
+        static_cast<const float*>(ls2), N, K, xh_re, xh_im, q, wh_re, wh_im, e, isx, isw, kl_kind,
+        kl_sum, kws);
   else
     vd_prepare_f16_kernel<false><<<grid, 256, 0, st>>>(
         static_cast<const float*>(x_re), nullptr, M, static_cast<const float*>(w_re), nullptr,
-        static_cast<const float*>(ls2), N, K, xh_re, nullptr, q, wh_re, nullptr, e, isx, isw);
+        static_cast<const float*>(ls2), N, K, xh_re, nullptr, q, wh_re, nullptr, e, isx, isw, kl_kind,
+        kl_sum, kws);
   CPLXK_CUDA_TRY(cudaGetLastError());
   const char* pe = std::getenv("CPLXK_PERSIST");
-  if (!(pe && pe[0] == '1'))
+  if (pe && pe[0] == '0')
     return fwd_tc2_half_dispatch(cplx, xh_re, xh_im, wh_re, wh_im, q, e, isx, isw, M, N, K, ep, st);
   Tc3Operands o{xh_re, xh_im, q, wh_re, wh_im, e, isx, isw, true};
   return cplx ? launch_tc3<float, true>(o, M, N, K, ep, st) : launch_tc3<float, false>(o, M, N, K, ep, st);

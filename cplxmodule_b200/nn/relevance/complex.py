@@ -33,7 +33,11 @@ class _CplxGaussianMixin:
 
     def _penalty_reduced(self, reduction):
         w = self.weight
-        return ops.kl(self._kl_kind, w.real, w.imag, self.log_sigma2, reduction)
+        pre = None
+        cache = self.__dict__.get("_kl_cache")
+        if cache is not None and reduction in ("sum", "mean"):
+            pre = cache.take((w.real, w.imag, self.log_sigma2))
+        return ops.kl(self._kl_kind, w.real, w.imag, self.log_sigma2, reduction, precomputed=pre)
 
     def relevance(self, *, threshold, **kwargs):
         w = self.weight
@@ -60,8 +64,14 @@ class CplxLinearGaussian(_CplxGaussianMixin, CplxLinear):
         w, b = self.weight, self.bias
         b_re, b_im = (None, None) if b is None else (b.real, b.imag)
         eps = None if eps is None else (eps.real, eps.imag)
+        # the operand pre-pass reads every weight: it hands back the KL sum for penalties()
+        kl_req = {"kind": self._kl_kind} if self._kl_kind is not None else None
         re, im = ops.cplx_linear_vd(input.real, input.imag, w.real, w.imag, b_re, b_im,
-                                    self.log_sigma2, eps=eps)
+                                    self.log_sigma2, eps=eps, kl_req=kl_req)
+        cache = self.__dict__.get("_kl_cache")
+        if cache is None:
+            cache = self.__dict__["_kl_cache"] = ops.FusedKLCache()
+        cache.put((w.real, w.imag, self.log_sigma2), kl_req)
         return cplx.Cplx(re, im)
 
 

@@ -27,7 +27,14 @@ class _RealGaussianLinear(torch.nn.Linear):
     def forward(self, input, eps=None):
         if not self.training:
             return ops.real_linear(input, self.weight, self.bias)
-        return ops.real_linear_vd(input, self.weight, self.bias, self.log_sigma2, eps=eps)
+        kl_req = {"kind": self._kl_kind} if self._kl_kind is not None else None
+        out = ops.real_linear_vd(input, self.weight, self.bias, self.log_sigma2, eps=eps,
+                                 kl_req=kl_req)
+        cache = self.__dict__.get("_kl_cache")
+        if cache is None:
+            cache = self.__dict__["_kl_cache"] = ops.FusedKLCache()
+        cache.put((self.weight, self.log_sigma2), kl_req)
+        return out
 
     @property
     def log_alpha(self):
@@ -38,7 +45,11 @@ class _RealGaussianLinear(torch.nn.Linear):
         return ops.kl(self._kl_kind, self.weight, None, self.log_sigma2, None)
 
     def _penalty_reduced(self, reduction):
-        return ops.kl(self._kl_kind, self.weight, None, self.log_sigma2, reduction)
+        pre = None
+        cache = self.__dict__.get("_kl_cache")
+        if cache is not None and reduction in ("sum", "mean"):
+            pre = cache.take((self.weight, self.log_sigma2))
+        return ops.kl(self._kl_kind, self.weight, None, self.log_sigma2, reduction, precomputed=pre)
 
     def relevance(self, *, threshold, **kwargs):
         with torch.no_grad():

@@ -12,7 +12,7 @@ import torch
 
 from . import _native as nv
 
-_state = {"noise": "torch", "math": "auto", "prepare": True}
+_state = {"noise": "torch", "math": "auto", "prepare": True, "fuse_kl": True}
 _MATH = {"auto": nv.MATH_AUTO, "tensor": nv.MATH_TENSOR, "simt": nv.MATH_SIMT}
 _NOISE = {"torch": nv.NOISE_PHILOX_TORCH, "fast": nv.NOISE_PHILOX_FAST}
 
@@ -41,6 +41,14 @@ def set_operand_prepass(enabled):
     _state["prepare"] = bool(enabled)
 
 
+def set_kl_fusion(enabled):
+    """True (default): a training-mode forward of a variational linear layer also produces the
+    layer's KL sum (its operand pre-pass reads every weight anyway) and the next
+    ``penalties(..., reduction="sum"|"mean")`` over unchanged parameters returns it instead of
+    running the stand-alone KL pass."""
+    _state["fuse_kl"] = bool(enabled)
+
+
 def get_noise_mode():
     return _state["noise"]
 
@@ -54,9 +62,11 @@ def _flat2d(t, K):
 
 
 def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise,
-                 want_s2=False, math=None):
+                 want_s2=False, math=None, kl_req=None):
     """Shared launcher. Returns (y_re, y_im|None, aux). ``noise`` is None for the plain map;
-    ``aux`` = dict(s2=..., philox=(seed, offset, threads)) for the variational forward."""
+    ``aux`` = dict(s2=..., philox=(seed, offset, threads)) for the variational forward.
+    ``kl_req`` = {"kind": k}: ask the operand pre-pass for the layer's KL sum as a by-product;
+    when the path taken produced it, ``kl_req["sum"]`` is set to the 0-d float32 result."""
     dev = nv.require_cuda(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im)
     cplx = x_im is not None
     dt = w_re.dtype
@@ -96,11 +106,24 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
                 ws_bytes = lib.cplxk_linear_vd_workspace_bytes(M, N, K, code)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             s2 = torch.empty((M, N), dtype=dt, device=dev) if want_s2 else None
-            nv.check(lib.cplxk_linear_vd_fwd(nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi),
-                                             nv.ptr(br), nv.ptr(bi), nv.ptr(ls2), nv.ptr(er),
-                                             nv.ptr(ei), noise, seed, offset, threads,
-                                             nv.ptr(y_re), nv.ptr(y_im), M, N, K, code, math,
-                                             nv.ptr(s2), nv.ptr(ws), ws_bytes, st))
+            if kl_req is not None and ws is not None and _state["fuse_kl"]:
+                kl_sum = torch.empty((), dtype=torch.float32, device=dev)
+                kl_ws = nv.kl_workspace(dev)
+                done = ctypes.c_int(0)
+                nv.check(lib.cplxk_linear_vd_fwd_kl(
+                    nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi), nv.ptr(br), nv.ptr(bi),
+                    nv.ptr(ls2), nv.ptr(er), nv.ptr(ei), noise, seed, offset, threads,
+                    nv.ptr(y_re), nv.ptr(y_im), M, N, K, code, math, nv.ptr(s2), nv.ptr(ws),
+                    ws_bytes, kl_req["kind"], nv.ptr(kl_sum), nv.ptr(kl_ws), kl_ws.numel() * 8,
+                    ctypes.byref(done), st))
+                if done.value:
+                    kl_req["sum"] = kl_sum
+            else:
+                nv.check(lib.cplxk_linear_vd_fwd(nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi),
+                                                 nv.ptr(br), nv.ptr(bi), nv.ptr(ls2), nv.ptr(er),
+                                                 nv.ptr(ei), noise, seed, offset, threads,
+                                                 nv.ptr(y_re), nv.ptr(y_im), M, N, K, code, math,
+                                                 nv.ptr(s2), nv.ptr(ws), ws_bytes, st))
             if noise != nv.NOISE_INJECT:
                 gen.set_offset(offset + inc)
             aux = {"s2": s2, "philox": (seed, offset, threads), "eps": (er, ei), "x": (xr, xi)}
@@ -267,12 +290,13 @@ def _save_vd(ctx, aux, log_sigma2, noise):
 
 class _CplxLinearVDFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise):
+    def forward(ctx, x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise,
+                kl_req=None):
         need = any(ctx.needs_input_grad)
         if need:
             _save_linear(ctx, x_re, x_im, w_re, w_im)
         re, im, aux = _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
-                                   noise, want_s2=need)
+                                   noise, want_s2=need, kl_req=kl_req)
         if need:
             _save_vd(ctx, aux, log_sigma2, noise)
         return re, im
@@ -289,17 +313,17 @@ class _CplxLinearVDFn(torch.autograd.Function):
             ctx, g_re, g_im, need_x, n[2] or n[3], n[4] or n[5])
         dls2 = _vd_backward_extra(ctx, g_re, g_im, dx_re, dx_im, need_x, n[6])
         return (_shape_back(dx_re, ctx.lead, K, ctx.x_dtype), _shape_back(dx_im, ctx.lead, K, ctx.x_dtype),
-                dw_re, dw_im, db_re, db_im, dls2, None, None, None)
+                dw_re, dw_im, db_re, db_im, dls2, None, None, None, None)
 
 
 class _RealLinearVDFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b, log_sigma2, eps, noise):
+    def forward(ctx, x, w, b, log_sigma2, eps, noise, kl_req=None):
         need = any(ctx.needs_input_grad)
         if need:
             _save_linear(ctx, x, None, w, None)
         y, _, aux = _forward_raw(x, None, w, None, b, None, log_sigma2, eps, None, noise,
-                                 want_s2=need)
+                                 want_s2=need, kl_req=kl_req)
         if need:
             _save_vd(ctx, aux, log_sigma2, noise)
         return y
@@ -313,7 +337,7 @@ class _RealLinearVDFn(torch.autograd.Function):
         n = ctx.needs_input_grad
         dx, _, dw, _, db, _ = _linear_backward(ctx, g, None, n[0], n[1], n[2])
         dls2 = _vd_backward_extra(ctx, g, None, dx, None, n[0], n[3])
-        return _shape_back(dx, ctx.lead, K, ctx.x_dtype), dw, db, dls2, None, None
+        return _shape_back(dx, ctx.lead, K, ctx.x_dtype), dw, db, dls2, None, None, None
 
 
 def cplx_linear(x_re, x_im, w_re, w_im, b_re=None, b_im=None):
@@ -331,18 +355,43 @@ def _noise_args(eps):
     return eps[0], eps[1], nv.NOISE_INJECT
 
 
-def cplx_linear_vd(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps=None):
+def cplx_linear_vd(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps=None, kl_req=None):
     """Fused local-reparameterisation forward (reference: CplxLinearGaussian.forward,
     nn/relevance/complex/base.py:43-56). ``eps=(eps_re, eps_im)`` injects the noise
-    (each ~ N(0, 1/2)); ``None`` draws it inside the kernel."""
+    (each ~ N(0, 1/2)); ``None`` draws it inside the kernel.  ``kl_req``: see ``_forward_raw``."""
     er, ei, mode = _noise_args(eps)
-    return _CplxLinearVDFn.apply(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, er, ei, mode)
+    return _CplxLinearVDFn.apply(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, er, ei, mode,
+                                 kl_req)
 
 
-def real_linear_vd(x, w, b, log_sigma2, eps=None):
+def real_linear_vd(x, w, b, log_sigma2, eps=None, kl_req=None):
     """Reference: LinearGaussian.forward, nn/relevance/real/base.py:43-49."""
     er, _, mode = _noise_args((eps, None) if eps is not None else None)
-    return _RealLinearVDFn.apply(x, w, b, log_sigma2, er, mode)
+    return _RealLinearVDFn.apply(x, w, b, log_sigma2, er, mode, kl_req)
+
+
+class FusedKLCache:
+    """KL sum produced by the last training-mode forward of a layer, valid while the
+    parameters it was computed from are untouched (tensor identity, storage and autograd
+    version counters) and handed out once."""
+
+    def __init__(self):
+        self._entry = None
+
+    @staticmethod
+    def _key(params):
+        return tuple((id(p), p.data_ptr(), p._version, p.dtype) for p in params if p is not None)
+
+    def put(self, params, kl_req):
+        self._entry = None
+        if kl_req is not None and "sum" in kl_req:
+            self._entry = (self._key(params), kl_req["sum"])
+
+    def take(self, params):
+        entry, self._entry = self._entry, None
+        if entry is not None and entry[0] == self._key(params):
+            return entry[1]
+        return None
 
 
 # ------------------------------------------------------------------------- KL path
@@ -375,12 +424,18 @@ def kl_penalty(kind, w_re, w_im, log_sigma2, reduction="sum"):
 
 class _KLFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, kind, reduction, w_re, w_im, log_sigma2):
+    def forward(ctx, kind, reduction, w_re, w_im, log_sigma2, precomputed=None):
         if any(ctx.needs_input_grad):
             dt = w_re.dtype
             ctx.kind, ctx.reduction = kind, reduction
             ctx.planes = (nv.plane(w_re), nv.plane(w_im), nv.plane(log_sigma2, dt))
             ctx.shape = tuple(w_re.shape)
+        if precomputed is not None and reduction in ("sum", "mean"):
+            # [sum] from the forward's operand pre-pass (FusedKLCache); the list hides it from autograd
+            out = precomputed[0]
+            if reduction == "mean":
+                out = out / max(w_re.numel(), 1)
+            return out.to(w_re.dtype) if w_re.dtype != torch.float32 else out
         return kl_penalty(kind, w_re, w_im, log_sigma2, reduction)
 
     @staticmethod
@@ -402,11 +457,13 @@ class _KLFn(torch.autograd.Function):
                                            1 if grad.dtype == torch.float32 else 0, scale,
                                            nv.ptr(d_wr), nv.ptr(d_wi), nv.ptr(d_ls2),
                                            nv.stream_ptr(dev)))
-        return None, None, d_wr, d_wi, d_ls2
+        return None, None, d_wr, d_wi, d_ls2, None
 
 
-def kl(kind, w_re, w_im, log_sigma2, reduction="sum"):
-    return _KLFn.apply(kind, reduction, w_re, w_im, log_sigma2)
+def kl(kind, w_re, w_im, log_sigma2, reduction="sum", precomputed=None):
+    """``precomputed``: 0-d float32 sum from ``FusedKLCache.take`` (or None)."""
+    pre = None if precomputed is None else [precomputed]
+    return _KLFn.apply(kind, reduction, w_re, w_im, log_sigma2, pre)
 
 
 def log_alpha(w_re, w_im, log_sigma2, threshold=None):

@@ -51,9 +51,11 @@ typedef enum { CPLXK_F32 = 0, CPLXK_BF16 = 1 } cplxk_dtype;
 /* arithmetic used by the GEMM-shaped part of a forward call */
 typedef enum {
   CPLXK_MATH_AUTO = 0,   /* tensor cores when the shape/alignment allows, else SIMT */
-  CPLXK_MATH_TENSOR = 1, /* tcgen05: tf32 operands for F32 planes, bf16 for BF16;
-                            fp32 accumulation in TMEM.  Needs 16-byte aligned
-                            planes and K*sizeof(elem) % 16 == 0.              */
+  CPLXK_MATH_TENSOR = 1, /* tcgen05, fp32 accumulation in TMEM.  BF16 planes: bf16 operands.
+                            F32 planes: 11-bit-significand operands -- per-row power-of-two
+                            scaled fp16 (variational forward with workspace) or tf32
+                            (round-to-nearest) otherwise.  Needs 16-byte aligned planes and
+                            K*sizeof(elem) % 16 == 0.                          */
   CPLXK_MATH_SIMT = 2    /* exact fp32 FMA on CUDA cores (any shape)          */
 } cplxk_math;
 
@@ -128,6 +130,33 @@ int cplxk_linear_vd_fwd(const void* x_re, const void* x_im,
                         int64_t M, int64_t N, int64_t K,
                         int dtype, int math, void* s2_out /* nullable [M,N]: saved variance */,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Same forward, with the layer's KL penalty as a by-product.  The operand pre-pass of the
+ * tensor-core path reads every weight row and log_sigma2 anyway; with kl_kind >= 0 it also
+ * evaluates sum(penalty(kl_kind, log_alpha)) over all N*K parameters (see cplxk_kl below: the
+ * same per-element device function, the same deterministic reduction) and writes it to
+ * *kl_sum -- no second HBM pass over the parameters.  *kl_done (HOST int) is set to 1 when the
+ * path taken produced the sum (fp32 planes, tensor cores, workspace given, M > 128, K % 8 == 0)
+ * and to 0 otherwise, in which case the caller runs cplxk_kl.  kl_kind < 0: plain forward.
+ *   kl_workspace : cplxk_kl_workspace_bytes() bytes, as for cplxk_kl.
+ * Replaces the pair CplxLinearGaussian.forward + CplxVDMixin.penalty.sum()
+ * (nn/relevance/complex/base.py:43-56, complex/vd.py:95-99, relevance/base.py:135-139).
+ */
+int cplxk_linear_vd_fwd_kl(const void* x_re, const void* x_im,
+                           const void* w_re, const void* w_im,
+                           const void* b_re, const void* b_im,
+                           const void* log_sigma2,
+                           const void* eps_re, const void* eps_im,
+                           int noise, uint64_t seed, uint64_t offset,
+                           uint32_t philox_threads,
+                           void* y_re, void* y_im,
+                           int64_t M, int64_t N, int64_t K,
+                           int dtype, int math, void* s2_out,
+                           void* workspace, size_t workspace_bytes,
+                           int kl_kind, float* kl_sum,
+                           void* kl_workspace, size_t kl_workspace_bytes,
+                           int* kl_done, void* stream);
 
 /*
  * KL penalty of a variational layer over n parameters, one HBM pass:

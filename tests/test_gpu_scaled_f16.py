@@ -1,0 +1,192 @@
+"""fp32 planes on the kind::f16 tensor-core path: per-row power-of-two scaled fp16 operands
+(pre-pass of fwd_tc3.cu), persistent CTA-pair kernel, and the KL sum fused into the pre-pass.
+All comparisons are against the float64 oracle on the same inputs and injected noise."""
+import os
+
+import pytest
+import torch
+
+import cplxmodule_b200 as cb
+from cplxmodule_b200 import cplx, ops
+from cplxmodule_b200.nn.relevance import CplxLinearARD, CplxLinearVD, LinearARD, LinearVD, penalties
+from oracle import cplx_oracle as orc
+from tests.conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-3   # north_star: 1e-3 relative (max-norm) for fp32 planes
+
+
+def _case(M, N, K, seed, row_scale_x=None, row_scale_w=None):
+    g = torch.Generator().manual_seed(seed)
+    x_re, x_im = torch.randn(M, K, generator=g), torch.randn(M, K, generator=g)
+    w_re = torch.randn(N, K, generator=g) / K ** 0.5
+    w_im = torch.randn(N, K, generator=g) / K ** 0.5
+    if row_scale_x is not None:
+        x_re, x_im = x_re * row_scale_x[:, None], x_im * row_scale_x[:, None]
+    if row_scale_w is not None:
+        w_re, w_im = w_re * row_scale_w[:, None], w_im * row_scale_w[:, None]
+    b_re, b_im = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    ls2 = torch.empty(N, K).uniform_(-12, 2, generator=g)
+    eps_re, eps_im = torch.randn(M, N, generator=g), torch.randn(M, N, generator=g)
+    return x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im
+
+
+def _run(case, cplx_=True):
+    x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im = case
+    d = lambda t: t.to(DEV)
+    if cplx_:
+        want = orc.cplx_linear_vd(*(t.double() for t in case))
+        got = ops.cplx_linear_vd(d(x_re), d(x_im), d(w_re), d(w_im), d(b_re), d(b_im), d(ls2),
+                                 eps=(d(eps_re), d(eps_im)))
+        return got, want
+    want = orc.real_linear_vd(x_re.double(), w_re.double(), b_re.double(), ls2.double(), eps_re.double())
+    got = ops.real_linear_vd(d(x_re), d(w_re), d(b_re), d(ls2), eps=d(eps_re))
+    return (got,), (want,)
+
+
+@pytest.fixture(params=["persistent", "tile_per_cluster"])
+def kernel(request):
+    if request.param == "tile_per_cluster":
+        os.environ["CPLXK_PERSIST"] = "0"
+    yield request.param
+    os.environ.pop("CPLXK_PERSIST", None)
+
+
+@pytest.mark.parametrize("M,N,K", [(129, 8, 8), (256, 128, 64), (300, 384, 1000), (513, 130, 264),
+                                   (1024, 640, 4096), (200, 72, 8200), (2000, 1000, 16384 + 8)])
+@pytest.mark.parametrize("cplx_", [True, False])
+def test_shapes(M, N, K, cplx_, kernel):
+    """ragged tiles in M and N, K tails past the register-cached 8192 columns, real and complex"""
+    got, want = _run(_case(M, N, K, seed=M + N + K), cplx_)
+    for a, b in zip(got, want):
+        assert rel_err(a, b) < TOL
+
+
+def test_rows_of_wildly_different_magnitude(kernel):
+    """every row carries its own power-of-two scale: a row of 1e-9 next to a row of 1e+9 keeps
+    full precision RELATIVE TO ITS OWN outputs, which a per-tensor fp16 scale could not do
+    (|x|^2 . exp(log_sigma2) must stay inside fp32, as in the reference, hence not wider)"""
+    M, N, K = 384, 256, 512
+    sx = torch.logspace(-9, 9, M)[torch.randperm(M, generator=torch.Generator().manual_seed(1))]
+    sw = torch.logspace(-12, 12, N)[torch.randperm(N, generator=torch.Generator().manual_seed(2))]
+    x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im = _case(M, N, K, 5, sx, sw)
+    d = lambda t: t.to(DEV)
+    mu = orc.cplx_linear(x_re.double(), x_im.double(), w_re.double(), w_im.double())
+    # noise off (eps = 0) and no bias: the output is the mean GEMM alone, checked row by row and
+    # column by column against the scale of that row / column
+    zero = torch.zeros(M, N)
+    got = ops.cplx_linear_vd(d(x_re), d(x_im), d(w_re), d(w_im), None, None, d(ls2), eps=(d(zero), d(zero)))
+    for g, w in zip(got, mu):
+        err = (g.double().cpu() - w).abs()
+        scale = sx.double()[:, None] * sw.double()[None, :]
+        assert float((err / scale).max()) < 4 * TOL * float((w.abs() / scale).max())
+        assert torch.isfinite(g).all()
+
+
+def test_zero_rows_and_tiny_values(kernel):
+    M, N, K = 260, 136, 128
+    case = list(_case(M, N, K, 11))
+    case[0][3].zero_(); case[1][3].zero_()          # an all-zero input row
+    case[2][7].zero_(); case[3][7].zero_()          # an all-zero weight row
+    case[0][5] *= 1e-42; case[1][5] *= 1e-42        # a subnormal input row
+    got, want = _run(case)
+    for a, b in zip(got, want):
+        assert torch.isfinite(a).all() and rel_err(a, b) < TOL
+    # outputs of the zero weight row: bias + noise only
+    assert rel_err(got[0][:, 7], want[0][:, 7]) < TOL
+
+
+def test_inf_and_nan_propagate_like_the_reference(kernel):
+    M, N, K = 256, 128, 64
+    case = list(_case(M, N, K, 13))
+    case[0][2, 3] = float("inf")
+    case[2][5, 1] = float("nan")
+    got, _ = _run(case)
+    re = got[0].cpu()
+    assert not torch.isfinite(re[2]).all()           # the row with the inf
+    assert torch.isnan(re[:, 5]).all()               # the column of the nan weight
+    keep = torch.ones(M, dtype=torch.bool); keep[2] = False
+    cols = torch.ones(N, dtype=torch.bool); cols[5] = False
+    assert torch.isfinite(re[keep][:, cols]).all()   # nothing else is contaminated
+
+
+def test_matches_tf32_path_and_exact_fp32_kernel():
+    """three independent implementations of the same forward on the device agree"""
+    case = _case(512, 256, 1024, 17)
+    got16, want = _run(case)
+    os.environ["CPLXK_F16"] = "0"
+    try:
+        got32, _ = _run(case)
+    finally:
+        os.environ.pop("CPLXK_F16", None)
+    ops.set_math_mode("simt")
+    try:
+        exact, _ = _run(case)
+    finally:
+        ops.set_math_mode("auto")
+    for a, b, c, w in zip(got16, got32, exact, want):
+        assert rel_err(c, w) < 2e-5
+        assert rel_err(a, w) < TOL and rel_err(b, w) < TOL
+        # same 11-bit significand, same rounding mode: errors of the same size
+        assert rel_err(a, w) < 2.5 * max(rel_err(b, w), 1e-4)
+
+
+@pytest.mark.parametrize("cls,kind", [(CplxLinearVD, "cplx_vd"), (CplxLinearARD, "cplx_ard"),
+                                      (LinearVD, "real_vd"), (LinearARD, "real_ard")])
+@pytest.mark.parametrize("reduction", ["sum", "mean"])
+def test_fused_kl_equals_standalone_pass(cls, kind, reduction):
+    """penalties() after a training forward returns the pre-pass by-product: same value as the
+    stand-alone KL kernel and as the float64 oracle; used once, invalidated by parameter updates"""
+    torch.manual_seed(3)
+    layer = cls(264, 200).to(DEV).train()
+    with torch.no_grad():
+        layer.log_sigma2.uniform_(-12, 4)
+    is_cplx = kind.startswith("cplx")
+    x = cplx.randn(300, 264, device=DEV) if is_cplx else torch.randn(300, 264, device=DEV)
+    with torch.no_grad():
+        cb.set_kl_fusion(False)
+        layer(x)
+        alone = float(sum(penalties(layer, reduction=reduction)))
+        cb.set_kl_fusion(True)
+        layer(x)
+        assert layer._kl_cache._entry is not None            # the forward produced it
+        fused = float(sum(penalties(layer, reduction=reduction)))
+        assert layer._kl_cache._entry is None                # handed out once
+        again = float(sum(penalties(layer, reduction=reduction)))
+    w = layer.weight
+    w_re, w_im = (w.real, w.imag) if is_cplx else (w, None)
+    c = lambda t: None if t is None else t.detach().double().cpu()
+    want = float(orc.layer_penalty(kind, c(w_re), c(w_im), c(layer.log_sigma2), reduction))
+    assert abs(fused - alone) <= 1e-6 * abs(alone)
+    assert again == alone
+    assert abs(fused - want) <= 1e-4 * abs(want)
+    # a parameter update between forward and penalties() must not return the stale sum
+    with torch.no_grad():
+        layer(x)
+        layer.log_sigma2.add_(1.0)
+        fresh = float(sum(penalties(layer, reduction=reduction)))
+        cb.set_kl_fusion(False)
+        ref = float(sum(penalties(layer, reduction=reduction)))
+        cb.set_kl_fusion(True)
+    assert fresh == ref and abs(fresh - alone) > 1e-3 * abs(alone)
+
+
+def test_fused_kl_keeps_gradients():
+    torch.manual_seed(4)
+    a = CplxLinearVD(256, 136).to(DEV).train()
+    b = CplxLinearVD(256, 136).to(DEV).train()
+    b.load_state_dict(a.state_dict())
+    x = cplx.randn(260, 256, device=DEV)
+    eps = cplx.randn(260, 136, device=DEV)
+    outs = []
+    for layer, fuse in ((a, True), (b, False)):
+        cb.set_kl_fusion(fuse)
+        y = layer(x, eps=eps)
+        loss = (y.real ** 2 + y.imag ** 2).mean() + 1e-3 * sum(penalties(layer))
+        loss.backward()
+        outs.append(float(loss))
+    cb.set_kl_fusion(True)
+    assert abs(outs[0] - outs[1]) <= 1e-6 * abs(outs[1])
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa.grad, pb.grad, rtol=1e-5, atol=1e-7)

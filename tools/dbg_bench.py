@@ -41,27 +41,34 @@ def main():
         b_im = torch.randn(N, device=DEV).to(dt)
         ls2 = torch.full((N, K), -10.0, device=DEV).to(dt)
         eps = (torch.randn(M, N, device=DEV).to(dt), torch.randn(M, N, device=DEV).to(dt))
-        variants = os.environ.get("DBG_VARIANTS", "default,persist,tf32").split(",")
+        variants = os.environ.get("DBG_VARIANTS", "default,nopersist,tf32").split(",")
         dbgs = os.environ.get("DBG_MODES", "0").split(",")
-        for variant in variants:
+        rounds = int(os.environ.get("DBG_ROUNDS", "4"))
+
+        def setenv(variant):
             os.environ.pop("CPLXK_PERSIST", None)
             os.environ.pop("CPLXK_F16", None)
-            if variant == "persist":
-                os.environ["CPLXK_PERSIST"] = "1"
+            if variant == "nopersist":
+                os.environ["CPLXK_PERSIST"] = "0"
             elif variant == "tf32":
-                if dt_name != "f32":
-                    continue
                 os.environ["CPLXK_F16"] = "0"
-            for noise in ("inject", "torch", "fast"):
-                for dbg in dbgs:
-                    os.environ["CPLXK_DBG"] = dbg
-                    if noise == "inject":
-                        fn = lambda: ops.cplx_linear_vd(xr, xi, w_re, w_im, b_re, b_im, ls2, eps=eps)
-                    else:
-                        cb.set_noise_mode(noise)
-                        fn = lambda: ops.cplx_linear_vd(xr, xi, w_re, w_im, b_re, b_im, ls2)
-                    ms = timeit(fn)
-                    rows.append(dict(dtype=dt_name, variant=variant, noise=noise, dbg=dbg, ms=round(ms, 4)))
+
+        for noise in os.environ.get("DBG_NOISE", "inject,torch,fast").split(","):
+            for dbg in dbgs:
+                os.environ["CPLXK_DBG"] = dbg
+                if noise == "inject":
+                    fn = lambda: ops.cplx_linear_vd(xr, xi, w_re, w_im, b_re, b_im, ls2, eps=eps)
+                else:
+                    cb.set_noise_mode(noise)
+                    fn = lambda: ops.cplx_linear_vd(xr, xi, w_re, w_im, b_re, b_im, ls2)
+                res = {v: [] for v in variants if not (v == "tf32" and dt_name != "f32")}
+                for _ in range(rounds):          # interleave the variants: clocks drift under the power cap
+                    for v in res:
+                        setenv(v)
+                        res[v].append(timeit(fn, iters=50))
+                for v, ts in res.items():
+                    rows.append(dict(dtype=dt_name, variant=v, noise=noise, dbg=dbg,
+                                     ms_min=round(min(ts), 4), ms_med=round(sorted(ts)[len(ts) // 2], 4)))
                     print(json.dumps(rows[-1]), flush=True)
         os.environ.pop("CPLXK_PERSIST", None)
         os.environ.pop("CPLXK_F16", None)
