@@ -28,6 +28,11 @@ METRIC = "CplxLinearVD forward+KL samples/sec (B=4096, d=4096)"
 FLOPS_PER_STEP = 10.0 * B * D * D          # 8 (complex mean GEMM, 4-multiply form) + 2 (variance GEMM)
 FWD_ALGO_BYTES = 4.0 * (2 * B * D + 2 * D * D + D * D + 2 * B * D)   # x, W, log_sigma2, y  (fp32)
 KL_ALGO_BYTES = 4.0 * 3 * D * D                                       # U, V, log_sigma2
+# operand pre-pass (fp32 planes): reads x (2 planes), W (2 planes), log_sigma2; writes 3 + 3 planes
+# of 16-bit operands (fp16 re/im + bf16 |x|^2, fp16 U/V + bf16 exp(log_sigma2)) and the row scales
+PREP_ALGO_BYTES = 4.0 * (2 * B * D + 3 * D * D) + 2.0 * (3 * B * D + 3 * D * D) + 4.0 * (B + D)
+# the GEMM kernel then streams those six 16-bit planes and writes y (fp32)
+GEMM_ALGO_BYTES = 2.0 * (3 * B * D + 3 * D * D) + 4.0 * 2 * B * D
 
 
 def measured_peaks():
@@ -88,6 +93,10 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+# dram bytes (read + write) per launch from the committed ncu --set full captures (profiles/)
+NCU_TRAFFIC = {}
 
 
 # ----------------------------------------------------------------------------- CPU side
@@ -178,6 +187,8 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cb.set_noise_mode(args.noise)
+    if world > 1:
+        cb.set_kl_fusion(False)                        # N > 1: KL is row-sharded + all-reduced instead
     torch.manual_seed(0)                               # identical (replicated) parameters
     layer = CplxLinearVD(D, D).to(dev).train()
     if args.dtype == "bf16":
@@ -340,6 +351,22 @@ def run_ours(args, rank, local_rank, world):
                    "fwd_ms_per_launch": f16, "fwd_tflops": FLOPS_PER_STEP / (f16 / 1e3) / 1e12}
             del layer16, x16
 
+        # ---- side measurements that explain the step (not part of `value`): the operand pre-pass
+        # alone (CPLXK_DBG=4 returns before the GEMM launch) and the stand-alone KL pass that the
+        # fused pre-pass replaces at N = 1
+        prep_ms = kl_alone_ms = None
+        if args.dtype == "f32":
+            os.environ["CPLXK_DBG"] = "4"
+            for _ in range(3):
+                layer(x)
+            prep_ms = timed(lambda: layer(x), 20) / 20
+            os.environ.pop("CPLXK_DBG")
+            cb.set_kl_fusion(False)
+            for _ in range(3):
+                sum(penalties(layer))
+            kl_alone_ms = timed(lambda: sum(penalties(layer)), 20) / 20
+            cb.set_kl_fusion(True)
+
     f_ms = statistics.mean(a.elapsed_time(b) for a, b in fwd_ms)
     k_ms = statistics.mean(a.elapsed_time(b) for a, b in kl_ms)
     if rank != 0:
@@ -351,33 +378,54 @@ def run_ours(args, rank, local_rank, world):
     esize = 4 if args.dtype != "bf16" else 2
     value = B * world * args.steps / (ms / 1e3)
     e2e_value = B * world * e2e_steps / (e2e_ms / 1e3)
-    achieved_tf = FLOPS_PER_STEP / (f_ms / 1e3) / 1e12
+    gemm_ms = f_ms - prep_ms if prep_ms is not None else f_ms
+    achieved_tf = FLOPS_PER_STEP / (gemm_ms / 1e3) / 1e12
     peak_tf = peaks["bf16_tflops_sustained"]
-    kl_gbs = KL_ALGO_BYTES * (esize / 4.0) / max(world, 1) / (k_ms / 1e3) / 1e9
-    roofline_kl = {
-        "kernel": "kl_kernel<CPLX_VD>", "bound": "hbm", "achieved": kl_gbs,
-        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": kl_gbs / peaks["hbm_gbs"],
-        "ms_per_launch": k_ms,
-        "note": "event pair around the Python-level penalties() call: includes launch latency",
-    } if world == 1 else {
-        "kernel": "kl_kernel<CPLX_VD> on a row shard + NCCL all-reduce of the scalar",
-        "note": "issued on a side stream and overlapped with the forward GEMM; not separately timed",
-    }
+    fused = world == 1 and args.dtype == "f32"
+    if fused:
+        kl_gbs = KL_ALGO_BYTES / (kl_alone_ms / 1e3) / 1e9
+        roofline_kl = {
+            "kernel": "kl_kernel<CPLX_VD> (stand-alone KL pass)", "bound": "hbm", "achieved": kl_gbs,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": kl_gbs / peaks["hbm_gbs"],
+            "ms_per_launch": kl_alone_ms,
+            "note": "NOT launched inside the timed step at N=1: the forward's operand pre-pass "
+                    "evaluates the same per-element penalty on the weight rows it converts and "
+                    "penalties() returns that sum (cplxk_linear_vd_fwd_kl); measured here with the "
+                    "fusion switched off, event pair around the Python-level penalties() call",
+            "ms_in_step": k_ms,
+        }
+    elif world == 1:
+        kl_gbs = KL_ALGO_BYTES * (esize / 4.0) / (k_ms / 1e3) / 1e9
+        roofline_kl = {
+            "kernel": "kl_kernel<CPLX_VD>", "bound": "hbm", "achieved": kl_gbs,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": kl_gbs / peaks["hbm_gbs"],
+            "ms_per_launch": k_ms,
+            "note": "event pair around the Python-level penalties() call: includes launch latency",
+        }
+    else:
+        roofline_kl = {
+            "kernel": "kl_kernel<CPLX_VD> on a row shard + NCCL all-reduce of the scalar",
+            "note": "issued on a side stream and overlapped with the forward GEMM; not separately timed",
+        }
+    f32 = args.dtype != "bf16"
     out = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32" if args.dtype != "bf16" else "bf16", "data": "synthetic",
+        "dtype": "f16" if f32 else "bf16", "data": "synthetic",
         "config": {
             "workload": "CplxLinearVD 4096->4096 fused local-reparam forward(train) + KL, "
                         "batch=4096 per GPU (BASELINE.json configs[2])",
             "per_gpu_batch": B, "global_batch": B * world, "features": D,
             "parallelism": f"dp{world}" + (" (batch rows sharded, KL row-sharded, 1 scalar all-reduce)"
                                             if world > 1 else ""),
-            "storage": "fp32 planes" if args.dtype != "bf16" else "bf16 planes",
-            "math": "tcgen05 kind::tf32, fp32 accumulate in TMEM" if args.dtype != "bf16"
+            "storage": "fp32 planes in and out" if f32 else "bf16 planes",
+            "math": ("tcgen05 kind::f16 on per-row power-of-two scaled fp16 copies of the fp32 planes "
+                     "(11-bit significand = tf32, round-to-nearest; variance GEMM operands bf16), "
+                     "fp32 accumulate in TMEM, scales undone in the epilogue") if f32
                     else "tcgen05 kind::f16 (bf16), fp32 accumulate in TMEM",
             "noise": f"in-kernel Philox4x32-10, layout={args.noise}",
+            "kl": "fused into the operand pre-pass" if fused else "kl_kernel",
             "l2": "no flush needed: each step streams 470 MB (fp32) of distinct operands, "
                   "larger than the 126 MB L2",
         },
@@ -388,22 +436,35 @@ def run_ours(args, rank, local_rank, world):
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                 "note": "pinned host x -> device, forward+KL, y and KL -> pinned host; copies "
                         "double-buffered on side streams, all inside the timed region"},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": (2 if fused else 3) * args.steps,
         "roofline": {
-            "kernel": "fwd_tc2_kernel (CTA-pair fused complex mean GEMM + variance GEMM + Philox + "
-                      "epilogue) timed together with its operand pre-pass vd_prepare_kernel",
+            "kernel": "fwd_tc3_kernel (persistent CTA-pair: complex mean GEMM + variance GEMM + Philox "
+                      "noise + epilogue)" + ("; ms_per_launch = event-timed forward call minus the "
+                      "separately timed pre-pass launch" if prep_ms is not None else
+                      " timed together with its operand pre-pass"),
             "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf,
-            "peak_source": f"{peaks['source']} bf16 cuBLAS sustained (MEASURED_PEAKS.json); "
-                           "tf32 hardware rate is half the bf16 rate",
-            "algorithmic_flops_per_launch": FLOPS_PER_STEP, "ms_per_launch": f_ms,
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE fwd_tc_kernel launch, from the
-            # committed `ncu --set full` capture (profiles/prof_fwd_*_v3.raw.csv)
-            "traffic": (1.259264e9 + 0.182723e9) if args.dtype != "bf16" else (0.610508e9 + 0.101000e9),
-            "traffic_unit": "bytes/launch", "algorithmic_bytes_per_launch": FWD_ALGO_BYTES * esize / 4.0,
+            "peak_source": f"{peaks['source']} bf16 cuBLAS sustained (MEASURED_PEAKS.json); kind::f16 "
+                           "runs fp16 and bf16 operands at the same rate",
+            "algorithmic_flops_per_launch": FLOPS_PER_STEP, "ms_per_launch": gemm_ms,
+            "forward_call_ms": f_ms,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed
+            # `ncu --set full` capture (profiles/README.md); None until re-captured for this kernel
+            "traffic": NCU_TRAFFIC.get("gemm_" + args.dtype),
+            "traffic_unit": "bytes/launch",
+            "algorithmic_bytes_per_launch": GEMM_ALGO_BYTES if f32 else FWD_ALGO_BYTES * esize / 4.0,
         },
         "roofline_kl": roofline_kl,
     }
+    if prep_ms is not None:
+        out["roofline_prepass"] = {
+            "kernel": "vd_prepare_f16_kernel (fp32 -> row-scaled fp16 operands, |x|^2, exp(log_sigma2), "
+                      "row scales, KL sum)", "bound": "hbm",
+            "achieved": PREP_ALGO_BYTES / (prep_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": PREP_ALGO_BYTES / (prep_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+            "ms_per_launch": prep_ms, "algorithmic_bytes_per_launch": PREP_ALGO_BYTES,
+            "traffic": NCU_TRAFFIC.get("prepass_f32"),
+        }
     if alt is not None:
         alt["fwd_frac_of_peak"] = alt["fwd_tflops"] / peak_tf
         out["alt_bf16"] = alt

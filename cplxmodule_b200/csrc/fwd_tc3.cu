@@ -200,7 +200,9 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------------- TMA producer
-    if (lane == 0 && p.dbg != 1) {
+    // (whole warp in the loop, one elected lane issues: see the MMA issuer below)
+    if (p.dbg != 1) {
+      const bool elected = ptx::elect_one();
       int s = 0;
       uint32_t ph = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
@@ -212,21 +214,30 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
           ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
           const uint32_t fb = bar_full + 8 * s;
           const uint32_t st = base + s * C::STAGE_BYTES;
-          if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * C::STAGE_BYTES);
           const int32_t k0 = kb * C::BK;
-          ptx::tma_load_2d_pair(st + C::OFF_A0, &tm_xr, fb, k0, m0);
-          if constexpr (kCplx) ptx::tma_load_2d_pair(st + C::OFF_A1, &tm_xi, fb, k0, m0);
-          ptx::tma_load_2d_pair(st + C::OFF_Q, &tm_q, fb, k0, m0);
-          ptx::tma_load_2d_pair(st + C::OFF_B0, &tm_wr, fb, k0, nb0);
-          if constexpr (kCplx) ptx::tma_load_2d_pair(st + C::OFF_B1, &tm_wi, fb, k0, nb0);
-          ptx::tma_load_2d_pair(st + C::OFF_E, &tm_e, fb, k0, nb0);
+          if (elected) {
+            if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * C::STAGE_BYTES);
+            ptx::tma_load_2d_pair(st + C::OFF_A0, &tm_xr, fb, k0, m0);
+            if constexpr (kCplx) ptx::tma_load_2d_pair(st + C::OFF_A1, &tm_xi, fb, k0, m0);
+            ptx::tma_load_2d_pair(st + C::OFF_Q, &tm_q, fb, k0, m0);
+            ptx::tma_load_2d_pair(st + C::OFF_B0, &tm_wr, fb, k0, nb0);
+            if constexpr (kCplx) ptx::tma_load_2d_pair(st + C::OFF_B1, &tm_wi, fb, k0, nb0);
+            ptx::tma_load_2d_pair(st + C::OFF_E, &tm_e, fb, k0, nb0);
+          }
+          __syncwarp();
           if (++s == C::STAGES) s = 0, ph ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
     // --------------------------------------------------------- MMA issuer: leader CTA only
-    if (leader && lane == 0) {
+    // The WHOLE warp walks the loop (waits included) and one elected lane issues: with
+    // warp-uniform control flow the descriptors live in uniform registers and a tcgen05.mma costs
+    // ~3 issue slots; inside an `if (lane == 0)` region the compiler re-elects and moves four
+    // registers to the uniform file per MMA, and the single issuing thread -- which shares its
+    // scheduler with two noise-generating warps -- cannot keep the tensor pipe fed.
+    if (leader) {
+      const bool elected = ptx::elect_one();
       const uint32_t fmt = p.f16 ? 0u : 1u;
       const uint32_t idesc = ptx::make_idesc_f16(fmt, 256, C::BN, false);
       const uint32_t idesc_na = ptx::make_idesc_f16(fmt, 256, C::BN, true);
@@ -248,23 +259,28 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
             const uint64_t b0 = ptx::make_kmajor_desc<128>(st + C::OFF_B0);
             const uint64_t b1 = ptx::make_kmajor_desc<128>(st + C::OFF_B1);
             const uint64_t be = ptx::make_kmajor_desc<128>(st + C::OFF_E);
+            const uint32_t acc0 = kb > 0 ? 1u : 0u;
+            if (elected) {
 #pragma unroll
-            for (int k = 0; k < C::KSTEPS; ++k) {
-              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-              const uint32_t off = k * 32;
-              ptx::umma_ss_pair<true>(t_re, ptx::desc_advance(a0, off), ptx::desc_advance(b0, off), idesc, acc);
-              if constexpr (kCplx) {
-                ptx::umma_ss_pair<true>(t_re, ptx::desc_advance(a1, off), ptx::desc_advance(b1, off), idesc_na, 1u);
-                ptx::umma_ss_pair<true>(t_im, ptx::desc_advance(a0, off), ptx::desc_advance(b1, off), idesc, acc);
-                ptx::umma_ss_pair<true>(t_im, ptx::desc_advance(a1, off), ptx::desc_advance(b0, off), idesc, 1u);
+              for (int k = 0; k < C::KSTEPS; ++k) {
+                const uint32_t acc = k > 0 ? 1u : acc0;
+                const uint32_t off = k * 32;
+                ptx::umma_ss_pair<true>(t_re, ptx::desc_advance(a0, off), ptx::desc_advance(b0, off), idesc, acc);
+                if constexpr (kCplx) {
+                  ptx::umma_ss_pair<true>(t_re, ptx::desc_advance(a1, off), ptx::desc_advance(b1, off), idesc_na, 1u);
+                  ptx::umma_ss_pair<true>(t_im, ptx::desc_advance(a0, off), ptx::desc_advance(b1, off), idesc, acc);
+                  ptx::umma_ss_pair<true>(t_im, ptx::desc_advance(a1, off), ptx::desc_advance(b0, off), idesc, 1u);
+                }
+                ptx::umma_ss_pair<true>(t_s2, ptx::desc_advance(aq, off), ptx::desc_advance(be, off), idesc_var, acc);
               }
-              ptx::umma_ss_pair<true>(t_s2, ptx::desc_advance(aq, off), ptx::desc_advance(be, off), idesc_var, acc);
             }
           }
-          ptx::umma_commit_pair(bar_empty + 8 * s);   // frees the stage in BOTH CTAs
+          if (elected) ptx::umma_commit_pair(bar_empty + 8 * s);   // frees the stage in BOTH CTAs
+          __syncwarp();
           if (++s == C::STAGES) s = 0, ph ^= 1u;
         }
-        ptx::umma_commit_pair(bar_accum);             // accumulators complete, both CTAs
+        if (elected) ptx::umma_commit_pair(bar_accum);             // accumulators complete, both CTAs
+        __syncwarp();
       }
     }
   } else {
@@ -636,6 +652,8 @@ int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re,
         static_cast<const float*>(ls2), N, K, xh_re, nullptr, q, wh_re, nullptr, e, isx, isw, kl_kind,
         kl_sum, kws);
   CPLXK_CUDA_TRY(cudaGetLastError());
+  const char* dbg_env = std::getenv("CPLXK_DBG");
+  if (dbg_env && std::atoi(dbg_env) == 4) return CPLXK_OK;   // measurement aid: pre-pass only
   const char* pe = std::getenv("CPLXK_PERSIST");
   if (pe && pe[0] == '0')
     return fwd_tc2_half_dispatch(cplx, xh_re, xh_im, wh_re, wh_im, q, e, isx, isw, M, N, K, ep, st);
