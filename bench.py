@@ -173,6 +173,50 @@ def run_reference(args, rank):
     print(json.dumps(out), flush=True)
 
 
+_ORIG_AFFINITY = []
+
+
+def unbind_all_threads():
+    """Give every thread of this process its original CPU set back (the CPU baseline leg must see
+    all host cores, including worker threads spawned while the process was bound)."""
+    if not _ORIG_AFFINITY:
+        return
+    for tid in os.listdir("/proc/self/task"):
+        try:
+            os.sched_setaffinity(int(tid), _ORIG_AFFINITY[0])
+        except OSError:
+            pass
+
+
+def bind_near_gpu(local_rank):
+    """Run this process (and first-touch its pinned staging buffers) on the NUMA node the GPU's
+    PCIe root port hangs off: host<->device copies that cross the socket interconnect lose a
+    large part of the PCIe bandwidth.  Placement only; best effort, returns a short description."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa: single node"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return f"numa: node {node} has no allowed cpus"
+        _ORIG_AFFINITY.append(os.sched_getaffinity(0))
+        os.sched_setaffinity(0, allowed)
+        return f"numa: bound to node {node} ({len(allowed)} cpus)"
+    except Exception as exc:  # noqa: BLE001 -- placement is optional
+        return f"numa: not bound ({type(exc).__name__})"
+
+
 # ----------------------------------------------------------------------------- GPU side
 def run_ours(args, rank, local_rank, world):
     import torch
@@ -184,6 +228,7 @@ def run_ours(args, rank, local_rank, world):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    placement = bind_near_gpu(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cb.set_noise_mode(args.noise)
@@ -435,7 +480,7 @@ def run_ours(args, rank, local_rank, world):
                 "d2h_bytes_per_step": 2 * B * D * esize + 4,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                 "note": "pinned host x -> device, forward+KL, y and KL -> pinned host; copies "
-                        "double-buffered on side streams, all inside the timed region"},
+                        "double-buffered on side streams, all inside the timed region; " + placement},
         "gpu_launches": (2 if fused else 3) * args.steps,
         "roofline": {
             "kernel": "fwd_tc3_kernel (persistent CTA-pair: complex mean GEMM + variance GEMM + Philox "
@@ -469,6 +514,7 @@ def run_ours(args, rank, local_rank, world):
         alt["fwd_frac_of_peak"] = alt["fwd_tflops"] / peak_tf
         out["alt_bf16"] = alt
     if world == 1 and not args.no_cpu:
+        unbind_all_threads()
         torch.set_num_threads(os.cpu_count() or 1)
         time_oracle(64)
         t = time_oracle(1)

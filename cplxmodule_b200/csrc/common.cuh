@@ -19,6 +19,17 @@ namespace cplxk {
 
 void set_last_cuda_error(cudaError_t e);
 
+// sqrt(max(s2, 1e-8)) of the reparameterisation: one MUFU.SQRT.  The IEEE sqrtf() expands to
+// rsqrt + two Newton steps + a BRANCH to a slow path per element, which serialises the epilogue
+// (no interleaving across the run) while the tensor pipe waits for its accumulators back; the
+// argument is >= 1e-8 (normal), and the result differs from the correctly rounded one by at most
+// a couple of ulp (~2e-7 relative; the acceptance bound is 1e-3).
+__device__ __forceinline__ float sd_of(float s2) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(s2, 1e-8f)));
+  return r;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T>

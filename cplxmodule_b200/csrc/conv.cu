@@ -153,7 +153,7 @@ conv_simt_kernel(const T* __restrict__ x_re, const T* __restrict__ x_im,
         if constexpr (kCplx) im += Elem<T>::to_f(static_cast<const T*>(ep.b_im)[o]);
       }
       if constexpr (kVD) {
-        const float sd = sqrtf(fmaxf(acc_s2[i][j], 1e-8f));
+        const float sd = sd_of(acc_s2[i][j]);
         float er, ei = 0.f;
         if (ep.noise.mode == CPLXK_NOISE_INJECT) {
           er = Elem<T>::to_f(static_cast<const T*>(ep.eps_re)[off]);

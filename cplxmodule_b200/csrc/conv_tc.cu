@@ -236,32 +236,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // Producer and MMA issuer: the WHOLE warp walks the loop and one elected lane issues -- with
+  // warp-uniform control flow the addresses / descriptors stay in uniform registers (a
+  // tcgen05.mma costs ~3 issue slots instead of ELECT + 4 R2UR + ... on a scheduler shared with
+  // the noise warps).
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const bool elected = ptx::elect_one();
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % C::STAGES;
         const uint32_t ph = (kb / C::STAGES) & 1;
         ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
         const uint32_t fb = bar_full + 8 * s;
         const uint32_t st = base + s * C::STAGE_BYTES;
-        ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
         const int rs = kb / cchunks, cc = kb - rs * cchunks;
         const int r = rs / g.kw, sx = rs - r * g.kw;
         const int32_t c0 = cc * C::BKC;
         // box origin in INPUT coordinates (may be negative: zero padding = OOB fill)
         const int32_t iw = ow0 * g.sw - g.pw + sx * g.dw;
         const int32_t ih = oh0 * g.sh - g.ph + r * g.dh;
-        ptx::tma_load_4d(st + C::OFF_XR, &tm_xr, fb, c0, iw, ih, b);
-        ptx::tma_load_4d(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
-        if constexpr (kVD) ptx::tma_load_4d(st + C::OFF_Q, &tm_q, fb, c0, iw, ih, b);
         const int32_t wrow = rs * g.Op + n0;
-        ptx::tma_load_2d(st + C::OFF_UV, &tm_u, fb, c0, wrow);
-        ptx::tma_load_2d(st + C::OFF_UV + C::A_TILE / 2, &tm_v, fb, c0, wrow);
-        if constexpr (kVD) ptx::tma_load_2d(st + C::OFF_E, &tm_e, fb, c0, wrow);
+        if (elected) {
+          ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
+          ptx::tma_load_4d(st + C::OFF_XR, &tm_xr, fb, c0, iw, ih, b);
+          ptx::tma_load_4d(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
+          if constexpr (kVD) ptx::tma_load_4d(st + C::OFF_Q, &tm_q, fb, c0, iw, ih, b);
+          ptx::tma_load_2d(st + C::OFF_UV, &tm_u, fb, c0, wrow);
+          ptx::tma_load_2d(st + C::OFF_UV + C::A_TILE / 2, &tm_v, fb, c0, wrow);
+          if constexpr (kVD) ptx::tma_load_2d(st + C::OFF_E, &tm_e, fb, c0, wrow);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool elected = ptx::elect_one();
       constexpr uint32_t idesc128 = ptx::make_idesc<C::kBF16>(128, 128, false, false);
       constexpr uint32_t idesc64 = ptx::make_idesc<C::kBF16>(128, 64, false, false);
       const uint32_t t_d1 = tmem_base, t_d2 = tmem_base + 128, t_s2 = tmem_base + 256;
@@ -276,18 +285,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
         const uint64_t a_q = ptx::make_kmajor_desc<128>(st + C::OFF_Q);
         const uint64_t b_uv = ptx::make_kmajor_desc<128>(st + C::OFF_UV);
         const uint64_t b_e = ptx::make_kmajor_desc<128>(st + C::OFF_E);
+        if (elected) {
 #pragma unroll
-        for (int k = 0; k < C::KSTEPS; ++k) {
-          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-          const uint32_t off = k * 32;
-          ptx::umma_ss<C::kBF16>(t_d1, ptx::desc_advance(a_r, off), ptx::desc_advance(b_uv, off), idesc128, acc);
-          ptx::umma_ss<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc128, acc);
-          if constexpr (kVD)
-            ptx::umma_ss<C::kBF16>(t_s2, ptx::desc_advance(a_q, off), ptx::desc_advance(b_e, off), idesc64, acc);
+          for (int k = 0; k < C::KSTEPS; ++k) {
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            const uint32_t off = k * 32;
+            ptx::umma_ss<C::kBF16>(t_d1, ptx::desc_advance(a_r, off), ptx::desc_advance(b_uv, off), idesc128, acc);
+            ptx::umma_ss<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc128, acc);
+            if constexpr (kVD)
+              ptx::umma_ss<C::kBF16>(t_s2, ptx::desc_advance(a_q, off), ptx::desc_advance(b_e, off), idesc64, acc);
+          }
+          ptx::umma_commit(bar_empty + 8 * s);
         }
-        ptx::umma_commit(bar_empty + 8 * s);
+        __syncwarp();
       }
-      ptx::umma_commit(bar_accum);
+      if (elected) ptx::umma_commit(bar_accum);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ epilogue
@@ -388,7 +401,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
           im += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_im) + o));
         }
         if constexpr (kVD) {
-          const float sd = sqrtf(fmaxf(__uint_as_float(s2r[j]), 1e-8f));
+          const float sd = sd_of(__uint_as_float(s2r[j]));
           re = fmaf(nre[cc * 8 + j], sd, re);
           im = fmaf(nim[cc * 8 + j], sd, im);
         }
@@ -488,7 +501,8 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_xr,
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const bool elected = ptx::elect_one();
       uint32_t kbg = 0;  // k-blocks issued so far, across tiles
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int b, oh0, ow0, n0;
@@ -497,22 +511,26 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_xr,
           const uint32_t s = kbg % C::STAGES, ph = (kbg / C::STAGES) & 1u;
           ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
           const uint32_t fb = bar_full + 8 * s, st = base + s * C::STAGE_BYTES;
-          ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
           const int rs = kb / cchunks, cc = kb - rs * cchunks;
           const int r = rs / g.kw, sx = rs - r * g.kw;
           const int32_t c0 = cc * C::BKC;
           const int32_t iw = ow0 * g.sw - g.pw + sx * g.dw;
           const int32_t ih = oh0 * g.sh - g.ph + r * g.dh;
-          ptx::tma_load_4d(st + C::OFF_XR, &tm_xr, fb, c0, iw, ih, b);
-          ptx::tma_load_4d(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
           const int32_t wrow = rs * g.Op + n0;
-          ptx::tma_load_2d(st + C::OFF_UV, &tm_u, fb, c0, wrow);
-          ptx::tma_load_2d(st + C::OFF_UV + C::A_TILE / 2, &tm_v, fb, c0, wrow);
+          if (elected) {
+            ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
+            ptx::tma_load_4d(st + C::OFF_XR, &tm_xr, fb, c0, iw, ih, b);
+            ptx::tma_load_4d(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
+            ptx::tma_load_2d(st + C::OFF_UV, &tm_u, fb, c0, wrow);
+            ptx::tma_load_2d(st + C::OFF_UV + C::A_TILE / 2, &tm_v, fb, c0, wrow);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool elected = ptx::elect_one();
       constexpr uint32_t idesc = ptx::make_idesc<C::kBF16>(128, 128, false, false);
       uint32_t kbg = 0, it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -528,16 +546,20 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_xr,
           const uint64_t a_r = ptx::make_kmajor_desc<128>(st + C::OFF_XR);
           const uint64_t a_i = ptx::make_kmajor_desc<128>(st + C::OFF_XI);
           const uint64_t b_uv = ptx::make_kmajor_desc<128>(st + C::OFF_UV);
+          if (elected) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            const uint32_t off = k * 32;
-            ptx::umma_ss<C::kBF16>(t_d1, ptx::desc_advance(a_r, off), ptx::desc_advance(b_uv, off), idesc, acc);
-            ptx::umma_ss<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc, acc);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+              const uint32_t off = k * 32;
+              ptx::umma_ss<C::kBF16>(t_d1, ptx::desc_advance(a_r, off), ptx::desc_advance(b_uv, off), idesc, acc);
+              ptx::umma_ss<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc, acc);
+            }
+            ptx::umma_commit(bar_empty + 8 * s);
           }
-          ptx::umma_commit(bar_empty + 8 * s);
+          __syncwarp();
         }
-        ptx::umma_commit(bar_tfull + 8 * buf);
+        if (elected) ptx::umma_commit(bar_tfull + 8 * buf);
+        __syncwarp();
       }
     }
   } else {

@@ -75,7 +75,7 @@ __device__ __forceinline__ void epilogue_run(const EpiParams& p, int64_t m, int6
     store_s2_run<T, C>(p, row_off, n0, nvalid, s2);
     float sd[C];
 #pragma unroll
-    for (int j = 0; j < C; ++j) sd[j] = sqrtf(fmaxf(s2[j], 1e-8f));
+    for (int j = 0; j < C; ++j) sd[j] = sd_of(s2[j]);
 
     if (p.noise.mode == CPLXK_NOISE_INJECT) {
       const T* er = static_cast<const T*>(p.eps_re) + row_off + n0;
@@ -282,7 +282,7 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams& p, int64_t m, i
   store_s2_run<T, C>(p, row_off, n0, nvalid, s2);
 #pragma unroll
   for (int j = 0; j < C; ++j) {
-    const float sd = sqrtf(fmaxf(s2[j], 1e-8f));
+    const float sd = sd_of(s2[j]);
     re[j] = fmaf(nre[j], sd, re[j]);
     if constexpr (kCplx) im[j] = fmaf(nim[j], sd, im[j]);
   }

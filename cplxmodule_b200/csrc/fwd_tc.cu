@@ -149,26 +149,34 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (whole warp in the loop, one elected lane issues: keeps addresses in uniform registers)
+    {
+      const bool elected = ptx::elect_one();
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % C::STAGES;
         const uint32_t ph = (kb / C::STAGES) & 1;
         ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
         const uint32_t fb = bar_full + 8 * s;
         const uint32_t st = base + s * C::STAGE_BYTES;
-        ptx::mbar_arrive_expect_tx(fb, C::LOAD_BYTES);
         const int32_t k0 = kb * C::BK;
-        ptx::tma_load_2d(st + C::OFF_A0, &tm_xr, fb, k0, m0);
-        if constexpr (kCplx) ptx::tma_load_2d(st + C::OFF_A1, &tm_xi, fb, k0, m0);
-        ptx::tma_load_2d(st + C::OFF_B0, &tm_wr, fb, k0, n0);
-        if constexpr (kCplx) ptx::tma_load_2d(st + C::OFF_B1, &tm_wi, fb, k0, n0);
-        if constexpr (kVD) ptx::tma_load_2d(st + C::OFF_E, &tm_ls, fb, k0, n0);  // log_sigma2 or exp() of it
-        if constexpr (kVD && !kXform) ptx::tma_load_2d(st + C::OFF_Q, &tm_q, fb, k0, m0);
+        if (elected) {
+          ptx::mbar_arrive_expect_tx(fb, C::LOAD_BYTES);
+          ptx::tma_load_2d(st + C::OFF_A0, &tm_xr, fb, k0, m0);
+          if constexpr (kCplx) ptx::tma_load_2d(st + C::OFF_A1, &tm_xi, fb, k0, m0);
+          ptx::tma_load_2d(st + C::OFF_B0, &tm_wr, fb, k0, n0);
+          if constexpr (kCplx) ptx::tma_load_2d(st + C::OFF_B1, &tm_wi, fb, k0, n0);
+          if constexpr (kVD) ptx::tma_load_2d(st + C::OFF_E, &tm_ls, fb, k0, n0);  // log_sigma2 or exp() of it
+          if constexpr (kVD && !kXform) ptx::tma_load_2d(st + C::OFF_Q, &tm_q, fb, k0, m0);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the loop, one elected lane issues: with warp-uniform control flow the
+    // descriptors live in uniform registers (~3 issue slots per tcgen05.mma instead of ~12).
+    {
+      const bool elected = ptx::elect_one();
       constexpr uint32_t idesc = ptx::make_idesc<C::kBF16>(C::BM, C::BN, false, false);
       constexpr uint32_t idesc_na = ptx::make_idesc<C::kBF16>(C::BM, C::BN, true, false);
       const uint32_t t_re = tmem_base;
@@ -187,13 +195,16 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__
         }
         const uint64_t aq = ptx::make_kmajor_desc<kSwz>(st + C::OFF_Q);
         const uint64_t be = ptx::make_kmajor_desc<kSwz>(st + C::OFF_E);
+        if (elected) {
 #pragma unroll
-        for (int k = 0; k < C::KSTEPS; ++k) {
-          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-          const uint32_t off = k * 32;
-          ptx::umma_ss<C::kBF16>(t_s2, ptx::desc_advance(aq, off), ptx::desc_advance(be, off), idesc, acc);
+          for (int k = 0; k < C::KSTEPS; ++k) {
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            const uint32_t off = k * 32;
+            ptx::umma_ss<C::kBF16>(t_s2, ptx::desc_advance(aq, off), ptx::desc_advance(be, off), idesc, acc);
+          }
+          ptx::umma_commit(bar_empty + 8 * s);  // stage reusable once everything issued so far retires
         }
-        ptx::umma_commit(bar_empty + 8 * s);  // stage reusable once everything issued so far retires
+        __syncwarp();
       };
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % C::STAGES;
@@ -205,27 +216,32 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__
         const uint64_t a1 = ptx::make_kmajor_desc<kSwz>(st + C::OFF_A1);
         const uint64_t b0 = ptx::make_kmajor_desc<kSwz>(st + C::OFF_B0);
         const uint64_t b1 = ptx::make_kmajor_desc<kSwz>(st + C::OFF_B1);
+        if (elected) {
 #pragma unroll
-        for (int k = 0; k < C::KSTEPS; ++k) {
-          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-          const uint32_t off = k * 32;
-          ptx::umma_ss<C::kBF16>(t_re, ptx::desc_advance(a0, off), ptx::desc_advance(b0, off), idesc, acc);
-          if constexpr (kCplx) {
-            ptx::umma_ss<C::kBF16>(t_re, ptx::desc_advance(a1, off), ptx::desc_advance(b1, off), idesc_na, 1u);
-            ptx::umma_ss<C::kBF16>(t_im, ptx::desc_advance(a0, off), ptx::desc_advance(b1, off), idesc, acc);
-            ptx::umma_ss<C::kBF16>(t_im, ptx::desc_advance(a1, off), ptx::desc_advance(b0, off), idesc, 1u);
+          for (int k = 0; k < C::KSTEPS; ++k) {
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            const uint32_t off = k * 32;
+            ptx::umma_ss<C::kBF16>(t_re, ptx::desc_advance(a0, off), ptx::desc_advance(b0, off), idesc, acc);
+            if constexpr (kCplx) {
+              ptx::umma_ss<C::kBF16>(t_re, ptx::desc_advance(a1, off), ptx::desc_advance(b1, off), idesc_na, 1u);
+              ptx::umma_ss<C::kBF16>(t_im, ptx::desc_advance(a0, off), ptx::desc_advance(b1, off), idesc, acc);
+              ptx::umma_ss<C::kBF16>(t_im, ptx::desc_advance(a1, off), ptx::desc_advance(b0, off), idesc, 1u);
+            }
           }
         }
+        __syncwarp();
         if constexpr (kVD && kXform) {
           if (kb > 0) issue_var(kb - 1);
         } else if constexpr (kVD) {
           issue_var(kb);  // operands landed with the same TMA transaction group
         } else {
-          ptx::umma_commit(bar_empty + 8 * s);
+          if (elected) ptx::umma_commit(bar_empty + 8 * s);
+          __syncwarp();
         }
       }
       if constexpr (kVD && kXform) issue_var(num_kb - 1);
-      ptx::umma_commit(bar_accum);  // accumulators complete
+      if (elected) ptx::umma_commit(bar_accum);  // accumulators complete
+      __syncwarp();
     }
   } else {
     // -------------------------------------------------- transform, then epilogue

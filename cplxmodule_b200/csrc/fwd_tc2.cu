@@ -124,26 +124,34 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
 
   if (warp == 0) {
     // ---------------------------------------------- TMA producer (one per CTA of the pair)
-    if (lane == 0 && p.dbg != 1) {
+    // (whole warp in the loop, one elected lane issues: see the MMA issuer)
+    if (p.dbg != 1) {
+      const bool elected = ptx::elect_one();
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % C::STAGES;
         const uint32_t ph = (kb / C::STAGES) & 1;
         ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
         const uint32_t fb = bar_full + 8 * s;
         const uint32_t st = base + s * C::STAGE_BYTES;
-        if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * C::STAGE_BYTES);   // both CTAs' bytes
         const int32_t k0 = kb * C::BK;
-        ptx::tma_load_2d_pair(st + C::OFF_A0, &tm_xr, fb, k0, m0);
-        if constexpr (kCplx) ptx::tma_load_2d_pair(st + C::OFF_A1, &tm_xi, fb, k0, m0);
-        ptx::tma_load_2d_pair(st + C::OFF_Q, &tm_q, fb, k0, m0);
-        ptx::tma_load_2d_pair(st + C::OFF_B0, &tm_wr, fb, k0, nb0);
-        if constexpr (kCplx) ptx::tma_load_2d_pair(st + C::OFF_B1, &tm_wi, fb, k0, nb0);
-        ptx::tma_load_2d_pair(st + C::OFF_E, &tm_e, fb, k0, nb0);
+        if (elected) {
+          if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * C::STAGE_BYTES);   // both CTAs' bytes
+          ptx::tma_load_2d_pair(st + C::OFF_A0, &tm_xr, fb, k0, m0);
+          if constexpr (kCplx) ptx::tma_load_2d_pair(st + C::OFF_A1, &tm_xi, fb, k0, m0);
+          ptx::tma_load_2d_pair(st + C::OFF_Q, &tm_q, fb, k0, m0);
+          ptx::tma_load_2d_pair(st + C::OFF_B0, &tm_wr, fb, k0, nb0);
+          if constexpr (kCplx) ptx::tma_load_2d_pair(st + C::OFF_B1, &tm_wi, fb, k0, nb0);
+          ptx::tma_load_2d_pair(st + C::OFF_E, &tm_e, fb, k0, nb0);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer: leader only
-    if (leader && lane == 0) {
+    // The whole warp walks the loop, one elected lane issues: warp-uniform control flow keeps the
+    // descriptors in uniform registers (~3 issue slots per tcgen05.mma instead of ~12).
+    if (leader) {
+      const bool elected = ptx::elect_one();
       // a/b format field: 0 = fp16 (scaled operands), 1 = bf16, 2 = tf32
       constexpr uint32_t fmt_fix = C::kHalfOps ? (1u << 7) | (1u << 10) : 0u;   // clears bf16 -> fp16
       constexpr uint32_t idesc = ptx::make_idesc<C::kBF16>(256, C::BN, false, false) ^ fmt_fix;
@@ -157,7 +165,8 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
         if (p.dbg != 1) ptx::mbar_wait(bar_full + 8 * s, ph);
         ptx::tcgen05_fence_after();
         if (p.dbg == 2) {
-          ptx::umma_commit_pair(bar_empty + 8 * s);
+          if (elected) ptx::umma_commit_pair(bar_empty + 8 * s);
+          __syncwarp();
           continue;
         }
         const uint64_t a0 = ptx::make_kmajor_desc<128>(st + C::OFF_A0);
@@ -166,6 +175,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
         const uint64_t b0 = ptx::make_kmajor_desc<128>(st + C::OFF_B0);
         const uint64_t b1 = ptx::make_kmajor_desc<128>(st + C::OFF_B1);
         const uint64_t be = ptx::make_kmajor_desc<C::VAR_SWZ>(st + C::OFF_E);
+        if (elected) {
 #pragma unroll
         for (int k = 0; k < C::KSTEPS; ++k) {
           const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
@@ -189,8 +199,11 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
           }
         }
         ptx::umma_commit_pair(bar_empty + 8 * s);   // frees the stage in BOTH CTAs
+        }
+        __syncwarp();
       }
-      ptx::umma_commit_pair(bar_accum);
+      if (elected) ptx::umma_commit_pair(bar_accum);
+      __syncwarp();
     }
   } else {
     // -------------------------------------- 8 epilogue warps: noise prefetch, then drain

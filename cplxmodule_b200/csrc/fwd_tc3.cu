@@ -343,7 +343,7 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
         for (int j = 0; j < 8; ++j) {
           const float sc = sxm * cvb[256 + col + j];
           f_s2[j] = __uint_as_float(r_s2[j]);
-          const float sd = sqrtf(fmaxf(f_s2[j], 1e-8f));
+          const float sd = sd_of(f_s2[j]);
           nre[col + j] = fmaf(nre[col + j], sd, fmaf(__uint_as_float(r_re[j]), sc, cvb[col + j]));
           if constexpr (kCplx)
             nim[col + j] = fmaf(nim[col + j], sd, fmaf(__uint_as_float(r_im[j]), sc, cvb[128 + col + j]));
@@ -377,7 +377,7 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
 // pass writes the variance-GEMM operands |x|^2 and exp(log_sigma2) as bf16 (unscaled: bf16 has
 // fp32's range).  K % 8 == 0.
 template <bool kCplx>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im, int64_t M,
                       const float* __restrict__ w_re, const float* __restrict__ w_im,
                       const float* __restrict__ ls2, int64_t N, int64_t K,
@@ -386,7 +386,7 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
                       __half* __restrict__ wh_im, __nv_bfloat16* __restrict__ e,
                       float* __restrict__ isx, float* __restrict__ isw, int kl_kind,
                       float* __restrict__ kl_sum, KlWorkspace* __restrict__ kl_ws) {
-  constexpr int kCache = 4;                  // 8-element groups per thread kept in registers (K <= 8192)
+  constexpr int kCache = 2;                  // 8-element groups per thread kept in registers (K <= 4096)
   __shared__ float red[8];
   __shared__ double kl_sh[kKlThreads / 32];
   __shared__ bool kl_last;

@@ -48,6 +48,7 @@ def row(name, ms, flops, nbytes, note=""):
 
 def main():
     torch.manual_seed(0)
+    cb.set_kl_fusion(False)      # forward and KL are timed as separate calls here
     out = []
     with torch.no_grad():
         # 1. real LinearVD 784 -> 256, batch 128, forward + penalties (launch-latency bound)
