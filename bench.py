@@ -96,7 +96,11 @@ class ClockSampler:
 
 
 # dram bytes (read + write) per launch from the committed ncu --set full captures (profiles/)
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {
+    "gemm_f32": 630.05e6 + 198.14e6,     # profiles/prof_tc3_f32_r1.raw.csv  (fwd_tc3_kernel<float, cplx>)
+    "gemm_bf16": 626.42e6 + 133.92e6,    # profiles/prof_tc3_bf16_r1.raw.csv
+    "prepass_f32": 335.61e6 + 176.92e6,  # profiles/prof_prep_f32_r1.raw.csv (vd_prepare_f16_kernel<cplx>)
+}
 
 
 # ----------------------------------------------------------------------------- CPU side
