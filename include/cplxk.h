@@ -112,11 +112,14 @@ int cplxk_linear_fwd(const void* x_re, const void* x_im,
  *                            philox_threads = 256 * grid of torch's randn kernel
  *                            (only used by PHILOX_TORCH).
  *   workspace (nullable)   : cplxk_linear_vd_workspace_bytes() bytes, 16-byte aligned,
- *                            uninitialised scratch.  With it the call first writes the two
- *                            derived GEMM operands |x|^2 [M,K] and exp(log_sigma2) [N,K]
- *                            there (one elementwise launch) and the GEMM kernel streams them
- *                            by TMA; without it they are produced inside the GEMM kernel's
- *                            shared-memory pipeline (one launch, slower mainloop).
+ *                            uninitialised scratch.  With it the call first writes the GEMM
+ *                            operands there (one pre-pass launch) and the GEMM kernel streams
+ *                            them by TMA: for F32 planes per-row power-of-two scaled fp16
+ *                            copies of x and W, bf16 |x|^2 and exp(log_sigma2), and the
+ *                            inverse row scales (M > 128, K >= 64, K % 8 == 0; otherwise, and
+ *                            for BF16 planes, only |x|^2 [M,K] and exp(log_sigma2) [N,K]);
+ *                            without it the derived operands are produced inside the GEMM
+ *                            kernel's shared-memory pipeline (one launch, slower mainloop).
  */
 size_t cplxk_linear_vd_workspace_bytes(int64_t M, int64_t N, int64_t K, int dtype);
 int cplxk_linear_vd_fwd(const void* x_re, const void* x_im,
