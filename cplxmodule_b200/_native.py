@@ -44,7 +44,8 @@ def _declare(lib):
                                         + [_i64] * 3 + [_int, _int, _vp, _vp, ctypes.c_size_t, _vp])
     lib.cplxk_linear_vd_fwd_kl.argtypes = ([_vp] * 9 + [_int, _u64, _u64, _u32] + [_vp] * 2
                                            + [_i64] * 3 + [_int, _int, _vp, _vp, ctypes.c_size_t]
-                                           + [_int, _vp, _vp, ctypes.c_size_t, ctypes.POINTER(_int), _vp])
+                                           + [_int, _vp, _vp, ctypes.c_size_t, _i64, _i64, _vp,
+                                              ctypes.POINTER(_int), _vp])
     lib.cplxk_linear_vd_workspace_bytes.restype = ctypes.c_size_t
     lib.cplxk_linear_vd_workspace_bytes.argtypes = [_i64, _i64, _i64, _int]
     lib.cplxk_kl_workspace_bytes.restype = ctypes.c_size_t

@@ -60,7 +60,7 @@ static int forward_common(bool vd, const void* x_re, const void* x_im, const voi
                           const void* eps_re, const void* eps_im, int noise, uint64_t seed,
                           uint64_t offset, uint32_t threads, void* y_re, void* y_im, int64_t M,
                           int64_t N, int64_t K, int dtype, int math, void* s2_out, void* workspace,
-                          size_t workspace_bytes, void* stream, KlFuse kl = KlFuse{-1, nullptr, nullptr},
+                          size_t workspace_bytes, void* stream, KlFuse kl = KlFuse{-1, nullptr, nullptr, 0, -1, nullptr},
                           int* kl_done = nullptr) {
   if (kl_done) *kl_done = 0;
   if (!x_re || !w_re || !y_re || M < 0 || N < 0 || K < 0) return CPLXK_ERR_BADARG;
@@ -174,16 +174,19 @@ extern "C" int cplxk_linear_vd_fwd_kl(const void* x_re, const void* x_im, const 
                                       int64_t N, int64_t K, int dtype, int math, void* s2_out,
                                       void* workspace, size_t workspace_bytes, int kl_kind,
                                       float* kl_sum, void* kl_workspace, size_t kl_workspace_bytes,
+                                      int64_t kl_row_begin, int64_t kl_row_end, void* kl_event,
                                       int* kl_done, void* stream) {
   if (kl_done) *kl_done = 0;
-  KlFuse kl{-1, nullptr, nullptr};
+  KlFuse kl{-1, nullptr, nullptr, 0, -1, nullptr};
   if (kl_kind >= 0) {
     const bool cplx_kind = kl_kind == CPLXK_KL_CPLX_VD || kl_kind == CPLXK_KL_CPLX_ARD;
     if (kl_kind > CPLXK_KL_CPLX_ARD || cplx_kind != (w_im != nullptr) || !kl_sum || !kl_done)
       return CPLXK_ERR_BADARG;
     if (!kl_workspace || kl_workspace_bytes < cplxk_kl_workspace_bytes()) return CPLXK_ERR_WORKSPACE;
     if (!aligned16(kl_workspace)) return CPLXK_ERR_ALIGN;
-    kl = KlFuse{kl_kind, kl_sum, kl_workspace};
+    if (kl_row_begin < 0 || kl_row_end > N || (kl_row_end >= 0 && kl_row_end < kl_row_begin))
+      return CPLXK_ERR_BADARG;
+    kl = KlFuse{kl_kind, kl_sum, kl_workspace, kl_row_begin, kl_row_end, kl_event};
   }
   return forward_common(true, x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise,
                         seed, offset, philox_threads, y_re, y_im, M, N, K, dtype, math, s2_out,

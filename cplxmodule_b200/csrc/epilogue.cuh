@@ -26,8 +26,11 @@ struct EpiParams {
 // pre-pass on the weight rows it reads anyway (kind < 0: not requested)
 struct KlFuse {
   int kind;
-  float* sum;   // device float
-  void* ws;     // KlWorkspace
+  float* sum;            // device float
+  void* ws;              // KlWorkspace
+  int64_t row_begin = 0; // weight rows [row_begin, row_end) enter the sum (a rank's KL shard);
+  int64_t row_end = -1;  // row_end < 0: all rows
+  void* event = nullptr; // cudaEvent_t recorded right after the pre-pass launch (nullable)
 };
 
 template <typename T, int C>

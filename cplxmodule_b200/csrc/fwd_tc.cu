@@ -471,7 +471,7 @@ size_t fwd_tc3_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K);
 bool fwd_tc3_supported(int dtype, int64_t M, int64_t N, int64_t K);
 int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                 const void* ls2, void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
-                cudaStream_t st, int kl_kind, float* kl_sum, void* kl_ws);
+                cudaStream_t st, const KlFuse& kl);
 int fwd_tc3_bf16(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                  const void* q, const void* e, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
                  cudaStream_t st);
@@ -517,8 +517,7 @@ static int launch_tc(const void* x_re, const void* x_im, const void* w_re, const
     if (!short_k && fwd_tc3_supported(std::is_same<T, float>::value ? CPLXK_F32 : CPLXK_BF16, M, N, K)) {
       if constexpr (std::is_same<T, float>::value) {
         if (!(f16e && f16e[0] == '0'))
-          return fwd_tc3_f32(kCplx, x_re, x_im, w_re, w_im, ls2, workspace, M, N, K, ep, st,
-                             kl.kind, kl.sum, kl.ws);
+          return fwd_tc3_f32(kCplx, x_re, x_im, w_re, w_im, ls2, workspace, M, N, K, ep, st, kl);
       } else if (persist) {
         const int64_t work3 = (M * K + N * K) / Elem<T>::kVec;
         const int grid3 = static_cast<int>(work3 / 256 + 1 > 148 * 16 ? 148 * 16 : work3 / 256 + 1);

@@ -385,7 +385,8 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
                       __nv_bfloat16* __restrict__ q, __half* __restrict__ wh_re,
                       __half* __restrict__ wh_im, __nv_bfloat16* __restrict__ e,
                       float* __restrict__ isx, float* __restrict__ isw, int kl_kind,
-                      float* __restrict__ kl_sum, KlWorkspace* __restrict__ kl_ws) {
+                      float* __restrict__ kl_sum, KlWorkspace* __restrict__ kl_ws,
+                      int64_t kl_row0, int64_t kl_row1) {
   constexpr int kCache = 2;                  // 8-element groups per thread kept in registers (K <= 4096)
   __shared__ float red[8];
   __shared__ double kl_sh[kKlThreads / 32];
@@ -474,7 +475,7 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
       } else {
         const float4 l0 = __ldg(reinterpret_cast<const float4*>(pl + k));
         const float4 l1 = __ldg(reinterpret_cast<const float4*>(pl + k + 4));
-        if (kl_kind >= 0) {   // the weights and log_sigma2 are in registers anyway: KL for free
+        if (kl_kind >= 0 && r >= kl_row0 && r < kl_row1) {   // weights and log_sigma2 are in registers anyway
           const float l[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) kl_acc += penalty_any(kl_kind, vr[j], kCplx ? vi[j] : 0.f, l[j]);
@@ -589,7 +590,10 @@ static int launch_tc3(const Tc3Operands& o, int64_t M, int64_t N, int64_t K, con
     CPLXK_CUDA_TRY(cudaGetDevice(&dev));
     CPLXK_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  int64_t clusters = sm_count / 2;
+  // CPLXK_SM_RESERVE=n leaves n SMs to kernels of other streams (a collective, the KL shard
+  // kernel): a persistent grid that owns every SM would make them wait for its last tile
+  const char* rsv = std::getenv("CPLXK_SM_RESERVE");
+  int64_t clusters = (sm_count - (rsv ? std::atoi(rsv) : 0)) / 2;
   if (clusters < 1) clusters = 1;
   if (clusters > pairs) clusters = pairs;
   auto kern = fwd_tc3_kernel<OutT, kCplx>;
@@ -625,7 +629,7 @@ int fwd_tc2_half_dispatch(bool cplx, const void* xh_re, const void* xh_im, const
 // (CPLXK_PERSIST=0) or, by default, the persistent kernel above.
 int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                 const void* ls2, void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
-                cudaStream_t st, int kl_kind, float* kl_sum, void* kl_ws) {
+                cudaStream_t st, const KlFuse& kl) {
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const size_t xb = align256(static_cast<size_t>(M) * K * 2), wb = align256(static_cast<size_t>(N) * K * 2);
   __half* xh_re = reinterpret_cast<__half*>(ws);
@@ -638,20 +642,24 @@ int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re,
   float* isw = reinterpret_cast<float*>(ws + 3 * xb + 3 * wb + align256(static_cast<size_t>(M) * 4));
   const int64_t rows = M + N;
   const int grid = static_cast<int>(rows > 148 * 8 ? 148 * 8 : rows);   // <= kKlMaxBlocks partials
-  if (!kl_sum || !kl_ws) kl_kind = -1;
-  auto kws = static_cast<KlWorkspace*>(kl_ws);
+  const int kl_kind = (kl.sum && kl.ws) ? kl.kind : -1;
+  float* kl_sum = kl.sum;
+  auto kws = static_cast<KlWorkspace*>(kl.ws);
+  const int64_t kl_row0 = kl.row_begin, kl_row1 = kl.row_end < 0 ? N : kl.row_end;
   if (cplx)
     vd_prepare_f16_kernel<true><<<grid, 256, 0, st>>>(
         static_cast<const float*>(x_re), static_cast<const float*>(x_im), M,
         static_cast<const float*>(w_re), static_cast<const float*>(w_im),
         static_cast<const float*>(ls2), N, K, xh_re, xh_im, q, wh_re, wh_im, e, isx, isw, kl_kind,
-        kl_sum, kws);
+        kl_sum, kws, kl_row0, kl_row1);
   else
     vd_prepare_f16_kernel<false><<<grid, 256, 0, st>>>(
         static_cast<const float*>(x_re), nullptr, M, static_cast<const float*>(w_re), nullptr,
         static_cast<const float*>(ls2), N, K, xh_re, nullptr, q, wh_re, nullptr, e, isx, isw, kl_kind,
-        kl_sum, kws);
+        kl_sum, kws, kl_row0, kl_row1);
   CPLXK_CUDA_TRY(cudaGetLastError());
+  // the KL (partial) sum is final here: let a collective on another stream start under the GEMM
+  if (kl.event) CPLXK_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(kl.event), st));
   const char* dbg_env = std::getenv("CPLXK_DBG");
   if (dbg_env && std::atoi(dbg_env) == 4) return CPLXK_OK;   // measurement aid: pre-pass only
   const char* pe = std::getenv("CPLXK_PERSIST");

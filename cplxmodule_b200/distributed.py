@@ -25,23 +25,38 @@ def _layer_planes(mod):
     return w, None
 
 
-def _default_partial(mod, lo, hi):
+def _default_partial(mod, lo, hi, stream=None):
+    """Partial KL sum of weight rows [lo, hi): the by-product of this step's forward when it was
+    asked for that shard (``ops.set_kl_shard``; no extra pass over the parameters), else the
+    stand-alone kernel on the row slice."""
     w_re, w_im = _layer_planes(mod)
     if hi <= lo:
         return torch.zeros((), dtype=torch.float32, device=w_re.device)
+    cache = mod.__dict__.get("_kl_cache")
+    if cache is not None:
+        params = (w_re, mod.log_sigma2) if w_im is None else (w_re, w_im, mod.log_sigma2)
+        pre, event = cache.take(params, rows=(lo, hi), with_event=True)
+        if pre is not None:
+            if stream is not None and event is not None:
+                stream.wait_event(event)     # final right after the pre-pass: do not wait for the GEMM
+                pre.record_stream(stream)
+            return pre
     return ops.kl(mod._kl_kind, w_re[lo:hi], None if w_im is None else w_im[lo:hi],
                   mod.log_sigma2[lo:hi], "sum").float()
 
 
-def sharded_penalties(module, group=None, partial_fn=None):
+def sharded_penalties(module, group=None, partial_fn=None, stream=None):
     """``sum``-reduced penalties of every variational layer, each computed on this rank's row
     shard and combined with a single all-reduce.  Returns ``(names, tensor[n_layers])``.
 
     ``partial_fn(mod, lo, hi) -> 0-d tensor`` overrides the shard kernel (tests use it to
-    exercise the sharding logic on CPU/gloo)."""
+    exercise the sharding logic on CPU/gloo).  ``stream``: the (current) side stream the call is
+    made under; partial sums that come from the forward's pre-pass are then waited for through
+    their own event instead of the whole forward, so the collective overlaps the GEMM."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    partial_fn = partial_fn or _default_partial
+    if partial_fn is None:
+        partial_fn = lambda mod, lo, hi: _default_partial(mod, lo, hi, stream)  # noqa: E731
     names, parts = [], []
     for name, mod in module.named_modules():
         if not isinstance(mod, BaseARD) or not hasattr(mod, "log_sigma2"):

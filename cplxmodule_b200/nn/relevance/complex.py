@@ -65,7 +65,7 @@ class CplxLinearGaussian(_CplxGaussianMixin, CplxLinear):
         b_re, b_im = (None, None) if b is None else (b.real, b.imag)
         eps = None if eps is None else (eps.real, eps.imag)
         # the operand pre-pass reads every weight: it hands back the KL sum for penalties()
-        kl_req = {"kind": self._kl_kind} if self._kl_kind is not None else None
+        kl_req = ops.kl_request(self._kl_kind, self.log_sigma2.shape[0])
         re, im = ops.cplx_linear_vd(input.real, input.imag, w.real, w.imag, b_re, b_im,
                                     self.log_sigma2, eps=eps, kl_req=kl_req)
         cache = self.__dict__.get("_kl_cache")

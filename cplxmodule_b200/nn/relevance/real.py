@@ -27,7 +27,7 @@ class _RealGaussianLinear(torch.nn.Linear):
     def forward(self, input, eps=None):
         if not self.training:
             return ops.real_linear(input, self.weight, self.bias)
-        kl_req = {"kind": self._kl_kind} if self._kl_kind is not None else None
+        kl_req = ops.kl_request(self._kl_kind, self.log_sigma2.shape[0])
         out = ops.real_linear_vd(input, self.weight, self.bias, self.log_sigma2, eps=eps,
                                  kl_req=kl_req)
         cache = self.__dict__.get("_kl_cache")

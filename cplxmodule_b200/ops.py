@@ -12,7 +12,7 @@ import torch
 
 from . import _native as nv
 
-_state = {"noise": "torch", "math": "auto", "prepare": True, "fuse_kl": True}
+_state = {"noise": "torch", "math": "auto", "prepare": True, "fuse_kl": True, "kl_shard": None}
 _MATH = {"auto": nv.MATH_AUTO, "tensor": nv.MATH_TENSOR, "simt": nv.MATH_SIMT}
 _NOISE = {"torch": nv.NOISE_PHILOX_TORCH, "fast": nv.NOISE_PHILOX_FAST}
 
@@ -49,6 +49,36 @@ def set_kl_fusion(enabled):
     _state["fuse_kl"] = bool(enabled)
 
 
+def set_kl_shard(rank=None, world=None):
+    """Multi-GPU: the KL by-product of a forward covers only this rank's block of weight rows
+    (``distributed.row_shard``); ``distributed.sharded_penalties`` all-reduces the partial sums.
+    ``set_kl_shard()`` (no arguments) returns to whole-layer sums."""
+    _state["kl_shard"] = None if rank is None or world is None or world <= 1 else (int(rank), int(world))
+
+
+def kl_request(kind, n_rows):
+    """The ``kl_req`` a layer passes to its training forward (None: nothing to ask for)."""
+    if kind is None or not _state["fuse_kl"]:
+        return None
+    req = {"kind": kind}
+    if _state["kl_shard"] is not None:
+        rank, world = _state["kl_shard"]
+        base, extra = divmod(n_rows, world)
+        lo = rank * base + min(rank, extra)
+        req["rows"] = (lo, lo + base + (1 if rank < extra else 0))
+    return req
+
+
+def set_sm_reserve(n_sms):
+    """Leave ``n_sms`` SMs out of the persistent GEMM grid so that kernels of other streams (a
+    collective, a KL shard kernel) do not wait for its last tile (0: use every SM)."""
+    import os
+    if n_sms:
+        os.environ["CPLXK_SM_RESERVE"] = str(int(n_sms))
+    else:
+        os.environ.pop("CPLXK_SM_RESERVE", None)
+
+
 def get_noise_mode():
     return _state["noise"]
 
@@ -65,8 +95,10 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
                  want_s2=False, math=None, kl_req=None):
     """Shared launcher. Returns (y_re, y_im|None, aux). ``noise`` is None for the plain map;
     ``aux`` = dict(s2=..., philox=(seed, offset, threads)) for the variational forward.
-    ``kl_req`` = {"kind": k}: ask the operand pre-pass for the layer's KL sum as a by-product;
-    when the path taken produced it, ``kl_req["sum"]`` is set to the 0-d float32 result."""
+    ``kl_req`` = {"kind": k[, "rows": (lo, hi)]}: ask the operand pre-pass for the layer's KL sum
+    (over the weight rows ``[lo, hi)``: a rank's shard) as a by-product; when the path taken
+    produced it, ``kl_req["sum"]`` is set to the 0-d float32 result and ``kl_req["event"]`` to a
+    CUDA event recorded right after the pre-pass (the sum is final there)."""
     dev = nv.require_cuda(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im)
     cplx = x_im is not None
     dt = w_re.dtype
@@ -110,14 +142,17 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
                 kl_sum = torch.empty((), dtype=torch.float32, device=dev)
                 kl_ws = nv.kl_workspace(dev)
                 done = ctypes.c_int(0)
+                lo, hi = kl_req.get("rows") or (0, -1)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))   # materialises the handle; re-recorded by the call
                 nv.check(lib.cplxk_linear_vd_fwd_kl(
                     nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi), nv.ptr(br), nv.ptr(bi),
                     nv.ptr(ls2), nv.ptr(er), nv.ptr(ei), noise, seed, offset, threads,
                     nv.ptr(y_re), nv.ptr(y_im), M, N, K, code, math, nv.ptr(s2), nv.ptr(ws),
                     ws_bytes, kl_req["kind"], nv.ptr(kl_sum), nv.ptr(kl_ws), kl_ws.numel() * 8,
-                    ctypes.byref(done), st))
+                    lo, hi, ctypes.c_void_p(ev.cuda_event), ctypes.byref(done), st))
                 if done.value:
-                    kl_req["sum"] = kl_sum
+                    kl_req["sum"], kl_req["event"] = kl_sum, ev
             else:
                 nv.check(lib.cplxk_linear_vd_fwd(nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi),
                                                  nv.ptr(br), nv.ptr(bi), nv.ptr(ls2), nv.ptr(er),
@@ -385,13 +420,14 @@ class FusedKLCache:
     def put(self, params, kl_req):
         self._entry = None
         if kl_req is not None and "sum" in kl_req:
-            self._entry = (self._key(params), kl_req["sum"])
+            self._entry = (self._key(params), kl_req["sum"], kl_req.get("rows"), kl_req.get("event"))
 
-    def take(self, params):
+    def take(self, params, rows=None, with_event=False):
+        """The cached sum if it covers ``rows`` (None: the whole layer) of unchanged parameters."""
         entry, self._entry = self._entry, None
-        if entry is not None and entry[0] == self._key(params):
-            return entry[1]
-        return None
+        if entry is not None and entry[0] == self._key(params) and entry[2] == rows:
+            return (entry[1], entry[3]) if with_event else entry[1]
+        return (None, None) if with_event else None
 
 
 # ------------------------------------------------------------------------- KL path

@@ -143,6 +143,12 @@ int cplxk_linear_vd_fwd(const void* x_re, const void* x_im,
  * path taken produced the sum (fp32 planes, tensor cores, workspace given, M > 128, K % 8 == 0)
  * and to 0 otherwise, in which case the caller runs cplxk_kl.  kl_kind < 0: plain forward.
  *   kl_workspace : cplxk_kl_workspace_bytes() bytes, as for cplxk_kl.
+ *   kl_row_begin, kl_row_end : only weight rows [begin, end) enter the sum (kl_row_end < 0: all
+ *                  N rows) -- a rank's shard of the row-sharded multi-GPU KL, whose partial
+ *                  sums are combined by ONE all-reduce;
+ *   kl_event     : cudaEvent_t (nullable) recorded on `stream` right after the pre-pass launch:
+ *                  *kl_sum is final there, so that all-reduce can run on another stream while
+ *                  the GEMM kernel computes.
  * Replaces the pair CplxLinearGaussian.forward + CplxVDMixin.penalty.sum()
  * (nn/relevance/complex/base.py:43-56, complex/vd.py:95-99, relevance/base.py:135-139).
  */
@@ -159,6 +165,7 @@ int cplxk_linear_vd_fwd_kl(const void* x_re, const void* x_im,
                            void* workspace, size_t workspace_bytes,
                            int kl_kind, float* kl_sum,
                            void* kl_workspace, size_t kl_workspace_bytes,
+                           int64_t kl_row_begin, int64_t kl_row_end, void* kl_event,
                            int* kl_done, void* stream);
 
 /*

@@ -190,3 +190,40 @@ def test_fused_kl_keeps_gradients():
     assert abs(outs[0] - outs[1]) <= 1e-6 * abs(outs[1])
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert torch.allclose(pa.grad, pb.grad, rtol=1e-5, atol=1e-7)
+
+
+def test_row_sharded_fused_kl_partials_add_up():
+    """multi-GPU layout on one device: each 'rank' asks its forward for the KL of its block of
+    weight rows; the partial sums equal the stand-alone kernel on the slices and add up to the
+    whole-layer KL (what the all-reduce computes)"""
+    from cplxmodule_b200.distributed import _default_partial, row_shard
+    torch.manual_seed(5)
+    layer = CplxLinearVD(128, 203).to(DEV).train()
+    with torch.no_grad():
+        layer.log_sigma2.uniform_(-10, 3)
+    x = cplx.randn(300, 128, device=DEV)
+    world, parts = 3, []
+    side = torch.cuda.Stream()
+    with torch.no_grad():
+        whole = float(ops.kl(layer._kl_kind, layer.weight.real, layer.weight.imag, layer.log_sigma2, "sum"))
+        for rank in range(world):
+            cb.set_kl_shard(rank, world)
+            try:
+                layer(x)
+                lo, hi = row_shard(203, rank, world)
+                assert layer._kl_cache._entry[2] == (lo, hi)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    part = _default_partial(layer, lo, hi, side)
+                torch.cuda.current_stream().wait_stream(side)
+                assert layer._kl_cache._entry is None          # consumed
+                w = layer.weight
+                ref = float(ops.kl(layer._kl_kind, w.real[lo:hi], w.imag[lo:hi], layer.log_sigma2[lo:hi], "sum"))
+                assert abs(float(part) - ref) <= 1e-6 * abs(ref)
+                parts.append(float(part))
+                # the whole-layer API must not hand out a shard's partial sum
+                layer(x)
+                assert abs(float(sum(penalties(layer))) - whole) <= 1e-6 * abs(whole)
+            finally:
+                cb.set_kl_shard()
+    assert abs(sum(parts) - whole) <= 1e-6 * abs(whole)
