@@ -158,3 +158,40 @@ def cplx_convnd(nd, input, weight, bias=None, stride=1, padding=0, dilation=1, g
     if nd == 1:
         re, im = re.squeeze(2), im.squeeze(2)
     return Cplx(re, im)
+
+
+def real_convnd(nd, input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                log_sigma2=None, eps=None):
+    """Real-valued cross-correlation / its variational forward through the same C-ABI entry
+    (reference: ``F.conv{1,2}d`` as used by ``ConvNdGaussianMixin._forward_impl``,
+    ``nn/relevance/real/base.py:149-163``).  Zero padding only, like the reference layers."""
+    stride, padding, dilation = _tuple(stride, nd), _tuple(padding, nd), _tuple(dilation, nd)
+    if input.dim() != nd + 2:
+        raise RuntimeError(f"expected a {nd + 2}-d input, got {input.dim()}-d")
+    if nd == 1:
+        lift = lambda t: None if t is None else t.unsqueeze(2)
+        x, w, ls2, e = lift(input), lift(weight), lift(log_sigma2), lift(eps)
+        geom = ((1,) + stride, (0,) + padding, (1,) + dilation)
+    else:
+        x, w, ls2, e = input, weight, log_sigma2, eps
+        geom = (stride, padding, dilation)
+    noise = nv.NOISE_INJECT if e is not None else ops._NOISE[ops.get_noise_mode()]
+
+    def run(x_, w_, b_, l2_, e_):
+        return _ConvFn.apply(x_, None, w_, None, b_, None, l2_, e_, None, noise, geom)[0]
+
+    if groups == 1:
+        out = run(x, w, bias, ls2, e)
+    else:
+        if ls2 is not None and e is None and noise == nv.NOISE_PHILOX_TORCH:
+            raise NotImplementedError(
+                "grouped variational conv with the torch-exact noise stream is not supported; "
+                "use set_noise_mode('fast') or pass eps")
+        cin, cout = x.shape[1] // groups, w.shape[0] // groups
+        outs = []
+        for gi in range(groups):
+            ci, co = slice(gi * cin, (gi + 1) * cin), slice(gi * cout, (gi + 1) * cout)
+            outs.append(run(x[:, ci], w[co], None if bias is None else bias[co],
+                            None if ls2 is None else ls2[co], None if e is None else e[:, co]))
+        out = torch.cat(outs, dim=1)
+    return out.squeeze(2) if nd == 1 else out

@@ -1,7 +1,8 @@
-"""Real-valued variational dropout / ARD linear layers.
+"""Real-valued variational dropout / ARD linear and convolutional layers.
 
 Reference: ``cplxmodule/nn/relevance/real/{base,vd,ard}.py``.  Parameters and
-state-dict keys are those of ``torch.nn.Linear`` plus ``log_sigma2`` (init -10).
+state-dict keys are those of ``torch.nn.Linear`` / ``torch.nn.Conv{1,2}d`` plus
+``log_sigma2`` (init -10).
 """
 import torch
 
@@ -70,3 +71,73 @@ class LinearVD(_RealGaussianLinear, BaseARD):
 class LinearARD(_RealGaussianLinear, BaseARD):
     """Automatic relevance determination: ``0.5 * softplus(-log_alpha)``."""
     _kl_kind = nv.KL_REAL_ARD
+
+
+class _RealGaussianConvNd:
+    """``ConvNdGaussianMixin`` (nn/relevance/real/base.py:83-163) on the CUDA conv kernels: the mean
+    conv, the variance conv ``x^2 * exp(log_sigma2)``, the noise and ``mu + eps sqrt(max(s2, 1e-8))``
+    are one C-ABI call.  Zero padding only, as in the reference (:109-112)."""
+
+    _kl_kind = None
+    _nd = None
+    __sparsity_ignore__ = ("log_sigma2",)
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                 groups=1, bias=True, padding_mode="zeros"):
+        super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=padding,
+                         dilation=dilation, groups=groups, bias=bias, padding_mode=padding_mode)
+        if self.padding_mode != "zeros":
+            raise ValueError(f"Only `zeros` padding mode is supported. Got `{self.padding_mode}`.")
+        self.log_sigma2 = torch.nn.Parameter(torch.empty(*self.weight.shape))
+        self.reset_variational_parameters()
+
+    def reset_variational_parameters(self):
+        self.log_sigma2.data.fill_(-10.0)
+
+    def forward(self, input, eps=None):
+        from ... import conv_ops
+        if isinstance(self.padding, str):
+            raise ValueError("string padding modes are not supported by the CUDA conv path")
+        ls2 = self.log_sigma2 if self.training else None
+        return conv_ops.real_convnd(self._nd, input, self.weight, self.bias, self.stride,
+                                    self.padding, self.dilation, self.groups, log_sigma2=ls2,
+                                    eps=eps if self.training else None)
+
+    @property
+    def log_alpha(self):
+        return ops.log_alpha(self.weight, None, self.log_sigma2)
+
+    @property
+    def penalty(self):
+        return ops.kl(self._kl_kind, self.weight, None, self.log_sigma2, None)
+
+    def _penalty_reduced(self, reduction):
+        return ops.kl(self._kl_kind, self.weight, None, self.log_sigma2, reduction)
+
+    def relevance(self, *, threshold, **kwargs):
+        with torch.no_grad():
+            return ops.log_alpha(self.weight, None, self.log_sigma2, threshold=threshold)
+
+    def sparsity(self, *, threshold, **kwargs):
+        n_relevant = float(self.relevance(threshold=threshold).sum().item())
+        return [(id(self.weight), self.weight.numel() - n_relevant)]
+
+
+class Conv1dVD(_RealGaussianConvNd, torch.nn.Conv1d, BaseARD):
+    """1D convolution with variational dropout (nn/relevance/real/vd.py:103-113)."""
+    _kl_kind, _nd = nv.KL_REAL_VD, 1
+
+
+class Conv2dVD(_RealGaussianConvNd, torch.nn.Conv2d, BaseARD):
+    """2D convolution with variational dropout (nn/relevance/real/vd.py:115-125)."""
+    _kl_kind, _nd = nv.KL_REAL_VD, 2
+
+
+class Conv1dARD(_RealGaussianConvNd, torch.nn.Conv1d, BaseARD):
+    """1D convolution with automatic relevance determination (nn/relevance/real/ard.py:48-51)."""
+    _kl_kind, _nd = nv.KL_REAL_ARD, 1
+
+
+class Conv2dARD(_RealGaussianConvNd, torch.nn.Conv2d, BaseARD):
+    """2D convolution with automatic relevance determination (nn/relevance/real/ard.py:54-57)."""
+    _kl_kind, _nd = nv.KL_REAL_ARD, 2

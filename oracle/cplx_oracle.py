@@ -80,6 +80,26 @@ def cplx_conv2d_vd(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_i
     return mu_re + eps_re * sd, mu_im + eps_im * sd
 
 
+def real_conv2d_vd(x, w, b, log_sigma2, eps, stride=1, padding=0, dilation=1, groups=1):
+    """ConvNdGaussianMixin._forward_impl with F.conv2d, nn/relevance/real/base.py:149-163
+    (training mode; ``eps`` is the ``torch.randn_like(s2)`` draw).  ``eps=None``: the mean only,
+    i.e. the eval-mode forward (:150-152)."""
+    mu = F.conv2d(x, w, b, stride, padding, dilation, groups)
+    if eps is None:
+        return mu
+    s2 = F.conv2d(x * x, torch.exp(log_sigma2), None, stride, padding, dilation, groups)
+    return mu + eps * torch.sqrt(torch.clamp(s2, 1e-8))
+
+
+def real_conv1d_vd(x, w, b, log_sigma2, eps, stride=1, padding=0, dilation=1, groups=1):
+    """Same with F.conv1d (Conv1dGaussian.forward, nn/relevance/real/base.py:166-177)."""
+    mu = F.conv1d(x, w, b, stride, padding, dilation, groups)
+    if eps is None:
+        return mu
+    s2 = F.conv1d(x * x, torch.exp(log_sigma2), None, stride, padding, dilation, groups)
+    return mu + eps * torch.sqrt(torch.clamp(s2, 1e-8))
+
+
 # -------------------------------------------------------------------------------- KL
 def log_alpha_real(w, log_sigma2):
     """GaussianMixin.log_alpha, nn/relevance/real/base.py:23-26."""

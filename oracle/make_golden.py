@@ -147,8 +147,49 @@ def main():
         b_re=cvd.bias.real, b_im=cvd.bias.imag, log_sigma2=cvd.log_sigma2, eps_re=eps.real,
         eps_im=eps.imag, y_re=out.real, y_im=out.imag,
         penalty_sum=sum(penalties(cvd, reduction="sum")))))
+    real_conv_fixtures()
     print("golden fixtures written to", os.path.normpath(OUT))
 
 
+def real_conv_fixtures():
+    """Real-valued Conv2dVD / Conv1dARD training forwards with captured noise
+    (nn/relevance/real/base.py:83-177, real/vd.py:103-125, real/ard.py:48-57)."""
+    import_reference()
+    from cplxmodule.nn.relevance import Conv1dARD, Conv2dVD, penalties
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(808)
+    m = Conv2dVD(6, 8, (3, 2), stride=(1, 2), padding=(1, 0), dilation=(2, 1), groups=2).train()
+    with torch.no_grad():
+        m.log_sigma2.uniform_(-12, 2)
+    x = torch.randn(3, 6, 10, 9)
+    state = torch.get_rng_state()
+    out = m(x)
+    torch.set_rng_state(state)
+    eps = torch.randn_like(out)
+    m.eval()
+    mu = m(x)
+    np.savez(os.path.join(OUT, "conv2d_vd.npz"), **npy(dict(
+        x=x, w=m.weight, b=m.bias, log_sigma2=m.log_sigma2, eps=eps, y=out, mu=mu,
+        log_alpha=m.log_alpha, penalty=m.penalty,
+        penalty_sum=sum(penalties(m, reduction="sum")))))
+    torch.manual_seed(909)
+    m = Conv1dARD(5, 7, 4, stride=2, padding=3).train()
+    with torch.no_grad():
+        m.log_sigma2.uniform_(-12, 2)
+    x = torch.randn(4, 5, 23)
+    state = torch.get_rng_state()
+    out = m(x)
+    torch.set_rng_state(state)
+    eps = torch.randn_like(out)
+    np.savez(os.path.join(OUT, "conv1d_ard.npz"), **npy(dict(
+        x=x, w=m.weight, b=m.bias, log_sigma2=m.log_sigma2, eps=eps, y=out,
+        log_alpha=m.log_alpha, penalty=m.penalty,
+        penalty_sum=sum(penalties(m, reduction="sum")),
+        relevance=m.relevance(threshold=3.0))))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "real_conv":
+        real_conv_fixtures()
+    else:
+        main()

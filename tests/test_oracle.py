@@ -57,6 +57,22 @@ def test_golden_real(name, kind):
                        g["penalty_sum"])
 
 
+def test_golden_real_conv_vd():
+    """real-valued Conv2dVD (grouped, strided, dilated) and Conv1dARD fixtures of the live reference"""
+    g = load_golden("conv2d_vd")
+    geom = ((1, 2), (1, 0), (2, 1), 2)
+    assert torch.equal(orc.real_conv2d_vd(g["x"], g["w"], g["b"], g["log_sigma2"], g["eps"], *geom), g["y"])
+    assert torch.equal(orc.real_conv2d_vd(g["x"], g["w"], g["b"], g["log_sigma2"], None, *geom), g["mu"])
+    la = orc.log_alpha_real(g["w"], g["log_sigma2"])
+    assert torch.equal(la, g["log_alpha"]) and torch.equal(orc.penalty_real_vd(la), g["penalty"])
+    assert torch.equal(orc.layer_penalty("real_vd", g["w"], None, g["log_sigma2"], "sum"), g["penalty_sum"])
+    g = load_golden("conv1d_ard")
+    assert torch.equal(orc.real_conv1d_vd(g["x"], g["w"], g["b"], g["log_sigma2"], g["eps"], 2, 3, 1, 1), g["y"])
+    la = orc.log_alpha_real(g["w"], g["log_sigma2"])
+    assert torch.equal(orc.penalty_real_ard(la), g["penalty"])
+    assert torch.equal((la <= 3.0).to(la), g["relevance"])
+
+
 def test_golden_penalty_sweep():
     g = load_golden("penalty_sweep")
     la = g["log_sigma2"]
