@@ -21,6 +21,7 @@ KL_REAL_VD, KL_REAL_ARD, KL_CPLX_VD, KL_CPLX_ARD = 0, 1, 2, 3
 
 EXPORTS = (
     "cplxk_abi_version", "cplxk_strerror", "cplxk_device_info", "cplxk_linear_fwd",
+    "cplxk_linear_fwd_ws", "cplxk_linear_workspace_bytes",
     "cplxk_linear_vd_fwd", "cplxk_linear_vd_fwd_kl", "cplxk_linear_vd_workspace_bytes", "cplxk_kl_workspace_bytes", "cplxk_kl", "cplxk_log_alpha",
     "cplxk_conv2d_fwd", "cplxk_conv2d_workspace_bytes", "cplxk_randn_philox_torch",
     "cplxk_transpose2d", "cplxk_colsum", "cplxk_vd_grad_s2", "cplxk_vd_grad_input",
@@ -40,6 +41,9 @@ def _declare(lib):
     lib.cplxk_strerror.argtypes = [_int]
     lib.cplxk_device_info.argtypes = [ctypes.POINTER(_int)] * 3
     lib.cplxk_linear_fwd.argtypes = [_vp] * 8 + [_i64] * 3 + [_int, _int, _vp]
+    lib.cplxk_linear_fwd_ws.argtypes = [_vp] * 8 + [_i64] * 3 + [_int, _int, _vp, ctypes.c_size_t, _vp]
+    lib.cplxk_linear_workspace_bytes.restype = ctypes.c_size_t
+    lib.cplxk_linear_workspace_bytes.argtypes = [_i64, _i64, _i64, _int]
     lib.cplxk_linear_vd_fwd.argtypes = ([_vp] * 9 + [_int, _u64, _u64, _u32] + [_vp] * 2
                                         + [_i64] * 3 + [_int, _int, _vp, _vp, ctypes.c_size_t, _vp])
     lib.cplxk_linear_vd_fwd_kl.argtypes = ([_vp] * 9 + [_int, _u64, _u64, _u32] + [_vp] * 2

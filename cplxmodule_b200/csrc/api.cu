@@ -21,6 +21,13 @@ int fwd_tc_dispatch(int dtype, bool cplx, bool vd, int swz, const void* x_re, co
                     int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st,
                     const KlFuse& kl);
 bool fwd_tc_fuses_kl(int dtype, int64_t M, int64_t N, int64_t K);
+// persistent double-buffered affine map on 16-bit operands (fwd_lin3.cu)
+size_t fwd_lin3_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K);
+bool fwd_lin3_supported(int64_t M, int64_t N, int64_t K);
+int fwd_lin3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
+                 void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st);
+int fwd_lin3_bf16(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
+                  int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st);
 size_t fwd_tc_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K);
 
 static int check_arch() {
@@ -93,7 +100,18 @@ static int forward_common(bool vd, const void* x_re, const void* x_im, const voi
     if (!swz) swz = (cplx && vd) ? 64 : 128;
     if (workspace) {
       if (!aligned16(workspace)) return CPLXK_ERR_ALIGN;
-      if (workspace_bytes < fwd_tc_workspace_bytes(dtype, M, N, K)) return CPLXK_ERR_WORKSPACE;
+      const size_t need = vd ? fwd_tc_workspace_bytes(dtype, M, N, K) : fwd_lin3_workspace_bytes(dtype, M, N, K);
+      if (workspace_bytes < need) return CPLXK_ERR_WORKSPACE;
+    }
+    if (!vd && fwd_lin3_supported(M, N, K)) {
+      // plain affine map: persistent CTA-pair kernel with double-buffered accumulators; fp32 planes
+      // need the workspace for their row-scaled fp16 copies (CPLXK_F16=0 / no workspace: tf32 below)
+      const char* f16e = std::getenv("CPLXK_F16");
+      const char* l3 = std::getenv("CPLXK_LIN3");
+      if (dtype == CPLXK_F32 && workspace && K >= 64 && !(f16e && f16e[0] == '0'))
+        return fwd_lin3_f32(cplx, x_re, x_im, w_re, w_im, workspace, M, N, K, ep, st);
+      if (dtype == CPLXK_BF16 && !(l3 && l3[0] == '0'))   // CPLXK_LIN3=0: one tile per CTA (fwd_tc.cu)
+        return fwd_lin3_bf16(cplx, x_re, x_im, w_re, w_im, M, N, K, ep, st);
     }
     const bool fuse = vd && workspace && kl.kind >= 0 && kl.sum && kl.ws && fwd_tc_fuses_kl(dtype, M, N, K);
     if (!fuse) kl.kind = -1;
@@ -152,6 +170,20 @@ extern "C" int cplxk_linear_fwd(const void* x_re, const void* x_im, const void* 
                                 void* stream) {
   return forward_common(false, x_re, x_im, w_re, w_im, b_re, b_im, nullptr, nullptr, nullptr, 0, 0,
                         0, 0, y_re, y_im, M, N, K, dtype, math, nullptr, nullptr, 0, stream);
+}
+
+extern "C" size_t cplxk_linear_workspace_bytes(int64_t M, int64_t N, int64_t K, int dtype) {
+  if (M < 0 || N < 0 || K < 0) return 0;
+  return fwd_lin3_workspace_bytes(dtype, M, N, K);
+}
+
+extern "C" int cplxk_linear_fwd_ws(const void* x_re, const void* x_im, const void* w_re,
+                                   const void* w_im, const void* b_re, const void* b_im, void* y_re,
+                                   void* y_im, int64_t M, int64_t N, int64_t K, int dtype, int math,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  return forward_common(false, x_re, x_im, w_re, w_im, b_re, b_im, nullptr, nullptr, nullptr, 0, 0,
+                        0, 0, y_re, y_im, M, N, K, dtype, math, nullptr, workspace, workspace_bytes,
+                        stream);
 }
 
 extern "C" int cplxk_linear_vd_fwd(const void* x_re, const void* x_im, const void* w_re,

@@ -28,6 +28,7 @@
 #include "epilogue.cuh"
 #include "kl_math.cuh"
 #include "ptx.cuh"
+#include "tc3_common.cuh"
 
 namespace cplxk {
 
@@ -62,78 +63,6 @@ struct Tc3Params {
   const float* sw;         // [N] inverse row scales of W (nullable)
   EpiParams ep;
 };
-
-namespace ptx {
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int32_t c0,
-                                             int32_t c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() {
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
-                                             uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
-               : "memory");
-}
-// kind::f16 instruction descriptor with explicit operand format (0 = fp16, 1 = bf16)
-__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t fmt, int M, int N, bool neg_a) {
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | (neg_a ? (1u << 13) : 0u) |
-         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
-}
-}  // namespace ptx
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// 64 consecutive outputs of one row, 16-byte vector stores when the row segment allows
-template <typename T>
-__device__ __forceinline__ void store_run64(T* dst, const float (&v)[64], int nvalid) {
-  constexpr int V = Elem<T>::kVec;
-  if (nvalid == 64 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-#pragma unroll
-    for (int c = 0; c < 64 / V; ++c) {
-      Vec16<T> o;
-#pragma unroll
-      for (int j = 0; j < V; ++j) o.v[j] = v[c * V + j];
-      o.store(dst + c * V);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 64; ++j)
-      if (j < nvalid) dst[j] = Elem<T>::from_f(v[j]);
-  }
-}
 
 template <typename OutT, bool kCplx>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
@@ -400,8 +329,9 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
     const float* pi = kCplx ? (is_x ? x_im : w_im) + r * K : nullptr;
     __half* hr = (is_x ? xh_re : wh_re) + r * K;
     __half* hi = kCplx ? (is_x ? xh_im : wh_im) + r * K : nullptr;
-    __nv_bfloat16* dv = (is_x ? q : e) + r * K;
-    const float* pl = is_x ? nullptr : ls2 + r * K;
+    const bool has_var = q != nullptr;        // plain affine map: no variance operands (fwd_lin3.cu)
+    __nv_bfloat16* dv = has_var ? (is_x ? q : e) + r * K : nullptr;
+    const float* pl = (is_x || !has_var) ? nullptr : ls2 + r * K;
 
     float cr[kCache][8], ci[kCache][8];
     float amax = 0.f;
@@ -464,6 +394,7 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
         for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(vi[2 * j] * scale, vi[2 * j + 1] * scale);
         *reinterpret_cast<uint4*>(hi + k) = o;
       }
+      if (!has_var) return;
       __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&o);
       if (is_x) {
 #pragma unroll
@@ -513,43 +444,6 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------ host side
-typedef CUresult (*PFN_encodeTiled3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled3 encode_fn3() {
-  static PFN_encodeTiled3 fn = nullptr;
-  if (!fn) {
-    void* q = nullptr;
-    cudaDriverEntryPointQueryResult r;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) != cudaSuccess ||
-        r != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<PFN_encodeTiled3>(q);
-  }
-  return fn;
-}
-
-// plane [rows, cols] row-major, element size es -> box {box_c, box_r}; swizzle = box_c * es bytes
-static int map2d(CUtensorMap* out, CUtensorMapDataType dt, size_t es, const void* ptr, int64_t rows,
-                 int64_t cols, int box_c, int box_r) {
-  auto enc = encode_fn3();
-  if (!enc) return CPLXK_ERR_CUDA;
-  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(cols) * es};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_r)};
-  cuuint32_t estr[2] = {1u, 1u};
-  const size_t inner = box_c * es;
-  const CUtensorMapSwizzle sw = inner == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                : inner == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                              : CU_TENSOR_MAP_SWIZZLE_32B;
-  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? CPLXK_OK : CPLXK_ERR_CUDA;
-}
-
 struct Tc3Operands {
   const void *a_re, *a_im, *q, *b_re, *b_im, *e;   // 16-bit planes [M,K] / [N,K]
   const float *sx, *sw;
@@ -604,7 +498,6 @@ static int launch_tc3(const Tc3Operands& o, int64_t M, int64_t N, int64_t K, con
   return CPLXK_OK;
 }
 
-static size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
 // workspace of the fp32-plane path: xh_re, xh_im, q [M,K]; wh_re, wh_im, E [N,K] (2 bytes each),
 // isx [M], isw [N] floats
@@ -625,6 +518,30 @@ int fwd_tc2_half_dispatch(bool cplx, const void* xh_re, const void* xh_im, const
                           const float* sw, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
                           cudaStream_t st);
 
+int vd_prepare_f16_launch(bool cplx, const void* x_re, const void* x_im, int64_t M, const void* w_re,
+                          const void* w_im, const void* ls2, int64_t N, int64_t K, void* xh_re,
+                          void* xh_im, void* q, void* wh_re, void* wh_im, void* e, float* isx,
+                          float* isw, const KlFuse& kl, cudaStream_t st) {
+  const int64_t rows = M + N;
+  const int grid = static_cast<int>(rows > 148 * 8 ? 148 * 8 : rows);   // <= kKlMaxBlocks partials
+  const int kl_kind = (kl.sum && kl.ws && q) ? kl.kind : -1;
+  auto kws = static_cast<KlWorkspace*>(kl.ws);
+  const int64_t kl_row0 = kl.row_begin, kl_row1 = kl.row_end < 0 ? N : kl.row_end;
+  auto f = [](const void* p) { return static_cast<const float*>(p); };
+  auto h = [](void* p) { return static_cast<__half*>(p); };
+  auto b = [](void* p) { return static_cast<__nv_bfloat16*>(p); };
+  if (cplx)
+    vd_prepare_f16_kernel<true><<<grid, 256, 0, st>>>(f(x_re), f(x_im), M, f(w_re), f(w_im), f(ls2), N, K,
+                                                      h(xh_re), h(xh_im), b(q), h(wh_re), h(wh_im), b(e),
+                                                      isx, isw, kl_kind, kl.sum, kws, kl_row0, kl_row1);
+  else
+    vd_prepare_f16_kernel<false><<<grid, 256, 0, st>>>(f(x_re), nullptr, M, f(w_re), nullptr, f(ls2), N, K,
+                                                       h(xh_re), nullptr, b(q), h(wh_re), nullptr, b(e),
+                                                       isx, isw, kl_kind, kl.sum, kws, kl_row0, kl_row1);
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
+}
+
 // fp32 planes: pre-pass to scaled fp16, then the CTA-pair kernel of fwd_tc2.cu on kind::f16
 // (CPLXK_PERSIST=0) or, by default, the persistent kernel above.
 int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
@@ -640,24 +557,9 @@ int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re,
   __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(ws + 3 * xb + 2 * wb);
   float* isx = reinterpret_cast<float*>(ws + 3 * xb + 3 * wb);
   float* isw = reinterpret_cast<float*>(ws + 3 * xb + 3 * wb + align256(static_cast<size_t>(M) * 4));
-  const int64_t rows = M + N;
-  const int grid = static_cast<int>(rows > 148 * 8 ? 148 * 8 : rows);   // <= kKlMaxBlocks partials
-  const int kl_kind = (kl.sum && kl.ws) ? kl.kind : -1;
-  float* kl_sum = kl.sum;
-  auto kws = static_cast<KlWorkspace*>(kl.ws);
-  const int64_t kl_row0 = kl.row_begin, kl_row1 = kl.row_end < 0 ? N : kl.row_end;
-  if (cplx)
-    vd_prepare_f16_kernel<true><<<grid, 256, 0, st>>>(
-        static_cast<const float*>(x_re), static_cast<const float*>(x_im), M,
-        static_cast<const float*>(w_re), static_cast<const float*>(w_im),
-        static_cast<const float*>(ls2), N, K, xh_re, xh_im, q, wh_re, wh_im, e, isx, isw, kl_kind,
-        kl_sum, kws, kl_row0, kl_row1);
-  else
-    vd_prepare_f16_kernel<false><<<grid, 256, 0, st>>>(
-        static_cast<const float*>(x_re), nullptr, M, static_cast<const float*>(w_re), nullptr,
-        static_cast<const float*>(ls2), N, K, xh_re, nullptr, q, wh_re, nullptr, e, isx, isw, kl_kind,
-        kl_sum, kws, kl_row0, kl_row1);
-  CPLXK_CUDA_TRY(cudaGetLastError());
+  int rc = vd_prepare_f16_launch(cplx, x_re, x_im, M, w_re, w_im, ls2, N, K, xh_re, xh_im, q, wh_re,
+                                 wh_im, e, isx, isw, kl, st);
+  if (rc) return rc;
   // the KL (partial) sum is final here: let a collective on another stream start under the GEMM
   if (kl.event) CPLXK_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(kl.event), st));
   const char* dbg_env = std::getenv("CPLXK_DBG");

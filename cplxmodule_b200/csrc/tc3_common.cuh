@@ -1,0 +1,123 @@
+// Pieces shared by the persistent CTA-pair kernels (fwd_tc3.cu: variational forward,
+// fwd_lin3.cu: plain affine map): cluster-scope mbarrier / TMA-store wrappers, the kind::f16
+// instruction descriptor with an explicit operand format, row stores, tensor-map encoding.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace cplxk {
+
+namespace ptx {
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int32_t c0,
+                                             int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+// kind::f16 instruction descriptor with explicit operand format (0 = fp16, 1 = bf16)
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t fmt, int M, int N, bool neg_a) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (neg_a ? (1u << 13) : 0u) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+}  // namespace ptx
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 64 consecutive outputs of one row, 16-byte vector stores when the row segment allows
+template <typename T>
+__device__ __forceinline__ void store_run64(T* dst, const float (&v)[64], int nvalid) {
+  constexpr int V = Elem<T>::kVec;
+  if (nvalid == 64 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+#pragma unroll
+    for (int c = 0; c < 64 / V; ++c) {
+      Vec16<T> o;
+#pragma unroll
+      for (int j = 0; j < V; ++j) o.v[j] = v[c * V + j];
+      o.store(dst + c * V);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 64; ++j)
+      if (j < nvalid) dst[j] = Elem<T>::from_f(v[j]);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline PFN_encodeTiled3 encode_fn3() {
+  static PFN_encodeTiled3 fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult r;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) != cudaSuccess ||
+        r != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled3>(q);
+  }
+  return fn;
+}
+
+// plane [rows, cols] row-major, element size es -> box {box_c, box_r}; swizzle = box_c * es bytes
+static inline int map2d(CUtensorMap* out, CUtensorMapDataType dt, size_t es, const void* ptr, int64_t rows,
+                 int64_t cols, int box_c, int box_r) {
+  auto enc = encode_fn3();
+  if (!enc) return CPLXK_ERR_CUDA;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(cols) * es};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_r)};
+  cuuint32_t estr[2] = {1u, 1u};
+  const size_t inner = box_c * es;
+  const CUtensorMapSwizzle sw = inner == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : inner == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                              : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CPLXK_OK : CPLXK_ERR_CUDA;
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+}  // namespace cplxk

@@ -121,9 +121,18 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
     with torch.cuda.device(dev):
         st = nv.stream_ptr(dev)
         if log_sigma2 is None:
-            nv.check(lib.cplxk_linear_fwd(nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi),
-                                          nv.ptr(br), nv.ptr(bi), nv.ptr(y_re), nv.ptr(y_im),
-                                          M, N, K, code, math, st))
+            ws_bytes = 0
+            if _state["prepare"] and math != nv.MATH_SIMT:
+                ws_bytes = lib.cplxk_linear_workspace_bytes(M, N, K, code)
+            if ws_bytes:
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                nv.check(lib.cplxk_linear_fwd_ws(nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi),
+                                                 nv.ptr(br), nv.ptr(bi), nv.ptr(y_re), nv.ptr(y_im),
+                                                 M, N, K, code, math, nv.ptr(ws), ws_bytes, st))
+            else:
+                nv.check(lib.cplxk_linear_fwd(nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi),
+                                              nv.ptr(br), nv.ptr(bi), nv.ptr(y_re), nv.ptr(y_im),
+                                              M, N, K, code, math, st))
         else:
             ls2 = nv.plane(log_sigma2, dt)
             if noise == nv.NOISE_INJECT:

@@ -99,6 +99,22 @@ int cplxk_linear_fwd(const void* x_re, const void* x_im,
                      int dtype, int math, void* stream);
 
 /*
+ * Same map with a caller-provided scratch buffer (nullable; cplxk_linear_workspace_bytes()
+ * bytes, 16-byte aligned, uninitialised).  With it, F32 planes (M > 128, K >= 64, K % 8 == 0)
+ * are first rewritten as per-row power-of-two scaled fp16 copies (one pre-pass launch) and the
+ * GEMM runs on kind::f16 -- tf32's 11-bit significand at twice the MMA rate -- in a persistent
+ * CTA-pair kernel whose TMEM accumulators are double buffered.  Without it: cplxk_linear_fwd.
+ */
+size_t cplxk_linear_workspace_bytes(int64_t M, int64_t N, int64_t K, int dtype);
+int cplxk_linear_fwd_ws(const void* x_re, const void* x_im,
+                        const void* w_re, const void* w_im,
+                        const void* b_re, const void* b_im,
+                        void* y_re, void* y_im,
+                        int64_t M, int64_t N, int64_t K,
+                        int dtype, int math,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Local-reparameterisation forward of a Gaussian (variational dropout) linear
  * layer, fused: mean GEMM(s), variance GEMM |x|^2 . exp(log_sigma2)^T, noise,
  * and  y = mu + eps * sqrt(max(s2, 1e-8)).
