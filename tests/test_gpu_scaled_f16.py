@@ -227,3 +227,44 @@ def test_row_sharded_fused_kl_partials_add_up():
             finally:
                 cb.set_kl_shard()
     assert abs(sum(parts) - whole) <= 1e-6 * abs(whole)
+
+
+def test_full_size_exact_properties():
+    """BASELINE headline size (B = d = 4096), properties that hold BIT FOR BIT on the scaled-fp16
+    path because every row carries a power-of-two scale of its own:
+      * rescaling input rows / weight rows by powers of two rescales the mean exactly;
+      * permuting the input rows permutes the output rows;
+    and the KL by-product of the forward equals the stand-alone KL pass."""
+    B = D = 4096
+    torch.manual_seed(9)
+    layer = CplxLinearVD(D, D).to(DEV).train()
+    with torch.no_grad():
+        layer.log_sigma2.uniform_(-12, 0)
+    w = layer.weight
+    x = cplx.randn(B, D, device=DEV)
+    zero = torch.zeros(B, D, device=DEV)
+    run = lambda xr, xi, wr, wi: ops.cplx_linear_vd(xr, xi, wr, wi, None, None, layer.log_sigma2,
+                                                     eps=(zero, zero))
+    with torch.no_grad():
+        y0 = run(x.real, x.imag, w.real, w.imag)
+        # per-row powers of two on x (2^-20 .. 2^20) and on W (2^-8 .. 2^8)
+        ex = torch.randint(-20, 21, (B, 1), device=DEV).float()
+        ew = torch.randint(-8, 9, (D, 1), device=DEV).float()
+        sx, sw = torch.exp2(ex), torch.exp2(ew)
+        y1 = run(x.real * sx, x.imag * sx, w.real * sw, w.imag * sw)
+        for a, b in zip(y0, y1):
+            assert torch.equal(a * sx * sw.t(), b)
+        perm = torch.randperm(B, device=DEV)
+        y2 = run(x.real[perm], x.imag[perm], w.real, w.imag)
+        for a, b in zip(y0, y2):
+            assert torch.equal(a[perm], b)
+        # sampled rows against the float64 oracle
+        rows = torch.arange(0, B, 97, device=DEV)
+        c = lambda t: t.detach().double().cpu()
+        want = orc.cplx_linear(c(x.real[rows]), c(x.imag[rows]), c(w.real), c(w.imag))
+        assert rel_err(y0[0][rows], want[0]) < TOL and rel_err(y0[1][rows], want[1]) < TOL
+        # fused KL == stand-alone KL at full size
+        layer(x)
+        fused = float(sum(penalties(layer)))
+        alone = float(sum(penalties(layer)))
+        assert abs(fused - alone) <= 1e-6 * abs(alone)
