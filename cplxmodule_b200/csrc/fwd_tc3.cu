@@ -322,9 +322,20 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
   __shared__ bool kl_last;
   float kl_acc = 0.f;                        // KL penalty of the weight rows this thread converts
   const int tid = threadIdx.x;
-  for (int64_t row = blockIdx.x; row < M + N; row += gridDim.x) {
-    const bool is_x = row < M;
-    const int64_t r = is_x ? row : row - M;
+  // x rows (pure streaming) and W rows (streaming + ~50 instructions of KL math per element)
+  // alternate in the global row order and the grid size is odd, so every block -- and every SM
+  // at any time -- works on a mix of the two instead of all x rows first and all W rows last
+  const int64_t mn = M < N ? M : N;
+  for (int64_t g = blockIdx.x; g < M + N; g += gridDim.x) {
+    bool is_x;
+    int64_t r;
+    if (g < 2 * mn) {
+      is_x = (g & 1) == 0;
+      r = g >> 1;
+    } else {
+      is_x = M > N;
+      r = mn + (g - 2 * mn);
+    }
     const float* pr = (is_x ? x_re : w_re) + r * K;
     const float* pi = kCplx ? (is_x ? x_im : w_im) + r * K : nullptr;
     __half* hr = (is_x ? xh_re : wh_re) + r * K;
@@ -333,6 +344,10 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
     __nv_bfloat16* dv = has_var ? (is_x ? q : e) + r * K : nullptr;
     const float* pl = (is_x || !has_var) ? nullptr : ls2 + r * K;
 
+    if (pl != nullptr) {   // log_sigma2 is needed after the block-wide max: pull it towards L2 now
+      for (int64_t k = static_cast<int64_t>(tid) * 32; k < K; k += 256 * 32)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl + k));
+    }
     float cr[kCache][8], ci[kCache][8];
     float amax = 0.f;
 #pragma unroll
@@ -523,7 +538,7 @@ int vd_prepare_f16_launch(bool cplx, const void* x_re, const void* x_im, int64_t
                           void* xh_im, void* q, void* wh_re, void* wh_im, void* e, float* isx,
                           float* isw, const KlFuse& kl, cudaStream_t st) {
   const int64_t rows = M + N;
-  const int grid = static_cast<int>(rows > 148 * 8 ? 148 * 8 : rows);   // <= kKlMaxBlocks partials
+  const int grid = static_cast<int>(rows > 148 * 8 - 1 ? 148 * 8 - 1 : rows);   // odd; <= kKlMaxBlocks partials
   const int kl_kind = (kl.sum && kl.ws && q) ? kl.kind : -1;
   auto kws = static_cast<KlWorkspace*>(kl.ws);
   const int64_t kl_row0 = kl.row_begin, kl_row1 = kl.row_end < 0 ? N : kl.row_end;

@@ -56,11 +56,12 @@ def main():
         for noise in os.environ.get("DBG_NOISE", "inject,torch,fast").split(","):
             for dbg in dbgs:
                 os.environ["CPLXK_DBG"] = dbg
+                klr = (lambda: {"kind": 2}) if os.environ.get("DBG_KL") else (lambda: None)
                 if noise == "inject":
-                    fn = lambda: ops.cplx_linear_vd(xr, xi, w_re, w_im, b_re, b_im, ls2, eps=eps)
+                    fn = lambda: ops.cplx_linear_vd(xr, xi, w_re, w_im, b_re, b_im, ls2, eps=eps, kl_req=klr())
                 else:
                     cb.set_noise_mode(noise)
-                    fn = lambda: ops.cplx_linear_vd(xr, xi, w_re, w_im, b_re, b_im, ls2)
+                    fn = lambda: ops.cplx_linear_vd(xr, xi, w_re, w_im, b_re, b_im, ls2, kl_req=klr())
                 res = {v: [] for v in variants if not (v == "tf32" and dt_name != "f32")}
                 for _ in range(rounds):          # interleave the variants: clocks drift under the power cap
                     for v in res:
