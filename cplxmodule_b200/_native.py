@@ -18,6 +18,7 @@ MATH_AUTO, MATH_TENSOR, MATH_SIMT = 0, 1, 2
 NOISE_INJECT, NOISE_PHILOX_TORCH, NOISE_PHILOX_FAST = 0, 1, 2
 ERR_UNSUPPORTED = -5
 KL_REAL_VD, KL_REAL_ARD, KL_CPLX_VD, KL_CPLX_ARD = 0, 1, 2, 3
+KL_CPLX_VD_APPROX, KL_CPLX_VD_SCALEFREE = 4, 5        # nn/relevance/extensions/complex.py
 
 EXPORTS = (
     "cplxk_abi_version", "cplxk_strerror", "cplxk_device_info", "cplxk_linear_fwd",

@@ -211,8 +211,8 @@ extern "C" int cplxk_linear_vd_fwd_kl(const void* x_re, const void* x_im, const 
   if (kl_done) *kl_done = 0;
   KlFuse kl{-1, nullptr, nullptr, 0, -1, nullptr};
   if (kl_kind >= 0) {
-    const bool cplx_kind = kl_kind == CPLXK_KL_CPLX_VD || kl_kind == CPLXK_KL_CPLX_ARD;
-    if (kl_kind > CPLXK_KL_CPLX_ARD || cplx_kind != (w_im != nullptr) || !kl_sum || !kl_done)
+    const bool cplx_kind = kl_kind >= CPLXK_KL_CPLX_VD;
+    if (kl_kind > CPLXK_KL_CPLX_VD_SCALEFREE || cplx_kind != (w_im != nullptr) || !kl_sum || !kl_done)
       return CPLXK_ERR_BADARG;
     if (!kl_workspace || kl_workspace_bytes < cplxk_kl_workspace_bytes()) return CPLXK_ERR_WORKSPACE;
     if (!aligned16(kl_workspace)) return CPLXK_ERR_ALIGN;

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256)
 kl_bwd_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T* __restrict__ ls2,
               int64_t n, const void* __restrict__ grad, int grad_is_tensor, int grad_is_f32,
               float scale, T* __restrict__ d_w_re, T* __restrict__ d_w_im, T* __restrict__ d_ls2) {
-  constexpr bool kCplx = (kKind == CPLXK_KL_CPLX_VD || kKind == CPLXK_KL_CPLX_ARD);
+  constexpr bool kCplx = kKind >= CPLXK_KL_CPLX_VD;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float wr = Elem<T>::to_f(w_re[i]);
@@ -168,6 +168,11 @@ kl_bwd_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T* _
       dn = 0.5f * __fdividef(1.f, 1.f + __expf(-nla));
     } else if constexpr (kKind == CPLXK_KL_CPLX_VD) {
       dn = -expm1f(-__expf(nla));                          // 1 - exp(-1/alpha)
+    } else if constexpr (kKind == CPLXK_KL_CPLX_VD_APPROX) {
+      const float s = __fdividef(1.f, 1.f + __expf(-fmaf(1.36526f, nla, -1.45926f)));
+      dn = __fdividef(1.f, 1.f + __expf(-nla)) + 0.57810f * 1.36526f * s * (1.f - s);
+    } else if constexpr (kKind == CPLXK_KL_CPLX_VD_SCALEFREE) {
+      dn = -0.5f * expm1f(-__expf(nla));                   // (Ein(t) - gamma - ls2) / 2 through t
     } else {
       dn = __fdividef(1.f, 1.f + __expf(-nla));
     }
@@ -176,12 +181,15 @@ kl_bwd_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T* _
       g = grad_is_f32 ? static_cast<const float*>(grad)[i] : Elem<T>::to_f(static_cast<const T*>(grad)[i]);
     else
       g = grad_is_f32 ? static_cast<const float*>(grad)[0] : Elem<T>::to_f(static_cast<const T*>(grad)[0]);
-    g *= scale * dn;
+    const float g0 = g * scale;
+    g = g0 * dn;
     // -log_alpha = log(r2) - ls2  =>  d/dw = 2 w / r2 ,  d/dls2 = -1
     const float k = 2.f * __fdividef(g, r2);
     d_w_re[i] = Elem<T>::from_f(k * wr);
     if constexpr (kCplx) d_w_im[i] = Elem<T>::from_f(k * wi);
-    d_ls2[i] = Elem<T>::from_f(-g);
+    // the scale-free penalty also depends on log_sigma2 directly (-ls2 / 2)
+    const float direct = kKind == CPLXK_KL_CPLX_VD_SCALEFREE ? -0.5f * g0 : 0.f;
+    d_ls2[i] = Elem<T>::from_f(direct - g);
   }
 }
 
@@ -299,9 +307,9 @@ extern "C" int cplxk_kl_bwd(int kind, const void* w_re, const void* w_im, const 
                             int64_t n, int dtype, const void* grad, int grad_is_tensor,
                             int grad_is_f32, double scale, void* d_w_re, void* d_w_im,
                             void* d_log_sigma2, void* stream) {
-  if (kind < 0 || kind > 3 || n < 0) return CPLXK_ERR_BADARG;
+  if (kind < 0 || kind > CPLXK_KL_CPLX_VD_SCALEFREE || n < 0) return CPLXK_ERR_BADARG;
   if (n == 0) return CPLXK_OK;
-  const bool cplx = (kind == CPLXK_KL_CPLX_VD || kind == CPLXK_KL_CPLX_ARD);
+  const bool cplx = kind >= CPLXK_KL_CPLX_VD;
   if (!w_re || !log_sigma2 || !grad || !d_w_re || !d_log_sigma2) return CPLXK_ERR_BADARG;
   if (cplx != (w_im != nullptr) || cplx != (d_w_im != nullptr)) return CPLXK_ERR_BADARG;
   auto st = static_cast<cudaStream_t>(stream);
@@ -316,6 +324,8 @@ extern "C" int cplxk_kl_bwd(int kind, const void* w_re, const void* w_im, const 
       case CPLXK_KL_REAL_VD: CPLXK_KLB(CPLXK_KL_REAL_VD); break;
       case CPLXK_KL_REAL_ARD: CPLXK_KLB(CPLXK_KL_REAL_ARD); break;
       case CPLXK_KL_CPLX_VD: CPLXK_KLB(CPLXK_KL_CPLX_VD); break;
+      case CPLXK_KL_CPLX_VD_APPROX: CPLXK_KLB(CPLXK_KL_CPLX_VD_APPROX); break;
+      case CPLXK_KL_CPLX_VD_SCALEFREE: CPLXK_KLB(CPLXK_KL_CPLX_VD_SCALEFREE); break;
       default: CPLXK_KLB(CPLXK_KL_CPLX_ARD); break;
     }
   })

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(kKlThreads)
 kl_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T* __restrict__ ls2,
           int64_t n, T* __restrict__ out_elem, float* __restrict__ out_sum, double scale,
           KlWorkspace* __restrict__ ws) {
-  constexpr bool kCplx = (kKind == CPLXK_KL_CPLX_VD || kKind == CPLXK_KL_CPLX_ARD);
+  constexpr bool kCplx = kl_kind_is_cplx(kKind);
   constexpr int V = Elem<T>::kVec;
   __shared__ double sh[kKlThreads / 32];
   __shared__ bool is_last;
@@ -158,6 +158,10 @@ static int dispatch_kl(int kind, const void* w_re, const void* w_im, const void*
       return launch_kl<T, CPLXK_KL_CPLX_VD>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st);
     case CPLXK_KL_CPLX_ARD:
       return launch_kl<T, CPLXK_KL_CPLX_ARD>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st);
+    case CPLXK_KL_CPLX_VD_APPROX:
+      return launch_kl<T, CPLXK_KL_CPLX_VD_APPROX>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st);
+    case CPLXK_KL_CPLX_VD_SCALEFREE:
+      return launch_kl<T, CPLXK_KL_CPLX_VD_SCALEFREE>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st);
   }
   return CPLXK_ERR_BADARG;
 }
@@ -173,11 +177,11 @@ extern "C" int cplxk_kl(int kind, const void* w_re, const void* w_im, const void
                         void* workspace, size_t workspace_bytes, void* stream) {
   if (n == 0) {  // empty layer: the sum of nothing
     if (out_sum) CPLXK_CUDA_TRY(cudaMemsetAsync(out_sum, 0, sizeof(float), static_cast<cudaStream_t>(stream)));
-    return (kind < 0 || kind > 3) ? CPLXK_ERR_BADARG : CPLXK_OK;
+    return (kind < 0 || kind >= kKlKinds) ? CPLXK_ERR_BADARG : CPLXK_OK;
   }
   if (!w_re || !log_sigma2 || n < 0 || (!out_elem && !out_sum)) return CPLXK_ERR_BADARG;
-  const bool cplx = (kind == CPLXK_KL_CPLX_VD || kind == CPLXK_KL_CPLX_ARD);
-  if (kind < 0 || kind > 3 || cplx != (w_im != nullptr)) return CPLXK_ERR_BADARG;
+  const bool cplx = kl_kind_is_cplx(kind);
+  if (kind < 0 || kind >= kKlKinds || cplx != (w_im != nullptr)) return CPLXK_ERR_BADARG;
   if (out_sum) {
     if (!workspace || workspace_bytes < sizeof(KlWorkspace)) return CPLXK_ERR_WORKSPACE;
     if (!aligned16(workspace)) return CPLXK_ERR_ALIGN;

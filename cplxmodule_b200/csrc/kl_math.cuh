@@ -87,9 +87,12 @@ __device__ __forceinline__ float ein_of(float t, float n) {
 // logarithm:  2 log(|w| + 1e-12) ~= log(|w|^2 + 1e-24)  (equal at |w| = 0 and for |w| >> 1e-12;
 // in between, |w| ~ 1e-9, log_alpha moves by < 2e-3 -- weights that are pruned anyway), which
 // saves the square root and lets t = 1/alpha = |w|^2 exp(-log_sigma2) come without a log/exp pair.
+constexpr bool kl_kind_is_cplx(int kind) { return kind >= CPLXK_KL_CPLX_VD; }
+constexpr int kKlKinds = 6;
+
 template <int kKind>
 __device__ __forceinline__ float modulus2_of(float wr, float wi) {
-  if constexpr (kKind == CPLXK_KL_CPLX_VD || kKind == CPLXK_KL_CPLX_ARD) {
+  if constexpr (kl_kind_is_cplx(kKind)) {
     return fmaf(wr, wr, wi * wi) + 1e-24f;
   } else {
     return fmaf(wr, wr, 1e-24f);
@@ -112,6 +115,16 @@ __device__ __forceinline__ float penalty_of(float wr, float wi, float ls2) {
     return 0.5f * softplus_f(n);
   } else if constexpr (kKind == CPLXK_KL_CPLX_VD) {
     return ein_of(f_exp(n), n);
+  } else if constexpr (kKind == CPLXK_KL_CPLX_VD_APPROX) {
+    // extensions/complex.py:97-99
+    float z = fmaf(1.36526f, n, -1.45926f);
+    float sig = f_rcp(1.0f + f_exp(-z));
+    return fmaf(0.57810f, sig, softplus_f(n));
+  } else if constexpr (kKind == CPLXK_KL_CPLX_VD_SCALEFREE) {
+    // extensions/complex.py:40-43: log|w| - ls2 - Ei(-t)/2 with t = 1/alpha; since
+    // -Ei(-t) = E1(t) = Ein(t) - gamma - ln t and ln t = 2 log|w| - ls2 this is
+    // (Ein(t) - gamma - ls2) / 2, again free of the cancellation at large log_alpha
+    return 0.5f * (ein_of(f_exp(n), n) - 0.57721566490153286f - ls2);
   } else {
     return softplus_f(n);
   }
@@ -162,6 +175,8 @@ __device__ __forceinline__ float penalty_any(int kind, float wr, float wi, float
     case CPLXK_KL_REAL_VD: return penalty_of<CPLXK_KL_REAL_VD>(wr, wi, ls2);
     case CPLXK_KL_REAL_ARD: return penalty_of<CPLXK_KL_REAL_ARD>(wr, wi, ls2);
     case CPLXK_KL_CPLX_VD: return penalty_of<CPLXK_KL_CPLX_VD>(wr, wi, ls2);
+    case CPLXK_KL_CPLX_VD_APPROX: return penalty_of<CPLXK_KL_CPLX_VD_APPROX>(wr, wi, ls2);
+    case CPLXK_KL_CPLX_VD_SCALEFREE: return penalty_of<CPLXK_KL_CPLX_VD_SCALEFREE>(wr, wi, ls2);
     default: return penalty_of<CPLXK_KL_CPLX_ARD>(wr, wi, ls2);
   }
 }

@@ -74,7 +74,10 @@ typedef enum {
   CPLXK_KL_REAL_VD = 0,  /* nn/relevance/real/vd.py:74-76     */
   CPLXK_KL_REAL_ARD = 1, /* nn/relevance/real/ard.py:39       */
   CPLXK_KL_CPLX_VD = 2,  /* nn/relevance/complex/vd.py:95-99  */
-  CPLXK_KL_CPLX_ARD = 3  /* nn/relevance/complex/ard.py:39    */
+  CPLXK_KL_CPLX_ARD = 3, /* nn/relevance/complex/ard.py:39    */
+  /* nn/relevance/extensions/complex.py */
+  CPLXK_KL_CPLX_VD_APPROX = 4,    /* :77-100  softplus(-la) + 0.57810 sigmoid(-1.36526 la - 1.45926) */
+  CPLXK_KL_CPLX_VD_SCALEFREE = 5  /* :18-44   log|w| - log_sigma2 - Ei(-1/alpha) / 2               */
 } cplxk_kl_kind;
 
 int cplxk_abi_version(void);
@@ -192,7 +195,7 @@ int cplxk_linear_vd_fwd_kl(const void* x_re, const void* x_im,
  * out_elem (nullable): per-element penalty, dtype planes  (reduction=None)
  * out_sum  (nullable): one float, scale * sum(penalty)    (reduction="sum"/"mean",
  *                      nn/relevance/base.py:135-139)
- * w_im must be NULL for the REAL kinds.
+ * w_im must be NULL for the REAL kinds (0, 1) and non-NULL for the complex ones (2..5).
  * workspace: cplxk_kl_workspace_bytes() bytes, 16-byte aligned, zero-filled
  *            once by the caller before first use (the kernel restores it).
  */

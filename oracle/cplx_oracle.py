@@ -113,10 +113,24 @@ def log_alpha_cplx(w_re, w_im, log_sigma2):
     return log_sigma2 - 2 * torch.log(modulus + 1e-12)
 
 
+class _Expi(torch.autograd.Function):
+    """ExpiFunction, nn/relevance/complex/vd.py:15-44: forward = host scipy in the input dtype
+    (:31-36), backward = grad * exp(x) / x (:38-41)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        x_np = x.detach().cpu().numpy()
+        return torch.from_numpy(scipy.special.expi(x_np, dtype=x_np.dtype))
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, = ctx.saved_tensors
+        return grad_output * torch.exp(x) / x
+
+
 def expi(x):
-    """ExpiFunction.forward, nn/relevance/complex/vd.py:31-36: host scipy in the input dtype."""
-    x_np = x.detach().cpu().numpy()
-    return torch.from_numpy(scipy.special.expi(x_np, dtype=x_np.dtype))
+    return _Expi.apply(x)
 
 
 def penalty_real_vd(log_alpha):
@@ -161,6 +175,20 @@ def penalty_cplx_vd_exact64(log_alpha):
     return torch.from_numpy(out)
 
 
+def penalty_cplx_vd_approx(log_alpha):
+    """CplxVDApproxMixin.penalty, nn/relevance/extensions/complex.py:97-99."""
+    n = -log_alpha
+    return F.softplus(n) + 0.57810 * torch.sigmoid(1.36526 * n - 1.45926)
+
+
+def penalty_cplx_vd_scalefree(w_re, w_im, log_sigma2):
+    """CplxVDScaleFreeMixin.penalty, nn/relevance/extensions/complex.py:40-43 (needs the
+    parameters, not just log_alpha)."""
+    log_abs_w = torch.log(torch.norm(torch.stack([w_re, w_im], dim=0), p=2, dim=0) + 1e-12)
+    n_log_alpha = 2 * log_abs_w - log_sigma2
+    return log_abs_w - log_sigma2 - 0.5 * expi(-torch.exp(n_log_alpha))
+
+
 PENALTY = {
     "real_vd": penalty_real_vd,
     "real_ard": penalty_real_ard,
@@ -171,9 +199,12 @@ PENALTY = {
 
 def layer_penalty(kind, w_re, w_im, log_sigma2, reduction="sum"):
     """named_penalties body, nn/relevance/base.py:132-141."""
-    la = log_alpha_cplx(w_re, w_im, log_sigma2) if kind.startswith("cplx") else \
-        log_alpha_real(w_re, log_sigma2)
-    p = PENALTY[kind](la)
+    if kind == "cplx_vd_scalefree":
+        p = penalty_cplx_vd_scalefree(w_re, w_im, log_sigma2)
+    else:
+        la = log_alpha_cplx(w_re, w_im, log_sigma2) if kind.startswith("cplx") else \
+            log_alpha_real(w_re, log_sigma2)
+        p = (penalty_cplx_vd_approx if kind == "cplx_vd_approx" else PENALTY[kind])(la)
     if reduction == "sum":
         return p.sum()
     if reduction == "mean":

@@ -148,6 +148,7 @@ def main():
         eps_im=eps.imag, y_re=out.real, y_im=out.imag,
         penalty_sum=sum(penalties(cvd, reduction="sum")))))
     real_conv_fixtures()
+    extension_fixtures()
     print("golden fixtures written to", os.path.normpath(OUT))
 
 
@@ -188,8 +189,28 @@ def real_conv_fixtures():
         relevance=m.relevance(threshold=3.0))))
 
 
+def extension_fixtures():
+    """CplxLinearVDApprox / CplxLinearVDScaleFree penalties (nn/relevance/extensions/complex.py)."""
+    import_reference()
+    from cplxmodule.nn.relevance.extensions import CplxLinearVDApprox, CplxLinearVDScaleFree
+    from cplxmodule.nn.relevance import penalties
+    os.makedirs(OUT, exist_ok=True)
+    out = {}
+    for name, cls, seed in (("approx", CplxLinearVDApprox, 1010), ("scalefree", CplxLinearVDScaleFree, 1111)):
+        torch.manual_seed(seed)
+        m = cls(29, 17)
+        with torch.no_grad():
+            m.log_sigma2.uniform_(-12, 2)
+        out.update({f"{name}_w_re": m.weight.real, f"{name}_w_im": m.weight.imag,
+                    f"{name}_log_sigma2": m.log_sigma2, f"{name}_penalty": m.penalty,
+                    f"{name}_penalty_sum": sum(penalties(m, reduction="sum"))})
+    np.savez(os.path.join(OUT, "ext_penalties.npz"), **npy(out))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "real_conv":
         real_conv_fixtures()
+    elif len(sys.argv) > 1 and sys.argv[1] == "extensions":
+        extension_fixtures()
     else:
         main()

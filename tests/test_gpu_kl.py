@@ -155,3 +155,46 @@ def test_module_level_penalties():
                            (m.log_alpha.cpu() <= 1.0).float())
     total = sum(penalties(net))
     assert total.shape == () and abs(total.item() - sum(got.values())) < 1e-3 * total.item()
+
+
+# ------------------------------------------------ extension penalties (extensions/complex.py)
+@pytest.mark.parametrize("name,kind,cls_name", [("approx", "cplx_vd_approx", "CplxLinearVDApprox"),
+                                                ("scalefree", "cplx_vd_scalefree", "CplxLinearVDScaleFree")])
+def test_extension_penalties(name, kind, cls_name):
+    """golden values of the live reference, float64 oracle on a wide log_alpha range, gradients
+    against float64 autograd over the oracle, and the pre-pass by-product of the forward"""
+    import cplxmodule_b200 as cb
+    from cplxmodule_b200 import cplx
+    from cplxmodule_b200.nn.relevance import extensions, penalties
+    from tests.conftest import load_golden
+    g = load_golden("ext_penalties")
+    w_re, w_im, ls2 = g[f"{name}_w_re"], g[f"{name}_w_im"], g[f"{name}_log_sigma2"]
+    cls = getattr(extensions, cls_name)
+    m = cls(w_re.shape[1], w_re.shape[0])
+    m.load_state_dict({"weight.real": w_re, "weight.imag": w_im, "bias.real": torch.zeros(w_re.shape[0]),
+                       "bias.imag": torch.zeros(w_re.shape[0]), "log_sigma2": ls2})
+    m = m.to(DEV)
+    want = orc.layer_penalty(kind, w_re.double(), w_im.double(), ls2.double(), None)
+    got = m.penalty.double().cpu()
+    assert float((got - want).abs().max()) <= 2e-5 * float(want.abs().max())
+    ref32 = g[f"{name}_penalty"].double()
+    assert float((got - ref32).abs().max()) <= 1e-3 * float(ref32.abs().max())
+    s = float(sum(penalties(m)))
+    assert abs(s - float(want.sum())) <= 1e-5 * abs(float(want.sum()))
+    # gradients
+    p64 = [t.double().clone().requires_grad_(True) for t in (w_re, w_im, ls2)]
+    orc.layer_penalty(kind, *p64, "sum").backward()
+    m.zero_grad()
+    sum(penalties(m)).backward()
+    for got_g, want_g in zip((m.weight.real.grad, m.weight.imag.grad, m.log_sigma2.grad), p64):
+        assert float((got_g.double().cpu() - want_g.grad).abs().max()) <= 2e-4 * float(want_g.grad.abs().max())
+    # fused into the forward's operand pre-pass
+    torch.manual_seed(0)
+    big = cls(256, 136).to(DEV).train()
+    with torch.no_grad():
+        big.log_sigma2.uniform_(-10, 3)
+        big(cplx.randn(300, 256, device=DEV))
+        assert big._kl_cache._entry is not None
+        fused = float(sum(penalties(big)))
+        alone = float(sum(penalties(big)))
+    assert abs(fused - alone) <= 1e-6 * abs(alone)

@@ -73,6 +73,15 @@ def test_golden_real_conv_vd():
     assert torch.equal((la <= 3.0).to(la), g["relevance"])
 
 
+def test_golden_extension_penalties():
+    """nn/relevance/extensions/complex.py: VDApprox and VDScaleFree penalties of the live reference"""
+    g = load_golden("ext_penalties")
+    for name, kind in (("approx", "cplx_vd_approx"), ("scalefree", "cplx_vd_scalefree")):
+        w_re, w_im, ls2 = g[f"{name}_w_re"], g[f"{name}_w_im"], g[f"{name}_log_sigma2"]
+        assert torch.equal(orc.layer_penalty(kind, w_re, w_im, ls2, None), g[f"{name}_penalty"])
+        assert torch.equal(orc.layer_penalty(kind, w_re, w_im, ls2, "sum"), g[f"{name}_penalty_sum"])
+
+
 def test_golden_penalty_sweep():
     g = load_golden("penalty_sweep")
     la = g["log_sigma2"]
