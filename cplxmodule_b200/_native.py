@@ -25,7 +25,7 @@ EXPORTS = (
     "cplxk_linear_fwd_ws", "cplxk_linear_workspace_bytes",
     "cplxk_linear_vd_fwd", "cplxk_linear_vd_fwd_kl", "cplxk_linear_vd_workspace_bytes", "cplxk_kl_workspace_bytes", "cplxk_kl", "cplxk_log_alpha",
     "cplxk_conv2d_fwd", "cplxk_conv2d_workspace_bytes", "cplxk_randn_philox_torch",
-    "cplxk_transpose2d", "cplxk_colsum", "cplxk_vd_grad_s2", "cplxk_vd_grad_input",
+    "cplxk_transpose2d", "cplxk_eltwise", "cplxk_colsum", "cplxk_vd_grad_s2", "cplxk_vd_grad_input",
     "cplxk_mul_exp", "cplxk_kl_bwd",
 )
 
@@ -63,6 +63,7 @@ def _declare(lib):
     lib.cplxk_conv2d_workspace_bytes.argtypes = [_i64] * 7 + [_int, _int]
     lib.cplxk_randn_philox_torch.argtypes = [_vp, _i64, _u64, _u64, _u32, ctypes.c_float, _vp]
     lib.cplxk_transpose2d.argtypes = [_vp, _vp, _vp, _i64, _i64, _int, _int, _vp]
+    lib.cplxk_eltwise.argtypes = [_int, _vp, _vp, _vp, _i64, _int, _vp]
     lib.cplxk_colsum.argtypes = [_vp, _vp, _i64, _i64, _int, _vp]
     lib.cplxk_vd_grad_s2.argtypes = [_vp] * 5 + [_int, _u64, _u64, _u32, _vp, _i64, _i64, _int, _vp]
     lib.cplxk_vd_grad_input.argtypes = [_vp] * 5 + [_i64, _int, _vp]

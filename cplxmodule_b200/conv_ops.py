@@ -27,14 +27,154 @@ def _circular_pad(input, padding):
 
 
 class _ConvFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, geom):
-        return _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, geom)
+    """Autograd seam of the conv path.  The backward runs on the same CUDA kernels:
+    * dx = g (*) conj(W): the forward conv kernel on the (zero-dilated, for stride > 1) output
+      gradient with the spatially flipped, channel-swapped, conjugated kernel;
+    * dW = g^T . conj(im2col(x)): a GEMM through ``ops._gemm`` (tcgen05 when the shape allows) on
+      an ``unfold`` of the input (data movement only), accumulated over batch chunks;
+    * db = column sums of g; variational part as for the linear layer (``ops._vd_backward_extra``):
+      s2 is recomputed by the conv kernel, the forward's noise regenerated from its Philox
+      coordinates.
+    The reference obtains all of this from torch autograd over ``cplx.py:729-742`` and
+    ``nn/relevance/complex/base.py:120-135``."""
 
     @staticmethod
-    def backward(ctx, *grads):
-        raise NotImplementedError("cplxmodule_b200: backward of the fused conv kernel is not "
-                                  "implemented yet (no silent torch fallback).")
+    def forward(ctx, x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, geom):
+        y_re, y_im, aux = _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, geom)
+        if any(ctx.needs_input_grad):
+            dt = w_re.dtype
+            ctx.geom, ctx.noise, ctx.philox = geom, noise, aux.get("philox")
+            ctx.planes = (x_re.to(dt), None if x_im is None else x_im.to(dt), w_re, w_im,
+                          None if ls2 is None else ls2.to(dt), aux.get("eps_re"), aux.get("eps_im"))
+            ctx.x_dtype = x_re.dtype
+            ctx.has_bias = b_re is not None
+        return y_re, y_im
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_re, g_im):
+        x_re, x_im, w_re, w_im, ls2, eps_re, eps_im = ctx.planes
+        cplx = x_im is not None
+        dt, dev = w_re.dtype, w_re.device
+        need = ctx.needs_input_grad
+        B, C, H, W = x_re.shape
+        O, _, kh, kw = w_re.shape
+        stride, padding, dilation = ctx.geom
+        Ho = (H + 2 * padding[0] - dilation[0] * (kh - 1) - 1) // stride[0] + 1
+        Wo = (W + 2 * padding[1] - dilation[1] * (kw - 1) - 1) // stride[1] + 1
+        zeros = lambda: torch.zeros((B, O, Ho, Wo), dtype=dt, device=dev)
+        g_re = zeros() if g_re is None else g_re.to(dt).contiguous()
+        g_im = (zeros() if g_im is None else g_im.to(dt).contiguous()) if cplx else None
+
+        dx_re = dx_im = dw_re = dw_im = db_re = db_im = dls2 = None
+        if need[0] or (cplx and need[1]):
+            dx_re, dx_im = _conv_dgrad(g_re, g_im, w_re, w_im, (H, W), ctx.geom)
+        if need[2] or (cplx and need[3]):
+            dw_re, dw_im = _conv_wgrad(g_re, g_im, x_re, x_im, (kh, kw), ctx.geom)
+        if ctx.has_bias and (need[4] or (cplx and need[5])):
+            rows = lambda g: g.permute(0, 2, 3, 1).reshape(-1, O).contiguous()
+            db_re = ops._colsum(rows(g_re))
+            db_im = ops._colsum(rows(g_im)) if cplx else None
+
+        if ls2 is not None and (need[0] or need[1] or need[6]):
+            if ctx.noise == nv.NOISE_PHILOX_FAST:
+                raise NotImplementedError(
+                    "backward of the variational conv with the private 'fast' noise layout is not "
+                    "supported; use the torch-exact layout (default) or pass eps")
+            E = ops._eltwise(ops.TR_EXP, ls2)
+            q = ops._eltwise(ops.TR_ABS2, x_re, x_im) if cplx else ops._eltwise(ops.TR_SQR, x_re)
+            s2, _, _ = _conv2d_raw(q, None, E, None, None, None, None, None, None, nv.NOISE_INJECT, ctx.geom)
+            gs2 = torch.empty_like(s2)
+            seed, offset, threads = ctx.philox or (0, 0, 0)
+            with torch.cuda.device(dev):
+                nv.check(nv.lib().cplxk_vd_grad_s2(
+                    nv.ptr(g_re), nv.ptr(g_im), nv.ptr(s2), nv.ptr(eps_re), nv.ptr(eps_im), ctx.noise,
+                    seed, offset, threads, nv.ptr(gs2), s2.numel() // Wo, Wo, nv.dtype_code(dt),
+                    nv.stream_ptr(dev)))
+            if need[0] or need[1]:
+                dq, _ = _conv_dgrad(gs2, None, E, None, (H, W), ctx.geom)
+                with torch.cuda.device(dev):
+                    nv.check(nv.lib().cplxk_vd_grad_input(
+                        nv.ptr(dx_re), nv.ptr(dx_im), nv.ptr(x_re.contiguous()),
+                        nv.ptr(None if x_im is None else x_im.contiguous()), nv.ptr(dq), dq.numel(),
+                        nv.dtype_code(dt), nv.stream_ptr(dev)))
+            if need[6]:
+                dE, _ = _conv_wgrad(gs2, None, q, None, (kh, kw), ctx.geom)
+                dls2 = torch.empty_like(dE)
+                with torch.cuda.device(dev):
+                    nv.check(nv.lib().cplxk_mul_exp(nv.ptr(dE), nv.ptr(ls2.contiguous()), nv.ptr(dls2),
+                                                    dE.numel(), nv.dtype_code(dt), 0, nv.stream_ptr(dev)))
+        cast = lambda t: None if t is None else (t if t.dtype == ctx.x_dtype else t.to(ctx.x_dtype))
+        return (cast(dx_re), cast(dx_im), dw_re, dw_im, db_re, db_im, dls2, None, None, None, None)
+
+
+def _conv_dgrad(g_re, g_im, w_re, w_im, in_hw, geom):
+    """dx = g (*) conj(W) as a forward conv: zero-dilate g by the stride, pad by d(k-1) - p,
+    correlate with W'[c, o, r, s] = conj(W[o, c, kh-1-r, kw-1-s]) at the forward's dilation."""
+    stride, padding, dilation = geom
+    H, W = in_hw
+    B, O, Ho, Wo = g_re.shape
+    _, C, kh, kw = w_re.shape
+    ph, pw = dilation[0] * (kh - 1) - padding[0], dilation[1] * (kw - 1) - padding[1]
+    if ph < 0 or pw < 0:
+        raise NotImplementedError("conv backward needs padding <= dilation * (kernel_size - 1)")
+
+    # the forward drops (H + 2p - d(k-1) - 1) mod s trailing positions from its last window
+    # start, but input rows up to the end of that window still receive gradient: extend the
+    # dilated gradient by that remainder (zeros) instead of padding asymmetrically
+    gh, gw = (Ho - 1) * stride[0] + 1, (Wo - 1) * stride[1] + 1
+    eh = H - (gh + dilation[0] * (kh - 1) - 2 * padding[0])
+    ew = W - (gw + dilation[1] * (kw - 1) - 2 * padding[1])
+
+    def dilate(g):
+        if g is None or (stride == (1, 1) and eh == 0 and ew == 0):
+            return g
+        out = g.new_zeros((B, O, gh + max(eh, 0), gw + max(ew, 0)))
+        out[:, :, :gh:stride[0], :gw:stride[1]] = g      # scatter (data movement)
+        return out
+
+    flip = lambda w: None if w is None else w.flip(2, 3).transpose(0, 1).contiguous()
+    wr, wi = flip(w_re), flip(w_im)
+    if wi is not None:
+        wi = ops._eltwise(ops.TR_NEG, wi)                 # conj
+    dx_re, dx_im, _ = _conv2d_raw(dilate(g_re), dilate(g_im), wr, wi, None, None, None, None, None,
+                                  nv.NOISE_INJECT, ((1, 1), (ph, pw), dilation))
+
+    def fit(t):      # (defensive) crop to the input size
+        if t is None or tuple(t.shape[2:]) == (H, W):
+            return t
+        return t[:, :, :H, :W].contiguous()
+    return fit(dx_re), fit(dx_im)
+
+
+def _conv_wgrad(g_re, g_im, x_re, x_im, khw, geom, max_bytes=1 << 29):
+    """dW[o, (c, r, s)] = sum over (b, pixel) g[b, o, pixel] conj(x_patch[b, (c, r, s), pixel]): one
+    K-major GEMM per batch chunk on an unfold (im2col gather) of the input planes."""
+    stride, padding, dilation = geom
+    B, O, Ho, Wo = g_re.shape
+    C = x_re.shape[1]
+    kh, kw = khw
+    L, ck = Ho * Wo, C * kh * kw
+    per_image = ck * L * x_re.element_size() * (2 if x_im is not None else 1)
+    chunk = max(1, min(B, max_bytes // max(per_image, 1)))
+    dw_re = dw_im = None
+    unfold = lambda t: F.unfold(t, (kh, kw), dilation=dilation, padding=padding, stride=stride)
+    for b0 in range(0, B, chunk):
+        sl = slice(b0, min(B, b0 + chunk))
+        nb = sl.stop - sl.start
+        cols = lambda t: unfold(t[sl]).permute(1, 0, 2).reshape(ck, nb * L).contiguous()
+        rows = lambda g: g[sl].reshape(nb, O, L).permute(1, 0, 2).reshape(O, nb * L).contiguous()
+        p_re = cols(x_re)
+        p_im = None if x_im is None else ops._eltwise(ops.TR_NEG, cols(x_im))     # conj
+        re, im = ops._gemm(rows(g_re), None if g_im is None else rows(g_im), p_re, p_im)
+        if dw_re is None:
+            dw_re, dw_im = re, im
+        else:
+            dw_re.add_(re)
+            if im is not None:
+                dw_im.add_(im)
+    shape = (O, C, kh, kw)
+    return dw_re.reshape(shape), None if dw_im is None else dw_im.reshape(shape)
 
 
 def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, geom):
@@ -106,7 +246,7 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
     nv.check(rc)
     if gen is not None:
         gen.set_offset(offset + inc)
-    return y_re, y_im
+    return y_re, y_im, {"philox": (seed, offset, threads), "eps_re": er, "eps_im": ei}
 
 
 def cplx_convnd(nd, input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,

@@ -193,6 +193,24 @@ kl_bwd_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T* _
   }
 }
 
+// out = op(a [, b]) elementwise: same op codes as the transposing kernel, no transposition
+template <typename T>
+__global__ void __launch_bounds__(256)
+eltwise_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n, int op) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float v = Elem<T>::to_f(a[i]);
+    if (op == TR_NEG) v = -v;
+    else if (op == TR_EXP) v = __expf(v);
+    else if (op == TR_SQR) v = v * v;
+    else if (op == TR_ABS2) {
+      const float w = Elem<T>::to_f(b[i]);
+      v = fmaf(v, v, w * w);
+    }
+    out[i] = Elem<T>::from_f(v);
+  }
+}
+
 static inline int ew_grid(int64_t n) {
   int64_t b = (n + 255) / 256;
   return static_cast<int>(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
@@ -226,6 +244,20 @@ extern "C" int cplxk_transpose2d(const void* in, const void* in2, void* out, int
       case TR_SQR: transpose_kernel<T, TR_SQR><<<grid, 256, 0, st>>>(a, b, o, rows, cols); break;
       default: transpose_kernel<T, TR_ABS2><<<grid, 256, 0, st>>>(a, b, o, rows, cols); break;
     }
+  })
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
+}
+
+extern "C" int cplxk_eltwise(int op, const void* a, const void* b, void* out, int64_t n, int dtype,
+                             void* stream) {
+  if (!a || !out || n < 0 || op < TR_COPY || op > TR_SQR) return CPLXK_ERR_BADARG;
+  if (op == TR_ABS2 && !b) return CPLXK_ERR_BADARG;
+  if (n == 0) return CPLXK_OK;
+  auto st = static_cast<cudaStream_t>(stream);
+  CPLXK_BY_DTYPE(dtype, {
+    eltwise_kernel<T><<<ew_grid(n), 256, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(b),
+                                                  static_cast<T*>(out), n, op);
   })
   CPLXK_CUDA_TRY(cudaGetLastError());
   return CPLXK_OK;

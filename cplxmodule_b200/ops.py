@@ -191,6 +191,17 @@ def _transpose(t, op=TR_COPY, t2=None):
     return out
 
 
+def _eltwise(op, a, b=None):
+    """op(a [, b]) elementwise through the C ABI (TR_NEG, TR_EXP, TR_SQR, TR_ABS2)."""
+    a = a.contiguous()
+    b = None if b is None else b.contiguous()
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        nv.check(nv.lib().cplxk_eltwise(op, nv.ptr(a), nv.ptr(b), nv.ptr(out), a.numel(),
+                                        nv.dtype_code(a.dtype), nv.stream_ptr(a.device)))
+    return out
+
+
 def _colsum(g):
     M, N = g.shape
     out = torch.empty(N, dtype=g.dtype, device=g.device)

@@ -258,6 +258,9 @@ int cplxk_conv2d_fwd(const void* x_re, const void* x_im,
 /* out[cols, rows] = op(in[rows, cols]); op: 0 copy, 1 negate, 2 exp, 3 in^2 + in2^2, 4 in^2 */
 int cplxk_transpose2d(const void* in, const void* in2, void* out, int64_t rows, int64_t cols,
                       int dtype, int op, void* stream);
+/* out = op(a [, b]) elementwise, same op codes, no transposition (conv backward: |x|^2,
+ * exp(log_sigma2), conj) */
+int cplxk_eltwise(int op, const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
 /* out[N] = sum over rows of g[M, N]  (bias gradient) */
 int cplxk_colsum(const void* g, void* out, int64_t M, int64_t N, int dtype, void* stream);
 /* g_s2 = (g_re eps_re + g_im eps_im) / (2 sqrt(s2)) where s2 > 1e-8 (eps as in the forward) */

@@ -197,3 +197,134 @@ def test_training_loop_drop_in():
     with torch.no_grad():
         out = model(x)
     assert torch.isfinite(out.real).all()
+
+
+# ------------------------------------------------------------------------------ convolutions
+CONV_CASES = [
+    # B, C, H, W, O, k, stride, padding, dilation
+    (2, 4, 9, 10, 6, 3, 1, 1, 1),
+    (3, 5, 12, 11, 4, (3, 2), (2, 1), (1, 0), (1, 2)),
+    (2, 8, 16, 16, 8, 3, 2, 1, 1),
+]
+
+
+@pytest.mark.parametrize("B,C,H,W,O,k,stride,padding,dilation", CONV_CASES)
+@pytest.mark.parametrize("vd", [False, True])
+def test_cplx_conv2d_gradients(B, C, H, W, O, k, stride, padding, dilation, vd):
+    """gradients of CplxConv2d / CplxConv2dVD (+ KL) w.r.t. input, kernel, bias and log_sigma2
+    against float64 autograd over the oracle (cplx.py:729-742, complex/base.py:120-135)"""
+    from cplxmodule_b200.nn import CplxConv2d
+    from cplxmodule_b200.nn.relevance import CplxConv2dVD
+    torch.manual_seed(B * 31 + C)
+    cls = CplxConv2dVD if vd else CplxConv2d
+    m = cls(C, O, k, stride=stride, padding=padding, dilation=dilation).to(DEV).train()
+    if vd:
+        with torch.no_grad():
+            m.log_sigma2.uniform_(-6, 0)
+    x_re = torch.randn(B, C, H, W, device=DEV, requires_grad=True)
+    x_im = torch.randn(B, C, H, W, device=DEV, requires_grad=True)
+    with torch.no_grad():
+        shape = m.eval()(cplx.Cplx(x_re, x_im)).shape
+        m.train()
+    c_re, c_im = torch.randn(shape, device=DEV), torch.randn(shape, device=DEV)
+    eps = cplx.Cplx(torch.randn(shape, device=DEV) / 2 ** 0.5, torch.randn(shape, device=DEV) / 2 ** 0.5)
+    out = m(cplx.Cplx(x_re, x_im), eps=eps) if vd else m(cplx.Cplx(x_re, x_im))
+    loss = (out.real * c_re).sum() + (out.imag * c_im).sum()
+    if vd:
+        loss = loss + 0.3 * sum(penalties(m))
+    loss.backward()
+
+    d = lambda t: t.detach().double().cpu().requires_grad_()
+    xr, xi, wr, wi, br, bi = map(d, (x_re, x_im, m.weight.real, m.weight.imag, m.bias.real, m.bias.imag))
+    geom = (m.stride, m.padding, m.dilation)
+    if vd:
+        l2 = d(m.log_sigma2)
+        o = orc.cplx_conv2d_vd(xr, xi, wr, wi, br, bi, l2, eps.real.double().cpu(), eps.imag.double().cpu(), *geom)
+        want = (o[0] * c_re.double().cpu()).sum() + (o[1] * c_im.double().cpu()).sum() \
+            + 0.3 * kl_with_grad64("cplx_vd", wr, wi, l2)
+    else:
+        o = orc.cplx_conv2d(xr, xi, wr, wi, br, bi, *geom)
+        want = (o[0] * c_re.double().cpu()).sum() + (o[1] * c_im.double().cpu()).sum()
+    want.backward()
+    assert abs(loss.item() - want.item()) <= 3e-3 * abs(want.item())
+    pairs = [(x_re.grad, xr.grad), (x_im.grad, xi.grad), (m.weight.real.grad, wr.grad),
+             (m.weight.imag.grad, wi.grad), (m.bias.real.grad, br.grad), (m.bias.imag.grad, bi.grad)]
+    if vd:
+        pairs.append((m.log_sigma2.grad, l2.grad))
+    for got, ref in pairs:
+        assert got is not None and got.shape == ref.shape and rel_err(got, ref) < 3e-3
+
+
+@pytest.mark.parametrize("nd", [1, 2])
+def test_real_conv_vd_gradients_and_fused_noise(nd):
+    """real Conv1dVD / Conv2dVD (grouped): gradients vs float64 autograd over the oracle with
+    injected noise; with in-kernel noise the backward regenerates the forward's draw"""
+    from cplxmodule_b200.nn.relevance import Conv1dVD, Conv2dVD
+    torch.manual_seed(40 + nd)
+    if nd == 1:
+        m = Conv1dVD(6, 4, 3, stride=2, padding=1, groups=2).to(DEV).train()
+        x = torch.randn(3, 6, 19, device=DEV, requires_grad=True)
+        ref_fn = orc.real_conv1d_vd
+    else:
+        m = Conv2dVD(4, 6, (2, 3), padding=(1, 1), dilation=(1, 2), groups=2).to(DEV).train()
+        x = torch.randn(2, 4, 8, 9, device=DEV, requires_grad=True)
+        ref_fn = orc.real_conv2d_vd
+    with torch.no_grad():
+        m.log_sigma2.uniform_(-5, 0)
+        shape = m.eval()(x).shape
+        m.train()
+    c = torch.randn(shape, device=DEV)
+    eps = torch.randn(shape, device=DEV)
+    out = m(x, eps=eps)
+    ((out * c).sum() + 0.7 * sum(penalties(m))).backward()
+    d = lambda t: t.detach().double().cpu().requires_grad_()
+    xr, w, b, l2 = map(d, (x, m.weight, m.bias, m.log_sigma2))
+    o = ref_fn(xr, w, b, l2, eps.double().cpu(), m.stride, m.padding, m.dilation, m.groups)
+    ((o * c.double().cpu()).sum() + 0.7 * kl_with_grad64("real_vd", w, None, l2)).backward()
+    for got, ref in [(x.grad, xr.grad), (m.weight.grad, w.grad), (m.bias.grad, b.grad),
+                     (m.log_sigma2.grad, l2.grad)]:
+        assert rel_err(got, ref) < 2e-4
+    if m.groups == 1:
+        return
+    # ungrouped twin with the torch-exact in-kernel noise: same gradients as with that draw injected
+    torch.manual_seed(5)
+    m1 = (Conv1dVD(6, 4, 3, padding=1) if nd == 1 else Conv2dVD(4, 6, 3, padding=1)).to(DEV).train()
+    xs = x.detach().clone().requires_grad_()
+    grads = []
+    for inject in (False, True):
+        m1.zero_grad(); xs.grad = None
+        torch.manual_seed(123)
+        if inject:
+            with torch.no_grad():
+                e = torch.randn_like(m1.eval()(xs)); m1.train()
+            y = m1(xs, eps=e)
+        else:
+            y = m1(xs)
+        (y * y).sum().backward()
+        grads.append([xs.grad.clone(), m1.weight.grad.clone(), m1.log_sigma2.grad.clone()])
+    for a, b_ in zip(*grads):
+        assert rel_err(a, b_) < 1e-5
+
+
+def test_conv_vd_training_loop_reduces_loss():
+    """drop-in use in a training loop (tests/test_relevance.py:62-73 shape): conv VD + linear VD"""
+    from cplxmodule_b200.nn.relevance import CplxConv2dVD
+    torch.manual_seed(0)
+    conv = CplxConv2dVD(2, 4, 3, padding=1).to(DEV)
+    head = CplxLinearVD(4 * 6 * 6, 3).to(DEV)
+    params = list(conv.parameters()) + list(head.parameters())
+    opt = torch.optim.Adam(params, lr=2e-2)
+    z = cplx.randn(32, 2, 6, 6, device=DEV)
+    target = torch.randn(32, 3, device=DEV)
+    losses = []
+    for _ in range(40):
+        opt.zero_grad()
+        h = conv(z)
+        h = cplx.Cplx(h.real.reshape(32, -1), h.imag.reshape(32, -1))
+        y = head(h)
+        loss = ((y.real - target) ** 2).mean() + (y.imag ** 2).mean() \
+            + 1e-4 * (sum(penalties(conv)) + sum(penalties(head)))
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < 0.5 * losses[0]
