@@ -213,8 +213,8 @@ lin_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
       const bool row_ok = m < p.M;
       OutT* yr = static_cast<OutT*>(p.y_re) + m * p.N + nb;
       OutT* yi = kCplx ? static_cast<OutT*>(p.y_im) + m * p.N + nb : nullptr;
-      const bool vec = (p.N - nb) >= 64 && ((reinterpret_cast<uintptr_t>(yr) & 15u) == 0) &&
-                       (!kCplx || (reinterpret_cast<uintptr_t>(yi) & 15u) == 0);
+      const bool vec = (p.N - nb) >= 64 && ((reinterpret_cast<uintptr_t>(yr) & 31u) == 0) &&
+                       (!kCplx || (reinterpret_cast<uintptr_t>(yi) & 31u) == 0);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int col = c * 16;
@@ -235,28 +235,9 @@ lin_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
           f_im[j] = kCplx ? fmaf(__uint_as_float(r_im[j]), sc, cvb[128 + col + j]) : 0.f;
         }
         if (row_ok && nb + col < p.N) {
-          if (vec) {
-            constexpr int V = Elem<OutT>::kVec;
-#pragma unroll
-            for (int v = 0; v < 16 / V; ++v) {
-              Vec16<OutT> o;
-#pragma unroll
-              for (int j = 0; j < V; ++j) o.v[j] = f_re[v * V + j];
-              o.store(yr + col + v * V);
-              if constexpr (kCplx) {
-#pragma unroll
-                for (int j = 0; j < V; ++j) o.v[j] = f_im[v * V + j];
-                o.store(yi + col + v * V);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (nb + col + j < p.N) {
-                yr[col + j] = Elem<OutT>::from_f(f_re[j]);
-                if constexpr (kCplx) yi[col + j] = Elem<OutT>::from_f(f_im[j]);
-              }
-          }
+          const int nvalid = (p.N - (nb + col)) < 16 ? static_cast<int>(p.N - (nb + col)) : 16;
+          store_run16<OutT>(yr + col, f_re, vec, nvalid);
+          if constexpr (kCplx) store_run16<OutT>(yi + col, f_im, vec, nvalid);
         }
       }
     }

@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -62,10 +64,36 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// 64 consecutive outputs of one row, 16-byte vector stores when the row segment allows
+// 64 consecutive outputs of one row: 32-byte (fp32: st.global.v8, one full sector per lane) or
+// 16-byte vector stores when the row segment allows
 template <typename T>
 __device__ __forceinline__ void store_run64(T* dst, const float (&v)[64], int nvalid) {
   constexpr int V = Elem<T>::kVec;
+  if constexpr (std::is_same<T, float>::value) {
+    if (nvalid == 64 && (reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * c),
+                     "f"(v[8 * c]), "f"(v[8 * c + 1]), "f"(v[8 * c + 2]), "f"(v[8 * c + 3]),
+                     "f"(v[8 * c + 4]), "f"(v[8 * c + 5]), "f"(v[8 * c + 6]), "f"(v[8 * c + 7])
+                     : "memory");
+      return;
+    }
+  }
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (nvalid == 64 && (reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(v[16 * c + 2 * j], v[16 * c + 2 * j + 1]);
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * c),
+                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                     : "memory");
+      }
+      return;
+    }
+  }
   if (nvalid == 64 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
 #pragma unroll
     for (int c = 0; c < 64 / V; ++c) {
@@ -85,6 +113,33 @@ typedef CUresult (*PFN_encodeTiled3)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// sixteen consecutive outputs of one row (16-column drain chunk of fwd_lin3.cu); `full`: all
+// sixteen are inside the row and dst is 32-byte (fp32) / 32-byte (bf16) aligned
+template <typename T>
+__device__ __forceinline__ void store_run16(T* dst, const float (&v)[16], bool full, int nvalid) {
+  if (full) {
+    if constexpr (std::is_same<T, float>::value) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * c),
+                     "f"(v[8 * c]), "f"(v[8 * c + 1]), "f"(v[8 * c + 2]), "f"(v[8 * c + 3]),
+                     "f"(v[8 * c + 4]), "f"(v[8 * c + 5]), "f"(v[8 * c + 6]), "f"(v[8 * c + 7])
+                     : "memory");
+    } else {
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(w[0]),
+                   "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                   : "memory");
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < nvalid) dst[j] = Elem<T>::from_f(v[j]);
+  }
+}
 
 static inline PFN_encodeTiled3 encode_fn3() {
   static PFN_encodeTiled3 fn = nullptr;
