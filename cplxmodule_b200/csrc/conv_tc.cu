@@ -24,6 +24,7 @@
 #include "noise.cuh"
 #include "ptx.cuh"
 #include "conv_tc.cuh"
+#include "tc3_common.cuh"
 
 namespace cplxk {
 
@@ -141,6 +142,32 @@ __device__ __forceinline__ void conv_store8(T* __restrict__ y, const ConvTcGeom&
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     if (o0 + j < g.O) dst[j] = Elem<T>::from_f(v[j]);
+}
+
+// Sixteen consecutive output channels of one pixel: NHWC bf16 rows are written as ONE 32-byte
+// store (a full sector; two 16-byte stores are two partial-sector writes), everything else goes
+// through conv_store8.
+template <typename T>
+__device__ __forceinline__ void conv_store16(T* __restrict__ y, const ConvTcGeom& g, bool nhwc,
+                                             int64_t nchw_off, int64_t hw, int64_t nhwc_off, int o0,
+                                             const float (&v)[16]) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    T* dst = y + nhwc_off + o0;
+    if (nhwc && o0 + 16 <= g.O && (g.O & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(w[0]),
+                   "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                   : "memory");
+      return;
+    }
+  }
+  float lo[8], hi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) lo[j] = v[j], hi[j] = v[8 + j];
+  conv_store8<T>(y, g, nhwc, nchw_off, hw, nhwc_off, o0, lo);
+  conv_store8<T>(y, g, nhwc, nchw_off, hw, nhwc_off, o0 + 8, hi);
 }
 
 // channels-last |x|^2 for the variational forward when the input needs no transposition
@@ -605,25 +632,16 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_xr,
         ptx::tmem_ld_32x32b_x16(lane_base + 128 + col, d2a);    // x_im * U
         ptx::tmem_ld_32x32b_x16(lane_base + 192 + col, d2b);    // x_im * V
         ptx::tmem_ld_wait();
+        float re16[16], im16[16];
 #pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          float re8[8], im8[8];
-          const float4* br4 = reinterpret_cast<const float4*>(sbias + c * 16 + h8 * 8);
-          const float4* bi4 = reinterpret_cast<const float4*>(sbias + 32 + c * 16 + h8 * 8);
-          const float4 r0 = br4[0], r1 = br4[1], i0 = bi4[0], i1 = bi4[1];
-          const float brv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-          const float biv[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int k = h8 * 8 + j;
-            re8[j] = __uint_as_float(d1a[k]) - __uint_as_float(d2b[k]) + brv[j];
-            im8[j] = __uint_as_float(d1b[k]) + __uint_as_float(d2a[k]) + biv[j];
-          }
-          if (pix_ok) {
-            const int o0 = n0 + col + h8 * 8;
-            conv_store8<T>(static_cast<T*>(ep.y_re), g, ep.nhwc != 0, pix_off, hw, cl_off, o0, re8);
-            conv_store8<T>(static_cast<T*>(ep.y_im), g, ep.nhwc != 0, pix_off, hw, cl_off, o0, im8);
-          }
+        for (int k = 0; k < 16; ++k) {
+          re16[k] = __uint_as_float(d1a[k]) - __uint_as_float(d2b[k]) + sbias[c * 16 + k];
+          im16[k] = __uint_as_float(d1b[k]) + __uint_as_float(d2a[k]) + sbias[32 + c * 16 + k];
+        }
+        if (pix_ok) {
+          const int o0 = n0 + col;
+          conv_store16<T>(static_cast<T*>(ep.y_re), g, ep.nhwc != 0, pix_off, hw, cl_off, o0, re16);
+          conv_store16<T>(static_cast<T*>(ep.y_im), g, ep.nhwc != 0, pix_off, hw, cl_off, o0, im16);
         }
       }
       ptx::tcgen05_fence_before();
@@ -636,6 +654,209 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_xr,
   if (warp == 1) {
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// CTA-pair (cta_group::2) version of the persistent conv kernel: the two CTAs of a cluster take
+// two pixel tiles of the same n-block; the stacked [U;V] B operand is split along N across the pair
+// (U in the leader's shared memory, V in the peer's), so every M = 256 MMA reads 4 KB of A and
+// 2 KB of B per CTA instead of 4 KB + 4 KB -- the single-CTA kernel runs at the 128 B/clk
+// shared-memory read limit.  Stages shrink to 40 KB (5 stages).
+template <typename T>
+struct ConvPairCfg {
+  static constexpr bool kBF16 = std::is_same<T, __nv_bfloat16>::value;
+  static constexpr int BKC = 128 / static_cast<int>(sizeof(T));
+  static constexpr int A_TILE = 128 * 128;
+  static constexpr int OFF_XR = 0, OFF_XI = A_TILE, OFF_UV = 2 * A_TILE;
+  static constexpr int STAGE_BYTES = 2 * A_TILE + A_TILE / 2;   // 40 KB
+  static constexpr int STAGES = 5;
+  static constexpr int OFF_BIAS = 256;
+  static constexpr int THREADS = 320;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + OFF_BIAS + 8 * 64 * 4;
+};
+
+template <typename T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
+                          const __grid_constant__ CUtensorMap tm_xi,
+                          const __grid_constant__ CUtensorMap tm_u,
+                          const __grid_constant__ CUtensorMap tm_v, const ConvTcGeom g,
+                          const ConvTcEpi ep, const int total_tiles) {
+  using C = ConvPairCfg<T>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t aux = base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bar_full = aux, bar_empty = aux + 8 * C::STAGES;
+  const uint32_t bar_tfull = aux + 16 * C::STAGES, bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_slot = bar_tempty + 16;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      smem + C::STAGES * C::STAGE_BYTES + 16 * C::STAGES + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  // work item = (pair of pixel tiles, n-block); this CTA's pixel tile is 2 * pair + rank
+  const int pix_tiles = total_tiles / g.tiles_n;
+  const int items = ((pix_tiles + 1) / 2) * g.tiles_n;
+  auto item_tile = [&](int item) { return ((item / g.tiles_n) * 2 + static_cast<int>(rank)) * g.tiles_n + item % g.tiles_n; };
+  const int cchunks = (g.Cp + C::BKC - 1) / C::BKC;
+  const int num_kb = g.kh * g.kw * cchunks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_xr);
+    ptx::prefetch_tensormap(&tm_xi);
+    ptx::prefetch_tensormap(&tm_u);
+    ptx::prefetch_tensormap(&tm_v);
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar_tfull + 8 * i, 1);
+      ptx::mbar_init(bar_tempty + 8 * i, 16);  // one arrive per epilogue warp of BOTH CTAs (leader's is used)
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, 512);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    {
+      const bool elected = ptx::elect_one();
+      uint32_t kbg = 0;  // k-blocks issued so far, across tiles
+      for (int item = cluster_id; item < items; item += num_clusters) {
+        int b, oh0, ow0, n0;
+        conv_tile_coords(g, item_tile(item), b, oh0, ow0, n0);   // b >= B for the odd tile out: OOB zero fill
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const uint32_t s = kbg % C::STAGES, ph = (kbg / C::STAGES) & 1u;
+          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          const uint32_t fb = bar_full + 8 * s, st = base + s * C::STAGE_BYTES;
+          const int rs = kb / cchunks, cc = kb - rs * cchunks;
+          const int r = rs / g.kw, sx = rs - r * g.kw;
+          const int32_t c0 = cc * C::BKC;
+          const int32_t iw = ow0 * g.sw - g.pw + sx * g.dw;
+          const int32_t ih = oh0 * g.sh - g.ph + r * g.dh;
+          const int32_t wrow = rs * g.Op + n0;
+          if (elected) {
+            if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * C::STAGE_BYTES);   // both CTAs' bytes
+            ptx::tma_load_4d_pair(st + C::OFF_XR, &tm_xr, fb, c0, iw, ih, b);
+            ptx::tma_load_4d_pair(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
+            // B = [U(64 rows); V(64 rows)] is split along N across the pair: U here, V in the peer
+            ptx::tma_load_2d_pair(st + C::OFF_UV, leader ? &tm_u : &tm_v, fb, c0, wrow);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      const bool elected = ptx::elect_one();
+      constexpr uint32_t idesc = ptx::make_idesc<C::kBF16>(256, 128, false, false);
+      uint32_t kbg = 0, it = 0;
+      for (int item = cluster_id; item < items; item += num_clusters, ++it) {
+        const uint32_t buf = it & 1u, tph = (it >> 1) & 1u;
+        ptx::mbar_wait_cluster(bar_tempty + 8 * buf, tph ^ 1u);   // both CTAs drained this half
+        ptx::tcgen05_fence_after();
+        const uint32_t t_d1 = tmem_base + buf * 256, t_d2 = t_d1 + 128;
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const uint32_t s = kbg % C::STAGES, ph = (kbg / C::STAGES) & 1u;
+          const uint32_t st = base + s * C::STAGE_BYTES;
+          ptx::mbar_wait(bar_full + 8 * s, ph);
+          ptx::tcgen05_fence_after();
+          const uint64_t a_r = ptx::make_kmajor_desc<128>(st + C::OFF_XR);
+          const uint64_t a_i = ptx::make_kmajor_desc<128>(st + C::OFF_XI);
+          const uint64_t b_uv = ptx::make_kmajor_desc<128>(st + C::OFF_UV);
+          if (elected) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+              const uint32_t off = k * 32;
+              ptx::umma_ss_pair<C::kBF16>(t_d1, ptx::desc_advance(a_r, off), ptx::desc_advance(b_uv, off), idesc, acc);
+              ptx::umma_ss_pair<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc, acc);
+            }
+            ptx::umma_commit_pair(bar_empty + 8 * s);
+          }
+          __syncwarp();
+        }
+        if (elected) ptx::umma_commit_pair(bar_tfull + 8 * buf);
+        __syncwarp();
+      }
+    }
+  } else {
+    // 8 epilogue warps: TMEM lane quarter = warp % 4, channel half = (warp - 2) / 4
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int p = quarter * 32 + lane;
+    const int hh = p / g.Wt, ww = p - hh * g.Wt;
+    const int64_t hw = g.Ho * g.Wo;
+    // this warp's 32 + 32 bias values, staged once per n-block and read back as broadcasts
+    float* sbias = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::OFF_BIAS) +
+                   (warp - 2) * 64;
+    int bias_n0 = -1;
+    uint32_t it = 0;
+    const uint32_t tempty_remote0 = ptx::mapa_u32(bar_tempty, 0);
+    for (int item = cluster_id; item < items; item += num_clusters, ++it) {
+      int b, oh0, ow0, n0;
+      conv_tile_coords(g, item_tile(item), b, oh0, ow0, n0);
+      if (n0 != bias_n0) {
+        __syncwarp();
+        const int o = n0 + half * 32 + lane;
+        float br = 0.f, bi = 0.f;
+        if (ep.b_re && o < g.O) {
+          br = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_re) + o));
+          bi = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_im) + o));
+        }
+        sbias[lane] = br, sbias[32 + lane] = bi;
+        __syncwarp();
+        bias_n0 = n0;
+      }
+      const uint32_t buf = it & 1u, tph = (it >> 1) & 1u;
+      const int64_t oh = oh0 + hh, ow = ow0 + ww;
+      const bool pix_ok = oh < g.Ho && ow < g.Wo && b < g.B;
+      const int64_t pix_off = static_cast<int64_t>(b) * g.O * hw + oh * g.Wo + ow;
+      const int64_t cl_off = ((static_cast<int64_t>(b) * g.Ho + oh) * g.Wo + ow) * g.O;
+      ptx::mbar_wait(bar_tfull + 8 * buf, tph);
+      ptx::tcgen05_fence_after();
+      const uint32_t lane_base = tmem_base + buf * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col = half * 32 + c * 16;
+        uint32_t d1a[16], d1b[16], d2a[16], d2b[16];
+        ptx::tmem_ld_32x32b_x16(lane_base + col, d1a);          // x_re * U
+        ptx::tmem_ld_32x32b_x16(lane_base + 64 + col, d1b);     // x_re * V
+        ptx::tmem_ld_32x32b_x16(lane_base + 128 + col, d2a);    // x_im * U
+        ptx::tmem_ld_32x32b_x16(lane_base + 192 + col, d2b);    // x_im * V
+        ptx::tmem_ld_wait();
+        float re16[16], im16[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          re16[k] = __uint_as_float(d1a[k]) - __uint_as_float(d2b[k]) + sbias[c * 16 + k];
+          im16[k] = __uint_as_float(d1b[k]) + __uint_as_float(d2a[k]) + sbias[32 + c * 16 + k];
+        }
+        if (pix_ok) {
+          const int o0 = n0 + col;
+          conv_store16<T>(static_cast<T*>(ep.y_re), g, ep.nhwc != 0, pix_off, hw, cl_off, o0, re16);
+          conv_store16<T>(static_cast<T*>(ep.y_im), g, ep.nhwc != 0, pix_off, hw, cl_off, o0, im16);
+        }
+      }
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(tempty_remote0 + 8 * buf);   // this half may be overwritten
+    }
+  }
+
+  ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, 512);
   }
 }
 
@@ -803,6 +1024,19 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
       int dev = 0, sms = 148;
       CPLXK_CUDA_TRY(cudaGetDevice(&dev));
       CPLXK_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      const char* pr = std::getenv("CPLXK_CONV_PAIR");
+      if (!(pr && pr[0] == '0') && tiles / g.tiles_n >= 2) {
+        auto pk2 = conv_tc_pair_kernel<T>;
+        CPLXK_CUDA_TRY(cudaFuncSetAttribute(pk2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            ConvPairCfg<T>::SMEM_BYTES));
+        const int64_t items = ((tiles / g.tiles_n + 1) / 2) * g.tiles_n;
+        int64_t clusters = sms / 2;
+        if (clusters > items) clusters = items;
+        pk2<<<static_cast<unsigned>(2 * clusters), ConvPairCfg<T>::THREADS, ConvPairCfg<T>::SMEM_BYTES, st>>>(
+            tm_xr, tm_xi, tm_u, tm_v, g, ep, static_cast<int>(tiles));
+        CPLXK_CUDA_TRY(cudaGetLastError());
+        return CPLXK_OK;
+      }
       auto pk = conv_tc_persistent_kernel<T>;
       CPLXK_CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ConvPCfg<T>::SMEM_BYTES));

@@ -1,5 +1,5 @@
 // Pieces shared by the persistent CTA-pair kernels (fwd_tc3.cu: variational forward,
-// fwd_lin3.cu: plain affine map): cluster-scope mbarrier / TMA-store wrappers, the kind::f16
+// fwd_lin3.cu: plain affine map): cluster-scope mbarrier wrappers, the kind::f16
 // instruction descriptor with an explicit operand format, row stores, tensor-map encoding.
 #pragma once
 #include <cuda_fp16.h>
@@ -33,24 +33,8 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         : "memory");
   }
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int32_t c0,
-                                             int32_t c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() {
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
-                                             uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
-               : "memory");
 }
 // kind::f16 instruction descriptor with explicit operand format (0 = fp16, 1 = bf16)
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t fmt, int M, int N, bool neg_a) {
