@@ -20,6 +20,7 @@ class _CplxGaussianMixin:
 
     def reset_variational_parameters(self):
         self.log_sigma2.data.fill_(-10.0)
+        self.__dict__.pop("_kl_cache", None)   # `.data` writes do not bump the version counter
 
     @property
     def log_alpha(self):

@@ -24,6 +24,7 @@ class _RealGaussianLinear(torch.nn.Linear):
 
     def reset_variational_parameters(self):
         self.log_sigma2.data.fill_(-10.0)
+        self.__dict__.pop("_kl_cache", None)   # `.data` writes do not bump the version counter
 
     def forward(self, input, eps=None):
         if not self.training:
@@ -93,6 +94,7 @@ class _RealGaussianConvNd:
 
     def reset_variational_parameters(self):
         self.log_sigma2.data.fill_(-10.0)
+        self.__dict__.pop("_kl_cache", None)   # `.data` writes do not bump the version counter
 
     def forward(self, input, eps=None):
         from ... import conv_ops

@@ -428,7 +428,9 @@ def real_linear_vd(x, w, b, log_sigma2, eps=None, kl_req=None):
 class FusedKLCache:
     """KL sum produced by the last training-mode forward of a layer, valid while the
     parameters it was computed from are untouched (tensor identity, storage and autograd
-    version counters) and handed out once."""
+    version counters) and handed out once.  Caveat: writes through ``param.data`` do not bump
+    the version counter -- code that edits parameters that way between a forward and the
+    ``penalties()`` of the same step should call ``set_kl_fusion(False)``."""
 
     def __init__(self):
         self._entry = None
