@@ -59,6 +59,7 @@ struct Tc3Params {
   int tiles_m2, tiles_n;   // tiles of 256 rows, 128 columns
   int f16;                 // mean operands are fp16 (else bf16)
   int dbg;                 // CPLXK_DBG: 1 = MMAs without loads, 2 = loads without MMAs, 3 = no mainloop
+  int group;               // 256-row tiles per raster group (CPLXK_RASTER, default 6)
   const float* sx;         // [M] inverse row scales of x (nullable)
   const float* sw;         // [N] inverse row scales of W (nullable)
   EpiParams ep;
@@ -91,7 +92,7 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
   const int num_kb = p.dbg == 3 ? 0 : static_cast<int>((p.K + C::BK - 1) / C::BK);
 
   auto decode_tile = [&](int t, int& tile_m, int& tile_n) {
-    constexpr int kGroup = 6;   // 256-row tiles per raster group
+    const int kGroup = p.group;   // 256-row tiles per raster group
     const int per_group = kGroup * p.tiles_n;
     const int g = t / per_group;
     const int first_m = g * kGroup;
@@ -489,6 +490,9 @@ static int launch_tc3(const Tc3Operands& o, int64_t M, int64_t N, int64_t K, con
   p.f16 = o.f16 ? 1 : 0;
   const char* dbg_env = std::getenv("CPLXK_DBG");
   p.dbg = dbg_env ? std::atoi(dbg_env) : 0;
+  const char* rs = std::getenv("CPLXK_RASTER");
+  p.group = rs ? std::atoi(rs) : 6;
+  if (p.group < 1) p.group = 6;
   p.sx = o.sx, p.sw = o.sw;
   p.ep = ep;
   const int64_t pairs = static_cast<int64_t>(p.tiles_m2) * p.tiles_n;

@@ -152,14 +152,16 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
                 kl_ws = nv.kl_workspace(dev)
                 done = ctypes.c_int(0)
                 lo, hi = kl_req.get("rows") or (0, -1)
-                ev = torch.cuda.Event()
-                ev.record(torch.cuda.current_stream(dev))   # materialises the handle; re-recorded by the call
+                ev = None
+                if "rows" in kl_req:     # multi-GPU shard: a collective on a side stream will wait for it
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream(dev))   # materialises the handle; re-recorded by the call
                 nv.check(lib.cplxk_linear_vd_fwd_kl(
                     nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi), nv.ptr(br), nv.ptr(bi),
                     nv.ptr(ls2), nv.ptr(er), nv.ptr(ei), noise, seed, offset, threads,
                     nv.ptr(y_re), nv.ptr(y_im), M, N, K, code, math, nv.ptr(s2), nv.ptr(ws),
                     ws_bytes, kl_req["kind"], nv.ptr(kl_sum), nv.ptr(kl_ws), kl_ws.numel() * 8,
-                    lo, hi, ctypes.c_void_p(ev.cuda_event), ctypes.byref(done), st))
+                    lo, hi, None if ev is None else ctypes.c_void_p(ev.cuda_event), ctypes.byref(done), st))
                 if done.value:
                     kl_req["sum"], kl_req["event"] = kl_sum, ev
             else:

@@ -48,6 +48,9 @@ def main():
         def setenv(variant):
             os.environ.pop("CPLXK_PERSIST", None)
             os.environ.pop("CPLXK_F16", None)
+            os.environ.pop("CPLXK_RASTER", None)
+            if variant.startswith("raster"):
+                os.environ["CPLXK_RASTER"] = variant[6:]
             if variant == "nopersist":
                 os.environ["CPLXK_PERSIST"] = "0"
             elif variant == "tf32":
