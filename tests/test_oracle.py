@@ -180,3 +180,45 @@ def test_oracle_vs_live_reference():
         eps = torch.randn(19, 45)
         assert torch.equal(orc.real_linear_vd(x, m.weight, m.bias, m.log_sigma2, eps), out)
         assert torch.equal(orc.layer_penalty(kind, m.weight, None, m.log_sigma2), sum(penalties(m)))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference not present on this machine")
+def test_oracle_vs_live_reference_conv_vd_and_extensions():
+    """real-valued conv VD forward (+ its gradients through the differentiable Ei restatement)
+    and the extension penalties, bit-for-bit against the live reference"""
+    from oracle.make_golden import import_reference
+    import_reference()
+    from cplxmodule.nn.relevance import Conv1dVD, Conv2dARD, penalties
+    from cplxmodule.nn.relevance.extensions import CplxLinearVDApprox, CplxLinearVDScaleFree
+
+    torch.manual_seed(4321)
+    m = Conv2dARD(4, 6, 3, stride=2, padding=1, dilation=1, groups=2).train()
+    with torch.no_grad():
+        m.log_sigma2.uniform_(-12, 2)
+    x = torch.randn(3, 4, 11, 9)
+    state = torch.get_rng_state()
+    out = m(x)
+    torch.set_rng_state(state)
+    eps = torch.randn_like(out)
+    assert torch.equal(orc.real_conv2d_vd(x, m.weight, m.bias, m.log_sigma2, eps, 2, 1, 1, 2), out)
+    assert torch.equal(orc.layer_penalty("real_ard", m.weight, None, m.log_sigma2), sum(penalties(m)))
+    m = Conv1dVD(3, 5, 4, padding=2).train()
+    x = torch.randn(2, 3, 17)
+    state = torch.get_rng_state()
+    out = m(x)
+    torch.set_rng_state(state)
+    eps = torch.randn_like(out)
+    assert torch.equal(orc.real_conv1d_vd(x, m.weight, m.bias, m.log_sigma2, eps, 1, 2, 1, 1), out)
+
+    for cls, kind in ((CplxLinearVDApprox, "cplx_vd_approx"), (CplxLinearVDScaleFree, "cplx_vd_scalefree")):
+        m = cls(23, 11)
+        with torch.no_grad():
+            m.log_sigma2.uniform_(-12, 2)
+        ref = sum(penalties(m))
+        w_re, w_im, ls2 = (t.detach().clone().requires_grad_() for t in
+                           (m.weight.real, m.weight.imag, m.log_sigma2))
+        mine = orc.layer_penalty(kind, w_re, w_im, ls2)
+        assert torch.equal(mine, ref)
+        ref.backward()
+        mine.backward()
+        assert torch.equal(w_re.grad, m.weight.real.grad) and torch.equal(ls2.grad, m.log_sigma2.grad)
