@@ -214,24 +214,46 @@ __device__ __forceinline__ void noise_prefetch(const EpiParams& p, int64_t m, in
     for (int trip = 0; trip < R / 8; ++trip) {
 #pragma unroll
       for (int j = 0; j < R - 8; ++j) nre[j] = nre[j + 8];
+      if (idx_re + 7u < Tn) {   // the run does not wrap the thread index: one slot for all eight
+        const uint64_t ctr = p.noise.ctr_base + (slot_re >> 2);
+        const uint32_t comp = static_cast<uint32_t>(slot_re) & 3u;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint32_t i = idx_re + j;
-        const bool wrap = i >= Tn;
-        i = wrap ? i - Tn : i;
-        nre[R - 8 + j] = philox_torch_normal(i, slot_re + (wrap ? 1u : 0u), p.noise) * p.noise.scale;
+        for (int j = 0; j < 8; ++j)
+          nre[R - 8 + j] = philox_torch_normal_at(ctr, idx_re + j, comp, p.noise) * p.noise.scale;
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+          uint32_t i = idx_re + j;
+          const bool wrap = i >= Tn;
+          i = wrap ? i - Tn : i;
+          const float v = philox_torch_normal(i, slot_re + (wrap ? 1u : 0u), p.noise) * p.noise.scale;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q == j) nre[R - 8 + q] = v;
+        }
       }
       idx_re += 8;
       if (idx_re >= Tn) idx_re -= Tn, ++slot_re;
       if constexpr (kCplx) {
 #pragma unroll
         for (int j = 0; j < R - 8; ++j) nim[j] = nim[j + 8];
+        if (idx_im + 7u < Tn) {
+          const uint64_t ctr = p.noise.ctr_base + (slot_im >> 2);
+          const uint32_t comp = static_cast<uint32_t>(slot_im) & 3u;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint32_t i = idx_im + j;
-          const bool wrap = i >= Tn;
-          i = wrap ? i - Tn : i;
-          nim[R - 8 + j] = philox_torch_normal(i, slot_im + (wrap ? 1u : 0u), p.noise) * p.noise.scale;
+          for (int j = 0; j < 8; ++j)
+            nim[R - 8 + j] = philox_torch_normal_at(ctr, idx_im + j, comp, p.noise) * p.noise.scale;
+        } else {
+#pragma unroll 1
+          for (int j = 0; j < 8; ++j) {
+            uint32_t i = idx_im + j;
+            const bool wrap = i >= Tn;
+            i = wrap ? i - Tn : i;
+            const float v = philox_torch_normal(i, slot_im + (wrap ? 1u : 0u), p.noise) * p.noise.scale;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q == j) nim[R - 8 + q] = v;
+          }
         }
         idx_im += 8;
         if (idx_im >= Tn) idx_im -= Tn, ++slot_im;

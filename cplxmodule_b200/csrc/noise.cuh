@@ -54,6 +54,24 @@ __device__ __forceinline__ float philox_torch_normal(uint32_t idx, uint64_t slot
   return (comp & 1u) ? g.y : g.x;
 }
 
+// Same normal with the slot-dependent parts (Philox counter, Box-Muller component) supplied by
+// the caller: a run of consecutive elements that does not wrap the thread index shares them, so
+// they are computed once per run.  Branch-free (selects): the eight chains of a run interleave.
+// Bit-identical to philox_torch_normal: _curand_box_muller is
+//   u = x * 2^-32 + 2^-33,  v = y * (2^-32 * 2 pi) + (2^-32 * 2 pi / 2),  s = sqrtf(-2 logf(u)),
+//   __sincosf(v, &sin, &cos)  ->  (sin * s, cos * s).
+__device__ __forceinline__ float philox_torch_normal_at(uint64_t ctr, uint32_t idx, uint32_t comp,
+                                                        const NoiseParams& np) {
+  uint4 c = make_uint4(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), idx, 0u);
+  uint4 r = philox4x32_10(c, PhiloxKey{np.seed_lo, np.seed_hi});
+  const uint32_t ux = comp < 2u ? r.x : r.z, uy = comp < 2u ? r.y : r.w;
+  const float u = ux * CURAND_2POW32_INV + (CURAND_2POW32_INV / 2);
+  const float v = uy * CURAND_2POW32_INV_2PI + (CURAND_2POW32_INV_2PI / 2);
+  const float s = sqrtf(-2.0f * logf(u));
+  const float t = (comp & 1u) ? __cosf(v) : __sinf(v);
+  return t * s;
+}
+
 // Walks consecutive linear elements li, li+1, ... of torch's layout without a
 // division per element.
 struct TorchNoiseCursor {

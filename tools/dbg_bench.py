@@ -31,7 +31,9 @@ def timeit(fn, iters=20, warm=3):
 def main():
     torch.manual_seed(0)
     rows = []
-    for dt_name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+    dts = [d for d in (("f32", torch.float32), ("bf16", torch.bfloat16))
+           if d[0] in os.environ.get("DBG_DTYPES", "f32,bf16").split(",")]
+    for dt_name, dt in dts:
         xr = (torch.randn(M, K, device=DEV) / 2 ** 0.5).to(dt)
         xi = (torch.randn(M, K, device=DEV) / 2 ** 0.5).to(dt)
         bound = 1 / (2 * K) ** 0.5
@@ -72,7 +74,8 @@ def main():
                         res[v].append(timeit(fn, iters=50))
                 for v, ts in res.items():
                     rows.append(dict(dtype=dt_name, variant=v, noise=noise, dbg=dbg,
-                                     ms_min=round(min(ts), 4), ms_med=round(sorted(ts)[len(ts) // 2], 4)))
+                                     ms_min=round(min(ts), 4), ms_med=round(sorted(ts)[len(ts) // 2], 4),
+                                     ms_mean=round(sum(ts) / len(ts), 4)))
                     print(json.dumps(rows[-1]), flush=True)
         os.environ.pop("CPLXK_PERSIST", None)
         os.environ.pop("CPLXK_F16", None)
