@@ -97,9 +97,9 @@ class ClockSampler:
 
 # dram bytes (read + write) per launch from the committed ncu --set full captures (profiles/)
 NCU_TRAFFIC = {
-    "gemm_f32": 632.00e6 + 189.00e6,     # profiles/prof_tc3_f32_r1.raw.csv  (fwd_tc3_kernel<float, cplx>)
-    "gemm_bf16": 625.78e6 + 122.52e6,    # profiles/prof_tc3_bf16_r1.raw.csv
-    "prepass_f32": 336.39e6 + 173.01e6,  # profiles/prof_prep_f32_r1.raw.csv (vd_prepare_f16_kernel<cplx>)
+    "gemm_f32": 631.48e6 + 186.73e6,     # profiles/prof_tc3_f32_r1.raw.csv  (fwd_tc3_kernel<float, cplx>)
+    "gemm_bf16": 625.43e6 + 120.13e6,    # profiles/prof_tc3_bf16_r1.raw.csv
+    "prepass_f32": 336.51e6 + 172.87e6,  # profiles/prof_prep_f32_r1.raw.csv (vd_prepare_f16_kernel<cplx>)
 }
 
 
