@@ -185,6 +185,134 @@ conv_abs2_kernel(const T* __restrict__ x_re, const T* __restrict__ x_im, T* __re
   }
 }
 
+// ---- fp32 planes on fp16 operands (NCHW inputs: a transposing pre-pass exists anyway) --------
+// The im2col rows of one image overlap, so only a per-IMAGE power-of-two scale factors out of the
+// GEMM (per output channel on the weight side).  Same 11-bit significand as tf32, twice the MMA
+// rate, half the operand bytes.  power-of-two scale that puts `amax` into [2^13, 2^14).
+__device__ __forceinline__ int f16_scale_exp(float amax) {
+  const int ex = static_cast<int>((__float_as_uint(amax) >> 23) & 0xffu) - 127;
+  int s = 13 - ex;
+  if (amax == 0.f || ex == 128) s = 0;      // empty, or inf / nan: leave as is
+  return s > 126 ? 126 : s;
+}
+__device__ __forceinline__ float pow2f(int s) { return __uint_as_float(static_cast<uint32_t>(s + 127) << 23); }
+
+// amax[b] = max |x_re|, |x_im| over image b (non-negative floats order like their bit patterns;
+// NaN bits compare above inf and end up as "leave as is")
+__global__ void __launch_bounds__(256)
+conv_amax_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im, int64_t per_image,
+                 unsigned int* __restrict__ amax) {
+  const int64_t b = blockIdx.y;
+  const float* xr = x_re + b * per_image;
+  const float* xi = x_im + b * per_image;
+  unsigned int mbits = 0u;      // largest |value| as a bit pattern
+  auto upd = [&](float v) {
+    const unsigned int bits = __float_as_uint(v) & 0x7fffffffu;
+    mbits = bits > mbits ? bits : mbits;
+  };
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  // 16-byte loads when every image starts on a 16-byte boundary
+  const bool vec = (per_image % 4 == 0) && (((reinterpret_cast<uintptr_t>(x_re) | reinterpret_cast<uintptr_t>(x_im)) & 15u) == 0);
+  if (vec) {
+    const float4* pr = reinterpret_cast<const float4*>(xr);
+    const float4* pi = reinterpret_cast<const float4*>(xi);
+    for (int64_t i = tid; i < per_image / 4; i += nth) {
+      const float4 a = __ldg(pr + i), c = __ldg(pi + i);
+      upd(a.x), upd(a.y), upd(a.z), upd(a.w), upd(c.x), upd(c.y), upd(c.z), upd(c.w);
+    }
+  } else {
+    for (int64_t i = tid; i < per_image; i += nth) upd(xr[i]), upd(xi[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned int other = __shfl_xor_sync(0xffffffffu, mbits, o);
+    mbits = other > mbits ? other : mbits;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(amax + b, mbits);
+}
+
+// NCHW fp32 -> channels-last fp16 (channels padded to Cp), scaled by the image's power of two.
+// One block = 64 channels x 32 pixels of one image row: reads are 128-byte rows along W, writes
+// are 128-byte rows along C (each lane two channels as one half2).
+__global__ void __launch_bounds__(256)
+conv_nhwc_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im,
+                     __half* __restrict__ o_re, __half* __restrict__ o_im,
+                     const unsigned int* __restrict__ amax, int C, int Cp, int H, int W) {
+  __shared__ float s_re[64][33], s_im[64][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int w0 = blockIdx.z * 32, c0 = blockIdx.y * 64;
+  const int64_t bh = blockIdx.x;
+  const int64_t b = bh / H, h = bh - b * H;
+  const float scale = pow2f(f16_scale_exp(__uint_as_float(amax[b])));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + ty + 8 * i, w = w0 + tx;
+    float vr = 0.f, vi = 0.f;
+    if (c < C && w < W) {
+      const int64_t off = ((b * C + c) * H + h) * W + w;
+      vr = x_re[off], vi = x_im[off];
+    }
+    s_re[ty + 8 * i][tx] = vr, s_im[ty + 8 * i][tx] = vi;
+  }
+  __syncthreads();
+  const int c = c0 + 2 * tx;          // Cp is a multiple of 16: channel pairs never straddle it
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int wl = ty + 8 * i, w = w0 + wl;
+    if (w < W && c < Cp) {
+      const int64_t off = ((b * H + h) * W + w) * Cp + c;
+      *reinterpret_cast<__half2*>(o_re + off) =
+          __floats2half2_rn(s_re[2 * tx][wl] * scale, s_re[2 * tx + 1][wl] * scale);
+      *reinterpret_cast<__half2*>(o_im + off) =
+          __floats2half2_rn(s_im[2 * tx][wl] * scale, s_im[2 * tx + 1][wl] * scale);
+    }
+  }
+}
+
+// weights [O, C, kh, kw] fp32 -> tap-major fp16 planes [(r*kw+s) * Op + o][Cp], one block per
+// output channel: its own power-of-two scale, inverse to isw[o]
+__global__ void __launch_bounds__(256)
+conv_wprep_f16_kernel(const float* __restrict__ w_re, const float* __restrict__ w_im,
+                      __half* __restrict__ u, __half* __restrict__ v, float* __restrict__ isw, int O,
+                      int Op, int C, int Cp, int khw) {
+  __shared__ unsigned int red[8];
+  const int o = blockIdx.x;
+  const int n = C * khw;
+  unsigned int m = 0u;
+  if (o < O) {
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const unsigned int a = __float_as_uint(w_re[static_cast<int64_t>(o) * n + i]) & 0x7fffffffu;
+      const unsigned int b = __float_as_uint(w_im[static_cast<int64_t>(o) * n + i]) & 0x7fffffffu;
+      m = a > m ? a : m;
+      m = b > m ? b : m;
+    }
+  }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) {
+    const unsigned int other = __shfl_xor_sync(0xffffffffu, m, k);
+    m = other > m ? other : m;
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) m = red[k] > m ? red[k] : m;
+  const int s = f16_scale_exp(__uint_as_float(m));
+  const float scale = pow2f(s);
+  if (threadIdx.x == 0) isw[o] = pow2f(-s);
+  for (int i = threadIdx.x; i < khw * Cp; i += 256) {
+    const int rs = i / Cp, c = i - rs * Cp;
+    float fu = 0.f, fv = 0.f;
+    if (o < O && c < C) {
+      const int64_t src = (static_cast<int64_t>(o) * C + c) * khw + rs;
+      fu = w_re[src] * scale, fv = w_im[src] * scale;
+    }
+    const int64_t dst = (static_cast<int64_t>(rs) * Op + o) * Cp + c;
+    u[dst] = __float2half_rn(fu), v[dst] = __float2half_rn(fv);
+  }
+}
+
 // ------------------------------------------------------------------------ main kernel
 template <typename T, bool kVD>
 struct ConvCfg {
@@ -662,27 +790,28 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_xr,
 // (U in the leader's shared memory, V in the peer's), so every M = 256 MMA reads 4 KB of A and
 // 2 KB of B per CTA instead of 4 KB + 4 KB -- the single-CTA kernel runs at the 128 B/clk
 // shared-memory read limit.  Stages shrink to 40 KB (5 stages).
-template <typename T>
+template <typename T, bool kHalf = false>
 struct ConvPairCfg {
-  static constexpr bool kBF16 = std::is_same<T, __nv_bfloat16>::value;
-  static constexpr int BKC = 128 / static_cast<int>(sizeof(T));
+  static_assert(!kHalf || std::is_same<T, float>::value, "fp16 operand copies: fp32 planes");
+  static constexpr bool kBF16 = std::is_same<T, __nv_bfloat16>::value || kHalf;   // kind::f16
+  static constexpr int BKC = kHalf ? 64 : 128 / static_cast<int>(sizeof(T));
   static constexpr int A_TILE = 128 * 128;
   static constexpr int OFF_XR = 0, OFF_XI = A_TILE, OFF_UV = 2 * A_TILE;
   static constexpr int STAGE_BYTES = 2 * A_TILE + A_TILE / 2;   // 40 KB
   static constexpr int STAGES = 5;
   static constexpr int OFF_BIAS = 256;
   static constexpr int THREADS = 320;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + OFF_BIAS + 8 * 64 * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + OFF_BIAS + 8 * 96 * 4;
 };
 
-template <typename T>
+template <typename T, bool kHalf = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
                           const __grid_constant__ CUtensorMap tm_xi,
                           const __grid_constant__ CUtensorMap tm_u,
                           const __grid_constant__ CUtensorMap tm_v, const ConvTcGeom g,
                           const ConvTcEpi ep, const int total_tiles) {
-  using C = ConvPairCfg<T>;
+  using C = ConvPairCfg<T, kHalf>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -760,7 +889,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
   } else if (warp == 1) {
     if (leader) {
       const bool elected = ptx::elect_one();
-      constexpr uint32_t idesc = ptx::make_idesc<C::kBF16>(256, 128, false, false);
+      // a/b format bits: 1 = bf16, 0 = fp16 (scaled fp32 planes), 2 = tf32
+      constexpr uint32_t idesc = ptx::make_idesc<C::kBF16>(256, 128, false, false) ^
+                                 (kHalf ? ((1u << 7) | (1u << 10)) : 0u);
       uint32_t kbg = 0, it = 0;
       for (int item = cluster_id; item < items; item += num_clusters, ++it) {
         const uint32_t buf = it & 1u, tph = (it >> 1) & 1u;
@@ -799,7 +930,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
     const int64_t hw = g.Ho * g.Wo;
     // this warp's 32 + 32 bias values, staged once per n-block and read back as broadcasts
     float* sbias = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::OFF_BIAS) +
-                   (warp - 2) * 64;
+                   (warp - 2) * 96;
     int bias_n0 = -1;
     uint32_t it = 0;
     const uint32_t tempty_remote0 = ptx::mapa_u32(bar_tempty, 0);
@@ -815,9 +946,12 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
           bi = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_im) + o));
         }
         sbias[lane] = br, sbias[32 + lane] = bi;
+        if constexpr (kHalf) sbias[64 + lane] = o < g.O ? __ldg(ep.isw + o) : 1.f;
         __syncwarp();
         bias_n0 = n0;
       }
+      [[maybe_unused]] float isx = 1.f;     // inverse of this image's power-of-two scale
+      if constexpr (kHalf) isx = b < g.B ? pow2f(-f16_scale_exp(__uint_as_float(__ldg(ep.amax + b)))) : 1.f;
       const uint32_t buf = it & 1u, tph = (it >> 1) & 1u;
       const int64_t oh = oh0 + hh, ow = ow0 + ww;
       const bool pix_ok = oh < g.Ho && ow < g.Wo && b < g.B;
@@ -838,8 +972,14 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
         float re16[16], im16[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          re16[k] = __uint_as_float(d1a[k]) - __uint_as_float(d2b[k]) + sbias[c * 16 + k];
-          im16[k] = __uint_as_float(d1b[k]) + __uint_as_float(d2a[k]) + sbias[32 + c * 16 + k];
+          if constexpr (kHalf) {
+            const float sc = isx * sbias[64 + c * 16 + k];
+            re16[k] = fmaf(__uint_as_float(d1a[k]) - __uint_as_float(d2b[k]), sc, sbias[c * 16 + k]);
+            im16[k] = fmaf(__uint_as_float(d1b[k]) + __uint_as_float(d2a[k]), sc, sbias[32 + c * 16 + k]);
+          } else {
+            re16[k] = __uint_as_float(d1a[k]) - __uint_as_float(d2b[k]) + sbias[c * 16 + k];
+            im16[k] = __uint_as_float(d1b[k]) + __uint_as_float(d2a[k]) + sbias[32 + c * 16 + k];
+          }
         }
         if (pix_ok) {
           const int o0 = n0 + col;
@@ -882,7 +1022,8 @@ static PFN_encodeTiledC conv_encode_fn() {
 template <typename T>
 static CUtensorMapDataType conv_dt() {
   return std::is_same<T, float>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-                                       : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+         : std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                          : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 }
 
 // channels-last activation plane [B, H, W, Cp]: box {BKC channels, Wt px (stride sw), Ht rows (stride sh), 1}
@@ -947,7 +1088,9 @@ size_t conv_tc_workspace_bytes(int dtype, bool vd, int64_t B, int64_t C, int64_t
   const size_t es = dtype == CPLXK_F32 ? 4 : 2;
   const size_t act = up256(static_cast<size_t>(B) * H * W * g.Cp * es);
   const size_t wgt = up256(static_cast<size_t>(kh) * kw * g.Op * g.Cp * es);
-  return (vd ? 3 : 2) * act + (vd ? 3 : 2) * wgt;
+  // + per-image maxima and per-output-channel scales of the fp16 operand path
+  return (vd ? 3 : 2) * act + (vd ? 3 : 2) * wgt + up256(static_cast<size_t>(B) * 4) +
+         up256(static_cast<size_t>(g.Op) * 4);
 }
 
 bool conv_tc_supported(int dtype, int64_t B, int64_t C, int64_t H, int64_t W, int64_t O, int64_t Ho,
@@ -959,6 +1102,68 @@ bool conv_tc_supported(int dtype, int64_t B, int64_t C, int64_t H, int64_t W, in
   if ((g.Wt - 1) * sw + 1 > 256 || (g.Ht - 1) * sh + 1 > 256) return false;  // TMA box limit
   const int64_t tiles = B * g.tiles_h * g.tiles_w * g.tiles_n;
   return tiles > 0 && tiles <= 0x7fffffff && kh * kw <= 4096;
+}
+
+// fp32 NCHW planes on fp16 operands: per-image amax -> transposing, scaling pre-pass -> weights
+// with per-output-channel scales -> CTA-pair kernel on kind::f16
+static int launch_conv_f16(const void* x_re, const void* x_im, const void* w_re, const void* w_im,
+                           void* workspace, ConvTcGeom g, const ConvTcEpi& ep_in, cudaStream_t st) {
+  const size_t act32 = up256(static_cast<size_t>(g.B) * g.H * g.W * g.Cp * 4);
+  const size_t wgt32 = up256(static_cast<size_t>(g.kh) * g.kw * g.Op * g.Cp * 4);
+  g.Cp = static_cast<int>((g.C + 15) / 16 * 16);          // whole 32-byte k-steps of fp16
+  const size_t act = up256(static_cast<size_t>(g.B) * g.H * g.W * g.Cp * 2);
+  const size_t wgt = up256(static_cast<size_t>(g.kh) * g.kw * g.Op * g.Cp * 2);
+  if (2 * act > 2 * act32 || 2 * wgt > 2 * wgt32) return CPLXK_ERR_WORKSPACE;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  __half* a_re = reinterpret_cast<__half*>(ws);
+  __half* a_im = reinterpret_cast<__half*>(ws + act);
+  __half* u = reinterpret_cast<__half*>(ws + 2 * act32);
+  __half* v = reinterpret_cast<__half*>(ws + 2 * act32 + wgt);
+  unsigned int* amax = reinterpret_cast<unsigned int*>(ws + 2 * act32 + 2 * wgt32);
+  float* isw = reinterpret_cast<float*>(ws + 2 * act32 + 2 * wgt32 + up256(static_cast<size_t>(g.B) * 4));
+
+  CPLXK_CUDA_TRY(cudaMemsetAsync(amax, 0, static_cast<size_t>(g.B) * 4, st));
+  const int64_t per_image = g.C * g.H * g.W;
+  int64_t chunks = per_image / (4 * 256 * 8) + 1;
+  if (chunks > 64) chunks = 64;
+  if (g.B > 65535) return CPLXK_ERR_UNSUPPORTED;
+  conv_amax_kernel<<<dim3(static_cast<unsigned>(chunks), static_cast<unsigned>(g.B)), 256, 0, st>>>(
+      static_cast<const float*>(x_re), static_cast<const float*>(x_im), per_image, amax);
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  dim3 tg(static_cast<unsigned>(g.B * g.H), static_cast<unsigned>((g.Cp + 63) / 64),
+          static_cast<unsigned>((g.W + 31) / 32));
+  if (tg.y > 65535u || tg.z > 65535u || g.B * g.H > 0x7fffffff) return CPLXK_ERR_UNSUPPORTED;
+  conv_nhwc_f16_kernel<<<tg, 256, 0, st>>>(static_cast<const float*>(x_re), static_cast<const float*>(x_im),
+                                           a_re, a_im, amax, static_cast<int>(g.C), g.Cp,
+                                           static_cast<int>(g.H), static_cast<int>(g.W));
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  conv_wprep_f16_kernel<<<static_cast<unsigned>(g.Op), 256, 0, st>>>(
+      static_cast<const float*>(w_re), static_cast<const float*>(w_im), u, v, isw, static_cast<int>(g.O),
+      g.Op, static_cast<int>(g.C), g.Cp, g.kh * g.kw);
+  CPLXK_CUDA_TRY(cudaGetLastError());
+
+  CUtensorMap tm_xr, tm_xi, tm_u, tm_v;
+  int rc;
+  if ((rc = make_act_map<__half>(&tm_xr, a_re, g))) return rc;
+  if ((rc = make_act_map<__half>(&tm_xi, a_im, g))) return rc;
+  if ((rc = make_w_map<__half>(&tm_u, u, g))) return rc;
+  if ((rc = make_w_map<__half>(&tm_v, v, g))) return rc;
+  ConvTcEpi ep = ep_in;
+  ep.amax = amax, ep.isw = isw;
+  int dev = 0, sms = 148;
+  CPLXK_CUDA_TRY(cudaGetDevice(&dev));
+  CPLXK_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t tiles = g.B * g.tiles_h * g.tiles_w * g.tiles_n;
+  const int64_t items = ((tiles / g.tiles_n + 1) / 2) * g.tiles_n;
+  int64_t clusters = sms / 2;
+  if (clusters > items) clusters = items;
+  auto pk = conv_tc_pair_kernel<float, true>;
+  using PC = ConvPairCfg<float, true>;
+  CPLXK_CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, PC::SMEM_BYTES));
+  pk<<<static_cast<unsigned>(2 * clusters), PC::THREADS, PC::SMEM_BYTES, st>>>(tm_xr, tm_xi, tm_u, tm_v, g, ep,
+                                                                            static_cast<int>(tiles));
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
 }
 
 template <typename T, bool kVD>
@@ -979,6 +1184,15 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
   T* e = kVD ? reinterpret_cast<T*>(wbase + 2 * wgt) : nullptr;
 
   const bool nhwc = ep.nhwc != 0;
+  if constexpr (std::is_same<T, float>::value && !kVD) {
+    // NCHW fp32: the transposing pre-pass exists anyway -- let it write per-image scaled fp16
+    // (CPLXK_CONV_F16=0: tf32 operands as below)
+    const char* f16e = std::getenv("CPLXK_CONV_F16");
+    const char* pr = std::getenv("CPLXK_CONV_PAIR");
+    const int64_t pix_tiles = g.B * g.tiles_h * g.tiles_w;
+    if (!nhwc && !(f16e && f16e[0] == '0') && !(pr && pr[0] == '0') && pix_tiles >= 2)
+      return launch_conv_f16(x_re, x_im, w_re, w_im, workspace, g, ep, st);
+  }
   if (nhwc) {
     // activations already channels-last: TMA reads them in place (rounding to tf32 on load)
     if (g.Cp != g.C || ((reinterpret_cast<uintptr_t>(x_re) | reinterpret_cast<uintptr_t>(x_im)) & 15u))

@@ -335,3 +335,36 @@ def test_real_conv_vd_rejects_nonzero_padding_mode_and_cpu():
     m = Conv2dVD(3, 3, 3)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.randn(1, 3, 5, 5))
+
+
+def test_fp32_nchw_conv_on_scaled_fp16_operands():
+    """fp32 NCHW planes run as per-image / per-output-channel scaled fp16 (conv_tc_pair_kernel
+    <float, half operands>): images and output channels of very different magnitude, zero image,
+    vs the float64 oracle, and against the tf32 path on the same inputs"""
+    import os
+    torch.manual_seed(21)
+    B, C, H, W, O = 6, 24, 20, 36, 40
+    m = CplxConv2d(C, O, 3, padding=1, bias=False).to(DEV)   # no bias: errors are judged per (image, channel) scale
+    z_re, z_im = torch.randn(B, C, H, W, device=DEV), torch.randn(B, C, H, W, device=DEV)
+    img_scale = torch.tensor([1e-6, 1.0, 1e4, 0.0, 3e-3, 7e2], device=DEV).view(B, 1, 1, 1)
+    z_re, z_im = z_re * img_scale, z_im * img_scale
+    with torch.no_grad():
+        ch_scale = torch.logspace(-4, 3, O, device=DEV).view(O, 1, 1, 1)
+        m.weight.real.mul_(ch_scale); m.weight.imag.mul_(ch_scale)
+        out = m(cplx.Cplx(z_re, z_im))
+        os.environ["CPLXK_CONV_F16"] = "0"
+        try:
+            out32 = m(cplx.Cplx(z_re, z_im))
+        finally:
+            os.environ.pop("CPLXK_CONV_F16")
+    c = lambda t: t.detach().double().cpu()
+    want = orc.cplx_conv2d(c(z_re), c(z_im), c(m.weight.real), c(m.weight.imag), None, None, 1, 1, 1)
+    for got, got32, ref in ((out.real, out32.real, want[0]), (out.imag, out32.imag, want[1])):
+        # relative to the scale of each (image, output channel) pair
+        scale = (img_scale.double().cpu().clamp_min(1e-30) * ch_scale.double().cpu().view(1, O, 1, 1))
+        err = ((c(got) - ref).abs() / scale).amax(dim=(2, 3))
+        mag = (ref.abs() / scale).amax(dim=(2, 3)).clamp_min(1e-30)
+        keep = img_scale.view(B).cpu() > 0
+        assert float((err / mag)[keep].max()) < 2e-3
+        assert torch.isfinite(got).all()
+        assert rel_err(got, ref) < TOL["tensor"] and rel_err(got32, ref) < TOL["tensor"]
