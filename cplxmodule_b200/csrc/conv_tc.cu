@@ -270,6 +270,48 @@ conv_nhwc_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ x
   }
 }
 
+// Same with 16-byte loads: 64 channels x 64 pixels per block (W % 4 == 0, 16-byte aligned planes)
+__global__ void __launch_bounds__(256)
+conv_nhwc_f16_v4_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im,
+                        __half* __restrict__ o_re, __half* __restrict__ o_im,
+                        const unsigned int* __restrict__ amax, int C, int Cp, int H, int W) {
+  __shared__ float s_re[64][65], s_im[64][65];
+  const int tid = threadIdx.x;
+  const int w0 = blockIdx.z * 64, c0 = blockIdx.y * 64;
+  const int64_t bh = blockIdx.x;
+  const int64_t b = bh / H, h = bh - b * H;
+  const float scale = pow2f(f16_scale_exp(__uint_as_float(amax[b])));
+  // 64 channel rows x 16 float4: 1024 vector loads per plane, 4 per thread
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + 256 * i;
+    const int cl = idx >> 4, q = idx & 15;
+    const int c = c0 + cl, w = w0 + 4 * q;
+    float4 vr = make_float4(0.f, 0.f, 0.f, 0.f), vi = vr;
+    if (c < C && w < W) {     // W % 4 == 0: a float4 never straddles the row end
+      const int64_t off = ((b * C + c) * H + h) * W + w;
+      vr = __ldg(reinterpret_cast<const float4*>(x_re + off));
+      vi = __ldg(reinterpret_cast<const float4*>(x_im + off));
+    }
+    s_re[cl][4 * q] = vr.x, s_re[cl][4 * q + 1] = vr.y, s_re[cl][4 * q + 2] = vr.z, s_re[cl][4 * q + 3] = vr.w;
+    s_im[cl][4 * q] = vi.x, s_im[cl][4 * q + 1] = vi.y, s_im[cl][4 * q + 2] = vi.z, s_im[cl][4 * q + 3] = vi.w;
+  }
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;
+  const int c = c0 + 2 * tx;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int wl = ty + 8 * i, w = w0 + wl;
+    if (w < W && c < Cp) {
+      const int64_t off = ((b * H + h) * W + w) * Cp + c;
+      *reinterpret_cast<__half2*>(o_re + off) =
+          __floats2half2_rn(s_re[2 * tx][wl] * scale, s_re[2 * tx + 1][wl] * scale);
+      *reinterpret_cast<__half2*>(o_im + off) =
+          __floats2half2_rn(s_im[2 * tx][wl] * scale, s_im[2 * tx + 1][wl] * scale);
+    }
+  }
+}
+
 // weights [O, C, kh, kw] fp32 -> tap-major fp16 planes [(r*kw+s) * Op + o][Cp], one block per
 // output channel: its own power-of-two scale, inverse to isw[o]
 __global__ void __launch_bounds__(256)
@@ -1133,9 +1175,19 @@ static int launch_conv_f16(const void* x_re, const void* x_im, const void* w_re,
   dim3 tg(static_cast<unsigned>(g.B * g.H), static_cast<unsigned>((g.Cp + 63) / 64),
           static_cast<unsigned>((g.W + 31) / 32));
   if (tg.y > 65535u || tg.z > 65535u || g.B * g.H > 0x7fffffff) return CPLXK_ERR_UNSUPPORTED;
-  conv_nhwc_f16_kernel<<<tg, 256, 0, st>>>(static_cast<const float*>(x_re), static_cast<const float*>(x_im),
-                                           a_re, a_im, amax, static_cast<int>(g.C), g.Cp,
-                                           static_cast<int>(g.H), static_cast<int>(g.W));
+  const bool v4 = (g.W % 4 == 0) &&
+                  (((reinterpret_cast<uintptr_t>(x_re) | reinterpret_cast<uintptr_t>(x_im)) & 15u) == 0);
+  if (v4) {
+    tg.z = static_cast<unsigned>((g.W + 63) / 64);
+    conv_nhwc_f16_v4_kernel<<<tg, 256, 0, st>>>(static_cast<const float*>(x_re),
+                                                static_cast<const float*>(x_im), a_re, a_im, amax,
+                                                static_cast<int>(g.C), g.Cp, static_cast<int>(g.H),
+                                                static_cast<int>(g.W));
+  } else {
+    conv_nhwc_f16_kernel<<<tg, 256, 0, st>>>(static_cast<const float*>(x_re), static_cast<const float*>(x_im),
+                                             a_re, a_im, amax, static_cast<int>(g.C), g.Cp,
+                                             static_cast<int>(g.H), static_cast<int>(g.W));
+  }
   CPLXK_CUDA_TRY(cudaGetLastError());
   conv_wprep_f16_kernel<<<static_cast<unsigned>(g.Op), 256, 0, st>>>(
       static_cast<const float*>(w_re), static_cast<const float*>(w_im), u, v, isw, static_cast<int>(g.O),
