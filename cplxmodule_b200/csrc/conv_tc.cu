@@ -77,6 +77,51 @@ conv_nhwc_kernel(const T* __restrict__ x_re, const T* __restrict__ x_im, T* __re
   }
 }
 
+// bf16 NCHW -> channels-last with 16-byte loads (8 pixels per lane) and 128-byte channel rows:
+// 64 channels x 64 pixels per block (W % 8 == 0, 16-byte aligned planes, Cp % 2 == 0)
+__global__ void __launch_bounds__(256)
+conv_nhwc_bf16_v8_kernel(const __nv_bfloat16* __restrict__ x_re, const __nv_bfloat16* __restrict__ x_im,
+                         __nv_bfloat16* __restrict__ o_re, __nv_bfloat16* __restrict__ o_im, int C,
+                         int Cp, int H, int W) {
+  __shared__ __nv_bfloat16 s_re[64][66], s_im[64][66];
+  const int tid = threadIdx.x;
+  const int w0 = blockIdx.z * 64, c0 = blockIdx.y * 64;
+  const int64_t bh = blockIdx.x;
+  const int64_t b = bh / H, h = bh - b * H;
+  // 64 channel rows x 8 uint4 (8 pixels each): 512 vector loads per plane, 2 per thread
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int idx = tid + 256 * i;
+    const int cl = idx >> 3, q = idx & 7;
+    const int c = c0 + cl, w = w0 + 8 * q;
+    uint4 vr = make_uint4(0u, 0u, 0u, 0u), vi = vr;
+    if (c < C && w < W) {
+      const int64_t off = ((b * C + c) * H + h) * W + w;
+      vr = __ldg(reinterpret_cast<const uint4*>(x_re + off));
+      vi = __ldg(reinterpret_cast<const uint4*>(x_im + off));
+    }
+    const __nv_bfloat16* pr = reinterpret_cast<const __nv_bfloat16*>(&vr);
+    const __nv_bfloat16* pi = reinterpret_cast<const __nv_bfloat16*>(&vi);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_re[cl][8 * q + j] = pr[j], s_im[cl][8 * q + j] = pi[j];
+  }
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;
+  const int c = c0 + 2 * tx;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int wl = ty + 8 * i, w = w0 + wl;
+    if (w < W && c < Cp) {
+      const int64_t off = ((b * H + h) * W + w) * Cp + c;
+      __nv_bfloat162 r2, i2;
+      r2.x = s_re[2 * tx][wl], r2.y = s_re[2 * tx + 1][wl];
+      i2.x = s_im[2 * tx][wl], i2.y = s_im[2 * tx + 1][wl];
+      *reinterpret_cast<__nv_bfloat162*>(o_re + off) = r2;
+      *reinterpret_cast<__nv_bfloat162*>(o_im + off) = i2;
+    }
+  }
+}
+
 // weights [O, C, kh, kw] -> tap-major planes [(r*kw+s) * Op + o][Cp]; E = exp(log_sigma2)
 template <typename T, bool kVD>
 __global__ void __launch_bounds__(256)
@@ -1261,9 +1306,22 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
     dim3 tg(static_cast<unsigned>(g.B * g.H), static_cast<unsigned>((g.Cp + 31) / 32),
             static_cast<unsigned>((g.W + 31) / 32));
     if (tg.y > 65535u || tg.z > 65535u || g.B * g.H > 0x7fffffff) return CPLXK_ERR_UNSUPPORTED;
-    conv_nhwc_kernel<T, kVD><<<tg, 256, 0, st>>>(static_cast<const T*>(x_re), static_cast<const T*>(x_im),
-                                                 a_re, a_im, a_q, static_cast<int>(g.C), g.Cp,
-                                                 static_cast<int>(g.H), static_cast<int>(g.W));
+    bool done = false;
+    if constexpr (std::is_same<T, __nv_bfloat16>::value && !kVD) {
+      if (g.W % 8 == 0 && g.Cp % 2 == 0 &&
+          (((reinterpret_cast<uintptr_t>(x_re) | reinterpret_cast<uintptr_t>(x_im)) & 15u) == 0)) {
+        dim3 t8(static_cast<unsigned>(g.B * g.H), static_cast<unsigned>((g.Cp + 63) / 64),
+                static_cast<unsigned>((g.W + 63) / 64));
+        conv_nhwc_bf16_v8_kernel<<<t8, 256, 0, st>>>(static_cast<const T*>(x_re), static_cast<const T*>(x_im),
+                                                     a_re, a_im, static_cast<int>(g.C), g.Cp,
+                                                     static_cast<int>(g.H), static_cast<int>(g.W));
+        done = true;
+      }
+    }
+    if (!done)
+      conv_nhwc_kernel<T, kVD><<<tg, 256, 0, st>>>(static_cast<const T*>(x_re), static_cast<const T*>(x_im),
+                                                   a_re, a_im, a_q, static_cast<int>(g.C), g.Cp,
+                                                   static_cast<int>(g.H), static_cast<int>(g.W));
     CPLXK_CUDA_TRY(cudaGetLastError());
   }
   const int64_t wtotal = static_cast<int64_t>(g.kh) * g.kw * g.Op * g.Cp;
