@@ -196,3 +196,47 @@ def test_masked_layer_mask_semantics_and_state_dict():
     sd["2.mask"] = torch.ones(2, 3)
     net.load_state_dict(sd, strict=False)
     assert net[2].is_sparse
+
+
+def test_fused_kl_cache_bookkeeping_and_shard_requests():
+    """host logic of the pre-pass KL by-product: which rows a forward is asked for under
+    set_kl_shard, and when a cached sum may be handed out (rows, parameter identity, version)"""
+    from cplxmodule_b200 import ops
+    from cplxmodule_b200.distributed import row_shard
+    try:
+        assert ops.kl_request(None, 10) is None
+        assert ops.kl_request(2, 10) == {"kind": 2}
+        for world in (2, 3, 8):
+            covered = []
+            for rank in range(world):
+                ops.set_kl_shard(rank, world)
+                req = ops.kl_request(3, 4099)
+                assert req["rows"] == row_shard(4099, rank, world)
+                covered.append(req["rows"])
+            assert covered[0][0] == 0 and covered[-1][1] == 4099
+            assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+        ops.set_kl_shard(0, 1)                      # a world of one is not sharded
+        assert "rows" not in ops.kl_request(3, 16)
+        ops.set_kl_fusion(False)
+        assert ops.kl_request(3, 16) is None
+    finally:
+        ops.set_kl_shard()
+        ops.set_kl_fusion(True)
+
+    w, ls2 = torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(4, 3))
+    cache = ops.FusedKLCache()
+    cache.put((w, ls2), {"kind": 0})                # the path taken produced nothing
+    assert cache.take((w, ls2)) is None
+    s = torch.tensor(1.5)
+    cache.put((w, ls2), {"kind": 0, "sum": s})
+    assert cache.take((w, ls2)) is s and cache.take((w, ls2)) is None      # handed out once
+    cache.put((w, ls2), {"kind": 0, "sum": s, "rows": (0, 2)})
+    assert cache.take((w, ls2)) is None             # a shard's partial sum is not the layer's
+    cache.put((w, ls2), {"kind": 0, "sum": s, "rows": (0, 2)})
+    assert cache.take((w, ls2), rows=(0, 2)) is s
+    cache.put((w, ls2), {"kind": 0, "sum": s})
+    with torch.no_grad():
+        ls2.add_(1.0)                               # optimiser-style in-place update
+    assert cache.take((w, ls2)) is None
+    cache.put((w, ls2), {"kind": 0, "sum": s})
+    assert cache.take((torch.nn.Parameter(w.detach().clone()), ls2)) is None   # other tensor
