@@ -33,7 +33,8 @@ def _default_partial(mod, lo, hi, stream=None):
     if hi <= lo:
         return torch.zeros((), dtype=torch.float32, device=w_re.device)
     cache = mod.__dict__.get("_kl_cache")
-    if cache is not None:
+    wants_grad = torch.is_grad_enabled() and mod.log_sigma2.requires_grad
+    if cache is not None and not wants_grad:     # the by-product carries no autograd graph
         params = (w_re, mod.log_sigma2) if w_im is None else (w_re, w_im, mod.log_sigma2)
         pre, event = cache.take(params, rows=(lo, hi), with_event=True)
         if pre is not None:
