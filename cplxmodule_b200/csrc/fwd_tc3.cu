@@ -214,7 +214,7 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
       }
     }
   } else {
-    // ------------------------------------ 8 epilogue warps: noise prefetch, then drain + TMA store
+    // ------------------------------------ 8 epilogue warps: noise prefetch, then drain + row stores
     // (little is kept live across noise_prefetch: it needs ~all of the 168 registers)
     uint32_t tile_par = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, tile_par ^= 1u) {
@@ -302,7 +302,7 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
 }
 
 // ------------------------------------------------------------------ fp32 -> fp16 operand pre-pass
-// One block per row of x ([0, M)) or of W ([M, M + N)).  Row maximum -> power-of-two scale that
+// One block per row of x or of W (interleaved).  Row maximum -> power-of-two scale that
 // puts it in [2^13, 2^14) -> fp16 planes; the row's inverse scale goes to isx / isw.  The same
 // pass writes the variance-GEMM operands |x|^2 and exp(log_sigma2) as bf16 (unscaled: bf16 has
 // fp32's range).  K % 8 == 0.
