@@ -70,7 +70,7 @@ def main():
             z = cplx.randn(4096, 4096, device=DEV).to(dt)
             ms_f = timeit(lambda: vd(z), 20)
             ms_k = timeit(lambda: sum(penalties(vd)), 50)
-            out.append(row(f"3 CplxLinearVD 4096->4096 B=4096 fwd ({'fp32/tf32' if es == 4 else 'bf16'})",
+            out.append(row(f"3 CplxLinearVD 4096->4096 B=4096 fwd ({'fp32 planes / scaled fp16 operands' if es == 4 else 'bf16'})",
                            ms_f, 10 * 4096 ** 3, es * 7 * 4096 ** 2, "pre-pass + fused GEMM"))
             out.append(row(f"3 CplxLinearVD KL ({'fp32' if es == 4 else 'bf16'})", ms_k,
                            0, es * 3 * 4096 ** 2, "kl_kernel, HBM bound"))
@@ -80,17 +80,17 @@ def main():
             conv = cls(64, 64, 3).to(DEV).train()
             z = cplx.randn(256, 64, 128, 128, device=DEV)
             flops = nconv * 2 * 256 * 64 * 126 * 126 * 64 * 9
-            for dt, es, tag in ((torch.float32, 4, "fp32/tf32"), (torch.bfloat16, 2, "bf16")):
+            for dt, es, tag in ((torch.float32, 4, "fp32"), (torch.bfloat16, 2, "bf16")):
                 convd, zd = conv.to(dt), z.to(dt)
                 ms = timeit(lambda: convd(zd), 5, 2)
                 nbytes = es * (2 * 256 * 64 * 128 * 128 + 2 * 256 * 64 * 126 * 126)
                 out.append(row(f"4 {name} 64->64 3x3 128x128 B=256 {tag}", ms, flops, nbytes,
-                               "channels-last pre-pass + conv_tc_kernel (tcgen05 implicit GEMM)"))
+                               "NCHW: transposing pre-pass (fp32 planes: per-image scaled fp16 operands) + CTA-pair tcgen05 implicit GEMM"))
                 zcl = cplx.Cplx(zd.real.contiguous(memory_format=torch.channels_last),
                                 zd.imag.contiguous(memory_format=torch.channels_last))
                 ms = timeit(lambda: convd(zcl), 5, 2)
                 out.append(row(f"4 {name} 64->64 3x3 128x128 B=256 {tag} channels_last in/out", ms,
-                               flops, nbytes, "conv_tc_kernel reads NHWC planes in place"))
+                               flops, nbytes, "CTA-pair implicit-GEMM kernel reads NHWC planes in place"))
                 if cls is CplxConv2dVD:
                     cb.set_noise_mode("fast")
                     ms = timeit(lambda: convd(zcl), 5, 2)
@@ -112,7 +112,7 @@ def main():
         w = ard.weight
         ms_k = timeit(lambda: ops.kl(nv.KL_CPLX_ARD, w.real[:1024], w.imag[:1024],
                                      ard.log_sigma2[:1024], "sum"), 50)
-        out.append(row("5 CplxLinearARD 8192->8192, per-GPU shard B=8192 fwd fp32/tf32", ms_f,
+        out.append(row("5 CplxLinearARD 8192->8192, per-GPU shard B=8192 fwd fp32 planes / scaled fp16 operands", ms_f,
                        10 * 8192 ** 3, 4 * 7 * 8192 ** 2, "1/8 of the global batch 65536"))
         out.append(row("5 CplxLinearARD KL row shard (1024 of 8192 rows)", ms_k, 0,
                        4 * 3 * 1024 * 8192, "all-reduce of the scalar not included"))
