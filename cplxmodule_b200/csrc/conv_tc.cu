@@ -1088,24 +1088,6 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
 }
 
 // -------------------------------------------------------------------------- host side
-typedef CUresult (*PFN_encodeTiledC)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiledC conv_encode_fn() {
-  static PFN_encodeTiledC fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<PFN_encodeTiledC>(p);
-  }
-  return fn;
-}
-
 template <typename T>
 static CUtensorMapDataType conv_dt() {
   return std::is_same<T, float>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
@@ -1116,7 +1098,7 @@ static CUtensorMapDataType conv_dt() {
 // channels-last activation plane [B, H, W, Cp]: box {BKC channels, Wt px (stride sw), Ht rows (stride sh), 1}
 template <typename T>
 static int make_act_map(CUtensorMap* out, const void* ptr, const ConvTcGeom& g, bool round_tf32 = false) {
-  auto enc = conv_encode_fn();
+  auto enc = tensor_map_encode_fn();
   if (!enc) return CPLXK_ERR_CUDA;
   const cuuint64_t es = sizeof(T);
   cuuint64_t gdim[4] = {static_cast<cuuint64_t>(g.Cp), static_cast<cuuint64_t>(g.W),
@@ -1138,7 +1120,7 @@ static int make_act_map(CUtensorMap* out, const void* ptr, const ConvTcGeom& g, 
 // tap-major weight plane [khw * Op, Cp]: box {BKC channels, 64 rows}
 template <typename T>
 static int make_w_map(CUtensorMap* out, const void* ptr, const ConvTcGeom& g) {
-  auto enc = conv_encode_fn();
+  auto enc = tensor_map_encode_fn();
   if (!enc) return CPLXK_ERR_CUDA;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(g.Cp),
                         static_cast<cuuint64_t>(g.kh) * g.kw * g.Op};

@@ -341,29 +341,11 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<PFN_encodeTiled>(p);
-  }
-  return fn;
-}
-
 // plane [rows, K] row-major -> box {kSwz bytes of K, 128 rows}
 template <typename T, int kSwz>
 static int make_plane_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K,
                           bool mma_operand = true) {
-  PFN_encodeTiled enc = get_encode_fn();
+  PFN_tensorMapEncodeTiled enc = tensor_map_encode_fn();
   if (!enc) return CPLXK_ERR_CUDA;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(K) * sizeof(T)};

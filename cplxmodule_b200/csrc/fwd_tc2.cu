@@ -252,29 +252,11 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------ host side
-typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled2 encode_fn2() {
-  static PFN_encodeTiled2 fn = nullptr;
-  if (!fn) {
-    void* q = nullptr;
-    cudaDriverEntryPointQueryResult r;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) != cudaSuccess ||
-        r != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<PFN_encodeTiled2>(q);
-  }
-  return fn;
-}
-
 // plane [rows, K] row-major of T -> box {box_k elements of K, box_rows}, swizzle = box bytes
 template <typename T>
 static int plane_map2(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K, int box_rows,
                       bool round_tf32, int box_k = 128 / static_cast<int>(sizeof(T))) {
-  auto enc = encode_fn2();
+  auto enc = tensor_map_encode_fn();
   if (!enc) return CPLXK_ERR_CUDA;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(K) * sizeof(T)};
@@ -293,7 +275,7 @@ static int plane_map2(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K
 
 // fp16 planes written by the pre-pass: box {64 elements of K, rows}, 128B swizzle
 static int half_map2(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K, int box_rows) {
-  auto enc = encode_fn2();
+  auto enc = tensor_map_encode_fn();
   if (!enc) return CPLXK_ERR_CUDA;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(K) * 2};

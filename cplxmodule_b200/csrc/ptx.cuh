@@ -9,6 +9,26 @@
 #include <stdint.h>
 
 namespace cplxk {
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time);
+// one lookup per process, shared by every tensor-core kernel's host side.
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                             const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline PFN_tensorMapEncodeTiled tensor_map_encode_fn() {
+  static PFN_tensorMapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult r;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) != cudaSuccess ||
+        r != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_tensorMapEncodeTiled>(q);
+  }
+  return fn;
+}
+
 namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -93,11 +93,6 @@ __device__ __forceinline__ void store_run64(T* dst, const float (&v)[64], int nv
   }
 }
 
-typedef CUresult (*PFN_encodeTiled3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 // sixteen consecutive outputs of one row (16-column drain chunk of fwd_lin3.cu); `full`: all
 // sixteen are inside the row and dst is 32-byte (fp32) / 32-byte (bf16) aligned
 template <typename T>
@@ -125,23 +120,10 @@ __device__ __forceinline__ void store_run16(T* dst, const float (&v)[16], bool f
   }
 }
 
-static inline PFN_encodeTiled3 encode_fn3() {
-  static PFN_encodeTiled3 fn = nullptr;
-  if (!fn) {
-    void* q = nullptr;
-    cudaDriverEntryPointQueryResult r;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) != cudaSuccess ||
-        r != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<PFN_encodeTiled3>(q);
-  }
-  return fn;
-}
-
 // plane [rows, cols] row-major, element size es -> box {box_c, box_r}; swizzle = box_c * es bytes
 static inline int map2d(CUtensorMap* out, CUtensorMapDataType dt, size_t es, const void* ptr, int64_t rows,
                  int64_t cols, int box_c, int box_r) {
-  auto enc = encode_fn3();
+  auto enc = tensor_map_encode_fn();
   if (!enc) return CPLXK_ERR_CUDA;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(cols) * es};
