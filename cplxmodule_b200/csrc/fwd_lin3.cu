@@ -72,14 +72,7 @@ lin_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
   const int num_kb = static_cast<int>((p.K + C::BK - 1) / C::BK);
 
   auto decode_tile = [&](int t, int& tile_m, int& tile_n) {
-    constexpr int kGroup = 6;
-    const int per_group = kGroup * p.tiles_n;
-    const int g = t / per_group;
-    const int first_m = g * kGroup;
-    const int gsize = (p.tiles_m2 - first_m) < kGroup ? (p.tiles_m2 - first_m) : kGroup;
-    const int r = t - g * per_group;
-    tile_m = first_m + r % gsize;
-    tile_n = r / gsize;
+    raster_tile(t, p.tiles_m2, p.tiles_n, 6, tile_m, tile_n);
   };
 
   if (warp == 0 && lane == 0) {

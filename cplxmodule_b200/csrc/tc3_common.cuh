@@ -48,6 +48,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Grouped raster of the persistent kernels: tiles of 256 rows x 128 columns, `group` row tiles
+// are walked against all column tiles before the next group (a wave of 74 tile pairs then
+// covers about 6 x 12 tiles: the smallest operand footprint per wave).
+__device__ __forceinline__ void raster_tile(int t, int tiles_m2, int tiles_n, int group, int& tile_m,
+                                            int& tile_n) {
+  const int per_group = group * tiles_n;
+  const int g = t / per_group;
+  const int first_m = g * group;
+  const int gsize = (tiles_m2 - first_m) < group ? (tiles_m2 - first_m) : group;
+  const int r = t - g * per_group;
+  tile_m = first_m + r % gsize;
+  tile_n = r / gsize;
+}
+
 // 64 consecutive outputs of one row: 32-byte (fp32: st.global.v8, one full sector per lane) or
 // 16-byte vector stores when the row segment allows
 template <typename T>
