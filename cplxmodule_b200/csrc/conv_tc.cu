@@ -155,6 +155,24 @@ __device__ __forceinline__ int64_t conv_y_offset(const ConvTcGeom& g, bool nhwc,
   return nhwc ? ((b * g.Ho + oh) * g.Wo + ow) * g.O + o : ((b * g.O + o) * g.Ho + oh) * g.Wo + ow;
 }
 
+// kN consecutive output channels of one pixel in an NCHW plane: `q` points at the first channel,
+// planes are `hw` elements apart, `left` channels remain before O.  The address is ONE pointer
+// walked by the plane stride and the channel bound is tested once per run: the per-store 64-bit
+// multiply + 64-bit compare + branch this replaces cost 18 instructions per store (ncu:
+// profiles/prof_convpair_r1) and made the epilogue, not the MMAs, the critical path.
+template <typename T, int kN>
+__device__ __forceinline__ void conv_store_nchw(T* __restrict__ q, int64_t hw, int left,
+                                                const float (&v)[kN]) {
+  if (left >= kN) {
+#pragma unroll
+    for (int j = 0; j < kN; ++j, q += hw) *q = Elem<T>::from_f(v[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kN; ++j, q += hw)
+      if (j < left) *q = Elem<T>::from_f(v[j]);
+  }
+}
+
 // Eight consecutive output channels of one pixel.  NCHW: one scalar store per channel (the 32
 // lanes of a warp hold 32 consecutive pixels, so each store instruction is one 128 B line).
 // NHWC: the eight values are contiguous, written as one 32 B (fp32) / 16 B (bf16) vector.
@@ -163,9 +181,7 @@ __device__ __forceinline__ void conv_store8(T* __restrict__ y, const ConvTcGeom&
                                             int64_t nchw_off, int64_t hw, int64_t nhwc_off, int o0,
                                             const float (&v)[8]) {
   if (!nhwc) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (o0 + j < g.O) y[nchw_off + static_cast<int64_t>(o0 + j) * hw] = Elem<T>::from_f(v[j]);
+    conv_store_nchw<T, 8>(y + nchw_off + static_cast<int64_t>(o0) * hw, hw, static_cast<int>(g.O) - o0, v);
     return;
   }
   T* dst = y + nhwc_off + o0;
@@ -207,6 +223,10 @@ __device__ __forceinline__ void conv_store16(T* __restrict__ y, const ConvTcGeom
                    : "memory");
       return;
     }
+  }
+  if (!nhwc) {
+    conv_store_nchw<T, 16>(y + nchw_off + static_cast<int64_t>(o0) * hw, hw, static_cast<int>(g.O) - o0, v);
+    return;
   }
   float lo[8], hi[8];
 #pragma unroll
