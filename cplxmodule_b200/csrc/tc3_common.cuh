@@ -17,9 +17,14 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Arrive on an mbarrier of another CTA of the cluster.  Used to hand TMEM accumulators back to the
+// MMA issuer: the tcgen05.ld's are complete (tcgen05.wait::ld) and fenced (tcgen05.fence::
+// before_thread_sync) when it is called, and no ordinary memory is published through it, so the
+// arrive carries no .release.cluster -- that form compiles to MEMBAR.ALL.GPU + ERRBAR and made
+// every epilogue warp wait for its outstanding global stores once per tile (ncu, conv pair kernel:
+// 20 % of all stall samples).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
