@@ -14,14 +14,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CPLXK_LIB") or os.path.join(_HERE, "csrc", "libcplxk.so")  # CPLXK_LIB: A/B builds
 
 F32, BF16 = 0, 1
-MATH_AUTO, MATH_TENSOR, MATH_SIMT = 0, 1, 2
+MATH_AUTO, MATH_TENSOR, MATH_SIMT, MATH_TENSOR_TF32 = 0, 1, 2, 3
 NOISE_INJECT, NOISE_PHILOX_TORCH, NOISE_PHILOX_FAST = 0, 1, 2
 ERR_UNSUPPORTED = -5
 KL_REAL_VD, KL_REAL_ARD, KL_CPLX_VD, KL_CPLX_ARD = 0, 1, 2, 3
 KL_CPLX_VD_APPROX, KL_CPLX_VD_SCALEFREE = 4, 5        # nn/relevance/extensions/complex.py
 
 EXPORTS = (
-    "cplxk_abi_version", "cplxk_strerror", "cplxk_device_info", "cplxk_linear_fwd",
+    "cplxk_abi_version", "cplxk_strerror", "cplxk_device_info", "cplxk_set_sm_reserve", "cplxk_linear_fwd",
+    "cplxk_linear_vd_prepare",
     "cplxk_linear_fwd_ws", "cplxk_linear_workspace_bytes",
     "cplxk_linear_vd_fwd", "cplxk_linear_vd_fwd_kl", "cplxk_linear_vd_workspace_bytes", "cplxk_kl_workspace_bytes", "cplxk_kl", "cplxk_log_alpha",
     "cplxk_conv2d_fwd", "cplxk_conv2d_workspace_bytes", "cplxk_randn_philox_torch",
@@ -51,6 +52,9 @@ def _declare(lib):
                                            + [_i64] * 3 + [_int, _int, _vp, _vp, ctypes.c_size_t]
                                            + [_int, _vp, _vp, ctypes.c_size_t, _i64, _i64, _vp,
                                               ctypes.POINTER(_int), _vp])
+    lib.cplxk_set_sm_reserve.argtypes = [_int]
+    lib.cplxk_linear_vd_prepare.argtypes = ([_vp] * 5 + [_i64] * 3 + [_int, _vp, ctypes.c_size_t, _int, _vp, _vp,
+                                            ctypes.c_size_t, _vp])
     lib.cplxk_linear_vd_workspace_bytes.restype = ctypes.c_size_t
     lib.cplxk_linear_vd_workspace_bytes.argtypes = [_i64, _i64, _i64, _int]
     lib.cplxk_kl_workspace_bytes.restype = ctypes.c_size_t

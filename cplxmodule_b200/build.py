@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libcplxk.so")
 OBJ = os.path.join(CSRC, "_obj")
-SOURCES = ["api.cu", "kl.cu", "fwd_simt.cu", "fwd_tc.cu", "fwd_tc2.cu", "fwd_tc3.cu", "fwd_lin3.cu", "conv.cu", "conv_tc.cu", "bwd.cu"]
+SOURCES = ["api.cu", "kl.cu", "fwd_simt.cu", "fwd_tc.cu", "fwd_tc3.cu", "fwd_lin3.cu", "conv.cu", "conv_tc.cu", "bwd.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -28,6 +28,7 @@ def nvcc_path():
 
 def _fingerprint():
     h = hashlib.sha256()
+    h.update(os.environ.get("CPLXK_DEBUG_BUILD", "0").encode())
     names = sorted(os.listdir(CSRC)) + ["../../include/cplxk.h"]
     for name in names:
         path = os.path.join(CSRC, name)
@@ -50,6 +51,8 @@ def build(force=False, verbose=False):
     nvcc = nvcc_path()
     flags = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
                     "--expt-relaxed-constexpr", "-I", os.path.join(HERE, "..", "include")]
+    if os.environ.get("CPLXK_DEBUG_BUILD") == "1":   # measurement aids (CPLXK_DBG); never shipped
+        flags += ["-DCPLXK_DEBUG"]
     if verbose:
         flags += ["-Xptxas", "-v"]
 

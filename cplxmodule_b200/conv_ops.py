@@ -191,8 +191,7 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
     Wo = (W + 2 * padding[1] - dilation[1] * (kw - 1) - 1) // stride[1] + 1
     if Ho <= 0 or Wo <= 0:
         raise RuntimeError("kernel size can't be greater than actual input size")
-    math = nv.MATH_SIMT if ops.get_math_mode() == "simt" else (
-        nv.MATH_TENSOR if ops.get_math_mode() == "tensor" else nv.MATH_AUTO)
+    math = ops._MATH[ops.get_math_mode()]
     # torch.channels_last activations (NCHW shape, NHWC strides) are consumed in place by the
     # tensor-core path and the output keeps that memory format, as F.conv2d would
     gran = 8 if dt == torch.float32 else 16

@@ -1,10 +1,12 @@
 // C-ABI entry points (include/cplxk.h): argument validation, path selection,
 // error reporting.  No torch types, no allocation, asynchronous on `stream`.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
 #include "epilogue.cuh"
+#include "knobs.cuh"
 
 namespace cplxk {
 
@@ -16,11 +18,11 @@ int fwd_simt_dispatch(int dtype, bool cplx, bool vd, const void* x_re, const voi
                       int64_t K, const EpiParams& ep, cudaStream_t st);
 bool fwd_tc_supported(int dtype, bool cplx, const void* x_re, const void* x_im, const void* w_re,
                       const void* w_im, const void* ls2, int64_t M, int64_t N, int64_t K);
-int fwd_tc_dispatch(int dtype, bool cplx, bool vd, int swz, const void* x_re, const void* x_im,
-                    const void* w_re, const void* w_im, const void* ls2, void* workspace,
-                    int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st,
-                    const KlFuse& kl);
-bool fwd_tc_fuses_kl(int dtype, int64_t M, int64_t N, int64_t K);
+int fwd_tc_dispatch(int dtype, bool cplx, bool vd, int swz, bool f16_ok, const void* x_re,
+                    const void* x_im, const void* w_re, const void* w_im, const void* ls2,
+                    void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
+                    cudaStream_t st, const KlFuse& kl);
+bool fwd_tc_fuses_kl(int dtype, bool f16_ok, int64_t M, int64_t N, int64_t K);
 // persistent double-buffered affine map on 16-bit operands (fwd_lin3.cu)
 size_t fwd_lin3_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K);
 bool fwd_lin3_supported(int64_t M, int64_t N, int64_t K);
@@ -30,24 +32,77 @@ int fwd_lin3_bf16(bool cplx, const void* x_re, const void* x_im, const void* w_r
                   int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st);
 size_t fwd_tc_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K);
 
+// ---- process-level switches: the environment is read once, on first use
+static int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e && e[0] ? std::atoi(e) : dflt;
+}
+
+const Knobs& knobs() {
+  static const Knobs k = [] {
+    Knobs v;
+    const int swz = env_int("CPLXK_TC_SWIZZLE", 0);
+    v.tc_swizzle = (swz == 64 || swz == 128) ? swz : 0;
+    v.raster = env_int("CPLXK_RASTER", 6);
+    if (v.raster < 1) v.raster = 6;
+    v.lin3 = env_int("CPLXK_LIN3", 1) != 0;
+    v.tma_raw_f32 = env_int("CPLXK_TMA_RAW_F32", 0) == 1;
+    v.conv_pair = env_int("CPLXK_CONV_PAIR", 1) != 0;
+    v.conv_persistent = env_int("CPLXK_CONV_NONPERSISTENT", 0) != 1;
+    v.pdl = env_int("CPLXK_PDL", 1) != 0;
+#ifdef CPLXK_DEBUG
+    v.dbg = env_int("CPLXK_DBG", 0);
+#else
+    v.dbg = 0;
+#endif
+    return v;
+  }();
+  return k;
+}
+
+static std::atomic<int> g_sm_reserve{-1};
+int sm_reserve() {
+  int v = g_sm_reserve.load(std::memory_order_relaxed);
+  if (v < 0) {
+    v = env_int("CPLXK_SM_RESERVE", 0);
+    if (v < 0) v = 0;
+    g_sm_reserve.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+// ---- per-device facts (a process may drive several GPUs: nothing is cached per process)
+static constexpr int kMaxDevices = 64;
+static std::atomic<int> g_sm_count[kMaxDevices];   // 0: unknown
+static std::atomic<int> g_cc_major[kMaxDevices];   // 0: unknown
+
+int current_device_sm_count(int* sms) {
+  int dev = 0;
+  CPLXK_CUDA_TRY(cudaGetDevice(&dev));
+  int v = (dev >= 0 && dev < kMaxDevices) ? g_sm_count[dev].load(std::memory_order_relaxed) : 0;
+  if (!v) {
+    CPLXK_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < kMaxDevices) g_sm_count[dev].store(v, std::memory_order_relaxed);
+  }
+  *sms = v;
+  return CPLXK_OK;
+}
+
 static int check_arch() {
-  static int ok = -1;  // per process; one process per GPU
-  if (ok < 0) {
-    int dev = 0, major = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_last_cuda_error(cudaGetLastError());
+    return CPLXK_ERR_CUDA;
+  }
+  int major = (dev >= 0 && dev < kMaxDevices) ? g_cc_major[dev].load(std::memory_order_relaxed) : 0;
+  if (!major) {
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
       set_last_cuda_error(cudaGetLastError());
       return CPLXK_ERR_CUDA;
     }
-    ok = (major == 10) ? 1 : 0;
+    if (dev >= 0 && dev < kMaxDevices) g_cc_major[dev].store(major, std::memory_order_relaxed);
   }
-  return ok ? CPLXK_OK : CPLXK_ERR_ARCH;
-}
-
-static int env_swizzle() {  // tuning knob, read per call (cheap) so one process can sweep it
-  const char* e = std::getenv("CPLXK_TC_SWIZZLE");
-  int v = e ? std::atoi(e) : 0;
-  return (v == 64 || v == 128) ? v : 0;
+  return major == 10 ? CPLXK_OK : CPLXK_ERR_ARCH;
 }
 
 static NoiseParams make_noise(int mode, uint64_t seed, uint64_t offset, uint32_t threads, bool cplx) {
@@ -75,7 +130,7 @@ static int forward_common(bool vd, const void* x_re, const void* x_im, const voi
   if (cplx != (w_im != nullptr) || cplx != (y_im != nullptr)) return CPLXK_ERR_BADARG;
   if ((b_re != nullptr) && cplx && !b_im) return CPLXK_ERR_BADARG;
   if (dtype != CPLXK_F32 && dtype != CPLXK_BF16) return CPLXK_ERR_BADARG;
-  if (math < CPLXK_MATH_AUTO || math > CPLXK_MATH_SIMT) return CPLXK_ERR_BADARG;
+  if (math < CPLXK_MATH_AUTO || math > CPLXK_MATH_TENSOR_TF32) return CPLXK_ERR_BADARG;
   if (vd) {
     if (!ls2) return CPLXK_ERR_BADARG;
     if (noise < CPLXK_NOISE_INJECT || noise > CPLXK_NOISE_PHILOX_FAST) return CPLXK_ERR_BADARG;
@@ -95,8 +150,10 @@ static int forward_common(bool vd, const void* x_re, const void* x_im, const voi
   auto st = static_cast<cudaStream_t>(stream);
   const bool tc_ok = fwd_tc_supported(dtype, cplx, x_re, x_im, w_re, w_im, vd ? ls2 : nullptr, M, N, K);
   if (math == CPLXK_MATH_TENSOR && !tc_ok) return CPLXK_ERR_ALIGN;
+  // F32 planes: per-row scaled fp16 operands unless the caller asked for tf32 ones
+  const bool f16_ok = math != CPLXK_MATH_TENSOR_TF32;
   if (math != CPLXK_MATH_SIMT && tc_ok) {
-    int swz = env_swizzle();
+    int swz = knobs().tc_swizzle;
     if (!swz) swz = (cplx && vd) ? 64 : 128;
     if (workspace) {
       if (!aligned16(workspace)) return CPLXK_ERR_ALIGN;
@@ -105,17 +162,15 @@ static int forward_common(bool vd, const void* x_re, const void* x_im, const voi
     }
     if (!vd && fwd_lin3_supported(M, N, K)) {
       // plain affine map: persistent CTA-pair kernel with double-buffered accumulators; fp32 planes
-      // need the workspace for their row-scaled fp16 copies (CPLXK_F16=0 / no workspace: tf32 below)
-      const char* f16e = std::getenv("CPLXK_F16");
-      const char* l3 = std::getenv("CPLXK_LIN3");
-      if (dtype == CPLXK_F32 && workspace && K >= 64 && !(f16e && f16e[0] == '0'))
+      // need the workspace for their row-scaled fp16 copies (MATH_TENSOR_TF32 / no workspace: tf32 below)
+      if (dtype == CPLXK_F32 && workspace && K >= 64 && f16_ok)
         return fwd_lin3_f32(cplx, x_re, x_im, w_re, w_im, workspace, M, N, K, ep, st);
-      if (dtype == CPLXK_BF16 && !(l3 && l3[0] == '0'))   // CPLXK_LIN3=0: one tile per CTA (fwd_tc.cu)
+      if (dtype == CPLXK_BF16 && knobs().lin3)   // CPLXK_LIN3=0: one tile per CTA (fwd_tc.cu)
         return fwd_lin3_bf16(cplx, x_re, x_im, w_re, w_im, M, N, K, ep, st);
     }
-    const bool fuse = vd && workspace && kl.kind >= 0 && kl.sum && kl.ws && fwd_tc_fuses_kl(dtype, M, N, K);
+    const bool fuse = vd && workspace && kl.kind >= 0 && kl.sum && kl.ws && fwd_tc_fuses_kl(dtype, f16_ok, M, N, K);
     if (!fuse) kl.kind = -1;
-    rc = fwd_tc_dispatch(dtype, cplx, vd, swz, x_re, x_im, w_re, w_im, ls2, vd ? workspace : nullptr,
+    rc = fwd_tc_dispatch(dtype, cplx, vd, swz, f16_ok, x_re, x_im, w_re, w_im, ls2, vd ? workspace : nullptr,
                          M, N, K, ep, st, kl);
     if (rc == CPLXK_OK && fuse && kl_done) *kl_done = 1;
     return rc;
@@ -153,6 +208,12 @@ extern "C" const char* cplxk_strerror(int status) {
     case CPLXK_ERR_WORKSPACE: return "cplxk: workspace missing or too small";
   }
   return "cplxk: unknown status";
+}
+
+extern "C" int cplxk_set_sm_reserve(int n_sms) {
+  if (n_sms < 0) return CPLXK_ERR_BADARG;
+  g_sm_reserve.store(n_sms, std::memory_order_relaxed);
+  return CPLXK_OK;
 }
 
 extern "C" int cplxk_device_info(int* sm_count, int* cc_major, int* cc_minor) {
@@ -223,6 +284,43 @@ extern "C" int cplxk_linear_vd_fwd_kl(const void* x_re, const void* x_im, const 
   return forward_common(true, x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise,
                         seed, offset, philox_threads, y_re, y_im, M, N, K, dtype, math, s2_out,
                         workspace, workspace_bytes, stream, kl, kl_done);
+}
+
+// operand pre-pass of the fp32-plane tensor-core path on its own (no GEMM launch)
+namespace cplxk {
+bool fwd_tc3_supported(int dtype, int64_t M, int64_t N, int64_t K);
+int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
+                const void* ls2, void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
+                cudaStream_t st, const KlFuse& kl);
+}  // namespace cplxk
+
+extern "C" int cplxk_linear_vd_prepare(const void* x_re, const void* x_im, const void* w_re,
+                                       const void* w_im, const void* log_sigma2, int64_t M,
+                                       int64_t N, int64_t K, int dtype, void* workspace,
+                                       size_t workspace_bytes, int kl_kind, float* kl_sum,
+                                       void* kl_workspace, size_t kl_workspace_bytes, void* stream) {
+  if (!x_re || !w_re || !log_sigma2 || !workspace || M < 0 || N < 0 || K < 0) return CPLXK_ERR_BADARG;
+  const bool cplx = x_im != nullptr;
+  if (cplx != (w_im != nullptr)) return CPLXK_ERR_BADARG;
+  int rc = check_arch();
+  if (rc) return rc;
+  if (dtype != CPLXK_F32 || K < 64 || !fwd_tc3_supported(dtype, M, N, K) ||
+      !fwd_tc_supported(dtype, cplx, x_re, x_im, w_re, w_im, log_sigma2, M, N, K))
+    return CPLXK_ERR_UNSUPPORTED;
+  if (!aligned16(workspace)) return CPLXK_ERR_ALIGN;
+  if (workspace_bytes < fwd_tc_workspace_bytes(dtype, M, N, K)) return CPLXK_ERR_WORKSPACE;
+  KlFuse kl{-1, nullptr, nullptr, 0, -1, nullptr};
+  if (kl_kind >= 0) {
+    const bool cplx_kind = kl_kind >= CPLXK_KL_CPLX_VD;
+    if (kl_kind > CPLXK_KL_CPLX_VD_SCALEFREE || cplx_kind != cplx || !kl_sum) return CPLXK_ERR_BADARG;
+    if (!kl_workspace || kl_workspace_bytes < cplxk_kl_workspace_bytes()) return CPLXK_ERR_WORKSPACE;
+    if (!aligned16(kl_workspace)) return CPLXK_ERR_ALIGN;
+    kl = KlFuse{kl_kind, kl_sum, kl_workspace, 0, -1, nullptr};
+  }
+  EpiParams ep{};          // y_re == nullptr: stop after the pre-pass
+  ep.M = M, ep.N = N;
+  return fwd_tc3_f32(cplx, x_re, x_im, w_re, w_im, log_sigma2, workspace, M, N, K, ep,
+                     static_cast<cudaStream_t>(stream), kl);
 }
 
 extern "C" size_t cplxk_linear_vd_workspace_bytes(int64_t M, int64_t N, int64_t K, int dtype) {

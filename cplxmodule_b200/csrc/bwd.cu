@@ -10,6 +10,7 @@
 // kernels here produce the transposed / derived operand planes, plus the small elementwise
 // pieces and the closed-form KL gradients (complex/vd.py:38-41: dEi(x)/dx = e^x / x).
 #include "common.cuh"
+#include "knobs.cuh"
 #include "noise.cuh"
 
 namespace cplxk {
@@ -212,8 +213,10 @@ eltwise_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__
 }
 
 static inline int ew_grid(int64_t n) {
-  int64_t b = (n + 255) / 256;
-  return static_cast<int>(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
+  int sms = 148;
+  if (current_device_sm_count(&sms) != CPLXK_OK || sms < 1) sms = 148;
+  const int64_t b = (n + 255) / 256, cap = static_cast<int64_t>(sms) * 16;
+  return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
 }  // namespace cplxk

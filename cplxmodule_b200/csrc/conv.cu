@@ -254,6 +254,7 @@ extern "C" int cplxk_conv2d_fwd(const void* x_re, const void* x_im, const void* 
   const bool tc_ok = cplx && workspace != nullptr && aligned16(workspace) && aligned16(x_re) &&
                      conv_tc_supported(dtype, B, C, H, W, O, g.Ho, g.Wo, g.kh, g.kw, g.sh, g.sw) &&
                      workspace_bytes >= conv_tc_workspace_bytes(dtype, vd, B, C, H, W, O, kh, kw);
+  if (math < CPLXK_MATH_AUTO || math > CPLXK_MATH_TENSOR_TF32) return CPLXK_ERR_BADARG;
   if (math == CPLXK_MATH_TENSOR && !tc_ok) return workspace ? CPLXK_ERR_UNSUPPORTED : CPLXK_ERR_WORKSPACE;
   if (channels_last && !(tc_ok && math != CPLXK_MATH_SIMT)) return CPLXK_ERR_UNSUPPORTED;  // NHWC: TC path only
   if (math != CPLXK_MATH_SIMT && tc_ok) {
@@ -261,6 +262,7 @@ extern "C" int cplxk_conv2d_fwd(const void* x_re, const void* x_im, const void* 
     te.b_re = b_re, te.b_im = b_im, te.eps_re = eps_re, te.eps_im = eps_im;
     te.y_re = y_re, te.y_im = y_im, te.plane_elems = ep.plane_elems, te.noise = ep.noise;
     te.nhwc = channels_last ? 1 : 0;
+    te.f16_ok = math != CPLXK_MATH_TENSOR_TF32;
     return conv_tc_dispatch(dtype, vd, channels_last != 0, x_re, x_im, w_re, w_im, log_sigma2, workspace, B, C, H, W, O,
                             g.Ho, g.Wo, g.kh, g.kw, g.sh, g.sw, g.ph, g.pw, g.dh, g.dw, te, st);
   }

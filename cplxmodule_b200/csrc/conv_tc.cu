@@ -21,6 +21,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "knobs.cuh"
 #include "noise.cuh"
 #include "ptx.cuh"
 #include "conv_tc.cuh"
@@ -1249,9 +1250,8 @@ static int launch_conv_f16(const void* x_re, const void* x_im, const void* w_re,
   if ((rc = make_w_map<__half>(&tm_v, v, g))) return rc;
   ConvTcEpi ep = ep_in;
   ep.amax = amax, ep.isw = isw;
-  int dev = 0, sms = 148;
-  CPLXK_CUDA_TRY(cudaGetDevice(&dev));
-  CPLXK_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int sms = 148;
+  if ((rc = current_device_sm_count(&sms))) return rc;
   const int64_t tiles = g.B * g.tiles_h * g.tiles_w * g.tiles_n;
   const int64_t items = ((tiles / g.tiles_n + 1) / 2) * g.tiles_n;
   int64_t clusters = sms / 2;
@@ -1285,11 +1285,9 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
   const bool nhwc = ep.nhwc != 0;
   if constexpr (std::is_same<T, float>::value && !kVD) {
     // NCHW fp32: the transposing pre-pass exists anyway -- let it write per-image scaled fp16
-    // (CPLXK_CONV_F16=0: tf32 operands as below)
-    const char* f16e = std::getenv("CPLXK_CONV_F16");
-    const char* pr = std::getenv("CPLXK_CONV_PAIR");
+    // (MATH_TENSOR_TF32: tf32 operands as below)
     const int64_t pix_tiles = g.B * g.tiles_h * g.tiles_w;
-    if (!nhwc && !(f16e && f16e[0] == '0') && !(pr && pr[0] == '0') && pix_tiles >= 2)
+    if (!nhwc && ep.f16_ok && knobs().conv_pair && pix_tiles >= 2)
       return launch_conv_f16(x_re, x_im, w_re, w_im, workspace, g, ep, st);
   }
   if (nhwc) {
@@ -1300,7 +1298,10 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
     a_im = const_cast<T*>(static_cast<const T*>(x_im));
     if (kVD) {
       const int64_t n = g.B * g.H * g.W * g.C;
-      conv_abs2_kernel<T><<<static_cast<unsigned>(n / (256 * Elem<T>::kVec) + 1 > 148 * 16 ? 148 * 16 : n / (256 * Elem<T>::kVec) + 1), 256, 0, st>>>(
+      int sms_q = 148;
+      if (current_device_sm_count(&sms_q) != CPLXK_OK) sms_q = 148;
+      const int64_t want_q = n / (256 * Elem<T>::kVec) + 1;
+      conv_abs2_kernel<T><<<static_cast<unsigned>(want_q > sms_q * 16 ? sms_q * 16 : want_q), 256, 0, st>>>(
           a_re, a_im, a_q, n);
       CPLXK_CUDA_TRY(cudaGetLastError());
     }
@@ -1345,13 +1346,10 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
   }
   const int64_t tiles = g.B * g.tiles_h * g.tiles_w * g.tiles_n;
   if constexpr (!kVD) {
-    const char* np = std::getenv("CPLXK_CONV_NONPERSISTENT");
-    if (!(np && np[0] == '1')) {
-      int dev = 0, sms = 148;
-      CPLXK_CUDA_TRY(cudaGetDevice(&dev));
-      CPLXK_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      const char* pr = std::getenv("CPLXK_CONV_PAIR");
-      if (!(pr && pr[0] == '0') && tiles / g.tiles_n >= 2) {
+    if (knobs().conv_persistent) {
+      int sms = 148;
+      if ((rc = current_device_sm_count(&sms))) return rc;
+      if (knobs().conv_pair && tiles / g.tiles_n >= 2) {
         auto pk2 = conv_tc_pair_kernel<T>;
         CPLXK_CUDA_TRY(cudaFuncSetAttribute(pk2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             ConvPairCfg<T>::SMEM_BYTES));

@@ -21,6 +21,7 @@ struct ConvTcEpi {
   void* y_re;
   void* y_im;
   int64_t plane_elems;
+  int f16_ok = 1;        // 0: MATH_TENSOR_TF32 -- fp32 planes keep tf32 operands
   int nhwc;              // 1: x / y planes are channels-last (torch.channels_last): no transposing pre-pass
   // fp32 planes on fp16 operands (conv_tc_pair_kernel<float, true>): per-image maxima of |x|
   // (float bits, written by conv_amax_kernel) and inverse per-output-channel scales of W

@@ -14,6 +14,7 @@
 #include <type_traits>
 
 #include "epilogue.cuh"
+#include "knobs.cuh"
 #include "ptx.cuh"
 #include "tc3_common.cuh"
 
@@ -274,14 +275,9 @@ static int launch_lin3(const Lin3Operands& o, int64_t M, int64_t N, int64_t K, c
   p.b_re = ep.b_re, p.b_im = ep.b_im, p.y_re = ep.y_re, p.y_im = ep.y_im;
   const int64_t pairs = static_cast<int64_t>(p.tiles_m2) * p.tiles_n;
   if (pairs > 0x3fffffff) return CPLXK_ERR_UNSUPPORTED;
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    CPLXK_CUDA_TRY(cudaGetDevice(&dev));
-    CPLXK_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
-  const char* rsv = std::getenv("CPLXK_SM_RESERVE");
-  int64_t clusters = (sm_count - (rsv ? std::atoi(rsv) : 0)) / 2;
+  int sm_count = 0;
+  if ((rc = current_device_sm_count(&sm_count))) return rc;
+  int64_t clusters = (sm_count - sm_reserve()) / 2;
   if (clusters < 1) clusters = 1;
   if (clusters > pairs) clusters = pairs;
   auto kern = lin_tc3_kernel<OutT, kCplx>;

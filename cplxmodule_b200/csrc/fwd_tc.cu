@@ -18,6 +18,7 @@
 #include <type_traits>
 
 #include "epilogue.cuh"
+#include "knobs.cuh"
 #include "ptx.cuh"
 
 namespace cplxk {
@@ -354,8 +355,7 @@ static int make_plane_map(CUtensorMap* out, const void* ptr, int64_t rows, int64
   // fp32 planes feed kind::tf32 MMAs: the TFLOAT32 tensor-map type makes TMA deliver tf32
   // values (round-to-nearest) instead of leaving the truncation to the tensor core, which
   // would bias every product by about -2^-10 relative.
-  const char* raw_env = std::getenv("CPLXK_TMA_RAW_F32");
-  const bool raw_f32 = raw_env && raw_env[0] == '1';
+  const bool raw_f32 = knobs().tma_raw_f32;
   CUtensorMapDataType dt = std::is_same<T, float>::value
                                ? ((raw_f32 || !mma_operand) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                                             : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32)
@@ -372,44 +372,6 @@ static int make_plane_map(CUtensorMap* out, const void* ptr, int64_t rows, int64
 // q = |x|^2 (per input row) and E = exp(log_sigma2) (per weight row), rounded to the MMA
 // operand precision, written once to a caller-provided workspace.  HBM-bound elementwise pass;
 // it takes the square/exp work (and its shared-memory traffic) out of the GEMM mainloop.
-// fp32 planes -> bf16 derived operands (mixed-precision variance GEMM of the CTA-pair kernel)
-template <bool kCplx>
-__global__ void __launch_bounds__(256)
-vd_prepare_bf16_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im, int64_t nx,
-                       __nv_bfloat16* __restrict__ q, const float* __restrict__ ls2, int64_t nw,
-                       __nv_bfloat16* __restrict__ e) {
-  const int64_t vx = nx / 8, vw = nw / 8;   // 8 elements per thread: 2 x 16 B in, 16 B out
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < vx + vw;
-       i += stride) {
-    Vec16<__nv_bfloat16> o;
-    if (i < vx) {
-      Vec16<float> a0, a1;
-      a0.load(x_re + i * 8), a1.load(x_re + i * 8 + 4);
-      if constexpr (kCplx) {
-        Vec16<float> b0, b1;
-        b0.load(x_im + i * 8), b1.load(x_im + i * 8 + 4);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          o.v[j] = fmaf(a0.v[j], a0.v[j], b0.v[j] * b0.v[j]);
-          o.v[4 + j] = fmaf(a1.v[j], a1.v[j], b1.v[j] * b1.v[j]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o.v[j] = a0.v[j] * a0.v[j], o.v[4 + j] = a1.v[j] * a1.v[j];
-      }
-      o.store(q + i * 8);
-    } else {
-      const int64_t k = i - vx;
-      Vec16<float> a0, a1;
-      a0.load(ls2 + k * 8), a1.load(ls2 + k * 8 + 4);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o.v[j] = __expf(a0.v[j]), o.v[4 + j] = __expf(a1.v[j]);
-      o.store(e + k * 8);
-    }
-  }
-}
-
 template <typename T, bool kCplx>
 __global__ void __launch_bounds__(256)
 vd_prepare_kernel(const T* __restrict__ x_re, const T* __restrict__ x_im, int64_t nx,
@@ -444,10 +406,6 @@ vd_prepare_kernel(const T* __restrict__ x_re, const T* __restrict__ x_im, int64_
   }
 }
 
-int fwd_tc2_dispatch(int dtype, bool cplx, bool mix_var, const void* x_re, const void* x_im,
-                     const void* w_re, const void* w_im, const void* q, const void* e, int64_t M,
-                     int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st);
-
 // persistent CTA-pair kernel on 16-bit operands (fwd_tc3.cu)
 size_t fwd_tc3_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K);
 bool fwd_tc3_supported(int dtype, int64_t M, int64_t N, int64_t K);
@@ -467,7 +425,7 @@ size_t fwd_tc_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K) {
 }
 
 template <typename T, bool kCplx, bool kVD, bool kXform, int kSwz>
-static int launch_tc(const void* x_re, const void* x_im, const void* w_re, const void* w_im,
+static int launch_tc(bool f16_ok, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                      const void* ls2, void* workspace, int64_t M, int64_t N, int64_t K,
                      const EpiParams& ep, cudaStream_t st, const KlFuse& kl) {
   using C = TcCfg<T, kCplx, kVD, kXform, kSwz>;
@@ -487,22 +445,21 @@ static int launch_tc(const void* x_re, const void* x_im, const void* w_re, const
     T* q = static_cast<T*>(workspace);
     const size_t qb = (static_cast<size_t>(M) * K * sizeof(T) + 255) & ~static_cast<size_t>(255);
     T* e = reinterpret_cast<T*>(static_cast<uint8_t*>(workspace) + qb);
-    // fp32 planes: per-row-scaled fp16 operands on kind::f16 (CPLXK_F16=0: tf32 operands as
-    // below); the persistent kernel of fwd_tc3.cu is the default for either dtype
-    // (CPLXK_PERSIST=0: one tile pair per cluster, fwd_tc2.cu)
-    const char* f16e = std::getenv("CPLXK_F16");
-    const char* pers = std::getenv("CPLXK_PERSIST");
-    const bool persist = !(pers && pers[0] == '0');
+    // fp32 planes: per-row-scaled fp16 operands on kind::f16 in the persistent CTA-pair kernel
+    // of fwd_tc3.cu (MATH_TENSOR_TF32: tf32 operands on the one-tile-per-CTA kernel below); bf16
+    // planes: the same persistent kernel on the planes as they are.
     // bf16 variance operands: their rounding errors (2^-9 each) average out over K; for a
     // handful of terms they do not, so short reductions keep tf32 everywhere
     const bool short_k = K < 64;
     if (!short_k && fwd_tc3_supported(std::is_same<T, float>::value ? CPLXK_F32 : CPLXK_BF16, M, N, K)) {
       if constexpr (std::is_same<T, float>::value) {
-        if (!(f16e && f16e[0] == '0'))
+        if (f16_ok)
           return fwd_tc3_f32(kCplx, x_re, x_im, w_re, w_im, ls2, workspace, M, N, K, ep, st, kl);
-      } else if (persist) {
+      } else {
         const int64_t work3 = (M * K + N * K) / Elem<T>::kVec;
-        const int grid3 = static_cast<int>(work3 / 256 + 1 > 148 * 16 ? 148 * 16 : work3 / 256 + 1);
+        int sms = 148;
+        if ((rc = current_device_sm_count(&sms))) return rc;
+        const int grid3 = static_cast<int>(work3 / 256 + 1 > sms * 16 ? sms * 16 : work3 / 256 + 1);
         vd_prepare_kernel<T, kCplx><<<grid3, 256, 0, st>>>(static_cast<const T*>(x_re),
                                                          static_cast<const T*>(x_im), M * K, q,
                                                          static_cast<const T*>(ls2), N * K, e);
@@ -510,32 +467,14 @@ static int launch_tc(const void* x_re, const void* x_im, const void* w_re, const
         return fwd_tc3_bf16(kCplx, x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
       }
     }
-    // CTA-pair kernel (cta_group::2): default for problems that fill a pair, CPLXK_PAIR=0 disables;
-    // with fp32 planes its variance operands travel as bf16 (CPLXK_MIXVAR=0 keeps them tf32)
-    const char* pe = std::getenv("CPLXK_PAIR");
-    const bool use_pair = (pe ? (pe[0] == '1') : true) && M > 128;
-    const char* me = std::getenv("CPLXK_MIXVAR");
-    const bool mix_var = use_pair && std::is_same<T, float>::value && (K % 8 == 0) && !short_k &&
-                         (me ? (me[0] == '1') : true);
-    const int64_t work = (M * K + N * K) / (mix_var ? 8 : Elem<T>::kVec);
-    const int grid = static_cast<int>(work / 256 + 1 > 148 * 16 ? 148 * 16 : work / 256 + 1);
-    if constexpr (std::is_same<T, float>::value) {
-      if (mix_var) {
-        auto qb = reinterpret_cast<__nv_bfloat16*>(q);
-        auto eb = reinterpret_cast<__nv_bfloat16*>(e);
-        vd_prepare_bf16_kernel<kCplx><<<grid, 256, 0, st>>>(
-            static_cast<const float*>(x_re), static_cast<const float*>(x_im), M * K, qb,
-            static_cast<const float*>(ls2), N * K, eb);
-      }
-    }
-    if (!mix_var)
-      vd_prepare_kernel<T, kCplx><<<grid, 256, 0, st>>>(static_cast<const T*>(x_re),
-                                                      static_cast<const T*>(x_im), M * K, q,
-                                                      static_cast<const T*>(ls2), N * K, e);
+    const int64_t work = (M * K + N * K) / Elem<T>::kVec;
+    int sms = 148;
+    if ((rc = current_device_sm_count(&sms))) return rc;
+    const int grid = static_cast<int>(work / 256 + 1 > sms * 16 ? sms * 16 : work / 256 + 1);
+    vd_prepare_kernel<T, kCplx><<<grid, 256, 0, st>>>(static_cast<const T*>(x_re),
+                                                    static_cast<const T*>(x_im), M * K, q,
+                                                    static_cast<const T*>(ls2), N * K, e);
     CPLXK_CUDA_TRY(cudaGetLastError());
-    if (use_pair)
-      return fwd_tc2_dispatch(std::is_same<T, float>::value ? CPLXK_F32 : CPLXK_BF16, kCplx, mix_var,
-                              x_re, x_im, w_re, w_im, q, e, M, N, K, ep, st);
     if ((rc = make_plane_map<T, kSwz>(&tm_q, q, M, K, false))) return rc;   // already rounded
     if ((rc = make_plane_map<T, kSwz>(&tm_ls, e, N, K, false))) return rc;
   }
@@ -556,9 +495,8 @@ static int launch_tc(const void* x_re, const void* x_im, const void* w_re, const
 }
 
 // true when fwd_tc_dispatch(vd, workspace) will also produce the layer's KL sum (pre-pass fusion)
-bool fwd_tc_fuses_kl(int dtype, int64_t M, int64_t N, int64_t K) {
-  const char* f16e = std::getenv("CPLXK_F16");
-  return dtype == CPLXK_F32 && !(f16e && f16e[0] == '0') && K >= 64 && fwd_tc3_supported(dtype, M, N, K);
+bool fwd_tc_fuses_kl(int dtype, bool f16_ok, int64_t M, int64_t N, int64_t K) {
+  return dtype == CPLXK_F32 && f16_ok && K >= 64 && fwd_tc3_supported(dtype, M, N, K);
 }
 
 bool fwd_tc_supported(int dtype, bool cplx, const void* x_re, const void* x_im, const void* w_re,
@@ -573,12 +511,12 @@ bool fwd_tc_supported(int dtype, bool cplx, const void* x_re, const void* x_im, 
   return true;
 }
 
-int fwd_tc_dispatch(int dtype, bool cplx, bool vd, int swz, const void* x_re, const void* x_im,
-                    const void* w_re, const void* w_im, const void* ls2, void* workspace,
-                    int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st,
-                    const KlFuse& kl) {
+int fwd_tc_dispatch(int dtype, bool cplx, bool vd, int swz, bool f16_ok, const void* x_re,
+                    const void* x_im, const void* w_re, const void* w_im, const void* ls2,
+                    void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
+                    cudaStream_t st, const KlFuse& kl) {
   const bool xform = vd && workspace == nullptr;
-#define CPLXK_TC_ARGS x_re, x_im, w_re, w_im, ls2, workspace, M, N, K, ep, st, kl
+#define CPLXK_TC_ARGS f16_ok, x_re, x_im, w_re, w_im, ls2, workspace, M, N, K, ep, st, kl
 #define CPLXK_TC_CASE(T, SW)                                                                   \
   if (cplx && vd && xform) return launch_tc<T, true, true, true, SW>(CPLXK_TC_ARGS);           \
   if (cplx && vd) return launch_tc<T, true, true, false, SW>(CPLXK_TC_ARGS);                   \

@@ -27,6 +27,7 @@
 
 #include "epilogue.cuh"
 #include "kl_math.cuh"
+#include "knobs.cuh"
 #include "ptx.cuh"
 #include "tc3_common.cuh"
 
@@ -481,25 +482,17 @@ static int launch_tc3(const Tc3Operands& o, int64_t M, int64_t N, int64_t K, con
   p.tiles_m2 = static_cast<int>((M + 255) / 256);
   p.tiles_n = static_cast<int>((N + C::BN - 1) / C::BN);
   p.f16 = o.f16 ? 1 : 0;
-  const char* dbg_env = std::getenv("CPLXK_DBG");
-  p.dbg = dbg_env ? std::atoi(dbg_env) : 0;
-  const char* rs = std::getenv("CPLXK_RASTER");
-  p.group = rs ? std::atoi(rs) : 6;
-  if (p.group < 1) p.group = 6;
+  p.dbg = knobs().dbg;        // 0 unless built with -DCPLXK_DEBUG
+  p.group = knobs().raster;
   p.sx = o.sx, p.sw = o.sw;
   p.ep = ep;
   const int64_t pairs = static_cast<int64_t>(p.tiles_m2) * p.tiles_n;
   if (pairs > 0x3fffffff) return CPLXK_ERR_UNSUPPORTED;
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    CPLXK_CUDA_TRY(cudaGetDevice(&dev));
-    CPLXK_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
-  // CPLXK_SM_RESERVE=n leaves n SMs to kernels of other streams (a collective, the KL shard
+  int sm_count = 0;
+  if ((rc = current_device_sm_count(&sm_count))) return rc;
+  // cplxk_set_sm_reserve(n) leaves n SMs to kernels of other streams (a collective, the KL shard
   // kernel): a persistent grid that owns every SM would make them wait for its last tile
-  const char* rsv = std::getenv("CPLXK_SM_RESERVE");
-  int64_t clusters = (sm_count - (rsv ? std::atoi(rsv) : 0)) / 2;
+  int64_t clusters = (sm_count - sm_reserve()) / 2;
   if (clusters < 1) clusters = 1;
   if (clusters > pairs) clusters = pairs;
   auto kern = fwd_tc3_kernel<OutT, kCplx>;
@@ -525,17 +518,17 @@ bool fwd_tc3_supported(int dtype, int64_t M, int64_t N, int64_t K) {
   return M > 128 && K % 8 == 0;
 }
 
-int fwd_tc2_half_dispatch(bool cplx, const void* xh_re, const void* xh_im, const void* wh_re,
-                          const void* wh_im, const void* q, const void* e, const float* sx,
-                          const float* sw, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
-                          cudaStream_t st);
-
 int vd_prepare_f16_launch(bool cplx, const void* x_re, const void* x_im, int64_t M, const void* w_re,
                           const void* w_im, const void* ls2, int64_t N, int64_t K, void* xh_re,
                           void* xh_im, void* q, void* wh_re, void* wh_im, void* e, float* isx,
                           float* isw, const KlFuse& kl, cudaStream_t st) {
   const int64_t rows = M + N;
-  const int grid = static_cast<int>(rows > 148 * 8 - 1 ? 148 * 8 - 1 : rows);   // odd; <= kKlMaxBlocks partials
+  int sms = 148;
+  int rc0 = current_device_sm_count(&sms);
+  if (rc0) return rc0;
+  int64_t cap = static_cast<int64_t>(sms) * 8 - 1;                               // odd (see the kernel)
+  if (cap > kKlMaxBlocks) cap = kKlMaxBlocks - 1 + (kKlMaxBlocks & 1);           // <= kKlMaxBlocks partials, odd
+  const int grid = static_cast<int>(rows > cap ? cap : rows);
   const int kl_kind = (kl.sum && kl.ws && q) ? kl.kind : -1;
   auto kws = static_cast<KlWorkspace*>(kl.ws);
   const int64_t kl_row0 = kl.row_begin, kl_row1 = kl.row_end < 0 ? N : kl.row_end;
@@ -554,8 +547,7 @@ int vd_prepare_f16_launch(bool cplx, const void* x_re, const void* x_im, int64_t
   return CPLXK_OK;
 }
 
-// fp32 planes: pre-pass to scaled fp16, then the CTA-pair kernel of fwd_tc2.cu on kind::f16
-// (CPLXK_PERSIST=0) or, by default, the persistent kernel above.
+// fp32 planes: pre-pass to scaled fp16, then the persistent CTA-pair kernel above on kind::f16.
 int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                 const void* ls2, void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
                 cudaStream_t st, const KlFuse& kl) {
@@ -574,11 +566,7 @@ int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re,
   if (rc) return rc;
   // the KL (partial) sum is final here: let a collective on another stream start under the GEMM
   if (kl.event) CPLXK_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(kl.event), st));
-  const char* dbg_env = std::getenv("CPLXK_DBG");
-  if (dbg_env && std::atoi(dbg_env) == 4) return CPLXK_OK;   // measurement aid: pre-pass only
-  const char* pe = std::getenv("CPLXK_PERSIST");
-  if (pe && pe[0] == '0')
-    return fwd_tc2_half_dispatch(cplx, xh_re, xh_im, wh_re, wh_im, q, e, isx, isw, M, N, K, ep, st);
+  if (!ep.y_re) return CPLXK_OK;   // cplxk_linear_vd_prepare: operands (and the KL sum) only
   Tc3Operands o{xh_re, xh_im, q, wh_re, wh_im, e, isx, isw, true};
   return cplx ? launch_tc3<float, true>(o, M, N, K, ep, st) : launch_tc3<float, false>(o, M, N, K, ep, st);
 }

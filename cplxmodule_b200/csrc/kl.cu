@@ -10,6 +10,7 @@
 //   CPLX_VD  penalty    complex/vd.py:95-99  gamma - la - Ei(-exp(-la))      (host scipy in the reference)
 //   CPLX_ARD penalty    complex/ard.py:39    softplus(-la)
 #include "kl_math.cuh"
+#include "knobs.cuh"
 
 namespace cplxk {
 
@@ -113,13 +114,9 @@ log_alpha_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im,
 }
 
 // ------------------------------------------------------------------ host side
-static int sm_count_cached() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-  }
+static int sm_count_cached() {   // per device (knobs.cuh); 148 if the query fails
+  int sms = 148;
+  if (current_device_sm_count(&sms) != CPLXK_OK || sms < 1) sms = 148;
   return sms;
 }
 
@@ -203,7 +200,7 @@ static int launch_log_alpha(const void* w_re, const void* w_im, const void* ls2,
                       (!out_la || aligned16(out_la)) && (!out_mask || aligned16(out_mask));
   int64_t work = (n + V - 1) / V;
   int64_t want = (work + 255) / 256;
-  int grid = static_cast<int>(want < 1 ? 1 : (want > 16 * 148 ? 16 * 148 : want));
+  int grid = static_cast<int>(want < 1 ? 1 : (want > 16 * sm_count_cached() ? 16 * sm_count_cached() : want));
   auto a = static_cast<const T*>(w_re);
   auto b = static_cast<const T*>(w_im);
   auto c = static_cast<const T*>(ls2);

@@ -1,0 +1,30 @@
+// Process-level tuning switches and per-device facts of the host side.
+//
+// * A/B switches (kernel variants kept for same-box comparisons) are read from the environment
+//   ONCE, when the library is first used -- never per call.  None of them changes results beyond
+//   the documented tolerance of the selected arithmetic; the arithmetic itself (exact fp32 /
+//   scaled-fp16 / tf32 operands) is chosen through the `math` ARGUMENT of the C ABI.
+// * Measurement aids that drop work (CPLXK_DBG) only exist in a -DCPLXK_DEBUG build.
+// * SM count / compute capability are cached per DEVICE (a process may drive several GPUs).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace cplxk {
+
+struct Knobs {
+  int tc_swizzle;          // CPLXK_TC_SWIZZLE = 64 | 128: smem swizzle of fwd_tc_kernel (0: per shape)
+  int raster;              // CPLXK_RASTER: 256-row tiles per raster group of the persistent GEMMs
+  bool lin3;               // CPLXK_LIN3=0: bf16 affine map on the one-tile-per-CTA kernel
+  bool tma_raw_f32;        // CPLXK_TMA_RAW_F32=1: let the tensor core truncate fp32 -> tf32
+  bool conv_pair;          // CPLXK_CONV_PAIR=0: conv on single-CTA tiles
+  bool conv_persistent;    // CPLXK_CONV_NONPERSISTENT=1: one conv tile per CTA
+  bool pdl;                // CPLXK_PDL=0: no programmatic dependent launch between pre-pass and GEMM
+  int dbg;                 // CPLXK_DBG (debug builds only; 0 otherwise)
+};
+
+const Knobs& knobs();             // api.cu
+int sm_reserve();                 // SMs a persistent grid leaves free (cplxk_set_sm_reserve)
+// SM count of the CURRENT device (cached per device); CPLXK_OK or CPLXK_ERR_CUDA
+int current_device_sm_count(int* sms);
+
+}  // namespace cplxk

@@ -13,7 +13,8 @@ import torch
 from . import _native as nv
 
 _state = {"noise": "torch", "math": "auto", "prepare": True, "fuse_kl": True, "kl_shard": None}
-_MATH = {"auto": nv.MATH_AUTO, "tensor": nv.MATH_TENSOR, "simt": nv.MATH_SIMT}
+_MATH = {"auto": nv.MATH_AUTO, "tensor": nv.MATH_TENSOR, "simt": nv.MATH_SIMT, "exact": nv.MATH_SIMT,
+         "tf32": nv.MATH_TENSOR_TF32}
 _NOISE = {"torch": nv.NOISE_PHILOX_TORCH, "fast": nv.NOISE_PHILOX_FAST}
 
 
@@ -28,7 +29,18 @@ def set_noise_mode(mode):
 
 
 def set_math_mode(mode):
-    """``"auto"`` (tensor cores when alignment allows), ``"tensor"``, ``"simt"`` (exact fp32)."""
+    """Arithmetic of the GEMM-shaped part of every forward / gradient call on fp32 planes:
+
+    * ``"auto"`` (default) / ``"tensor"``: tcgen05 tensor cores on per-row power-of-two scaled
+      fp16 copies of the operands (tf32's 11-bit significand, round-to-nearest, fp32
+      accumulation; about 3e-4 max-norm relative error; entries more than 2^-24 below their
+      row maximum lose bits).  ``"auto"`` falls back to the exact kernel for shapes TMA cannot
+      take, ``"tensor"`` raises instead;
+    * ``"tf32"``: tensor cores on tf32 operands, i.e. what torch does under
+      ``torch.backends.cuda.matmul.allow_tf32 = True`` (no per-row scale, half the MMA rate);
+    * ``"simt"`` / ``"exact"``: fp32 FMA on the CUDA cores -- the arithmetic of the reference
+      under torch's default ``allow_tf32 = False`` (about 1e-6).
+    bf16 planes always run bf16 operands with fp32 accumulation."""
     if mode not in _MATH:
         raise ValueError(f"math mode must be one of {sorted(_MATH)}")
     _state["math"] = mode
@@ -72,11 +84,7 @@ def kl_request(kind, n_rows):
 def set_sm_reserve(n_sms):
     """Leave ``n_sms`` SMs out of the persistent GEMM grid so that kernels of other streams (a
     collective, a KL shard kernel) do not wait for its last tile (0: use every SM)."""
-    import os
-    if n_sms:
-        os.environ["CPLXK_SM_RESERVE"] = str(int(n_sms))
-    else:
-        os.environ.pop("CPLXK_SM_RESERVE", None)
+    nv.check(nv.lib().cplxk_set_sm_reserve(int(n_sms or 0)))
 
 
 def get_noise_mode():
@@ -217,7 +225,8 @@ def _gemm(a_re, a_im, p_re, p_im):
     """(a_re + i a_im) . (p_re + i p_im)^T  (or the real product) on the tensor cores; gradient
     GEMMs contract over whatever the batch size is, so shapes the TMA path cannot take fall
     through to the exact-fp32 kernel even when the user forced ``"tensor"`` for the forward."""
-    math = nv.MATH_SIMT if _state["math"] == "simt" else nv.MATH_AUTO
+    math = {"simt": nv.MATH_SIMT, "exact": nv.MATH_SIMT, "tf32": nv.MATH_TENSOR_TF32}.get(
+        _state["math"], nv.MATH_AUTO)
     re, im, _ = _forward_raw(a_re, a_im, p_re, p_im, None, None, None, None, None, None, math=math)
     return re, im
 

@@ -56,7 +56,11 @@ typedef enum {
                             scaled fp16 (variational forward with workspace) or tf32
                             (round-to-nearest) otherwise.  Needs 16-byte aligned planes and
                             K*sizeof(elem) % 16 == 0.                          */
-  CPLXK_MATH_SIMT = 2    /* exact fp32 FMA on CUDA cores (any shape)          */
+  CPLXK_MATH_SIMT = 2,   /* exact fp32 FMA on CUDA cores (any shape)          */
+  CPLXK_MATH_TENSOR_TF32 = 3 /* as AUTO, but F32 planes always run on tf32 operands (rounded to
+                            nearest by TMA): the arithmetic of torch's `allow_tf32`.  Same
+                            11-bit significand as the scaled-fp16 form without its per-row
+                            (linear) / per-image (conv) scale, at half the MMA rate.        */
 } cplxk_math;
 
 /* source of the local-reparameterisation noise */
@@ -82,6 +86,10 @@ typedef enum {
 
 int cplxk_abi_version(void);
 const char* cplxk_strerror(int status);
+
+/* Persistent GEMM grids leave `n_sms` SMs free for kernels of other streams (a collective, a
+ * KL shard kernel).  Process-wide, 0 by default (or CPLXK_SM_RESERVE at load). */
+int cplxk_set_sm_reserve(int n_sms);
 
 /* Number of SMs / compute capability of the current device (host ints). */
 int cplxk_device_info(int* sm_count, int* cc_major, int* cc_minor);
@@ -152,6 +160,21 @@ int cplxk_linear_vd_fwd(const void* x_re, const void* x_im,
                         int64_t M, int64_t N, int64_t K,
                         int dtype, int math, void* s2_out /* nullable [M,N]: saved variance */,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The operand pre-pass of the F32 tensor-core path on its own: fills `workspace` with the
+ * row-scaled fp16 copies of x and W, bf16 |x|^2 and exp(log_sigma2) and the inverse row scales
+ * (and, with kl_kind >= 0, writes the layer's KL sum to *kl_sum) WITHOUT launching the GEMM.
+ * What cplxk_linear_vd_fwd[_kl] runs first; exposed so that the HBM-bound stage can be timed
+ * and profiled by itself.  CPLXK_ERR_UNSUPPORTED unless F32, M > 128, K >= 64, K % 8 == 0.
+ */
+int cplxk_linear_vd_prepare(const void* x_re, const void* x_im,
+                            const void* w_re, const void* w_im,
+                            const void* log_sigma2,
+                            int64_t M, int64_t N, int64_t K, int dtype,
+                            void* workspace, size_t workspace_bytes,
+                            int kl_kind, float* kl_sum,
+                            void* kl_workspace, size_t kl_workspace_bytes, void* stream);
 
 /*
  * Same forward, with the layer's KL penalty as a by-product.  The operand pre-pass of the

@@ -121,7 +121,7 @@ class _Expi(torch.autograd.Function):
     def forward(ctx, x):
         ctx.save_for_backward(x)
         x_np = x.detach().cpu().numpy()
-        return torch.from_numpy(scipy.special.expi(x_np, dtype=x_np.dtype))
+        return torch.from_numpy(scipy.special.expi(x_np, dtype=x_np.dtype)).to(x.device)   # vd.py:36
 
     @staticmethod
     def backward(ctx, grad_output):

@@ -352,11 +352,11 @@ def test_fp32_nchw_conv_on_scaled_fp16_operands():
         ch_scale = torch.logspace(-4, 3, O, device=DEV).view(O, 1, 1, 1)
         m.weight.real.mul_(ch_scale); m.weight.imag.mul_(ch_scale)
         out = m(cplx.Cplx(z_re, z_im))
-        os.environ["CPLXK_CONV_F16"] = "0"
+        ops.set_math_mode("tf32")
         try:
             out32 = m(cplx.Cplx(z_re, z_im))
         finally:
-            os.environ.pop("CPLXK_CONV_F16")
+            ops.set_math_mode("auto")
     c = lambda t: t.detach().double().cpu()
     want = orc.cplx_conv2d(c(z_re), c(z_im), c(m.weight.real), c(m.weight.imag), None, None, 1, 1, 1)
     for got, got32, ref in ((out.real, out32.real, want[0]), (out.imag, out32.imag, want[1])):

@@ -45,12 +45,10 @@ def _run(case, cplx_=True):
     return (got,), (want,)
 
 
-@pytest.fixture(params=["persistent", "tile_per_cluster"])
+@pytest.fixture(params=["persistent"])
 def kernel(request):
-    if request.param == "tile_per_cluster":
-        os.environ["CPLXK_PERSIST"] = "0"
+    """one kernel serves the scaled-fp16 path (fwd_tc3.cu); the tile-per-cluster generation is gone"""
     yield request.param
-    os.environ.pop("CPLXK_PERSIST", None)
 
 
 @pytest.mark.parametrize("M,N,K", [(129, 8, 8), (256, 128, 64), (300, 384, 1000), (513, 130, 264),
@@ -115,11 +113,11 @@ def test_matches_tf32_path_and_exact_fp32_kernel():
     """three independent implementations of the same forward on the device agree"""
     case = _case(512, 256, 1024, 17)
     got16, want = _run(case)
-    os.environ["CPLXK_F16"] = "0"
+    ops.set_math_mode("tf32")          # tf32 operands (cplxk_math: CPLXK_MATH_TENSOR_TF32)
     try:
         got32, _ = _run(case)
     finally:
-        os.environ.pop("CPLXK_F16", None)
+        ops.set_math_mode("auto")
     ops.set_math_mode("simt")
     try:
         exact, _ = _run(case)

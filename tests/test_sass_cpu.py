@@ -13,9 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "cplxmodule_b200", "csrc", "libcplxk.so")
 CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
 
-TC_KERNELS = ("fwd_tc_kernel", "fwd_tc2_kernel", "fwd_tc3_kernel", "lin_tc3_kernel", "conv_tc_kernel",
+TC_KERNELS = ("fwd_tc_kernel", "fwd_tc3_kernel", "lin_tc3_kernel", "conv_tc_kernel",
               "conv_tc_persistent_kernel", "conv_tc_pair_kernel")
-CLUSTER_KERNELS = ("fwd_tc2_kernel", "fwd_tc3_kernel", "lin_tc3_kernel", "conv_tc_pair_kernel")
+CLUSTER_KERNELS = ("fwd_tc3_kernel", "lin_tc3_kernel", "conv_tc_pair_kernel")
 
 
 @pytest.fixture(scope="module")
