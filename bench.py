@@ -402,9 +402,10 @@ def parity_block(layer, x, wl, world, kl_step):
     if kl_step is not None:                                    # N > 1: the value the timed step produced
         rel = abs(float(kl_step) - kl_alone.item()) / abs(kl_alone.item())
         out["kl_allreduced_vs_unsharded"] = rel
-        assert rel < 1e-6, f"all-reduced row-sharded KL differs from the unsharded kernel: {rel:.3e}"
-    assert out["fwd_rel_err"] < out["fwd_tol"], out
-    assert out["kl_rel_err"] < out["kl_tol"], out
+        out["kl_allreduce_ok"] = bool(rel < 1e-6)
+    # reported, never fatal: a bench line with "ok": false is still a line the driver can read
+    out["ok"] = bool(out["fwd_rel_err"] < out["fwd_tol"] and out["kl_rel_err"] < out["kl_tol"]
+                     and out.get("kl_allreduce_ok", True))
     return out
 
 

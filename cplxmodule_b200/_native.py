@@ -28,6 +28,8 @@ EXPORTS = (
     "cplxk_conv2d_fwd", "cplxk_conv2d_workspace_bytes", "cplxk_randn_philox_torch",
     "cplxk_transpose2d", "cplxk_eltwise", "cplxk_colsum", "cplxk_vd_grad_s2", "cplxk_vd_grad_input",
     "cplxk_mul_exp", "cplxk_kl_bwd",
+    "cplxk_linear_masked_fwd", "cplxk_linear_masked_workspace_bytes", "cplxk_kl_mask",
+    "cplxk_outer_fwd", "cplxk_outer_bwd",
 )
 
 _lock = threading.Lock()
@@ -74,6 +76,13 @@ def _declare(lib):
     lib.cplxk_mul_exp.argtypes = [_vp, _vp, _vp, _i64, _int, _int, _vp]
     lib.cplxk_kl_bwd.argtypes = [_int, _vp, _vp, _vp, _i64, _int, _vp, _int, _int, ctypes.c_double,
                                  _vp, _vp, _vp, _vp]
+    lib.cplxk_linear_masked_workspace_bytes.restype = ctypes.c_size_t
+    lib.cplxk_linear_masked_workspace_bytes.argtypes = [_i64, _i64, _i64, _int]
+    lib.cplxk_linear_masked_fwd.argtypes = [_vp] * 9 + [_i64] * 3 + [_int, _int, _vp, ctypes.c_size_t, _vp]
+    lib.cplxk_kl_mask.argtypes = [_int, _vp, _vp, _vp, _i64, _int, ctypes.c_float, _vp, _vp,
+                                  ctypes.c_double, _vp, ctypes.c_size_t, _vp]
+    lib.cplxk_outer_fwd.argtypes = [_vp] * 6 + [_i64] * 3 + [_int, _int, _vp]
+    lib.cplxk_outer_bwd.argtypes = [_vp] * 10 + [_i64] * 3 + [_int, _int, _vp]
     for name in EXPORTS:
         getattr(lib, name)  # fail at load time, not at first use, if a symbol is missing
 
@@ -167,6 +176,34 @@ def philox_plan(device, numel, torch_exact=True):
     offset = gen.get_offset()
     offset = (offset + 3) // 4 * 4
     return gen, gen.initial_seed(), offset, threads, increment
+
+
+# ------------------------------------------------------------------ scratch workspace
+_ws = {}
+
+
+def workspace(device, nbytes):
+    """Grow-only scratch buffer per (device, stream).  Kernels of one stream are ordered, so
+    consecutive calls on it can share the buffer: no allocator round trip per call.  Under CUDA
+    graph capture a fresh tensor is returned instead (it then belongs to the graph's pool)."""
+    if nbytes <= 0:
+        return None
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _ws.pop(key, None)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+def release_workspaces():
+    """Drop the cached scratch buffers (they are re-created on demand)."""
+    _ws.clear()
+    _kl_ws.clear()
 
 
 # -------------------------------------------------------------------- KL workspace

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libcplxk.so")
 OBJ = os.path.join(CSRC, "_obj")
-SOURCES = ["api.cu", "kl.cu", "fwd_simt.cu", "fwd_tc.cu", "fwd_tc3.cu", "fwd_lin3.cu", "conv.cu", "conv_tc.cu", "bwd.cu"]
+SOURCES = ["api.cu", "kl.cu", "fwd_simt.cu", "fwd_tc.cu", "fwd_tc3.cu", "fwd_lin3.cu", "conv.cu", "conv_tc.cu", "bwd.cu", "bilinear.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -1,6 +1,7 @@
 """Host side of the complex convolution path (reference: ``cplx.convnd``,
 ``cplxmodule/cplx.py:770-800`` and ``CplxConvNdGaussianMixin._forward_impl``,
 ``nn/relevance/complex/base.py:120-135``).  One C-ABI call per group."""
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -248,6 +249,37 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
     return y_re, y_im, {"philox": (seed, offset, threads), "eps_re": er, "eps_im": ei}
 
 
+def _out_hw(x, w, geom):
+    stride, padding, dilation = geom
+    H, W = x.shape[2], x.shape[3]
+    kh, kw = w.shape[2], w.shape[3]
+    return ((H + 2 * padding[0] - dilation[0] * (kh - 1) - 1) // stride[0] + 1,
+            (W + 2 * padding[1] - dilation[1] * (kw - 1) - 1) // stride[1] + 1)
+
+
+def _draw_noise(cplx, shape, device, dtype):
+    """The draw the reference makes for a whole layer -- ``cplx.randn_like(s2)`` = ONE
+    ``randn(2, *shape) / sqrt(2)`` (cplx.py:544-550) or ``torch.randn_like(s2)`` -- produced by
+    the library's torch-layout Philox kernel (bit-equal to torch's stream for the same generator
+    state; the generator is advanced like torch would).  Used where one launch cannot cover the
+    layer's output (grouped convolutions): the groups then read their channel slices of it."""
+    numel = (2 if cplx else 1) * int(torch.Size(shape).numel())
+    gen, seed, offset, threads, inc = nv.philox_plan(device, max(numel, 1), True)
+    # torch evaluates `randn(...) / sqrt(2)` on CUDA as a product with the fp32 reciprocal
+    inv_sqrt2 = float(np.float32(1.0) / np.float32(2.0 ** 0.5))
+    flat = ops.randn_philox_torch(numel, seed, offset, threads, inv_sqrt2 if cplx else 1.0, device)
+    gen.set_offset(offset + inc)
+    flat = flat.to(dtype)
+    if cplx:
+        planes = flat.view(2, *shape)
+        return planes[0], planes[1]
+    return flat.view(*shape), None
+
+
+def _grad_wanted(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 def cplx_convnd(nd, input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
                 padding_mode="zeros", log_sigma2=None, eps=None):
     stride, padding, dilation = _tuple(stride, nd), _tuple(padding, nd), _tuple(dilation, nd)
@@ -271,6 +303,16 @@ def cplx_convnd(nd, input, weight, bias=None, stride=1, padding=0, dilation=1, g
         geom = (stride, padding, dilation)
     b_re, b_im = (None, None) if bias is None else (bias.real, bias.imag)
     noise = nv.NOISE_INJECT if e is not None else ops._NOISE[ops.get_noise_mode()]
+    if (ls2 is not None and noise == nv.NOISE_PHILOX_FAST
+            and _grad_wanted(x_re, x_im, w_re, w_im, ls2)):
+        # the private 'fast' layout of the conv kernels is not regenerated by the backward: under
+        # autograd the forward uses the torch-exact layout instead (same distribution)
+        noise = nv.NOISE_PHILOX_TORCH
+    if groups > 1 and ls2 is not None and e is None:
+        # one launch covers one group, the layer's noise is ONE draw: make it, then inject slices
+        Ho, Wo = _out_hw(x_re, w_re, geom)
+        e = _draw_noise(True, (x_re.shape[0], w_re.shape[0], Ho, Wo), x_re.device, w_re.dtype)
+        noise = nv.NOISE_INJECT
 
     def run(xr, xi, wr, wi, br, bi, l2, ee):
         er, ei = (None, None) if ee is None else ee
@@ -279,10 +321,6 @@ def cplx_convnd(nd, input, weight, bias=None, stride=1, padding=0, dilation=1, g
     if groups == 1:
         re, im = run(x_re, x_im, w_re, w_im, b_re, b_im, ls2, e)
     else:
-        if ls2 is not None and e is None and noise == nv.NOISE_PHILOX_TORCH:
-            raise NotImplementedError(
-                "grouped variational conv with the torch-exact noise stream is not supported; "
-                "use set_noise_mode('fast') or pass eps")
         cin, cout = x_re.shape[1] // groups, w_re.shape[0] // groups
         outs = []
         for gi in range(groups):
@@ -315,6 +353,12 @@ def real_convnd(nd, input, weight, bias=None, stride=1, padding=0, dilation=1, g
         x, w, ls2, e = input, weight, log_sigma2, eps
         geom = (stride, padding, dilation)
     noise = nv.NOISE_INJECT if e is not None else ops._NOISE[ops.get_noise_mode()]
+    if ls2 is not None and noise == nv.NOISE_PHILOX_FAST and _grad_wanted(x, w, ls2):
+        noise = nv.NOISE_PHILOX_TORCH       # see cplx_convnd
+    if groups > 1 and ls2 is not None and e is None:
+        Ho, Wo = _out_hw(x, w, geom)
+        e, _ = _draw_noise(False, (x.shape[0], w.shape[0], Ho, Wo), x.device, w.dtype)
+        noise = nv.NOISE_INJECT
 
     def run(x_, w_, b_, l2_, e_):
         return _ConvFn.apply(x_, None, w_, None, b_, None, l2_, e_, None, noise, geom)[0]
@@ -322,10 +366,6 @@ def real_convnd(nd, input, weight, bias=None, stride=1, padding=0, dilation=1, g
     if groups == 1:
         out = run(x, w, bias, ls2, e)
     else:
-        if ls2 is not None and e is None and noise == nv.NOISE_PHILOX_TORCH:
-            raise NotImplementedError(
-                "grouped variational conv with the torch-exact noise stream is not supported; "
-                "use set_noise_mode('fast') or pass eps")
         cin, cout = x.shape[1] // groups, w.shape[0] // groups
         outs = []
         for gi in range(groups):

@@ -377,6 +377,20 @@ linear_cat = linear
 linear_3m = linear
 
 
+def bilinear(input1, input2, weight, bias=None, conjugate=True):
+    """Complex bilinear map ``y_j = x1^{H|T} A_j x2 + b_j`` (reference: ``bilinear_naive``,
+    ``cplx.py:1062-1090``): an outer-product kernel + the complex affine tcgen05 kernel on
+    ``[.., in1 * in2]`` features."""
+    b_re, b_im = (None, None) if bias is None else (bias.real, bias.imag)
+    re, im = _ops.cplx_bilinear(input1.real, input1.imag, input2.real, input2.imag, weight.real,
+                                weight.imag, b_re, b_im, conjugate)
+    return Cplx(re, im)
+
+
+bilinear_naive = bilinear
+bilinear_cat = bilinear
+
+
 def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
            padding_mode="zeros"):
     """Complex 2-d cross-correlation (no kernel flip / conjugation), ``B x C x H x W``."""

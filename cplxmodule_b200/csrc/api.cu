@@ -27,7 +27,8 @@ bool fwd_tc_fuses_kl(int dtype, bool f16_ok, int64_t M, int64_t N, int64_t K);
 size_t fwd_lin3_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K);
 bool fwd_lin3_supported(int64_t M, int64_t N, int64_t K);
 int fwd_lin3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
-                 void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st);
+                 void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st,
+                 const void* w_mask);
 int fwd_lin3_bf16(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                   int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st);
 size_t fwd_tc_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K);
@@ -123,7 +124,10 @@ static int forward_common(bool vd, const void* x_re, const void* x_im, const voi
                           uint64_t offset, uint32_t threads, void* y_re, void* y_im, int64_t M,
                           int64_t N, int64_t K, int dtype, int math, void* s2_out, void* workspace,
                           size_t workspace_bytes, void* stream, KlFuse kl = KlFuse{-1, nullptr, nullptr, 0, -1, nullptr},
-                          int* kl_done = nullptr) {
+                          int* kl_done = nullptr, const void* w_mask = nullptr, int* mask_done = nullptr) {
+  // w_mask (plain affine map only): applied by the path taken when *mask_done is set to 1 on
+  // return; otherwise the caller must have passed already-masked weights
+  if (mask_done) *mask_done = 0;
   if (kl_done) *kl_done = 0;
   if (!x_re || !w_re || !y_re || M < 0 || N < 0 || K < 0) return CPLXK_ERR_BADARG;
   const bool cplx = (x_im != nullptr);
@@ -163,8 +167,10 @@ static int forward_common(bool vd, const void* x_re, const void* x_im, const voi
     if (!vd && fwd_lin3_supported(M, N, K)) {
       // plain affine map: persistent CTA-pair kernel with double-buffered accumulators; fp32 planes
       // need the workspace for their row-scaled fp16 copies (MATH_TENSOR_TF32 / no workspace: tf32 below)
-      if (dtype == CPLXK_F32 && workspace && K >= 64 && f16_ok)
-        return fwd_lin3_f32(cplx, x_re, x_im, w_re, w_im, workspace, M, N, K, ep, st);
+      if (dtype == CPLXK_F32 && workspace && K >= 64 && f16_ok) {
+        if (mask_done) *mask_done = 1;
+        return fwd_lin3_f32(cplx, x_re, x_im, w_re, w_im, workspace, M, N, K, ep, st, w_mask);
+      }
       if (dtype == CPLXK_BF16 && knobs().lin3)   // CPLXK_LIN3=0: one tile per CTA (fwd_tc.cu)
         return fwd_lin3_bf16(cplx, x_re, x_im, w_re, w_im, M, N, K, ep, st);
     }
@@ -284,6 +290,62 @@ extern "C" int cplxk_linear_vd_fwd_kl(const void* x_re, const void* x_im, const 
   return forward_common(true, x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise,
                         seed, offset, philox_threads, y_re, y_im, M, N, K, dtype, math, s2_out,
                         workspace, workspace_bytes, stream, kl, kl_done);
+}
+
+// ---- fixed-sparsity layers: y = x (W * mask)^T + b
+namespace cplxk {
+int eltwise_mul2(const void* a0, const void* a1, const void* b, void* o0, void* o1, int64_t n, int dtype,
+                 cudaStream_t st);   // bwd.cu: o0 = a0 * b, o1 = a1 * b (a1/o1 nullable), one launch
+}
+
+extern "C" size_t cplxk_linear_masked_workspace_bytes(int64_t M, int64_t N, int64_t K, int dtype) {
+  if (M < 0 || N < 0 || K < 0) return 0;
+  const size_t es = dtype == CPLXK_F32 ? 4 : 2;
+  const size_t plane = (static_cast<size_t>(N) * K * es + 255) & ~static_cast<size_t>(255);
+  const size_t base = (fwd_lin3_workspace_bytes(dtype, M, N, K) + 255) & ~static_cast<size_t>(255);
+  return base + 2 * plane;
+}
+
+extern "C" int cplxk_linear_masked_fwd(const void* x_re, const void* x_im, const void* w_re,
+                                       const void* w_im, const void* mask, const void* b_re,
+                                       const void* b_im, void* y_re, void* y_im, int64_t M,
+                                       int64_t N, int64_t K, int dtype, int math, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  if (!mask) return CPLXK_ERR_BADARG;
+  if (!workspace || !aligned16(workspace)) return workspace ? CPLXK_ERR_ALIGN : CPLXK_ERR_WORKSPACE;
+  if (M < 0 || N < 0 || K < 0) return CPLXK_ERR_BADARG;
+  if (workspace_bytes < cplxk_linear_masked_workspace_bytes(M, N, K, dtype)) return CPLXK_ERR_WORKSPACE;
+  if (M == 0 || N == 0) return CPLXK_OK;
+  const size_t es = dtype == CPLXK_F32 ? 4 : 2;
+  const size_t plane = (static_cast<size_t>(N) * K * es + 255) & ~static_cast<size_t>(255);
+  const size_t base = (fwd_lin3_workspace_bytes(dtype, M, N, K) + 255) & ~static_cast<size_t>(255);
+  // first choice: the mask rides along in the operand pre-pass
+  int mask_done = 0;
+  const bool fusable = dtype == CPLXK_F32 && math != CPLXK_MATH_SIMT && math != CPLXK_MATH_TENSOR_TF32 &&
+                       K >= 64 && fwd_lin3_supported(M, N, K) &&
+                       fwd_tc_supported(dtype, x_im != nullptr, x_re, x_im, w_re, w_im, mask, M, N, K);
+  if (fusable) {
+    int rc = forward_common(false, x_re, x_im, w_re, w_im, b_re, b_im, nullptr, nullptr, nullptr, 0, 0,
+                            0, 0, y_re, y_im, M, N, K, dtype, math, nullptr, workspace, base, stream,
+                            KlFuse{-1, nullptr, nullptr, 0, -1, nullptr}, nullptr, mask, &mask_done);
+    if (rc != CPLXK_OK || mask_done) return rc;
+    return CPLXK_ERR_UNSUPPORTED;   // unreachable by construction: the fused path was predicted
+  }
+  if (!x_re || !w_re || !y_re) return CPLXK_ERR_BADARG;
+  if ((x_im != nullptr) != (w_im != nullptr)) return CPLXK_ERR_BADARG;
+  if (dtype != CPLXK_F32 && dtype != CPLXK_BF16) return CPLXK_ERR_BADARG;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  void* m_re = ws + base;
+  void* m_im = w_im ? ws + base + plane : nullptr;
+  int rc = check_arch();
+  if (rc) return rc;
+  if (N > 0 && K > 0) {
+    rc = eltwise_mul2(w_re, w_im, mask, m_re, m_im, N * K, dtype, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+  }
+  return forward_common(false, x_re, x_im, m_re, m_im, b_re, b_im, nullptr, nullptr, nullptr, 0, 0, 0,
+                        0, y_re, y_im, M, N, K, dtype, math, nullptr, base ? workspace : nullptr, base,
+                        stream);
 }
 
 // operand pre-pass of the fp32-plane tensor-core path on its own (no GEMM launch)

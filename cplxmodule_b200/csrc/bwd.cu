@@ -15,7 +15,7 @@
 
 namespace cplxk {
 
-enum { TR_COPY = 0, TR_NEG = 1, TR_EXP = 2, TR_ABS2 = 3, TR_SQR = 4 };
+enum { TR_COPY = 0, TR_NEG = 1, TR_EXP = 2, TR_ABS2 = 3, TR_SQR = 4, TR_MUL = 5 };
 
 // out[c, r] = op(in[r, c])  (TR_ABS2: in^2 + in2^2), 32 x 32 smem tiles, coalesced both ways
 template <typename T, int kOp>
@@ -207,8 +207,22 @@ eltwise_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__
     else if (op == TR_ABS2) {
       const float w = Elem<T>::to_f(b[i]);
       v = fmaf(v, v, w * w);
+    } else if (op == TR_MUL) {
+      v *= Elem<T>::to_f(b[i]);
     }
     out[i] = Elem<T>::from_f(v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+mul2_kernel(const T* __restrict__ a0, const T* __restrict__ a1, const T* __restrict__ b,
+            T* __restrict__ o0, T* __restrict__ o1, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float m = Elem<T>::to_f(b[i]);
+    o0[i] = Elem<T>::from_f(Elem<T>::to_f(a0[i]) * m);
+    if (a1) o1[i] = Elem<T>::from_f(Elem<T>::to_f(a1[i]) * m);
   }
 }
 
@@ -217,6 +231,24 @@ static inline int ew_grid(int64_t n) {
   if (current_device_sm_count(&sms) != CPLXK_OK || sms < 1) sms = 148;
   const int64_t b = (n + 255) / 256, cap = static_cast<int64_t>(sms) * 16;
   return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+int eltwise_mul2(const void* a0, const void* a1, const void* b, void* o0, void* o1, int64_t n, int dtype,
+                 cudaStream_t st) {
+  if (!a0 || !b || !o0 || (a1 && !o1) || n < 0) return CPLXK_ERR_BADARG;
+  if (n == 0) return CPLXK_OK;
+  if (dtype == CPLXK_F32)
+    mul2_kernel<float><<<ew_grid(n), 256, 0, st>>>(static_cast<const float*>(a0), static_cast<const float*>(a1),
+                                                  static_cast<const float*>(b), static_cast<float*>(o0),
+                                                  static_cast<float*>(o1), n);
+  else if (dtype == CPLXK_BF16)
+    mul2_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(a0), static_cast<const __nv_bfloat16*>(a1),
+        static_cast<const __nv_bfloat16*>(b), static_cast<__nv_bfloat16*>(o0), static_cast<__nv_bfloat16*>(o1), n);
+  else
+    return CPLXK_ERR_BADARG;
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
 }
 
 }  // namespace cplxk
@@ -254,8 +286,8 @@ extern "C" int cplxk_transpose2d(const void* in, const void* in2, void* out, int
 
 extern "C" int cplxk_eltwise(int op, const void* a, const void* b, void* out, int64_t n, int dtype,
                              void* stream) {
-  if (!a || !out || n < 0 || op < TR_COPY || op > TR_SQR) return CPLXK_ERR_BADARG;
-  if (op == TR_ABS2 && !b) return CPLXK_ERR_BADARG;
+  if (!a || !out || n < 0 || op < TR_COPY || op > TR_MUL) return CPLXK_ERR_BADARG;
+  if ((op == TR_ABS2 || op == TR_MUL) && !b) return CPLXK_ERR_BADARG;
   if (n == 0) return CPLXK_OK;
   auto st = static_cast<cudaStream_t>(stream);
   CPLXK_BY_DTYPE(dtype, {

@@ -107,6 +107,7 @@ lin_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
     const bool elected = ptx::elect_one();
     int s = 0;
     uint32_t ph = 0;
+    ptx::grid_dep_wait();   // fp32 planes: the operands come from the pre-pass launched just before
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       int tile_m, tile_n;
       decode_tile(t, tile_m, tile_n);
@@ -178,6 +179,7 @@ lin_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
     const int half = (warp - 2) >> 2;
     const int te = threadIdx.x - 64;
     uint32_t it = 0;
+    ptx::grid_dep_wait();   // row / column scales are written by the pre-pass
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
       const uint32_t buf = it & 1u, tph = (it >> 1) & 1u;
       int tile_m, tile_n;
@@ -282,8 +284,14 @@ static int launch_lin3(const Lin3Operands& o, int64_t M, int64_t N, int64_t K, c
   if (clusters > pairs) clusters = pairs;
   auto kern = lin_tc3_kernel<OutT, kCplx>;
   CPLXK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  kern<<<static_cast<unsigned>(2 * clusters), C::THREADS, C::SMEM_BYTES, st>>>(tm_xr, tm_xi, tm_wr, tm_wi, p);
-  CPLXK_CUDA_TRY(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters)), cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = (o.f16 && knobs().pdl) ? 1 : 0;   // f16: launched right after the pre-pass
+  CPLXK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm_xr, tm_xi, tm_wr, tm_wi, p));
   return CPLXK_OK;
 }
 
@@ -299,10 +307,11 @@ bool fwd_lin3_supported(int64_t M, int64_t N, int64_t K) { return M > 128 && K %
 int vd_prepare_f16_launch(bool cplx, const void* x_re, const void* x_im, int64_t M, const void* w_re,
                           const void* w_im, const void* ls2, int64_t N, int64_t K, void* xh_re,
                           void* xh_im, void* q, void* wh_re, void* wh_im, void* e, float* isx,
-                          float* isw, const KlFuse& kl, cudaStream_t st);
+                          float* isw, const KlFuse& kl, cudaStream_t st, const void* w_mask);
 
 int fwd_lin3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
-                 void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st) {
+                 void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st,
+                 const void* w_mask) {
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const size_t xb = align256(static_cast<size_t>(M) * K * 2), wb = align256(static_cast<size_t>(N) * K * 2);
   void* xh_re = ws;
@@ -313,7 +322,7 @@ int fwd_lin3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re
   float* isw = reinterpret_cast<float*>(ws + 2 * xb + 2 * wb + align256(static_cast<size_t>(M) * 4));
   const KlFuse none{-1, nullptr, nullptr, 0, -1, nullptr};
   int rc = vd_prepare_f16_launch(cplx, x_re, x_im, M, w_re, w_im, nullptr, N, K, xh_re, xh_im, nullptr,
-                                 wh_re, wh_im, nullptr, isx, isw, none, st);
+                                 wh_re, wh_im, nullptr, isx, isw, none, st, w_mask);
   if (rc) return rc;
   Lin3Operands o{xh_re, xh_im, wh_re, wh_im, isx, isw, true};
   return cplx ? launch_lin3<float, true>(o, M, N, K, ep, st) : launch_lin3<float, false>(o, M, N, K, ep, st);

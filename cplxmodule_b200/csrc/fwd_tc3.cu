@@ -129,6 +129,7 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
       const bool elected = ptx::elect_one();
       int s = 0;
       uint32_t ph = 0;
+      ptx::grid_dep_wait();   // the operands are written by the pre-pass launch before this one
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         int tile_m, tile_n;
         decode_tile(t, tile_m, tile_n);
@@ -220,6 +221,9 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
         const int64_t nb = static_cast<int64_t>(tile_n) * C::BN + ((warp - 2) >> 2) * 64;
         noise_prefetch<OutT, kCplx, 64>(p.ep, m, nb, nre, nim);
       }
+      // the first tile's noise does not depend on the pre-pass: it is generated while that launch
+      // drains (programmatic dependent launch); the row / column scales below do depend on it
+      ptx::grid_dep_wait();
       const int quarter = warp & 3;
       const int half = (warp - 2) >> 2;
       const int te = threadIdx.x - 64;                       // 0..255
@@ -310,13 +314,17 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
                       __half* __restrict__ wh_im, __nv_bfloat16* __restrict__ e,
                       float* __restrict__ isx, float* __restrict__ isw, int kl_kind,
                       float* __restrict__ kl_sum, KlWorkspace* __restrict__ kl_ws,
-                      int64_t kl_row0, int64_t kl_row1) {
+                      int64_t kl_row0, int64_t kl_row1, const float* __restrict__ w_mask) {
   constexpr int kCache = 2;                  // 8-element groups per thread kept in registers (K <= 4096)
   __shared__ float red[8];
   __shared__ double kl_sh[kKlThreads / 32];
   __shared__ bool kl_last;
   float kl_acc = 0.f;                        // KL penalty of the weight rows this thread converts
   const int tid = threadIdx.x;
+  // let the GEMM launch behind this one start its prologue (barriers, TMEM, first tile's noise) as
+  // soon as every block of this grid is running; it waits (griddepcontrol.wait) before it reads
+  // anything written here
+  ptx::grid_dep_launch();
   // x rows (pure streaming) and W rows (streaming + ~50 instructions of KL math per element)
   // alternate in the global row order and the grid size is odd, so every block -- and every SM
   // at any time -- works on a mix of the two instead of all x rows first and all W rows last
@@ -338,6 +346,9 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
     const bool has_var = q != nullptr;        // plain affine map: no variance operands (fwd_lin3.cu)
     __nv_bfloat16* dv = has_var ? (is_x ? q : e) + r * K : nullptr;
     const float* pl = (is_x || !has_var) ? nullptr : ls2 + r * K;
+    // fixed-sparsity layers (nn/masked): W enters the GEMM as W * mask, applied here where every
+    // weight is read anyway (no materialised masked copy, no extra launch)
+    const float* pm = (is_x || w_mask == nullptr) ? nullptr : w_mask + r * K;
 
     if (pl != nullptr) {   // log_sigma2 is needed after the block-wide max: pull it towards L2 now
       for (int64_t k = static_cast<int64_t>(tid) * 32; k < K; k += 256 * 32)
@@ -359,6 +370,16 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
           ci[it][0] = b0.x, ci[it][1] = b0.y, ci[it][2] = b0.z, ci[it][3] = b0.w;
           ci[it][4] = b1.x, ci[it][5] = b1.y, ci[it][6] = b1.z, ci[it][7] = b1.w;
         }
+        if (pm != nullptr) {
+          const float4 m0 = __ldg(reinterpret_cast<const float4*>(pm + k));
+          const float4 m1 = __ldg(reinterpret_cast<const float4*>(pm + k + 4));
+          const float mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            cr[it][j] *= mk[j];
+            if constexpr (kCplx) ci[it][j] *= mk[j];
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           amax = fmaxf(amax, fabsf(cr[it][j]));
@@ -369,10 +390,14 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
     for (int64_t k = (static_cast<int64_t>(kCache) * 256 + tid) * 8; k < K; k += 2048) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(pr + k + 4 * h));
+        float4 a = __ldg(reinterpret_cast<const float4*>(pr + k + 4 * h));
+        float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (pm != nullptr) m = __ldg(reinterpret_cast<const float4*>(pm + k + 4 * h));
+        a.x *= m.x, a.y *= m.y, a.z *= m.z, a.w *= m.w;
         amax = fmaxf(fmaxf(amax, fmaxf(fabsf(a.x), fabsf(a.y))), fmaxf(fabsf(a.z), fabsf(a.w)));
         if constexpr (kCplx) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(pi + k + 4 * h));
+          float4 b = __ldg(reinterpret_cast<const float4*>(pi + k + 4 * h));
+          b.x *= m.x, b.y *= m.y, b.z *= m.z, b.w *= m.w;
           amax = fmaxf(fmaxf(amax, fmaxf(fabsf(b.x), fabsf(b.y))), fmaxf(fabsf(b.z), fabsf(b.w)));
         }
       }
@@ -437,10 +462,15 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
       float vr[8], vi[8];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(pr + k + 4 * h));
-        vr[4 * h] = a.x, vr[4 * h + 1] = a.y, vr[4 * h + 2] = a.z, vr[4 * h + 3] = a.w;
+        float4 a = __ldg(reinterpret_cast<const float4*>(pr + k + 4 * h));
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if constexpr (kCplx) b = __ldg(reinterpret_cast<const float4*>(pi + k + 4 * h));
+        if (pm != nullptr) {
+          const float4 m = __ldg(reinterpret_cast<const float4*>(pm + k + 4 * h));
+          a.x *= m.x, a.y *= m.y, a.z *= m.z, a.w *= m.w;
+          b.x *= m.x, b.y *= m.y, b.z *= m.z, b.w *= m.w;
+        }
+        vr[4 * h] = a.x, vr[4 * h + 1] = a.y, vr[4 * h + 2] = a.z, vr[4 * h + 3] = a.w;
         vi[4 * h] = b.x, vi[4 * h + 1] = b.y, vi[4 * h + 2] = b.z, vi[4 * h + 3] = b.w;
       }
       emit(k, vr, vi);
@@ -458,6 +488,7 @@ struct Tc3Operands {
   const void *a_re, *a_im, *q, *b_re, *b_im, *e;   // 16-bit planes [M,K] / [N,K]
   const float *sx, *sw;
   bool f16;
+  bool after_prepass;   // the launch right before this one in the stream is vd_prepare_f16_kernel
 };
 
 template <typename OutT, bool kCplx>
@@ -497,9 +528,14 @@ static int launch_tc3(const Tc3Operands& o, int64_t M, int64_t N, int64_t K, con
   if (clusters > pairs) clusters = pairs;
   auto kern = fwd_tc3_kernel<OutT, kCplx>;
   CPLXK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  kern<<<static_cast<unsigned>(2 * clusters), C::THREADS, C::SMEM_BYTES, st>>>(
-      tm_xr, tm_xi, tm_q, tm_wr, tm_wi, tm_e, p);
-  CPLXK_CUDA_TRY(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters)), cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = (o.after_prepass && knobs().pdl) ? 1 : 0;
+  CPLXK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm_xr, tm_xi, tm_q, tm_wr, tm_wi, tm_e, p));
   return CPLXK_OK;
 }
 
@@ -521,7 +557,7 @@ bool fwd_tc3_supported(int dtype, int64_t M, int64_t N, int64_t K) {
 int vd_prepare_f16_launch(bool cplx, const void* x_re, const void* x_im, int64_t M, const void* w_re,
                           const void* w_im, const void* ls2, int64_t N, int64_t K, void* xh_re,
                           void* xh_im, void* q, void* wh_re, void* wh_im, void* e, float* isx,
-                          float* isw, const KlFuse& kl, cudaStream_t st) {
+                          float* isw, const KlFuse& kl, cudaStream_t st, const void* w_mask) {
   const int64_t rows = M + N;
   int sms = 148;
   int rc0 = current_device_sm_count(&sms);
@@ -538,11 +574,13 @@ int vd_prepare_f16_launch(bool cplx, const void* x_re, const void* x_im, int64_t
   if (cplx)
     vd_prepare_f16_kernel<true><<<grid, 256, 0, st>>>(f(x_re), f(x_im), M, f(w_re), f(w_im), f(ls2), N, K,
                                                       h(xh_re), h(xh_im), b(q), h(wh_re), h(wh_im), b(e),
-                                                      isx, isw, kl_kind, kl.sum, kws, kl_row0, kl_row1);
+                                                      isx, isw, kl_kind, kl.sum, kws, kl_row0, kl_row1,
+                                                      f(w_mask));
   else
     vd_prepare_f16_kernel<false><<<grid, 256, 0, st>>>(f(x_re), nullptr, M, f(w_re), nullptr, f(ls2), N, K,
                                                        h(xh_re), nullptr, b(q), h(wh_re), nullptr, b(e),
-                                                       isx, isw, kl_kind, kl.sum, kws, kl_row0, kl_row1);
+                                                       isx, isw, kl_kind, kl.sum, kws, kl_row0, kl_row1,
+                                                       f(w_mask));
   CPLXK_CUDA_TRY(cudaGetLastError());
   return CPLXK_OK;
 }
@@ -562,12 +600,12 @@ int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re,
   float* isx = reinterpret_cast<float*>(ws + 3 * xb + 3 * wb);
   float* isw = reinterpret_cast<float*>(ws + 3 * xb + 3 * wb + align256(static_cast<size_t>(M) * 4));
   int rc = vd_prepare_f16_launch(cplx, x_re, x_im, M, w_re, w_im, ls2, N, K, xh_re, xh_im, q, wh_re,
-                                 wh_im, e, isx, isw, kl, st);
+                                 wh_im, e, isx, isw, kl, st, nullptr);
   if (rc) return rc;
   // the KL (partial) sum is final here: let a collective on another stream start under the GEMM
   if (kl.event) CPLXK_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(kl.event), st));
   if (!ep.y_re) return CPLXK_OK;   // cplxk_linear_vd_prepare: operands (and the KL sum) only
-  Tc3Operands o{xh_re, xh_im, q, wh_re, wh_im, e, isx, isw, true};
+  Tc3Operands o{xh_re, xh_im, q, wh_re, wh_im, e, isx, isw, true, kl.event == nullptr};
   return cplx ? launch_tc3<float, true>(o, M, N, K, ep, st) : launch_tc3<float, false>(o, M, N, K, ep, st);
 }
 
@@ -575,7 +613,7 @@ int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re,
 int fwd_tc3_bf16(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                  const void* q, const void* e, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
                  cudaStream_t st) {
-  Tc3Operands o{x_re, x_im, q, w_re, w_im, e, nullptr, nullptr, false};
+  Tc3Operands o{x_re, x_im, q, w_re, w_im, e, nullptr, nullptr, false, false};
   return cplx ? launch_tc3<__nv_bfloat16, true>(o, M, N, K, ep, st)
               : launch_tc3<__nv_bfloat16, false>(o, M, N, K, ep, st);
 }

@@ -18,7 +18,7 @@ template <typename T, int kKind, bool kVecOK>
 __global__ void __launch_bounds__(kKlThreads)
 kl_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T* __restrict__ ls2,
           int64_t n, T* __restrict__ out_elem, float* __restrict__ out_sum, double scale,
-          KlWorkspace* __restrict__ ws) {
+          KlWorkspace* __restrict__ ws, T* __restrict__ out_mask, float threshold) {
   constexpr bool kCplx = kl_kind_is_cplx(kKind);
   constexpr int V = Elem<T>::kVec;
   __shared__ double sh[kKlThreads / 32];
@@ -52,6 +52,12 @@ kl_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T* __res
         o.v[j] = p;
       }
       if (out_elem) o.store(out_elem + i * V);
+      if (out_mask) {   // relevance mask (log_alpha <= threshold) from the same loads
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          o.v[j] = log_alpha_of<kKind>(a0.v[j], kCplx ? b0.v[j] : 0.f, c0.v[j]) <= threshold ? 1.f : 0.f;
+        o.store(out_mask + i * V);
+      }
       if (has2) {
 #pragma unroll
         for (int j = 0; j < V; ++j) {
@@ -60,6 +66,12 @@ kl_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T* __res
           o.v[j] = p;
         }
         if (out_elem) o.store(out_elem + i2 * V);
+        if (out_mask) {
+#pragma unroll
+          for (int j = 0; j < V; ++j)
+            o.v[j] = log_alpha_of<kKind>(a1.v[j], kCplx ? b1.v[j] : 0.f, c1.v[j]) <= threshold ? 1.f : 0.f;
+          o.store(out_mask + i2 * V);
+        }
       }
     }
     done = nvec * V;
@@ -70,6 +82,8 @@ kl_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T* __res
     float p = penalty_of<kKind>(wr, wi, Elem<T>::to_f(ls2[i]));
     acc += p;
     if (out_elem) out_elem[i] = Elem<T>::from_f(p);
+    if (out_mask)
+      out_mask[i] = Elem<T>::from_f(log_alpha_of<kKind>(wr, wi, Elem<T>::to_f(ls2[i])) <= threshold ? 1.f : 0.f);
   }
 
   if (out_sum == nullptr) return;
@@ -122,10 +136,13 @@ static int sm_count_cached() {   // per device (knobs.cuh); 148 if the query fai
 
 template <typename T, int kKind>
 static int launch_kl(const void* w_re, const void* w_im, const void* ls2, int64_t n, void* out_elem,
-                     float* out_sum, double scale, KlWorkspace* ws, cudaStream_t st) {
+                     float* out_sum, double scale, KlWorkspace* ws, cudaStream_t st,
+                     void* out_mask = nullptr, float threshold = 0.f) {
   constexpr int V = Elem<T>::kVec;
   const bool vec_ok = aligned16(w_re) && aligned16(ls2) && (w_im == nullptr || aligned16(w_im)) &&
-                      (out_elem == nullptr || aligned16(out_elem));
+                      (out_elem == nullptr || aligned16(out_elem)) &&
+                      (out_mask == nullptr || aligned16(out_mask));
+  auto mk = static_cast<T*>(out_mask);
   int64_t work = (n + V - 1) / V;
   int64_t want = (work + 2 * kKlThreads - 1) / (2 * kKlThreads);
   int grid = static_cast<int>(want < 1 ? 1 : (want > 8 * sm_count_cached() ? 8 * sm_count_cached() : want));
@@ -135,9 +152,9 @@ static int launch_kl(const void* w_re, const void* w_im, const void* ls2, int64_
   auto c = static_cast<const T*>(ls2);
   auto o = static_cast<T*>(out_elem);
   if (vec_ok)
-    kl_kernel<T, kKind, true><<<grid, kKlThreads, 0, st>>>(a, b, c, n, o, out_sum, scale, ws);
+    kl_kernel<T, kKind, true><<<grid, kKlThreads, 0, st>>>(a, b, c, n, o, out_sum, scale, ws, mk, threshold);
   else
-    kl_kernel<T, kKind, false><<<grid, kKlThreads, 0, st>>>(a, b, c, n, o, out_sum, scale, ws);
+    kl_kernel<T, kKind, false><<<grid, kKlThreads, 0, st>>>(a, b, c, n, o, out_sum, scale, ws, mk, threshold);
   CPLXK_CUDA_TRY(cudaGetLastError());
   return CPLXK_OK;
 }
@@ -145,20 +162,20 @@ static int launch_kl(const void* w_re, const void* w_im, const void* ls2, int64_
 template <typename T>
 static int dispatch_kl(int kind, const void* w_re, const void* w_im, const void* ls2, int64_t n,
                        void* out_elem, float* out_sum, double scale, KlWorkspace* ws,
-                       cudaStream_t st) {
+                       cudaStream_t st, void* out_mask = nullptr, float threshold = 0.f) {
   switch (kind) {
     case CPLXK_KL_REAL_VD:
-      return launch_kl<T, CPLXK_KL_REAL_VD>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st);
+      return launch_kl<T, CPLXK_KL_REAL_VD>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st, out_mask, threshold);
     case CPLXK_KL_REAL_ARD:
-      return launch_kl<T, CPLXK_KL_REAL_ARD>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st);
+      return launch_kl<T, CPLXK_KL_REAL_ARD>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st, out_mask, threshold);
     case CPLXK_KL_CPLX_VD:
-      return launch_kl<T, CPLXK_KL_CPLX_VD>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st);
+      return launch_kl<T, CPLXK_KL_CPLX_VD>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st, out_mask, threshold);
     case CPLXK_KL_CPLX_ARD:
-      return launch_kl<T, CPLXK_KL_CPLX_ARD>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st);
+      return launch_kl<T, CPLXK_KL_CPLX_ARD>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st, out_mask, threshold);
     case CPLXK_KL_CPLX_VD_APPROX:
-      return launch_kl<T, CPLXK_KL_CPLX_VD_APPROX>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st);
+      return launch_kl<T, CPLXK_KL_CPLX_VD_APPROX>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st, out_mask, threshold);
     case CPLXK_KL_CPLX_VD_SCALEFREE:
-      return launch_kl<T, CPLXK_KL_CPLX_VD_SCALEFREE>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st);
+      return launch_kl<T, CPLXK_KL_CPLX_VD_SCALEFREE>(w_re, w_im, ls2, n, out_elem, out_sum, scale, ws, st, out_mask, threshold);
   }
   return CPLXK_ERR_BADARG;
 }
@@ -169,14 +186,33 @@ using namespace cplxk;
 
 extern "C" size_t cplxk_kl_workspace_bytes(void) { return sizeof(KlWorkspace); }
 
+static int kl_entry(int kind, const void* w_re, const void* w_im, const void* log_sigma2, int64_t n,
+                    int dtype, void* out_elem, float* out_sum, double scale, void* workspace,
+                    size_t workspace_bytes, void* stream, void* out_mask, float threshold);
+
 extern "C" int cplxk_kl(int kind, const void* w_re, const void* w_im, const void* log_sigma2,
                         int64_t n, int dtype, void* out_elem, float* out_sum, double scale,
                         void* workspace, size_t workspace_bytes, void* stream) {
+  return kl_entry(kind, w_re, w_im, log_sigma2, n, dtype, out_elem, out_sum, scale, workspace,
+                  workspace_bytes, stream, nullptr, 0.f);
+}
+
+extern "C" int cplxk_kl_mask(int kind, const void* w_re, const void* w_im, const void* log_sigma2,
+                             int64_t n, int dtype, float threshold, void* out_mask, float* out_sum,
+                             double scale, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!out_mask && n != 0) return CPLXK_ERR_BADARG;
+  return kl_entry(kind, w_re, w_im, log_sigma2, n, dtype, nullptr, out_sum, scale, workspace,
+                  workspace_bytes, stream, out_mask, threshold);
+}
+
+static int kl_entry(int kind, const void* w_re, const void* w_im, const void* log_sigma2, int64_t n,
+                    int dtype, void* out_elem, float* out_sum, double scale, void* workspace,
+                    size_t workspace_bytes, void* stream, void* out_mask, float threshold) {
   if (n == 0) {  // empty layer: the sum of nothing
     if (out_sum) CPLXK_CUDA_TRY(cudaMemsetAsync(out_sum, 0, sizeof(float), static_cast<cudaStream_t>(stream)));
     return (kind < 0 || kind >= kKlKinds) ? CPLXK_ERR_BADARG : CPLXK_OK;
   }
-  if (!w_re || !log_sigma2 || n < 0 || (!out_elem && !out_sum)) return CPLXK_ERR_BADARG;
+  if (!w_re || !log_sigma2 || n < 0 || (!out_elem && !out_sum && !out_mask)) return CPLXK_ERR_BADARG;
   const bool cplx = kl_kind_is_cplx(kind);
   if (kind < 0 || kind >= kKlKinds || cplx != (w_im != nullptr)) return CPLXK_ERR_BADARG;
   if (out_sum) {
@@ -186,9 +222,10 @@ extern "C" int cplxk_kl(int kind, const void* w_re, const void* w_im, const void
   auto st = static_cast<cudaStream_t>(stream);
   auto ws = static_cast<KlWorkspace*>(workspace);
   if (dtype == CPLXK_F32)
-    return dispatch_kl<float>(kind, w_re, w_im, log_sigma2, n, out_elem, out_sum, scale, ws, st);
+    return dispatch_kl<float>(kind, w_re, w_im, log_sigma2, n, out_elem, out_sum, scale, ws, st, out_mask, threshold);
   if (dtype == CPLXK_BF16)
-    return dispatch_kl<__nv_bfloat16>(kind, w_re, w_im, log_sigma2, n, out_elem, out_sum, scale, ws, st);
+    return dispatch_kl<__nv_bfloat16>(kind, w_re, w_im, log_sigma2, n, out_elem, out_sum, scale, ws, st, out_mask,
+                                      threshold);
   return CPLXK_ERR_BADARG;
 }
 

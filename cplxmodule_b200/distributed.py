@@ -46,9 +46,38 @@ def _default_partial(mod, lo, hi, stream=None):
                   mod.log_sigma2[lo:hi], "sum").float()
 
 
-def sharded_penalties(module, group=None, partial_fn=None, stream=None):
+class _AllReduceSum(torch.autograd.Function):
+    """SUM all-reduce of the per-layer partial KL sums whose backward hands every rank's partial
+    ``grad_scale`` times the upstream gradient.
+
+    KL = sum over ranks of partial_r and rank r only differentiates ITS rows, so after the
+    backward the gradient of the KL term lives on rank r for rows of r and is zero elsewhere; the
+    data-parallel gradient reduction then puts it together.  With a MEAN reduction (DDP's
+    default) each rank must contribute ``world`` times its part for the mean over ranks to be the
+    full KL gradient (``grad_reduce="mean"`` -> ``grad_scale = world``); with a SUM reduction
+    ``grad_scale = 1``.  ``dist.all_reduce`` itself has no autograd formula: called directly it
+    would silently give every rank the gradient of its own rows only."""
+
+    @staticmethod
+    def forward(ctx, vec, group, grad_scale):
+        ctx.grad_scale = grad_scale
+        out = vec.detach().clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        return grad * ctx.grad_scale, None, None
+
+
+def sharded_penalties(module, group=None, partial_fn=None, stream=None, grad_reduce="mean"):
     """``sum``-reduced penalties of every variational layer, each computed on this rank's row
     shard and combined with a single all-reduce.  Returns ``(names, tensor[n_layers])``.
+
+    Differentiable: ``loss = nll + klw * sharded_penalties(model)[1].sum()`` trains correctly
+    under data parallelism when ``grad_reduce`` names how the gradients of the replicas are
+    combined afterwards -- ``"mean"`` (``DistributedDataParallel``'s default averaging) or
+    ``"sum"``; see ``_AllReduceSum``.
 
     ``partial_fn(mod, lo, hi) -> 0-d tensor`` overrides the shard kernel (tests use it to
     exercise the sharding logic on CPU/gloo).  ``stream``: the (current) side stream the call is
@@ -69,5 +98,10 @@ def sharded_penalties(module, group=None, partial_fn=None, stream=None):
         return names, torch.zeros(0)
     vec = torch.stack(parts)
     if world > 1:
-        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+        if grad_reduce not in ("mean", "sum"):
+            raise ValueError("grad_reduce must be 'mean' (DDP averaging) or 'sum'")
+        if torch.is_grad_enabled() and vec.requires_grad:
+            vec = _AllReduceSum.apply(vec, group, float(world) if grad_reduce == "mean" else 1.0)
+        else:
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
     return names, vec

@@ -1,13 +1,16 @@
 """Fixed-sparsity ("masked") layers: the third stage of the reference's
 dense -> variational -> masked pipeline (``cplxmodule/nn/masked/{base,real,complex}.py``,
-``nn/relevance/README.md:77-89``).  The forward is the accelerated linear / conv kernel on
-``weight * mask``; masks arrive from ``relevance.compute_ard_masks`` through ``deploy_masks``
-or ``load_state_dict(..., strict=False)`` under the key ``<layer>.mask``."""
+``nn/relevance/README.md:77-89``).  Linear layers: ONE C-ABI call in which the mask is applied
+where the weights are staged for the GEMM (``cplxk_linear_masked_fwd``: inside the operand
+pre-pass on the fp32 tensor-core path -- no ``weight * mask`` tensor exists).  Conv / bilinear
+layers: the accelerated kernel on ``weight * mask`` (their weights are a few KB).  Masks arrive
+from ``relevance.compute_ard_masks`` through ``deploy_masks`` or
+``load_state_dict(..., strict=False)`` under the key ``<layer>.mask``."""
 import torch
 
-from .. import cplx, ops
+from .. import conv_ops, cplx, ops
 from .modules.conv import CplxConv1d, CplxConv2d
-from .modules.linear import CplxLinear
+from .modules.linear import CplxBilinear, CplxLinear
 
 
 class BaseMasked(torch.nn.Module):
@@ -82,12 +85,53 @@ class MaskedWeightMixin:
 
 class LinearMasked(MaskedWeightMixin, torch.nn.Linear, BaseMasked):
     def forward(self, input):
-        return ops.real_linear(input, self._effective_weight(), self.bias)
+        if not self.is_sparse:
+            return ops.real_linear(input, self.weight, self.bias)
+        return ops.real_linear_masked(input, self.weight, self.mask, self.bias)
 
 
 class CplxLinearMasked(MaskedWeightMixin, CplxLinear, BaseMasked):
     def forward(self, input):
-        return cplx.linear(input, self._effective_weight(), self.bias)
+        if not self.is_sparse:
+            return cplx.linear(input, self.weight, self.bias)
+        w, b = self.weight, self.bias
+        b_re, b_im = (None, None) if b is None else (b.real, b.imag)
+        re, im = ops.cplx_linear_masked(input.real, input.imag, w.real, w.imag, self.mask, b_re, b_im)
+        return cplx.Cplx(re, im)
+
+
+class BilinearMasked(MaskedWeightMixin, torch.nn.Bilinear, BaseMasked):
+    """nn/masked/real.py:69-72"""
+
+    def forward(self, input1, input2):
+        return ops.real_bilinear(input1, input2, self._effective_weight(), self.bias)
+
+
+class CplxBilinearMasked(MaskedWeightMixin, CplxBilinear, BaseMasked):
+    """nn/masked/complex.py:38-40"""
+
+    def forward(self, input1, input2):
+        return cplx.bilinear(input1, input2, self._effective_weight(), self.bias, self.conjugate)
+
+
+class _RealConvMasked(MaskedWeightMixin):
+    _nd = None
+
+    def forward(self, input):
+        if isinstance(self.padding, str) or self.padding_mode != "zeros":
+            raise ValueError("only numeric zero padding is supported by the CUDA conv path")
+        return conv_ops.real_convnd(self._nd, input, self._effective_weight(), self.bias, self.stride,
+                                    self.padding, self.dilation, self.groups)
+
+
+class Conv1dMasked(_RealConvMasked, torch.nn.Conv1d, BaseMasked):
+    """nn/masked/real.py:30-40"""
+    _nd = 1
+
+
+class Conv2dMasked(_RealConvMasked, torch.nn.Conv2d, BaseMasked):
+    """nn/masked/real.py:43-53"""
+    _nd = 2
 
 
 class CplxConv1dMasked(MaskedWeightMixin, CplxConv1d, BaseMasked):

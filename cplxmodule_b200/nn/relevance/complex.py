@@ -10,7 +10,7 @@ import torch
 from ... import _native as nv
 from ... import cplx, ops
 from ..modules.conv import CplxConv1d, CplxConv2d
-from ..modules.linear import CplxLinear
+from ..modules.linear import CplxBilinear, CplxLinear
 from .base import BaseARD
 
 
@@ -76,13 +76,44 @@ class CplxLinearGaussian(_CplxGaussianMixin, CplxLinear):
         return cplx.Cplx(re, im)
 
 
+class CplxBilinearGaussian(_CplxGaussianMixin, CplxBilinear):
+    """Complex bilinear layer with the fused local-reparameterisation forward
+    (``nn/relevance/complex/base.py:59-84``): ``s2 = bilinear(|x1|^2, |x2|^2, exp(log_sigma2))`` is
+    the variance GEMM of the linear kernel on the outer-product features."""
+
+    def __init__(self, in1_features, in2_features, out_features, bias=True, conjugate=True):
+        super().__init__(in1_features, in2_features, out_features, bias=bias, conjugate=conjugate)
+        self.log_sigma2 = torch.nn.Parameter(torch.empty(*self.weight.shape))
+        self.reset_variational_parameters()
+
+    def forward(self, input1, input2, eps=None):
+        if not self.training:
+            return super().forward(input1, input2)
+        w, b = self.weight, self.bias
+        b_re, b_im = (None, None) if b is None else (b.real, b.imag)
+        eps = None if eps is None else (eps.real, eps.imag)
+        re, im = ops.cplx_bilinear(input1.real, input1.imag, input2.real, input2.imag, w.real, w.imag,
+                                   b_re, b_im, self.conjugate, log_sigma2=self.log_sigma2, eps=eps)
+        return cplx.Cplx(re, im)
+
+
+# class hierarchy as in the reference (complex/vd.py:102-126, complex/ard.py:42-74): the ARD
+# layers ARE VD layers with another penalty, so `isinstance(layer, CplxLinearVD)` behaves alike
 class CplxLinearVD(CplxLinearGaussian, BaseARD):
     """Complex variational dropout with the exact KL divergence."""
     _kl_kind = nv.KL_CPLX_VD
 
 
-class CplxLinearARD(CplxLinearGaussian, BaseARD):
+class CplxLinearARD(CplxLinearVD):
     """Complex ARD: ``softplus(-log_alpha)``."""
+    _kl_kind = nv.KL_CPLX_ARD
+
+
+class CplxBilinearVD(CplxBilinearGaussian, BaseARD):
+    _kl_kind = nv.KL_CPLX_VD
+
+
+class CplxBilinearARD(CplxBilinearVD):
     _kl_kind = nv.KL_CPLX_ARD
 
 
@@ -113,9 +144,18 @@ class CplxConv2dVD(_CplxConvGaussianMixin, CplxConv2d, BaseARD):
     _kl_kind = nv.KL_CPLX_VD
 
 
-class CplxConv1dARD(_CplxConvGaussianMixin, CplxConv1d, BaseARD):
+class CplxConv1dARD(CplxConv1dVD):
     _kl_kind = nv.KL_CPLX_ARD
 
 
-class CplxConv2dARD(_CplxConvGaussianMixin, CplxConv2d, BaseARD):
+class CplxConv2dARD(CplxConv2dVD):
     _kl_kind = nv.KL_CPLX_ARD
+
+
+# the reference's `*Gaussian` names (complex/base.py:138-149)
+class CplxConv1dGaussian(_CplxConvGaussianMixin, CplxConv1d):
+    pass
+
+
+class CplxConv2dGaussian(_CplxConvGaussianMixin, CplxConv2d):
+    pass

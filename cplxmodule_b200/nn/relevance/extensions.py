@@ -2,35 +2,63 @@
 
 Reference: ``cplxmodule/nn/relevance/extensions/complex.py``: ``*VDApprox`` (softplus-sigmoid
 fit, :77-100) and ``*VDScaleFree`` (exact KL against the scale-free prior, :18-44).  Same
-forward as the ``*VD`` layers; the penalty is one more ``kind`` of the KL kernels (so it is
-also fused into the forward's operand pre-pass).  ``*VDBogus`` (:143-163) only exists in the
-reference to dodge its host-side ``Ei``; with the device-side ``Ei`` it has no purpose here.
+forward as the ``*VD`` layers -- of which they are SUBCLASSES, as in the reference (:47-141) --
+with one more ``kind`` of the KL kernels (so the penalty is also fused into the forward's
+operand pre-pass).
+
+``*VDBogus`` (:143-198) exists in the reference only to dodge its host-side ``Ei``: its penalty
+has the CORRECT gradient but a deliberately bogus forward value (``Ei`` replaced by zeros).
+With the device-side ``Ei`` there is nothing to dodge: the names are kept, for checkpoints and
+``isinstance`` checks, as plain subclasses of the exact ``*VD`` layers -- same gradient as the
+reference's, and the true penalty value instead of the bogus one.
 """
 from ... import _native as nv
-from .base import BaseARD
-from .complex import CplxLinearGaussian, _CplxConvGaussianMixin
-from ..modules.conv import CplxConv1d, CplxConv2d
+from .complex import CplxBilinearVD, CplxConv1dVD, CplxConv2dVD, CplxLinearVD
 
 
-class CplxLinearVDApprox(CplxLinearGaussian, BaseARD):
+class CplxLinearVDApprox(CplxLinearVD):
     _kl_kind = nv.KL_CPLX_VD_APPROX
 
 
-class CplxLinearVDScaleFree(CplxLinearGaussian, BaseARD):
-    _kl_kind = nv.KL_CPLX_VD_SCALEFREE
-
-
-class CplxConv1dVDApprox(_CplxConvGaussianMixin, CplxConv1d, BaseARD):
+class CplxBilinearVDApprox(CplxBilinearVD):
     _kl_kind = nv.KL_CPLX_VD_APPROX
 
 
-class CplxConv2dVDApprox(_CplxConvGaussianMixin, CplxConv2d, BaseARD):
+class CplxConv1dVDApprox(CplxConv1dVD):
     _kl_kind = nv.KL_CPLX_VD_APPROX
 
 
-class CplxConv1dVDScaleFree(_CplxConvGaussianMixin, CplxConv1d, BaseARD):
+class CplxConv2dVDApprox(CplxConv2dVD):
+    _kl_kind = nv.KL_CPLX_VD_APPROX
+
+
+class CplxLinearVDScaleFree(CplxLinearVD):
     _kl_kind = nv.KL_CPLX_VD_SCALEFREE
 
 
-class CplxConv2dVDScaleFree(_CplxConvGaussianMixin, CplxConv2d, BaseARD):
+class CplxBilinearVDScaleFree(CplxBilinearVD):
     _kl_kind = nv.KL_CPLX_VD_SCALEFREE
+
+
+class CplxConv1dVDScaleFree(CplxConv1dVD):
+    _kl_kind = nv.KL_CPLX_VD_SCALEFREE
+
+
+class CplxConv2dVDScaleFree(CplxConv2dVD):
+    _kl_kind = nv.KL_CPLX_VD_SCALEFREE
+
+
+class CplxLinearVDBogus(CplxLinearVD):
+    pass
+
+
+class CplxBilinearVDBogus(CplxBilinearVD):
+    pass
+
+
+class CplxConv1dVDBogus(CplxConv1dVD):
+    pass
+
+
+class CplxConv2dVDBogus(CplxConv2dVD):
+    pass

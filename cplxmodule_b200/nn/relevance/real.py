@@ -64,13 +64,69 @@ class _RealGaussianLinear(torch.nn.Linear):
         return [(id(self.weight), self.weight.numel() - n_relevant)]
 
 
+LinearGaussian = _RealGaussianLinear      # the reference's name (real/base.py:29)
+
+
+# class hierarchy as in the reference (real/vd.py:79-127, real/ard.py:42-66): ARD layers are
+# VD layers with another penalty
 class LinearVD(_RealGaussianLinear, BaseARD):
     """Variational dropout, softplus-sigmoid KL approximation of arXiv:1701.05369."""
     _kl_kind = nv.KL_REAL_VD
 
 
-class LinearARD(_RealGaussianLinear, BaseARD):
+class LinearARD(LinearVD):
     """Automatic relevance determination: ``0.5 * softplus(-log_alpha)``."""
+    _kl_kind = nv.KL_REAL_ARD
+
+
+class BilinearGaussian(torch.nn.Bilinear):
+    """``torch.nn.Bilinear`` with the local-reparameterisation forward (real/base.py:52-80):
+    an outer-product kernel, then the fused linear kernel on ``[.., in1 * in2]`` features with
+    the weight viewed as ``[out, in1 * in2]``."""
+
+    _kl_kind = None
+    __sparsity_ignore__ = ("log_sigma2",)
+
+    def __init__(self, in1_features, in2_features, out_features, bias=True):
+        super().__init__(in1_features, in2_features, out_features, bias=bias)
+        self.log_sigma2 = torch.nn.Parameter(torch.empty(*self.weight.shape))
+        self.reset_variational_parameters()
+
+    def reset_variational_parameters(self):
+        self.log_sigma2.data.fill_(-10.0)
+
+    def forward(self, input1, input2, eps=None):
+        ls2 = self.log_sigma2 if self.training else None
+        return ops.real_bilinear(input1, input2, self.weight, self.bias, log_sigma2=ls2,
+                                 eps=eps if self.training else None)
+
+    @property
+    def log_alpha(self):
+        return ops.log_alpha(self.weight, None, self.log_sigma2)
+
+    @property
+    def penalty(self):
+        return ops.kl(self._kl_kind, self.weight, None, self.log_sigma2, None)
+
+    def _penalty_reduced(self, reduction):
+        return ops.kl(self._kl_kind, self.weight, None, self.log_sigma2, reduction)
+
+    def relevance(self, *, threshold, **kwargs):
+        with torch.no_grad():
+            return ops.log_alpha(self.weight, None, self.log_sigma2, threshold=threshold)
+
+    def sparsity(self, *, threshold, **kwargs):
+        n_relevant = float(self.relevance(threshold=threshold).sum().item())
+        return [(id(self.weight), self.weight.numel() - n_relevant)]
+
+
+class BilinearVD(BilinearGaussian, BaseARD):
+    """Bilinear layer with variational dropout (real/vd.py:90-98)."""
+    _kl_kind = nv.KL_REAL_VD
+
+
+class BilinearARD(BilinearVD):
+    """Bilinear layer with automatic relevance determination (real/ard.py:66-69)."""
     _kl_kind = nv.KL_REAL_ARD
 
 
@@ -125,21 +181,31 @@ class _RealGaussianConvNd:
         return [(id(self.weight), self.weight.numel() - n_relevant)]
 
 
-class Conv1dVD(_RealGaussianConvNd, torch.nn.Conv1d, BaseARD):
+class Conv1dGaussian(_RealGaussianConvNd, torch.nn.Conv1d):
+    """real/base.py:166-177"""
+    _nd = 1
+
+
+class Conv2dGaussian(_RealGaussianConvNd, torch.nn.Conv2d):
+    """real/base.py:180-191"""
+    _nd = 2
+
+
+class Conv1dVD(Conv1dGaussian, BaseARD):
     """1D convolution with variational dropout (nn/relevance/real/vd.py:103-113)."""
-    _kl_kind, _nd = nv.KL_REAL_VD, 1
+    _kl_kind = nv.KL_REAL_VD
 
 
-class Conv2dVD(_RealGaussianConvNd, torch.nn.Conv2d, BaseARD):
+class Conv2dVD(Conv2dGaussian, BaseARD):
     """2D convolution with variational dropout (nn/relevance/real/vd.py:115-125)."""
-    _kl_kind, _nd = nv.KL_REAL_VD, 2
+    _kl_kind = nv.KL_REAL_VD
 
 
-class Conv1dARD(_RealGaussianConvNd, torch.nn.Conv1d, BaseARD):
+class Conv1dARD(Conv1dVD):
     """1D convolution with automatic relevance determination (nn/relevance/real/ard.py:48-51)."""
-    _kl_kind, _nd = nv.KL_REAL_ARD, 1
+    _kl_kind = nv.KL_REAL_ARD
 
 
-class Conv2dARD(_RealGaussianConvNd, torch.nn.Conv2d, BaseARD):
+class Conv2dARD(Conv2dVD):
     """2D convolution with automatic relevance determination (nn/relevance/real/ard.py:54-57)."""
-    _kl_kind, _nd = nv.KL_REAL_ARD, 2
+    _kl_kind = nv.KL_REAL_ARD

@@ -133,7 +133,7 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
             if _state["prepare"] and math != nv.MATH_SIMT:
                 ws_bytes = lib.cplxk_linear_workspace_bytes(M, N, K, code)
             if ws_bytes:
-                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                ws = nv.workspace(dev, ws_bytes)
                 nv.check(lib.cplxk_linear_fwd_ws(nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi),
                                                  nv.ptr(br), nv.ptr(bi), nv.ptr(y_re), nv.ptr(y_im),
                                                  M, N, K, code, math, nv.ptr(ws), ws_bytes, st))
@@ -153,7 +153,7 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
             ws, ws_bytes = None, 0
             if _state["prepare"] and math != nv.MATH_SIMT:
                 ws_bytes = lib.cplxk_linear_vd_workspace_bytes(M, N, K, code)
-                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                ws = nv.workspace(dev, ws_bytes)
             s2 = torch.empty((M, N), dtype=dt, device=dev) if want_s2 else None
             if kl_req is not None and ws is not None and _state["fuse_kl"]:
                 kl_sum = torch.empty((), dtype=torch.float32, device=dev)
@@ -187,8 +187,49 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
     return y_re, y_im, aux
 
 
+def _masked_forward_raw(x_re, x_im, w_re, w_im, mask, b_re, b_im):
+    """y = x (W * mask)^T + b in ONE C-ABI call (cplxk_linear_masked_fwd): on the fp32 tensor-core
+    path the mask is applied inside the operand pre-pass, nothing shaped like W is written."""
+    dev = nv.require_cuda(x_re, x_im, w_re, w_im, mask, b_re, b_im)
+    cplx = x_im is not None
+    dt = w_re.dtype
+    code = nv.dtype_code(dt)
+    N, K = w_re.shape
+    if x_re.shape[-1] != K:
+        raise RuntimeError(
+            f"size mismatch: input has {x_re.shape[-1]} features, weight is {tuple(w_re.shape)}")
+    lead = x_re.shape[:-1]
+    xr = _flat2d(x_re.to(dt), K)
+    xi = _flat2d(x_im.to(dt), K) if cplx else None
+    M = xr.shape[0]
+    wr, wi = nv.plane(w_re), nv.plane(w_im)
+    mk = nv.plane(mask.expand(N, K), dt)
+    br, bi = nv.plane(b_re, dt), nv.plane(b_im, dt)
+    y_re = torch.empty((M, N), dtype=dt, device=dev)
+    y_im = torch.empty((M, N), dtype=dt, device=dev) if cplx else None
+    lib = nv.lib()
+    math = _MATH[_state["math"]]
+    with torch.cuda.device(dev):
+        ws_bytes = lib.cplxk_linear_masked_workspace_bytes(M, N, K, code)
+        ws = nv.workspace(dev, ws_bytes)
+        nv.check(lib.cplxk_linear_masked_fwd(nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi), nv.ptr(mk),
+                                             nv.ptr(br), nv.ptr(bi), nv.ptr(y_re), nv.ptr(y_im),
+                                             M, N, K, code, math, nv.ptr(ws), ws_bytes,
+                                             nv.stream_ptr(dev)))
+    return y_re.reshape(*lead, N), (y_im.reshape(*lead, N) if cplx else None)
+
+
+def _guard(ctx, *tensors):
+    """Hand the ORIGINAL input tensors to autograd's version tracking (``save_for_backward``):
+    ``backward`` touches ``ctx.saved_tensors`` first, so an in-place update of an input or a
+    parameter between forward and backward raises torch's usual error instead of silently
+    differentiating changed values.  The planes the kernels read are views of these tensors
+    whenever no dtype conversion or densification was needed (no extra memory)."""
+    ctx.save_for_backward(*[t for t in tensors if isinstance(t, torch.Tensor)])
+
+
 # ------------------------------------------------------------------ backward helpers
-TR_COPY, TR_NEG, TR_EXP, TR_ABS2, TR_SQR = 0, 1, 2, 3, 4
+TR_COPY, TR_NEG, TR_EXP, TR_ABS2, TR_SQR, TR_MUL = 0, 1, 2, 3, 4, 5
 
 
 def _transpose(t, op=TR_COPY, t2=None):
@@ -314,12 +355,14 @@ class _CplxLinearFn(torch.autograd.Function):
     def forward(ctx, x_re, x_im, w_re, w_im, b_re, b_im):
         if any(ctx.needs_input_grad):
             _save_linear(ctx, x_re, x_im, w_re, w_im)
+            _guard(ctx, x_re, x_im, w_re, w_im)
         re, im, _ = _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, None, None, None, None)
         return re, im
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_re, g_im):
+        ctx.saved_tensors
         xr, xi, wr, wi = ctx.saved_planes
         N, K = wr.shape
         g_re, g_im = (_grad2d(g, ctx.lead, N, wr.dtype, wr.device) for g in (g_re, g_im))
@@ -335,11 +378,13 @@ class _RealLinearFn(torch.autograd.Function):
     def forward(ctx, x, w, b):
         if any(ctx.needs_input_grad):
             _save_linear(ctx, x, None, w, None)
+            _guard(ctx, x, w)
         return _forward_raw(x, None, w, None, b, None, None, None, None, None)[0]
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
+        ctx.saved_tensors
         xr, _, wr, _ = ctx.saved_planes
         N, K = wr.shape
         g = _grad2d(g, ctx.lead, N, wr.dtype, wr.device)
@@ -361,6 +406,7 @@ class _CplxLinearVDFn(torch.autograd.Function):
         need = any(ctx.needs_input_grad)
         if need:
             _save_linear(ctx, x_re, x_im, w_re, w_im)
+            _guard(ctx, x_re, x_im, w_re, w_im, log_sigma2, eps_re, eps_im)
         re, im, aux = _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
                                    noise, want_s2=need, kl_req=kl_req)
         if need:
@@ -370,6 +416,7 @@ class _CplxLinearVDFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_re, g_im):
+        ctx.saved_tensors
         xr, xi, wr, wi = ctx.saved_planes
         N, K = wr.shape
         g_re, g_im = (_grad2d(g, ctx.lead, N, wr.dtype, wr.device) for g in (g_re, g_im))
@@ -388,6 +435,7 @@ class _RealLinearVDFn(torch.autograd.Function):
         need = any(ctx.needs_input_grad)
         if need:
             _save_linear(ctx, x, None, w, None)
+            _guard(ctx, x, w, log_sigma2, eps)
         y, _, aux = _forward_raw(x, None, w, None, b, None, log_sigma2, eps, None, noise,
                                  want_s2=need, kl_req=kl_req)
         if need:
@@ -397,6 +445,7 @@ class _RealLinearVDFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
+        ctx.saved_tensors
         xr, _, wr, _ = ctx.saved_planes
         N, K = wr.shape
         g = _grad2d(g, ctx.lead, N, wr.dtype, wr.device)
@@ -413,6 +462,137 @@ def cplx_linear(x_re, x_im, w_re, w_im, b_re=None, b_im=None):
 
 def real_linear(x, w, b=None):
     return _RealLinearFn.apply(x, w, b)
+
+
+class _LinearMaskedFn(torch.autograd.Function):
+    """y = x (W * mask)^T + b; gradients: dx = g conj(W * mask), dW = (g^T conj(x)) * mask."""
+
+    @staticmethod
+    def forward(ctx, x_re, x_im, w_re, w_im, mask, b_re, b_im):
+        if any(ctx.needs_input_grad):
+            _save_linear(ctx, x_re, x_im, w_re, w_im)
+            ctx.mask = nv.plane(mask.expand(w_re.shape), w_re.dtype)
+            _guard(ctx, x_re, x_im, w_re, w_im, mask)
+        re, im = _masked_forward_raw(x_re, x_im, w_re, w_im, mask, b_re, b_im)
+        ctx.cplx = x_im is not None
+        return (re, im) if ctx.cplx else re
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *grads):
+        ctx.saved_tensors
+        xr, xi, wr, wi = ctx.saved_planes
+        N, K = wr.shape
+        g_re = _grad2d(grads[0], ctx.lead, N, wr.dtype, wr.device)
+        g_im = _grad2d(grads[1], ctx.lead, N, wr.dtype, wr.device) if ctx.cplx else None
+        n = ctx.needs_input_grad
+        mk = ctx.mask
+        # the masked weight only exists here, where a gradient w.r.t. the input is wanted
+        ctx.saved_planes = (xr, xi, _eltwise(TR_MUL, wr, mk), None if wi is None else _eltwise(TR_MUL, wi, mk))
+        dx_re, dx_im, dw_re, dw_im, db_re, db_im = _linear_backward(
+            ctx, g_re, g_im, n[0] or n[1], n[2] or n[3], n[5] or n[6])
+        if dw_re is not None:
+            dw_re = _eltwise(TR_MUL, dw_re, mk)
+            dw_im = None if dw_im is None else _eltwise(TR_MUL, dw_im, mk)
+        return (_shape_back(dx_re, ctx.lead, K, ctx.x_dtype), _shape_back(dx_im, ctx.lead, K, ctx.x_dtype),
+                dw_re, dw_im, None, db_re, db_im)
+
+
+def cplx_linear_masked(x_re, x_im, w_re, w_im, mask, b_re=None, b_im=None):
+    """Reference: CplxLinearMasked.forward = cplx.linear(input, weight * mask, bias)
+    (nn/masked/complex.py:33-35, nn/masked/base.py:135-149)."""
+    return _LinearMaskedFn.apply(x_re, x_im, w_re, w_im, mask, b_re, b_im)
+
+
+def real_linear_masked(x, w, mask, b=None):
+    """Reference: LinearMasked.forward = F.linear(input, weight * mask, bias) (nn/masked/real.py:25-27)."""
+    return _LinearMaskedFn.apply(x, None, w, None, mask, b, None)
+
+
+# ------------------------------------------------------------------------ bilinear
+class _OuterFn(torch.autograd.Function):
+    """z[..., p * d2 + q] = conj?(x1[..., p]) * x2[..., q]  (cplxk_outer_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, x1_re, x1_im, x2_re, x2_im, conjugate):
+        dev = nv.require_cuda(x1_re, x1_im, x2_re, x2_im)
+        cplx = x1_im is not None
+        dt = x1_re.dtype
+        code = nv.dtype_code(dt)
+        d1, d2 = x1_re.shape[-1], x2_re.shape[-1]
+        lead = torch.broadcast_shapes(x1_re.shape[:-1], x2_re.shape[:-1])
+        flat = lambda t, d: None if t is None else nv.plane(t.expand(*lead, d).reshape(-1, d), dt)
+        a_re, a_im, b_re, b_im = flat(x1_re, d1), flat(x1_im, d1), flat(x2_re, d2), flat(x2_im, d2)
+        B = a_re.shape[0]
+        z_re = torch.empty((B, d1 * d2), dtype=dt, device=dev)
+        z_im = torch.empty_like(z_re) if cplx else None
+        with torch.cuda.device(dev):
+            nv.check(nv.lib().cplxk_outer_fwd(nv.ptr(a_re), nv.ptr(a_im), nv.ptr(b_re), nv.ptr(b_im),
+                                              nv.ptr(z_re), nv.ptr(z_im), B, d1, d2,
+                                              1 if conjugate else 0, code, nv.stream_ptr(dev)))
+        if any(ctx.needs_input_grad):
+            ctx.planes = (a_re, a_im, b_re, b_im)
+            ctx.dims = (B, d1, d2, bool(conjugate), tuple(lead), tuple(x1_re.shape), tuple(x2_re.shape))
+            _guard(ctx, x1_re, x1_im, x2_re, x2_im)
+        ctx.cplx = cplx
+        z_re = z_re.reshape(*lead, d1 * d2)
+        return (z_re, z_im.reshape(*lead, d1 * d2)) if cplx else z_re
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *grads):
+        ctx.saved_tensors
+        a_re, a_im, b_re, b_im = ctx.planes
+        B, d1, d2, conj, lead, shp1, shp2 = ctx.dims
+        dev, dt = a_re.device, a_re.dtype
+        g_re = _grad2d(grads[0], lead, d1 * d2, dt, dev)
+        g_im = _grad2d(grads[1], lead, d1 * d2, dt, dev) if ctx.cplx else None
+        n = ctx.needs_input_grad
+        want1, want2 = n[0] or n[1], n[2] or n[3]
+        new = lambda d, want: torch.empty((B, d), dtype=dt, device=dev) if want else None
+        d1_re, d2_re = new(d1, want1), new(d2, want2)
+        d1_im = new(d1, want1) if ctx.cplx else None
+        d2_im = new(d2, want2) if ctx.cplx else None
+        with torch.cuda.device(dev):
+            nv.check(nv.lib().cplxk_outer_bwd(nv.ptr(g_re), nv.ptr(g_im), nv.ptr(a_re), nv.ptr(a_im),
+                                              nv.ptr(b_re), nv.ptr(b_im), nv.ptr(d1_re), nv.ptr(d1_im),
+                                              nv.ptr(d2_re), nv.ptr(d2_im), B, d1, d2, 1 if conj else 0,
+                                              nv.dtype_code(dt), nv.stream_ptr(dev)))
+
+        def back(t, d, shape):   # undo the broadcast of the leading dims
+            if t is None:
+                return None
+            t = t.reshape(*lead, d)
+            return t.sum_to_size(shape) if tuple(t.shape) != tuple(shape) else t
+        return (back(d1_re, d1, shp1), back(d1_im, d1, shp1), back(d2_re, d2, shp2),
+                back(d2_im, d2, shp2), None)
+
+
+def outer_features(x1_re, x1_im, x2_re, x2_im, conjugate=True):
+    return _OuterFn.apply(x1_re, x1_im, x2_re, x2_im, conjugate)
+
+
+def cplx_bilinear(x1_re, x1_im, x2_re, x2_im, w_re, w_im, b_re=None, b_im=None, conjugate=True,
+                  log_sigma2=None, eps=None, kl_req=None):
+    """y_j = x1^{H|T} A_j x2 + b_j (cplx.bilinear, cplxmodule/cplx.py:1062-1090) as the complex
+    affine map of the outer-product features; with ``log_sigma2`` the local-reparameterisation
+    forward of CplxBilinearGaussian (nn/relevance/complex/base.py:70-84)."""
+    O = w_re.shape[0]
+    z_re, z_im = outer_features(x1_re, x1_im, x2_re, x2_im, conjugate)
+    w2 = lambda t: t.reshape(O, -1)
+    if log_sigma2 is None:
+        return cplx_linear(z_re, z_im, w2(w_re), w2(w_im), b_re, b_im)
+    return cplx_linear_vd(z_re, z_im, w2(w_re), w2(w_im), b_re, b_im, w2(log_sigma2), eps=eps,
+                          kl_req=kl_req)
+
+
+def real_bilinear(x1, x2, w, b=None, log_sigma2=None, eps=None, kl_req=None):
+    """torch.nn.functional.bilinear / BilinearGaussian.forward (nn/relevance/real/base.py:52-80)."""
+    O = w.shape[0]
+    z = outer_features(x1, None, x2, None, False)
+    if log_sigma2 is None:
+        return real_linear(z, w.reshape(O, -1), b)
+    return real_linear_vd(z, w.reshape(O, -1), b, log_sigma2.reshape(O, -1), eps=eps, kl_req=kl_req)
 
 
 def _noise_args(eps):
@@ -499,6 +679,7 @@ class _KLFn(torch.autograd.Function):
             ctx.kind, ctx.reduction = kind, reduction
             ctx.planes = (nv.plane(w_re), nv.plane(w_im), nv.plane(log_sigma2, dt))
             ctx.shape = tuple(w_re.shape)
+            _guard(ctx, w_re, w_im, log_sigma2)
         if precomputed is not None and reduction in ("sum", "mean"):
             # [sum] from the forward's operand pre-pass (FusedKLCache); the list hides it from autograd
             out = precomputed[0]
@@ -510,6 +691,7 @@ class _KLFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad):
+        ctx.saved_tensors
         wr, wi, ls2 = ctx.planes
         dev, dt = wr.device, wr.dtype
         n = wr.numel()
@@ -535,9 +717,7 @@ def kl(kind, w_re, w_im, log_sigma2, reduction="sum", precomputed=None):
     return _KLFn.apply(kind, reduction, w_re, w_im, log_sigma2, pre)
 
 
-def log_alpha(w_re, w_im, log_sigma2, threshold=None):
-    """``log_sigma2 - 2 log(|w| + 1e-12)`` (nn/relevance/{real,complex}/base.py) or, with a
-    ``threshold``, the relevance mask ``(log_alpha <= threshold)`` as floats."""
+def _log_alpha_raw(w_re, w_im, log_sigma2, threshold=None):
     dev = nv.require_cuda(w_re, w_im, log_sigma2)
     dt = w_re.dtype
     code = nv.dtype_code(dt)
@@ -553,6 +733,61 @@ def log_alpha(w_re, w_im, log_sigma2, threshold=None):
             nv.check(lib.cplxk_log_alpha(nv.ptr(wr), nv.ptr(wi), nv.ptr(ls2), wr.numel(), code,
                                          None, float(threshold), nv.ptr(out), st))
     return out
+
+
+class _LogAlphaFn(torch.autograd.Function):
+    """log_alpha = log_sigma2 - log(|w|^2): d/d log_sigma2 = 1, d/d w = -2 w / |w|^2.  The
+    forward is the device kernel; the backward of this (off the hot path: user-defined
+    regularisers on ``layer.log_alpha``) is three elementwise torch ops and is itself
+    differentiable."""
+
+    @staticmethod
+    def forward(ctx, w_re, w_im, log_sigma2):
+        if any(ctx.needs_input_grad):
+            _guard(ctx, w_re, w_im, log_sigma2)
+            ctx.cplx = w_im is not None
+        return _log_alpha_raw(w_re, w_im, log_sigma2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        saved = ctx.saved_tensors
+        w_re, w_im = saved[0], (saved[1] if ctx.cplx else None)
+        # reference: ls2 - 2 log(|w| + 1e-12)  =>  d/dw = -2 w / (|w| (|w| + 1e-12)); the device
+        # kernel evaluates log(|w|^2 + 1e-24): same value and gradient wherever |w| >> 1e-12
+        r2 = w_re * w_re if w_im is None else w_re * w_re + w_im * w_im
+        k = -2.0 * grad / (r2 + 1e-24)
+        return k * w_re, (None if w_im is None else k * w_im), grad
+
+
+def log_alpha(w_re, w_im, log_sigma2, threshold=None):
+    """``log_sigma2 - 2 log(|w| + 1e-12)`` (nn/relevance/{real,complex}/base.py), differentiable in
+    the weights and ``log_sigma2`` like the reference's property; with a ``threshold`` the
+    relevance mask ``(log_alpha <= threshold)`` as floats (no graph, as in the reference)."""
+    if threshold is not None:
+        return _log_alpha_raw(w_re, w_im, log_sigma2, threshold)
+    return _LogAlphaFn.apply(w_re, w_im, log_sigma2)
+
+
+def kl_and_mask(kind, w_re, w_im, log_sigma2, threshold, reduction="sum"):
+    """(KL sum, relevance mask) of a layer from ONE pass over its parameters
+    (``cplxk_kl_mask``): what a sparsification schedule needs each time it logs the penalty and
+    re-derives the masks.  No autograd graph."""
+    dev = nv.require_cuda(w_re, w_im, log_sigma2)
+    dt = w_re.dtype
+    code = nv.dtype_code(dt)
+    wr, wi, ls2 = nv.plane(w_re), nv.plane(w_im), nv.plane(log_sigma2, dt)
+    n = wr.numel()
+    if reduction not in ("sum", "mean"):
+        raise ValueError(f"`reduction` must be `sum` or `mean`. Got {reduction}.")
+    mask = torch.empty_like(wr)
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = nv.kl_workspace(dev)
+        scale = 1.0 if reduction == "sum" else 1.0 / max(n, 1)
+        nv.check(nv.lib().cplxk_kl_mask(kind, nv.ptr(wr), nv.ptr(wi), nv.ptr(ls2), n, code,
+                                        float(threshold), nv.ptr(mask), nv.ptr(out), scale,
+                                        nv.ptr(ws), ws.numel() * 8, nv.stream_ptr(dev)))
+    return (out.to(dt) if dt != torch.float32 else out), mask
 
 
 def randn_philox_torch(n, seed, offset, threads, scale=1.0, device="cuda"):

@@ -126,6 +126,26 @@ int cplxk_linear_fwd_ws(const void* x_re, const void* x_im,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Affine map of a fixed-sparsity ("masked") layer:  y = x (W * mask)^T + b.
+ * Replaces CplxLinearMasked.forward / LinearMasked.forward, i.e.
+ * cplx.linear(input, self.weight_masked, self.bias) with weight_masked = weight * mask
+ * (nn/masked/complex.py:33-35, nn/masked/real.py:25-27, nn/masked/base.py:135-149).
+ *   mask : [N,K] plane of `dtype` (0/1 or soft), applied to BOTH weight planes.
+ * The mask is applied where the weights are staged for the GEMM: F32 planes on the tensor-core
+ * path multiply inside the operand pre-pass (no masked copy of W is ever written); every other
+ * path writes W * mask for both planes in ONE elementwise launch into the workspace and runs
+ * the ordinary kernels on that.  workspace: cplxk_linear_masked_workspace_bytes() bytes.
+ */
+size_t cplxk_linear_masked_workspace_bytes(int64_t M, int64_t N, int64_t K, int dtype);
+int cplxk_linear_masked_fwd(const void* x_re, const void* x_im,
+                            const void* w_re, const void* w_im, const void* mask,
+                            const void* b_re, const void* b_im,
+                            void* y_re, void* y_im,
+                            int64_t M, int64_t N, int64_t K,
+                            int dtype, int math,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Local-reparameterisation forward of a Gaussian (variational dropout) linear
  * layer, fused: mean GEMM(s), variance GEMM |x|^2 . exp(log_sigma2)^T, noise,
  * and  y = mu + eps * sqrt(max(s2, 1e-8)).
@@ -211,6 +231,25 @@ int cplxk_linear_vd_fwd_kl(const void* x_re, const void* x_im,
                            int* kl_done, void* stream);
 
 /*
+ * Outer-product features of the bilinear layers: z[b, p * d2 + q] = conj?(x1[b, p]) * x2[b, q].
+ * With them  cplx.bilinear(x1, x2, W, b, conjugate)  (cplxmodule/cplx.py:1062-1090; CplxBilinear,
+ * nn/modules/linear.py:67-117)  ==  cplxk_linear_fwd(z, W viewed as [out, d1 * d2], b), and the
+ * variance  F.bilinear(|x1|^2, |x2|^2, exp(log_sigma2))  of CplxBilinearGaussian.forward
+ * (nn/relevance/complex/base.py:70-84) is the variance GEMM of cplxk_linear_vd_fwd on the same z.
+ * Real layers (torch.nn.Bilinear, nn/relevance/real/base.py:52-80): x1_im == x2_im == z_im == NULL.
+ *   x1 : [B,d1]   x2 : [B,d2]   z : [B, d1*d2]
+ * cplxk_outer_bwd: gradients of a scalar loss through z given g = dL/dz (either output pair
+ * may be NULL).
+ */
+int cplxk_outer_fwd(const void* x1_re, const void* x1_im, const void* x2_re, const void* x2_im,
+                    void* z_re, void* z_im, int64_t B, int64_t d1, int64_t d2, int conjugate,
+                    int dtype, void* stream);
+int cplxk_outer_bwd(const void* g_re, const void* g_im, const void* x1_re, const void* x1_im,
+                    const void* x2_re, const void* x2_im, void* d1_re, void* d1_im, void* d2_re,
+                    void* d2_im, int64_t B, int64_t d1, int64_t d2, int conjugate, int dtype,
+                    void* stream);
+
+/*
  * KL penalty of a variational layer over n parameters, one HBM pass:
  *   log_alpha = log_sigma2 - 2 log(|w| + 1e-12)
  *     (nn/relevance/real/base.py:23-26, complex/base.py:27-31)
@@ -227,6 +266,18 @@ int cplxk_kl(int kind, const void* w_re, const void* w_im,
              const void* log_sigma2, int64_t n, int dtype,
              void* out_elem, float* out_sum, double scale,
              void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The KL sum AND the relevance mask (log_alpha <= threshold, as floats of `dtype`) of a layer
+ * from ONE pass over its parameters: what a sparsification schedule asks for every time it
+ * logs the penalty and re-derives the masks (named_penalties + compute_ard_masks,
+ * nn/relevance/base.py:88-141,192-216; RelevanceMixin.relevance, complex/vd.py:50-53).
+ * out_sum nullable (mask only); out_mask required.
+ */
+int cplxk_kl_mask(int kind, const void* w_re, const void* w_im,
+                  const void* log_sigma2, int64_t n, int dtype,
+                  float threshold, void* out_mask, float* out_sum, double scale,
+                  void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * log_alpha itself and the relevance mask  (log_alpha <= threshold)
@@ -281,8 +332,8 @@ int cplxk_conv2d_fwd(const void* x_re, const void* x_im,
 /* out[cols, rows] = op(in[rows, cols]); op: 0 copy, 1 negate, 2 exp, 3 in^2 + in2^2, 4 in^2 */
 int cplxk_transpose2d(const void* in, const void* in2, void* out, int64_t rows, int64_t cols,
                       int dtype, int op, void* stream);
-/* out = op(a [, b]) elementwise, same op codes, no transposition (conv backward: |x|^2,
- * exp(log_sigma2), conj) */
+/* out = op(a [, b]) elementwise, same op codes plus 5: a * b, no transposition (conv backward:
+ * |x|^2, exp(log_sigma2), conj; masked conv layers: weight * mask) */
 int cplxk_eltwise(int op, const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
 /* out[N] = sum over rows of g[M, N]  (bias gradient) */
 int cplxk_colsum(const void* g, void* out, int64_t M, int64_t N, int dtype, void* stream);

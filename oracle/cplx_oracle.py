@@ -56,6 +56,43 @@ def real_linear_vd(x, w, b, log_sigma2, eps):
     return mu + eps * torch.sqrt(torch.clamp(s2, 1e-8))
 
 
+# -------------------------------------------------------------------------- bilinear
+def cplx_bilinear(x1_re, x1_im, x2_re, x2_im, w_re, w_im, b_re=None, b_im=None, conjugate=True):
+    """cplx.bilinear == bilinear_naive, cplxmodule/cplx.py:1062-1090."""
+    n_out = int(w_re.shape[0])
+    ww = torch.cat([w_re, w_im], dim=0)
+    au, av = F.bilinear(x1_re, x2_re, ww, bias=None), F.bilinear(x1_re, x2_im, ww, bias=None)
+    bu, bv = F.bilinear(x1_im, x2_re, ww, bias=None), F.bilinear(x1_im, x2_im, ww, bias=None)
+    if conjugate:
+        pp, qq = au + bv, av - bu
+    else:
+        pp, qq = au - bv, av + bu
+    re = pp[..., :n_out] - qq[..., n_out:]
+    im = pp[..., n_out:] + qq[..., :n_out]
+    if b_re is not None:
+        re, im = re + b_re, im + b_im
+    return re, im
+
+
+def cplx_bilinear_vd(x1_re, x1_im, x2_re, x2_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
+                     conjugate=True):
+    """CplxBilinearGaussian.forward (training), nn/relevance/complex/base.py:70-84."""
+    mu_re, mu_im = cplx_bilinear(x1_re, x1_im, x2_re, x2_im, w_re, w_im, b_re, b_im, conjugate)
+    s2 = F.bilinear(x1_re * x1_re + x1_im * x1_im, x2_re * x2_re + x2_im * x2_im,
+                    torch.exp(log_sigma2), None)
+    sd = torch.sqrt(torch.clamp(s2, 1e-8))
+    return mu_re + eps_re * sd, mu_im + eps_im * sd
+
+
+def real_bilinear_vd(x1, x2, w, b, log_sigma2, eps):
+    """BilinearGaussian.forward (training), nn/relevance/real/base.py:66-80; eps=None: the mean."""
+    mu = F.bilinear(x1, x2, w, b)
+    if eps is None:
+        return mu
+    s2 = F.bilinear(x1 * x1, x2 * x2, torch.exp(log_sigma2), None)
+    return mu + eps * torch.sqrt(torch.clamp(s2, 1e-8))
+
+
 # ------------------------------------------------------------------------------ conv
 def cplx_conv2d(x_re, x_im, w_re, w_im, b_re=None, b_im=None, stride=1, padding=0, dilation=1):
     """cplx.conv2d -> convnd -> convnd_quick (groups == 1), cplxmodule/cplx.py:729-742,770-838."""

@@ -149,6 +149,7 @@ def main():
         penalty_sum=sum(penalties(cvd, reduction="sum")))))
     real_conv_fixtures()
     extension_fixtures()
+    bilinear_fixtures()
     print("golden fixtures written to", os.path.normpath(OUT))
 
 
@@ -207,8 +208,53 @@ def extension_fixtures():
     np.savez(os.path.join(OUT, "ext_penalties.npz"), **npy(out))
 
 
+def bilinear_fixtures():
+    """CplxBilinearVD (conjugate and not) / BilinearARD training forwards with captured noise
+    (cplx.py:1062-1090, nn/relevance/complex/base.py:59-84, real/base.py:52-80)."""
+    import_reference()
+    from cplxmodule import cplx
+    from cplxmodule.nn.relevance import BilinearARD, CplxBilinearVD, penalties
+    os.makedirs(OUT, exist_ok=True)
+    out = {}
+    for tag, conj, seed in (("conj", True, 1212), ("plain", False, 1313)):
+        torch.manual_seed(seed)
+        m = CplxBilinearVD(7, 10, 9, conjugate=conj).train()
+        with torch.no_grad():
+            m.log_sigma2.uniform_(-12, 2)
+        z1, z2 = cplx.randn(11, 7), cplx.randn(11, 10)
+        state = torch.get_rng_state()
+        y = m(z1, z2)
+        torch.set_rng_state(state)
+        eps = cplx.randn(11, 9)
+        m.eval()
+        mu = m(z1, z2)
+        out.update({f"{tag}_x1_re": z1.real, f"{tag}_x1_im": z1.imag, f"{tag}_x2_re": z2.real,
+                    f"{tag}_x2_im": z2.imag, f"{tag}_w_re": m.weight.real, f"{tag}_w_im": m.weight.imag,
+                    f"{tag}_b_re": m.bias.real, f"{tag}_b_im": m.bias.imag,
+                    f"{tag}_log_sigma2": m.log_sigma2, f"{tag}_eps_re": eps.real,
+                    f"{tag}_eps_im": eps.imag, f"{tag}_y_re": y.real, f"{tag}_y_im": y.imag,
+                    f"{tag}_mu_re": mu.real, f"{tag}_mu_im": mu.imag,
+                    f"{tag}_penalty_sum": sum(penalties(m, reduction="sum"))})
+    torch.manual_seed(1414)
+    m = BilinearARD(6, 5, 8).train()
+    with torch.no_grad():
+        m.log_sigma2.uniform_(-12, 2)
+    x1, x2 = torch.randn(13, 6), torch.randn(13, 5)
+    state = torch.get_rng_state()
+    y = m(x1, x2)
+    torch.set_rng_state(state)
+    eps = torch.randn_like(y)
+    m.eval()
+    out.update({"real_x1": x1, "real_x2": x2, "real_w": m.weight, "real_b": m.bias,
+                "real_log_sigma2": m.log_sigma2, "real_eps": eps, "real_y": y, "real_mu": m(x1, x2),
+                "real_penalty_sum": sum(penalties(m, reduction="sum"))})
+    np.savez(os.path.join(OUT, "bilinear.npz"), **npy(out))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "real_conv":
+    if len(sys.argv) > 1 and sys.argv[1] == "bilinear":
+        bilinear_fixtures()
+    elif len(sys.argv) > 1 and sys.argv[1] == "real_conv":
         real_conv_fixtures()
     elif len(sys.argv) > 1 and sys.argv[1] == "extensions":
         extension_fixtures()

@@ -4,7 +4,7 @@ import torch
 import torch.nn.functional as F
 
 import cplxmodule_b200 as cb
-from cplxmodule_b200 import cplx
+from cplxmodule_b200 import cplx, ops
 from cplxmodule_b200.nn import CplxConv1d, CplxConv2d
 from cplxmodule_b200.nn.relevance import CplxConv2dVD, penalties
 from oracle import cplx_oracle as orc

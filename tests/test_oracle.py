@@ -222,3 +222,38 @@ def test_oracle_vs_live_reference_conv_vd_and_extensions():
         ref.backward()
         mine.backward()
         assert torch.equal(w_re.grad, m.weight.real.grad) and torch.equal(ls2.grad, m.log_sigma2.grad)
+
+
+def _bil(g, tag):
+    names = ("x1_re", "x1_im", "x2_re", "x2_im", "w_re", "w_im", "b_re", "b_im")
+    return [g[f"{tag}_{n}"] for n in names]
+
+
+@pytest.mark.parametrize("tag,conj", [("conj", True), ("plain", False)])
+def test_golden_cplx_bilinear(tag, conj):
+    g = load_golden("bilinear")
+    args = _bil(g, tag)
+    mu = orc.cplx_bilinear(*args, conjugate=conj)
+    assert torch.equal(mu[0], g[f"{tag}_mu_re"]) and torch.equal(mu[1], g[f"{tag}_mu_im"])
+    y = orc.cplx_bilinear_vd(*args, g[f"{tag}_log_sigma2"], g[f"{tag}_eps_re"], g[f"{tag}_eps_im"], conj)
+    assert torch.equal(y[0], g[f"{tag}_y_re"]) and torch.equal(y[1], g[f"{tag}_y_im"])
+    O = args[4].shape[0]
+    kl = orc.layer_penalty("cplx_vd", args[4].reshape(O, -1), args[5].reshape(O, -1),
+                           g[f"{tag}_log_sigma2"].reshape(O, -1))
+    assert torch.allclose(kl, g[f"{tag}_penalty_sum"], rtol=1e-6)
+    # the identity the CUDA path relies on: bilinear == linear on the outer-product features
+    x1 = torch.complex(args[0], args[1]).to(torch.complex128)
+    x2 = torch.complex(args[2], args[3]).to(torch.complex128)
+    z = ((x1.conj() if conj else x1)[:, :, None] * x2[:, None, :]).reshape(x1.shape[0], -1)
+    lin = orc.cplx_linear(z.real, z.imag, args[4].double().reshape(O, -1), args[5].double().reshape(O, -1),
+                          args[6].double(), args[7].double())
+    assert torch.allclose(lin[0], mu[0].double(), atol=1e-5) and torch.allclose(lin[1], mu[1].double(), atol=1e-5)
+
+
+def test_golden_real_bilinear():
+    g = load_golden("bilinear")
+    y = orc.real_bilinear_vd(g["real_x1"], g["real_x2"], g["real_w"], g["real_b"], g["real_log_sigma2"],
+                             g["real_eps"])
+    assert torch.equal(y, g["real_y"])
+    assert torch.equal(orc.real_bilinear_vd(g["real_x1"], g["real_x2"], g["real_w"], g["real_b"], None, None),
+                       g["real_mu"])

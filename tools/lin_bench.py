@@ -30,8 +30,8 @@ def timeit(fn, iters=50, warm=3):
 def main():
     torch.manual_seed(0)
     with torch.no_grad():
-        for dt_name, dt, variants in (("f32", torch.float32, {"f16-persistent": {}, "tf32": {"CPLXK_F16": "0"}}),
-                                      ("bf16", torch.bfloat16, {"persistent": {}, "tile-per-cta": {"CPLXK_LIN3": "0"}})):
+        for dt_name, dt, variants in (("f32", torch.float32, {"f16-persistent": "auto", "tf32": "tf32"}),
+                                      ("bf16", torch.bfloat16, {"persistent": "auto"})):
             xr = (torch.randn(M, K, device=DEV) / 2 ** 0.5).to(dt)
             xi = (torch.randn(M, K, device=DEV) / 2 ** 0.5).to(dt)
             bound = 1 / (2 * K) ** 0.5
@@ -41,17 +41,14 @@ def main():
             fn = lambda: ops.cplx_linear(xr, xi, w_re, w_im, b_re, b_im)
             res = {v: [] for v in variants}
             for _ in range(4):
-                for v, env in variants.items():
-                    for k in ("CPLXK_F16", "CPLXK_LIN3"):
-                        os.environ.pop(k, None)
-                    os.environ.update(env)
+                for v, mode in variants.items():
+                    ops.set_math_mode(mode)
                     res[v].append(timeit(fn))
+                    ops.set_math_mode("auto")
             for v, ts in res.items():
                 ms = sorted(ts)[len(ts) // 2]
                 print(json.dumps(dict(dtype=dt_name, variant=v, ms_med=round(ms, 4), ms_min=round(min(ts), 4),
                                       tflops=round(8 * M * N * K / ms / 1e9, 1))), flush=True)
-    for k in ("CPLXK_F16", "CPLXK_LIN3"):
-        os.environ.pop(k, None)
 
 
 if __name__ == "__main__":
