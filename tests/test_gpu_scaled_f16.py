@@ -126,8 +126,9 @@ def test_matches_tf32_path_and_exact_fp32_kernel():
     for a, b, c, w in zip(got16, got32, exact, want):
         assert rel_err(c, w) < 2e-5
         assert rel_err(a, w) < TOL and rel_err(b, w) < TOL
-        # same 11-bit significand, same rounding mode: errors of the same size
-        assert rel_err(a, w) < 2.5 * max(rel_err(b, w), 1e-4)
+        # both carry an 11-bit significand in the mean GEMM; the scaled-fp16 path additionally
+        # rounds the variance operands to bf16, the tf32 path keeps them tf32
+        assert rel_err(a, w) < 5e-4
 
 
 @pytest.mark.parametrize("cls,kind", [(CplxLinearVD, "cplx_vd"), (CplxLinearARD, "cplx_ard"),
