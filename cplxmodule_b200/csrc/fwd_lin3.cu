@@ -15,6 +15,7 @@
 
 #include "epilogue.cuh"
 #include "knobs.cuh"
+#include "prep_row.cuh"
 #include "ptx.cuh"
 #include "tc3_common.cuh"
 
@@ -304,27 +305,30 @@ size_t fwd_lin3_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K) {
 
 bool fwd_lin3_supported(int64_t M, int64_t N, int64_t K) { return M > 128 && K % 8 == 0 && K >= 8 && N >= 1; }
 
-int vd_prepare_f16_launch(bool cplx, const void* x_re, const void* x_im, int64_t M, const void* w_re,
-                          const void* w_im, const void* ls2, int64_t N, int64_t K, void* xh_re,
-                          void* xh_im, void* q, void* wh_re, void* wh_im, void* e, float* isx,
-                          float* isw, const KlFuse& kl, cudaStream_t st, const void* w_mask);
+int vd_prepare_f16_launch(bool cplx, const PrepArgs& a, int64_t m_rows, int64_t n_rows, const KlFuse& kl,
+                          double* kl_rows, unsigned int* zero, int n_zero, cudaStream_t st);
 
 int fwd_lin3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                  void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st,
                  const void* w_mask) {
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const size_t xb = align256(static_cast<size_t>(M) * K * 2), wb = align256(static_cast<size_t>(N) * K * 2);
-  void* xh_re = ws;
-  void* xh_im = ws + xb;
-  void* wh_re = ws + 2 * xb;
-  void* wh_im = ws + 2 * xb + wb;
-  float* isx = reinterpret_cast<float*>(ws + 2 * xb + 2 * wb);
-  float* isw = reinterpret_cast<float*>(ws + 2 * xb + 2 * wb + align256(static_cast<size_t>(M) * 4));
+  auto f = [](const void* p) { return static_cast<const float*>(p); };
+  PrepArgs a{};
+  a.x_re = f(x_re), a.x_im = f(x_im), a.w_re = f(w_re), a.w_im = f(w_im), a.ls2 = nullptr, a.w_mask = f(w_mask);
+  a.M = M, a.N = N, a.K = K;
+  a.xh_re = reinterpret_cast<__half*>(ws);
+  a.xh_im = reinterpret_cast<__half*>(ws + xb);
+  a.wh_re = reinterpret_cast<__half*>(ws + 2 * xb);
+  a.wh_im = reinterpret_cast<__half*>(ws + 2 * xb + wb);
+  a.q = nullptr, a.e = nullptr;
+  a.isx = reinterpret_cast<float*>(ws + 2 * xb + 2 * wb);
+  a.isw = reinterpret_cast<float*>(ws + 2 * xb + 2 * wb + align256(static_cast<size_t>(M) * 4));
+  a.kl_kind = -1, a.kl_row0 = 0, a.kl_row1 = 0;
   const KlFuse none{-1, nullptr, nullptr, 0, -1, nullptr};
-  int rc = vd_prepare_f16_launch(cplx, x_re, x_im, M, w_re, w_im, nullptr, N, K, xh_re, xh_im, nullptr,
-                                 wh_re, wh_im, nullptr, isx, isw, none, st, w_mask);
+  int rc = vd_prepare_f16_launch(cplx, a, M, N, none, nullptr, nullptr, 0, st);
   if (rc) return rc;
-  Lin3Operands o{xh_re, xh_im, wh_re, wh_im, isx, isw, true};
+  Lin3Operands o{a.xh_re, a.xh_im, a.wh_re, a.wh_im, a.isx, a.isw, true};
   return cplx ? launch_lin3<float, true>(o, M, N, K, ep, st) : launch_lin3<float, false>(o, M, N, K, ep, st);
 }
 

@@ -56,7 +56,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // Grouped raster of the persistent kernels: tiles of 256 rows x 128 columns, `group` row tiles
 // are walked against all column tiles before the next group (a wave of 74 tile pairs then
 // covers about 6 x 12 tiles: the smallest operand footprint per wave).
-__device__ __forceinline__ void raster_tile(int t, int tiles_m2, int tiles_n, int group, int& tile_m,
+__host__ __device__ __forceinline__ void raster_tile(int t, int tiles_m2, int tiles_n, int group, int& tile_m,
                                             int& tile_n) {
   const int per_group = group * tiles_n;
   const int g = t / per_group;

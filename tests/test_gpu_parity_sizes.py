@@ -198,3 +198,63 @@ def test_ard_config5_shard_8192():
     with torch.no_grad():
         inject = layer(x, eps=eps)
     assert torch.equal(fused.real, inject.real) and torch.equal(fused.imag, inject.imag)
+
+
+# ------------------------------------------------- in-kernel conversion of the tail operand rows
+@pytest.mark.parametrize("M,N,K", [(2500, 1300, 264), (1000, 3000 + 8, 512), (4096, 4096, 1024),
+                                   (20000, 136, 256), (136 * 2, 20000, 256)])
+@pytest.mark.parametrize("cplx_", [True, False])
+def test_tail_rows_converted_inside_the_gemm_kernel(M, N, K, cplx_):
+    """more tile pairs than one wave of the persistent grid: only the first wave's operand rows are
+    converted by the stand-alone pre-pass, two warps of the GEMM kernel convert the rest while it
+    runs.  Every output row vs the float64 oracle; the KL sum (per-row sums written by whichever
+    CTA converted the row, added in index order) vs the stand-alone kernel; bit-reproducible."""
+    torch.manual_seed(M + N + K)
+    cls = CplxLinearVD if cplx_ else LinearVD
+    layer = cls(K, N).to(DEV).train()
+    with torch.no_grad():
+        layer.log_sigma2.uniform_(-10, 0)
+    x = cplx.randn(M, K, device=DEV) if cplx_ else torch.randn(M, K, device=DEV)
+    eps = cplx.randn(M, N, device=DEV) if cplx_ else torch.randn(M, N, device=DEV)
+    with torch.no_grad():
+        y1 = layer(x, eps=eps)
+        kl1 = sum(penalties(layer))
+        y2 = layer(x, eps=eps)
+        kl2 = sum(penalties(layer))
+        cb.set_kl_fusion(False)
+        try:
+            kl_alone = sum(penalties(layer))
+        finally:
+            cb.set_kl_fusion(True)
+    c = lambda t: t.detach().cpu().double()
+    if cplx_:
+        assert torch.equal(y1.real, y2.real) and torch.equal(y1.imag, y2.imag)
+        w, b = layer.weight, layer.bias
+        want = orc.cplx_linear_vd(c(x.real), c(x.imag), c(w.real), c(w.imag), c(b.real), c(b.imag),
+                                  c(layer.log_sigma2), c(eps.real), c(eps.imag))
+        assert rel_err(y1.real, want[0]) < 1e-3 and rel_err(y1.imag, want[1]) < 1e-3
+    else:
+        assert torch.equal(y1, y2)
+        want = orc.real_linear_vd(c(x), c(layer.weight), c(layer.bias), c(layer.log_sigma2), c(eps))
+        assert rel_err(y1, want) < 1e-3
+    assert torch.equal(kl1, kl2)
+    assert abs(kl1.item() - kl_alone.item()) <= 2e-6 * abs(kl_alone.item())
+
+
+def test_tail_conversion_repeated_calls_are_bit_stable():
+    """40 back-to-back calls on one stream share the workspace and its control words (re-zeroed by
+    each call's pre-pass): all results identical to the first."""
+    torch.manual_seed(77)
+    M, N, K = 3000, 2500, 512
+    layer = CplxLinearVD(K, N).to(DEV).train()
+    with torch.no_grad():
+        layer.log_sigma2.uniform_(-10, 0)
+    x, eps = cplx.randn(M, K, device=DEV), cplx.randn(M, N, device=DEV)
+    with torch.no_grad():
+        first = layer(x, eps=eps)
+        kl0 = sum(penalties(layer))
+        for _ in range(40):
+            y = layer(x, eps=eps)
+            kl = sum(penalties(layer))
+            assert torch.equal(y.real, first.real) and torch.equal(y.imag, first.imag)
+            assert torch.equal(kl, kl0)
