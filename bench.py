@@ -552,7 +552,7 @@ def run_workload(args, wl, h, rank, local_rank, world, placement, full):
         # ---- side measurements that explain the step (not part of `value`): the operand pre-pass
         # alone (cplxk_linear_vd_prepare: the same launch the forward starts with) and the
         # stand-alone KL pass that the fused pre-pass replaces at N = 1
-        res["prep_ms"] = res["head_ms"] = res["kl_alone_ms"] = None
+        res["prep_ms"] = res["kl_alone_ms"] = None
         if args.dtype == "f32":
             lib = nv.lib()
             code = nv.dtype_code(dt)
@@ -563,16 +563,13 @@ def run_workload(args, wl, h, rank, local_rank, world, placement, full):
             w = layer.weight
             kind = layer._kl_kind
 
-            def prep_call(HEAD):
+            def prep_only():
                 nv.check(lib.cplxk_linear_vd_prepare(
                     nv.ptr(x.real), nv.ptr(x.imag), nv.ptr(w.real), nv.ptr(w.imag),
                     nv.ptr(layer.log_sigma2), B, D, D, code, nv.ptr(ws), ws_bytes, kind,
-                    nv.ptr(kl_sum), nv.ptr(kl_ws), kl_ws.numel() * 8, HEAD, nv.stream_ptr(dev)))
+                    nv.ptr(kl_sum), nv.ptr(kl_ws), kl_ws.numel() * 8, nv.stream_ptr(dev)))
 
-            # full pre-pass (every row: the HBM-bound stage by itself) and the head the forward call
-            # really launches in front of the GEMM kernel (which converts the other rows itself)
-            res["prep_ms"] = h.device_time(lambda: prep_call(0))
-            res["head_ms"] = h.device_time(lambda: prep_call(1))
+            res["prep_ms"] = h.device_time(prep_only)
             del ws
             cb.set_kl_fusion(False)
             shard = cb.ops._state["kl_shard"]
@@ -701,13 +698,12 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.empty_cache()
         r5 = run_workload(sub, WORKLOADS[5], h, rank, local_rank, world, placement, full=False)
         w5 = WORKLOADS[5]
-        g5 = r5["f_ms"] - r5["head_ms"] if r5["head_ms"] is not None else r5["f_ms"]
+        g5 = r5["f_ms"] - r5["prep_ms"] if r5["prep_ms"] is not None else r5["f_ms"]
         extra["config5"] = {
             "workload": w5["name"], "value": w5["B"] * world * sub.steps / (r5["ms"] / 1e3),
             "unit": "samples/s", "n_gpus": world, "steps": sub.steps, "ms_per_step": r5["ms"] / sub.steps,
             "global_batch": w5["B"] * world, "step_tflops": flops_per_step(w5["B"], w5["D"]) / (r5["ms"] / sub.steps / 1e3) / 1e12,
-            "gemm_ms": g5, "head_prepass_ms": r5["head_ms"], "full_prepass_ms": r5["prep_ms"],
-            "parity": r5["parity"],
+            "gemm_ms": g5, "prepass_ms": r5["prep_ms"], "parity": r5["parity"],
         }
         torch.cuda.empty_cache()
 
@@ -728,12 +724,11 @@ def run_ours(args, rank, local_rank, world):
     traffic = ncu_traffic()
     esize = 4 if args.dtype != "bf16" else 2
     ms, f_ms, k_ms, prep_ms, kl_alone_ms = res["ms"], res["f_ms"], res["k_ms"], res["prep_ms"], res["kl_alone_ms"]
-    head_ms = res["head_ms"]
     e2e_steps, e2e_ms = res["e2e_steps"], res["e2e_ms"]
     value = B * world * args.steps / (ms / 1e3)
     e2e_value = B * world * e2e_steps / (e2e_ms / 1e3)
     copy_value = B * world / (res["copy_ms_per_step"] / 1e3)
-    gemm_ms = f_ms - head_ms if head_ms is not None else f_ms
+    gemm_ms = f_ms - prep_ms if prep_ms is not None else f_ms
     FLOPS = flops_per_step(B, D)
     achieved_tf = FLOPS / (gemm_ms / 1e3) / 1e12
     step_tf = FLOPS / (ms / args.steps / 1e3) / 1e12
@@ -784,7 +779,7 @@ def run_ours(args, rank, local_rank, world):
                      "fp32 accumulate in TMEM, scales undone in the epilogue") if f32
                     else "tcgen05 kind::f16 (bf16), fp32 accumulate in TMEM",
             "noise": f"in-kernel Philox4x32-10, layout={args.noise}",
-            "kl": "fused into the operand conversion (pre-pass head + in-GEMM tail)" if fused else (
+            "kl": "fused into the operand pre-pass" if fused else (
                 "row shard fused into the operand pre-pass + 1 all-reduce" if world > 1 and f32 else "kl_kernel"),
             "l2": f"no flush needed: each step streams {(4 * B * D + 3 * D * D) * esize / 1e6:.0f} MB of "
                   "distinct operands and outputs, larger than the 126 MB L2",
@@ -806,17 +801,16 @@ def run_ours(args, rank, local_rank, world):
         "parity": res["parity"],
         "roofline": {
             "kernel": "fwd_tc3_kernel (persistent CTA-pair: complex mean GEMM + variance GEMM + Philox "
-                      "noise + epilogue" + (" + conversion of the operand rows its first wave of tiles does "
-                      "not need, by two dedicated warps under the MMAs); ms_per_launch = event-timed forward "
-                      "call (inside the timed loop) minus the device time of the head pre-pass launch"
-                      if head_ms is not None else "), timed together with its operand pre-pass"),
+                      "noise + epilogue)" + ("; ms_per_launch = event-timed forward call (inside the timed loop) "
+                      "minus the device time of the pre-pass launch" if prep_ms is not None else
+                      " timed together with its operand pre-pass"),
             "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf,
             "step_achieved": step_tf, "step_frac": step_tf / peak_tf,
             "peak_source": f"{peaks['source']} bf16 cuBLAS sustained (MEASURED_PEAKS.json); kind::f16 "
                            "runs fp16 and bf16 operands at the same rate",
             "algorithmic_flops_per_launch": FLOPS, "ms_per_launch": gemm_ms,
-            "forward_call_ms": f_ms, "head_prepass_ms": head_ms,
+            "forward_call_ms": f_ms,
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed
             # `ncu --set full` capture (profiles/traffic.json); None until captured for this kernel/shape
             "traffic": traffic.get(f"gemm_{args.dtype}_{D}"),
@@ -834,9 +828,6 @@ def run_ours(args, rank, local_rank, world):
             "unit": "GB/s", "frac": pb / (prep_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
             "ms_per_launch": prep_ms, "algorithmic_bytes_per_launch": pb,
             "traffic": traffic.get(f"prepass_f32_{D}"),
-            "note": "the stage by itself over EVERY operand row (cplxk_linear_vd_prepare); inside the "
-                    "step only its head runs as a separate launch (head_prepass_ms), the other rows are "
-                    "converted inside the GEMM kernel",
         }
     if res.get("alt") is not None:
         res["alt"]["fwd_frac_of_peak"] = res["alt"]["fwd_tflops"] / peak_tf

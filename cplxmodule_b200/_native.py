@@ -56,7 +56,7 @@ def _declare(lib):
                                               ctypes.POINTER(_int), _vp])
     lib.cplxk_set_sm_reserve.argtypes = [_int]
     lib.cplxk_linear_vd_prepare.argtypes = ([_vp] * 5 + [_i64] * 3 + [_int, _vp, ctypes.c_size_t, _int, _vp, _vp,
-                                            ctypes.c_size_t, _int, _vp])
+                                            ctypes.c_size_t, _vp])
     lib.cplxk_linear_vd_workspace_bytes.restype = ctypes.c_size_t
     lib.cplxk_linear_vd_workspace_bytes.argtypes = [_i64, _i64, _i64, _int]
     lib.cplxk_kl_workspace_bytes.restype = ctypes.c_size_t

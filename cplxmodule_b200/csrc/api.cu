@@ -51,9 +51,6 @@ const Knobs& knobs() {
     v.conv_pair = env_int("CPLXK_CONV_PAIR", 1) != 0;
     v.conv_persistent = env_int("CPLXK_CONV_NONPERSISTENT", 0) != 1;
     v.pdl = env_int("CPLXK_PDL", 1) != 0;
-    v.tail = env_int("CPLXK_TAIL", 1) != 0;
-    v.tail_waves = env_int("CPLXK_TAIL_WAVES", 1);
-    if (v.tail_waves < 1) v.tail_waves = 1;
 #ifdef CPLXK_DEBUG
     v.dbg = env_int("CPLXK_DBG", 0);
 #else
@@ -363,8 +360,7 @@ extern "C" int cplxk_linear_vd_prepare(const void* x_re, const void* x_im, const
                                        const void* w_im, const void* log_sigma2, int64_t M,
                                        int64_t N, int64_t K, int dtype, void* workspace,
                                        size_t workspace_bytes, int kl_kind, float* kl_sum,
-                                       void* kl_workspace, size_t kl_workspace_bytes, int head_only,
-                                       void* stream) {
+                                       void* kl_workspace, size_t kl_workspace_bytes, void* stream) {
   if (!x_re || !w_re || !log_sigma2 || !workspace || M < 0 || N < 0 || K < 0) return CPLXK_ERR_BADARG;
   const bool cplx = x_im != nullptr;
   if (cplx != (w_im != nullptr)) return CPLXK_ERR_BADARG;
@@ -385,8 +381,6 @@ extern "C" int cplxk_linear_vd_prepare(const void* x_re, const void* x_im, const
   }
   EpiParams ep{};          // y_re == nullptr: stop after the pre-pass
   ep.M = M, ep.N = N;
-  ep.plane_elems = head_only ? -1 : 0;   // -1: only the rows the forward's own pre-pass launch converts
-  if (head_only) kl.kind = -1;           // the KL sum needs every weight row
   return fwd_tc3_f32(cplx, x_re, x_im, w_re, w_im, log_sigma2, workspace, M, N, K, ep,
                      static_cast<cudaStream_t>(stream), kl);
 }

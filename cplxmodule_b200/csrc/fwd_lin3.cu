@@ -305,8 +305,7 @@ size_t fwd_lin3_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K) {
 
 bool fwd_lin3_supported(int64_t M, int64_t N, int64_t K) { return M > 128 && K % 8 == 0 && K >= 8 && N >= 1; }
 
-int vd_prepare_f16_launch(bool cplx, const PrepArgs& a, int64_t m_rows, int64_t n_rows, const KlFuse& kl,
-                          double* kl_rows, unsigned int* zero, int n_zero, cudaStream_t st);
+int vd_prepare_f16_launch(bool cplx, const PrepArgs& a, const KlFuse& kl, cudaStream_t st);
 
 int fwd_lin3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                  void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t st,
@@ -326,7 +325,7 @@ int fwd_lin3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re
   a.isw = reinterpret_cast<float*>(ws + 2 * xb + 2 * wb + align256(static_cast<size_t>(M) * 4));
   a.kl_kind = -1, a.kl_row0 = 0, a.kl_row1 = 0;
   const KlFuse none{-1, nullptr, nullptr, 0, -1, nullptr};
-  int rc = vd_prepare_f16_launch(cplx, a, M, N, none, nullptr, nullptr, 0, st);
+  int rc = vd_prepare_f16_launch(cplx, a, none, st);
   if (rc) return rc;
   Lin3Operands o{a.xh_re, a.xh_im, a.wh_re, a.wh_im, a.isx, a.isw, true};
   return cplx ? launch_lin3<float, true>(o, M, N, K, ep, st) : launch_lin3<float, false>(o, M, N, K, ep, st);

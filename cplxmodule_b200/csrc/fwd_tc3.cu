@@ -52,26 +52,8 @@ struct Tc3Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;
   static constexpr int NACC = NA + 1;
   static constexpr int TMEM_COLS = NACC * BN <= 256 ? 256 : 512;
-  static constexpr int CONV_WARPS = 2;               // tail-row converters (idle when there is no tail)
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * CONV_WARPS;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static_assert(STAGES >= 3, "ring too shallow");
-};
-
-// "Tail" rows: the operand rows the first wave of tiles does not need.  They are converted by two
-// dedicated warps of THIS kernel while its tensor cores work (the stand-alone pre-pass launch in
-// front of it then only covers the head), in first-use order, claimed one row at a time through
-// a global counter; per-chunk completion counters tell the TMA producers when a tile's operand
-// rows are in place.
-struct TailWork {
-  PrepArgs a;
-  unsigned int* ctl;       // [0] next tail item, [1] exit ticket   (zeroed by the head pre-pass)
-  unsigned int* w_done;    // rows converted per 64-row chunk of W   (    "    )
-  unsigned int* x_done;    // rows converted per 128-row chunk of x  (    "    )
-  double* kl_rows;         // per weight row KL sums (head rows: written by the pre-pass)
-  float* kl_sum;           // final sum, written by the last CTA to leave
-  int64_t m_head, n_head;  // rows converted before this kernel starts (multiples of 128 / 64)
-  unsigned int total;      // tail items: W rows [n_head, N) first, then x rows [m_head, M)
-  unsigned int n_tail_w;
 };
 
 struct Tc3Params {
@@ -83,32 +65,10 @@ struct Tc3Params {
   const float* sx;         // [M] inverse row scales of x (nullable)
   const float* sw;         // [N] inverse row scales of W (nullable)
   EpiParams ep;
-  TailWork tail;           // tail.total == 0: every operand row was converted before the launch
 };
 
-// acquire-load of a completion counter written by another CTA
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ bool tail_chunk_ready(const unsigned int* done, int64_t chunk, int chunk_rows,
-                                                 int64_t head_rows, int64_t rows) {
-  const int64_t r0 = chunk * chunk_rows;
-  if (r0 >= rows || r0 + chunk_rows <= head_rows) return true;     // no such rows / converted up front
-  const int64_t want = (rows - r0) < chunk_rows ? (rows - r0) : chunk_rows;
-  return ld_acquire_gpu(done + chunk) >= static_cast<unsigned int>(want);
-}
-// all four operand chunks of the 256 x 128 tile pair (both CTAs' A rows, both halves of B)
-__device__ __forceinline__ bool tail_tile_ready(const TailWork& tw, int tile_m, int tile_n) {
-  return tail_chunk_ready(tw.x_done, 2 * static_cast<int64_t>(tile_m), 128, tw.m_head, tw.a.M) &&
-         tail_chunk_ready(tw.x_done, 2 * static_cast<int64_t>(tile_m) + 1, 128, tw.m_head, tw.a.M) &&
-         tail_chunk_ready(tw.w_done, 2 * static_cast<int64_t>(tile_n), 64, tw.n_head, tw.a.N) &&
-         tail_chunk_ready(tw.w_done, 2 * static_cast<int64_t>(tile_n) + 1, 64, tw.n_head, tw.a.N);
-}
-
 template <typename OutT, bool kCplx>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__ CUtensorMap tm_xi,
                const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_wr,
                const __grid_constant__ CUtensorMap tm_wi, const __grid_constant__ CUtensorMap tm_e,
@@ -176,15 +136,6 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
         decode_tile(t, tile_m, tile_n);
         const int32_t m0 = tile_m * 256 + static_cast<int32_t>(rank) * 128;
         const int32_t nb0 = tile_n * C::BN + static_cast<int32_t>(rank) * 64;
-        if (p.tail.total) {
-          // this CTA's A rows and its half of the B rows may still be in conversion (tail rows)
-          while (!(tail_chunk_ready(p.tail.x_done, m0 / 128, 128, p.tail.m_head, p.M) &&
-                   tail_chunk_ready(p.tail.w_done, nb0 / 64, 64, p.tail.n_head, p.N)))
-            __nanosleep(200);
-          // they were written through the generic proxy, TMA reads through the async proxy
-          asm volatile("fence.proxy.async;" ::: "memory");
-          __syncwarp();
-        }
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
           const uint32_t fb = bar_full + 8 * s;
@@ -258,41 +209,6 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
         __syncwarp();
       }
     }
-  } else if (warp >= 2 + C::EPI_WARPS) {
-    // ---------------------------------------------- 2 converter warps: the tail operand rows
-    // Rows are claimed one at a time (global counter, first-use order) and converted without ever
-    // waiting for anything, so every producer's wait for a tile's rows ends; the whole K = 4096 row
-    // of both planes sits in registers between the max pass and the write pass.
-    if (p.tail.total) {
-      const TailWork& tw = p.tail;
-      constexpr int kT = 32 * C::CONV_WARPS;
-      const int ct = threadIdx.x - 32 * (2 + C::EPI_WARPS);
-      volatile unsigned int* slot = reinterpret_cast<volatile unsigned int*>(aux_ptr + 256);
-      float* red = reinterpret_cast<float*>(aux_ptr + 288);
-      double* ksh = reinterpret_cast<double*>(aux_ptr + 320);
-      auto sync = [] { ptx::named_bar_sync(2, kT); };
-      ptx::grid_dep_wait();                        // the control words are zeroed by the head pre-pass
-      while (true) {
-        if (ct == 0) slot[0] = ld_acquire_gpu(tw.ctl) < tw.total ? atomicAdd(tw.ctl, 1u) : 0xffffffffu;
-        sync();
-        const unsigned int idx = slot[0];
-        sync();                                    // slot consumed before it is rewritten
-        if (idx >= tw.total) break;
-        const bool is_x = idx >= tw.n_tail_w;
-        const int64_t r = is_x ? tw.m_head + (idx - tw.n_tail_w) : tw.n_head + idx;
-        const float kl = prep_convert_row<kCplx, kT, 8>(tw.a, is_x, r, ct, red, sync);
-        if (!is_x && tw.kl_rows != nullptr && tw.a.kl_kind >= 0) {
-          const double rs = prep_group_sum<kT>(static_cast<double>(kl), ct, ksh, sync);
-          if (ct == 0) tw.kl_rows[r] = rs;
-        }
-        __threadfence();                           // this thread's operand stores, GPU scope
-        sync();
-        if (ct == 0) {
-          __threadfence();
-          atomicAdd(is_x ? tw.x_done + r / 128 : tw.w_done + r / 64, 1u);
-        }
-      }
-    }
   } else {
     // ------------------------------------ 8 epilogue warps: noise prefetch, then drain + row stores
     // (little is kept live across noise_prefetch: it needs ~all of the 168 registers)
@@ -329,9 +245,9 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
         const OutT* bi = static_cast<const OutT*>(p.ep.b_im);
         cv[te] = (ok && br) ? Elem<OutT>::to_f(__ldg(br + n)) : 0.f;
         cv[128 + te] = (kCplx && ok && bi) ? Elem<OutT>::to_f(__ldg(bi + n)) : 0.f;
-        cv[256 + te] = (ok && p.sw) ? __ldcg(p.sw + n) : 1.f;    // .cg: tail rows are written in-kernel
+        cv[256 + te] = (ok && p.sw) ? __ldg(p.sw + n) : 1.f;
       }
-      const float sxm = (p.sx && m < p.M) ? __ldcg(p.sx + m) : 1.f;
+      const float sxm = (p.sx && m < p.M) ? __ldg(p.sx + m) : 1.f;
       ptx::named_bar_sync(1, 32 * C::EPI_WARPS);            // column vectors visible
 
       ptx::mbar_wait(bar_accum, tile_par);
@@ -382,43 +298,28 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
   }
-  if (p.tail.total && p.tail.kl_rows != nullptr && p.tail.a.kl_kind >= 0 && warp >= 2 + C::EPI_WARPS) {
-    // every weight row's KL sum sits in kl_rows (head rows: pre-pass, tail rows: whoever converted
-    // them); the last CTA to get here adds them in index order -- deterministic, schedule-free
-    const TailWork& tw = p.tail;
-    constexpr int kT = 32 * C::CONV_WARPS;
-    const int ct = threadIdx.x - 32 * (2 + C::EPI_WARPS);
-    volatile unsigned int* slot = reinterpret_cast<volatile unsigned int*>(aux_ptr + 256);
-    double* ksh = reinterpret_cast<double*>(aux_ptr + 320);
-    auto sync = [] { ptx::named_bar_sync(2, kT); };
-    if (ct == 0) {
-      __threadfence();
-      slot[0] = atomicAdd(tw.ctl + 1, 1u);
-    }
-    sync();
-    const bool last = slot[0] == gridDim.x - 1;
-    if (last) {
-      __threadfence();
-      double v = 0.0;
-      for (int64_t r = tw.a.kl_row0 + ct; r < tw.a.kl_row1; r += kT)
-        v += *reinterpret_cast<const volatile double*>(tw.kl_rows + r);
-      const double total = prep_group_sum<kT>(v, ct, ksh, sync);
-      if (ct == 0) *tw.kl_sum = static_cast<float>(total);
-    }
-  }
 }
 
 // ------------------------------------------------------------------ fp32 -> fp16 operand pre-pass
 // One block per row of x or of W (interleaved); the row conversion itself is prep_row.cuh.
-// `m_rows` / `n_rows`: only x rows [0, m_rows) and W rows [0, n_rows) are converted here (the
-// head); the GEMM kernel converts the rest itself (TailWork).  Then `zero` / `n_zero` name the
-// control words this launch clears for it and `kl_rows` receives one KL sum per weight row
-// instead of the grid-wide sum.
-template <bool kCplx>
+template <bool kCplx, bool kMask>
 __global__ void __launch_bounds__(256, 4)
-vd_prepare_f16_kernel(const PrepArgs a, int64_t m_rows, int64_t n_rows, float* __restrict__ kl_sum,
-                      KlWorkspace* __restrict__ kl_ws, double* __restrict__ kl_rows,
-                      unsigned int* __restrict__ zero, int n_zero) {
+vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im, int64_t M_,
+                      const float* __restrict__ w_re, const float* __restrict__ w_im,
+                      const float* __restrict__ ls2, const float* __restrict__ w_mask, int64_t N_,
+                      int64_t K_, __half* __restrict__ xh_re, __half* __restrict__ xh_im,
+                      __nv_bfloat16* __restrict__ q, __half* __restrict__ wh_re,
+                      __half* __restrict__ wh_im, __nv_bfloat16* __restrict__ e,
+                      float* __restrict__ isx, float* __restrict__ isw, int kl_kind,
+                      float* __restrict__ kl_sum, KlWorkspace* __restrict__ kl_ws, int64_t kl_row0,
+                      int64_t kl_row1) {
+  // (separate __restrict__ parameters, not the struct: the no-alias facts let the loads of the
+  // write pass be hoisted above its stores)
+  PrepArgs a;
+  a.x_re = x_re, a.x_im = x_im, a.w_re = w_re, a.w_im = w_im, a.ls2 = ls2, a.w_mask = w_mask;
+  a.M = M_, a.N = N_, a.K = K_;
+  a.xh_re = xh_re, a.xh_im = xh_im, a.wh_re = wh_re, a.wh_im = wh_im, a.q = q, a.e = e;
+  a.isx = isx, a.isw = isw, a.kl_kind = kl_kind, a.kl_row0 = kl_row0, a.kl_row1 = kl_row1;
   __shared__ float red[8];
   __shared__ double kl_sh[kKlThreads / 32];
   __shared__ bool kl_last;
@@ -428,12 +329,11 @@ vd_prepare_f16_kernel(const PrepArgs a, int64_t m_rows, int64_t n_rows, float* _
   // soon as every block of this grid is running; it waits (griddepcontrol.wait) before it reads
   // anything written here
   ptx::grid_dep_launch();
-  for (int i = blockIdx.x * 256 + tid; i < n_zero; i += gridDim.x * 256) zero[i] = 0u;
   auto sync = [] { __syncthreads(); };
   // x rows (pure streaming) and W rows (streaming + ~50 instructions of KL math per element)
   // alternate in the global row order and the grid size is odd, so every block -- and every SM
   // at any time -- works on a mix of the two instead of all x rows first and all W rows last
-  const int64_t M = m_rows, N = n_rows;
+  const int64_t M = a.M, N = a.N;
   const int64_t mn = M < N ? M : N;
   for (int64_t g = blockIdx.x; g < M + N; g += gridDim.x) {
     bool is_x;
@@ -445,17 +345,9 @@ vd_prepare_f16_kernel(const PrepArgs a, int64_t m_rows, int64_t n_rows, float* _
       is_x = M > N;
       r = mn + (g - 2 * mn);
     }
-    const float kl = prep_convert_row<kCplx, 256, 2>(a, is_x, r, tid, red, sync);
-    if (kl_rows != nullptr) {
-      if (!is_x && a.kl_kind >= 0) {
-        const double rs = prep_group_sum<256>(static_cast<double>(kl), tid, kl_sh, sync);
-        if (tid == 0) kl_rows[r] = rs;
-      }
-    } else {
-      kl_acc += kl;
-    }
+    kl_acc += prep_convert_row<kCplx, 256, 2, kMask>(a, is_x, r, tid, red, sync);
   }
-  if (a.kl_kind >= 0 && kl_rows == nullptr) {
+  if (a.kl_kind >= 0) {
     __syncthreads();
     const double bsum = block_sum(static_cast<double>(kl_acc), kl_sh);
     grid_sum_finish(bsum, kl_ws, kl_sum, 1.0, kl_sh, &kl_last);
@@ -468,7 +360,6 @@ struct Tc3Operands {
   const float *sx, *sw;
   bool f16;
   bool after_prepass;   // the launch right before this one in the stream is vd_prepare_f16_kernel
-  TailWork tail;        // tail.total == 0: none
 };
 
 template <typename OutT, bool kCplx>
@@ -497,7 +388,6 @@ static int launch_tc3(const Tc3Operands& o, int64_t M, int64_t N, int64_t K, con
   p.group = knobs().raster;
   p.sx = o.sx, p.sw = o.sw;
   p.ep = ep;
-  p.tail = o.tail;
   const int64_t pairs = static_cast<int64_t>(p.tiles_m2) * p.tiles_n;
   if (pairs > 0x3fffffff) return CPLXK_ERR_UNSUPPORTED;
   int sm_count = 0;
@@ -522,13 +412,11 @@ static int launch_tc3(const Tc3Operands& o, int64_t M, int64_t N, int64_t K, con
 
 
 // workspace of the fp32-plane path: xh_re, xh_im, q [M,K]; wh_re, wh_im, E [N,K] (2 bytes each),
-// isx [M], isw [N] floats, the tail-conversion control words and per-row KL sums
-static size_t tc3_ctl_bytes(int64_t M, int64_t N);
-
+// isx [M], isw [N] floats
 size_t fwd_tc3_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K) {
   if (dtype != CPLXK_F32) return 0;
   return 3 * align256(static_cast<size_t>(M) * K * 2) + 3 * align256(static_cast<size_t>(N) * K * 2) +
-         align256(static_cast<size_t>(M) * 4) + align256(static_cast<size_t>(N) * 4) + tc3_ctl_bytes(M, N);
+         align256(static_cast<size_t>(M) * 4) + align256(static_cast<size_t>(N) * 4);
 }
 
 bool fwd_tc3_supported(int dtype, int64_t M, int64_t N, int64_t K) {
@@ -537,33 +425,8 @@ bool fwd_tc3_supported(int dtype, int64_t M, int64_t N, int64_t K) {
   return M > 128 && K % 8 == 0;
 }
 
-// rows the first `waves` waves of the persistent grid need (raster order of the kernel):
-// x rows [0, *m_head), W rows [0, *n_head); multiples of the 128 / 64 row chunks
-static void tc3_head_rows(int64_t M, int64_t N, int sm_count, int waves, int64_t* m_head, int64_t* n_head) {
-  const int tiles_m2 = static_cast<int>((M + 255) / 256), tiles_n = static_cast<int>((N + 127) / 128);
-  const int64_t pairs = static_cast<int64_t>(tiles_m2) * tiles_n;
-  int64_t clusters = (sm_count - sm_reserve()) / 2;
-  if (clusters < 1) clusters = 1;
-  const int64_t first = clusters * waves < pairs ? clusters * waves : pairs;
-  int max_m = 0, max_n = 0;
-  for (int64_t t = 0; t < first; ++t) {
-    int tm, tn;
-    raster_tile(static_cast<int>(t), tiles_m2, tiles_n, knobs().raster, tm, tn);
-    max_m = tm > max_m ? tm : max_m, max_n = tn > max_n ? tn : max_n;
-  }
-  *m_head = (max_m + 1) * 256LL < M ? (max_m + 1) * 256LL : M;
-  *n_head = (max_n + 1) * 128LL < N ? (max_n + 1) * 128LL : N;
-}
-
-static size_t tc3_ctl_bytes(int64_t M, int64_t N) {
-  // [work, exit ticket, pad, pad] + w_done[ceil(N/64)] + x_done[ceil(M/128)] (uint32), kl_rows[N] (double)
-  const size_t words = 4 + static_cast<size_t>((N + 63) / 64) + static_cast<size_t>((M + 127) / 128);
-  return align256(words * 4) + align256(static_cast<size_t>(N) * 8);
-}
-
-int vd_prepare_f16_launch(bool cplx, const PrepArgs& a, int64_t m_rows, int64_t n_rows, const KlFuse& kl,
-                          double* kl_rows, unsigned int* zero, int n_zero, cudaStream_t st) {
-  const int64_t rows = m_rows + n_rows;
+int vd_prepare_f16_launch(bool cplx, const PrepArgs& a, const KlFuse& kl, cudaStream_t st) {
+  const int64_t rows = a.M + a.N;
   int sms = 148;
   int rc0 = current_device_sm_count(&sms);
   if (rc0) return rc0;
@@ -571,18 +434,25 @@ int vd_prepare_f16_launch(bool cplx, const PrepArgs& a, int64_t m_rows, int64_t 
   if (cap > kKlMaxBlocks) cap = kKlMaxBlocks - 1 + (kKlMaxBlocks & 1);           // <= kKlMaxBlocks partials, odd
   const int grid = static_cast<int>(rows > cap ? cap : (rows < 1 ? 1 : rows));
   auto kws = static_cast<KlWorkspace*>(kl.ws);
-  if (cplx)
-    vd_prepare_f16_kernel<true><<<grid, 256, 0, st>>>(a, m_rows, n_rows, kl.sum, kws, kl_rows, zero, n_zero);
-  else
-    vd_prepare_f16_kernel<false><<<grid, 256, 0, st>>>(a, m_rows, n_rows, kl.sum, kws, kl_rows, zero, n_zero);
+  const bool mask = a.w_mask != nullptr;
+#define CPLXK_PREP(C, MK)                                                                          \
+  vd_prepare_f16_kernel<C, MK><<<grid, 256, 0, st>>>(a.x_re, a.x_im, a.M, a.w_re, a.w_im, a.ls2, a.w_mask, \
+                                                     a.N, a.K, a.xh_re, a.xh_im, a.q, a.wh_re, a.wh_im,   \
+                                                     a.e, a.isx, a.isw, a.kl_kind, kl.sum, kws, a.kl_row0, \
+                                                     a.kl_row1)
+  if (cplx && mask) CPLXK_PREP(true, true);
+  else if (cplx) CPLXK_PREP(true, false);
+  else if (mask) CPLXK_PREP(false, true);
+  else CPLXK_PREP(false, false);
+#undef CPLXK_PREP
   CPLXK_CUDA_TRY(cudaGetLastError());
   return CPLXK_OK;
 }
 
 // fp32 planes: pre-pass to scaled fp16, then the persistent CTA-pair kernel above on kind::f16.
-// When the problem has more tiles than one wave of the persistent grid, the stand-alone pre-pass
-// only converts the rows that wave needs and the GEMM kernel's epilogue warps convert the rest
-// under the MMAs (CPLXK_TAIL=0 restores the full pre-pass).
+// (Converting part of the rows INSIDE the GEMM kernel, under its MMAs, was built and measured in
+// round 2 -- profiles/tail_ab_r2_*.jsonl: two extra warps per CTA are too slow for the KL / exp
+// math of the weight rows and even pure x rows cost the GEMM more than the shorter pre-pass saves.)
 int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                 const void* ls2, void* workspace, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
                 cudaStream_t st, const KlFuse& kl) {
@@ -600,46 +470,15 @@ int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re,
   a.e = reinterpret_cast<__nv_bfloat16*>(ws + 3 * xb + 2 * wb);
   a.isx = reinterpret_cast<float*>(ws + 3 * xb + 3 * wb);
   a.isw = reinterpret_cast<float*>(ws + 3 * xb + 3 * wb + align256(static_cast<size_t>(M) * 4));
-  uint8_t* ctl_base = ws + 3 * xb + 3 * wb + align256(static_cast<size_t>(M) * 4) + align256(static_cast<size_t>(N) * 4);
   const bool want_kl = kl.sum && kl.ws && kl.kind >= 0;
   a.kl_kind = want_kl ? kl.kind : -1;
   a.kl_row0 = kl.row_begin, a.kl_row1 = kl.row_end < 0 ? N : kl.row_end;
-
-  // ---- split into head (converted here) and tail (converted inside the GEMM kernel)
-  TailWork tw{};
-  int64_t m_head = M, n_head = N;
-  int sms = 148;
-  int rc = current_device_sm_count(&sms);
-  if (rc) return rc;
-  const int64_t pairs = ((M + 255) / 256) * ((N + 127) / 128);
-  const int64_t clusters = (sms - sm_reserve()) / 2 > 0 ? (sms - sm_reserve()) / 2 : 1;
-  // a multi-GPU KL shard wants its partial sum right after the pre-pass (kl.event): keep the
-  // full pre-pass there; otherwise overlap whenever there is more than one wave of tiles
-  const bool head_probe = !ep.y_re && ep.plane_elems < 0;   // cplxk_linear_vd_prepare(head_only)
-  if (knobs().tail && (ep.y_re || head_probe) && !kl.event && pairs > clusters * knobs().tail_waves &&
-      K >= 256) {
-    tc3_head_rows(M, N, sms, knobs().tail_waves, &m_head, &n_head);
-  }
-  const unsigned int n_tail_w = static_cast<unsigned int>(N - n_head);
-  const unsigned int total = n_tail_w + static_cast<unsigned int>(M - m_head);
-  unsigned int* ctl = reinterpret_cast<unsigned int*>(ctl_base);
-  const int n_words = 4 + static_cast<int>((N + 63) / 64) + static_cast<int>((M + 127) / 128);
-  double* kl_rows = reinterpret_cast<double*>(ctl_base + align256(static_cast<size_t>(n_words) * 4));
-  if (total) {
-    tw.a = a;
-    tw.ctl = ctl, tw.w_done = ctl + 4, tw.x_done = ctl + 4 + (N + 63) / 64;
-    tw.kl_rows = want_kl ? kl_rows : nullptr;
-    tw.kl_sum = kl.sum;
-    tw.m_head = m_head, tw.n_head = n_head;
-    tw.total = total, tw.n_tail_w = n_tail_w;
-  }
-  rc = vd_prepare_f16_launch(cplx, a, m_head, n_head, kl, (total && want_kl) ? kl_rows : nullptr,
-                             (total && !head_probe) ? ctl : nullptr, (total && !head_probe) ? n_words : 0, st);
+  int rc = vd_prepare_f16_launch(cplx, a, kl, st);
   if (rc) return rc;
   // the KL (partial) sum is final here: let a collective on another stream start under the GEMM
   if (kl.event) CPLXK_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(kl.event), st));
   if (!ep.y_re) return CPLXK_OK;   // cplxk_linear_vd_prepare: operands (and the KL sum) only
-  Tc3Operands o{a.xh_re, a.xh_im, a.q, a.wh_re, a.wh_im, a.e, a.isx, a.isw, true, kl.event == nullptr, tw};
+  Tc3Operands o{a.xh_re, a.xh_im, a.q, a.wh_re, a.wh_im, a.e, a.isx, a.isw, true, kl.event == nullptr};
   return cplx ? launch_tc3<float, true>(o, M, N, K, ep, st) : launch_tc3<float, false>(o, M, N, K, ep, st);
 }
 
@@ -647,7 +486,7 @@ int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re,
 int fwd_tc3_bf16(bool cplx, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                  const void* q, const void* e, int64_t M, int64_t N, int64_t K, const EpiParams& ep,
                  cudaStream_t st) {
-  Tc3Operands o{x_re, x_im, q, w_re, w_im, e, nullptr, nullptr, false, false, TailWork{}};
+  Tc3Operands o{x_re, x_im, q, w_re, w_im, e, nullptr, nullptr, false, false};
   return cplx ? launch_tc3<__nv_bfloat16, true>(o, M, N, K, ep, st)
               : launch_tc3<__nv_bfloat16, false>(o, M, N, K, ep, st);
 }

@@ -18,8 +18,6 @@ struct Knobs {
   bool tma_raw_f32;        // CPLXK_TMA_RAW_F32=1: let the tensor core truncate fp32 -> tf32
   bool conv_pair;          // CPLXK_CONV_PAIR=0: conv on single-CTA tiles
   bool conv_persistent;    // CPLXK_CONV_NONPERSISTENT=1: one conv tile per CTA
-  bool tail;               // CPLXK_TAIL=0: the stand-alone pre-pass converts every operand row
-  int tail_waves;          // CPLXK_TAIL_WAVES: waves of tiles whose rows the pre-pass converts up front
   bool pdl;                // CPLXK_PDL=0: no programmatic dependent launch between pre-pass and GEMM
   int dbg;                 // CPLXK_DBG (debug builds only; 0 otherwise)
 };

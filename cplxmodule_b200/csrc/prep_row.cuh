@@ -1,15 +1,12 @@
-// One row of the fp32 -> 16-bit operand conversion of the variational forward, written as a
-// device function so that two callers share it:
-//   * vd_prepare_f16_kernel (fwd_tc3.cu): 256-thread blocks, one row at a time, before the GEMM;
-//   * the epilogue warps of fwd_tc3_kernel, which convert the rows the first wave of tiles does
-//     not need WHILE the tensor cores work on that wave ("tail" rows).
+// One row of the fp32 -> 16-bit operand conversion in front of the persistent tensor-core GEMMs
+// (variational forward: fwd_tc3.cu; plain / masked affine map: fwd_lin3.cu), as a device function
+// of kThreads cooperating threads.
 //
 // Row maximum -> power-of-two scale that puts it in [2^13, 2^14) -> fp16 planes; the row's
 // inverse scale goes to isx / isw.  The same pass writes the variance-GEMM operands |x|^2 and
 // exp(log_sigma2) as bf16 (unscaled: bf16 has fp32's range), multiplies a fixed-sparsity mask
-// into the weights, and evaluates the layer's KL penalty on the weight row it holds in registers.
-// kThreads cooperating threads (256: a block of the pre-pass kernel; 64: the two converter warps of
-// the GEMM kernel, which keep a whole K = 4096 row in registers); K % 8 == 0.
+// into the weights (kMask), and evaluates the layer's KL penalty on the weight row it holds in
+// registers.  K % 8 == 0.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -30,25 +27,27 @@ struct PrepArgs {
   int64_t kl_row0, kl_row1;            // weight rows that enter the KL sum
 };
 
-// `sync()` is a barrier over the kThreads cooperating threads (block: __syncthreads, converter
-// warps of the GEMM kernel: a named barrier); `red` points at kThreads / 32 floats of shared
+// `sync()` is a barrier over the kThreads cooperating threads (a block: __syncthreads); `red`
+// points at kThreads / 32 floats of shared
 // memory.  kCache = 8-element groups per thread kept in registers between the two passes (the
 // rest of the row is re-read, from L2).  Returns this thread's share of the row's KL penalty
 // (0 for x rows / rows outside [kl_row0, kl_row1)).
-template <bool kCplx, int kThreads, int kCache, typename Sync>
+template <bool kCplx, int kThreads, int kCache, bool kMask, typename Sync>
 __device__ __forceinline__ float prep_convert_row(const PrepArgs& a, bool is_x, int64_t r, int tid,
                                                   float* red, Sync sync) {
   const int64_t K = a.K;
-  const float* pr = (is_x ? a.x_re : a.w_re) + r * K;
-  const float* pi = kCplx ? (is_x ? a.x_im : a.w_im) + r * K : nullptr;
-  __half* hr = (is_x ? a.xh_re : a.wh_re) + r * K;
-  __half* hi = kCplx ? (is_x ? a.xh_im : a.wh_im) + r * K : nullptr;
+  // (the planes never alias: without __restrict__ the loads of the write pass could not be
+  // hoisted above its stores)
+  const float* __restrict__ pr = (is_x ? a.x_re : a.w_re) + r * K;
+  const float* __restrict__ pi = kCplx ? (is_x ? a.x_im : a.w_im) + r * K : nullptr;
+  __half* __restrict__ hr = (is_x ? a.xh_re : a.wh_re) + r * K;
+  __half* __restrict__ hi = kCplx ? (is_x ? a.xh_im : a.wh_im) + r * K : nullptr;
   const bool has_var = a.q != nullptr;       // plain affine map: no variance operands (fwd_lin3.cu)
-  __nv_bfloat16* dv = has_var ? (is_x ? a.q : a.e) + r * K : nullptr;
-  const float* pl = (is_x || !has_var) ? nullptr : a.ls2 + r * K;
+  __nv_bfloat16* __restrict__ dv = has_var ? (is_x ? a.q : a.e) + r * K : nullptr;
+  const float* __restrict__ pl = (is_x || !has_var) ? nullptr : a.ls2 + r * K;
   // fixed-sparsity layers (nn/masked): W enters the GEMM as W * mask, applied here where every
   // weight is read anyway (no materialised masked copy, no extra launch)
-  const float* pm = (is_x || a.w_mask == nullptr) ? nullptr : a.w_mask + r * K;
+  const float* __restrict__ pm = (!kMask || is_x || a.w_mask == nullptr) ? nullptr : a.w_mask + r * K;
   float kl_acc = 0.f;
 
   if (pl != nullptr) {   // log_sigma2 is needed after the group-wide max: pull it towards L2 now
@@ -71,7 +70,7 @@ __device__ __forceinline__ float prep_convert_row(const PrepArgs& a, bool is_x, 
         ci[it][0] = b0.x, ci[it][1] = b0.y, ci[it][2] = b0.z, ci[it][3] = b0.w;
         ci[it][4] = b1.x, ci[it][5] = b1.y, ci[it][6] = b1.z, ci[it][7] = b1.w;
       }
-      if (pm != nullptr) {
+      if (kMask && pm != nullptr) {
         const float4 m0 = __ldg(reinterpret_cast<const float4*>(pm + k));
         const float4 m1 = __ldg(reinterpret_cast<const float4*>(pm + k + 4));
         const float mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
@@ -93,7 +92,7 @@ __device__ __forceinline__ float prep_convert_row(const PrepArgs& a, bool is_x, 
     for (int h = 0; h < 2; ++h) {
       float4 v = __ldg(reinterpret_cast<const float4*>(pr + k + 4 * h));
       float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (pm != nullptr) m = __ldg(reinterpret_cast<const float4*>(pm + k + 4 * h));
+      if (kMask && pm != nullptr) m = __ldg(reinterpret_cast<const float4*>(pm + k + 4 * h));
       v.x *= m.x, v.y *= m.y, v.z *= m.z, v.w *= m.w;
       amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
       if constexpr (kCplx) {
@@ -118,7 +117,6 @@ __device__ __forceinline__ float prep_convert_row(const PrepArgs& a, bool is_x, 
   s = s > 126 ? 126 : s;
   const float scale = __uint_as_float(static_cast<uint32_t>(s + 127) << 23);
   if (tid == 0) (is_x ? a.isx : a.isw)[r] = __uint_as_float(static_cast<uint32_t>(127 - s) << 23);
-  const bool kl_row = a.kl_kind >= 0 && !is_x && r >= a.kl_row0 && r < a.kl_row1;
 
   auto emit = [&](int64_t k, const float (&vr)[8], const float (&vi)[8]) {
     uint4 o;
@@ -143,7 +141,7 @@ __device__ __forceinline__ float prep_convert_row(const PrepArgs& a, bool is_x, 
     } else {
       const float4 l0 = __ldg(reinterpret_cast<const float4*>(pl + k));
       const float4 l1 = __ldg(reinterpret_cast<const float4*>(pl + k + 4));
-      if (kl_row) {   // weights and log_sigma2 are in registers anyway
+      if (a.kl_kind >= 0 && r >= a.kl_row0 && r < a.kl_row1) {   // weights and log_sigma2 are in registers anyway
         const float l[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) kl_acc += penalty_any(a.kl_kind, vr[j], kCplx ? vi[j] : 0.f, l[j]);
@@ -167,7 +165,7 @@ __device__ __forceinline__ float prep_convert_row(const PrepArgs& a, bool is_x, 
       float4 v = __ldg(reinterpret_cast<const float4*>(pr + k + 4 * h));
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
       if constexpr (kCplx) b = __ldg(reinterpret_cast<const float4*>(pi + k + 4 * h));
-      if (pm != nullptr) {
+      if (kMask && pm != nullptr) {
         const float4 m = __ldg(reinterpret_cast<const float4*>(pm + k + 4 * h));
         v.x *= m.x, v.y *= m.y, v.z *= m.z, v.w *= m.w;
         b.x *= m.x, b.y *= m.y, b.z *= m.z, b.w *= m.w;

@@ -194,11 +194,7 @@ int cplxk_linear_vd_prepare(const void* x_re, const void* x_im,
                             int64_t M, int64_t N, int64_t K, int dtype,
                             void* workspace, size_t workspace_bytes,
                             int kl_kind, float* kl_sum,
-                            void* kl_workspace, size_t kl_workspace_bytes,
-                            int head_only /* 1: only the rows the forward call's own pre-pass launch
-                                             converts (those the first wave of GEMM tiles needs; the
-                                             GEMM kernel converts the rest under its MMAs); no KL */,
-                            void* stream);
+                            void* kl_workspace, size_t kl_workspace_bytes, void* stream);
 
 /*
  * Same forward, with the layer's KL penalty as a by-product.  The operand pre-pass of the

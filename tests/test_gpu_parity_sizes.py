@@ -200,15 +200,14 @@ def test_ard_config5_shard_8192():
     assert torch.equal(fused.real, inject.real) and torch.equal(fused.imag, inject.imag)
 
 
-# ------------------------------------------------- in-kernel conversion of the tail operand rows
+# ------------------------------------------- several waves of tiles per persistent CTA pair
 @pytest.mark.parametrize("M,N,K", [(2500, 1300, 264), (1000, 3000 + 8, 512), (4096, 4096, 1024),
                                    (20000, 136, 256), (136 * 2, 20000, 256)])
 @pytest.mark.parametrize("cplx_", [True, False])
-def test_tail_rows_converted_inside_the_gemm_kernel(M, N, K, cplx_):
-    """more tile pairs than one wave of the persistent grid: only the first wave's operand rows are
-    converted by the stand-alone pre-pass, two warps of the GEMM kernel convert the rest while it
-    runs.  Every output row vs the float64 oracle; the KL sum (per-row sums written by whichever
-    CTA converted the row, added in index order) vs the stand-alone kernel; bit-reproducible."""
+def test_multi_wave_shapes_every_row(M, N, K, cplx_):
+    """more tile pairs than one wave of the persistent grid, ragged in M and N, tall-skinny and
+    short-wide: EVERY output row vs the float64 oracle (the full-size tests sample rows); the KL
+    by-product of the pre-pass vs the stand-alone kernel; bit-reproducible."""
     torch.manual_seed(M + N + K)
     cls = CplxLinearVD if cplx_ else LinearVD
     layer = cls(K, N).to(DEV).train()
@@ -241,9 +240,9 @@ def test_tail_rows_converted_inside_the_gemm_kernel(M, N, K, cplx_):
     assert abs(kl1.item() - kl_alone.item()) <= 2e-6 * abs(kl_alone.item())
 
 
-def test_tail_conversion_repeated_calls_are_bit_stable():
-    """40 back-to-back calls on one stream share the workspace and its control words (re-zeroed by
-    each call's pre-pass): all results identical to the first."""
+def test_repeated_calls_share_the_workspace_and_are_bit_stable():
+    """40 back-to-back calls on one stream share the cached scratch workspace (and the KL
+    reduction's ticket workspace): all results identical to the first."""
     torch.manual_seed(77)
     M, N, K = 3000, 2500, 512
     layer = CplxLinearVD(K, N).to(DEV).train()

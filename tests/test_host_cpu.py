@@ -36,10 +36,8 @@ def test_library_reports_errors_not_aborts_without_gpu():
     rc = lib.cplxk_device_info(None, None, None)
     assert rc == -4 and b"CUDA error" in lib.cplxk_strerror(rc)
     assert lib.cplxk_kl(0, None, None, None, 5, 0, None, None, 1.0, None, 0, None) == -1
-    # fp32 planes: three 16-bit operand planes per side + the two row-scale vectors + the control
-    # words of the in-kernel tail conversion (4 + 64 + 32 uint32, padded to 256 B) + per-row KL sums
-    assert lib.cplxk_linear_vd_workspace_bytes(4096, 4096, 4096, 0) == (
-        6 * 4096 * 4096 * 2 + 2 * 4096 * 4 + 512 + 4096 * 8)
+    # fp32 planes: three 16-bit operand planes per side + the two row-scale vectors
+    assert lib.cplxk_linear_vd_workspace_bytes(4096, 4096, 4096, 0) == 6 * 4096 * 4096 * 2 + 2 * 4096 * 4
     assert lib.cplxk_linear_vd_workspace_bytes(4096, 4096, 4096, 1) == 2 * 4096 * 4096 * 2
 
 

@@ -47,24 +47,22 @@ def main():
     kl_ws = nv.kl_workspace(dev)
     w = layer.weight
 
-    def prep(HEAD=0):
+    def prep():
         nv.check(lib.cplxk_linear_vd_prepare(nv.ptr(x.real), nv.ptr(x.imag), nv.ptr(w.real), nv.ptr(w.imag),
                                              nv.ptr(layer.log_sigma2), B, D, D, 0, nv.ptr(ws), ws_bytes,
                                              layer._kl_kind, nv.ptr(kl_sum), nv.ptr(kl_ws), kl_ws.numel() * 8,
-                                             HEAD, nv.stream_ptr(dev)))
+                                             nv.stream_ptr(dev)))
 
-    fwd, pre, head = [], [], []
+    fwd, pre = [], []
     with torch.no_grad():
         for _ in range(int(os.environ.get("ROUNDS", "5"))):
             fwd.append(device_time(lambda: layer(x)))
             pre.append(device_time(prep))
-            head.append(device_time(lambda: prep(1)))
-    f, p, hd = statistics.median(fwd), statistics.median(pre), statistics.median(head)
+    f, p = statistics.median(fwd), statistics.median(pre)
     print(json.dumps({"B": B, "D": D, "layer": name, "lib": os.environ.get("CPLXK_LIB", "default"),
                       "pdl": os.environ.get("CPLXK_PDL", "1"), "raster": os.environ.get("CPLXK_RASTER", "6"),
-                      "tail": os.environ.get("CPLXK_TAIL", "1"), "waves": os.environ.get("CPLXK_TAIL_WAVES", "1"),
                       "fwd_ms": round(f, 4), "fwd_min": round(min(fwd), 4), "prep_ms": round(p, 4),
-                      "head_ms": round(hd, 4), "gemm_ms": round(f - hd, 4), "step_tflops": round(10.0 * B * D * D / f / 1e9, 1)}))
+                      "gemm_ms": round(f - p, 4), "step_tflops": round(10.0 * B * D * D / f / 1e9, 1)}))
 
 
 if __name__ == "__main__":
