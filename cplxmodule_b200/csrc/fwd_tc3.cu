@@ -471,8 +471,15 @@ int fwd_tc3_f32(bool cplx, const void* x_re, const void* x_im, const void* w_re,
   a.isx = reinterpret_cast<float*>(ws + 3 * xb + 3 * wb);
   a.isw = reinterpret_cast<float*>(ws + 3 * xb + 3 * wb + align256(static_cast<size_t>(M) * 4));
   const bool want_kl = kl.sum && kl.ws && kl.kind >= 0;
+  const int64_t row0 = kl.row_begin, row1 = kl.row_end < 0 ? N : kl.row_end;
+  // The KL sum is a by-product of this pass (the weight rows and log_sigma2 are in registers
+  // anyway).  Its ~50 instructions per weight cost 25-30 us of issue slots at 4096^2 wherever they
+  // run serially; evaluating it inside the GEMM kernel instead (epilogue warps between two tiles,
+  // or two extra warps) was built and measured in round 2 and is SLOWER (profiles/
+  // kl_in_gemm_ab_r2.jsonl, tail_ab_r2_*.jsonl): those warps share their schedulers with the
+  // Philox generation that already fills the mainloop's shadow.
   a.kl_kind = want_kl ? kl.kind : -1;
-  a.kl_row0 = kl.row_begin, a.kl_row1 = kl.row_end < 0 ? N : kl.row_end;
+  a.kl_row0 = row0, a.kl_row1 = row1;
   int rc = vd_prepare_f16_launch(cplx, a, kl, st);
   if (rc) return rc;
   // the KL (partial) sum is final here: let a collective on another stream start under the GEMM

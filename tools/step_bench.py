@@ -37,6 +37,8 @@ def main():
     name = sys.argv[3] if len(sys.argv) > 3 else "CplxLinearVD"
     dev = torch.device("cuda")
     cb.set_noise_mode(os.environ.get("NOISE", "torch"))
+    if os.environ.get("NOKL") == "1":
+        cb.set_kl_fusion(False)
     torch.manual_seed(0)
     layer = getattr(relevance, name)(D, D).to(dev).train()
     x = cplx.randn(B, D, device=dev)
@@ -50,7 +52,7 @@ def main():
     def prep():
         nv.check(lib.cplxk_linear_vd_prepare(nv.ptr(x.real), nv.ptr(x.imag), nv.ptr(w.real), nv.ptr(w.imag),
                                              nv.ptr(layer.log_sigma2), B, D, D, 0, nv.ptr(ws), ws_bytes,
-                                             layer._kl_kind, nv.ptr(kl_sum), nv.ptr(kl_ws), kl_ws.numel() * 8,
+                                             (-1 if os.environ.get("NOKL") == "1" else layer._kl_kind), nv.ptr(kl_sum), nv.ptr(kl_ws), kl_ws.numel() * 8,
                                              nv.stream_ptr(dev)))
 
     fwd, pre = [], []
@@ -60,7 +62,7 @@ def main():
             pre.append(device_time(prep))
     f, p = statistics.median(fwd), statistics.median(pre)
     print(json.dumps({"B": B, "D": D, "layer": name, "lib": os.environ.get("CPLXK_LIB", "default"),
-                      "pdl": os.environ.get("CPLXK_PDL", "1"), "raster": os.environ.get("CPLXK_RASTER", "6"),
+                      "pdl": os.environ.get("CPLXK_PDL", "1"), "nokl": os.environ.get("NOKL", "0"), "raster": os.environ.get("CPLXK_RASTER", "6"),
                       "fwd_ms": round(f, 4), "fwd_min": round(min(fwd), 4), "prep_ms": round(p, 4),
                       "gemm_ms": round(f - p, 4), "step_tflops": round(10.0 * B * D * D / f / 1e9, 1)}))
 
