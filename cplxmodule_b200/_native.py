@@ -25,7 +25,8 @@ EXPORTS = (
     "cplxk_linear_vd_prepare",
     "cplxk_linear_fwd_ws", "cplxk_linear_workspace_bytes",
     "cplxk_linear_vd_fwd", "cplxk_linear_vd_fwd_kl", "cplxk_linear_vd_workspace_bytes", "cplxk_kl_workspace_bytes", "cplxk_kl", "cplxk_log_alpha",
-    "cplxk_conv2d_fwd", "cplxk_conv2d_workspace_bytes", "cplxk_randn_philox_torch",
+    "cplxk_conv2d_fwd", "cplxk_conv2d_workspace_bytes", "cplxk_conv2d_fwd_g",
+    "cplxk_conv2d_workspace_bytes_g", "cplxk_randn_philox_torch",
     "cplxk_transpose2d", "cplxk_eltwise", "cplxk_colsum", "cplxk_vd_grad_s2", "cplxk_vd_grad_input",
     "cplxk_mul_exp", "cplxk_kl_bwd",
     "cplxk_linear_masked_fwd", "cplxk_linear_masked_workspace_bytes", "cplxk_kl_mask",
@@ -67,6 +68,10 @@ def _declare(lib):
                                      + [_i64] * 13 + [_int, _int, _int, _vp, ctypes.c_size_t, _vp])
     lib.cplxk_conv2d_workspace_bytes.restype = ctypes.c_size_t
     lib.cplxk_conv2d_workspace_bytes.argtypes = [_i64] * 7 + [_int, _int]
+    lib.cplxk_conv2d_fwd_g.argtypes = ([_vp] * 9 + [_int, _u64, _u64, _u32] + [_vp] * 2
+                                       + [_i64] * 14 + [_int, _int, _int, _vp, ctypes.c_size_t, _vp])
+    lib.cplxk_conv2d_workspace_bytes_g.restype = ctypes.c_size_t
+    lib.cplxk_conv2d_workspace_bytes_g.argtypes = [_i64] * 8 + [_int, _int, _int]
     lib.cplxk_randn_philox_torch.argtypes = [_vp, _i64, _u64, _u64, _u32, ctypes.c_float, _vp]
     lib.cplxk_transpose2d.argtypes = [_vp, _vp, _vp, _i64, _i64, _int, _int, _vp]
     lib.cplxk_eltwise.argtypes = [_int, _vp, _vp, _vp, _i64, _int, _vp]

@@ -1,6 +1,6 @@
 """Host side of the complex convolution path (reference: ``cplx.convnd``,
 ``cplxmodule/cplx.py:770-800`` and ``CplxConvNdGaussianMixin._forward_impl``,
-``nn/relevance/complex/base.py:120-135``).  One C-ABI call per group."""
+``nn/relevance/complex/base.py:120-135``).  One C-ABI call per layer call, groups included."""
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -40,11 +40,13 @@ class _ConvFn(torch.autograd.Function):
     ``nn/relevance/complex/base.py:120-135``."""
 
     @staticmethod
-    def forward(ctx, x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, geom):
-        y_re, y_im, aux = _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, geom)
+    def forward(ctx, x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, geom, groups=1):
+        y_re, y_im, aux = _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise,
+                                      geom, groups)
         if any(ctx.needs_input_grad):
             dt = w_re.dtype
-            ctx.geom, ctx.noise, ctx.philox = geom, noise, aux.get("philox")
+            ctx.geom, ctx.noise, ctx.philox = geom, aux.get("noise", noise), aux.get("philox")
+            ctx.groups = groups
             ctx.planes = (x_re.to(dt), None if x_im is None else x_im.to(dt), w_re, w_im,
                           None if ls2 is None else ls2.to(dt), aux.get("eps_re"), aux.get("eps_im"))
             ctx.x_dtype = x_re.dtype
@@ -60,6 +62,7 @@ class _ConvFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         B, C, H, W = x_re.shape
         O, _, kh, kw = w_re.shape
+        G = ctx.groups
         stride, padding, dilation = ctx.geom
         Ho = (H + 2 * padding[0] - dilation[0] * (kh - 1) - 1) // stride[0] + 1
         Wo = (W + 2 * padding[1] - dilation[1] * (kw - 1) - 1) // stride[1] + 1
@@ -69,9 +72,9 @@ class _ConvFn(torch.autograd.Function):
 
         dx_re = dx_im = dw_re = dw_im = db_re = db_im = dls2 = None
         if need[0] or (cplx and need[1]):
-            dx_re, dx_im = _conv_dgrad(g_re, g_im, w_re, w_im, (H, W), ctx.geom)
+            dx_re, dx_im = _conv_dgrad(g_re, g_im, w_re, w_im, (H, W), ctx.geom, G)
         if need[2] or (cplx and need[3]):
-            dw_re, dw_im = _conv_wgrad(g_re, g_im, x_re, x_im, (kh, kw), ctx.geom)
+            dw_re, dw_im = _conv_wgrad_grouped(g_re, g_im, x_re, x_im, (kh, kw), ctx.geom, G)
         if ctx.has_bias and (need[4] or (cplx and need[5])):
             rows = lambda g: g.permute(0, 2, 3, 1).reshape(-1, O).contiguous()
             db_re = ops._colsum(rows(g_re))
@@ -84,7 +87,8 @@ class _ConvFn(torch.autograd.Function):
                     "supported; use the torch-exact layout (default) or pass eps")
             E = ops._eltwise(ops.TR_EXP, ls2)
             q = ops._eltwise(ops.TR_ABS2, x_re, x_im) if cplx else ops._eltwise(ops.TR_SQR, x_re)
-            s2, _, _ = _conv2d_raw(q, None, E, None, None, None, None, None, None, nv.NOISE_INJECT, ctx.geom)
+            s2, _, _ = _conv2d_raw(q, None, E, None, None, None, None, None, None, nv.NOISE_INJECT,
+                                   ctx.geom, G)
             gs2 = torch.empty_like(s2)
             seed, offset, threads = ctx.philox or (0, 0, 0)
             with torch.cuda.device(dev):
@@ -93,29 +97,30 @@ class _ConvFn(torch.autograd.Function):
                     seed, offset, threads, nv.ptr(gs2), s2.numel() // Wo, Wo, nv.dtype_code(dt),
                     nv.stream_ptr(dev)))
             if need[0] or need[1]:
-                dq, _ = _conv_dgrad(gs2, None, E, None, (H, W), ctx.geom)
+                dq, _ = _conv_dgrad(gs2, None, E, None, (H, W), ctx.geom, G)
                 with torch.cuda.device(dev):
                     nv.check(nv.lib().cplxk_vd_grad_input(
                         nv.ptr(dx_re), nv.ptr(dx_im), nv.ptr(x_re.contiguous()),
                         nv.ptr(None if x_im is None else x_im.contiguous()), nv.ptr(dq), dq.numel(),
                         nv.dtype_code(dt), nv.stream_ptr(dev)))
             if need[6]:
-                dE, _ = _conv_wgrad(gs2, None, q, None, (kh, kw), ctx.geom)
+                dE, _ = _conv_wgrad_grouped(gs2, None, q, None, (kh, kw), ctx.geom, G)
                 dls2 = torch.empty_like(dE)
                 with torch.cuda.device(dev):
                     nv.check(nv.lib().cplxk_mul_exp(nv.ptr(dE), nv.ptr(ls2.contiguous()), nv.ptr(dls2),
                                                     dE.numel(), nv.dtype_code(dt), 0, nv.stream_ptr(dev)))
         cast = lambda t: None if t is None else (t if t.dtype == ctx.x_dtype else t.to(ctx.x_dtype))
-        return (cast(dx_re), cast(dx_im), dw_re, dw_im, db_re, db_im, dls2, None, None, None, None)
+        return (cast(dx_re), cast(dx_im), dw_re, dw_im, db_re, db_im, dls2, None, None, None, None, None)
 
 
-def _conv_dgrad(g_re, g_im, w_re, w_im, in_hw, geom):
+def _conv_dgrad(g_re, g_im, w_re, w_im, in_hw, geom, groups=1):
     """dx = g (*) conj(W) as a forward conv: zero-dilate g by the stride, pad by d(k-1) - p,
-    correlate with W'[c, o, r, s] = conj(W[o, c, kh-1-r, kw-1-s]) at the forward's dilation."""
+    correlate with W'[c, o, r, s] = conj(W[o, c, kh-1-r, kw-1-s]) at the forward's dilation
+    (grouped: the same inside every group, still one launch)."""
     stride, padding, dilation = geom
     H, W = in_hw
     B, O, Ho, Wo = g_re.shape
-    _, C, kh, kw = w_re.shape
+    _, Cg, kh, kw = w_re.shape
     ph, pw = dilation[0] * (kh - 1) - padding[0], dilation[1] * (kw - 1) - padding[1]
     if ph < 0 or pw < 0:
         raise NotImplementedError("conv backward needs padding <= dilation * (kernel_size - 1)")
@@ -134,12 +139,16 @@ def _conv_dgrad(g_re, g_im, w_re, w_im, in_hw, geom):
         out[:, :, :gh:stride[0], :gw:stride[1]] = g      # scatter (data movement)
         return out
 
-    flip = lambda w: None if w is None else w.flip(2, 3).transpose(0, 1).contiguous()
+    def flip(w):       # [G*Og, Cg, kh, kw] -> [G*Cg, Og, kh, kw], taps reversed
+        if w is None:
+            return None
+        w = w.flip(2, 3).reshape(groups, O // groups, Cg, kh, kw).transpose(1, 2)
+        return w.reshape(groups * Cg, O // groups, kh, kw).contiguous()
     wr, wi = flip(w_re), flip(w_im)
     if wi is not None:
         wi = ops._eltwise(ops.TR_NEG, wi)                 # conj
     dx_re, dx_im, _ = _conv2d_raw(dilate(g_re), dilate(g_im), wr, wi, None, None, None, None, None,
-                                  nv.NOISE_INJECT, ((1, 1), (ph, pw), dilation))
+                                  nv.NOISE_INJECT, ((1, 1), (ph, pw), dilation), groups)
 
     def fit(t):      # (defensive) crop to the input size
         if t is None or tuple(t.shape[2:]) == (H, W):
@@ -178,7 +187,45 @@ def _conv_wgrad(g_re, g_im, x_re, x_im, khw, geom, max_bytes=1 << 29):
     return dw_re.reshape(shape), None if dw_im is None else dw_im.reshape(shape)
 
 
-def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, geom):
+def _conv_wgrad_grouped(g_re, g_im, x_re, x_im, khw, geom, groups):
+    """Grouped layers: the weight gradient of a group only sees its own channel slices -- one
+    GEMM (chain) per group."""
+    if groups == 1:
+        return _conv_wgrad(g_re, g_im, x_re, x_im, khw, geom)
+    cin, cout = x_re.shape[1] // groups, g_re.shape[1] // groups
+    re, im = [], []
+    for gi in range(groups):
+        ci, co = slice(gi * cin, (gi + 1) * cin), slice(gi * cout, (gi + 1) * cout)
+        a, b = _conv_wgrad(g_re[:, co].contiguous(), None if g_im is None else g_im[:, co].contiguous(),
+                           x_re[:, ci].contiguous(), None if x_im is None else x_im[:, ci].contiguous(),
+                           khw, geom)
+        re.append(a), im.append(b)
+    return torch.cat(re, 0), None if g_im is None else torch.cat(im, 0)
+
+
+def _conv2d_raw_per_group(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, geom, groups):
+    """One C-ABI call per group: only for what the single-launch grouped kernel cannot take
+    (exact-fp32 'simt' math mode, geometries outside the TMA box limits).  The layer's noise is
+    still ONE draw (torch layout), injected slice by slice."""
+    cplx = x_im is not None
+    aux = {}
+    if ls2 is not None and noise != nv.NOISE_INJECT:
+        Ho, Wo = _out_hw(x_re, w_re, geom)
+        eps_re, eps_im = _draw_noise(cplx, (x_re.shape[0], w_re.shape[0], Ho, Wo), x_re.device, w_re.dtype)
+        noise = nv.NOISE_INJECT
+    cin, cout = x_re.shape[1] // groups, w_re.shape[0] // groups
+    sl = lambda t, s, d=0: None if t is None else (t[s] if d == 0 else t[:, s])
+    re, im = [], []
+    for gi in range(groups):
+        ci, co = slice(gi * cin, (gi + 1) * cin), slice(gi * cout, (gi + 1) * cout)
+        a, b, _ = _conv2d_raw(sl(x_re, ci, 1), sl(x_im, ci, 1), sl(w_re, co), sl(w_im, co), sl(b_re, co),
+                              sl(b_im, co), sl(ls2, co), sl(eps_re, co, 1), sl(eps_im, co, 1), noise, geom)
+        re.append(a), im.append(b)
+    aux.update(noise=noise, philox=(0, 0, 0), eps_re=eps_re, eps_im=eps_im)
+    return torch.cat(re, 1), torch.cat(im, 1) if cplx else None, aux
+
+
+def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, geom, groups=1):
     stride, padding, dilation = geom
     dev = nv.require_cuda(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im)
     dt = w_re.dtype
@@ -186,8 +233,10 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
     cplx = x_im is not None
     B, C, H, W = x_re.shape
     O, Cw, kh, kw = w_re.shape
-    if Cw != C:
-        raise RuntimeError(f"expected input with {Cw} channels, got {C}")
+    if groups < 1 or C % groups or O % groups:
+        raise ValueError("in_channels and out_channels must be divisible by groups")
+    if Cw * groups != C:
+        raise RuntimeError(f"expected input with {Cw * groups} channels, got {C}")
     Ho = (H + 2 * padding[0] - dilation[0] * (kh - 1) - 1) // stride[0] + 1
     Wo = (W + 2 * padding[1] - dilation[1] * (kw - 1) - 1) // stride[1] + 1
     if Ho <= 0 or Wo <= 0:
@@ -196,7 +245,7 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
     # torch.channels_last activations (NCHW shape, NHWC strides) are consumed in place by the
     # tensor-core path and the output keeps that memory format, as F.conv2d would
     gran = 8 if dt == torch.float32 else 16
-    cl = (cplx and math != nv.MATH_SIMT and C % gran == 0 and C > 1
+    cl = (cplx and groups == 1 and math != nv.MATH_SIMT and C % gran == 0 and C > 1
           and x_re.dtype == dt and x_im.dtype == dt
           and x_re.is_contiguous(memory_format=torch.channels_last) and not x_re.is_contiguous()
           and x_im.is_contiguous(memory_format=torch.channels_last))
@@ -222,17 +271,18 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
             numel = (2 if cplx else 1) * y_re.numel()
             gen, seed, offset, threads, inc = nv.philox_plan(dev, max(numel, 1), noise == nv.NOISE_PHILOX_TORCH)
     ws, ws_bytes = None, 0
-    if cplx and math != nv.MATH_SIMT:
-        ws_bytes = nv.lib().cplxk_conv2d_workspace_bytes(B, C, H, W, O, kh, kw, code,
-                                                         1 if ls2 is not None else 0)
+    if math != nv.MATH_SIMT:
+        # complex AND real planes run the tcgen05 implicit GEMM (real: one A tile, one accumulator)
+        ws_bytes = nv.lib().cplxk_conv2d_workspace_bytes_g(B, C, H, W, O, kh, kw, groups, 1 if cplx else 0,
+                                                           code, 1 if ls2 is not None else 0)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     def call(xr, xi, y_re, y_im, cl):
         with torch.cuda.device(dev):
-            return nv.lib().cplxk_conv2d_fwd(
+            return nv.lib().cplxk_conv2d_fwd_g(
                 nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi), nv.ptr(br), nv.ptr(bi), nv.ptr(l2),
                 nv.ptr(er), nv.ptr(ei), mode, seed, offset, threads, nv.ptr(y_re), nv.ptr(y_im),
                 B, C, H, W, O, kh, kw, stride[0], stride[1], padding[0], padding[1],
-                dilation[0], dilation[1], code, math, 1 if cl else 0, nv.ptr(ws), ws_bytes,
+                dilation[0], dilation[1], groups, code, math, 1 if cl else 0, nv.ptr(ws), ws_bytes,
                 nv.stream_ptr(dev))
 
     rc = call(xr, xi, y_re, y_im, cl)
@@ -243,6 +293,9 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
         y_re = torch.empty((B, O, Ho, Wo), dtype=dt, device=dev)
         y_im = torch.empty_like(y_re)
         rc = call(xr, xi, y_re, y_im, False)
+    if groups > 1 and rc == nv.ERR_UNSUPPORTED:
+        return _conv2d_raw_per_group(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise,
+                                     geom, groups)
     nv.check(rc)
     if gen is not None:
         gen.set_offset(offset + inc)
@@ -308,30 +361,8 @@ def cplx_convnd(nd, input, weight, bias=None, stride=1, padding=0, dilation=1, g
         # the private 'fast' layout of the conv kernels is not regenerated by the backward: under
         # autograd the forward uses the torch-exact layout instead (same distribution)
         noise = nv.NOISE_PHILOX_TORCH
-    if groups > 1 and ls2 is not None and e is None:
-        # one launch covers one group, the layer's noise is ONE draw: make it, then inject slices
-        Ho, Wo = _out_hw(x_re, w_re, geom)
-        e = _draw_noise(True, (x_re.shape[0], w_re.shape[0], Ho, Wo), x_re.device, w_re.dtype)
-        noise = nv.NOISE_INJECT
-
-    def run(xr, xi, wr, wi, br, bi, l2, ee):
-        er, ei = (None, None) if ee is None else ee
-        return _ConvFn.apply(xr, xi, wr, wi, br, bi, l2, er, ei, noise, geom)
-
-    if groups == 1:
-        re, im = run(x_re, x_im, w_re, w_im, b_re, b_im, ls2, e)
-    else:
-        cin, cout = x_re.shape[1] // groups, w_re.shape[0] // groups
-        outs = []
-        for gi in range(groups):
-            ci, co = slice(gi * cin, (gi + 1) * cin), slice(gi * cout, (gi + 1) * cout)
-            ee = None if e is None else (e[0][:, co], e[1][:, co])
-            outs.append(Cplx(*run(x_re[:, ci], x_im[:, ci], w_re[co], w_im[co],
-                                  None if b_re is None else b_re[co],
-                                  None if b_im is None else b_im[co],
-                                  None if ls2 is None else ls2[co], ee)))
-        out = cat(outs, dim=1)
-        re, im = out.real, out.imag
+    er, ei = (None, None) if e is None else e
+    re, im = _ConvFn.apply(x_re, x_im, w_re, w_im, b_re, b_im, ls2, er, ei, noise, geom, groups)
     if nd == 1:
         re, im = re.squeeze(2), im.squeeze(2)
     return Cplx(re, im)
@@ -355,22 +386,5 @@ def real_convnd(nd, input, weight, bias=None, stride=1, padding=0, dilation=1, g
     noise = nv.NOISE_INJECT if e is not None else ops._NOISE[ops.get_noise_mode()]
     if ls2 is not None and noise == nv.NOISE_PHILOX_FAST and _grad_wanted(x, w, ls2):
         noise = nv.NOISE_PHILOX_TORCH       # see cplx_convnd
-    if groups > 1 and ls2 is not None and e is None:
-        Ho, Wo = _out_hw(x, w, geom)
-        e, _ = _draw_noise(False, (x.shape[0], w.shape[0], Ho, Wo), x.device, w.dtype)
-        noise = nv.NOISE_INJECT
-
-    def run(x_, w_, b_, l2_, e_):
-        return _ConvFn.apply(x_, None, w_, None, b_, None, l2_, e_, None, noise, geom)[0]
-
-    if groups == 1:
-        out = run(x, w, bias, ls2, e)
-    else:
-        cin, cout = x.shape[1] // groups, w.shape[0] // groups
-        outs = []
-        for gi in range(groups):
-            ci, co = slice(gi * cin, (gi + 1) * cin), slice(gi * cout, (gi + 1) * cout)
-            outs.append(run(x[:, ci], w[co], None if bias is None else bias[co],
-                            None if ls2 is None else ls2[co], None if e is None else e[:, co]))
-        out = torch.cat(outs, dim=1)
+    out = _ConvFn.apply(x, None, w, None, bias, None, ls2, e, None, noise, geom, groups)[0]
     return out.squeeze(2) if nd == 1 else out

@@ -203,19 +203,20 @@ static int launch_conv(const void* x_re, const void* x_im, const void* w_re, con
 
 using namespace cplxk;
 
-extern "C" int cplxk_conv2d_fwd(const void* x_re, const void* x_im, const void* w_re,
-                                const void* w_im, const void* b_re, const void* b_im,
-                                const void* log_sigma2, const void* eps_re, const void* eps_im,
-                                int noise, uint64_t seed, uint64_t offset, uint32_t philox_threads,
-                                void* y_re, void* y_im, int64_t B, int64_t C, int64_t H, int64_t W,
-                                int64_t O, int64_t kh, int64_t kw, int64_t stride_h,
-                                int64_t stride_w, int64_t pad_h, int64_t pad_w, int64_t dil_h,
-                                int64_t dil_w, int dtype, int math, int channels_last,
-                                void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int cplxk_conv2d_fwd_g(const void* x_re, const void* x_im, const void* w_re,
+                                  const void* w_im, const void* b_re, const void* b_im,
+                                  const void* log_sigma2, const void* eps_re, const void* eps_im,
+                                  int noise, uint64_t seed, uint64_t offset, uint32_t philox_threads,
+                                  void* y_re, void* y_im, int64_t B, int64_t C, int64_t H, int64_t W,
+                                  int64_t O, int64_t kh, int64_t kw, int64_t stride_h,
+                                  int64_t stride_w, int64_t pad_h, int64_t pad_w, int64_t dil_h,
+                                  int64_t dil_w, int64_t groups, int dtype, int math, int channels_last,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
   if (!x_re || !w_re || !y_re) return CPLXK_ERR_BADARG;
   if (B < 0 || C < 1 || H < 1 || W < 1 || O < 0 || kh < 1 || kw < 1 || stride_h < 1 ||
       stride_w < 1 || pad_h < 0 || pad_w < 0 || dil_h < 1 || dil_w < 1)
     return CPLXK_ERR_BADARG;
+  if (groups < 1 || groups > 0x7fffffff || C % groups || O % groups) return CPLXK_ERR_BADARG;
   const bool cplx = x_im != nullptr;
   if (cplx != (w_im != nullptr) || cplx != (y_im != nullptr)) return CPLXK_ERR_BADARG;
   if (b_re && cplx && !b_im) return CPLXK_ERR_BADARG;
@@ -250,13 +251,18 @@ extern "C" int cplxk_conv2d_fwd(const void* x_re, const void* x_im, const void* 
   ep.noise.scale = cplx ? (1.0f / static_cast<float>(1.4142135623730951)) : 1.0f;
 
   auto st = static_cast<cudaStream_t>(stream);
-  // tensor-core implicit GEMM: complex, workspace supplied, geometry within the TMA box limits
-  const bool tc_ok = cplx && workspace != nullptr && aligned16(workspace) && aligned16(x_re) &&
-                     conv_tc_supported(dtype, B, C, H, W, O, g.Ho, g.Wo, g.kh, g.kw, g.sh, g.sw) &&
-                     workspace_bytes >= conv_tc_workspace_bytes(dtype, vd, B, C, H, W, O, kh, kw);
+  // tensor-core implicit GEMM: workspace supplied, geometry within the TMA box limits.  Complex
+  // planes with groups == 1 take the CTA-pair / persistent kernels; real planes and grouped
+  // convolutions the one-tile-per-CTA kernel (a group = one more factor of the n-block index).
+  const int ng = static_cast<int>(groups);
+  const bool tc_ok = workspace != nullptr && aligned16(workspace) && aligned16(x_re) &&
+                     (cplx || !channels_last) &&
+                     conv_tc_supported(dtype, B, C, H, W, O, g.Ho, g.Wo, g.kh, g.kw, g.sh, g.sw, ng, !cplx) &&
+                     workspace_bytes >= conv_tc_workspace_bytes(dtype, vd, B, C, H, W, O, kh, kw, ng, !cplx);
   if (math < CPLXK_MATH_AUTO || math > CPLXK_MATH_TENSOR_TF32) return CPLXK_ERR_BADARG;
   if (math == CPLXK_MATH_TENSOR && !tc_ok) return workspace ? CPLXK_ERR_UNSUPPORTED : CPLXK_ERR_WORKSPACE;
   if (channels_last && !(tc_ok && math != CPLXK_MATH_SIMT)) return CPLXK_ERR_UNSUPPORTED;  // NHWC: TC path only
+  if (channels_last && ng > 1) return CPLXK_ERR_UNSUPPORTED;
   if (math != CPLXK_MATH_SIMT && tc_ok) {
     ConvTcEpi te;
     te.b_re = b_re, te.b_im = b_im, te.eps_re = eps_re, te.eps_im = eps_im;
@@ -264,8 +270,10 @@ extern "C" int cplxk_conv2d_fwd(const void* x_re, const void* x_im, const void* 
     te.nhwc = channels_last ? 1 : 0;
     te.f16_ok = math != CPLXK_MATH_TENSOR_TF32;
     return conv_tc_dispatch(dtype, vd, channels_last != 0, x_re, x_im, w_re, w_im, log_sigma2, workspace, B, C, H, W, O,
-                            g.Ho, g.Wo, g.kh, g.kw, g.sh, g.sw, g.ph, g.pw, g.dh, g.dw, te, st);
+                            g.Ho, g.Wo, g.kh, g.kw, g.sh, g.sw, g.ph, g.pw, g.dh, g.dw, te, st, ng);
   }
+  // the exact-fp32 CUDA-core kernel covers one group per launch: the caller loops
+  if (ng > 1) return CPLXK_ERR_UNSUPPORTED;
 #define CPLXK_CONV_CASE(T)                                                                  \
   if (cplx && vd) return launch_conv<T, true, true>(x_re, x_im, w_re, w_im, log_sigma2, g, ep, st);   \
   if (cplx && !vd) return launch_conv<T, true, false>(x_re, x_im, w_re, w_im, log_sigma2, g, ep, st); \
@@ -277,8 +285,32 @@ extern "C" int cplxk_conv2d_fwd(const void* x_re, const void* x_im, const void* 
   return CPLXK_ERR_BADARG;
 }
 
+extern "C" int cplxk_conv2d_fwd(const void* x_re, const void* x_im, const void* w_re,
+                                const void* w_im, const void* b_re, const void* b_im,
+                                const void* log_sigma2, const void* eps_re, const void* eps_im,
+                                int noise, uint64_t seed, uint64_t offset, uint32_t philox_threads,
+                                void* y_re, void* y_im, int64_t B, int64_t C, int64_t H, int64_t W,
+                                int64_t O, int64_t kh, int64_t kw, int64_t stride_h,
+                                int64_t stride_w, int64_t pad_h, int64_t pad_w, int64_t dil_h,
+                                int64_t dil_w, int dtype, int math, int channels_last,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  return cplxk_conv2d_fwd_g(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise, seed,
+                            offset, philox_threads, y_re, y_im, B, C, H, W, O, kh, kw, stride_h, stride_w,
+                            pad_h, pad_w, dil_h, dil_w, 1, dtype, math, channels_last, workspace,
+                            workspace_bytes, stream);
+}
+
+extern "C" size_t cplxk_conv2d_workspace_bytes_g(int64_t B, int64_t C, int64_t H, int64_t W, int64_t O,
+                                                 int64_t kh, int64_t kw, int64_t groups, int is_complex,
+                                                 int dtype, int variational) {
+  if (B < 0 || C < 1 || H < 1 || W < 1 || O < 0 || kh < 1 || kw < 1 || groups < 1 || C % groups ||
+      O % groups)
+    return 0;
+  return conv_tc_workspace_bytes(dtype, variational != 0, B, C, H, W, O, kh, kw,
+                                 static_cast<int>(groups), is_complex == 0);
+}
+
 extern "C" size_t cplxk_conv2d_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t O,
                                                int64_t kh, int64_t kw, int dtype, int variational) {
-  if (B < 0 || C < 1 || H < 1 || W < 1 || O < 0 || kh < 1 || kw < 1) return 0;
-  return conv_tc_workspace_bytes(dtype, variational != 0, B, C, H, W, O, kh, kw);
+  return cplxk_conv2d_workspace_bytes_g(B, C, H, W, O, kh, kw, 1, 1, dtype, variational);
 }

@@ -59,7 +59,7 @@ conv_nhwc_kernel(const T* __restrict__ x_re, const T* __restrict__ x_im, T* __re
     if (c < C && w < W) {
       const int64_t off = ((b * C + c) * H + h) * W + w;
       vr = Elem<T>::to_f(x_re[off]);
-      vi = Elem<T>::to_f(x_im[off]);
+      if (x_im) vi = Elem<T>::to_f(x_im[off]);        // real planes: x_im == nullptr
     }
     s_re[ty + 8 * i][tx] = vr;
     s_im[ty + 8 * i][tx] = vi;
@@ -72,7 +72,7 @@ conv_nhwc_kernel(const T* __restrict__ x_re, const T* __restrict__ x_im, T* __re
       const float vr = s_re[tx][ty + 8 * i], vi = s_im[tx][ty + 8 * i];
       const int64_t off = ((b * H + h) * W + w) * Cp + c;
       o_re[off] = Elem<T>::from_f(round_mma_operand<T>(vr));
-      o_im[off] = Elem<T>::from_f(round_mma_operand<T>(vi));
+      if (o_im) o_im[off] = Elem<T>::from_f(round_mma_operand<T>(vi));
       if constexpr (kVD) o_q[off] = Elem<T>::from_f(round_mma_operand<T>(fmaf(vr, vr, vi * vi)));
     }
   }
@@ -123,28 +123,32 @@ conv_nhwc_bf16_v8_kernel(const __nv_bfloat16* __restrict__ x_re, const __nv_bflo
   }
 }
 
-// weights [O, C, kh, kw] -> tap-major planes [(r*kw+s) * Op + o][Cp]; E = exp(log_sigma2)
+// weights [O, tCg, kh, kw] -> tap-major planes [(r*kw+s) * Op + grp * Ogp + o][Cgp], grp / o / c
+// counting (super-)groups of Og output and Cg input channels; a super-group packs Og / tOg true
+// groups block-diagonally (tCg x tOg blocks, zeros elsewhere).  E = exp(log_sigma2) (zero off the
+// diagonal: exp is only taken of entries that exist).  Real planes: w_im == v == nullptr.
 template <typename T, bool kVD>
 __global__ void __launch_bounds__(256)
 conv_wprep_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T* __restrict__ ls2,
-                  T* __restrict__ u, T* __restrict__ v, T* __restrict__ e, int O, int Op, int C,
-                  int Cp, int khw) {
-  const int64_t total = static_cast<int64_t>(khw) * Op * Cp;
+                  T* __restrict__ u, T* __restrict__ v, T* __restrict__ e, int Og, int Ogp, int Op,
+                  int Cg, int Cgp, int tOg, int tCg, int khw) {
+  const int64_t total = static_cast<int64_t>(khw) * Op * Cgp;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % Cp);
-    const int64_t t = i / Cp;
-    const int o = static_cast<int>(t % Op);
+    const int c = static_cast<int>(i % Cgp);
+    const int64_t t = i / Cgp;
+    const int op = static_cast<int>(t % Op);
     const int rs = static_cast<int>(t / Op);
+    const int grp = op / Ogp, o = op - grp * Ogp;
     float fu = 0.f, fv = 0.f, fe = 0.f;
-    if (o < O && c < C) {
-      const int64_t src = (static_cast<int64_t>(o) * C + c) * khw + rs;
+    if (o < Og && c < Cg && o / tOg == c / tCg) {
+      const int64_t src = (static_cast<int64_t>(grp * Og + o) * tCg + (c % tCg)) * khw + rs;
       fu = Elem<T>::to_f(w_re[src]);
-      fv = Elem<T>::to_f(w_im[src]);
+      if (w_im) fv = Elem<T>::to_f(w_im[src]);
       if constexpr (kVD) fe = __expf(Elem<T>::to_f(ls2[src]));
     }
     u[i] = Elem<T>::from_f(round_mma_operand<T>(fu));
-    v[i] = Elem<T>::from_f(round_mma_operand<T>(fv));
+    if (v) v[i] = Elem<T>::from_f(round_mma_operand<T>(fv));
     if constexpr (kVD) e[i] = Elem<T>::from_f(round_mma_operand<T>(fe));
   }
 }
@@ -180,13 +184,14 @@ __device__ __forceinline__ void conv_store_nchw(T* __restrict__ q, int64_t hw, i
 template <typename T>
 __device__ __forceinline__ void conv_store8(T* __restrict__ y, const ConvTcGeom& g, bool nhwc,
                                             int64_t nchw_off, int64_t hw, int64_t nhwc_off, int o0,
-                                            const float (&v)[8]) {
+                                            const float (&v)[8], int o_end = -1) {
+  if (o_end < 0) o_end = static_cast<int>(g.O);      // grouped: end of the group's channels
   if (!nhwc) {
-    conv_store_nchw<T, 8>(y + nchw_off + static_cast<int64_t>(o0) * hw, hw, static_cast<int>(g.O) - o0, v);
+    conv_store_nchw<T, 8>(y + nchw_off + static_cast<int64_t>(o0) * hw, hw, o_end - o0, v);
     return;
   }
   T* dst = y + nhwc_off + o0;
-  if (o0 + 8 <= g.O && (g.O & 7) == 0) {
+  if (o0 + 8 <= o_end && ((g.O | o0) & 7) == 0) {
     if constexpr (std::is_same<T, float>::value) {
       asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(v[0]),
                    "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
@@ -203,7 +208,7 @@ __device__ __forceinline__ void conv_store8(T* __restrict__ y, const ConvTcGeom&
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j)
-    if (o0 + j < g.O) dst[j] = Elem<T>::from_f(v[j]);
+    if (o0 + j < o_end) dst[j] = Elem<T>::from_f(v[j]);
 }
 
 // Sixteen consecutive output channels of one pixel: NHWC bf16 rows are written as ONE 32-byte
@@ -378,15 +383,17 @@ conv_nhwc_f16_v4_kernel(const float* __restrict__ x_re, const float* __restrict_
   }
 }
 
-// weights [O, C, kh, kw] fp32 -> tap-major fp16 planes [(r*kw+s) * Op + o][Cp], one block per
-// output channel: its own power-of-two scale, inverse to isw[o]
+// weights [O, tCg, kh, kw] fp32 -> tap-major fp16 planes [(r*kw+s) * Op + o][Cp], one block per
+// output channel: its own power-of-two scale, inverse to isw[o].  tCg < C: grouped layer packed
+// block-diagonally (output channel o reads input channels [o / tOg * tCg, + tCg)).
 __global__ void __launch_bounds__(256)
 conv_wprep_f16_kernel(const float* __restrict__ w_re, const float* __restrict__ w_im,
                       __half* __restrict__ u, __half* __restrict__ v, float* __restrict__ isw, int O,
-                      int Op, int C, int Cp, int khw) {
+                      int Op, int C, int Cp, int tOg, int tCg, int khw) {
   __shared__ unsigned int red[8];
   const int o = blockIdx.x;
-  const int n = C * khw;
+  const int n = tCg * khw;
+  const int c_lo = (o / tOg) * tCg;
   unsigned int m = 0u;
   if (o < O) {
     for (int i = threadIdx.x; i < n; i += 256) {
@@ -412,8 +419,8 @@ conv_wprep_f16_kernel(const float* __restrict__ w_re, const float* __restrict__ 
   for (int i = threadIdx.x; i < khw * Cp; i += 256) {
     const int rs = i / Cp, c = i - rs * Cp;
     float fu = 0.f, fv = 0.f;
-    if (o < O && c < C) {
-      const int64_t src = (static_cast<int64_t>(o) * C + c) * khw + rs;
+    if (o < O && c >= c_lo && c < c_lo + tCg) {
+      const int64_t src = (static_cast<int64_t>(o) * tCg + (c - c_lo)) * khw + rs;
       fu = w_re[src] * scale, fv = w_im[src] * scale;
     }
     const int64_t dst = (static_cast<int64_t>(rs) * Op + o) * Cp + c;
@@ -422,34 +429,39 @@ conv_wprep_f16_kernel(const float* __restrict__ w_re, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------ main kernel
-template <typename T, bool kVD>
+// kReal: real planes.  One A tile (x) per k-block, the 128-row B tile holds 128 REAL output
+// channels (two 64-row boxes of the one weight plane), one accumulator (+ one for the variance):
+// the tensor pipe does exactly the multiplies a real convolution has.
+template <typename T, bool kVD, bool kReal = false>
 struct ConvCfg {
   static constexpr bool kBF16 = std::is_same<T, __nv_bfloat16>::value;
-  static constexpr int BM = 128, BNO = 64;                 // pixels x complex output channels
+  static constexpr int BM = 128, BNO = kReal ? 128 : 64;   // pixels x output channels (complex: stacked [U;V])
   static constexpr int BKC = 128 / static_cast<int>(sizeof(T));  // channels per k-block
   static constexpr int KSTEPS = 4;
   static constexpr int A_TILE = 128 * 128;                 // 16 KB
-  static constexpr int OFF_XR = 0, OFF_XI = A_TILE, OFF_Q = 2 * A_TILE;
-  static constexpr int OFF_UV = (kVD ? 3 : 2) * A_TILE;    // [U(64 rows); V(64 rows)] = 16 KB
-  static constexpr int OFF_E = OFF_UV + A_TILE;            // 64 rows = 8 KB
-  static constexpr int STAGE_BYTES = OFF_UV + A_TILE + (kVD ? A_TILE / 2 : 0);
-  static constexpr int STAGES = kVD ? 3 : 2;               // VD: 1 CTA/SM, plain: 2 CTAs/SM
-  static constexpr int TMEM_COLS = kVD ? 512 : 256;        // D1 128 | D2 128 | (s2 64)
+  static constexpr int OFF_XR = 0, OFF_XI = A_TILE, OFF_Q = (kReal ? 1 : 2) * A_TILE;
+  static constexpr int OFF_UV = ((kReal ? 1 : 2) + (kVD ? 1 : 0)) * A_TILE;   // 128 rows = 16 KB
+  static constexpr int OFF_E = OFF_UV + A_TILE;            // BNO rows
+  static constexpr int STAGE_BYTES = OFF_E + (kVD ? BNO * 128 : 0);
+  static constexpr int STAGES = (kVD || kReal) ? 3 : 2;    // VD: 1 CTA/SM, plain: 2 CTAs/SM
+  // complex: D1 128 | D2 128 | (s2 64);  real: D1 128 | (s2 128)
+  static constexpr int TMEM_COLS = kReal ? (kVD ? 256 : 128) : (kVD ? 512 : 256);
+  static constexpr int OFF_S2 = kReal ? 128 : 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 1024;
-  // VD: sixteen epilogue warps (four per TMEM lane quarter, 16 channels each).  The kernel is
+  // VD: sixteen epilogue warps (four per TMEM lane quarter).  The kernel is
   // bound by the torch-exact noise (one Philox-10 + Box-Muller per normal, branchy libm inside),
   // and only more resident warps hide its fixed-latency dependency stalls.
   static constexpr int THREADS = kVD ? 576 : 192;
-  static constexpr int CH_PER_WARP = kVD ? 16 : 64;
+  static constexpr int CH_PER_WARP = kVD ? BNO / 4 : BNO;
 };
 
-template <typename T, bool kVD>
+template <typename T, bool kVD, bool kReal = false>
 __global__ void __launch_bounds__((kVD ? 576 : 192), (kVD ? 1 : 2))
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__ CUtensorMap tm_xi,
                const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_u,
                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_e,
                const ConvTcGeom g, const ConvTcEpi ep) {
-  using C = ConvCfg<T, kVD>;
+  using C = ConvCfg<T, kVD, kReal>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -462,7 +474,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // tile -> (n block, w block, h block, image)
+  // tile -> (n block [group, block inside the group], w block, h block, image)
   int t = blockIdx.x;
   const int n_blk = t % g.tiles_n;
   t /= g.tiles_n;
@@ -470,15 +482,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
   t /= g.tiles_w;
   const int h_blk = t % g.tiles_h;
   const int b = t / g.tiles_h;
-  const int ow0 = w_blk * g.Wt, oh0 = h_blk * g.Ht, n0 = n_blk * C::BNO;
-  const int cchunks = (g.Cp + C::BKC - 1) / C::BKC;
+  const int grp = n_blk / g.tiles_ng;
+  const int ow0 = w_blk * g.Wt, oh0 = h_blk * g.Ht;
+  const int n0 = (n_blk - grp * g.tiles_ng) * C::BNO;   // first output channel INSIDE the group
+  const int obase = grp * g.Og;                          // the group's first output channel
+  const int cchunks = (g.Cgp + C::BKC - 1) / C::BKC;
   const int num_kb = g.kh * g.kw * cchunks;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_xr);
-    ptx::prefetch_tensormap(&tm_xi);
     ptx::prefetch_tensormap(&tm_u);
-    ptx::prefetch_tensormap(&tm_v);
+    if constexpr (!kReal) {
+      ptx::prefetch_tensormap(&tm_xi);
+      ptx::prefetch_tensormap(&tm_v);
+    }
     if constexpr (kVD) {
       ptx::prefetch_tensormap(&tm_q);
       ptx::prefetch_tensormap(&tm_e);
@@ -514,19 +531,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
         const uint32_t st = base + s * C::STAGE_BYTES;
         const int rs = kb / cchunks, cc = kb - rs * cchunks;
         const int r = rs / g.kw, sx = rs - r * g.kw;
-        const int32_t c0 = cc * C::BKC;
+        const int32_t cw = cc * C::BKC;                 // channel inside the group (weight planes)
+        const int32_t c0 = grp * g.Cg + cw;             // channel of the activation planes
         // box origin in INPUT coordinates (may be negative: zero padding = OOB fill)
         const int32_t iw = ow0 * g.sw - g.pw + sx * g.dw;
         const int32_t ih = oh0 * g.sh - g.ph + r * g.dh;
-        const int32_t wrow = rs * g.Op + n0;
+        const int32_t wrow = rs * g.Op + grp * g.Ogp + n0;
         if (elected) {
           ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
           ptx::tma_load_4d(st + C::OFF_XR, &tm_xr, fb, c0, iw, ih, b);
-          ptx::tma_load_4d(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
+          if constexpr (!kReal) ptx::tma_load_4d(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
           if constexpr (kVD) ptx::tma_load_4d(st + C::OFF_Q, &tm_q, fb, c0, iw, ih, b);
-          ptx::tma_load_2d(st + C::OFF_UV, &tm_u, fb, c0, wrow);
-          ptx::tma_load_2d(st + C::OFF_UV + C::A_TILE / 2, &tm_v, fb, c0, wrow);
-          if constexpr (kVD) ptx::tma_load_2d(st + C::OFF_E, &tm_e, fb, c0, wrow);
+          ptx::tma_load_2d(st + C::OFF_UV, &tm_u, fb, cw, wrow);
+          if constexpr (kReal) {
+            ptx::tma_load_2d(st + C::OFF_UV + C::A_TILE / 2, &tm_u, fb, cw, wrow + 64);
+            if constexpr (kVD) {
+              ptx::tma_load_2d(st + C::OFF_E, &tm_e, fb, cw, wrow);
+              ptx::tma_load_2d(st + C::OFF_E + C::A_TILE / 2, &tm_e, fb, cw, wrow + 64);
+            }
+          } else {
+            ptx::tma_load_2d(st + C::OFF_UV + C::A_TILE / 2, &tm_v, fb, cw, wrow);
+            if constexpr (kVD) ptx::tma_load_2d(st + C::OFF_E, &tm_e, fb, cw, wrow);
+          }
         }
         __syncwarp();
       }
@@ -535,8 +561,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
     {
       const bool elected = ptx::elect_one();
       constexpr uint32_t idesc128 = ptx::make_idesc<C::kBF16>(128, 128, false, false);
-      constexpr uint32_t idesc64 = ptx::make_idesc<C::kBF16>(128, 64, false, false);
-      const uint32_t t_d1 = tmem_base, t_d2 = tmem_base + 128, t_s2 = tmem_base + 256;
+      constexpr uint32_t idesc_s2 = ptx::make_idesc<C::kBF16>(128, C::BNO, false, false);
+      const uint32_t t_d1 = tmem_base, t_d2 = tmem_base + 128, t_s2 = tmem_base + C::OFF_S2;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % C::STAGES;
         const uint32_t ph = (kb / C::STAGES) & 1;
@@ -554,9 +580,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
             const uint32_t off = k * 32;
             ptx::umma_ss<C::kBF16>(t_d1, ptx::desc_advance(a_r, off), ptx::desc_advance(b_uv, off), idesc128, acc);
-            ptx::umma_ss<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc128, acc);
+            if constexpr (!kReal)
+              ptx::umma_ss<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc128, acc);
             if constexpr (kVD)
-              ptx::umma_ss<C::kBF16>(t_s2, ptx::desc_advance(a_q, off), ptx::desc_advance(b_e, off), idesc64, acc);
+              ptx::umma_ss<C::kBF16>(t_s2, ptx::desc_advance(a_q, off), ptx::desc_advance(b_e, off), idesc_s2, acc);
           }
           ptx::umma_commit(bar_empty + 8 * s);
         }
@@ -575,28 +602,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
     const int64_t hw = g.Ho * g.Wo;
     const int64_t pix_off = static_cast<int64_t>(b) * g.O * hw + oh * g.Wo + ow;  // + o * hw
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int o_end = obase + g.Og;               // one past the group's last output channel
 
-    // VD: the 2 x 32 normals (this warp's half of the tile's channels) of this pixel (one per output channel and plane) are generated /
-    // fetched while the MMAs run and stay in registers.  Consecutive channels are `hw` apart in
-    // torch's linear element order, so (subsequence, slot) advance by a constant -- no division.
+    // VD: the normals of this pixel for this warp's share of the tile's channels (one per output
+    // channel and plane) are generated / fetched while the MMAs run and stay in registers.
+    // Consecutive channels are `hw` apart in torch's linear element order, so (subsequence, slot)
+    // advance by a constant -- no division.
     constexpr int NCH = C::CH_PER_WARP;            // channels this thread owns
     const int cbase = kVD ? ((warp - 2) >> 2) * NCH : 0;   // first of them inside the tile
-    float nre[kVD ? NCH : 1], nim[kVD ? NCH : 1];
+    const int ofirst = obase + n0 + cbase;         // ... as a channel of the layer
+    float nre[kVD ? NCH : 1], nim[(kVD && !kReal) ? NCH : 1];
     if constexpr (kVD) {
 #pragma unroll
-      for (int j = 0; j < NCH; ++j) nre[j] = 0.f, nim[j] = 0.f;
+      for (int j = 0; j < NCH; ++j) {
+        nre[j] = 0.f;
+        if constexpr (!kReal) nim[j] = 0.f;
+      }
       if (pix_ok) {
         if (ep.noise.mode == CPLXK_NOISE_INJECT) {
 #pragma unroll
           for (int j = 0; j < NCH; ++j)
-            if (n0 + cbase + j < g.O) {
-              const int64_t off = pix_off + static_cast<int64_t>(n0 + cbase + j) * hw;
+            if (ofirst + j < o_end) {
+              const int64_t off = pix_off + static_cast<int64_t>(ofirst + j) * hw;
               nre[j] = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.eps_re) + off));
-              nim[j] = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.eps_im) + off));
+              if constexpr (!kReal) nim[j] = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.eps_im) + off));
             }
         } else if (ep.noise.mode == CPLXK_NOISE_PHILOX_TORCH) {
           const uint32_t T_ = ep.noise.threads;
-          const uint64_t li0 = static_cast<uint64_t>(pix_off + static_cast<int64_t>(n0 + cbase) * hw);
+          const uint64_t li0 = static_cast<uint64_t>(pix_off + static_cast<int64_t>(ofirst) * hw);
           uint64_t slot_re = li0 / T_;
           uint32_t idx_re = static_cast<uint32_t>(li0 - slot_re * T_);
           const uint64_t li1 = li0 + static_cast<uint64_t>(ep.plane_elems);
@@ -607,7 +640,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
 #pragma unroll 1
           for (int trip = 0; trip < NCH / 8; ++trip) {
 #pragma unroll
-            for (int j = 0; j < NCH - 8; ++j) nre[j] = nre[j + 8], nim[j] = nim[j + 8];
+            for (int j = 0; j < NCH - 8; ++j) {
+              nre[j] = nre[j + 8];
+              if constexpr (!kReal) nim[j] = nim[j + 8];
+            }
             uint32_t ir[8], ii[8];
             uint64_t sr[8], si[8];
 #pragma unroll
@@ -621,20 +657,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               nre[NCH - 8 + j] = philox_torch_normal(ir[j], sr[j], ep.noise) * ep.noise.scale;
-              nim[NCH - 8 + j] = philox_torch_normal(ii[j], si[j], ep.noise) * ep.noise.scale;
+              if constexpr (!kReal)
+                nim[NCH - 8 + j] = philox_torch_normal(ii[j], si[j], ep.noise) * ep.noise.scale;
             }
           }
         } else {
 #pragma unroll 1
           for (int trip = 0; trip < NCH / 8; ++trip) {
 #pragma unroll
-            for (int j = 0; j < NCH - 8; ++j) nre[j] = nre[j + 8], nim[j] = nim[j + 8];
+            for (int j = 0; j < NCH - 8; ++j) {
+              nre[j] = nre[j + 8];
+              if constexpr (!kReal) nim[j] = nim[j + 8];
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int64_t off = pix_off + static_cast<int64_t>(n0 + cbase + trip * 8 + j) * hw;
-              const float2 z = philox_fast_pair(static_cast<uint64_t>(off), ep.noise);
-              nre[NCH - 8 + j] = z.x * ep.noise.scale;
-              nim[NCH - 8 + j] = z.y * ep.noise.scale;
+              const int64_t off = pix_off + static_cast<int64_t>(ofirst + trip * 8 + j) * hw;
+              if constexpr (kReal) {
+                // the real layout of the CUDA-core kernel (conv.cu): element -> quad, component
+                const float4 a = philox_fast_normal4(static_cast<uint64_t>(off) >> 2, 0u, ep.noise);
+                const int comp = static_cast<int>(off & 3);
+                nre[NCH - 8 + j] = (comp == 0 ? a.x : comp == 1 ? a.y : comp == 2 ? a.z : a.w) * ep.noise.scale;
+              } else {
+                const float2 z = philox_fast_pair(static_cast<uint64_t>(off), ep.noise);
+                nre[NCH - 8 + j] = z.x * ep.noise.scale;
+                nim[NCH - 8 + j] = z.y * ep.noise.scale;
+              }
             }
           }
         }
@@ -643,37 +690,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
 
     ptx::mbar_wait(bar_accum, 0);
     ptx::tcgen05_fence_after();
+    const int64_t cl_off = ((static_cast<int64_t>(b) * g.Ho + oh) * g.Wo + ow) * g.O;
 #pragma unroll
     for (int cc = 0; cc < NCH / 8; ++cc) {
       const int c = cbase / 8 + cc;                             // 8-channel chunk inside the tile
-      uint32_t d1a[8], d1b[8], d2a[8], d2b[8], s2r[8];
-      ptx::tmem_ld_32x32b_x8(lane_base + c * 8, d1a);          // x_re * U
-      ptx::tmem_ld_32x32b_x8(lane_base + 64 + c * 8, d1b);     // x_re * V
-      ptx::tmem_ld_32x32b_x8(lane_base + 128 + c * 8, d2a);    // x_im * U
-      ptx::tmem_ld_32x32b_x8(lane_base + 192 + c * 8, d2b);    // x_im * V
-      if constexpr (kVD) ptx::tmem_ld_32x32b_x8(lane_base + 256 + c * 8, s2r);
-      ptx::tmem_ld_wait();
-      float re8[8], im8[8];
+      const int o0 = obase + n0 + c * 8;
+      if constexpr (kReal) {
+        uint32_t d1[8], s2r[8];
+        ptx::tmem_ld_32x32b_x8(lane_base + c * 8, d1);
+        if constexpr (kVD) ptx::tmem_ld_32x32b_x8(lane_base + C::OFF_S2 + c * 8, s2r);
+        ptx::tmem_ld_wait();
+        float re8[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int o = n0 + c * 8 + j;
-        float re = __uint_as_float(d1a[j]) - __uint_as_float(d2b[j]);
-        float im = __uint_as_float(d1b[j]) + __uint_as_float(d2a[j]);
-        if (ep.b_re && o < g.O) {
-          re += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_re) + o));
-          im += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_im) + o));
+        for (int j = 0; j < 8; ++j) {
+          float re = __uint_as_float(d1[j]);
+          if (ep.b_re && o0 + j < o_end) re += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_re) + o0 + j));
+          if constexpr (kVD) {
+            re = fmaf(nre[cc * 8 + j], sd_of(__uint_as_float(s2r[j])), re);
+          }
+          re8[j] = re;
         }
-        if constexpr (kVD) {
-          const float sd = sd_of(__uint_as_float(s2r[j]));
-          re = fmaf(nre[cc * 8 + j], sd, re);
-          im = fmaf(nim[cc * 8 + j], sd, im);
+        if (pix_ok && o0 < o_end)
+          conv_store8<T>(static_cast<T*>(ep.y_re), g, ep.nhwc != 0, pix_off, hw, cl_off, o0, re8, o_end);
+      } else {
+        uint32_t d1a[8], d1b[8], d2a[8], d2b[8], s2r[8];
+        ptx::tmem_ld_32x32b_x8(lane_base + c * 8, d1a);          // x_re * U
+        ptx::tmem_ld_32x32b_x8(lane_base + 64 + c * 8, d1b);     // x_re * V
+        ptx::tmem_ld_32x32b_x8(lane_base + 128 + c * 8, d2a);    // x_im * U
+        ptx::tmem_ld_32x32b_x8(lane_base + 192 + c * 8, d2b);    // x_im * V
+        if constexpr (kVD) ptx::tmem_ld_32x32b_x8(lane_base + C::OFF_S2 + c * 8, s2r);
+        ptx::tmem_ld_wait();
+        float re8[8], im8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int o = o0 + j;
+          float re = __uint_as_float(d1a[j]) - __uint_as_float(d2b[j]);
+          float im = __uint_as_float(d1b[j]) + __uint_as_float(d2a[j]);
+          if (ep.b_re && o < o_end) {
+            re += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_re) + o));
+            im += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_im) + o));
+          }
+          if constexpr (kVD) {
+            const float sd = sd_of(__uint_as_float(s2r[j]));
+            re = fmaf(nre[cc * 8 + j], sd, re);
+            im = fmaf(nim[cc * 8 + j], sd, im);
+          }
+          re8[j] = re, im8[j] = im;
         }
-        re8[j] = re, im8[j] = im;
-      }
-      if (pix_ok) {
-        const int64_t cl_off = ((static_cast<int64_t>(b) * g.Ho + oh) * g.Wo + ow) * g.O;
-        conv_store8<T>(static_cast<T*>(ep.y_re), g, ep.nhwc != 0, pix_off, hw, cl_off, n0 + c * 8, re8);
-        conv_store8<T>(static_cast<T*>(ep.y_im), g, ep.nhwc != 0, pix_off, hw, cl_off, n0 + c * 8, im8);
+        if (pix_ok && o0 < o_end) {
+          conv_store8<T>(static_cast<T*>(ep.y_re), g, ep.nhwc != 0, pix_off, hw, cl_off, o0, re8, o_end);
+          conv_store8<T>(static_cast<T*>(ep.y_im), g, ep.nhwc != 0, pix_off, hw, cl_off, o0, im8, o_end);
+        }
       }
     }
     ptx::tcgen05_fence_before();
@@ -1138,14 +1205,14 @@ static int make_act_map(CUtensorMap* out, const void* ptr, const ConvTcGeom& g, 
   return r == CUDA_SUCCESS ? CPLXK_OK : CPLXK_ERR_CUDA;
 }
 
-// tap-major weight plane [khw * Op, Cp]: box {BKC channels, 64 rows}
+// tap-major weight plane [khw * Op, Cgp]: box {BKC channels, 64 rows}
 template <typename T>
 static int make_w_map(CUtensorMap* out, const void* ptr, const ConvTcGeom& g) {
   auto enc = tensor_map_encode_fn();
   if (!enc) return CPLXK_ERR_CUDA;
-  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(g.Cp),
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(g.Cgp),
                         static_cast<cuuint64_t>(g.kh) * g.kw * g.Op};
-  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(g.Cp) * sizeof(T)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(g.Cgp) * sizeof(T)};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / sizeof(T)), 64u};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(out, conv_dt<T>(), 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
@@ -1156,42 +1223,62 @@ static int make_w_map(CUtensorMap* out, const void* ptr, const ConvTcGeom& g) {
 
 static inline size_t up256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
-static void conv_tc_plan(ConvTcGeom& g, int dtype) {
+static void conv_tc_plan(ConvTcGeom& g, int dtype, int groups = 1, bool real = false) {
   const int gran = dtype == CPLXK_F32 ? 8 : 16;   // pitch % 32 B, whole k-steps
+  const int bn = real ? 128 : 64;                 // output channels per n-block
+  g.tCg = static_cast<int>(g.C / groups), g.tOg = static_cast<int>(g.O / groups);
+  if (g.tOg < 1) g.tOg = 1;
+  if (g.tCg < 1) g.tCg = 1;
+  // groups narrower than an n-block: pack `ng` of them (a divisor of `groups`) into a super-group
+  int ng = 1;
+  if (groups > 1 && g.tOg < bn)
+    for (int d = 1; d <= groups && d * g.tOg <= bn; ++d)
+      if (groups % d == 0) ng = d;
+  groups /= ng;
+  g.groups = groups;
+  g.Cg = ng * g.tCg, g.Og = ng * g.tOg;
   g.Cp = static_cast<int>((g.C + gran - 1) / gran * gran);
-  g.Op = static_cast<int>((g.O + 63) / 64 * 64);
+  g.Cgp = groups == 1 ? g.Cp : (g.Cg + gran - 1) / gran * gran;
+  g.Ogp = (g.Og + bn - 1) / bn * bn;
+  g.Op = groups * g.Ogp;
   int wt = 128;
   while (wt > 8 && wt / 2 >= g.Wo) wt /= 2;       // smallest power of two covering Wo (>= 8)
   g.Wt = wt;
   g.Ht = 128 / wt;
   g.tiles_w = static_cast<int>((g.Wo + g.Wt - 1) / g.Wt);
   g.tiles_h = static_cast<int>((g.Ho + g.Ht - 1) / g.Ht);
-  g.tiles_n = g.Op / 64;
+  g.tiles_ng = g.Ogp / bn;
+  g.tiles_n = groups * g.tiles_ng;
 }
 
 size_t conv_tc_workspace_bytes(int dtype, bool vd, int64_t B, int64_t C, int64_t H, int64_t W,
-                               int64_t O, int64_t kh, int64_t kw) {
+                               int64_t O, int64_t kh, int64_t kw, int groups, bool real) {
   ConvTcGeom g{};
   g.B = B, g.C = C, g.H = H, g.W = W, g.O = O, g.kh = static_cast<int>(kh), g.kw = static_cast<int>(kw);
   g.Wo = g.Ho = 128;
-  conv_tc_plan(g, dtype);
+  conv_tc_plan(g, dtype, groups, real);
   const size_t es = dtype == CPLXK_F32 ? 4 : 2;
   const size_t act = up256(static_cast<size_t>(B) * H * W * g.Cp * es);
-  const size_t wgt = up256(static_cast<size_t>(kh) * kw * g.Op * g.Cp * es);
+  const size_t wgt = up256(static_cast<size_t>(kh) * kw * g.Op * g.Cgp * es);
+  const size_t planes = (real ? 1 : 2) + (vd ? 1 : 0);
   // + per-image maxima and per-output-channel scales of the fp16 operand path
-  return (vd ? 3 : 2) * act + (vd ? 3 : 2) * wgt + up256(static_cast<size_t>(B) * 4) +
+  return planes * act + planes * wgt + up256(static_cast<size_t>(B) * 4) +
          up256(static_cast<size_t>(g.Op) * 4);
 }
 
 bool conv_tc_supported(int dtype, int64_t B, int64_t C, int64_t H, int64_t W, int64_t O, int64_t Ho,
-                       int64_t Wo, int kh, int kw, int sh, int sw) {
+                       int64_t Wo, int kh, int kw, int sh, int sw, int groups, bool real) {
   if (B < 1 || B > 0x7fffffff || H > 0x7fffffff || W > 0x7fffffff) return false;
+  if (groups < 1 || C % groups || O % groups || C > 0x3fffffff || O > 0x3fffffff) return false;
   ConvTcGeom g{};
   g.C = C, g.O = O, g.Ho = Ho, g.Wo = Wo;
-  conv_tc_plan(g, dtype);
+  conv_tc_plan(g, dtype, groups, real);
   if ((g.Wt - 1) * sw + 1 > 256 || (g.Ht - 1) * sh + 1 > 256) return false;  // TMA box limit
+  // the channel coordinate of a (super-)group's first k-block must be 16-byte aligned
+  if (g.groups > 1 && (g.Cg * (dtype == CPLXK_F32 ? 4 : 2)) % 16 != 0) return false;
   const int64_t tiles = B * g.tiles_h * g.tiles_w * g.tiles_n;
-  return tiles > 0 && tiles <= 0x7fffffff && kh * kw <= 4096;
+  return tiles > 0 && tiles <= 0x7fffffff && kh * kw <= 4096 &&
+         static_cast<int64_t>(kh) * kw * g.Op <= 0x7fffffff;
 }
 
 // fp32 NCHW planes on fp16 operands: per-image amax -> transposing, scaling pre-pass -> weights
@@ -1200,7 +1287,7 @@ static int launch_conv_f16(const void* x_re, const void* x_im, const void* w_re,
                            void* workspace, ConvTcGeom g, const ConvTcEpi& ep_in, cudaStream_t st) {
   const size_t act32 = up256(static_cast<size_t>(g.B) * g.H * g.W * g.Cp * 4);
   const size_t wgt32 = up256(static_cast<size_t>(g.kh) * g.kw * g.Op * g.Cp * 4);
-  g.Cp = static_cast<int>((g.C + 15) / 16 * 16);          // whole 32-byte k-steps of fp16
+  g.Cp = g.Cgp = static_cast<int>((g.C + 15) / 16 * 16);  // whole 32-byte k-steps of fp16
   const size_t act = up256(static_cast<size_t>(g.B) * g.H * g.W * g.Cp * 2);
   const size_t wgt = up256(static_cast<size_t>(g.kh) * g.kw * g.Op * g.Cp * 2);
   if (2 * act > 2 * act32 || 2 * wgt > 2 * wgt32) return CPLXK_ERR_WORKSPACE;
@@ -1239,7 +1326,7 @@ static int launch_conv_f16(const void* x_re, const void* x_im, const void* w_re,
   CPLXK_CUDA_TRY(cudaGetLastError());
   conv_wprep_f16_kernel<<<static_cast<unsigned>(g.Op), 256, 0, st>>>(
       static_cast<const float*>(w_re), static_cast<const float*>(w_im), u, v, isw, static_cast<int>(g.O),
-      g.Op, static_cast<int>(g.C), g.Cp, g.kh * g.kw);
+      g.Op, static_cast<int>(g.C), g.Cp, g.tOg, g.tCg, g.kh * g.kw);
   CPLXK_CUDA_TRY(cudaGetLastError());
 
   CUtensorMap tm_xr, tm_xi, tm_u, tm_v;
@@ -1330,7 +1417,7 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
   const int64_t wtotal = static_cast<int64_t>(g.kh) * g.kw * g.Op * g.Cp;
   conv_wprep_kernel<T, kVD><<<static_cast<unsigned>(wtotal / 256 + 1 > 1184 ? 1184 : wtotal / 256 + 1), 256, 0, st>>>(
       static_cast<const T*>(w_re), static_cast<const T*>(w_im), static_cast<const T*>(ls2), u, v, e,
-      static_cast<int>(g.O), g.Op, static_cast<int>(g.C), g.Cp, g.kh * g.kw);
+      g.Og, g.Ogp, g.Op, g.Cg, g.Cgp, g.tOg, g.tCg, g.kh * g.kw);
   CPLXK_CUDA_TRY(cudaGetLastError());
 
   CUtensorMap tm_xr, tm_xi, tm_q, tm_u, tm_v, tm_e;
@@ -1379,24 +1466,94 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
   return CPLXK_OK;
 }
 
+// Real planes and / or (super-)groups > 1 after packing: conv_tc_kernel<T, kVD, kReal> (one tile
+// per CTA), a group is one more factor of the n-block index.  NCHW planes only.  (Grouped complex
+// layers whose groups all fit ONE n-block are a dense layer with block-diagonal weights and take
+// the CTA-pair / persistent kernels.)  A k-block of a group whose channel
+// count is not a multiple of the block's width also loads the first channels of the NEXT group;
+// their weight rows are zero in the prepared planes, so they contribute 0 (0 * inf = nan aside).
+template <typename T, bool kVD, bool kReal>
+static int launch_conv_rg(const void* x_re, const void* x_im, const void* w_re, const void* w_im,
+                          const void* ls2, void* workspace, const ConvTcGeom& g, const ConvTcEpi& ep,
+                          cudaStream_t st) {
+  using C = ConvCfg<T, kVD, kReal>;
+  if (ep.nhwc) return CPLXK_ERR_UNSUPPORTED;
+  const size_t es = sizeof(T);
+  const size_t act = up256(static_cast<size_t>(g.B) * g.H * g.W * g.Cp * es);
+  const size_t wgt = up256(static_cast<size_t>(g.kh) * g.kw * g.Op * g.Cgp * es);
+  constexpr int NP = kReal ? 1 : 2;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  T* a_re = reinterpret_cast<T*>(ws);
+  T* a_im = kReal ? nullptr : reinterpret_cast<T*>(ws + act);
+  T* a_q = kVD ? reinterpret_cast<T*>(ws + NP * act) : nullptr;
+  uint8_t* wbase = ws + (NP + (kVD ? 1 : 0)) * act;
+  T* u = reinterpret_cast<T*>(wbase);
+  T* v = kReal ? nullptr : reinterpret_cast<T*>(wbase + wgt);
+  T* e = kVD ? reinterpret_cast<T*>(wbase + NP * wgt) : nullptr;
+
+  dim3 tg(static_cast<unsigned>(g.B * g.H), static_cast<unsigned>((g.Cp + 31) / 32),
+          static_cast<unsigned>((g.W + 31) / 32));
+  if (tg.y > 65535u || tg.z > 65535u || g.B * g.H > 0x7fffffff) return CPLXK_ERR_UNSUPPORTED;
+  conv_nhwc_kernel<T, kVD><<<tg, 256, 0, st>>>(static_cast<const T*>(x_re), static_cast<const T*>(x_im),
+                                               a_re, a_im, a_q, static_cast<int>(g.C), g.Cp,
+                                               static_cast<int>(g.H), static_cast<int>(g.W));
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  const int64_t wtotal = static_cast<int64_t>(g.kh) * g.kw * g.Op * g.Cgp;
+  conv_wprep_kernel<T, kVD><<<static_cast<unsigned>(wtotal / 256 + 1 > 1184 ? 1184 : wtotal / 256 + 1), 256, 0, st>>>(
+      static_cast<const T*>(w_re), static_cast<const T*>(w_im), static_cast<const T*>(ls2), u, v, e,
+      g.Og, g.Ogp, g.Op, g.Cg, g.Cgp, g.tOg, g.tCg, g.kh * g.kw);
+  CPLXK_CUDA_TRY(cudaGetLastError());
+
+  CUtensorMap tm_xr, tm_xi, tm_q, tm_u, tm_v, tm_e;
+  int rc;
+  if ((rc = make_act_map<T>(&tm_xr, a_re, g))) return rc;
+  if ((rc = make_w_map<T>(&tm_u, u, g))) return rc;
+  tm_xi = tm_xr, tm_v = tm_u, tm_q = tm_xr, tm_e = tm_u;
+  if (!kReal) {
+    if ((rc = make_act_map<T>(&tm_xi, a_im, g))) return rc;
+    if ((rc = make_w_map<T>(&tm_v, v, g))) return rc;
+  }
+  if (kVD) {
+    if ((rc = make_act_map<T>(&tm_q, a_q, g))) return rc;
+    if ((rc = make_w_map<T>(&tm_e, e, g))) return rc;
+  }
+  const int64_t tiles = g.B * g.tiles_h * g.tiles_w * g.tiles_n;
+  auto kern = conv_tc_kernel<T, kVD, kReal>;
+  CPLXK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  kern<<<static_cast<unsigned>(tiles), C::THREADS, C::SMEM_BYTES, st>>>(tm_xr, tm_xi, tm_q, tm_u, tm_v,
+                                                                      tm_e, g, ep);
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
+}
+
 int conv_tc_dispatch(int dtype, bool vd, bool nhwc, const void* x_re, const void* x_im, const void* w_re,
                      const void* w_im, const void* ls2, void* workspace, int64_t B, int64_t C,
                      int64_t H, int64_t W, int64_t O, int64_t Ho, int64_t Wo, int kh, int kw, int sh,
-                     int sw, int ph, int pw, int dh, int dw, const ConvTcEpi& ep_in, cudaStream_t st) {
+                     int sw, int ph, int pw, int dh, int dw, const ConvTcEpi& ep_in, cudaStream_t st,
+                     int groups) {
   ConvTcEpi ep = ep_in;
   ep.nhwc = nhwc ? 1 : 0;
+  const bool real = x_im == nullptr;
   ConvTcGeom g{};
   g.B = B, g.C = C, g.H = H, g.W = W, g.O = O, g.Ho = Ho, g.Wo = Wo;
   g.kh = kh, g.kw = kw, g.sh = sh, g.sw = sw, g.ph = ph, g.pw = pw, g.dh = dh, g.dw = dw;
-  conv_tc_plan(g, dtype);
+  conv_tc_plan(g, dtype, groups, real);
+#define CPLXK_RG(T)                                                                                       \
+  if (real && vd) return launch_conv_rg<T, true, true>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st);   \
+  if (real) return launch_conv_rg<T, false, true>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st);        \
+  if (g.groups > 1 && vd) return launch_conv_rg<T, true, false>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st); \
+  if (g.groups > 1) return launch_conv_rg<T, false, false>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st);
   if (dtype == CPLXK_F32) {
+    CPLXK_RG(float)
     if (vd) return launch_conv_tc<float, true>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st);
     return launch_conv_tc<float, false>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st);
   }
   if (dtype == CPLXK_BF16) {
+    CPLXK_RG(__nv_bfloat16)
     if (vd) return launch_conv_tc<__nv_bfloat16, true>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st);
     return launch_conv_tc<__nv_bfloat16, false>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st);
   }
+#undef CPLXK_RG
   return CPLXK_ERR_BADARG;
 }
 

@@ -118,6 +118,7 @@ __device__ __forceinline__ float prep_convert_row(const PrepArgs& a, bool is_x, 
   const float scale = __uint_as_float(static_cast<uint32_t>(s + 127) << 23);
   if (tid == 0) (is_x ? a.isx : a.isw)[r] = __uint_as_float(static_cast<uint32_t>(127 - s) << 23);
 
+  float vcarry = 0.f;                       // rounding error carried along the variance operand
   auto emit = [&](int64_t k, const float (&vr)[8], const float (&vi)[8]) {
     uint4 o;
     __half2* h = reinterpret_cast<__half2*>(&o);
@@ -131,26 +132,40 @@ __device__ __forceinline__ float prep_convert_row(const PrepArgs& a, bool is_x, 
     }
     if (!has_var) return;
     __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&o);
+    float var[8];
     if (is_x) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float q0 = vr[2 * j] * vr[2 * j], q1 = vr[2 * j + 1] * vr[2 * j + 1];
-        if constexpr (kCplx) q0 = fmaf(vi[2 * j], vi[2 * j], q0), q1 = fmaf(vi[2 * j + 1], vi[2 * j + 1], q1);
-        b[j] = __floats2bfloat162_rn(q0, q1);
+      for (int j = 0; j < 8; ++j) {
+        var[j] = vr[j] * vr[j];
+        if constexpr (kCplx) var[j] = fmaf(vi[j], vi[j], var[j]);
       }
     } else {
       const float4 l0 = __ldg(reinterpret_cast<const float4*>(pl + k));
       const float4 l1 = __ldg(reinterpret_cast<const float4*>(pl + k + 4));
+      const float l[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
       if (a.kl_kind >= 0 && r >= a.kl_row0 && r < a.kl_row1) {   // weights and log_sigma2 are in registers anyway
-        const float l[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) kl_acc += penalty_any(a.kl_kind, vr[j], kCplx ? vi[j] : 0.f, l[j]);
       }
-      b[0] = __floats2bfloat162_rn(__expf(l0.x), __expf(l0.y));
-      b[1] = __floats2bfloat162_rn(__expf(l0.z), __expf(l0.w));
-      b[2] = __floats2bfloat162_rn(__expf(l1.x), __expf(l1.y));
-      b[3] = __floats2bfloat162_rn(__expf(l1.z), __expf(l1.w));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) var[j] = __expf(l[j]);
     }
+    // bf16 keeps 8 significant bits: rounding a CONSTANT row (log_sigma2 at its initial value, a
+    // constant input) is a systematic relative error of up to 2^-9 in s2.  The rounding error of
+    // each element is therefore carried into the next one of this thread's run (error diffusion):
+    // the run's sum is preserved to half an ulp of ONE element, the bias drops by the run length.
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = var[j] + vcarry;
+      const __nv_bfloat16 h = __float2bfloat16_rn(fmaxf(t, 0.f));
+      const float c = t - __bfloat162float(h);
+      vcarry = fabsf(c) <= 3.0e38f ? c : 0.f;          // inf / nan stay in their element
+      const uint32_t bits = static_cast<uint32_t>(__bfloat16_as_ushort(h));
+      if (j & 1) pk[j >> 1] |= bits << 16; else pk[j >> 1] = bits;
+    }
+    o = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    (void)b;
     *reinterpret_cast<uint4*>(dv + k) = o;
   };
 #pragma unroll

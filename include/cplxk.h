@@ -288,20 +288,28 @@ int cplxk_log_alpha(const void* w_re, const void* w_im, const void* log_sigma2,
                     float threshold, void* out_mask, void* stream);
 
 /*
- * Complex (or real) 2-d cross-correlation, NCHW, groups == 1, zero padding.
- * Replaces cplx.conv2d -> convnd_quick (cplxmodule/cplx.py:729-742,822-838);
- * with log_sigma2 != NULL also the variational forward
- * CplxConvNdGaussianMixin._forward_impl (nn/relevance/complex/base.py:120-135).
- * conv1d is the H == kh == 1 case.
- *   x : [B,C,H,W]  w,log_sigma2 : [O,C,kh,kw]  b : [O]  y,eps : [B,O,Ho,Wo]
- *   workspace (nullable): cplxk_conv2d_workspace_bytes() bytes of scratch, 16-byte aligned.
- *     With it (complex planes only) the call runs the tcgen05 implicit GEMM: two elementwise
- *     launches write channels-last copies of the input (and |x|^2, exp(log_sigma2), tap-major
- *     weights) to the workspace, one kernel does the MMAs + epilogue.  Without it, or for
- *     geometries outside the TMA box limits, the exact-fp32 CUDA-core kernel runs.
+ * Complex (or real: x_im == w_im == y_im == NULL) 2-d cross-correlation, NCHW, zero padding.
+ * Replaces cplx.conv2d -> convnd_quick (cplxmodule/cplx.py:729-742,822-838) and the F.conv2d
+ * calls of the real layers (nn/relevance/real/base.py:149-163); with log_sigma2 != NULL also the
+ * variational forward CplxConvNdGaussianMixin._forward_impl (nn/relevance/complex/base.py:120-135)
+ * / ConvNdGaussianMixin._forward_impl (real/base.py:149-163).  conv1d is the H == kh == 1 case.
+ *   x : [B,C,H,W]  w,log_sigma2 : [O,C/groups,kh,kw]  b : [O]  y,eps : [B,O,Ho,Wo]
+ *   workspace (nullable): cplxk_conv2d_workspace_bytes[_g]() bytes of scratch, 16-byte aligned.
+ *     With it the call runs the tcgen05 implicit GEMM: two elementwise launches write
+ *     channels-last copies of the input (and |x|^2, exp(log_sigma2), tap-major weights) to the
+ *     workspace, one kernel does the MMAs + epilogue.  Complex planes with groups == 1: CTA-pair
+ *     / persistent kernels on the stacked [U;V] operand.  Real planes: one A tile and one
+ *     accumulator per 128 real output channels.  groups > 1 (cplx.py:717-726 passes `groups` on
+ *     to F.conv): ONE launch, the group is a factor of the n-block index.
+ *     Without a workspace, or for geometries outside the TMA box limits, the exact-fp32
+ *     CUDA-core kernel runs (groups == 1 only: CPLXK_ERR_UNSUPPORTED otherwise, the caller
+ *     then issues one call per group).
  */
 size_t cplxk_conv2d_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t O,
                                     int64_t kh, int64_t kw, int dtype, int variational);
+size_t cplxk_conv2d_workspace_bytes_g(int64_t B, int64_t C, int64_t H, int64_t W, int64_t O,
+                                      int64_t kh, int64_t kw, int64_t groups, int is_complex,
+                                      int dtype, int variational);
 int cplxk_conv2d_fwd(const void* x_re, const void* x_im,
                      const void* w_re, const void* w_im,
                      const void* b_re, const void* b_im,
@@ -317,9 +325,27 @@ int cplxk_conv2d_fwd(const void* x_re, const void* x_im,
                      int64_t dil_h, int64_t dil_w,
                      int dtype, int math,
                      int channels_last /* 1: x and y planes are NHWC in memory (torch.channels_last);
-                                          tensor-core path only, C % 8 == 0 (fp32) / 16 (bf16); skips
-                                          the transposing pre-pass.  eps stays NCHW. */,
+                                          tensor-core path only, complex planes, groups == 1,
+                                          C % 8 == 0 (fp32) / 16 (bf16); skips the transposing
+                                          pre-pass.  eps stays NCHW. */,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* the same with `groups` (cplxk_conv2d_fwd is groups == 1) */
+int cplxk_conv2d_fwd_g(const void* x_re, const void* x_im,
+                       const void* w_re, const void* w_im,
+                       const void* b_re, const void* b_im,
+                       const void* log_sigma2,
+                       const void* eps_re, const void* eps_im,
+                       int noise, uint64_t seed, uint64_t offset,
+                       uint32_t philox_threads,
+                       void* y_re, void* y_im,
+                       int64_t B, int64_t C, int64_t H, int64_t W,
+                       int64_t O, int64_t kh, int64_t kw,
+                       int64_t stride_h, int64_t stride_w,
+                       int64_t pad_h, int64_t pad_w,
+                       int64_t dil_h, int64_t dil_w,
+                       int64_t groups,
+                       int dtype, int math, int channels_last,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * ---- backward pass ---------------------------------------------------------------------

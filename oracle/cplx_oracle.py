@@ -107,12 +107,27 @@ def cplx_conv2d(x_re, x_im, w_re, w_im, b_re=None, b_im=None, stride=1, padding=
     return re, im
 
 
+def cplx_conv2d_grouped(x_re, x_im, w_re, w_im, b_re=None, b_im=None, stride=1, padding=0, dilation=1,
+                        groups=1):
+    """cplx.conv2d -> convnd -> convnd_naive (groups > 1), cplxmodule/cplx.py:717-726,790-800."""
+    conv = lambda a, w: F.conv2d(a, w, None, stride, padding, dilation, groups)
+    re = conv(x_re, w_re) - conv(x_im, w_im)
+    im = conv(x_re, w_im) + conv(x_im, w_re)
+    if b_re is not None:
+        re, im = re + b_re.reshape(-1, 1, 1), im + b_im.reshape(-1, 1, 1)
+    return re, im
+
+
 def cplx_conv2d_vd(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, stride=1,
-                   padding=0, dilation=1):
+                   padding=0, dilation=1, groups=1):
     """CplxConvNdGaussianMixin._forward_impl, nn/relevance/complex/base.py:120-135."""
-    mu_re, mu_im = cplx_conv2d(x_re, x_im, w_re, w_im, b_re, b_im, stride, padding, dilation)
+    if groups == 1:
+        mu_re, mu_im = cplx_conv2d(x_re, x_im, w_re, w_im, b_re, b_im, stride, padding, dilation)
+    else:
+        mu_re, mu_im = cplx_conv2d_grouped(x_re, x_im, w_re, w_im, b_re, b_im, stride, padding,
+                                           dilation, groups)
     s2 = F.conv2d(x_re * x_re + x_im * x_im, torch.exp(log_sigma2), None, stride, padding,
-                  dilation, 1)
+                  dilation, groups)
     sd = torch.sqrt(torch.clamp(s2, 1e-8))
     return mu_re + eps_re * sd, mu_im + eps_im * sd
 

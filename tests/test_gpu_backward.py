@@ -283,7 +283,7 @@ def test_real_conv_vd_gradients_and_fused_noise(nd):
     ((o * c.double().cpu()).sum() + 0.7 * kl_with_grad64("real_vd", w, None, l2)).backward()
     for got, ref in [(x.grad, xr.grad), (m.weight.grad, w.grad), (m.bias.grad, b.grad),
                      (m.log_sigma2.grad, l2.grad)]:
-        assert rel_err(got, ref) < 2e-4
+        assert rel_err(got, ref) < 3e-3      # real planes run on the tcgen05 kernel (tf32 operands)
     if m.groups == 1:
         return
     # ungrouped twin with the torch-exact in-kernel noise: same gradients as with that draw injected

@@ -88,7 +88,7 @@ def test_real_masked_layers_and_conv_masked():
     conv.mask = (torch.rand_like(conv.weight) < 0.5).float()
     xi = torch.randn(3, 6, 12, 10, device=DEV)
     want = F.conv2d(c64(xi), c64(conv.weight) * c64(conv.mask), c64(conv.bias), padding=1)
-    assert rel_err(conv(xi), want) < 1e-4
+    assert rel_err(conv(xi), want) < 1e-3      # real planes run on the tcgen05 kernel (tf32 operands)
     bil = masked.CplxBilinearMasked(5, 6, 7).to(DEV)
     bil.mask = (torch.rand(7, 5, 6, device=DEV) < 0.5).float()
     z1, z2 = cplx.randn(9, 5, device=DEV), cplx.randn(9, 6, device=DEV)
@@ -264,7 +264,7 @@ def test_grouped_variational_conv_draws_the_layers_single_noise(cplx_):
     else:
         assert torch.equal(fused, inject)
         want = orc.real_conv2d_vd(c64(x), c64(m.weight), c64(m.bias), c64(m.log_sigma2), c64(eps), 1, 1, 1, 2)
-        assert rel_err(inject, want) < 1e-4
+        assert rel_err(inject, want) < 1e-3
     out = m(x)                                                  # and it trains
     loss = (out.real.square().mean() + out.imag.square().mean()) if cplx_ else out.square().mean()
     (loss + 1e-3 * sum(rel.penalties(m))).backward()

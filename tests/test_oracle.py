@@ -224,6 +224,34 @@ def test_oracle_vs_live_reference_conv_vd_and_extensions():
         assert torch.equal(w_re.grad, m.weight.real.grad) and torch.equal(ls2.grad, m.log_sigma2.grad)
 
 
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference not present on this machine")
+def test_oracle_vs_live_reference_grouped_complex_conv():
+    """groups > 1: cplx.conv2d -> convnd_naive (cplx.py:717-726) and the grouped CplxConv2dVD
+    training forward (complex/base.py:120-135), bit-for-bit against the live reference"""
+    from oracle.make_golden import import_reference
+    import_reference()
+    from cplxmodule import cplx
+    from cplxmodule.nn.relevance import CplxConv2dVD
+
+    torch.manual_seed(99)
+    m = CplxConv2dVD(6, 4, (3, 2), stride=(1, 2), padding=(1, 0), dilation=(2, 1), groups=2).train()
+    with torch.no_grad():
+        m.log_sigma2.uniform_(-12, 2)
+    z = cplx.randn(3, 6, 11, 9)
+    w, b = m.weight, m.bias
+    mu = m.eval()(z)
+    re, im = orc.cplx_conv2d_grouped(z.real, z.imag, w.real, w.imag, b.real, b.imag, (1, 2), (1, 0), (2, 1), 2)
+    assert torch.equal(re, mu.real) and torch.equal(im, mu.imag)
+    m.train()
+    state = torch.get_rng_state()
+    out = m(z)
+    torch.set_rng_state(state)
+    er, ei = orc.cplx_randn(*out.shape)
+    re, im = orc.cplx_conv2d_vd(z.real, z.imag, w.real, w.imag, b.real, b.imag, m.log_sigma2, er, ei,
+                                (1, 2), (1, 0), (2, 1), 2)
+    assert torch.equal(re, out.real) and torch.equal(im, out.imag)
+
+
 def _bil(g, tag):
     names = ("x1_re", "x1_im", "x2_re", "x2_im", "w_re", "w_im", "b_re", "b_im")
     return [g[f"{tag}_{n}"] for n in names]
