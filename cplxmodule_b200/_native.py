@@ -30,7 +30,7 @@ EXPORTS = (
     "cplxk_transpose2d", "cplxk_eltwise", "cplxk_colsum", "cplxk_vd_grad_s2", "cplxk_vd_grad_input",
     "cplxk_mul_exp", "cplxk_kl_bwd",
     "cplxk_linear_masked_fwd", "cplxk_linear_masked_workspace_bytes", "cplxk_kl_mask",
-    "cplxk_outer_fwd", "cplxk_outer_bwd",
+    "cplxk_outer_fwd", "cplxk_outer_bwd", "cplxk_kl_guard", "cplxk_linear_vd_fuses_kl",
 )
 
 _lock = threading.Lock()
@@ -53,7 +53,7 @@ def _declare(lib):
                                         + [_i64] * 3 + [_int, _int, _vp, _vp, ctypes.c_size_t, _vp])
     lib.cplxk_linear_vd_fwd_kl.argtypes = ([_vp] * 9 + [_int, _u64, _u64, _u32] + [_vp] * 2
                                            + [_i64] * 3 + [_int, _int, _vp, _vp, ctypes.c_size_t]
-                                           + [_int, _vp, _vp, ctypes.c_size_t, _i64, _i64, _vp,
+                                           + [_int, _vp, _vp, ctypes.c_size_t, _i64, _i64, _vp, _vp,
                                               ctypes.POINTER(_int), _vp])
     lib.cplxk_set_sm_reserve.argtypes = [_int]
     lib.cplxk_linear_vd_prepare.argtypes = ([_vp] * 5 + [_i64] * 3 + [_int, _vp, ctypes.c_size_t, _int, _vp, _vp,
@@ -81,6 +81,8 @@ def _declare(lib):
     lib.cplxk_mul_exp.argtypes = [_vp, _vp, _vp, _i64, _int, _int, _vp]
     lib.cplxk_kl_bwd.argtypes = [_int, _vp, _vp, _vp, _i64, _int, _vp, _int, _int, ctypes.c_double,
                                  _vp, _vp, _vp, _vp]
+    lib.cplxk_linear_vd_fuses_kl.argtypes = [_i64, _i64, _i64, _int, _int]
+    lib.cplxk_kl_guard.argtypes = [_vp, _vp, _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp]
     lib.cplxk_linear_masked_workspace_bytes.restype = ctypes.c_size_t
     lib.cplxk_linear_masked_workspace_bytes.argtypes = [_i64, _i64, _i64, _int]
     lib.cplxk_linear_masked_fwd.argtypes = [_vp] * 9 + [_i64] * 3 + [_int, _int, _vp, ctypes.c_size_t, _vp]
@@ -147,6 +149,25 @@ def ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(device):
+    """``torch.cuda.device(device)`` only when ``device`` is not already current (the context
+    manager costs several microseconds per call; single-GPU processes never need it)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
 def stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -161,26 +182,52 @@ def plane(t, dtype=None):
 
 
 # --------------------------------------------------------------- philox bookkeeping
+_props = {}          # device index -> (SM count, resident 256-thread blocks per SM)
+_capture_noise = {"offset": 0}
+
+
+def _launch_props(device):
+    p = _props.get(device.index)
+    if p is None:
+        props = torch.cuda.get_device_properties(device)
+        p = _props[device.index] = (props.multi_processor_count, props.max_threads_per_multi_processor // 256)
+    return p
+
+
 def philox_plan(device, numel, torch_exact=True):
-    """(seed, offset, threads, increment) replicating torch's CUDA ``normal_`` launch for
-    ``numel`` floats (ATen/native/cuda/DistributionTemplates.h: calc_execution_policy)."""
+    """(generator, seed, offset, threads, increment) replicating torch's CUDA ``normal_`` launch
+    for ``numel`` floats (ATen/native/cuda/DistributionTemplates.h: calc_execution_policy).
+
+    While a CUDA graph is being captured torch's generator may not be read or advanced from
+    Python: the coordinates then come from a private counter (generator ``None``) and are baked
+    into the captured launch -- every replay of the graph repeats that draw."""
     if torch_exact and numel >= 2 ** 31:
         # torch splits such tensors into 32-bit-indexable pieces with one generator advance each;
         # that stream is not reproduced -- ask for the private layout instead
         raise NotImplementedError(
             "torch-exact noise is limited to outputs below 2**31 elements; "
             "use cplxmodule_b200.set_noise_mode('fast') for this size")
-    props = torch.cuda.get_device_properties(device)
+    sms, blocks_per_sm = _launch_props(device)
     block = 256
-    blocks_per_sm = props.max_threads_per_multi_processor // block
-    grid = min(props.multi_processor_count * blocks_per_sm, (numel + block - 1) // block)
+    grid = min(sms * blocks_per_sm, (numel + block - 1) // block)
     grid = max(grid, 1)
     threads = block * grid
     increment = ((numel - 1) // (threads * 4) + 1) * 4
+    if torch.cuda.is_current_stream_capturing():
+        offset = _capture_noise["offset"]
+        _capture_noise["offset"] = offset + increment
+        return None, torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, offset, threads, increment
     gen = torch.cuda.default_generators[device.index]
     offset = gen.get_offset()
     offset = (offset + 3) // 4 * 4
     return gen, gen.initial_seed(), offset, threads, increment
+
+
+def philox_advance(gen, offset, increment):
+    """Advance torch's generator past the draw a kernel made (nothing to do for the private
+    coordinates used under graph capture)."""
+    if gen is not None:
+        gen.set_offset(offset + increment)
 
 
 # ------------------------------------------------------------------ scratch workspace
@@ -216,6 +263,8 @@ _kl_ws = {}
 
 
 def kl_workspace(device):
+    if torch.cuda.is_current_stream_capturing():      # belongs to the graph's pool: never cached
+        return torch.zeros((lib().cplxk_kl_workspace_bytes() + 7) // 8, dtype=torch.int64, device=device)
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _kl_ws.get(key)
     if ws is None:

@@ -91,14 +91,14 @@ class _ConvFn(torch.autograd.Function):
                                    ctx.geom, G)
             gs2 = torch.empty_like(s2)
             seed, offset, threads = ctx.philox or (0, 0, 0)
-            with torch.cuda.device(dev):
+            with nv.device_guard(dev):
                 nv.check(nv.lib().cplxk_vd_grad_s2(
                     nv.ptr(g_re), nv.ptr(g_im), nv.ptr(s2), nv.ptr(eps_re), nv.ptr(eps_im), ctx.noise,
                     seed, offset, threads, nv.ptr(gs2), s2.numel() // Wo, Wo, nv.dtype_code(dt),
                     nv.stream_ptr(dev)))
             if need[0] or need[1]:
                 dq, _ = _conv_dgrad(gs2, None, E, None, (H, W), ctx.geom, G)
-                with torch.cuda.device(dev):
+                with nv.device_guard(dev):
                     nv.check(nv.lib().cplxk_vd_grad_input(
                         nv.ptr(dx_re), nv.ptr(dx_im), nv.ptr(x_re.contiguous()),
                         nv.ptr(None if x_im is None else x_im.contiguous()), nv.ptr(dq), dq.numel(),
@@ -106,7 +106,7 @@ class _ConvFn(torch.autograd.Function):
             if need[6]:
                 dE, _ = _conv_wgrad_grouped(gs2, None, q, None, (kh, kw), ctx.geom, G)
                 dls2 = torch.empty_like(dE)
-                with torch.cuda.device(dev):
+                with nv.device_guard(dev):
                     nv.check(nv.lib().cplxk_mul_exp(nv.ptr(dE), nv.ptr(ls2.contiguous()), nv.ptr(dls2),
                                                     dE.numel(), nv.dtype_code(dt), 0, nv.stream_ptr(dev)))
         cast = lambda t: None if t is None else (t if t.dtype == ctx.x_dtype else t.to(ctx.x_dtype))
@@ -277,7 +277,7 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
                                                            code, 1 if ls2 is not None else 0)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     def call(xr, xi, y_re, y_im, cl):
-        with torch.cuda.device(dev):
+        with nv.device_guard(dev):
             return nv.lib().cplxk_conv2d_fwd_g(
                 nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi), nv.ptr(br), nv.ptr(bi), nv.ptr(l2),
                 nv.ptr(er), nv.ptr(ei), mode, seed, offset, threads, nv.ptr(y_re), nv.ptr(y_im),
@@ -297,8 +297,8 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
         return _conv2d_raw_per_group(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise,
                                      geom, groups)
     nv.check(rc)
-    if gen is not None:
-        gen.set_offset(offset + inc)
+    if mode != nv.NOISE_INJECT:
+        nv.philox_advance(gen, offset, inc)
     return y_re, y_im, {"philox": (seed, offset, threads), "eps_re": er, "eps_im": ei}
 
 
@@ -321,7 +321,7 @@ def _draw_noise(cplx, shape, device, dtype):
     # torch evaluates `randn(...) / sqrt(2)` on CUDA as a product with the fp32 reciprocal
     inv_sqrt2 = float(np.float32(1.0) / np.float32(2.0 ** 0.5))
     flat = ops.randn_philox_torch(numel, seed, offset, threads, inv_sqrt2 if cplx else 1.0, device)
-    gen.set_offset(offset + inc)
+    nv.philox_advance(gen, offset, inc)
     flat = flat.to(dtype)
     if cplx:
         planes = flat.view(2, *shape)

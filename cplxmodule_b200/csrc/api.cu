@@ -274,7 +274,7 @@ extern "C" int cplxk_linear_vd_fwd_kl(const void* x_re, const void* x_im, const 
                                       void* workspace, size_t workspace_bytes, int kl_kind,
                                       float* kl_sum, void* kl_workspace, size_t kl_workspace_bytes,
                                       int64_t kl_row_begin, int64_t kl_row_end, void* kl_event,
-                                      int* kl_done, void* stream) {
+                                      void* kl_fingerprint, int* kl_done, void* stream) {
   if (kl_done) *kl_done = 0;
   KlFuse kl{-1, nullptr, nullptr, 0, -1, nullptr};
   if (kl_kind >= 0) {
@@ -285,11 +285,15 @@ extern "C" int cplxk_linear_vd_fwd_kl(const void* x_re, const void* x_im, const 
     if (!aligned16(kl_workspace)) return CPLXK_ERR_ALIGN;
     if (kl_row_begin < 0 || kl_row_end > N || (kl_row_end >= 0 && kl_row_end < kl_row_begin))
       return CPLXK_ERR_BADARG;
-    kl = KlFuse{kl_kind, kl_sum, kl_workspace, kl_row_begin, kl_row_end, kl_event};
+    kl = KlFuse{kl_kind, kl_sum, kl_workspace, kl_row_begin, kl_row_end, kl_event, kl_fingerprint};
   }
   return forward_common(true, x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise,
                         seed, offset, philox_threads, y_re, y_im, M, N, K, dtype, math, s2_out,
                         workspace, workspace_bytes, stream, kl, kl_done);
+}
+
+extern "C" int cplxk_linear_vd_fuses_kl(int64_t M, int64_t N, int64_t K, int dtype, int math) {
+  return (math != CPLXK_MATH_SIMT && fwd_tc_fuses_kl(dtype, math != CPLXK_MATH_TENSOR_TF32, M, N, K)) ? 1 : 0;
 }
 
 // ---- fixed-sparsity layers: y = x (W * mask)^T + b

@@ -31,6 +31,7 @@ struct KlFuse {
   int64_t row_begin = 0; // weight rows [row_begin, row_end) enter the sum (a rank's KL shard);
   int64_t row_end = -1;  // row_end < 0: all rows
   void* event = nullptr; // cudaEvent_t recorded right after the pre-pass launch (nullable)
+  void* fp = nullptr;    // device uint64: fingerprint of the parameters the sum was computed from (nullable)
 };
 
 template <typename T, int C>

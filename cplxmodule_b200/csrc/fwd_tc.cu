@@ -424,6 +424,8 @@ size_t fwd_tc_workspace_bytes(int dtype, int64_t M, int64_t N, int64_t K) {
   return qb + eb > v3 ? qb + eb : v3;
 }
 
+constexpr int64_t kShortK = 128;   // below: tf32 operands everywhere (see launch_tc)
+
 template <typename T, bool kCplx, bool kVD, bool kXform, int kSwz>
 static int launch_tc(bool f16_ok, const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                      const void* ls2, void* workspace, int64_t M, int64_t N, int64_t K,
@@ -449,8 +451,9 @@ static int launch_tc(bool f16_ok, const void* x_re, const void* x_im, const void
     // of fwd_tc3.cu (MATH_TENSOR_TF32: tf32 operands on the one-tile-per-CTA kernel below); bf16
     // planes: the same persistent kernel on the planes as they are.
     // bf16 variance operands: their rounding errors (2^-9 each) average out over K; for a
-    // handful of terms they do not, so short reductions keep tf32 everywhere
-    const bool short_k = K < 64;
+    // few dozen terms they do not (K = 64, log_sigma2 spread over 14 units: 1.0e-3 measured),
+    // so short reductions keep tf32 everywhere
+    const bool short_k = K < kShortK;
     if (!short_k && fwd_tc3_supported(std::is_same<T, float>::value ? CPLXK_F32 : CPLXK_BF16, M, N, K)) {
       if constexpr (std::is_same<T, float>::value) {
         if (f16_ok)
@@ -496,7 +499,7 @@ static int launch_tc(bool f16_ok, const void* x_re, const void* x_im, const void
 
 // true when fwd_tc_dispatch(vd, workspace) will also produce the layer's KL sum (pre-pass fusion)
 bool fwd_tc_fuses_kl(int dtype, bool f16_ok, int64_t M, int64_t N, int64_t K) {
-  return dtype == CPLXK_F32 && f16_ok && K >= 64 && fwd_tc3_supported(dtype, M, N, K);
+  return dtype == CPLXK_F32 && f16_ok && K >= kShortK && fwd_tc3_supported(dtype, M, N, K);
 }
 
 bool fwd_tc_supported(int dtype, bool cplx, const void* x_re, const void* x_im, const void* w_re,

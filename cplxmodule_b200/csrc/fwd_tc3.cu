@@ -312,7 +312,7 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
                       __half* __restrict__ wh_im, __nv_bfloat16* __restrict__ e,
                       float* __restrict__ isx, float* __restrict__ isw, int kl_kind,
                       float* __restrict__ kl_sum, KlWorkspace* __restrict__ kl_ws, int64_t kl_row0,
-                      int64_t kl_row1) {
+                      int64_t kl_row1, unsigned long long* __restrict__ kl_fp) {
   // (separate __restrict__ parameters, not the struct: the no-alias facts let the loads of the
   // write pass be hoisted above its stores)
   PrepArgs a;
@@ -320,6 +320,8 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
   a.M = M_, a.N = N_, a.K = K_;
   a.xh_re = xh_re, a.xh_im = xh_im, a.wh_re = wh_re, a.wh_im = wh_im, a.q = q, a.e = e;
   a.isx = isx, a.isw = isw, a.kl_kind = kl_kind, a.kl_row0 = kl_row0, a.kl_row1 = kl_row1;
+  a.want_fp = (kl_kind >= 0 && kl_fp != nullptr) ? 1 : 0;
+  unsigned long long fp_acc = 0ull;          // fingerprint share of the weight rows this block converts
   __shared__ float red[8];
   __shared__ double kl_sh[kKlThreads / 32];
   __shared__ bool kl_last;
@@ -345,12 +347,13 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
       is_x = M > N;
       r = mn + (g - 2 * mn);
     }
-    kl_acc += prep_convert_row<kCplx, 256, 2, kMask>(a, is_x, r, tid, red, sync);
+    kl_acc += prep_convert_row<kCplx, 256, 2, kMask>(a, is_x, r, tid, red, sync, fp_acc);
   }
   if (a.kl_kind >= 0) {
     __syncthreads();
+    if (a.want_fp && fp_acc != 0ull) atomicAdd(&kl_ws->fp, fp_acc);   // thread 0 only; before its ticket
     const double bsum = block_sum(static_cast<double>(kl_acc), kl_sh);
-    grid_sum_finish(bsum, kl_ws, kl_sum, 1.0, kl_sh, &kl_last);
+    grid_sum_finish(bsum, kl_ws, kl_sum, 1.0, kl_sh, &kl_last, a.want_fp ? kl_fp : nullptr);
   }
 }
 
@@ -439,7 +442,7 @@ int vd_prepare_f16_launch(bool cplx, const PrepArgs& a, const KlFuse& kl, cudaSt
   vd_prepare_f16_kernel<C, MK><<<grid, 256, 0, st>>>(a.x_re, a.x_im, a.M, a.w_re, a.w_im, a.ls2, a.w_mask, \
                                                      a.N, a.K, a.xh_re, a.xh_im, a.q, a.wh_re, a.wh_im,   \
                                                      a.e, a.isx, a.isw, a.kl_kind, kl.sum, kws, a.kl_row0, \
-                                                     a.kl_row1)
+                                                     a.kl_row1, static_cast<unsigned long long*>(kl.fp))
   if (cplx && mask) CPLXK_PREP(true, true);
   else if (cplx) CPLXK_PREP(true, false);
   else if (mask) CPLXK_PREP(false, true);

@@ -18,9 +18,25 @@ constexpr int kKlMaxBlocks = 2048;
 
 struct KlWorkspace {
   unsigned int ticket;
-  unsigned int pad[3];
+  unsigned int pad;
+  unsigned long long fp;     // running parameter fingerprint of the launch in flight (0 between launches)
   double partial[kKlMaxBlocks];
 };
+
+// ---- parameter fingerprint (guard of the fused KL by-product, see kl.cu: cplxk_kl_guard) ------
+// wrapping sum over the first 8 entries of every row of every plane of mix64(bits ^ position tag)
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ unsigned long long fingerprint_elem(float w_re, float w_im, bool cplx,
+                                                               float ls2, int64_t row, int j) {
+  const unsigned long long tag = static_cast<unsigned long long>(row * 8 + j) * 3ull;
+  unsigned long long acc = mix64(static_cast<unsigned long long>(__float_as_uint(w_re)) ^ (tag << 32));
+  if (cplx) acc += mix64(static_cast<unsigned long long>(__float_as_uint(w_im)) ^ ((tag + 1) << 32));
+  return acc + mix64(static_cast<unsigned long long>(__float_as_uint(ls2)) ^ ((tag + 2) << 32));
+}
 
 // MUFU approximations without the denormal/range fix-up code of __logf/__expf/__fdividef:
 // every argument in this kernel is a normal number well inside the fast range.
@@ -148,7 +164,8 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 // finish of a grid-wide sum: every block deposits one double, the last one (ticket) adds them in
 // index order -- deterministic, no float atomics.  `sh` holds kKlThreads / 32 doubles.
 __device__ __forceinline__ void grid_sum_finish(double bsum, KlWorkspace* ws, float* out_sum,
-                                                double scale, double* sh, bool* is_last) {
+                                                double scale, double* sh, bool* is_last,
+                                                unsigned long long* fp_out = nullptr) {
   if (threadIdx.x == 0) {
     ws->partial[blockIdx.x] = bsum;
     __threadfence();
@@ -165,6 +182,10 @@ __device__ __forceinline__ void grid_sum_finish(double bsum, KlWorkspace* ws, fl
   double total = block_sum(v, sh);
   if (threadIdx.x == 0) {
     *out_sum = static_cast<float>(total * scale);
+    if (fp_out) {    // every block added its share before taking its ticket
+      *fp_out = *reinterpret_cast<volatile unsigned long long*>(&ws->fp);
+      ws->fp = 0ull;
+    }
     ws->ticket = 0;  // restore the workspace for the next call on this stream
   }
 }

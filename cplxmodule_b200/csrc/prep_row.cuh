@@ -25,6 +25,7 @@ struct PrepArgs {
   float *isx, *isw;
   int kl_kind;                         // < 0: no KL
   int64_t kl_row0, kl_row1;            // weight rows that enter the KL sum
+  int want_fp;                         // also fingerprint the parameters (kl_math.cuh; KL requests only)
 };
 
 // `sync()` is a barrier over the kThreads cooperating threads (a block: __syncthreads); `red`
@@ -34,7 +35,7 @@ struct PrepArgs {
 // (0 for x rows / rows outside [kl_row0, kl_row1)).
 template <bool kCplx, int kThreads, int kCache, bool kMask, typename Sync>
 __device__ __forceinline__ float prep_convert_row(const PrepArgs& a, bool is_x, int64_t r, int tid,
-                                                  float* red, Sync sync) {
+                                                  float* red, Sync sync, unsigned long long& fp_acc) {
   const int64_t K = a.K;
   // (the planes never alias: without __restrict__ the loads of the write pass could not be
   // hoisted above its stores)
@@ -149,20 +150,35 @@ __device__ __forceinline__ float prep_convert_row(const PrepArgs& a, bool is_x, 
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) var[j] = __expf(l[j]);
-    }
-    // bf16 keeps 8 significant bits: rounding a CONSTANT row (log_sigma2 at its initial value, a
-    // constant input) is a systematic relative error of up to 2^-9 in s2.  The rounding error of
-    // each element is therefore carried into the next one of this thread's run (error diffusion):
-    // the run's sum is preserved to half an ulp of ONE element, the bias drops by the run length.
-    uint32_t pk[4];
+      if (!kMask && a.want_fp && k == 0) {   // thread 0 holds the head of the row
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float t = var[j] + vcarry;
-      const __nv_bfloat16 h = __float2bfloat16_rn(fmaxf(t, 0.f));
-      const float c = t - __bfloat162float(h);
-      vcarry = fabsf(c) <= 3.0e38f ? c : 0.f;          // inf / nan stay in their element
-      const uint32_t bits = static_cast<uint32_t>(__bfloat16_as_ushort(h));
-      if (j & 1) pk[j >> 1] |= bits << 16; else pk[j >> 1] = bits;
+        for (int j = 0; j < 8; ++j) fp_acc += fingerprint_elem(vr[j], kCplx ? vi[j] : 0.f, kCplx, l[j], r, j);
+      }
+    }
+    uint32_t pk[4];
+    if (is_x) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(var[2 * j], var[2 * j + 1]);
+        pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+    } else {
+      // bf16 keeps 8 significant bits: rounding a CONSTANT row of exp(log_sigma2) (log_sigma2 at
+      // its initial value: every freshly constructed layer) is a systematic relative error of up
+      // to 2^-9 in s2 -- it does not average out over K like the rounding of |x|^2 does.  The
+      // rounding error of each element is therefore carried into the next one of this thread's
+      // run (error diffusion, round-to-nearest): a run's sum is preserved to half an ulp of ONE
+      // element.  On rows with scattered values this is as accurate as plain rounding
+      // (simulated and measured: profiles/README.md), on constant rows 8x more.
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = var[j] + vcarry;
+        const __nv_bfloat16 h = __float2bfloat16_rn(fmaxf(t, 0.f));
+        const float c = t - __bfloat162float(h);
+        vcarry = fabsf(c) <= 3.0e38f ? c : 0.f;          // inf / nan stay in their element
+        const uint32_t bits = static_cast<uint32_t>(__bfloat16_as_ushort(h));
+        if (j & 1) pk[j >> 1] |= bits << 16; else pk[j >> 1] = bits;
+      }
     }
     o = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     (void)b;

@@ -7,6 +7,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace cplxk {
 
@@ -16,7 +17,7 @@ typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, 
                                              const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-inline PFN_tensorMapEncodeTiled tensor_map_encode_fn() {
+inline PFN_tensorMapEncodeTiled tensor_map_driver_fn() {
   static PFN_tensorMapEncodeTiled fn = nullptr;
   if (!fn) {
     void* q = nullptr;
@@ -27,6 +28,52 @@ inline PFN_tensorMapEncodeTiled tensor_map_encode_fn() {
     fn = reinterpret_cast<PFN_tensorMapEncodeTiled>(q);
   }
   return fn;
+}
+
+// Descriptor cache: a layer called step after step passes the same (pointer, shape, box) tuples,
+// so every host-side launcher encodes through a small per-thread direct-mapped table keyed by
+// ALL arguments of the encode (and the current device) instead of calling the driver each time.
+// Nothing but the 128-byte descriptors is kept; a colliding tuple simply overwrites its slot.
+struct TensorMapKey {
+  uint64_t ptr, gdim[5], gstr[4];
+  uint32_t box[5], estr[5], dt, rank, interleave, swizzle, l2, oob;
+  int32_t dev;
+};
+inline CUresult tensor_map_encode_cached(CUtensorMap* out, CUtensorMapDataType dt, cuuint32_t rank,
+                                         void* ptr, const cuuint64_t* gdim, const cuuint64_t* gstr,
+                                         const cuuint32_t* box, const cuuint32_t* estr,
+                                         CUtensorMapInterleave il, CUtensorMapSwizzle sw,
+                                         CUtensorMapL2promotion l2, CUtensorMapFloatOOBfill oob) {
+  PFN_tensorMapEncodeTiled enc = tensor_map_driver_fn();
+  if (!enc) return CUDA_ERROR_NOT_INITIALIZED;
+  if (rank < 1 || rank > 5) return enc(out, dt, rank, ptr, gdim, gstr, box, estr, il, sw, l2, oob);
+  TensorMapKey k;
+  memset(&k, 0, sizeof(k));
+  k.ptr = reinterpret_cast<uint64_t>(ptr);
+  for (cuuint32_t i = 0; i < rank; ++i) k.gdim[i] = gdim[i], k.box[i] = box[i], k.estr[i] = estr[i];
+  for (cuuint32_t i = 0; i + 1 < rank; ++i) k.gstr[i] = gstr[i];
+  k.dt = static_cast<uint32_t>(dt), k.rank = rank, k.interleave = static_cast<uint32_t>(il);
+  k.swizzle = static_cast<uint32_t>(sw), k.l2 = static_cast<uint32_t>(l2), k.oob = static_cast<uint32_t>(oob);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  k.dev = dev;
+  uint64_t h = 1469598103934665603ull;           // FNV-1a over the key's 8-byte words
+  const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+  for (size_t i = 0; i < sizeof(k) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+  struct Slot { TensorMapKey key; CUtensorMap map; bool valid; };
+  constexpr int kSlots = 256;
+  static thread_local Slot table[kSlots];
+  Slot& s = table[(h ^ (h >> 29)) & (kSlots - 1)];
+  if (s.valid && memcmp(&s.key, &k, sizeof(k)) == 0) {
+    *out = s.map;
+    return CUDA_SUCCESS;
+  }
+  const CUresult r = enc(out, dt, rank, ptr, gdim, gstr, box, estr, il, sw, l2, oob);
+  if (r == CUDA_SUCCESS) s.key = k, s.map = *out, s.valid = true;
+  return r;
+}
+inline PFN_tensorMapEncodeTiled tensor_map_encode_fn() {
+  return tensor_map_driver_fn() ? &tensor_map_encode_cached : nullptr;
 }
 
 namespace ptx {

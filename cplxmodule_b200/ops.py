@@ -57,8 +57,9 @@ def set_kl_fusion(enabled):
     """True (default): a training-mode forward of a variational linear layer also produces the
     layer's KL sum (its operand pre-pass reads every weight anyway) and the next
     ``penalties(..., reduction="sum"|"mean")`` over unchanged parameters returns it instead of
-    running the stand-alone KL pass."""
-    _state["fuse_kl"] = bool(enabled)
+    running the stand-alone KL pass.  ``"unchecked"``: the same without the device-side
+    fingerprint check of ``FusedKLCache`` (two tiny launches per layer and step)."""
+    _state["fuse_kl"] = "unchecked" if enabled == "unchecked" else bool(enabled)
 
 
 def set_kl_shard(rank=None, world=None):
@@ -126,7 +127,7 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
     aux = {}
     lib = nv.lib()
     math = _MATH[_state["math"]] if math is None else math
-    with torch.cuda.device(dev):
+    with nv.device_guard(dev):
         st = nv.stream_ptr(dev)
         if log_sigma2 is None:
             ws_bytes = 0
@@ -155,7 +156,11 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
                 ws_bytes = lib.cplxk_linear_vd_workspace_bytes(M, N, K, code)
                 ws = nv.workspace(dev, ws_bytes)
             s2 = torch.empty((M, N), dtype=dt, device=dev) if want_s2 else None
-            if kl_req is not None and ws is not None and _state["fuse_kl"]:
+            if (kl_req is not None and ws is not None and _state["fuse_kl"]
+                    and lib.cplxk_linear_vd_fuses_kl(M, N, K, code, math)):
+                # the pre-pass also fingerprints the parameters it reads (FusedKLCache compares at hand-out)
+                fp = (torch.empty(1, dtype=torch.int64, device=dev)
+                      if _state["fuse_kl"] != "unchecked" else None)
                 kl_sum = torch.empty((), dtype=torch.float32, device=dev)
                 kl_ws = nv.kl_workspace(dev)
                 done = ctypes.c_int(0)
@@ -169,9 +174,10 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
                     nv.ptr(ls2), nv.ptr(er), nv.ptr(ei), noise, seed, offset, threads,
                     nv.ptr(y_re), nv.ptr(y_im), M, N, K, code, math, nv.ptr(s2), nv.ptr(ws),
                     ws_bytes, kl_req["kind"], nv.ptr(kl_sum), nv.ptr(kl_ws), kl_ws.numel() * 8,
-                    lo, hi, None if ev is None else ctypes.c_void_p(ev.cuda_event), ctypes.byref(done), st))
+                    lo, hi, None if ev is None else ctypes.c_void_p(ev.cuda_event), nv.ptr(fp),
+                    ctypes.byref(done), st))
                 if done.value:
-                    kl_req["sum"], kl_req["event"] = kl_sum, ev
+                    kl_req["sum"], kl_req["event"], kl_req["fp"] = kl_sum, ev, fp
             else:
                 nv.check(lib.cplxk_linear_vd_fwd(nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi),
                                                  nv.ptr(br), nv.ptr(bi), nv.ptr(ls2), nv.ptr(er),
@@ -179,7 +185,7 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
                                                  nv.ptr(y_re), nv.ptr(y_im), M, N, K, code, math,
                                                  nv.ptr(s2), nv.ptr(ws), ws_bytes, st))
             if noise != nv.NOISE_INJECT:
-                gen.set_offset(offset + inc)
+                nv.philox_advance(gen, offset, inc)
             aux = {"s2": s2, "philox": (seed, offset, threads), "eps": (er, ei), "x": (xr, xi)}
     y_re = y_re.reshape(*lead, N)
     if cplx:
@@ -209,7 +215,7 @@ def _masked_forward_raw(x_re, x_im, w_re, w_im, mask, b_re, b_im):
     y_im = torch.empty((M, N), dtype=dt, device=dev) if cplx else None
     lib = nv.lib()
     math = _MATH[_state["math"]]
-    with torch.cuda.device(dev):
+    with nv.device_guard(dev):
         ws_bytes = lib.cplxk_linear_masked_workspace_bytes(M, N, K, code)
         ws = nv.workspace(dev, ws_bytes)
         nv.check(lib.cplxk_linear_masked_fwd(nv.ptr(xr), nv.ptr(xi), nv.ptr(wr), nv.ptr(wi), nv.ptr(mk),
@@ -313,14 +319,14 @@ def _vd_backward_extra(ctx, g_re, g_im, dx_re, dx_im, need_x, need_ls2):
     gs2 = torch.empty_like(s2)
     seed, offset, threads = ctx.philox
     er, ei = ctx.eps
-    with torch.cuda.device(dev):
+    with nv.device_guard(dev):
         nv.check(nv.lib().cplxk_vd_grad_s2(nv.ptr(g_re), nv.ptr(g_im), nv.ptr(s2), nv.ptr(er),
                                            nv.ptr(ei), ctx.noise, seed, offset, threads,
                                            nv.ptr(gs2), M, N, nv.dtype_code(dt), nv.stream_ptr(dev)))
     dls2 = None
     if need_x:   # dq = g_s2 . E ; dx += 2 x dq
         dq, _ = _gemm(gs2, None, _transpose(ls2, TR_EXP), None)
-        with torch.cuda.device(dev):
+        with nv.device_guard(dev):
             nv.check(nv.lib().cplxk_vd_grad_input(nv.ptr(dx_re), nv.ptr(dx_im), nv.ptr(xr),
                                                   nv.ptr(xi), nv.ptr(dq), dq.numel(),
                                                   nv.dtype_code(dt), nv.stream_ptr(dev)))
@@ -328,7 +334,7 @@ def _vd_backward_extra(ctx, g_re, g_im, dx_re, dx_im, need_x, need_ls2):
         qT = _transpose(xr, TR_ABS2, xi) if cplx else _transpose(xr, TR_SQR)
         dE, _ = _gemm(_transpose(gs2), None, qT, None)
         dls2 = torch.empty_like(dE)
-        with torch.cuda.device(dev):
+        with nv.device_guard(dev):
             nv.check(nv.lib().cplxk_mul_exp(nv.ptr(dE), nv.ptr(ls2), nv.ptr(dls2), dE.numel(),
                                             nv.dtype_code(dt), 0, nv.stream_ptr(dev)))
     return dls2
@@ -455,12 +461,24 @@ class _RealLinearVDFn(torch.autograd.Function):
         return _shape_back(dx, ctx.lead, K, ctx.x_dtype), dw, db, dls2, None, None, None
 
 
+def _wants_grad(*tensors):
+    """False: nothing would be recorded anyway -- call the launcher directly (torch's
+    autograd.Function.apply costs more host time than the small-shape kernels take)."""
+    if not torch.is_grad_enabled():
+        return False
+    return any(t is not None and t.requires_grad for t in tensors)
+
+
 def cplx_linear(x_re, x_im, w_re, w_im, b_re=None, b_im=None):
     """y = x W^T + b on split planes (reference: cplx.linear_naive, cplx.py:634-648)."""
+    if not _wants_grad(x_re, x_im, w_re, w_im, b_re, b_im):
+        return _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, None, None, None, None)[:2]
     return _CplxLinearFn.apply(x_re, x_im, w_re, w_im, b_re, b_im)
 
 
 def real_linear(x, w, b=None):
+    if not _wants_grad(x, w, b):
+        return _forward_raw(x, None, w, None, b, None, None, None, None, None)[0]
     return _RealLinearFn.apply(x, w, b)
 
 
@@ -526,7 +544,7 @@ class _OuterFn(torch.autograd.Function):
         B = a_re.shape[0]
         z_re = torch.empty((B, d1 * d2), dtype=dt, device=dev)
         z_im = torch.empty_like(z_re) if cplx else None
-        with torch.cuda.device(dev):
+        with nv.device_guard(dev):
             nv.check(nv.lib().cplxk_outer_fwd(nv.ptr(a_re), nv.ptr(a_im), nv.ptr(b_re), nv.ptr(b_im),
                                               nv.ptr(z_re), nv.ptr(z_im), B, d1, d2,
                                               1 if conjugate else 0, code, nv.stream_ptr(dev)))
@@ -553,7 +571,7 @@ class _OuterFn(torch.autograd.Function):
         d1_re, d2_re = new(d1, want1), new(d2, want2)
         d1_im = new(d1, want1) if ctx.cplx else None
         d2_im = new(d2, want2) if ctx.cplx else None
-        with torch.cuda.device(dev):
+        with nv.device_guard(dev):
             nv.check(nv.lib().cplxk_outer_bwd(nv.ptr(g_re), nv.ptr(g_im), nv.ptr(a_re), nv.ptr(a_im),
                                               nv.ptr(b_re), nv.ptr(b_im), nv.ptr(d1_re), nv.ptr(d1_im),
                                               nv.ptr(d2_re), nv.ptr(d2_im), B, d1, d2, 1 if conj else 0,
@@ -606,6 +624,9 @@ def cplx_linear_vd(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps=None, kl_
     nn/relevance/complex/base.py:43-56). ``eps=(eps_re, eps_im)`` injects the noise
     (each ~ N(0, 1/2)); ``None`` draws it inside the kernel.  ``kl_req``: see ``_forward_raw``."""
     er, ei, mode = _noise_args(eps)
+    if not _wants_grad(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, er, ei):
+        return _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, er, ei, mode,
+                            kl_req=kl_req)[:2]
     return _CplxLinearVDFn.apply(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, er, ei, mode,
                                  kl_req)
 
@@ -613,15 +634,40 @@ def cplx_linear_vd(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps=None, kl_
 def real_linear_vd(x, w, b, log_sigma2, eps=None, kl_req=None):
     """Reference: LinearGaussian.forward, nn/relevance/real/base.py:43-49."""
     er, _, mode = _noise_args((eps, None) if eps is not None else None)
+    if not _wants_grad(x, w, b, log_sigma2, er):
+        return _forward_raw(x, None, w, None, b, None, log_sigma2, er, None, mode, kl_req=kl_req)[0]
     return _RealLinearVDFn.apply(x, w, b, log_sigma2, er, mode, kl_req)
 
 
+_stale_flags = {}     # device index -> pinned int32[1] the guard kernel raises on a mismatch
+
+
+def _stale_flag(dev):
+    flag = _stale_flags.get(dev.index)
+    if flag is None:
+        flag = _stale_flags[dev.index] = torch.zeros(1, dtype=torch.int32).pin_memory()
+    return flag
+
+
+def _check_stale(dev):
+    flag = _stale_flags.get(dev.index)
+    if flag is not None and int(flag[0]) != 0:
+        flag[0] = 0
+        raise RuntimeError(
+            "cplxmodule_b200: the parameters of a variational layer were modified through `.data` "
+            "(or another write autograd does not see) between its forward and penalties(); the KL "
+            "sum handed out for that step was NaN.  Edit parameters before the forward, or call "
+            "cplxmodule_b200.set_kl_fusion(False).")
+
+
 class FusedKLCache:
-    """KL sum produced by the last training-mode forward of a layer, valid while the
-    parameters it was computed from are untouched (tensor identity, storage and autograd
-    version counters) and handed out once.  Caveat: writes through ``param.data`` do not bump
-    the version counter -- code that edits parameters that way between a forward and the
-    ``penalties()`` of the same step should call ``set_kl_fusion(False)``."""
+    """KL sum produced by the last training-mode forward of a layer, handed out once and only
+    for unchanged parameters.  Two checks: on the host tensor identity, storage and autograd
+    version counters (catches optimizer steps, ``load_state_dict``, ``.to()``); on the device a
+    fingerprint of a strided sample of the parameters taken after the forward and again at
+    hand-out (``cplxk_kl_guard``: catches writes through ``param.data``, which bump no version
+    counter).  On a device mismatch the value handed out is NaN and the next call into the
+    cache raises -- nothing synchronises."""
 
     def __init__(self):
         self._entry = None
@@ -630,16 +676,43 @@ class FusedKLCache:
     def _key(params):
         return tuple((id(p), p.data_ptr(), p._version, p.dtype) for p in params if p is not None)
 
+    @staticmethod
+    def _planes(params):
+        # (w_re, w_im | None, log_sigma2) as dense [N, K] planes (views when already dense)
+        w_re, w_im, ls2 = params if len(params) == 3 else (params[0], None, params[1])
+        N = w_re.shape[0]
+        flat = lambda t: None if t is None else nv.plane(t.detach()).reshape(N, -1)
+        return flat(w_re), flat(w_im), flat(ls2.to(w_re.dtype) if ls2.dtype != w_re.dtype else ls2)
+
+    def _guard(self, params, fp, fused, out):
+        wr, wi, ls2 = self._planes(params)
+        dev = wr.device
+        with nv.device_guard(dev):
+            nv.check(nv.lib().cplxk_kl_guard(
+                nv.ptr(wr), nv.ptr(wi), nv.ptr(ls2), wr.shape[0], wr.shape[1], nv.dtype_code(wr.dtype),
+                None, nv.ptr(fp), nv.ptr(fused), nv.ptr(out),
+                ctypes.c_void_p(_stale_flag(dev).data_ptr()), nv.stream_ptr(dev)))
+
     def put(self, params, kl_req):
         self._entry = None
         if kl_req is not None and "sum" in kl_req:
-            self._entry = (self._key(params), kl_req["sum"], kl_req.get("rows"), kl_req.get("event"))
+            _check_stale(kl_req["sum"].device)
+            self._entry = (self._key(params), kl_req["sum"], kl_req.get("rows"), kl_req.get("event"),
+                           kl_req.get("fp"))
 
     def take(self, params, rows=None, with_event=False):
         """The cached sum if it covers ``rows`` (None: the whole layer) of unchanged parameters."""
         entry, self._entry = self._entry, None
         if entry is not None and entry[0] == self._key(params) and entry[2] == rows:
-            return (entry[1], entry[3]) if with_event else entry[1]
+            value, fp = entry[1], entry[4]
+            _check_stale(value.device)
+            if fp is not None:
+                if entry[3] is not None:     # shard request: the sum is final at this event (after the pre-pass)
+                    torch.cuda.current_stream(value.device).wait_event(entry[3])
+                out = torch.empty_like(value)
+                self._guard(params, fp, value, out)
+                value = out
+            return (value, entry[3]) if with_event else value
         return (None, None) if with_event else None
 
 
@@ -654,7 +727,7 @@ def kl_penalty(kind, w_re, w_im, log_sigma2, reduction="sum"):
     wr, wi, ls2 = nv.plane(w_re), nv.plane(w_im), nv.plane(log_sigma2, dt)
     n = wr.numel()
     lib = nv.lib()
-    with torch.cuda.device(dev):
+    with nv.device_guard(dev):
         st = nv.stream_ptr(dev)
         if reduction is None:
             out = torch.empty_like(wr)
@@ -702,7 +775,7 @@ class _KLFn(torch.autograd.Function):
         scale = 1.0 / max(n, 1) if ctx.reduction == "mean" else 1.0
         d_wr, d_ls2 = torch.empty_like(wr), torch.empty_like(ls2)
         d_wi = torch.empty_like(wi) if wi is not None else None
-        with torch.cuda.device(dev):
+        with nv.device_guard(dev):
             nv.check(nv.lib().cplxk_kl_bwd(ctx.kind, nv.ptr(wr), nv.ptr(wi), nv.ptr(ls2), n,
                                            nv.dtype_code(dt), nv.ptr(grad), 1 if per_elem else 0,
                                            1 if grad.dtype == torch.float32 else 0, scale,
@@ -713,6 +786,11 @@ class _KLFn(torch.autograd.Function):
 
 def kl(kind, w_re, w_im, log_sigma2, reduction="sum", precomputed=None):
     """``precomputed``: 0-d float32 sum from ``FusedKLCache.take`` (or None)."""
+    if not _wants_grad(w_re, w_im, log_sigma2):
+        if precomputed is not None and reduction in ("sum", "mean"):
+            out = precomputed / max(w_re.numel(), 1) if reduction == "mean" else precomputed
+            return out.to(w_re.dtype) if w_re.dtype != torch.float32 else out
+        return kl_penalty(kind, w_re, w_im, log_sigma2, reduction)
     pre = None if precomputed is None else [precomputed]
     return _KLFn.apply(kind, reduction, w_re, w_im, log_sigma2, pre)
 
@@ -724,7 +802,7 @@ def _log_alpha_raw(w_re, w_im, log_sigma2, threshold=None):
     wr, wi, ls2 = nv.plane(w_re), nv.plane(w_im), nv.plane(log_sigma2, dt)
     out = torch.empty_like(wr)
     lib = nv.lib()
-    with torch.cuda.device(dev):
+    with nv.device_guard(dev):
         st = nv.stream_ptr(dev)
         if threshold is None:
             nv.check(lib.cplxk_log_alpha(nv.ptr(wr), nv.ptr(wi), nv.ptr(ls2), wr.numel(), code,
@@ -781,7 +859,7 @@ def kl_and_mask(kind, w_re, w_im, log_sigma2, threshold, reduction="sum"):
         raise ValueError(f"`reduction` must be `sum` or `mean`. Got {reduction}.")
     mask = torch.empty_like(wr)
     out = torch.empty((), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with nv.device_guard(dev):
         ws = nv.kl_workspace(dev)
         scale = 1.0 if reduction == "sum" else 1.0 / max(n, 1)
         nv.check(nv.lib().cplxk_kl_mask(kind, nv.ptr(wr), nv.ptr(wi), nv.ptr(ls2), n, code,

@@ -211,6 +211,9 @@ int cplxk_linear_vd_prepare(const void* x_re, const void* x_im,
  *   kl_event     : cudaEvent_t (nullable) recorded on `stream` right after the pre-pass launch:
  *                  *kl_sum is final there, so that all-reduce can run on another stream while
  *                  the GEMM kernel computes.
+ *   kl_fingerprint : device uint64 (nullable): fingerprint of the parameters the sum was computed
+ *                  from, written with the sum; cplxk_kl_guard compares it with the parameters
+ *                  as they are when the sum is handed out.
  * Replaces the pair CplxLinearGaussian.forward + CplxVDMixin.penalty.sum()
  * (nn/relevance/complex/base.py:43-56, complex/vd.py:95-99, relevance/base.py:135-139).
  */
@@ -228,7 +231,11 @@ int cplxk_linear_vd_fwd_kl(const void* x_re, const void* x_im,
                            int kl_kind, float* kl_sum,
                            void* kl_workspace, size_t kl_workspace_bytes,
                            int64_t kl_row_begin, int64_t kl_row_end, void* kl_event,
-                           int* kl_done, void* stream);
+                           void* kl_fingerprint, int* kl_done, void* stream);
+/* 1 if cplxk_linear_vd_fwd_kl would produce the KL by-product for this shape / dtype / math mode
+ * (given a workspace), 0 if it runs a path without the fused pre-pass */
+int cplxk_linear_vd_fuses_kl(int64_t M, int64_t N, int64_t K, int dtype, int math);
+
 
 /*
  * Outer-product features of the bilinear layers: z[b, p * d2 + q] = conj?(x1[b, p]) * x2[b, q].
@@ -278,6 +285,20 @@ int cplxk_kl_mask(int kind, const void* w_re, const void* w_im,
                   const void* log_sigma2, int64_t n, int dtype,
                   float threshold, void* out_mask, float* out_sum, double scale,
                   void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Guard of the KL by-product of cplxk_linear_vd_fwd_kl (the reference recomputes the penalty from
+ * the current parameters on every penalties() call, nn/relevance/base.py:88-141; handing out a
+ * sum computed earlier is only valid while the parameters are unchanged).  A 64-bit fingerprint
+ * of the first 8 entries of every row of w_re, w_im (nullable), log_sigma2 ([N, K] each):
+ *   fp_ref == NULL : record   -> fp_out[0] (device uint64)
+ *   fp_ref != NULL : compare  -> out_sum[0] = fused_sum[0] if the fingerprint still equals
+ *                    fp_ref[0], NaN otherwise; *stale_flag (nullable, host-mapped int) = 1 then.
+ * One 1024-thread block, asynchronous on `stream`.
+ */
+int cplxk_kl_guard(const void* w_re, const void* w_im, const void* log_sigma2,
+                   int64_t N, int64_t K, int dtype, void* fp_out, const void* fp_ref,
+                   const float* fused_sum, float* out_sum, int* stale_flag, void* stream);
 
 /*
  * log_alpha itself and the relevance mask  (log_alpha <= threshold)

@@ -171,6 +171,39 @@ def test_fused_kl_equals_standalone_pass(cls, kind, reduction):
     assert fresh == ref and abs(fresh - alone) > 1e-3 * abs(alone)
 
 
+def test_fused_kl_data_edit_is_caught_on_the_device():
+    """a write through `.data` bumps no version counter: the hand-out is checked against a device
+    fingerprint of the parameters -> NaN for that step (never the stale sum), and the next call
+    into the cache raises; `set_kl_fusion("unchecked")` skips the check"""
+    torch.manual_seed(5)
+    layer = CplxLinearVD(264, 200).to(DEV).train()
+    x = cplx.randn(300, 264, device=DEV)
+    with torch.no_grad():
+        layer(x)
+        ok = sum(penalties(layer))
+        assert torch.isfinite(ok)
+        layer(x)
+        v = layer.log_sigma2._version
+        layer.log_sigma2.data.add_(1.0)
+        assert layer.log_sigma2._version == v            # invisible to the host-side key
+        stale = sum(penalties(layer))
+        torch.cuda.synchronize()
+        assert torch.isnan(stale)
+        with pytest.raises(RuntimeError, match=r"\.data"):
+            layer(x)
+        # the flag is cleared by the raise; the layer works again and sees the edited parameters
+        layer(x)
+        fresh = float(sum(penalties(layer)))
+        cb.set_kl_fusion(False)
+        ref = float(sum(penalties(layer)))
+        cb.set_kl_fusion("unchecked")
+        layer(x)
+        unchecked = float(sum(penalties(layer)))
+        cb.set_kl_fusion(True)
+    assert abs(fresh - ref) <= 1e-6 * abs(ref) and abs(unchecked - ref) <= 1e-6 * abs(ref)
+    assert abs(fresh - float(ok)) > 1e-3 * abs(ref)
+
+
 def test_fused_kl_keeps_gradients():
     torch.manual_seed(4)
     a = CplxLinearVD(256, 136).to(DEV).train()
