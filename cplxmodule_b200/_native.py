@@ -82,7 +82,8 @@ def _declare(lib):
     lib.cplxk_kl_bwd.argtypes = [_int, _vp, _vp, _vp, _i64, _int, _vp, _int, _int, ctypes.c_double,
                                  _vp, _vp, _vp, _vp]
     lib.cplxk_linear_vd_fuses_kl.argtypes = [_i64, _i64, _i64, _int, _int]
-    lib.cplxk_kl_guard.argtypes = [_vp, _vp, _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp]
+    lib.cplxk_kl_guard.argtypes = [_vp, _vp, _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   ctypes.c_size_t, _vp]
     lib.cplxk_linear_masked_workspace_bytes.restype = ctypes.c_size_t
     lib.cplxk_linear_masked_workspace_bytes.argtypes = [_i64, _i64, _i64, _int]
     lib.cplxk_linear_masked_fwd.argtypes = [_vp] * 9 + [_i64] * 3 + [_int, _int, _vp, ctypes.c_size_t, _vp]

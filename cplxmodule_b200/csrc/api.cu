@@ -51,6 +51,7 @@ const Knobs& knobs() {
     v.conv_pair = env_int("CPLXK_CONV_PAIR", 1) != 0;
     v.conv_persistent = env_int("CPLXK_CONV_NONPERSISTENT", 0) != 1;
     v.pdl = env_int("CPLXK_PDL", 1) != 0;
+    v.prep_prefetch = env_int("CPLXK_PREP_PREFETCH", 0) != 0;   // measured: slower (profiles/prep_prefetch_ab_r2.jsonl)
 #ifdef CPLXK_DEBUG
     v.dbg = env_int("CPLXK_DBG", 0);
 #else

@@ -312,7 +312,7 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
                       __half* __restrict__ wh_im, __nv_bfloat16* __restrict__ e,
                       float* __restrict__ isx, float* __restrict__ isw, int kl_kind,
                       float* __restrict__ kl_sum, KlWorkspace* __restrict__ kl_ws, int64_t kl_row0,
-                      int64_t kl_row1, unsigned long long* __restrict__ kl_fp) {
+                      int64_t kl_row1, unsigned long long* __restrict__ kl_fp, int prefetch_next) {
   // (separate __restrict__ parameters, not the struct: the no-alias facts let the loads of the
   // write pass be hoisted above its stores)
   PrepArgs a;
@@ -337,15 +337,24 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
   // at any time -- works on a mix of the two instead of all x rows first and all W rows last
   const int64_t M = a.M, N = a.N;
   const int64_t mn = M < N ? M : N;
-  for (int64_t g = blockIdx.x; g < M + N; g += gridDim.x) {
-    bool is_x;
-    int64_t r;
+  auto row_of = [&](int64_t g, bool& is_x, int64_t& r) {
     if (g < 2 * mn) {
       is_x = (g & 1) == 0;
       r = g >> 1;
     } else {
       is_x = M > N;
       r = mn + (g - 2 * mn);
+    }
+  };
+  for (int64_t g = blockIdx.x; g < M + N; g += gridDim.x) {
+    bool is_x;
+    int64_t r;
+    row_of(g, is_x, r);
+    if (prefetch_next && g + gridDim.x < M + N) {     // the row this block converts next: towards L2 now
+      bool nx;
+      int64_t nr;
+      row_of(g + gridDim.x, nx, nr);
+      prep_prefetch_row<kCplx, 256>(a, nx, nr, tid);
     }
     kl_acc += prep_convert_row<kCplx, 256, 2, kMask>(a, is_x, r, tid, red, sync, fp_acc);
   }
@@ -442,7 +451,8 @@ int vd_prepare_f16_launch(bool cplx, const PrepArgs& a, const KlFuse& kl, cudaSt
   vd_prepare_f16_kernel<C, MK><<<grid, 256, 0, st>>>(a.x_re, a.x_im, a.M, a.w_re, a.w_im, a.ls2, a.w_mask, \
                                                      a.N, a.K, a.xh_re, a.xh_im, a.q, a.wh_re, a.wh_im,   \
                                                      a.e, a.isx, a.isw, a.kl_kind, kl.sum, kws, a.kl_row0, \
-                                                     a.kl_row1, static_cast<unsigned long long*>(kl.fp))
+                                                     a.kl_row1, static_cast<unsigned long long*>(kl.fp), \
+                                                     knobs().prep_prefetch ? 1 : 0)
   if (cplx && mask) CPLXK_PREP(true, true);
   else if (cplx) CPLXK_PREP(true, false);
   else if (mask) CPLXK_PREP(false, true);

@@ -236,79 +236,71 @@ static int kl_entry(int kind, const void* w_re, const void* w_im, const void* lo
 // fingerprint of a strided sample of the parameters (the first 8 entries of every row of every
 // plane: any whole-tensor edit -- mul_, clamp_, copy_, fill_ -- changes it) is taken right after
 // the forward and again when the sum is asked for.  One tiny launch each, no synchronisation.
+// One row head per thread (first 8 entries of each plane), many small blocks: the loads are
+// scattered 32-byte sectors a row pitch apart, and one SM cannot keep enough of them in flight (a
+// single 1024-thread block needed 45 us for 4096 rows).  Block sums go to ws->fp, the last block
+// (ticket) finishes.
+constexpr int kGuardThreads = 128;
+
 template <typename T>
-__device__ __forceinline__ unsigned long long fingerprint_block(const T* __restrict__ w_re,
-                                                                const T* __restrict__ w_im,
-                                                                const T* __restrict__ ls2, int64_t N,
-                                                                int64_t K, unsigned long long* sh) {
+__global__ void __launch_bounds__(kGuardThreads)
+kl_guard_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T* __restrict__ ls2,
+                int64_t N, int64_t K, KlWorkspace* __restrict__ ws, unsigned long long* __restrict__ fp_out,
+                const unsigned long long* __restrict__ fp_ref, const float* __restrict__ fused,
+                float* __restrict__ out, int* __restrict__ stale_flag) {
+  __shared__ unsigned long long sh[kGuardThreads / 32];
+  __shared__ bool is_last;
   const int ncol = K < 8 ? static_cast<int>(K) : 8;
-  unsigned long long acc = 0ull;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   const bool vec = ncol == 8 && (K % 4) == 0 && std::is_same<T, float>::value && al16(w_re) &&
                    al16(ls2) && (!w_im || al16(w_im));
-  if (vec) {
-    // four rows per trip, all 24 16-byte loads issued before the first mix: one memory round trip
-    const float* a = reinterpret_cast<const float*>(w_re);
-    const float* b = reinterpret_cast<const float*>(w_im);
-    const float* c = reinterpret_cast<const float*>(ls2);
-    for (int64_t r0 = threadIdx.x; r0 < N; r0 += 4 * static_cast<int64_t>(blockDim.x)) {
-      float4 va[4][2], vb[4][2], vc[4][2];
+  unsigned long long acc = 0ull;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kGuardThreads + threadIdx.x; r < N;
+       r += static_cast<int64_t>(gridDim.x) * kGuardThreads) {
+    if (vec) {
+      const float* a = reinterpret_cast<const float*>(w_re) + r * K;
+      const float* b = w_im ? reinterpret_cast<const float*>(w_im) + r * K : nullptr;
+      const float* c = reinterpret_cast<const float*>(ls2) + r * K;
+      float4 va[2], vb[2], vc[2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int64_t r = r0 + i * static_cast<int64_t>(blockDim.x);
-        if (r < N) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            va[i][h] = __ldg(reinterpret_cast<const float4*>(a + r * K + 4 * h));
-            vb[i][h] = b ? __ldg(reinterpret_cast<const float4*>(b + r * K + 4 * h)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            vc[i][h] = __ldg(reinterpret_cast<const float4*>(c + r * K + 4 * h));
-          }
-        }
+      for (int h = 0; h < 2; ++h) {
+        va[h] = __ldg(reinterpret_cast<const float4*>(a + 4 * h));
+        vb[h] = b ? __ldg(reinterpret_cast<const float4*>(b + 4 * h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vc[h] = __ldg(reinterpret_cast<const float4*>(c + 4 * h));
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int64_t r = r0 + i * static_cast<int64_t>(blockDim.x);
-        if (r < N) {
+      for (int h = 0; h < 2; ++h) {
+        const float fa[4] = {va[h].x, va[h].y, va[h].z, va[h].w};
+        const float fb[4] = {vb[h].x, vb[h].y, vb[h].z, vb[h].w};
+        const float fc[4] = {vc[h].x, vc[h].y, vc[h].z, vc[h].w};
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float fa[4] = {va[i][h].x, va[i][h].y, va[i][h].z, va[i][h].w};
-            const float fb[4] = {vb[i][h].x, vb[i][h].y, vb[i][h].z, vb[i][h].w};
-            const float fc[4] = {vc[i][h].x, vc[i][h].y, vc[i][h].z, vc[i][h].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc += fingerprint_elem(fa[j], fb[j], b != nullptr, fc[j], r, 4 * h + j);
-          }
-        }
+        for (int j = 0; j < 4; ++j) acc += fingerprint_elem(fa[j], fb[j], b != nullptr, fc[j], r, 4 * h + j);
       }
-    }
-  } else {
-    for (int64_t r = threadIdx.x; r < N; r += blockDim.x)
+    } else {
       for (int j = 0; j < ncol; ++j) {
         const int64_t i = r * K + j;
         acc += fingerprint_elem(Elem<T>::to_f(w_re[i]), w_im ? Elem<T>::to_f(w_im[i]) : 0.f, w_im != nullptr,
                                 Elem<T>::to_f(ls2[i]), r, j);
       }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
   __syncthreads();
-  unsigned long long total = 0ull;
-  for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) total += sh[w];
-  return total;
-}
-
-// fp_ref == nullptr: record (fp_out[0] = fingerprint).  Otherwise compare: out = fused sum when
-// the fingerprints agree, NaN (and *stale_flag = 1, a host-mapped int the caller polls) if not.
-template <typename T>
-__global__ void __launch_bounds__(1024)
-kl_guard_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T* __restrict__ ls2,
-                int64_t N, int64_t K, unsigned long long* __restrict__ fp_out,
-                const unsigned long long* __restrict__ fp_ref, const float* __restrict__ fused,
-                float* __restrict__ out, int* __restrict__ stale_flag) {
-  __shared__ unsigned long long sh[32];
-  const unsigned long long fp = fingerprint_block<T>(w_re, w_im, ls2, N, K, sh);
-  if (threadIdx.x != 0) return;
-  if (fp_ref == nullptr) {
+  if (threadIdx.x == 0) {
+    unsigned long long total = 0ull;
+    for (int w = 0; w < kGuardThreads / 32; ++w) total += sh[w];
+    if (total != 0ull) atomicAdd(&ws->fp, total);
+    __threadfence();
+    is_last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  const unsigned long long fp = *reinterpret_cast<volatile unsigned long long*>(&ws->fp);
+  ws->fp = 0ull, ws->ticket = 0;     // restore the workspace for the next call on this stream
+  if (fp_ref == nullptr) {           // record
     fp_out[0] = fp;
     return;
   }
@@ -322,20 +314,26 @@ kl_guard_kernel(const T* __restrict__ w_re, const T* __restrict__ w_im, const T*
 
 extern "C" int cplxk_kl_guard(const void* w_re, const void* w_im, const void* log_sigma2, int64_t N,
                               int64_t K, int dtype, void* fp_out, const void* fp_ref,
-                              const float* fused_sum, float* out_sum, int* stale_flag, void* stream) {
+                              const float* fused_sum, float* out_sum, int* stale_flag,
+                              void* kl_workspace, size_t kl_workspace_bytes, void* stream) {
   if (!w_re || !log_sigma2 || N < 0 || K < 0) return CPLXK_ERR_BADARG;
   if (fp_ref ? (!fused_sum || !out_sum) : !fp_out) return CPLXK_ERR_BADARG;
+  if (!kl_workspace || kl_workspace_bytes < sizeof(KlWorkspace)) return CPLXK_ERR_WORKSPACE;
+  if (!aligned16(kl_workspace)) return CPLXK_ERR_ALIGN;
   auto st = static_cast<cudaStream_t>(stream);
+  auto ws = static_cast<KlWorkspace*>(kl_workspace);
   auto fo = static_cast<unsigned long long*>(fp_out);
   auto fr = static_cast<const unsigned long long*>(fp_ref);
+  int64_t want = (N + kGuardThreads - 1) / kGuardThreads;
+  const int grid = static_cast<int>(want < 1 ? 1 : (want > 1024 ? 1024 : want));
   if (dtype == CPLXK_F32)
-    kl_guard_kernel<float><<<1, 1024, 0, st>>>(static_cast<const float*>(w_re), static_cast<const float*>(w_im),
-                                               static_cast<const float*>(log_sigma2), N, K, fo, fr, fused_sum,
-                                               out_sum, stale_flag);
+    kl_guard_kernel<float><<<grid, kGuardThreads, 0, st>>>(
+        static_cast<const float*>(w_re), static_cast<const float*>(w_im), static_cast<const float*>(log_sigma2),
+        N, K, ws, fo, fr, fused_sum, out_sum, stale_flag);
   else if (dtype == CPLXK_BF16)
-    kl_guard_kernel<__nv_bfloat16><<<1, 1024, 0, st>>>(
+    kl_guard_kernel<__nv_bfloat16><<<grid, kGuardThreads, 0, st>>>(
         static_cast<const __nv_bfloat16*>(w_re), static_cast<const __nv_bfloat16*>(w_im),
-        static_cast<const __nv_bfloat16*>(log_sigma2), N, K, fo, fr, fused_sum, out_sum, stale_flag);
+        static_cast<const __nv_bfloat16*>(log_sigma2), N, K, ws, fo, fr, fused_sum, out_sum, stale_flag);
   else
     return CPLXK_ERR_BADARG;
   CPLXK_CUDA_TRY(cudaGetLastError());

@@ -24,20 +24,19 @@ struct KlWorkspace {
 };
 
 // ---- parameter fingerprint (guard of the fused KL by-product, see kl.cu: cplxk_kl_guard) ------
-// wrapping sum over the first 8 entries of every row of every plane of mix64(bits ^ position tag)
-__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
-  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
-  x ^= x >> 27; x *= 0x94d049bb133111ebull;
-  return x ^ (x >> 31);
+// wrapping 64-bit sum over the first 8 entries of every row of every plane of
+// (bits ^ position tag) * odd constant: a change detector (any whole-tensor edit moves it), not a
+// cryptographic hash -- two multiply-adds per entry, so the guard kernel stays a few microseconds
+__device__ __forceinline__ unsigned long long fp_term(float v, unsigned int tag) {
+  return static_cast<unsigned long long>(__float_as_uint(v) ^ (tag * 0x9E3779B1u)) * 0xD6E8FEB86659FD93ull;
 }
 __device__ __forceinline__ unsigned long long fingerprint_elem(float w_re, float w_im, bool cplx,
                                                                float ls2, int64_t row, int j) {
-  const unsigned long long tag = static_cast<unsigned long long>(row * 8 + j) * 3ull;
-  unsigned long long acc = mix64(static_cast<unsigned long long>(__float_as_uint(w_re)) ^ (tag << 32));
-  if (cplx) acc += mix64(static_cast<unsigned long long>(__float_as_uint(w_im)) ^ ((tag + 1) << 32));
-  return acc + mix64(static_cast<unsigned long long>(__float_as_uint(ls2)) ^ ((tag + 2) << 32));
+  const unsigned int tag = (static_cast<unsigned int>(row) * 8u + static_cast<unsigned int>(j)) * 3u;
+  unsigned long long acc = fp_term(w_re, tag);
+  if (cplx) acc += fp_term(w_im, tag + 1u);
+  return acc + fp_term(ls2, tag + 2u);
 }
-
 // MUFU approximations without the denormal/range fix-up code of __logf/__expf/__fdividef:
 // every argument in this kernel is a normal number well inside the fast range.
 __device__ __forceinline__ float f_lg2(float x) {

@@ -19,6 +19,7 @@ struct Knobs {
   bool conv_pair;          // CPLXK_CONV_PAIR=0: conv on single-CTA tiles
   bool conv_persistent;    // CPLXK_CONV_NONPERSISTENT=1: one conv tile per CTA
   bool pdl;                // CPLXK_PDL=0: no programmatic dependent launch between pre-pass and GEMM
+  bool prep_prefetch;      // CPLXK_PREP_PREFETCH=1: the operand pre-pass prefetches its next row to L2 (default off: slower)
   int dbg;                 // CPLXK_DBG (debug builds only; 0 otherwise)
 };
 

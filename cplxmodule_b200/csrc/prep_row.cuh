@@ -26,6 +26,7 @@ struct PrepArgs {
   int kl_kind;                         // < 0: no KL
   int64_t kl_row0, kl_row1;            // weight rows that enter the KL sum
   int want_fp;                         // also fingerprint the parameters (kl_math.cuh; KL requests only)
+  int prefetch_next;                   // prefetch the group's next row to L2 (knob CPLXK_PREP_PREFETCH)
 };
 
 // `sync()` is a barrier over the kThreads cooperating threads (a block: __syncthreads); `red`
@@ -207,6 +208,22 @@ __device__ __forceinline__ float prep_convert_row(const PrepArgs& a, bool is_x, 
     emit(k, vr, vi);
   }
   return kl_acc;
+}
+
+// Pull the row this group converts NEXT towards L2 while the current one is being processed: the
+// pass is bound by the latency of its global loads (ncu: long-scoreboard stalls, 55 % of the DRAM
+// peak, half the issue slots idle), and an L2 hit costs a third of a DRAM round trip.
+template <bool kCplx, int kThreads>
+__device__ __forceinline__ void prep_prefetch_row(const PrepArgs& a, bool is_x, int64_t r, int tid) {
+  const int64_t K = a.K;
+  const float* pr = (is_x ? a.x_re : a.w_re) + r * K;
+  const float* pi = kCplx ? (is_x ? a.x_im : a.w_im) + r * K : nullptr;
+  const float* pl = (is_x || a.q == nullptr) ? nullptr : a.ls2 + r * K;
+  for (int64_t k = static_cast<int64_t>(tid) * 32; k < K; k += kThreads * 32) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + k));
+    if (kCplx) asm volatile("prefetch.global.L2 [%0];" ::"l"(pi + k));
+    if (pl) asm volatile("prefetch.global.L2 [%0];" ::"l"(pl + k));
+  }
 }
 
 // Sum of `v` over the kThreads cooperating threads (deterministic: fixed shuffle tree, then the

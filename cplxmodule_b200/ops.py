@@ -688,10 +688,12 @@ class FusedKLCache:
         wr, wi, ls2 = self._planes(params)
         dev = wr.device
         with nv.device_guard(dev):
+            kl_ws = nv.kl_workspace(dev)
             nv.check(nv.lib().cplxk_kl_guard(
                 nv.ptr(wr), nv.ptr(wi), nv.ptr(ls2), wr.shape[0], wr.shape[1], nv.dtype_code(wr.dtype),
                 None, nv.ptr(fp), nv.ptr(fused), nv.ptr(out),
-                ctypes.c_void_p(_stale_flag(dev).data_ptr()), nv.stream_ptr(dev)))
+                ctypes.c_void_p(_stale_flag(dev).data_ptr()), nv.ptr(kl_ws), kl_ws.numel() * 8,
+                nv.stream_ptr(dev)))
 
     def put(self, params, kl_req):
         self._entry = None

@@ -294,11 +294,13 @@ int cplxk_kl_mask(int kind, const void* w_re, const void* w_im,
  *   fp_ref == NULL : record   -> fp_out[0] (device uint64)
  *   fp_ref != NULL : compare  -> out_sum[0] = fused_sum[0] if the fingerprint still equals
  *                    fp_ref[0], NaN otherwise; *stale_flag (nullable, host-mapped int) = 1 then.
- * One 1024-thread block, asynchronous on `stream`.
+ * kl_workspace: cplxk_kl_workspace_bytes() bytes as for cplxk_kl (block sums + ticket).
+ * One row head per thread over N / 128 blocks, asynchronous on `stream`.
  */
 int cplxk_kl_guard(const void* w_re, const void* w_im, const void* log_sigma2,
                    int64_t N, int64_t K, int dtype, void* fp_out, const void* fp_ref,
-                   const float* fused_sum, float* out_sum, int* stale_flag, void* stream);
+                   const float* fused_sum, float* out_sum, int* stale_flag,
+                   void* kl_workspace, size_t kl_workspace_bytes, void* stream);
 
 /*
  * log_alpha itself and the relevance mask  (log_alpha <= threshold)
