@@ -13,8 +13,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(CSRC, "libcplxk.so")
-OBJ = os.path.join(CSRC, "_obj")
+# CPLXK_BUILD_TAG=<tag> [CPLXK_BUILD_FLAGS="-D..."]: a side build csrc/libcplxk_<tag>.so for same-box A/B
+# runs and instrumented measurements (loaded with CPLXK_LIB=<path>); never the shipped library
+_TAG = os.environ.get("CPLXK_BUILD_TAG", "")
+OUT = os.path.join(CSRC, f"libcplxk_{_TAG}.so" if _TAG else "libcplxk.so")
+OBJ = os.path.join(CSRC, f"_obj_{_TAG}" if _TAG else "_obj")
 SOURCES = ["api.cu", "kl.cu", "fwd_simt.cu", "fwd_tc.cu", "fwd_tc3.cu", "fwd_lin3.cu", "conv.cu", "conv_tc.cu", "bwd.cu", "bilinear.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -29,6 +32,7 @@ def nvcc_path():
 def _fingerprint():
     h = hashlib.sha256()
     h.update(os.environ.get("CPLXK_DEBUG_BUILD", "0").encode())
+    h.update(os.environ.get("CPLXK_BUILD_FLAGS", "").encode())
     names = sorted(os.listdir(CSRC)) + ["../../include/cplxk.h"]
     for name in names:
         path = os.path.join(CSRC, name)
@@ -53,6 +57,7 @@ def build(force=False, verbose=False):
                     "--expt-relaxed-constexpr", "-I", os.path.join(HERE, "..", "include")]
     if os.environ.get("CPLXK_DEBUG_BUILD") == "1":   # measurement aids (CPLXK_DBG); never shipped
         flags += ["-DCPLXK_DEBUG"]
+    flags += os.environ.get("CPLXK_BUILD_FLAGS", "").split()
     if verbose:
         flags += ["-Xptxas", "-v"]
 

@@ -65,7 +65,23 @@ struct Tc3Params {
   const float* sx;         // [M] inverse row scales of x (nullable)
   const float* sw;         // [N] inverse row scales of W (nullable)
   EpiParams ep;
+#ifdef CPLXK_TRACE
+  long long* trace;        // -DCPLXK_TRACE builds: per-tile SM clock stamps of cluster 0's leader CTA
+#endif
 };
+
+#ifdef CPLXK_TRACE
+// slots per tile: 0 MMA warp past tmem_empty, 1 last MMA committed, 2 noise prefetched (warp 2),
+// 3 accumulators seen full, 4 TMEM handed back, 5 stores issued; 6 producer issued the tile's last load
+#define CPLXK_STAMP(slot)                                                                  \
+  do {                                                                                     \
+    if (p.trace && cluster_id == 0 && leader && lane == 0) p.trace[(t / num_clusters) * 8 + (slot)] = clock64(); \
+  } while (0)
+static long long* g_tc3_trace = nullptr;
+extern "C" void cplxk_debug_set_trace(void* dev_ptr) { g_tc3_trace = static_cast<long long*>(dev_ptr); }
+#else
+#define CPLXK_STAMP(slot) do { } while (0)
+#endif
 
 template <typename OutT, bool kCplx>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
@@ -153,6 +169,7 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
           __syncwarp();
           if (++s == C::STAGES) s = 0, ph ^= 1u;
         }
+        CPLXK_STAMP(6);
       }
     }
   } else if (warp == 1) {
@@ -174,6 +191,7 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
       for (int t = cluster_id; t < num_tiles; t += num_clusters, tile_par ^= 1u) {
         ptx::mbar_wait_cluster(bar_tfree, tile_par ^ 1u);   // previous tile drained by both CTAs
         ptx::tcgen05_fence_after();
+        CPLXK_STAMP(0);
         for (int kb = 0; kb < num_kb; ++kb) {
           const uint32_t st = base + s * C::STAGE_BYTES;
           if (p.dbg != 1) ptx::mbar_wait(bar_full + 8 * s, ph);
@@ -207,6 +225,7 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
         }
         if (elected) ptx::umma_commit_pair(bar_accum);             // accumulators complete, both CTAs
         __syncwarp();
+        CPLXK_STAMP(1);
       }
     }
   } else {
@@ -222,6 +241,7 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
         const int64_t nb = static_cast<int64_t>(tile_n) * C::BN + ((warp - 2) >> 2) * 64;
         noise_prefetch<OutT, kCplx, 64>(p.ep, m, nb, nre, nim);
       }
+      if (warp == 2) CPLXK_STAMP(2);
       // the first tile's noise does not depend on the pre-pass: it is generated while that launch
       // drains (programmatic dependent launch); the row / column scales below do depend on it
       ptx::grid_dep_wait();
@@ -252,30 +272,41 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
 
       ptx::mbar_wait(bar_accum, tile_par);
       ptx::tcgen05_fence_after();
+      if (warp == 2) CPLXK_STAMP(3);
       const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 64;
       const float* cvb = cv + half * 64;
+      // The TMEM reads are software-pipelined: the loads of chunk c + 1 are issued right after the
+      // wait for chunk c and fly while chunk c is folded into the noise registers.  (Serialised
+      // load -> wait -> math rounds kept the accumulators busy for 2.5-5 us per tile and the tensor
+      // pipe idle for as long: tools/tc3_trace.py, profiles/tc3_trace_r2.jsonl.)
+      uint32_t r_re[2][8], r_im[2][8], r_s2[2][8];
+      ptx::tmem_ld_32x32b_x8(lane_base, r_re[0]);
+      if constexpr (kCplx) ptx::tmem_ld_32x32b_x8(lane_base + C::BN, r_im[0]);
+      ptx::tmem_ld_32x32b_x8(lane_base + C::NA * C::BN, r_s2[0]);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int col = c * 8;
-        uint32_t r_re[8], r_im[8], r_s2[8];
-        ptx::tmem_ld_32x32b_x8(lane_base + col, r_re);
-        if constexpr (kCplx) ptx::tmem_ld_32x32b_x8(lane_base + C::BN + col, r_im);
-        ptx::tmem_ld_32x32b_x8(lane_base + C::NA * C::BN + col, r_s2);
+        const int cur = c & 1, nxt = cur ^ 1;
         ptx::tmem_ld_wait();
-        if (c == 7) {   // last TMEM read of this warp: hand the accumulators back to the MMA issuer
+        if (c < 7) {
+          ptx::tmem_ld_32x32b_x8(lane_base + col + 8, r_re[nxt]);
+          if constexpr (kCplx) ptx::tmem_ld_32x32b_x8(lane_base + C::BN + col + 8, r_im[nxt]);
+          ptx::tmem_ld_32x32b_x8(lane_base + C::NA * C::BN + col + 8, r_s2[nxt]);
+        } else {   // last TMEM read of this warp: hand the accumulators back to the MMA issuer
           ptx::tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_cluster(tfree_remote);
+          if (warp == 2) CPLXK_STAMP(4);
         }
         float f_s2[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float sc = sxm * cvb[256 + col + j];
-          f_s2[j] = __uint_as_float(r_s2[j]);
+          f_s2[j] = __uint_as_float(r_s2[cur][j]);
           const float sd = sd_of(f_s2[j]);
-          nre[col + j] = fmaf(nre[col + j], sd, fmaf(__uint_as_float(r_re[j]), sc, cvb[col + j]));
+          nre[col + j] = fmaf(nre[col + j], sd, fmaf(__uint_as_float(r_re[cur][j]), sc, cvb[col + j]));
           if constexpr (kCplx)
-            nim[col + j] = fmaf(nim[col + j], sd, fmaf(__uint_as_float(r_im[j]), sc, cvb[128 + col + j]));
+            nim[col + j] = fmaf(nim[col + j], sd, fmaf(__uint_as_float(r_im[cur][j]), sc, cvb[128 + col + j]));
         }
         if (p.ep.s2_out && m < p.M && nb + col < p.N) {
           const int64_t ncol = nb + col;
@@ -289,6 +320,7 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
         store_run64<OutT>(static_cast<OutT*>(p.ep.y_re) + m * p.N + nb, nre, nvalid);
         if constexpr (kCplx) store_run64<OutT>(static_cast<OutT*>(p.ep.y_im) + m * p.N + nb, nim, nvalid);
       }
+      if (warp == 2) CPLXK_STAMP(5);
     }
     ptx::tcgen05_fence_before();
   }
@@ -400,6 +432,9 @@ static int launch_tc3(const Tc3Operands& o, int64_t M, int64_t N, int64_t K, con
   p.group = knobs().raster;
   p.sx = o.sx, p.sw = o.sw;
   p.ep = ep;
+#ifdef CPLXK_TRACE
+  p.trace = g_tc3_trace;
+#endif
   const int64_t pairs = static_cast<int64_t>(p.tiles_m2) * p.tiles_n;
   if (pairs > 0x3fffffff) return CPLXK_ERR_UNSUPPORTED;
   int sm_count = 0;
