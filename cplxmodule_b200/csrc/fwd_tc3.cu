@@ -147,6 +147,11 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       ptx::grid_dep_wait();   // the operands are written by the pre-pass launch before this one
+      // From here on everything launched before this kernel is complete: a kernel launched behind
+      // it WITH the programmatic attribute (cplxk_kl_guard: it reads the parameters and the
+      // pre-pass's KL sum, nothing of this kernel) may run under the mainloop.  Ordinary launches
+      // still wait for this grid to finish.
+      ptx::grid_dep_launch();
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         int tile_m, tile_n;
         decode_tile(t, tile_m, tile_n);

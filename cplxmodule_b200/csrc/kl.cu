@@ -326,16 +326,31 @@ extern "C" int cplxk_kl_guard(const void* w_re, const void* w_im, const void* lo
   auto fr = static_cast<const unsigned long long*>(fp_ref);
   int64_t want = (N + kGuardThreads - 1) / kGuardThreads;
   const int grid = static_cast<int>(want < 1 ? 1 : (want > 1024 ? 1024 : want));
-  if (dtype == CPLXK_F32)
-    kl_guard_kernel<float><<<grid, kGuardThreads, 0, st>>>(
-        static_cast<const float*>(w_re), static_cast<const float*>(w_im), static_cast<const float*>(log_sigma2),
-        N, K, ws, fo, fr, fused_sum, out_sum, stale_flag);
-  else if (dtype == CPLXK_BF16)
-    kl_guard_kernel<__nv_bfloat16><<<grid, kGuardThreads, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(w_re), static_cast<const __nv_bfloat16*>(w_im),
-        static_cast<const __nv_bfloat16*>(log_sigma2), N, K, ws, fo, fr, fused_sum, out_sum, stale_flag);
-  else
+  // Launched as a programmatic dependent: behind the persistent forward GEMM (which triggers
+  // its dependents once the pre-pass in front of it is complete) the check runs under the GEMM's
+  // mainloop instead of behind its last tile; behind any other kernel it starts when that kernel
+  // has finished, like an ordinary launch.  It never calls griddepcontrol.wait: nothing it reads
+  // is written by the kernel right before it.
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid)), cfg.blockDim = dim3(kGuardThreads);
+  cfg.dynamicSmemBytes = 0, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = knobs().pdl ? 1 : 0;
+  if (dtype == CPLXK_F32) {
+    CPLXK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kl_guard_kernel<float>, static_cast<const float*>(w_re),
+                                      static_cast<const float*>(w_im), static_cast<const float*>(log_sigma2), N,
+                                      K, ws, fo, fr, fused_sum, out_sum, stale_flag));
+  } else if (dtype == CPLXK_BF16) {
+    CPLXK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kl_guard_kernel<__nv_bfloat16>,
+                                      static_cast<const __nv_bfloat16*>(w_re),
+                                      static_cast<const __nv_bfloat16*>(w_im),
+                                      static_cast<const __nv_bfloat16*>(log_sigma2), N, K, ws, fo, fr, fused_sum,
+                                      out_sum, stale_flag));
+  } else {
     return CPLXK_ERR_BADARG;
+  }
   CPLXK_CUDA_TRY(cudaGetLastError());
   return CPLXK_OK;
 }
