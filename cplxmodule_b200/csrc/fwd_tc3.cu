@@ -339,8 +339,16 @@ fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
 
 // ------------------------------------------------------------------ fp32 -> fp16 operand pre-pass
 // One block per row of x or of W (interleaved); the row conversion itself is prep_row.cuh.
+// resident blocks per SM / 8-element groups a thread keeps in registers between the two passes
+// (side builds for A/B runs: -DCPLXK_PREP_BLOCKS=.. -DCPLXK_PREP_CACHE=..)
+#ifndef CPLXK_PREP_BLOCKS
+#define CPLXK_PREP_BLOCKS 4
+#endif
+#ifndef CPLXK_PREP_CACHE
+#define CPLXK_PREP_CACHE 2
+#endif
 template <bool kCplx, bool kMask>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, CPLXK_PREP_BLOCKS)
 vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im, int64_t M_,
                       const float* __restrict__ w_re, const float* __restrict__ w_im,
                       const float* __restrict__ ls2, const float* __restrict__ w_mask, int64_t N_,
@@ -393,7 +401,7 @@ vd_prepare_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ 
       row_of(g + gridDim.x, nx, nr);
       prep_prefetch_row<kCplx, 256>(a, nx, nr, tid);
     }
-    kl_acc += prep_convert_row<kCplx, 256, 2, kMask>(a, is_x, r, tid, red, sync, fp_acc);
+    kl_acc += prep_convert_row<kCplx, 256, CPLXK_PREP_CACHE, kMask>(a, is_x, r, tid, red, sync, fp_acc);
   }
   if (a.kl_kind >= 0) {
     __syncthreads();
@@ -482,7 +490,7 @@ int vd_prepare_f16_launch(bool cplx, const PrepArgs& a, const KlFuse& kl, cudaSt
   int sms = 148;
   int rc0 = current_device_sm_count(&sms);
   if (rc0) return rc0;
-  int64_t cap = static_cast<int64_t>(sms) * 8 - 1;                               // odd (see the kernel)
+  int64_t cap = static_cast<int64_t>(sms) * (2 * CPLXK_PREP_BLOCKS) - 1;         // odd (see the kernel)
   if (cap > kKlMaxBlocks) cap = kKlMaxBlocks - 1 + (kKlMaxBlocks & 1);           // <= kKlMaxBlocks partials, odd
   const int grid = static_cast<int>(rows > cap ? cap : (rows < 1 ? 1 : rows));
   auto kws = static_cast<KlWorkspace*>(kl.ws);
