@@ -803,7 +803,9 @@ def run_ours(args, rank, local_rank, world):
                     "frac": e2e_value / copy_value},
                 "note": "pinned host x -> device, forward+KL, y and KL -> pinned host; copies "
                         "double-buffered on side streams, all inside the timed region; " + placement},
-        "gpu_launches": (2 if fused or world > 1 else 3) * args.steps,
+        # our kernels per step: operand pre-pass (+ KL sum + parameter fingerprint), persistent GEMM,
+        # KL guard -- or, bf16 planes: |x|^2 / exp pre-pass, GEMM, kl_kernel
+        "gpu_launches": 3 * args.steps,
         "parity": res["parity"],
         "roofline": {
             "kernel": "fwd_tc3_kernel (persistent CTA-pair: complex mean GEMM + variance GEMM + Philox "

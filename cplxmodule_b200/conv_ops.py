@@ -259,6 +259,8 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
     fmt = torch.channels_last if cl else torch.contiguous_format
     y_re = torch.empty((B, O, Ho, Wo), dtype=dt, device=dev, memory_format=fmt)
     y_im = torch.empty_like(y_re) if cplx else None
+    if y_re.numel() == 0:      # empty batch / no output channels: empty outputs, as F.conv2d gives
+        return y_re, y_im, {"philox": (0, 0, 0), "eps_re": None, "eps_im": None}
     er = ei = None
     seed = offset = threads = 0
     gen = None

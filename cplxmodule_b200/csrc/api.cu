@@ -130,7 +130,9 @@ static int forward_common(bool vd, const void* x_re, const void* x_im, const voi
   // return; otherwise the caller must have passed already-masked weights
   if (mask_done) *mask_done = 0;
   if (kl_done) *kl_done = 0;
-  if (!x_re || !w_re || !y_re || M < 0 || N < 0 || K < 0) return CPLXK_ERR_BADARG;
+  if (M < 0 || N < 0 || K < 0) return CPLXK_ERR_BADARG;
+  if (M == 0 || N == 0) return CPLXK_OK;     // empty batch / layer: nothing to write (pointers may be null)
+  if (!x_re || !w_re || !y_re) return CPLXK_ERR_BADARG;
   const bool cplx = (x_im != nullptr);
   if (cplx != (w_im != nullptr) || cplx != (y_im != nullptr)) return CPLXK_ERR_BADARG;
   if ((b_re != nullptr) && cplx && !b_im) return CPLXK_ERR_BADARG;

@@ -212,10 +212,11 @@ extern "C" int cplxk_conv2d_fwd_g(const void* x_re, const void* x_im, const void
                                   int64_t stride_w, int64_t pad_h, int64_t pad_w, int64_t dil_h,
                                   int64_t dil_w, int64_t groups, int dtype, int math, int channels_last,
                                   void* workspace, size_t workspace_bytes, void* stream) {
-  if (!x_re || !w_re || !y_re) return CPLXK_ERR_BADARG;
   if (B < 0 || C < 1 || H < 1 || W < 1 || O < 0 || kh < 1 || kw < 1 || stride_h < 1 ||
       stride_w < 1 || pad_h < 0 || pad_w < 0 || dil_h < 1 || dil_w < 1)
     return CPLXK_ERR_BADARG;
+  if (B == 0 || O == 0) return CPLXK_OK;     // empty batch / layer (pointers may be null)
+  if (!x_re || !w_re || !y_re) return CPLXK_ERR_BADARG;
   if (groups < 1 || groups > 0x7fffffff || C % groups || O % groups) return CPLXK_ERR_BADARG;
   const bool cplx = x_im != nullptr;
   if (cplx != (w_im != nullptr) || cplx != (y_im != nullptr)) return CPLXK_ERR_BADARG;

@@ -97,7 +97,19 @@ def get_math_mode():
 
 
 def _flat2d(t, K):
-    return None if t is None else nv.plane(t.reshape(-1, K))
+    """[..., K] -> dense [M, K]; M is spelled out so that empty batches reshape too"""
+    if t is None:
+        return None
+    rows = 1
+    for d in t.shape[:-1]:
+        rows *= int(d)
+    return nv.plane(t.reshape(rows, K))
+
+
+def _check_features(x, w):
+    if x.shape[-1] != w.shape[-1]:
+        raise RuntimeError(
+            f"size mismatch: input has {x.shape[-1]} features, weight is {tuple(w.shape)}")
 
 
 def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im, noise,
@@ -125,6 +137,13 @@ def _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps_re, eps_im,
     y_re = torch.empty((M, N), dtype=dt, device=dev)
     y_im = torch.empty((M, N), dtype=dt, device=dev) if cplx else None
     aux = {}
+    if M == 0 or N == 0:
+        # empty batch / layer: empty outputs, as F.linear gives; nothing is drawn (torch's normal_
+        # does not advance its generator for zero elements) and no KL by-product is produced
+        if log_sigma2 is not None:
+            aux = {"s2": torch.empty((M, N), dtype=dt, device=dev) if want_s2 else None,
+                   "philox": (0, 0, 0), "eps": (None, None), "x": (xr, xi)}
+        return y_re.reshape(*lead, N), (y_im.reshape(*lead, N) if cplx else None), aux
     lib = nv.lib()
     math = _MATH[_state["math"]] if math is None else math
     with nv.device_guard(dev):
@@ -279,12 +298,12 @@ def _gemm(a_re, a_im, p_re, p_im):
 
 
 def _grad2d(g, like_lead, N, dt, dev):
+    M = 1
+    for s_ in like_lead:
+        M *= s_
     if g is None:
-        M = 1
-        for s_ in like_lead:
-            M *= s_
         return torch.zeros((M, N), dtype=dt, device=dev)
-    return nv.plane(g.reshape(-1, N).to(dt))
+    return nv.plane(g.reshape(M, N).to(dt))
 
 
 def _linear_backward(ctx, g_re, g_im, need_x, need_w, need_b):
@@ -471,12 +490,14 @@ def _wants_grad(*tensors):
 
 def cplx_linear(x_re, x_im, w_re, w_im, b_re=None, b_im=None):
     """y = x W^T + b on split planes (reference: cplx.linear_naive, cplx.py:634-648)."""
+    _check_features(x_re, w_re)
     if not _wants_grad(x_re, x_im, w_re, w_im, b_re, b_im):
         return _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, None, None, None, None)[:2]
     return _CplxLinearFn.apply(x_re, x_im, w_re, w_im, b_re, b_im)
 
 
 def real_linear(x, w, b=None):
+    _check_features(x, w)
     if not _wants_grad(x, w, b):
         return _forward_raw(x, None, w, None, b, None, None, None, None, None)[0]
     return _RealLinearFn.apply(x, w, b)
@@ -623,6 +644,7 @@ def cplx_linear_vd(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps=None, kl_
     """Fused local-reparameterisation forward (reference: CplxLinearGaussian.forward,
     nn/relevance/complex/base.py:43-56). ``eps=(eps_re, eps_im)`` injects the noise
     (each ~ N(0, 1/2)); ``None`` draws it inside the kernel.  ``kl_req``: see ``_forward_raw``."""
+    _check_features(x_re, w_re)
     er, ei, mode = _noise_args(eps)
     if not _wants_grad(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, er, ei):
         return _forward_raw(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, er, ei, mode,
@@ -633,6 +655,7 @@ def cplx_linear_vd(x_re, x_im, w_re, w_im, b_re, b_im, log_sigma2, eps=None, kl_
 
 def real_linear_vd(x, w, b, log_sigma2, eps=None, kl_req=None):
     """Reference: LinearGaussian.forward, nn/relevance/real/base.py:43-49."""
+    _check_features(x, w)
     er, _, mode = _noise_args((eps, None) if eps is not None else None)
     if not _wants_grad(x, w, b, log_sigma2, er):
         return _forward_raw(x, None, w, None, b, None, log_sigma2, er, None, mode, kl_req=kl_req)[0]
