@@ -10,7 +10,9 @@ A "step" = one training-mode forward of the layer on one batch (fused local
 reparameterisation, in-kernel Philox noise) + sum(penalties(model)).
 
 Legs of the default run (rank 0 prints them all in the one line):
-  value / roofline   device-timed steps, inputs resident in HBM
+  value / roofline   device-timed steps, inputs resident in HBM (W warm-up + K timed steps: the
+                     burst regime, compared with the burst cuBLAS peak); roofline.sustained = the
+                     same K steps after > 0.4 s under load, against the sustained cuBLAS peak
   e2e                the same step from pinned host buffers and back, every step, + the box's
                      measured duplex copy rate for the same bytes (e2e.roofline)
   parity             64 sampled rows of the timed layer's output + its KL against the oracle
@@ -531,11 +533,23 @@ def run_workload(args, wl, h, rank, local_rank, world, placement, full):
         if rank == 0 and full:
             sampler.start()
             time.sleep(0.3)
-        # the timed loop is the bare step: an event record between two launches would break their
-        # programmatic-dependent-launch adjacency (pre-pass -> GEMM -> KL guard); the per-call
-        # breakdown (forward / penalties) comes from a second, instrumented loop further down
-        ms = h.timed(step, args.steps)
+        # Every 4th step of the timed loop carries the event pairs of the per-call breakdown
+        # (forward / penalties): an event record between two launches breaks their programmatic-
+        # dependent-launch adjacency (GEMM -> KL guard), so the other steps run bare.
+        counter = {"i": 0}
+
+        def timed_step():
+            counter["i"] += 1
+            step(record=(counter["i"] & 3) == 0)
+
+        ms = h.timed(timed_step, args.steps)
         res["ms"] = ms
+        if not fwd_ms:                        # fewer than 4 timed steps: one instrumented step behind them
+            step(record=True)
+            torch.cuda.synchronize(dev)
+        res["f_ms"] = statistics.mean(a.elapsed_time(b) for a, b in fwd_ms)
+        res["k_ms"] = statistics.mean(a.elapsed_time(b) for a, b in kl_ms)
+        res["sustained_ms"] = None
         if full:
             # the timed loop may be shorter than nvidia-smi's sampling period: keep the identical
             # loop running (untimed) until ~0.4 s of load has been sampled (`ms` is the all-reduced
@@ -543,15 +557,16 @@ def run_workload(args, wl, h, rank, local_rank, world, placement, full):
             extra = int(max(0.0, 400.0 - ms) / max(ms / args.steps, 1e-3)) + 1
             for _ in range(min(extra, 5000)):
                 step()
+            # ... and the same K steps once more, now that the part has been under load for > 0.4 s
+            # (the 1 kW power cap has pulled the SM clock down by then): the SUSTAINED figure next
+            # to the contract's `value` (W warm-up steps, then K timed steps)
+            res["sustained_ms"] = h.timed(step, args.steps)
             torch.cuda.synchronize(dev)
             clocks = sampler.stop() if rank == 0 else None
             if clocks is not None:
-                clocks["window"] = "timed loop + identical untimed continuation, >= 0.4 s under load"
+                clocks["window"] = "timed loop + identical continuation (>= 0.4 s under load) + sustained loop"
             res["clocks"] = clocks
         res["kl_value"] = float(last["kl"].item())
-        h.timed(lambda: step(record=True), max(5, min(args.steps, 20)))     # breakdown only, not `value`
-        res["f_ms"] = statistics.mean(a.elapsed_time(b) for a, b in fwd_ms)
-        res["k_ms"] = statistics.mean(a.elapsed_time(b) for a, b in kl_ms)
 
         # ---- side measurements that explain the step (not part of `value`): the operand pre-pass
         # alone (cplxk_linear_vd_prepare: the same launch the forward starts with) and the
@@ -738,7 +753,8 @@ def run_ours(args, rank, local_rank, world):
     FLOPS = flops_per_step(B, D)
     achieved_tf = FLOPS / (gemm_ms / 1e3) / 1e12
     step_tf = FLOPS / (ms / args.steps / 1e3) / 1e12
-    peak_tf = peaks["bf16_tflops_sustained"]
+    peak_tf = peaks["bf16_tflops"]                 # burst: the regime of W warm-up + K timed steps
+    peak_sus = peaks["bf16_tflops_sustained"]
     fused = world == 1 and args.dtype == "f32"
     KL_BYTES = 4.0 * 3 * D * D
     if fused:
@@ -815,8 +831,18 @@ def run_ours(args, rank, local_rank, world):
             "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf,
             "step_achieved": step_tf, "step_frac": step_tf / peak_tf,
-            "peak_source": f"{peaks['source']} bf16 cuBLAS sustained (MEASURED_PEAKS.json); kind::f16 "
-                           "runs fp16 and bf16 operands at the same rate",
+            "peak_source": f"{peaks['source']} bf16 cuBLAS BURST peak (MEASURED_PEAKS.json: best of 10) -- the "
+                           "timed loop is W warm-up + K steps, i.e. tens of milliseconds, before the 1 kW "
+                           "power cap settles the clocks; `sustained` below is the same loop after > 0.4 s "
+                           "under load against the SUSTAINED cuBLAS peak; kind::f16 runs fp16 and bf16 "
+                           "operands at the same rate",
+            "frac_of_sustained_peak": achieved_tf / peak_sus,
+            "sustained": None if res.get("sustained_ms") is None else {
+                "ms_per_step": res["sustained_ms"] / args.steps,
+                "value": B * world * args.steps / (res["sustained_ms"] / 1e3), "unit": "samples/s",
+                "step_achieved": FLOPS / (res["sustained_ms"] / args.steps / 1e3) / 1e12,
+                "peak": peak_sus,
+                "step_frac": FLOPS / (res["sustained_ms"] / args.steps / 1e3) / 1e12 / peak_sus},
             "algorithmic_flops_per_launch": FLOPS, "ms_per_launch": gemm_ms,
             "forward_call_ms": f_ms,
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed
