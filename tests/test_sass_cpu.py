@@ -66,3 +66,19 @@ def test_cta_pair_kernels(sass, stem):
         assert ops["UTCHMMA.2CTA"] > 0, f"{name}: MMAs are not cta_group::2"
         # the two cluster-wide syncs (after barrier init, before TMEM dealloc) and nothing per tile
         assert ops["MEMBAR.ALL.GPU"] <= 2, f"{name}: GPU-scope membar inside the tile loop"
+
+
+def test_real_and_grouped_conv_variants_are_built(sass):
+    """conv_tc_kernel<T, VD, real> for both plane types, with and without the
+    variational part, complex and real planes -- eight tcgen05 kernels"""
+    names = kernels_of(sass, "conv_tc_kernel")
+    assert len(names) == 8, sorted(names)
+    # real-plane instantiations issue fewer MMAs per k-step than the complex ones (one A plane)
+    real = [v["UTCHMMA"] for k, v in names.items() if k.endswith("Lb1EEEv14CUtensorMap_stS2_S2_S2_S2_S2_NS_10ConvTcGeomENS_9ConvTcEpiE")
+            or "Lb1EEEv14CUtensorMap_stS1_" in k]
+    assert real, "no real-plane instantiation found"
+
+
+def test_guard_and_fingerprint_kernels_exist(sass):
+    assert any("kl_guard_kernel" in k for k in sass), "kl_guard_kernel missing"
+    assert any("vd_grad_s2_torch_kernel" in k for k in sass), "vd_grad_s2_torch_kernel missing"
