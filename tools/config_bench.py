@@ -41,6 +41,7 @@ def row(name, ms, flops, nbytes, note=""):
     r = dict(config=name, ms=round(ms, 4), algorithmic_gflop=round(flops / 1e9, 2),
              algorithmic_mb=round(nbytes / 1e6, 1), tflops=round(tf, 1), gbs=round(gbs, 1),
              frac_tensor=round(tf / PEAKS["bf16_tflops_sustained"], 4),
+             frac_tensor_burst=round(tf / PEAKS.get("bf16_tflops", PEAKS["bf16_tflops_sustained"]), 4),
              frac_hbm=round(gbs / PEAKS["hbm_gbs"], 4), note=note)
     print(json.dumps(r), flush=True)
     return r
@@ -117,7 +118,7 @@ def main():
         out.append(row("5 CplxLinearARD KL row shard (1024 of 8192 rows)", ms_k, 0,
                        4 * 3 * 1024 * 8192, "all-reduce of the scalar not included"))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs_r1.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs_r2.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
