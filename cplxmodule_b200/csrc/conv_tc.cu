@@ -99,7 +99,7 @@ conv_nhwc_bf16_v8_kernel(const __nv_bfloat16* __restrict__ x_re, const __nv_bflo
     if (c < C && w < W) {
       const int64_t off = ((b * C + c) * H + h) * W + w;
       vr = __ldg(reinterpret_cast<const uint4*>(x_re + off));
-      vi = __ldg(reinterpret_cast<const uint4*>(x_im + off));
+      if (x_im) vi = __ldg(reinterpret_cast<const uint4*>(x_im + off));     // real planes: x_im == nullptr
     }
     const __nv_bfloat16* pr = reinterpret_cast<const __nv_bfloat16*>(&vr);
     const __nv_bfloat16* pi = reinterpret_cast<const __nv_bfloat16*>(&vi);
@@ -118,7 +118,49 @@ conv_nhwc_bf16_v8_kernel(const __nv_bfloat16* __restrict__ x_re, const __nv_bflo
       r2.x = s_re[2 * tx][wl], r2.y = s_re[2 * tx + 1][wl];
       i2.x = s_im[2 * tx][wl], i2.y = s_im[2 * tx + 1][wl];
       *reinterpret_cast<__nv_bfloat162*>(o_re + off) = r2;
-      *reinterpret_cast<__nv_bfloat162*>(o_im + off) = i2;
+      if (o_im) *reinterpret_cast<__nv_bfloat162*>(o_im + off) = i2;
+    }
+  }
+}
+
+// fp32 NCHW -> channels-last fp32 (tf32-rounded MMA operands) with 16-byte loads: 64 channels x
+// 64 pixels per block, float2 stores (256-byte channel rows per warp).  x_im / o_im nullable
+// (real planes).  W % 4 == 0, 16-byte aligned planes, Cp % 2 == 0.
+__global__ void __launch_bounds__(256)
+conv_nhwc_f32_v4_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im,
+                        float* __restrict__ o_re, float* __restrict__ o_im, int C, int Cp, int H, int W) {
+  __shared__ float s_re[64][65], s_im[64][65];
+  const int tid = threadIdx.x;
+  const int w0 = blockIdx.z * 64, c0 = blockIdx.y * 64;
+  const int64_t bh = blockIdx.x;
+  const int64_t b = bh / H, h = bh - b * H;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + 256 * i;
+    const int cl = idx >> 4, q = idx & 15;
+    const int c = c0 + cl, w = w0 + 4 * q;
+    float4 vr = make_float4(0.f, 0.f, 0.f, 0.f), vi = vr;
+    if (c < C && w < W) {     // W % 4 == 0: a float4 never straddles the row end
+      const int64_t off = ((b * C + c) * H + h) * W + w;
+      vr = __ldg(reinterpret_cast<const float4*>(x_re + off));
+      if (x_im) vi = __ldg(reinterpret_cast<const float4*>(x_im + off));
+    }
+    s_re[cl][4 * q] = vr.x, s_re[cl][4 * q + 1] = vr.y, s_re[cl][4 * q + 2] = vr.z, s_re[cl][4 * q + 3] = vr.w;
+    s_im[cl][4 * q] = vi.x, s_im[cl][4 * q + 1] = vi.y, s_im[cl][4 * q + 2] = vi.z, s_im[cl][4 * q + 3] = vi.w;
+  }
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;
+  const int c = c0 + 2 * tx;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int wl = ty + 8 * i, w = w0 + wl;
+    if (w < W && c < Cp) {
+      const int64_t off = ((b * H + h) * W + w) * Cp + c;
+      *reinterpret_cast<float2*>(o_re + off) =
+          make_float2(round_mma_operand<float>(s_re[2 * tx][wl]), round_mma_operand<float>(s_re[2 * tx + 1][wl]));
+      if (o_im)
+        *reinterpret_cast<float2*>(o_im + off) =
+            make_float2(round_mma_operand<float>(s_im[2 * tx][wl]), round_mma_operand<float>(s_im[2 * tx + 1][wl]));
     }
   }
 }
@@ -443,7 +485,7 @@ struct ConvCfg {
   static constexpr int OFF_UV = ((kReal ? 1 : 2) + (kVD ? 1 : 0)) * A_TILE;   // 128 rows = 16 KB
   static constexpr int OFF_E = OFF_UV + A_TILE;            // BNO rows
   static constexpr int STAGE_BYTES = OFF_E + (kVD ? BNO * 128 : 0);
-  static constexpr int STAGES = (kVD || kReal) ? 3 : 2;    // VD: 1 CTA/SM, plain: 2 CTAs/SM
+  static constexpr int STAGES = kVD ? 3 : 2;               // VD: 1 CTA/SM, plain: 2 (complex) / 3 (real) CTAs/SM
   // complex: D1 128 | D2 128 | (s2 64);  real: D1 128 | (s2 128)
   static constexpr int TMEM_COLS = kReal ? (kVD ? 256 : 128) : (kVD ? 512 : 256);
   static constexpr int OFF_S2 = kReal ? 128 : 256;
@@ -456,7 +498,7 @@ struct ConvCfg {
 };
 
 template <typename T, bool kVD, bool kReal = false>
-__global__ void __launch_bounds__((kVD ? 576 : 192), (kVD ? 1 : 2))
+__global__ void __launch_bounds__((kVD ? 576 : 192), (kVD ? 1 : (kReal ? 3 : 2)))
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__ CUtensorMap tm_xi,
                const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_u,
                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_e,
@@ -691,6 +733,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xr, const __grid_constant_
     ptx::mbar_wait(bar_accum, 0);
     ptx::tcgen05_fence_after();
     const int64_t cl_off = ((static_cast<int64_t>(b) * g.Ho + oh) * g.Wo + ow) * g.O;
+    if constexpr (kReal && !kVD) {
+      // plain real convolution: 128 channels per thread in 16-column chunks, the loads of the next
+      // chunk in flight while this one is biased and stored (one-tile-per-CTA kernel: the drain
+      // is on the critical path of every CTA)
+      uint32_t d[2][16];
+      ptx::tmem_ld_32x32b_x16(lane_base, d[0]);
+#pragma unroll
+      for (int q = 0; q < NCH / 16; ++q) {
+        const int cur = q & 1;
+        ptx::tmem_ld_wait();
+        if (q + 1 < NCH / 16) ptx::tmem_ld_32x32b_x16(lane_base + 16 * (q + 1), d[cur ^ 1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int o0 = obase + n0 + q * 16 + h * 8;
+          float re8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float re = __uint_as_float(d[cur][h * 8 + j]);
+            if (ep.b_re && o0 + j < o_end) re += Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_re) + o0 + j));
+            re8[j] = re;
+          }
+          if (pix_ok && o0 < o_end)
+            conv_store8<T>(static_cast<T*>(ep.y_re), g, ep.nhwc != 0, pix_off, hw, cl_off, o0, re8, o_end);
+        }
+      }
+    } else
 #pragma unroll
     for (int cc = 0; cc < NCH / 8; ++cc) {
       const int c = cbase / 8 + cc;                             // 8-channel chunk inside the tile
@@ -1494,9 +1562,34 @@ static int launch_conv_rg(const void* x_re, const void* x_im, const void* w_re, 
   dim3 tg(static_cast<unsigned>(g.B * g.H), static_cast<unsigned>((g.Cp + 31) / 32),
           static_cast<unsigned>((g.W + 31) / 32));
   if (tg.y > 65535u || tg.z > 65535u || g.B * g.H > 0x7fffffff) return CPLXK_ERR_UNSUPPORTED;
-  conv_nhwc_kernel<T, kVD><<<tg, 256, 0, st>>>(static_cast<const T*>(x_re), static_cast<const T*>(x_im),
-                                               a_re, a_im, a_q, static_cast<int>(g.C), g.Cp,
-                                               static_cast<int>(g.H), static_cast<int>(g.W));
+  bool done = false;
+  if constexpr (std::is_same<T, __nv_bfloat16>::value && !kVD) {
+    // 16-byte loads, 128-byte channel rows (the complex layers' fast transposer; x_im may be null)
+    if (g.W % 8 == 0 && g.Cp % 2 == 0 && (reinterpret_cast<uintptr_t>(x_re) & 15u) == 0 &&
+        (!x_im || (reinterpret_cast<uintptr_t>(x_im) & 15u) == 0)) {
+      dim3 t8(static_cast<unsigned>(g.B * g.H), static_cast<unsigned>((g.Cp + 63) / 64),
+              static_cast<unsigned>((g.W + 63) / 64));
+      conv_nhwc_bf16_v8_kernel<<<t8, 256, 0, st>>>(static_cast<const T*>(x_re), static_cast<const T*>(x_im),
+                                                   a_re, a_im, static_cast<int>(g.C), g.Cp,
+                                                   static_cast<int>(g.H), static_cast<int>(g.W));
+      done = true;
+    }
+  }
+  if constexpr (std::is_same<T, float>::value && !kVD) {
+    if (g.W % 4 == 0 && g.Cp % 2 == 0 && (reinterpret_cast<uintptr_t>(x_re) & 15u) == 0 &&
+        (!x_im || (reinterpret_cast<uintptr_t>(x_im) & 15u) == 0)) {
+      dim3 t4(static_cast<unsigned>(g.B * g.H), static_cast<unsigned>((g.Cp + 63) / 64),
+              static_cast<unsigned>((g.W + 63) / 64));
+      conv_nhwc_f32_v4_kernel<<<t4, 256, 0, st>>>(static_cast<const float*>(x_re), static_cast<const float*>(x_im),
+                                                  a_re, a_im, static_cast<int>(g.C), g.Cp,
+                                                  static_cast<int>(g.H), static_cast<int>(g.W));
+      done = true;
+    }
+  }
+  if (!done)
+    conv_nhwc_kernel<T, kVD><<<tg, 256, 0, st>>>(static_cast<const T*>(x_re), static_cast<const T*>(x_im),
+                                                 a_re, a_im, a_q, static_cast<int>(g.C), g.Cp,
+                                                 static_cast<int>(g.H), static_cast<int>(g.W));
   CPLXK_CUDA_TRY(cudaGetLastError());
   const int64_t wtotal = static_cast<int64_t>(g.kh) * g.kw * g.Op * g.Cgp;
   conv_wprep_kernel<T, kVD><<<static_cast<unsigned>(wtotal / 256 + 1 > 1184 ? 1184 : wtotal / 256 + 1), 256, 0, st>>>(
