@@ -1,0 +1,22 @@
+import sys, json, torch
+sys.path.insert(0, '/root/repo')
+from cplxmodule_b200 import cplx, ops, conv_ops
+from cplxmodule_b200.nn.relevance import CplxConv2dVD
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+torch.manual_seed(0)
+with torch.no_grad():
+    conv = CplxConv2dVD(64, 64, 3).cuda().train()
+    z = cplx.randn(256, 64, 128, 128, device="cuda")
+    eps = cplx.randn(256, 64, 126, 126, device="cuda")
+    for dt, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+        c, zz, ee = conv.to(dt), z.to(dt), eps.to(dt)
+        print(json.dumps({"dtype": tag, "fused_torch_ms": round(timeit(lambda: c(zz)), 3),
+                          "inject_ms": round(timeit(lambda: c(zz, eps=ee)), 3),
+                          "draw_ms": round(timeit(lambda: conv_ops._draw_noise(True, (256, 64, 126, 126), zz.real.device, dt)), 3)}))
