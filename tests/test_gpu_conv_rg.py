@@ -177,3 +177,40 @@ def test_simt_mode_still_loops_over_groups():
         assert rel_err(out, want) < 2e-5
     finally:
         ops.set_math_mode("auto")
+
+
+def test_grouped_conv1d_and_circular_padding(tensor_only):
+    """conv1d is the H == 1 case of the same launch; circular padding pads first (cplx.py:701-714,
+    784-786), then the grouped kernel runs on the padded planes"""
+    torch.manual_seed(9)
+    from cplxmodule_b200.nn import CplxConv1d
+    m = CplxConv1d(12, 8, 5, stride=2, padding=3, dilation=2, groups=4).to(DEV)
+    z = cplx.randn(3, 12, 50, device=DEV)
+    with torch.no_grad():
+        out = m(z)
+    conv = lambda a, w: F.conv1d(c64(a), c64(w), None, 2, 3, 2, 4)
+    re = conv(z.real, m.weight.real) - conv(z.imag, m.weight.imag) + c64(m.bias.real)[None, :, None]
+    im = conv(z.real, m.weight.imag) + conv(z.imag, m.weight.real) + c64(m.bias.imag)[None, :, None]
+    assert out.shape == re.shape
+    assert rel_err(out.real, re) < 1e-3 and rel_err(out.imag, im) < 1e-3
+    m2 = CplxConv2d(8, 8, 3, padding=2, padding_mode="circular", groups=2).to(DEV)
+    z2 = cplx.randn(2, 8, 9, 10, device=DEV)
+    with torch.no_grad():
+        out2 = m2(z2)
+    pad = lambda a: F.pad(c64(a), (1, 1, 1, 1), mode="circular")
+    want = orc.cplx_conv2d_grouped(pad(z2.real), pad(z2.imag), c64(m2.weight.real), c64(m2.weight.imag),
+                                   c64(m2.bias.real), c64(m2.bias.imag), 1, 0, 1, 2)
+    assert rel_err(out2.real, want[0]) < 1e-3 and rel_err(out2.imag, want[1]) < 1e-3
+
+
+def test_real_masked_conv_with_groups(tensor_only):
+    """Conv2dMasked (nn/masked/real.py) with groups: weight * mask on the grouped tcgen05 path"""
+    from cplxmodule_b200.nn import masked
+    torch.manual_seed(10)
+    conv = masked.Conv2dMasked(8, 12, 3, padding=1, groups=2).to(DEV)
+    conv.mask = (torch.rand_like(conv.weight) < 0.6).float()
+    x = torch.randn(2, 8, 11, 13, device=DEV)
+    with torch.no_grad():
+        out = conv(x)
+    want = F.conv2d(c64(x), c64(conv.weight) * c64(conv.mask), c64(conv.bias), 1, 1, 1, 2)
+    assert rel_err(out, want) < 1e-3
