@@ -30,7 +30,7 @@ EXPORTS = (
     "cplxk_transpose2d", "cplxk_eltwise", "cplxk_colsum", "cplxk_vd_grad_s2", "cplxk_vd_grad_input",
     "cplxk_mul_exp", "cplxk_kl_bwd",
     "cplxk_linear_masked_fwd", "cplxk_linear_masked_workspace_bytes", "cplxk_kl_mask",
-    "cplxk_outer_fwd", "cplxk_outer_bwd", "cplxk_kl_guard", "cplxk_linear_vd_fuses_kl",
+    "cplxk_outer_fwd", "cplxk_outer_bwd", "cplxk_kl_guard", "cplxk_linear_vd_fuses_kl", "cplxk_vd_combine",
 )
 
 _lock = threading.Lock()
@@ -77,6 +77,7 @@ def _declare(lib):
     lib.cplxk_eltwise.argtypes = [_int, _vp, _vp, _vp, _i64, _int, _vp]
     lib.cplxk_colsum.argtypes = [_vp, _vp, _i64, _i64, _int, _vp]
     lib.cplxk_vd_grad_s2.argtypes = [_vp] * 5 + [_int, _u64, _u64, _u32, _vp, _i64, _i64, _int, _vp]
+    lib.cplxk_vd_combine.argtypes = [_vp] * 5 + [_int, _u64, _u64, _u32, _i64, _int, _vp]
     lib.cplxk_vd_grad_input.argtypes = [_vp] * 5 + [_i64, _int, _vp]
     lib.cplxk_mul_exp.argtypes = [_vp, _vp, _vp, _i64, _int, _int, _vp]
     lib.cplxk_kl_bwd.argtypes = [_int, _vp, _vp, _vp, _i64, _int, _vp, _int, _int, ctypes.c_double,

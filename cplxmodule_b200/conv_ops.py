@@ -272,6 +272,22 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
         else:
             numel = (2 if cplx else 1) * y_re.numel()
             gen, seed, offset, threads, inc = nv.philox_plan(dev, max(numel, 1), noise == nv.NOISE_PHILOX_TORCH)
+    if ls2 is not None and math != nv.MATH_SIMT and not cl and ops.conv_vd_composed(cplx, dt):
+        # mean conv + variance conv on the fast plain kernels, then ONE in-place launch for the
+        # noise: y += eps sqrt(max(s2, 1e-8))  (ops.set_conv_vd_mode)
+        y_re = y_im = None
+        y_re, y_im, _ = _conv2d_raw(xr, xi, wr, wi, br, bi, None, None, None, nv.NOISE_INJECT, geom, groups)
+        E = ops._eltwise(ops.TR_EXP, l2)
+        q = ops._eltwise(ops.TR_ABS2, xr, xi) if cplx else ops._eltwise(ops.TR_SQR, xr)
+        s2, _, _ = _conv2d_raw(q, None, E, None, None, None, None, None, None, nv.NOISE_INJECT, geom, groups)
+        del q
+        with nv.device_guard(dev):
+            nv.check(nv.lib().cplxk_vd_combine(
+                nv.ptr(y_re), nv.ptr(y_im), nv.ptr(s2), nv.ptr(er), nv.ptr(ei), mode, seed, offset,
+                threads, y_re.numel(), code, nv.stream_ptr(dev)))
+        if mode != nv.NOISE_INJECT:
+            nv.philox_advance(gen, offset, inc)
+        return y_re, y_im, {"philox": (seed, offset, threads), "eps_re": er, "eps_im": ei}
     ws, ws_bytes = None, 0
     if math != nv.MATH_SIMT:
         # complex AND real planes run the tcgen05 implicit GEMM (real: one A tile, one accumulator)

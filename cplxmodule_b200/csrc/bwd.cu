@@ -204,6 +204,96 @@ vd_grad_s2_torch_kernel(const T* __restrict__ g_re, const T* __restrict__ g_im, 
   }
 }
 
+// ---- y += eps * sqrt(max(s2, 1e-8)) in place (variational conv forward built from the mean conv
+// and the variance conv of the fast kernels; complex/base.py:120-135, real/base.py:149-163).
+// Torch-exact noise is generated BY PHILOX CALL as in vd_grad_s2_torch_kernel: a thread owns the
+// four elements one call serves (T apart), the imaginary-plane noise of those elements comes from
+// at most two more calls, every Box-Muller evaluation yields two used normals.
+template <typename T, bool kCplx>
+__global__ void __launch_bounds__(256)
+vd_combine_torch_kernel(T* __restrict__ y_re, T* __restrict__ y_im, const T* __restrict__ s2, int64_t MN,
+                        uint32_t r0, uint64_t q0, uint64_t calls, NoiseParams np) {
+  const uint32_t Tn = np.threads;
+  const PhiloxKey key{np.seed_lo, np.seed_hi};
+  const uint64_t total = static_cast<uint64_t>(Tn) * calls;
+  for (uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t c = t / Tn;
+    const uint32_t idx = static_cast<uint32_t>(t - c * Tn);
+    const uint64_t e0 = idx + static_cast<uint64_t>(Tn) * 4u * c;
+    if (e0 >= static_cast<uint64_t>(MN)) continue;
+    float er[4], ei[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      const uint64_t ctr = np.ctr_base + c;
+      const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), idx, 0u), key);
+      const float2 a = _curand_box_muller(r.x, r.y), b = _curand_box_muller(r.z, r.w);
+      er[0] = a.x * np.scale, er[1] = a.y * np.scale, er[2] = b.x * np.scale, er[3] = b.y * np.scale;
+    }
+    if constexpr (kCplx) {
+      uint32_t idx2 = idx + r0;
+      uint64_t sl0 = 4u * c + q0;
+      if (idx2 >= Tn) idx2 -= Tn, ++sl0;
+      const uint32_t c0 = static_cast<uint32_t>(sl0) & 3u;
+      const uint64_t ctr = np.ctr_base + (sl0 >> 2);
+      float n8[8];
+      {
+        const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), idx2, 0u), key);
+        const float2 a = _curand_box_muller(r.x, r.y), b = _curand_box_muller(r.z, r.w);
+        n8[0] = a.x, n8[1] = a.y, n8[2] = b.x, n8[3] = b.y;
+      }
+      n8[4] = n8[5] = n8[6] = n8[7] = 0.f;
+      if (c0 != 0u) {
+        const uint64_t ctr1 = ctr + 1;
+        const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(ctr1), static_cast<uint32_t>(ctr1 >> 32), idx2, 0u), key);
+        const float2 a = _curand_box_muller(r.x, r.y);
+        n8[4] = a.x, n8[5] = a.y;
+        if (c0 == 3u) n8[6] = _curand_box_muller(r.z, r.w).x;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) v = (static_cast<uint32_t>(j) == c0 + k) ? n8[j] : v;
+        ei[k] = v * np.scale;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t e = e0 + static_cast<uint64_t>(Tn) * k;
+      if (e < static_cast<uint64_t>(MN)) {
+        const float sd = sd_of(Elem<T>::to_f(s2[e]));
+        y_re[e] = Elem<T>::from_f(fmaf(er[k], sd, Elem<T>::to_f(y_re[e])));
+        if constexpr (kCplx) y_im[e] = Elem<T>::from_f(fmaf(ei[k], sd, Elem<T>::to_f(y_im[e])));
+      }
+    }
+  }
+}
+
+// injected noise / the private `fast` layout of the conv kernels (one element per thread)
+template <typename T, bool kCplx>
+__global__ void __launch_bounds__(256)
+vd_combine_kernel(T* __restrict__ y_re, T* __restrict__ y_im, const T* __restrict__ s2,
+                  const T* __restrict__ eps_re, const T* __restrict__ eps_im, int64_t MN, NoiseParams np) {
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < MN;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float er, ei = 0.f;
+    if (np.mode == CPLXK_NOISE_INJECT) {
+      er = Elem<T>::to_f(eps_re[e]);
+      if constexpr (kCplx) ei = Elem<T>::to_f(eps_im[e]);
+    } else if constexpr (kCplx) {
+      const float2 z = philox_fast_pair(static_cast<uint64_t>(e), np);
+      er = z.x * np.scale, ei = z.y * np.scale;
+    } else {
+      const float4 a = philox_fast_normal4(static_cast<uint64_t>(e) >> 2, 0u, np);
+      const int comp = static_cast<int>(e & 3);
+      er = (comp == 0 ? a.x : comp == 1 ? a.y : comp == 2 ? a.z : a.w) * np.scale;
+    }
+    const float sd = sd_of(Elem<T>::to_f(s2[e]));
+    y_re[e] = Elem<T>::from_f(fmaf(er, sd, Elem<T>::to_f(y_re[e])));
+    if constexpr (kCplx) y_im[e] = Elem<T>::from_f(fmaf(ei, sd, Elem<T>::to_f(y_im[e])));
+  }
+}
+
 // dx_re += 2 x_re dq ; dx_im += 2 x_im dq
 template <typename T, bool kCplx>
 __global__ void __launch_bounds__(256)
@@ -492,6 +582,42 @@ extern "C" int cplxk_kl_bwd(int kind, const void* w_re, const void* w_im, const 
     }
   })
 #undef CPLXK_KLB
+  CPLXK_CUDA_TRY(cudaGetLastError());
+  return CPLXK_OK;
+}
+
+extern "C" int cplxk_vd_combine(void* y_re, void* y_im, const void* s2, const void* eps_re,
+                                const void* eps_im, int noise, uint64_t seed, uint64_t offset,
+                                uint32_t philox_threads, int64_t numel, int dtype, void* stream) {
+  if (!y_re || !s2 || numel < 0) return CPLXK_ERR_BADARG;
+  if (noise < CPLXK_NOISE_INJECT || noise > CPLXK_NOISE_PHILOX_FAST) return CPLXK_ERR_BADARG;
+  const bool cplx = y_im != nullptr;
+  if (noise == CPLXK_NOISE_INJECT && (!eps_re || (cplx && !eps_im))) return CPLXK_ERR_BADARG;
+  if (noise == CPLXK_NOISE_PHILOX_TORCH && (philox_threads == 0 || (offset & 3u))) return CPLXK_ERR_BADARG;
+  if (numel == 0) return CPLXK_OK;
+  NoiseParams np;
+  np.mode = noise, np.seed_lo = static_cast<uint32_t>(seed), np.seed_hi = static_cast<uint32_t>(seed >> 32);
+  np.ctr_base = offset >> 2, np.threads = philox_threads ? philox_threads : 1u;
+  np.scale = cplx ? (1.0f / static_cast<float>(1.4142135623730951)) : 1.0f;
+  auto st = static_cast<cudaStream_t>(stream);
+  CPLXK_BY_DTYPE(dtype, {
+    auto yr = static_cast<T*>(y_re); auto yi = static_cast<T*>(y_im);
+    auto v = static_cast<const T*>(s2);
+    if (noise == CPLXK_NOISE_PHILOX_TORCH) {
+      const uint64_t Tn = np.threads;
+      const uint64_t calls = (static_cast<uint64_t>(numel) + 4 * Tn - 1) / (4 * Tn);
+      const uint32_t r0 = static_cast<uint32_t>(static_cast<uint64_t>(numel) % Tn);
+      const uint64_t q0 = static_cast<uint64_t>(numel) / Tn;
+      const int grid = ew_grid(static_cast<int64_t>(Tn * calls));
+      if (cplx) vd_combine_torch_kernel<T, true><<<grid, 256, 0, st>>>(yr, yi, v, numel, r0, q0, calls, np);
+      else vd_combine_torch_kernel<T, false><<<grid, 256, 0, st>>>(yr, yi, v, numel, r0, q0, calls, np);
+    } else {
+      auto e1 = static_cast<const T*>(eps_re); auto e2 = static_cast<const T*>(eps_im);
+      const int grid = ew_grid(numel);
+      if (cplx) vd_combine_kernel<T, true><<<grid, 256, 0, st>>>(yr, yi, v, e1, e2, numel, np);
+      else vd_combine_kernel<T, false><<<grid, 256, 0, st>>>(yr, yi, v, e1, e2, numel, np);
+    }
+  })
   CPLXK_CUDA_TRY(cudaGetLastError());
   return CPLXK_OK;
 }

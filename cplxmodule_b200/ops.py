@@ -12,7 +12,8 @@ import torch
 
 from . import _native as nv
 
-_state = {"noise": "torch", "math": "auto", "prepare": True, "fuse_kl": True, "kl_shard": None}
+_state = {"noise": "torch", "math": "auto", "prepare": True, "fuse_kl": True, "kl_shard": None,
+          "conv_vd": "auto"}
 _MATH = {"auto": nv.MATH_AUTO, "tensor": nv.MATH_TENSOR, "simt": nv.MATH_SIMT, "exact": nv.MATH_SIMT,
          "tf32": nv.MATH_TENSOR_TF32}
 _NOISE = {"torch": nv.NOISE_PHILOX_TORCH, "fast": nv.NOISE_PHILOX_FAST}
@@ -44,6 +45,31 @@ def set_math_mode(mode):
     if mode not in _MATH:
         raise ValueError(f"math mode must be one of {sorted(_MATH)}")
     _state["math"] = mode
+
+
+def set_conv_vd_mode(mode):
+    """Variational convolution forward on the tensor-core path (NCHW planes):
+
+    * ``"composed"``: mean conv and variance conv through the fast plain kernels (CTA-pair /
+      scaled-fp16 complex kernel, real-plane kernel) + ONE in-place launch that draws the noise by
+      Philox call (three calls per four complex outputs) and adds ``eps * sqrt(max(s2, 1e-8))``;
+    * ``"fused"``: the single kernel with three accumulators and the noise in its epilogue (no
+      scratch planes; always used for channels-last inputs);
+    * ``"auto"`` (default): whichever measured faster on config-4-sized work
+      (``tools/convvd_probe.py``, 256 x 64 x 128^2, 3 x 3, 64 -> 64, torch-exact noise, ms composed /
+      fused): complex fp32 6.04 / 5.92 -> fused; complex bf16 4.58 / 5.44, real fp32 4.09 / 4.55,
+      real bf16 2.98 / 4.37 -> composed.
+    Same values either way (same noise stream, same tolerance)."""
+    if mode not in ("auto", "composed", "fused"):
+        raise ValueError("conv VD mode must be 'auto', 'composed' or 'fused'")
+    _state["conv_vd"] = mode
+
+
+def conv_vd_composed(cplx, dtype):
+    mode = _state["conv_vd"]
+    if mode == "auto":
+        return not (cplx and dtype == torch.float32)
+    return mode == "composed"
 
 
 def set_operand_prepass(enabled):

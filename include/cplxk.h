@@ -391,6 +391,14 @@ int cplxk_vd_grad_s2(const void* g_re, const void* g_im, const void* s2, const v
                      const void* eps_im, int noise, uint64_t seed, uint64_t offset,
                      uint32_t philox_threads, void* out, int64_t M, int64_t N, int dtype,
                      void* stream);
+/* y += eps sqrt(max(s2, 1e-8)) in place (y_im, eps_im nullable: real planes); eps injected,
+ * drawn in torch's layout (generated by Philox call: three calls per four complex outputs) or in
+ * the conv kernels' private `fast` layout.  The variational conv forward
+ * (nn/relevance/complex/base.py:120-135, real/base.py:149-163) as mean conv + variance conv of the
+ * fast kernels + this. */
+int cplxk_vd_combine(void* y_re, void* y_im, const void* s2, const void* eps_re,
+                     const void* eps_im, int noise, uint64_t seed, uint64_t offset,
+                     uint32_t philox_threads, int64_t numel, int dtype, void* stream);
 /* dx_re += 2 x_re dq, dx_im += 2 x_im dq  (in place) */
 int cplxk_vd_grad_input(void* dx_re, void* dx_im, const void* x_re, const void* x_im,
                         const void* dq, int64_t n, int dtype, void* stream);

@@ -214,3 +214,45 @@ def test_real_masked_conv_with_groups(tensor_only):
         out = conv(x)
     want = F.conv2d(c64(x), c64(conv.weight) * c64(conv.mask), c64(conv.bias), 1, 1, 1, 2)
     assert rel_err(out, want) < 1e-3
+
+
+@pytest.mark.parametrize("mode", ["composed", "fused"])
+@pytest.mark.parametrize("cplx_", [True, False])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_conv_vd_modes_agree_with_oracle_and_each_other(mode, cplx_, dt):
+    """ops.set_conv_vd_mode: mean conv + variance conv + in-place noise launch ('composed') and the
+    single fused kernel draw the SAME torch-exact noise and meet the same tolerance"""
+    torch.manual_seed(21)
+    tol = 1e-3 if dt == torch.float32 else 1e-2
+    cls = rel.CplxConv2dVD if cplx_ else rel.Conv2dVD
+    m = cls(16, 24, 3, padding=1, stride=(1, 2)).to(DEV).train()
+    with torch.no_grad():
+        m.log_sigma2.uniform_(-8, 0)
+    m = m.to(dt)
+    x = (cplx.randn(3, 16, 20, 37, device=DEV) if cplx_ else torch.randn(3, 16, 20, 37, device=DEV)).to(dt)
+    planes = (lambda t: (t.real, t.imag)) if cplx_ else (lambda t: (t,))
+    cb.set_conv_vd_mode(mode)
+    try:
+        with torch.no_grad():
+            torch.manual_seed(5)
+            fused = m(x)
+            torch.manual_seed(5)
+            eps = (cplx.randn(*fused.shape, device=DEV) if cplx_ else torch.randn(*fused.shape, device=DEV))
+            out = m(x, eps=eps.to(dt))
+    finally:
+        cb.set_conv_vd_mode("auto")
+    f32 = lambda t: t.float()
+    if dt == torch.float32:                      # same stream: bit-equal to the injected draw
+        for a, b in zip(planes(fused), planes(out)):
+            assert torch.equal(a, b)
+    else:                                        # the injected draw is rounded to bf16 first
+        for a, b in zip(planes(fused), planes(out)):
+            assert rel_err(f32(a), f32(b)) < 2e-2
+    w, b = m.weight, m.bias
+    if cplx_:
+        want = orc.cplx_conv2d_vd(c64(x.real), c64(x.imag), c64(w.real), c64(w.imag), c64(b.real), c64(b.imag),
+                                  c64(m.log_sigma2), c64(eps.real.to(dt)), c64(eps.imag.to(dt)), (1, 2), 1, 1)
+    else:
+        want = (orc.real_conv2d_vd(c64(x), c64(w), c64(b), c64(m.log_sigma2), c64(eps.to(dt)), (1, 2), 1, 1, 1),)
+    for a, r in zip(planes(out), want):
+        assert rel_err(f32(a), r) < tol
