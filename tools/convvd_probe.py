@@ -2,7 +2,8 @@
 noise launch) against the fused single kernel, injected noise and the stand-alone draw, complex and
 real planes (ops.set_conv_vd_mode).  One JSON line per case."""
 import sys, json, torch
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cplxmodule_b200 import cplx, ops, conv_ops
 from cplxmodule_b200.nn.relevance import CplxConv2dVD
 def timeit(fn, iters=5, warm=2):
