@@ -345,84 +345,158 @@ conv_amax_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im,
   if ((threadIdx.x & 31) == 0) atomicMax(amax + b, mbits);
 }
 
-// NCHW fp32 -> channels-last fp16 (channels padded to Cp), scaled by the image's power of two.
-// One block = 64 channels x 32 pixels of one image row: reads are 128-byte rows along W, writes
-// are 128-byte rows along C (each lane two channels as one half2).
-__global__ void __launch_bounds__(256)
-conv_nhwc_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im,
-                     __half* __restrict__ o_re, __half* __restrict__ o_im,
-                     const unsigned int* __restrict__ amax, int C, int Cp, int H, int W) {
-  __shared__ float s_re[64][33], s_im[64][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  const int w0 = blockIdx.z * 32, c0 = blockIdx.y * 64;
-  const int64_t bh = blockIdx.x;
-  const int64_t b = bh / H, h = bh - b * H;
-  const float scale = pow2f(f16_scale_exp(__uint_as_float(amax[b])));
+// Scale exponent of one IMAGE's fp16 copy.  Images whose largest magnitude already lies in
+// [2^-2, 2^15) are copied unscaled: every element above 2^-14 keeps its 11-bit significand and
+// the absolute error of the ones below (<= 2^-25) is <= 2^-23 of the image's maximum.  That is what
+// lets the transposing pass run BEFORE the amax is known (kMode 1 below): the common case needs
+// no separate amax pass over the 2 x 4-byte planes.
+__device__ __forceinline__ int f16_image_scale_exp(float amax) {
+  const int ex = static_cast<int>((__float_as_uint(amax) >> 23) & 0xffu) - 127;
+  if (amax == 0.f || (ex >= -2 && ex <= 14)) return 0;
+  return f16_scale_exp(amax);
+}
+
+// block-wide max of |value| bit patterns -> atomicMax(amax + b) (skipped when it cannot raise it)
+__device__ __forceinline__ void conv_block_amax(unsigned int mbits, unsigned int* red, unsigned int* amax_b) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = c0 + ty + 8 * i, w = w0 + tx;
-    float vr = 0.f, vi = 0.f;
-    if (c < C && w < W) {
-      const int64_t off = ((b * C + c) * H + h) * W + w;
-      vr = x_re[off], vi = x_im[off];
-    }
-    s_re[ty + 8 * i][tx] = vr, s_im[ty + 8 * i][tx] = vi;
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned int other = __shfl_xor_sync(0xffffffffu, mbits, o);
+    mbits = other > mbits ? other : mbits;
   }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mbits;
   __syncthreads();
-  const int c = c0 + 2 * tx;          // Cp is a multiple of 16: channel pairs never straddle it
+  if (threadIdx.x == 0) {
+    unsigned int m = red[0];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int wl = ty + 8 * i, w = w0 + wl;
-    if (w < W && c < Cp) {
-      const int64_t off = ((b * H + h) * W + w) * Cp + c;
-      *reinterpret_cast<__half2*>(o_re + off) =
-          __floats2half2_rn(s_re[2 * tx][wl] * scale, s_re[2 * tx + 1][wl] * scale);
-      *reinterpret_cast<__half2*>(o_im + off) =
-          __floats2half2_rn(s_im[2 * tx][wl] * scale, s_im[2 * tx + 1][wl] * scale);
-    }
+    for (int k = 1; k < 8; ++k) m = red[k] > m ? red[k] : m;
+    if (m > *reinterpret_cast<volatile unsigned int*>(amax_b)) atomicMax(amax_b, m);
   }
 }
 
+// NCHW fp32 -> channels-last fp16 (channels padded to Cp), scaled by the image's power of two.
+// One block = 64 channels x 32 pixels of `rows` image rows: reads are 128-byte rows along W, writes
+// are 128-byte rows along C (each lane two channels as one half2).
+//   kMode 0: amax[] is known (conv_amax_kernel ran): scale by 2^f16_image_scale_exp
+//   kMode 1: optimistic single pass: copy UNSCALED and collect amax[] on the way
+//   kMode 2: fix-up after a kMode-1 pass: images whose amax asks for a scale are converted again
+//            (every block of the others returns at once)
+template <int kMode>
+__global__ void __launch_bounds__(256, kMode == 2 ? 1 : 6)
+conv_nhwc_f16_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im,
+                     __half* __restrict__ o_re, __half* __restrict__ o_im,
+                     unsigned int* __restrict__ amax, int C, int Cp, int H, int W, int rows) {
+  __shared__ float s_re[64][33], s_im[64][33];
+  __shared__ unsigned int red[8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int w0 = blockIdx.z * 32, c0 = blockIdx.y * 64;
+  // only the fix-up blocks (kMode 2) walk several rows
+  const int chunks = kMode == 2 ? (H + rows - 1) / rows : H;
+  const int64_t b = blockIdx.x / chunks;
+  const int h_lo = static_cast<int>(blockIdx.x - b * chunks) * (kMode == 2 ? rows : 1);
+  const int h_hi = kMode == 2 ? (h_lo + rows < H ? h_lo + rows : H) : h_lo + 1;
+  float scale = 1.f;
+  if constexpr (kMode != 1) {
+    const int s = f16_image_scale_exp(__uint_as_float(amax[b]));
+    if (kMode == 2 && s == 0) return;
+    scale = pow2f(s);
+  }
+  unsigned int mbits = 0u;
+  for (int h = h_lo; h < h_hi; ++h) {
+    if (h != h_lo) __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + ty + 8 * i, w = w0 + tx;
+      float vr = 0.f, vi = 0.f;
+      if (c < C && w < W) {
+        const int64_t off = ((b * C + c) * H + h) * W + w;
+        vr = x_re[off], vi = x_im[off];
+      }
+      if constexpr (kMode == 1) {
+        const unsigned int a = __float_as_uint(vr) & 0x7fffffffu, d = __float_as_uint(vi) & 0x7fffffffu;
+        mbits = a > mbits ? a : mbits;
+        mbits = d > mbits ? d : mbits;
+      }
+      s_re[ty + 8 * i][tx] = vr, s_im[ty + 8 * i][tx] = vi;
+    }
+    __syncthreads();
+    const int c = c0 + 2 * tx;          // Cp is a multiple of 16: channel pairs never straddle it
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int wl = ty + 8 * i, w = w0 + wl;
+      if (w < W && c < Cp) {
+        const int64_t off = ((b * H + h) * W + w) * Cp + c;
+        *reinterpret_cast<__half2*>(o_re + off) =
+            __floats2half2_rn(s_re[2 * tx][wl] * scale, s_re[2 * tx + 1][wl] * scale);
+        *reinterpret_cast<__half2*>(o_im + off) =
+            __floats2half2_rn(s_im[2 * tx][wl] * scale, s_im[2 * tx + 1][wl] * scale);
+      }
+    }
+  }
+  if constexpr (kMode == 1) conv_block_amax(mbits, red, amax + b);
+}
+
 // Same with 16-byte loads: 64 channels x 64 pixels per block (W % 4 == 0, 16-byte aligned planes)
-__global__ void __launch_bounds__(256)
+template <int kMode>
+__global__ void __launch_bounds__(256, kMode == 2 ? 1 : 6)
 conv_nhwc_f16_v4_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im,
                         __half* __restrict__ o_re, __half* __restrict__ o_im,
-                        const unsigned int* __restrict__ amax, int C, int Cp, int H, int W) {
+                        unsigned int* __restrict__ amax, int C, int Cp, int H, int W, int rows) {
   __shared__ float s_re[64][65], s_im[64][65];
+  __shared__ unsigned int red[8];
   const int tid = threadIdx.x;
   const int w0 = blockIdx.z * 64, c0 = blockIdx.y * 64;
-  const int64_t bh = blockIdx.x;
-  const int64_t b = bh / H, h = bh - b * H;
-  const float scale = pow2f(f16_scale_exp(__uint_as_float(amax[b])));
-  // 64 channel rows x 16 float4: 1024 vector loads per plane, 4 per thread
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int idx = tid + 256 * i;
-    const int cl = idx >> 4, q = idx & 15;
-    const int c = c0 + cl, w = w0 + 4 * q;
-    float4 vr = make_float4(0.f, 0.f, 0.f, 0.f), vi = vr;
-    if (c < C && w < W) {     // W % 4 == 0: a float4 never straddles the row end
-      const int64_t off = ((b * C + c) * H + h) * W + w;
-      vr = __ldg(reinterpret_cast<const float4*>(x_re + off));
-      vi = __ldg(reinterpret_cast<const float4*>(x_im + off));
-    }
-    s_re[cl][4 * q] = vr.x, s_re[cl][4 * q + 1] = vr.y, s_re[cl][4 * q + 2] = vr.z, s_re[cl][4 * q + 3] = vr.w;
-    s_im[cl][4 * q] = vi.x, s_im[cl][4 * q + 1] = vi.y, s_im[cl][4 * q + 2] = vi.z, s_im[cl][4 * q + 3] = vi.w;
+  // only the fix-up blocks (kMode 2) walk several rows
+  const int chunks = kMode == 2 ? (H + rows - 1) / rows : H;
+  const int64_t b = blockIdx.x / chunks;
+  const int h_lo = static_cast<int>(blockIdx.x - b * chunks) * (kMode == 2 ? rows : 1);
+  const int h_hi = kMode == 2 ? (h_lo + rows < H ? h_lo + rows : H) : h_lo + 1;
+  float scale = 1.f;
+  if constexpr (kMode != 1) {
+    const int s = f16_image_scale_exp(__uint_as_float(amax[b]));
+    if (kMode == 2 && s == 0) return;
+    scale = pow2f(s);
   }
-  __syncthreads();
-  const int tx = tid & 31, ty = tid >> 5;
-  const int c = c0 + 2 * tx;
+  unsigned int mbits = 0u;
+  auto upd = [&](float v) {
+    const unsigned int bits = __float_as_uint(v) & 0x7fffffffu;
+    mbits = bits > mbits ? bits : mbits;
+  };
+  for (int h = h_lo; h < h_hi; ++h) {
+    if (h != h_lo) __syncthreads();
+    // 64 channel rows x 16 float4: 1024 vector loads per plane, 4 per thread
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int wl = ty + 8 * i, w = w0 + wl;
-    if (w < W && c < Cp) {
-      const int64_t off = ((b * H + h) * W + w) * Cp + c;
-      *reinterpret_cast<__half2*>(o_re + off) =
-          __floats2half2_rn(s_re[2 * tx][wl] * scale, s_re[2 * tx + 1][wl] * scale);
-      *reinterpret_cast<__half2*>(o_im + off) =
-          __floats2half2_rn(s_im[2 * tx][wl] * scale, s_im[2 * tx + 1][wl] * scale);
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 256 * i;
+      const int cl = idx >> 4, q = idx & 15;
+      const int c = c0 + cl, w = w0 + 4 * q;
+      float4 vr = make_float4(0.f, 0.f, 0.f, 0.f), vi = vr;
+      if (c < C && w < W) {     // W % 4 == 0: a float4 never straddles the row end
+        const int64_t off = ((b * C + c) * H + h) * W + w;
+        vr = __ldg(reinterpret_cast<const float4*>(x_re + off));
+        vi = __ldg(reinterpret_cast<const float4*>(x_im + off));
+      }
+      if constexpr (kMode == 1) {
+        upd(vr.x), upd(vr.y), upd(vr.z), upd(vr.w), upd(vi.x), upd(vi.y), upd(vi.z), upd(vi.w);
+      }
+      s_re[cl][4 * q] = vr.x, s_re[cl][4 * q + 1] = vr.y, s_re[cl][4 * q + 2] = vr.z, s_re[cl][4 * q + 3] = vr.w;
+      s_im[cl][4 * q] = vi.x, s_im[cl][4 * q + 1] = vi.y, s_im[cl][4 * q + 2] = vi.z, s_im[cl][4 * q + 3] = vi.w;
+    }
+    __syncthreads();
+    const int tx = tid & 31, ty = tid >> 5;
+    const int c = c0 + 2 * tx;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int wl = ty + 8 * i, w = w0 + wl;
+      if (w < W && c < Cp) {
+        const int64_t off = ((b * H + h) * W + w) * Cp + c;
+        *reinterpret_cast<__half2*>(o_re + off) =
+            __floats2half2_rn(s_re[2 * tx][wl] * scale, s_re[2 * tx + 1][wl] * scale);
+        *reinterpret_cast<__half2*>(o_im + off) =
+            __floats2half2_rn(s_im[2 * tx][wl] * scale, s_im[2 * tx + 1][wl] * scale);
+      }
     }
   }
+  if constexpr (kMode == 1) conv_block_amax(mbits, red, amax + b);
 }
 
 // weights [O, tCg, kh, kw] fp32 -> tap-major fp16 planes [(r*kw+s) * Op + o][Cp], one block per
@@ -1194,7 +1268,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
         bias_n0 = n0;
       }
       [[maybe_unused]] float isx = 1.f;     // inverse of this image's power-of-two scale
-      if constexpr (kHalf) isx = b < g.B ? pow2f(-f16_scale_exp(__uint_as_float(__ldg(ep.amax + b)))) : 1.f;
+      if constexpr (kHalf) isx = b < g.B ? pow2f(-f16_image_scale_exp(__uint_as_float(__ldg(ep.amax + b)))) : 1.f;
       const uint32_t buf = it & 1u, tph = (it >> 1) & 1u;
       const int64_t oh = oh0 + hh, ow = ow0 + ww;
       const bool pix_ok = oh < g.Ho && ow < g.Wo && b < g.B;
@@ -1368,28 +1442,40 @@ static int launch_conv_f16(const void* x_re, const void* x_im, const void* w_re,
   float* isw = reinterpret_cast<float*>(ws + 2 * act32 + 2 * wgt32 + up256(static_cast<size_t>(g.B) * 4));
 
   CPLXK_CUDA_TRY(cudaMemsetAsync(amax, 0, static_cast<size_t>(g.B) * 4, st));
-  const int64_t per_image = g.C * g.H * g.W;
-  int64_t chunks = per_image / (4 * 256 * 8) + 1;
-  if (chunks > 64) chunks = 64;
   if (g.B > 65535) return CPLXK_ERR_UNSUPPORTED;
-  conv_amax_kernel<<<dim3(static_cast<unsigned>(chunks), static_cast<unsigned>(g.B)), 256, 0, st>>>(
-      static_cast<const float*>(x_re), static_cast<const float*>(x_im), per_image, amax);
-  CPLXK_CUDA_TRY(cudaGetLastError());
-  dim3 tg(static_cast<unsigned>(g.B * g.H), static_cast<unsigned>((g.Cp + 63) / 64),
-          static_cast<unsigned>((g.W + 31) / 32));
-  if (tg.y > 65535u || tg.z > 65535u || g.B * g.H > 0x7fffffff) return CPLXK_ERR_UNSUPPORTED;
   const bool v4 = (g.W % 4 == 0) &&
                   (((reinterpret_cast<uintptr_t>(x_re) | reinterpret_cast<uintptr_t>(x_im)) & 15u) == 0);
-  if (v4) {
-    tg.z = static_cast<unsigned>((g.W + 63) / 64);
-    conv_nhwc_f16_v4_kernel<<<tg, 256, 0, st>>>(static_cast<const float*>(x_re),
-                                                static_cast<const float*>(x_im), a_re, a_im, amax,
-                                                static_cast<int>(g.C), g.Cp, static_cast<int>(g.H),
-                                                static_cast<int>(g.W));
+  const unsigned cy = static_cast<unsigned>((g.Cp + 63) / 64);
+  const unsigned cz = static_cast<unsigned>(v4 ? (g.W + 63) / 64 : (g.W + 31) / 32);
+  if (cy > 65535u || cz > 65535u || g.B * g.H > 0x7fffffff) return CPLXK_ERR_UNSUPPORTED;
+  const float* xr = static_cast<const float*>(x_re);
+  const float* xi = static_cast<const float*>(x_im);
+  const int Ci = static_cast<int>(g.C), Hi = static_cast<int>(g.H), Wi = static_cast<int>(g.W);
+  // kMode (see conv_nhwc_f16_kernel), image rows per block
+  auto convert = [&](int mode, int rows) {
+    const dim3 tg(static_cast<unsigned>(g.B * ((Hi + rows - 1) / rows)), cy, cz);
+#define CPLXK_CONV_CVT(MODE)                                                                        \
+    if (v4) conv_nhwc_f16_v4_kernel<MODE><<<tg, 256, 0, st>>>(xr, xi, a_re, a_im, amax, Ci, g.Cp, Hi, Wi, rows); \
+    else conv_nhwc_f16_kernel<MODE><<<tg, 256, 0, st>>>(xr, xi, a_re, a_im, amax, Ci, g.Cp, Hi, Wi, rows);
+    if (mode == 0) { CPLXK_CONV_CVT(0) } else if (mode == 1) { CPLXK_CONV_CVT(1) } else { CPLXK_CONV_CVT(2) }
+#undef CPLXK_CONV_CVT
+  };
+  if (knobs().conv_amax_pass) {
+    // CPLXK_CONV_AMAX_PASS=1 (A/B): per-image amax first, then ONE scaled conversion
+    const int64_t per_image = g.C * g.H * g.W;
+    int64_t chunks = per_image / (4 * 256 * 8) + 1;
+    if (chunks > 64) chunks = 64;
+    conv_amax_kernel<<<dim3(static_cast<unsigned>(chunks), static_cast<unsigned>(g.B)), 256, 0, st>>>(
+        xr, xi, per_image, amax);
+    CPLXK_CUDA_TRY(cudaGetLastError());
+    convert(0, 1);
   } else {
-    conv_nhwc_f16_kernel<<<tg, 256, 0, st>>>(static_cast<const float*>(x_re), static_cast<const float*>(x_im),
-                                             a_re, a_im, amax, static_cast<int>(g.C), g.Cp,
-                                             static_cast<int>(g.H), static_cast<int>(g.W));
+    // optimistic: convert unscaled while collecting the amax; images that do need a scale (largest
+    // magnitude outside [2^-2, 2^15)) are converted again by the fix-up launch, whose blocks (an
+    // eighth of an image each) return at once otherwise
+    convert(1, 1);
+    CPLXK_CUDA_TRY(cudaGetLastError());
+    convert(2, (Hi + 7) / 8);
   }
   CPLXK_CUDA_TRY(cudaGetLastError());
   conv_wprep_f16_kernel<<<static_cast<unsigned>(g.Op), 256, 0, st>>>(

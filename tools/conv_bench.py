@@ -32,7 +32,7 @@ def main():
     torch.manual_seed(0)
     lib = os.environ.get("CPLXK_LIB", "default")
     with torch.no_grad():
-        for cls in (CplxConv2d, CplxConv2dVD):
+        for cls in ((CplxConv2d,) if "--plain" in sys.argv else (CplxConv2d, CplxConv2dVD)):
             conv = cls(64, 64, 3).to(DEV).train()
             z = cplx.randn(256, 64, 128, 128, device=DEV)
             for dt, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
@@ -41,7 +41,8 @@ def main():
                                 zd.imag.contiguous(memory_format=torch.channels_last))
                 for name, inp in (("nchw", zd), ("nhwc", zcl)):
                     ms = timeit(lambda: convd(inp))
-                    print(json.dumps(dict(lib=os.path.basename(lib), layer=cls.__name__, dtype=tag,
+                    print(json.dumps(dict(lib=os.path.basename(lib), amax_pass=os.environ.get("CPLXK_CONV_AMAX_PASS", "0"),
+                                          layer=cls.__name__, dtype=tag,
                                           layout=name, ms=round(ms, 4))), flush=True)
                 del zcl, zd
             del conv, z
