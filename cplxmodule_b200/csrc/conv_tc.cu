@@ -1107,28 +1107,36 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_xr,
 // (U in the leader's shared memory, V in the peer's), so every M = 256 MMA reads 4 KB of A and
 // 2 KB of B per CTA instead of 4 KB + 4 KB -- the single-CTA kernel runs at the 128 B/clk
 // shared-memory read limit.  Stages shrink to 40 KB (5 stages).
-template <typename T, bool kHalf = false>
+// kRow (wide images: one output row of 128 pixels per tile, unit stride along W): a k-block is one
+// kernel ROW and channel chunk -- the 128 + (kw-1)*dw input pixels are loaded ONCE and the kw taps
+// read them through shared-memory descriptors shifted by whole 128-byte pixel rows, so the
+// activation traffic L2 -> SM drops kw-fold
+// (at 40 KB per 512 MMA cycles the per-tap version sits on the ~64 B/clk per-SM L2 ingest limit).
+template <typename T, bool kHalf = false, bool kRow = false>
 struct ConvPairCfg {
   static_assert(!kHalf || std::is_same<T, float>::value, "fp16 operand copies: fp32 planes");
   static constexpr bool kBF16 = std::is_same<T, __nv_bfloat16>::value || kHalf;   // kind::f16
   static constexpr int BKC = kHalf ? 64 : 128 / static_cast<int>(sizeof(T));
-  static constexpr int A_TILE = 128 * 128;
+  static constexpr int MAX_TAPS = kRow ? 3 : 1;           // taps served by one k-block
+  static constexpr int MAX_HALO = 8;                      // (kw - 1) * dw pixels beyond the 128
+  static constexpr int A_TILE = (kRow ? 128 + MAX_HALO : 128) * 128;
+  static constexpr int B_TILE = 64 * 128;                 // this CTA's half of one tap's [U;V]
   static constexpr int OFF_XR = 0, OFF_XI = A_TILE, OFF_UV = 2 * A_TILE;
-  static constexpr int STAGE_BYTES = 2 * A_TILE + A_TILE / 2;   // 40 KB
-  static constexpr int STAGES = 5;
+  static constexpr int STAGE_BYTES = 2 * A_TILE + MAX_TAPS * B_TILE;   // 40 KB / 58 KB
+  static constexpr int STAGES = kRow ? 3 : 5;
   static constexpr int OFF_BIAS = 256;
   static constexpr int THREADS = 320;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + OFF_BIAS + 8 * 96 * 4;
 };
 
-template <typename T, bool kHalf = false>
+template <typename T, bool kHalf = false, bool kRow = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
                           const __grid_constant__ CUtensorMap tm_xi,
                           const __grid_constant__ CUtensorMap tm_u,
                           const __grid_constant__ CUtensorMap tm_v, const ConvTcGeom g,
                           const ConvTcEpi ep, const int total_tiles) {
-  using C = ConvPairCfg<T, kHalf>;
+  using C = ConvPairCfg<T, kHalf, kRow>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1149,7 +1157,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
   const int items = ((pix_tiles + 1) / 2) * g.tiles_n;
   auto item_tile = [&](int item) { return ((item / g.tiles_n) * 2 + static_cast<int>(rank)) * g.tiles_n + item % g.tiles_n; };
   const int cchunks = (g.Cp + C::BKC - 1) / C::BKC;
-  const int num_kb = g.kh * g.kw * cchunks;
+  const int num_kb = (kRow ? g.kh : g.kh * g.kw) * cchunks;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_xr);
@@ -1186,18 +1194,36 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
           const uint32_t s = kbg % C::STAGES, ph = (kbg / C::STAGES) & 1u;
           ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
           const uint32_t fb = bar_full + 8 * s, st = base + s * C::STAGE_BYTES;
-          const int rs = kb / cchunks, cc = kb - rs * cchunks;
-          const int r = rs / g.kw, sx = rs - r * g.kw;
-          const int32_t c0 = cc * C::BKC;
-          const int32_t iw = ow0 * g.sw - g.pw + sx * g.dw;
-          const int32_t ih = oh0 * g.sh - g.ph + r * g.dh;
-          const int32_t wrow = rs * g.Op + n0;
-          if (elected) {
-            if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * C::STAGE_BYTES);   // both CTAs' bytes
-            ptx::tma_load_4d_pair(st + C::OFF_XR, &tm_xr, fb, c0, iw, ih, b);
-            ptx::tma_load_4d_pair(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
-            // B = [U(64 rows); V(64 rows)] is split along N across the pair: U here, V in the peer
-            ptx::tma_load_2d_pair(st + C::OFF_UV, leader ? &tm_u : &tm_v, fb, c0, wrow);
+          if constexpr (kRow) {
+            // one kernel row r, one channel chunk: 128 + halo input pixels, kw weight tiles
+            const int r = kb / cchunks, cc = kb - r * cchunks;
+            const int32_t c0 = cc * C::BKC;
+            const int32_t iw = ow0 - g.pw;                       // sw == 1
+            const int32_t ih = oh0 * g.sh - g.ph + r * g.dh;
+            const uint32_t tx = 2u * static_cast<uint32_t>(128 + (g.kw - 1) * g.dw) * 128u +
+                                static_cast<uint32_t>(g.kw) * C::B_TILE;
+            if (elected) {
+              if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * tx);   // both CTAs' bytes
+              ptx::tma_load_4d_pair(st + C::OFF_XR, &tm_xr, fb, c0, iw, ih, b);
+              ptx::tma_load_4d_pair(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
+              for (int sx = 0; sx < g.kw; ++sx)
+                ptx::tma_load_2d_pair(st + C::OFF_UV + sx * C::B_TILE, leader ? &tm_u : &tm_v, fb, c0,
+                                      (r * g.kw + sx) * g.Op + n0);
+            }
+          } else {
+            const int rs = kb / cchunks, cc = kb - rs * cchunks;
+            const int r = rs / g.kw, sx = rs - r * g.kw;
+            const int32_t c0 = cc * C::BKC;
+            const int32_t iw = ow0 * g.sw - g.pw + sx * g.dw;
+            const int32_t ih = oh0 * g.sh - g.ph + r * g.dh;
+            const int32_t wrow = rs * g.Op + n0;
+            if (elected) {
+              if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * C::STAGE_BYTES);   // both CTAs' bytes
+              ptx::tma_load_4d_pair(st + C::OFF_XR, &tm_xr, fb, c0, iw, ih, b);
+              ptx::tma_load_4d_pair(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
+              // B = [U(64 rows); V(64 rows)] is split along N across the pair: U here, V in the peer
+              ptx::tma_load_2d_pair(st + C::OFF_UV, leader ? &tm_u : &tm_v, fb, c0, wrow);
+            }
           }
           __syncwarp();
         }
@@ -1220,18 +1246,42 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
           const uint32_t st = base + s * C::STAGE_BYTES;
           ptx::mbar_wait(bar_full + 8 * s, ph);
           ptx::tcgen05_fence_after();
-          const uint64_t a_r = ptx::make_kmajor_desc<128>(st + C::OFF_XR);
-          const uint64_t a_i = ptx::make_kmajor_desc<128>(st + C::OFF_XI);
-          const uint64_t b_uv = ptx::make_kmajor_desc<128>(st + C::OFF_UV);
-          if (elected) {
+          if constexpr (kRow) {
+            for (int sx = 0; sx < g.kw; ++sx) {
+              // tap sx reads pixels [sx*dw, sx*dw + 128) of the row: the start address moves by whole
+              // 128-byte rows.  The tensor core applies the 128B swizzle to ABSOLUTE shared-memory
+              // address bits (as TMA did when it wrote the tile), so the descriptor's base-offset
+              // field [49,52) stays 0 -- measured: with (start >> 7) & 7 there the results are wrong
+              // (profiles/conv_row_ab_r2.jsonl, gpurun log pytest_row_bo / pytest_row_nobo)
+              const uint32_t rows = static_cast<uint32_t>(sx * g.dw);
+              const uint64_t a_r = ptx::make_kmajor_desc<128>(st + C::OFF_XR + rows * 128u);
+              const uint64_t a_i = ptx::make_kmajor_desc<128>(st + C::OFF_XI + rows * 128u);
+              const uint64_t b_uv = ptx::make_kmajor_desc<128>(st + C::OFF_UV + sx * C::B_TILE);
+              if (elected) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-              const uint32_t off = k * 32;
-              ptx::umma_ss_pair<C::kBF16>(t_d1, ptx::desc_advance(a_r, off), ptx::desc_advance(b_uv, off), idesc, acc);
-              ptx::umma_ss_pair<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc, acc);
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t acc = (kb > 0 || sx > 0 || k > 0) ? 1u : 0u;
+                  const uint32_t off = k * 32;
+                  ptx::umma_ss_pair<C::kBF16>(t_d1, ptx::desc_advance(a_r, off), ptx::desc_advance(b_uv, off), idesc, acc);
+                  ptx::umma_ss_pair<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc, acc);
+                }
+              }
             }
-            ptx::umma_commit_pair(bar_empty + 8 * s);
+            if (elected) ptx::umma_commit_pair(bar_empty + 8 * s);
+          } else {
+            const uint64_t a_r = ptx::make_kmajor_desc<128>(st + C::OFF_XR);
+            const uint64_t a_i = ptx::make_kmajor_desc<128>(st + C::OFF_XI);
+            const uint64_t b_uv = ptx::make_kmajor_desc<128>(st + C::OFF_UV);
+            if (elected) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                const uint32_t off = k * 32;
+                ptx::umma_ss_pair<C::kBF16>(t_d1, ptx::desc_advance(a_r, off), ptx::desc_advance(b_uv, off), idesc, acc);
+                ptx::umma_ss_pair<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc, acc);
+              }
+              ptx::umma_commit_pair(bar_empty + 8 * s);
+            }
           }
           __syncwarp();
         }
@@ -1326,8 +1376,10 @@ static CUtensorMapDataType conv_dt() {
 }
 
 // channels-last activation plane [B, H, W, Cp]: box {BKC channels, Wt px (stride sw), Ht rows (stride sh), 1}
+// (+ `halo` pixels for the row mode of the CTA-pair kernel, which serves every tap of a kernel row from one load)
 template <typename T>
-static int make_act_map(CUtensorMap* out, const void* ptr, const ConvTcGeom& g, bool round_tf32 = false) {
+static int make_act_map(CUtensorMap* out, const void* ptr, const ConvTcGeom& g, bool round_tf32 = false,
+                        int halo = 0) {
   auto enc = tensor_map_encode_fn();
   if (!enc) return CPLXK_ERR_CUDA;
   const cuuint64_t es = sizeof(T);
@@ -1336,7 +1388,7 @@ static int make_act_map(CUtensorMap* out, const void* ptr, const ConvTcGeom& g, 
   cuuint64_t gstr[3] = {g.Cp * es, static_cast<cuuint64_t>(g.W) * g.Cp * es,
                         static_cast<cuuint64_t>(g.H) * g.W * g.Cp * es};
   cuuint32_t box[4] = {static_cast<cuuint32_t>(128 / sizeof(T)),
-                       static_cast<cuuint32_t>((g.Wt - 1) * g.sw + 1),
+                       static_cast<cuuint32_t>((g.Wt - 1) * g.sw + 1 + halo),   // halo: row mode (sw == 1)
                        static_cast<cuuint32_t>((g.Ht - 1) * g.sh + 1), 1u};
   cuuint32_t estr[4] = {1u, static_cast<cuuint32_t>(g.sw), static_cast<cuuint32_t>(g.sh), 1u};
   const CUtensorMapDataType dt = (round_tf32 && std::is_same<T, float>::value)
@@ -1423,6 +1475,38 @@ bool conv_tc_supported(int dtype, int64_t B, int64_t C, int64_t H, int64_t W, in
          static_cast<int64_t>(kh) * kw * g.Op <= 0x7fffffff;
 }
 
+// Row mode of the CTA-pair kernel (ConvPairCfg<.., kRow>): tiles are single output rows of 128
+// pixels, unit stride along W, 2 or 3 taps per kernel row within 8 pixels
+static bool conv_row_mode(const ConvTcGeom& g) {
+  return knobs().conv_row && g.Ht == 1 && g.Wt == 128 && g.sw == 1 && g.kw >= 2 && g.kw <= 3 &&
+         (g.kw - 1) * g.dw <= 8;
+}
+static int conv_row_halo(const ConvTcGeom& g) { return conv_row_mode(g) ? (g.kw - 1) * g.dw : 0; }
+
+template <typename T, bool kHalf>
+static int launch_conv_pair(const CUtensorMap& tm_xr, const CUtensorMap& tm_xi, const CUtensorMap& tm_u,
+                            const CUtensorMap& tm_v, const ConvTcGeom& g, const ConvTcEpi& ep,
+                            int64_t tiles, cudaStream_t st) {
+  int sms = 148, rc;
+  if ((rc = current_device_sm_count(&sms))) return rc;
+  const int64_t items = ((tiles / g.tiles_n + 1) / 2) * g.tiles_n;
+  int64_t clusters = sms / 2;
+  if (clusters > items) clusters = items;
+  auto go = [&](auto kern, int threads, int smem) -> int {
+    CPLXK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<static_cast<unsigned>(2 * clusters), threads, smem, st>>>(tm_xr, tm_xi, tm_u, tm_v, g, ep,
+                                                                    static_cast<int>(tiles));
+    CPLXK_CUDA_TRY(cudaGetLastError());
+    return CPLXK_OK;
+  };
+  if (conv_row_mode(g)) {
+    using PC = ConvPairCfg<T, kHalf, true>;
+    return go(conv_tc_pair_kernel<T, kHalf, true>, PC::THREADS, PC::SMEM_BYTES);
+  }
+  using PC = ConvPairCfg<T, kHalf, false>;
+  return go(conv_tc_pair_kernel<T, kHalf, false>, PC::THREADS, PC::SMEM_BYTES);
+}
+
 // fp32 NCHW planes on fp16 operands: per-image amax -> transposing, scaling pre-pass -> weights
 // with per-output-channel scales -> CTA-pair kernel on kind::f16
 static int launch_conv_f16(const void* x_re, const void* x_im, const void* w_re, const void* w_im,
@@ -1485,25 +1569,15 @@ static int launch_conv_f16(const void* x_re, const void* x_im, const void* w_re,
 
   CUtensorMap tm_xr, tm_xi, tm_u, tm_v;
   int rc;
-  if ((rc = make_act_map<__half>(&tm_xr, a_re, g))) return rc;
-  if ((rc = make_act_map<__half>(&tm_xi, a_im, g))) return rc;
+  const int halo = conv_row_halo(g);
+  if ((rc = make_act_map<__half>(&tm_xr, a_re, g, false, halo))) return rc;
+  if ((rc = make_act_map<__half>(&tm_xi, a_im, g, false, halo))) return rc;
   if ((rc = make_w_map<__half>(&tm_u, u, g))) return rc;
   if ((rc = make_w_map<__half>(&tm_v, v, g))) return rc;
   ConvTcEpi ep = ep_in;
   ep.amax = amax, ep.isw = isw;
-  int sms = 148;
-  if ((rc = current_device_sm_count(&sms))) return rc;
   const int64_t tiles = g.B * g.tiles_h * g.tiles_w * g.tiles_n;
-  const int64_t items = ((tiles / g.tiles_n + 1) / 2) * g.tiles_n;
-  int64_t clusters = sms / 2;
-  if (clusters > items) clusters = items;
-  auto pk = conv_tc_pair_kernel<float, true>;
-  using PC = ConvPairCfg<float, true>;
-  CPLXK_CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, PC::SMEM_BYTES));
-  pk<<<static_cast<unsigned>(2 * clusters), PC::THREADS, PC::SMEM_BYTES, st>>>(tm_xr, tm_xi, tm_u, tm_v, g, ep,
-                                                                            static_cast<int>(tiles));
-  CPLXK_CUDA_TRY(cudaGetLastError());
-  return CPLXK_OK;
+  return launch_conv_pair<float, true>(tm_xr, tm_xi, tm_u, tm_v, g, ep, tiles, st);
 }
 
 template <typename T, bool kVD>
@@ -1576,8 +1650,11 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
 
   CUtensorMap tm_xr, tm_xi, tm_q, tm_u, tm_v, tm_e;
   int rc;
-  if ((rc = make_act_map<T>(&tm_xr, a_re, g, nhwc))) return rc;
-  if ((rc = make_act_map<T>(&tm_xi, a_im, g, nhwc))) return rc;
+  const int64_t tiles = g.B * g.tiles_h * g.tiles_w * g.tiles_n;
+  const bool pair = !kVD && knobs().conv_persistent && knobs().conv_pair && tiles / g.tiles_n >= 2;
+  const int halo = pair ? conv_row_halo(g) : 0;
+  if ((rc = make_act_map<T>(&tm_xr, a_re, g, nhwc, halo))) return rc;
+  if ((rc = make_act_map<T>(&tm_xi, a_im, g, nhwc, halo))) return rc;
   if ((rc = make_w_map<T>(&tm_u, u, g))) return rc;
   if ((rc = make_w_map<T>(&tm_v, v, g))) return rc;
   tm_q = tm_xr, tm_e = tm_u;
@@ -1585,23 +1662,11 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
     if ((rc = make_act_map<T>(&tm_q, a_q, g))) return rc;
     if ((rc = make_w_map<T>(&tm_e, e, g))) return rc;
   }
-  const int64_t tiles = g.B * g.tiles_h * g.tiles_w * g.tiles_n;
   if constexpr (!kVD) {
     if (knobs().conv_persistent) {
       int sms = 148;
       if ((rc = current_device_sm_count(&sms))) return rc;
-      if (knobs().conv_pair && tiles / g.tiles_n >= 2) {
-        auto pk2 = conv_tc_pair_kernel<T>;
-        CPLXK_CUDA_TRY(cudaFuncSetAttribute(pk2, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            ConvPairCfg<T>::SMEM_BYTES));
-        const int64_t items = ((tiles / g.tiles_n + 1) / 2) * g.tiles_n;
-        int64_t clusters = sms / 2;
-        if (clusters > items) clusters = items;
-        pk2<<<static_cast<unsigned>(2 * clusters), ConvPairCfg<T>::THREADS, ConvPairCfg<T>::SMEM_BYTES, st>>>(
-            tm_xr, tm_xi, tm_u, tm_v, g, ep, static_cast<int>(tiles));
-        CPLXK_CUDA_TRY(cudaGetLastError());
-        return CPLXK_OK;
-      }
+      if (pair) return launch_conv_pair<T, false>(tm_xr, tm_xi, tm_u, tm_v, g, ep, tiles, st);
       auto pk = conv_tc_persistent_kernel<T>;
       CPLXK_CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ConvPCfg<T>::SMEM_BYTES));

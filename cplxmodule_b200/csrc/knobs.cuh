@@ -18,6 +18,7 @@ struct Knobs {
   bool tma_raw_f32;        // CPLXK_TMA_RAW_F32=1: let the tensor core truncate fp32 -> tf32
   bool conv_pair;          // CPLXK_CONV_PAIR=0: conv on single-CTA tiles
   bool conv_persistent;    // CPLXK_CONV_NONPERSISTENT=1: one conv tile per CTA
+  bool conv_row;           // CPLXK_CONV_ROW=0: CTA-pair conv kernel loads every tap separately (no row mode)
   bool conv_amax_pass;     // CPLXK_CONV_AMAX_PASS=1: fp32 NCHW conv input: separate amax pass before the fp16 conversion (default: optimistic single pass + fix-up)
   bool pdl;                // CPLXK_PDL=0: no programmatic dependent launch between pre-pass and GEMM
   bool prep_prefetch;      // CPLXK_PREP_PREFETCH=1: the operand pre-pass prefetches its next row to L2 (default off: slower)

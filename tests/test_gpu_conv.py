@@ -371,3 +371,40 @@ def test_fp32_nchw_conv_on_scaled_fp16_operands():
         assert float((err / mag)[keep].max()) < 2e-3
         assert torch.isfinite(got).all()
         assert rel_err(got, ref) < TOL["tensor"] and rel_err(got32, ref) < TOL["tensor"]
+
+
+@pytest.mark.parametrize("shape", [
+    # (B, C, H, W, O, k, stride, padding, dilation): output rows wider than 64 pixels, unit stride along W
+    (2, 64, 9, 200, 64, 3, 1, 1, 1),                      # padding: the row box starts at iw = -1; two w-tiles
+    (2, 24, 9, 150, 72, (3, 2), (2, 1), (1, 0), (1, 3)),  # kw = 2, dilation 3 (halo 3), vertical stride 2, two n-blocks
+    (1, 16, 5, 300, 8, (2, 3), 1, (0, 4), (1, 4)),        # kw = 3, dilation 4 (halo 8 = the maximum), three w-tiles
+    (3, 32, 4, 131, 16, (1, 3), 1, 0, (1, 2)),            # row kernel, halo 4, odd tile out (3 * 4 * 2 tiles ... pairs)
+])
+@pytest.mark.parametrize("mode", ["f16", "tf32", "bf16", "f32_cl", "bf16_cl"])
+def test_row_mode_conv_shapes(shape, mode):
+    """Row mode of the CTA-pair kernel (ConvPairCfg<.., kRow>): one load of 128 + (kw-1)*dw pixels
+    serves every tap of a kernel row through shifted shared-memory descriptors -- every operand
+    format that reaches the kernel (scaled fp16 copies of fp32 NCHW planes, tf32, bf16, channels-last
+    in place) against the float64 oracle."""
+    B, C, H, W, O, k, stride, padding, dilation = shape
+    torch.manual_seed(7 + len(mode))
+    m = CplxConv2d(C, O, k, stride=stride, padding=padding, dilation=dilation).to(DEV)
+    z = cplx.randn(B, C, H, W, device=DEV)
+    bf16 = mode.startswith("bf16")
+    if bf16:
+        m, z = m.bfloat16(), z.to(torch.bfloat16)
+    c = lambda t: t.detach().cpu().double()
+    want = orc.cplx_conv2d(c(z.real), c(z.imag), c(m.weight.real), c(m.weight.imag), c(m.bias.real),
+                           c(m.bias.imag), m.stride, m.padding, m.dilation)
+    if mode.endswith("_cl"):
+        z = cplx.Cplx(z.real.contiguous(memory_format=torch.channels_last),
+                      z.imag.contiguous(memory_format=torch.channels_last))
+    ops.set_math_mode("tf32" if mode == "tf32" else "tensor")
+    try:
+        with torch.no_grad():
+            out = m(z)
+    finally:
+        ops.set_math_mode("auto")
+    tol = 1e-2 if bf16 else 1e-3
+    assert out.shape == want[0].shape
+    assert rel_err(out.real.float(), want[0]) < tol and rel_err(out.imag.float(), want[1]) < tol

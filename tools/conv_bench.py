@@ -41,7 +41,7 @@ def main():
                                 zd.imag.contiguous(memory_format=torch.channels_last))
                 for name, inp in (("nchw", zd), ("nhwc", zcl)):
                     ms = timeit(lambda: convd(inp))
-                    print(json.dumps(dict(lib=os.path.basename(lib), amax_pass=os.environ.get("CPLXK_CONV_AMAX_PASS", "0"),
+                    print(json.dumps(dict(lib=os.path.basename(lib), amax_pass=os.environ.get("CPLXK_CONV_AMAX_PASS", "0"), row=os.environ.get("CPLXK_CONV_ROW", "1"),
                                           layer=cls.__name__, dtype=tag,
                                           layout=name, ms=round(ms, 4))), flush=True)
                 del zcl, zd
