@@ -17,7 +17,9 @@
 // map's element stride, dilation an offset of the box origin.  The channels-last copies (and
 // |x|^2, exp(log_sigma2), and the tap-major weight planes) are written once per call by
 // elementwise pre-pass kernels into a caller-provided workspace.
+#include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <type_traits>
 
 #include "common.cuh"
@@ -1507,8 +1509,40 @@ static int launch_conv_pair(const CUtensorMap& tm_xr, const CUtensorMap& tm_xi, 
   return go(conv_tc_pair_kernel<T, kHalf, false>, PC::THREADS, PC::SMEM_BYTES);
 }
 
-// fp32 NCHW planes on fp16 operands: per-image amax -> transposing, scaling pre-pass -> weights
-// with per-output-channel scales -> CTA-pair kernel on kind::f16
+// Side stream of the chunked fp32 NCHW path (one per device, HIGHEST priority: it runs the
+// persistent GEMM launches, whose CTAs are then placed before the pending conversion blocks of the
+// caller's stream -- which take what a GEMM CTA leaves free on an SM)
+struct ConvSide {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t join = nullptr;
+  cudaEvent_t done[16] = {};
+  std::mutex mu;        // one enqueue sequence at a time (the events are shared)
+  bool ok = false;
+};
+static ConvSide* conv_side_stream() {
+  static ConvSide sides[64];
+  static std::mutex init_mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  ConvSide& s = sides[dev];
+  std::lock_guard<std::mutex> lock(init_mu);
+  if (!s.ok) {
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    for (auto& e : s.done)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    s.ok = true;
+  }
+  return &s;
+}
+
+// fp32 NCHW planes on fp16 operands: transposing pre-pass (optimistic per-image scale, see
+// f16_image_scale_exp) -> weights with per-output-channel scales -> CTA-pair kernel on kind::f16.
+// The pre-pass is HBM bound and the GEMM tensor bound, so large batches run in CHUNKS of images:
+// chunk c + 1 is converted on the caller's stream while the GEMM of chunk c runs on a
+// high-priority side stream (fork / join through events; nothing synchronises with the host).
 static int launch_conv_f16(const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                            void* workspace, ConvTcGeom g, const ConvTcEpi& ep_in, cudaStream_t st) {
   const size_t act32 = up256(static_cast<size_t>(g.B) * g.H * g.W * g.Cp * 4);
@@ -1525,7 +1559,6 @@ static int launch_conv_f16(const void* x_re, const void* x_im, const void* w_re,
   unsigned int* amax = reinterpret_cast<unsigned int*>(ws + 2 * act32 + 2 * wgt32);
   float* isw = reinterpret_cast<float*>(ws + 2 * act32 + 2 * wgt32 + up256(static_cast<size_t>(g.B) * 4));
 
-  CPLXK_CUDA_TRY(cudaMemsetAsync(amax, 0, static_cast<size_t>(g.B) * 4, st));
   if (g.B > 65535) return CPLXK_ERR_UNSUPPORTED;
   const bool v4 = (g.W % 4 == 0) &&
                   (((reinterpret_cast<uintptr_t>(x_re) | reinterpret_cast<uintptr_t>(x_im)) & 15u) == 0);
@@ -1535,49 +1568,149 @@ static int launch_conv_f16(const void* x_re, const void* x_im, const void* w_re,
   const float* xr = static_cast<const float*>(x_re);
   const float* xi = static_cast<const float*>(x_im);
   const int Ci = static_cast<int>(g.C), Hi = static_cast<int>(g.H), Wi = static_cast<int>(g.W);
-  // kMode (see conv_nhwc_f16_kernel), image rows per block
-  auto convert = [&](int mode, int rows) {
-    const dim3 tg(static_cast<unsigned>(g.B * ((Hi + rows - 1) / rows)), cy, cz);
+  const int64_t img_in = g.C * g.H * g.W, img_a = g.H * g.W * g.Cp;
+  // the conversion blocks are to share SMs with a resident GEMM CTA (chunked path below): same
+  // (maximal) shared-memory carve-out as the GEMM kernel
+  static const bool carve_set = [] {
+    const int mx = cudaSharedmemCarveoutMaxShared;
+    cudaFuncSetAttribute(conv_nhwc_f16_v4_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(conv_nhwc_f16_v4_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(conv_nhwc_f16_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(conv_nhwc_f16_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    return true;
+  }();
+  (void)carve_set;
+  // kMode (see conv_nhwc_f16_kernel), image rows per block, images [b0, b0 + nb), stream
+  auto convert = [&](int mode, int rows, int64_t b0, int64_t nb, cudaStream_t cs) {
+    const dim3 tg(static_cast<unsigned>(nb * ((Hi + rows - 1) / rows)), cy, cz);
+    const float *pr = xr + b0 * img_in, *pi = xi + b0 * img_in;
+    __half *or_ = a_re + b0 * img_a, *oi = a_im + b0 * img_a;
+    unsigned int* am = amax + b0;
 #define CPLXK_CONV_CVT(MODE)                                                                        \
-    if (v4) conv_nhwc_f16_v4_kernel<MODE><<<tg, 256, 0, st>>>(xr, xi, a_re, a_im, amax, Ci, g.Cp, Hi, Wi, rows); \
-    else conv_nhwc_f16_kernel<MODE><<<tg, 256, 0, st>>>(xr, xi, a_re, a_im, amax, Ci, g.Cp, Hi, Wi, rows);
+    if (v4) conv_nhwc_f16_v4_kernel<MODE><<<tg, 256, 0, cs>>>(pr, pi, or_, oi, am, Ci, g.Cp, Hi, Wi, rows); \
+    else conv_nhwc_f16_kernel<MODE><<<tg, 256, 0, cs>>>(pr, pi, or_, oi, am, Ci, g.Cp, Hi, Wi, rows);
     if (mode == 0) { CPLXK_CONV_CVT(0) } else if (mode == 1) { CPLXK_CONV_CVT(1) } else { CPLXK_CONV_CVT(2) }
 #undef CPLXK_CONV_CVT
   };
-  if (knobs().conv_amax_pass) {
-    // CPLXK_CONV_AMAX_PASS=1 (A/B): per-image amax first, then ONE scaled conversion
-    const int64_t per_image = g.C * g.H * g.W;
-    int64_t chunks = per_image / (4 * 256 * 8) + 1;
-    if (chunks > 64) chunks = 64;
-    conv_amax_kernel<<<dim3(static_cast<unsigned>(chunks), static_cast<unsigned>(g.B)), 256, 0, st>>>(
-        xr, xi, per_image, amax);
+  // the whole pre-pass of images [b0, b0 + nb) on stream cs
+  auto prepass = [&](int64_t b0, int64_t nb, cudaStream_t cs) -> int {
+    if (knobs().conv_amax_pass) {
+      // CPLXK_CONV_AMAX_PASS=1 (A/B): per-image amax first, then ONE scaled conversion
+      int64_t chunks = img_in / (4 * 256 * 8) + 1;
+      if (chunks > 64) chunks = 64;
+      conv_amax_kernel<<<dim3(static_cast<unsigned>(chunks), static_cast<unsigned>(nb)), 256, 0, cs>>>(
+          xr + b0 * img_in, xi + b0 * img_in, img_in, amax + b0);
+      CPLXK_CUDA_TRY(cudaGetLastError());
+      convert(0, 1, b0, nb, cs);
+    } else {
+      // optimistic: convert unscaled while collecting the amax; images that do need a scale (largest
+      // magnitude outside [2^-2, 2^15)) are converted again by the fix-up launch, whose blocks (an
+      // eighth of an image each) return at once otherwise
+      convert(1, 1, b0, nb, cs);
+      CPLXK_CUDA_TRY(cudaGetLastError());
+      convert(2, (Hi + 7) / 8, b0, nb, cs);
+    }
     CPLXK_CUDA_TRY(cudaGetLastError());
-    convert(0, 1);
-  } else {
-    // optimistic: convert unscaled while collecting the amax; images that do need a scale (largest
-    // magnitude outside [2^-2, 2^15)) are converted again by the fix-up launch, whose blocks (an
-    // eighth of an image each) return at once otherwise
-    convert(1, 1);
-    CPLXK_CUDA_TRY(cudaGetLastError());
-    convert(2, (Hi + 7) / 8);
-  }
-  CPLXK_CUDA_TRY(cudaGetLastError());
+    return CPLXK_OK;
+  };
+  // the GEMM of images [b0, b0 + nb) on stream gs
+  const int halo = conv_row_halo(g);
+  CUtensorMap tm_u, tm_v;
+  int rc;
+  if ((rc = make_w_map<__half>(&tm_u, u, g))) return rc;
+  if ((rc = make_w_map<__half>(&tm_v, v, g))) return rc;
+  const int64_t img_out = g.O * g.Ho * g.Wo;
+  auto gemm = [&](int64_t b0, int64_t nb, cudaStream_t gs) -> int {
+    ConvTcGeom gc = g;
+    gc.B = nb;
+    CUtensorMap tm_xr, tm_xi;
+    int r;
+    if ((r = make_act_map<__half>(&tm_xr, a_re + b0 * img_a, gc, false, halo))) return r;
+    if ((r = make_act_map<__half>(&tm_xi, a_im + b0 * img_a, gc, false, halo))) return r;
+    ConvTcEpi ep = ep_in;
+    ep.amax = amax + b0, ep.isw = isw;
+    ep.y_re = static_cast<float*>(ep_in.y_re) + b0 * img_out;
+    ep.y_im = static_cast<float*>(ep_in.y_im) + b0 * img_out;
+    const int64_t tiles = nb * gc.tiles_h * gc.tiles_w * gc.tiles_n;
+    return launch_conv_pair<float, true>(tm_xr, tm_xi, tm_u, tm_v, gc, ep, tiles, gs);
+  };
+
+  CPLXK_CUDA_TRY(cudaMemsetAsync(amax, 0, static_cast<size_t>(g.B) * 4, st));
   conv_wprep_f16_kernel<<<static_cast<unsigned>(g.Op), 256, 0, st>>>(
       static_cast<const float*>(w_re), static_cast<const float*>(w_im), u, v, isw, static_cast<int>(g.O),
       g.Op, static_cast<int>(g.C), g.Cp, g.tOg, g.tCg, g.kh * g.kw);
   CPLXK_CUDA_TRY(cudaGetLastError());
 
-  CUtensorMap tm_xr, tm_xi, tm_u, tm_v;
-  int rc;
-  const int halo = conv_row_halo(g);
-  if ((rc = make_act_map<__half>(&tm_xr, a_re, g, false, halo))) return rc;
-  if ((rc = make_act_map<__half>(&tm_xi, a_im, g, false, halo))) return rc;
-  if ((rc = make_w_map<__half>(&tm_u, u, g))) return rc;
-  if ((rc = make_w_map<__half>(&tm_v, v, g))) return rc;
-  ConvTcEpi ep = ep_in;
-  ep.amax = amax, ep.isw = isw;
-  const int64_t tiles = g.B * g.tiles_h * g.tiles_w * g.tiles_n;
-  return launch_conv_pair<float, true>(tm_xr, tm_xi, tm_u, tm_v, g, ep, tiles, st);
+  // chunks of >= 2 waves of pixel-tile pairs each, at most 16; none while the stream is being captured
+  // (a captured graph keeps the simple serial form)
+  int sms = 148;
+  if ((rc = current_device_sm_count(&sms))) return rc;
+  const int64_t tiles_img = static_cast<int64_t>(g.tiles_h) * g.tiles_w;
+  int64_t per = (2 * static_cast<int64_t>(sms) + tiles_img - 1) / tiles_img;   // images per chunk, lower bound
+  int64_t nchunk = knobs().conv_overlap > 0 ? knobs().conv_overlap : 0;
+  if (nchunk > 16) nchunk = 16;
+  if (nchunk * per > g.B) nchunk = g.B / per;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (nchunk >= 2 && cudaStreamIsCapturing(st, &cap) != cudaSuccess) {
+    (void)cudaGetLastError();          // cannot tell: keep the serial form
+    cap = cudaStreamCaptureStatusActive;
+  }
+  ConvSide* side = (nchunk >= 2 && cap == cudaStreamCaptureStatusNone) ? conv_side_stream() : nullptr;
+  if (!side) {
+    if ((rc = prepass(0, g.B, st))) return rc;
+    return gemm(0, g.B, st);
+  }
+  std::lock_guard<std::mutex> lock(side->mu);
+  const int64_t nb = (g.B + nchunk - 1) / nchunk;
+  int64_t c = 0;
+#ifdef CPLXK_CONV_TRACE_BUILD      // side builds: begin / end of every chunk's pre-pass and GEMM on stderr
+  static cudaEvent_t tr[4][16];
+  static bool tr_ok = false;
+  if (!tr_ok) {
+    for (auto& row : tr)
+      for (auto& e : row) cudaEventCreate(&e);
+    tr_ok = true;
+  }
+#endif
+  for (int64_t b0 = 0; b0 < g.B; ++c, b0 += nb) {
+    const int64_t n = b0 + nb <= g.B ? nb : g.B - b0;
+#ifdef CPLXK_CONV_TRACE_BUILD
+    cudaEventRecord(tr[0][c], st);
+#endif
+    if ((rc = prepass(b0, n, st))) break;
+#ifdef CPLXK_CONV_TRACE_BUILD
+    cudaEventRecord(tr[1][c], st);
+#endif
+    if (cudaEventRecord(side->done[c], st) != cudaSuccess ||
+        cudaStreamWaitEvent(side->stream, side->done[c], 0) != cudaSuccess) {
+      rc = CPLXK_ERR_CUDA;
+      break;
+    }
+#ifdef CPLXK_CONV_TRACE_BUILD
+    cudaEventRecord(tr[2][c], side->stream);
+#endif
+    if ((rc = gemm(b0, n, side->stream))) break;
+#ifdef CPLXK_CONV_TRACE_BUILD
+    cudaEventRecord(tr[3][c], side->stream);
+#endif
+  }
+#ifdef CPLXK_CONV_TRACE_BUILD
+  if (rc == CPLXK_OK && std::getenv("CPLXK_CONV_TRACE")) {
+    cudaStreamSynchronize(side->stream);
+    cudaStreamSynchronize(st);
+    for (int64_t i = 0; i < c; ++i) {
+      float t[4];
+      for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tr[0][0], tr[k][i]);
+      std::fprintf(stderr, "conv_trace chunk %d: prepass %.3f .. %.3f ms, gemm %.3f .. %.3f ms\n",
+                   static_cast<int>(i), t[0], t[1], t[2], t[3]);
+    }
+  }
+#endif
+  // join (also on the error paths: the caller's stream never runs ahead of the side stream)
+  if (cudaEventRecord(side->join, side->stream) != cudaSuccess ||
+      cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess)
+    return CPLXK_ERR_CUDA;
+  return rc;
 }
 
 template <typename T, bool kVD>

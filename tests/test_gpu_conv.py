@@ -408,3 +408,38 @@ def test_row_mode_conv_shapes(shape, mode):
     tol = 1e-2 if bf16 else 1e-3
     assert out.shape == want[0].shape
     assert rel_err(out.real.float(), want[0]) < tol and rel_err(out.imag.float(), want[1]) < tol
+
+
+def test_fp32_nchw_conv_chunked_prepass_overlap():
+    """Large fp32 NCHW batches run in chunks of images (pre-pass of chunk c + 1 on the caller's stream
+    under the GEMM of chunk c on a high-priority side stream, launch_conv_f16): uneven chunks
+    (21 images -> 6 + 6 + 6 + 3), images that take the fix-up conversion in either chunk, a second call
+    right behind the first on the same workspace, and a call on a non-default stream."""
+    torch.manual_seed(5)
+    B, C, H, W, O = 21, 16, 40, 130, 16
+    m = CplxConv2d(C, O, 3, padding=1).to(DEV)
+    z = cplx.randn(B, C, H, W, device=DEV)
+    scale = torch.ones(B, device=DEV)
+    scale[3], scale[12], scale[20] = 1e-5, 3e4, 0.0
+    z = cplx.Cplx(z.real * scale.view(B, 1, 1, 1), z.imag * scale.view(B, 1, 1, 1))
+    z2 = cplx.Cplx(z.imag.clone(), z.real.clone())
+    c = lambda t: t.detach().cpu().double()
+    with torch.no_grad():
+        out = m(z)
+        out2 = m(z2)               # same workspace, enqueued while the first call's chunks are in flight
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            out3 = m(z)
+        torch.cuda.current_stream().wait_stream(s)
+    w = [c(m.weight.real), c(m.weight.imag), c(m.bias.real), c(m.bias.imag)]
+    want = orc.cplx_conv2d(c(z.real), c(z.imag), *w, 1, 1, 1)
+    want2 = orc.cplx_conv2d(c(z2.real), c(z2.imag), *w, 1, 1, 1)
+    for b in range(B):      # per image: the scales differ by nine orders of magnitude
+        if float(scale[b]) == 0.0:
+            continue
+        for got, ref in ((out.real, want[0]), (out.imag, want[1]), (out2.real, want2[0]), (out2.imag, want2[1])):
+            bias_mag = float(m.bias.real.abs().max())
+            err = float((c(got[b]) - ref[b]).abs().max()) / max(float(ref[b].abs().max()), bias_mag)
+            assert err < 1e-3, (b, err)
+    assert torch.equal(out3.real, out.real) and torch.equal(out3.imag, out.imag)

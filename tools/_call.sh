@@ -1,9 +1,10 @@
-T="tests/test_gpu_conv.py -k row_mode_conv_shapes"
-timeout 150 python -m pytest $T -m gpu -q -x > gpurun_out/pytest_row_bo.log 2>&1; echo "baseoff rc=$?"; tail -4 gpurun_out/pytest_row_bo.log
-CPLXK_LIB=$PWD/cplxmodule_b200/csrc/libcplxk_nobo.so timeout 150 python -m pytest $T -m gpu -q -x > gpurun_out/pytest_row_nobo.log 2>&1; echo "nobo rc=$?"; tail -4 gpurun_out/pytest_row_nobo.log
-rm -f gpurun_out/conv_row_ab.jsonl
-for i in 1 2; do
- timeout 120 python tools/conv_bench.py --plain >> gpurun_out/conv_row_ab.jsonl 2>gpurun_out/conv_row_ab.err
- CPLXK_CONV_ROW=0 timeout 120 python tools/conv_bench.py --plain >> gpurun_out/conv_row_ab.jsonl 2>>gpurun_out/conv_row_ab.err
+L=$PWD/cplxmodule_b200/csrc/libcplxk_ctrace.so
+for ov in 4 8; do
+ echo "== overlap $ov"
+ CPLXK_LIB=$L CPLXK_CONV_TRACE=1 CPLXK_CONV_OVERLAP=$ov timeout 120 python tools/prof_conv.py 3 f32 nchw 2>&1 | tail -$((ov+1))
 done
-cat gpurun_out/conv_row_ab.jsonl
+rm -f gpurun_out/conv_overlap_ab2.jsonl
+for ov in 4 0 8 0; do
+ CPLXK_CONV_OVERLAP=$ov timeout 120 python tools/conv_bench.py --plain --fp32-nchw >> gpurun_out/conv_overlap_ab2.jsonl 2>gpurun_out/conv_overlap_ab2.err
+done
+cat gpurun_out/conv_overlap_ab2.jsonl
