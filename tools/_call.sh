@@ -1,10 +1,9 @@
-L=$PWD/cplxmodule_b200/csrc/libcplxk_ctrace.so
-for ov in 4 8; do
- echo "== overlap $ov"
- CPLXK_LIB=$L CPLXK_CONV_TRACE=1 CPLXK_CONV_OVERLAP=$ov timeout 120 python tools/prof_conv.py 3 f32 nchw 2>&1 | tail -$((ov+1))
+timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_final2.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_final2.log
+timeout 300 python tools/config_bench.py > gpurun_out/configs_r2b.log 2>&1; echo "cfg rc=$?"; grep -c config gpurun_out/configs_r2b.log
+timeout 400 python bench.py > gpurun_out/bench_final2.json 2> gpurun_out/bench_final2.err; echo "bench rc=$?"; cut -c1-400 gpurun_out/bench_final2.json
+for v in "f32 nchw" "bf16 nhwc"; do
+ set -- $v
+ timeout 200 ncu --set full --clock-control none -k regex:conv_tc_pair -s 2 -c 1 -o /tmp/p_$1 -f python tools/prof_conv.py 4 $1 $2 > /tmp/p.log 2>&1
+ ncu -i /tmp/p_$1.ncu-rep --page raw --csv > gpurun_out/prof_convpair_row_$1_r2.raw.csv 2>/dev/null
 done
-rm -f gpurun_out/conv_overlap_ab2.jsonl
-for ov in 4 0 8 0; do
- CPLXK_CONV_OVERLAP=$ov timeout 120 python tools/conv_bench.py --plain --fp32-nchw >> gpurun_out/conv_overlap_ab2.jsonl 2>gpurun_out/conv_overlap_ab2.err
-done
-cat gpurun_out/conv_overlap_ab2.jsonl
+ls -la gpurun_out/*.raw.csv | tail -3
