@@ -51,6 +51,8 @@ const Knobs& knobs() {
     v.conv_pair = env_int("CPLXK_CONV_PAIR", 1) != 0;
     v.conv_persistent = env_int("CPLXK_CONV_NONPERSISTENT", 0) != 1;
     v.conv_row = env_int("CPLXK_CONV_ROW", 1) != 0;
+    v.combine_flat = env_int("CPLXK_COMBINE_FLAT", 1) != 0;
+    v.conv_real_pair = env_int("CPLXK_CONV_REAL_PAIR", 1) != 0;
     v.conv_overlap = env_int("CPLXK_CONV_OVERLAP", 4);
     v.conv_amax_pass = env_int("CPLXK_CONV_AMAX_PASS", 0) == 1;
     v.pdl = env_int("CPLXK_PDL", 1) != 0;

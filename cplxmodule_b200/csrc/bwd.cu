@@ -269,6 +269,44 @@ vd_combine_torch_kernel(T* __restrict__ y_re, T* __restrict__ y_im, const T* __r
   }
 }
 
+// Complex planes, flat form: torch draws the 2 MN normals of a complex tensor as ONE stream (real
+// plane first, cplx.py:544-550), so a thread may simply own one Philox call of that stream and add
+// its four normals wherever they land -- real or imaginary plane.  Two calls and four Box-Muller
+// evaluations per four complex outputs (the minimum; the form above needs three and five to six,
+// plus the component selects), paid for with a second read of s2 (the two planes of one element are
+// MN normals apart in the stream).
+template <typename T>
+__global__ void __launch_bounds__(256)
+vd_combine_torch_flat_kernel(T* __restrict__ y_re, T* __restrict__ y_im, const T* __restrict__ s2,
+                             int64_t MN, uint64_t calls, NoiseParams np) {
+  const uint32_t Tn = np.threads;
+  const PhiloxKey key{np.seed_lo, np.seed_hi};
+  const uint64_t total = static_cast<uint64_t>(Tn) * calls;
+  const uint64_t n2 = 2u * static_cast<uint64_t>(MN);
+  for (uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t c = t / Tn;
+    const uint32_t idx = static_cast<uint32_t>(t - c * Tn);
+    const uint64_t l0 = idx + static_cast<uint64_t>(Tn) * 4u * c;
+    if (l0 >= n2) continue;
+    const uint64_t ctr = np.ctr_base + c;
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), idx, 0u), key);
+    const float2 a = _curand_box_muller(r.x, r.y), b = _curand_box_muller(r.z, r.w);
+    const float n[4] = {a.x * np.scale, a.y * np.scale, b.x * np.scale, b.y * np.scale};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t l = l0 + static_cast<uint64_t>(Tn) * k;
+      if (l < n2) {
+        const bool im = l >= static_cast<uint64_t>(MN);
+        const uint64_t e = im ? l - static_cast<uint64_t>(MN) : l;
+        T* y = im ? y_im : y_re;
+        const float sd = sd_of(Elem<T>::to_f(s2[e]));
+        y[e] = Elem<T>::from_f(fmaf(n[k], sd, Elem<T>::to_f(y[e])));
+      }
+    }
+  }
+}
+
 // injected noise / the private `fast` layout of the conv kernels (one element per thread)
 template <typename T, bool kCplx>
 __global__ void __launch_bounds__(256)
@@ -608,9 +646,15 @@ extern "C" int cplxk_vd_combine(void* y_re, void* y_im, const void* s2, const vo
       const uint64_t calls = (static_cast<uint64_t>(numel) + 4 * Tn - 1) / (4 * Tn);
       const uint32_t r0 = static_cast<uint32_t>(static_cast<uint64_t>(numel) % Tn);
       const uint64_t q0 = static_cast<uint64_t>(numel) / Tn;
-      const int grid = ew_grid(static_cast<int64_t>(Tn * calls));
-      if (cplx) vd_combine_torch_kernel<T, true><<<grid, 256, 0, st>>>(yr, yi, v, numel, r0, q0, calls, np);
-      else vd_combine_torch_kernel<T, false><<<grid, 256, 0, st>>>(yr, yi, v, numel, r0, q0, calls, np);
+      if (cplx && knobs().combine_flat) {
+        const uint64_t calls2 = (2u * static_cast<uint64_t>(numel) + 4 * Tn - 1) / (4 * Tn);
+        vd_combine_torch_flat_kernel<T><<<ew_grid(static_cast<int64_t>(Tn * calls2)), 256, 0, st>>>(
+            yr, yi, v, numel, calls2, np);
+      } else {
+        const int grid = ew_grid(static_cast<int64_t>(Tn * calls));
+        if (cplx) vd_combine_torch_kernel<T, true><<<grid, 256, 0, st>>>(yr, yi, v, numel, r0, q0, calls, np);
+        else vd_combine_torch_kernel<T, false><<<grid, 256, 0, st>>>(yr, yi, v, numel, r0, q0, calls, np);
+      }
     } else {
       auto e1 = static_cast<const T*>(eps_re); auto e2 = static_cast<const T*>(eps_im);
       const int grid = ew_grid(numel);

@@ -1114,31 +1114,37 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_xr,
 // read them through shared-memory descriptors shifted by whole 128-byte pixel rows, so the
 // activation traffic L2 -> SM drops kw-fold
 // (at 40 KB per 512 MMA cycles the per-tap version sits on the ~64 B/clk per-SM L2 ingest limit).
-template <typename T, bool kHalf = false, bool kRow = false>
+// kReal: real planes (round 2): one activation plane, the pair's B operand is 128 REAL output
+// channels (rows [n0, n0+64) of the one weight plane in the leader, [n0+64, n0+128) in the peer),
+// one accumulator of 128 columns per TMEM half, one MMA per k-step.
+template <typename T, bool kHalf = false, bool kRow = false, bool kReal = false>
 struct ConvPairCfg {
   static_assert(!kHalf || std::is_same<T, float>::value, "fp16 operand copies: fp32 planes");
+  static_assert(!(kHalf && kReal), "real planes: tf32 / bf16 operands");
   static constexpr bool kBF16 = std::is_same<T, __nv_bfloat16>::value || kHalf;   // kind::f16
   static constexpr int BKC = kHalf ? 64 : 128 / static_cast<int>(sizeof(T));
   static constexpr int MAX_TAPS = kRow ? 3 : 1;           // taps served by one k-block
   static constexpr int MAX_HALO = 8;                      // (kw - 1) * dw pixels beyond the 128
   static constexpr int A_TILE = (kRow ? 128 + MAX_HALO : 128) * 128;
   static constexpr int B_TILE = 64 * 128;                 // this CTA's half of one tap's [U;V]
-  static constexpr int OFF_XR = 0, OFF_XI = A_TILE, OFF_UV = 2 * A_TILE;
-  static constexpr int STAGE_BYTES = 2 * A_TILE + MAX_TAPS * B_TILE;   // 40 KB / 58 KB
-  static constexpr int STAGES = kRow ? 3 : 5;
+  static constexpr int PLANES = kReal ? 1 : 2;
+  static constexpr int OFF_XR = 0, OFF_XI = A_TILE, OFF_UV = PLANES * A_TILE;
+  static constexpr int STAGE_BYTES = PLANES * A_TILE + MAX_TAPS * B_TILE;   // 40 KB / 58 KB (real: 24 / 41)
+  static constexpr int STAGES = kRow ? (kReal ? 4 : 3) : 5;
+  static constexpr int BN = kReal ? 128 : 64;             // output channels per n-block
   static constexpr int OFF_BIAS = 256;
   static constexpr int THREADS = 320;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + OFF_BIAS + 8 * 96 * 4;
 };
 
-template <typename T, bool kHalf = false, bool kRow = false>
+template <typename T, bool kHalf = false, bool kRow = false, bool kReal = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
                           const __grid_constant__ CUtensorMap tm_xi,
                           const __grid_constant__ CUtensorMap tm_u,
                           const __grid_constant__ CUtensorMap tm_v, const ConvTcGeom g,
                           const ConvTcEpi ep, const int total_tiles) {
-  using C = ConvPairCfg<T, kHalf, kRow>;
+  using C = ConvPairCfg<T, kHalf, kRow, kReal>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1192,6 +1198,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
       for (int item = cluster_id; item < items; item += num_clusters) {
         int b, oh0, ow0, n0;
         conv_tile_coords(g, item_tile(item), b, oh0, ow0, n0);   // b >= B for the odd tile out: OOB zero fill
+        if constexpr (kReal) n0 = 2 * n0 + (leader ? 0 : 64);   // 128-channel n-blocks, this CTA's 64 rows
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const uint32_t s = kbg % C::STAGES, ph = (kbg / C::STAGES) & 1u;
           ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
@@ -1202,15 +1209,15 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
             const int32_t c0 = cc * C::BKC;
             const int32_t iw = ow0 - g.pw;                       // sw == 1
             const int32_t ih = oh0 * g.sh - g.ph + r * g.dh;
-            const uint32_t tx = 2u * static_cast<uint32_t>(128 + (g.kw - 1) * g.dw) * 128u +
+            const uint32_t tx = C::PLANES * static_cast<uint32_t>(128 + (g.kw - 1) * g.dw) * 128u +
                                 static_cast<uint32_t>(g.kw) * C::B_TILE;
             if (elected) {
               if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * tx);   // both CTAs' bytes
               ptx::tma_load_4d_pair(st + C::OFF_XR, &tm_xr, fb, c0, iw, ih, b);
-              ptx::tma_load_4d_pair(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
+              if constexpr (!kReal) ptx::tma_load_4d_pair(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
               for (int sx = 0; sx < g.kw; ++sx)
-                ptx::tma_load_2d_pair(st + C::OFF_UV + sx * C::B_TILE, leader ? &tm_u : &tm_v, fb, c0,
-                                      (r * g.kw + sx) * g.Op + n0);
+                ptx::tma_load_2d_pair(st + C::OFF_UV + sx * C::B_TILE, (leader || kReal) ? &tm_u : &tm_v, fb,
+                                      c0, (r * g.kw + sx) * g.Op + n0);
             }
           } else {
             const int rs = kb / cchunks, cc = kb - rs * cchunks;
@@ -1222,9 +1229,10 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
             if (elected) {
               if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * C::STAGE_BYTES);   // both CTAs' bytes
               ptx::tma_load_4d_pair(st + C::OFF_XR, &tm_xr, fb, c0, iw, ih, b);
-              ptx::tma_load_4d_pair(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
+              if constexpr (!kReal) ptx::tma_load_4d_pair(st + C::OFF_XI, &tm_xi, fb, c0, iw, ih, b);
               // B = [U(64 rows); V(64 rows)] is split along N across the pair: U here, V in the peer
-              ptx::tma_load_2d_pair(st + C::OFF_UV, leader ? &tm_u : &tm_v, fb, c0, wrow);
+              // (real planes: the two 64-row halves of the n-block's 128 weight rows)
+              ptx::tma_load_2d_pair(st + C::OFF_UV, (leader || kReal) ? &tm_u : &tm_v, fb, c0, wrow);
             }
           }
           __syncwarp();
@@ -1265,7 +1273,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
                   const uint32_t acc = (kb > 0 || sx > 0 || k > 0) ? 1u : 0u;
                   const uint32_t off = k * 32;
                   ptx::umma_ss_pair<C::kBF16>(t_d1, ptx::desc_advance(a_r, off), ptx::desc_advance(b_uv, off), idesc, acc);
-                  ptx::umma_ss_pair<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc, acc);
+                  if constexpr (!kReal)
+                    ptx::umma_ss_pair<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc, acc);
                 }
               }
             }
@@ -1280,7 +1289,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
                 const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
                 const uint32_t off = k * 32;
                 ptx::umma_ss_pair<C::kBF16>(t_d1, ptx::desc_advance(a_r, off), ptx::desc_advance(b_uv, off), idesc, acc);
-                ptx::umma_ss_pair<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc, acc);
+                if constexpr (!kReal)
+                  ptx::umma_ss_pair<C::kBF16>(t_d2, ptx::desc_advance(a_i, off), ptx::desc_advance(b_uv, off), idesc, acc);
               }
               ptx::umma_commit_pair(bar_empty + 8 * s);
             }
@@ -1306,16 +1316,26 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
     for (int item = cluster_id; item < items; item += num_clusters, ++it) {
       int b, oh0, ow0, n0;
       conv_tile_coords(g, item_tile(item), b, oh0, ow0, n0);
+      if constexpr (kReal) n0 *= 2;                  // 128-channel n-blocks
       if (n0 != bias_n0) {
         __syncwarp();
-        const int o = n0 + half * 32 + lane;
-        float br = 0.f, bi = 0.f;
-        if (ep.b_re && o < g.O) {
-          br = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_re) + o));
-          bi = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_im) + o));
+        if constexpr (kReal) {
+          // this warp's 64 channels: half * 64 + [0, 64)
+          const int o = n0 + half * 64 + lane;
+          float b0 = 0.f, b1 = 0.f;
+          if (ep.b_re && o < g.O) b0 = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_re) + o));
+          if (ep.b_re && o + 32 < g.O) b1 = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_re) + o + 32));
+          sbias[lane] = b0, sbias[32 + lane] = b1;
+        } else {
+          const int o = n0 + half * 32 + lane;
+          float br = 0.f, bi = 0.f;
+          if (ep.b_re && o < g.O) {
+            br = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_re) + o));
+            bi = Elem<T>::to_f(__ldg(static_cast<const T*>(ep.b_im) + o));
+          }
+          sbias[lane] = br, sbias[32 + lane] = bi;
+          if constexpr (kHalf) sbias[64 + lane] = o < g.O ? __ldg(ep.isw + o) : 1.f;
         }
-        sbias[lane] = br, sbias[32 + lane] = bi;
-        if constexpr (kHalf) sbias[64 + lane] = o < g.O ? __ldg(ep.isw + o) : 1.f;
         __syncwarp();
         bias_n0 = n0;
       }
@@ -1329,6 +1349,23 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_xr,
       ptx::mbar_wait(bar_tfull + 8 * buf, tph);
       ptx::tcgen05_fence_after();
       const uint32_t lane_base = tmem_base + buf * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+      if constexpr (kReal) {
+        // one accumulator: columns [0, 128) = the n-block's real output channels; the next
+        // chunk's tcgen05.ld is in flight while this one is stored
+        uint32_t d[2][16];
+        ptx::tmem_ld_32x32b_x16(lane_base + half * 64, d[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col = half * 64 + c * 16;
+          ptx::tmem_ld_wait();
+          if (c < 3) ptx::tmem_ld_32x32b_x16(lane_base + col + 16, d[(c + 1) & 1]);
+          float v16[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v16[k] = __uint_as_float(d[c & 1][k]) + sbias[c * 16 + k];
+          if (pix_ok)
+            conv_store16<T>(static_cast<T*>(ep.y_re), g, ep.nhwc != 0, pix_off, hw, cl_off, n0 + col, v16);
+        }
+      } else
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int col = half * 32 + c * 16;
@@ -1485,7 +1522,7 @@ static bool conv_row_mode(const ConvTcGeom& g) {
 }
 static int conv_row_halo(const ConvTcGeom& g) { return conv_row_mode(g) ? (g.kw - 1) * g.dw : 0; }
 
-template <typename T, bool kHalf>
+template <typename T, bool kHalf, bool kReal = false>
 static int launch_conv_pair(const CUtensorMap& tm_xr, const CUtensorMap& tm_xi, const CUtensorMap& tm_u,
                             const CUtensorMap& tm_v, const ConvTcGeom& g, const ConvTcEpi& ep,
                             int64_t tiles, cudaStream_t st) {
@@ -1502,11 +1539,11 @@ static int launch_conv_pair(const CUtensorMap& tm_xr, const CUtensorMap& tm_xi, 
     return CPLXK_OK;
   };
   if (conv_row_mode(g)) {
-    using PC = ConvPairCfg<T, kHalf, true>;
-    return go(conv_tc_pair_kernel<T, kHalf, true>, PC::THREADS, PC::SMEM_BYTES);
+    using PC = ConvPairCfg<T, kHalf, true, kReal>;
+    return go(conv_tc_pair_kernel<T, kHalf, true, kReal>, PC::THREADS, PC::SMEM_BYTES);
   }
-  using PC = ConvPairCfg<T, kHalf, false>;
-  return go(conv_tc_pair_kernel<T, kHalf, false>, PC::THREADS, PC::SMEM_BYTES);
+  using PC = ConvPairCfg<T, kHalf, false, kReal>;
+  return go(conv_tc_pair_kernel<T, kHalf, false, kReal>, PC::THREADS, PC::SMEM_BYTES);
 }
 
 // Side stream of the chunked fp32 NCHW path (one per device, HIGHEST priority: it runs the
@@ -1883,6 +1920,18 @@ static int launch_conv_rg(const void* x_re, const void* x_im, const void* w_re, 
 
   CUtensorMap tm_xr, tm_xi, tm_q, tm_u, tm_v, tm_e;
   int rc;
+  if constexpr (kReal && !kVD) {
+    // ungrouped real planes: the persistent CTA-pair kernel (ConvPairCfg<.., kReal>; row mode for
+    // wide images) -- the one-tile-per-CTA kernel below pulls 32 KB per 256 MMA cycles through L2,
+    // twice what an SM can ingest
+    const int64_t pix_tiles = g.B * g.tiles_h * g.tiles_w;
+    if (g.groups == 1 && knobs().conv_real_pair && knobs().conv_persistent && knobs().conv_pair &&
+        pix_tiles >= 2) {
+      if ((rc = make_act_map<T>(&tm_xr, a_re, g, false, conv_row_halo(g)))) return rc;
+      if ((rc = make_w_map<T>(&tm_u, u, g))) return rc;
+      return launch_conv_pair<T, false, true>(tm_xr, tm_xr, tm_u, tm_u, g, ep, pix_tiles * g.tiles_n, st);
+    }
+  }
   if ((rc = make_act_map<T>(&tm_xr, a_re, g))) return rc;
   if ((rc = make_w_map<T>(&tm_u, u, g))) return rc;
   tm_xi = tm_xr, tm_v = tm_u, tm_q = tm_xr, tm_e = tm_u;

@@ -19,6 +19,8 @@ struct Knobs {
   bool conv_pair;          // CPLXK_CONV_PAIR=0: conv on single-CTA tiles
   bool conv_persistent;    // CPLXK_CONV_NONPERSISTENT=1: one conv tile per CTA
   bool conv_row;           // CPLXK_CONV_ROW=0: CTA-pair conv kernel loads every tap separately (no row mode)
+  bool combine_flat;       // CPLXK_COMBINE_FLAT=0: complex cplxk_vd_combine with the paired (three calls per four outputs) noise kernel
+  bool conv_real_pair;     // CPLXK_CONV_REAL_PAIR=0: ungrouped real-plane conv on the one-tile-per-CTA kernel
   int conv_overlap;        // CPLXK_CONV_OVERLAP: image chunks of the fp32 NCHW conv whose pre-pass overlaps the previous chunk's GEMM (0 / 1: serial)
   bool conv_amax_pass;     // CPLXK_CONV_AMAX_PASS=1: fp32 NCHW conv input: separate amax pass before the fp16 conversion (default: optimistic single pass + fix-up)
   bool pdl;                // CPLXK_PDL=0: no programmatic dependent launch between pre-pass and GEMM

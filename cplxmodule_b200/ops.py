@@ -55,10 +55,10 @@ def set_conv_vd_mode(mode):
       Philox call (three calls per four complex outputs) and adds ``eps * sqrt(max(s2, 1e-8))``;
     * ``"fused"``: the single kernel with three accumulators and the noise in its epilogue (no
       scratch planes; always used for channels-last inputs);
-    * ``"auto"`` (default): whichever measured faster on config-4-sized work
+    * ``"auto"`` (default): composed for NCHW planes.  Measured on config-4-sized work
       (``tools/convvd_probe.py``, 256 x 64 x 128^2, 3 x 3, 64 -> 64, torch-exact noise, ms composed /
-      fused): complex fp32 6.04 / 5.92 -> fused; complex bf16 4.58 / 5.44, real fp32 4.09 / 4.55,
-      real bf16 2.98 / 4.37 -> composed.
+      fused, after the plain kernels' row mode): complex fp32 5.12 / 5.83, complex bf16 4.09 / 5.49,
+      real fp32 3.36 / 4.74, real bf16 2.33 / 4.64.
     Same values either way (same noise stream, same tolerance)."""
     if mode not in ("auto", "composed", "fused"):
         raise ValueError("conv VD mode must be 'auto', 'composed' or 'fused'")
@@ -68,7 +68,7 @@ def set_conv_vd_mode(mode):
 def conv_vd_composed(cplx, dtype):
     mode = _state["conv_vd"]
     if mode == "auto":
-        return not (cplx and dtype == torch.float32)
+        return True
     return mode == "composed"
 
 

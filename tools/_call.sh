@@ -1,9 +1,7 @@
-timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_final2.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_final2.log
-timeout 300 python tools/config_bench.py > gpurun_out/configs_r2b.log 2>&1; echo "cfg rc=$?"; grep -c config gpurun_out/configs_r2b.log
-timeout 400 python bench.py > gpurun_out/bench_final2.json 2> gpurun_out/bench_final2.err; echo "bench rc=$?"; cut -c1-400 gpurun_out/bench_final2.json
-for v in "f32 nchw" "bf16 nhwc"; do
- set -- $v
- timeout 200 ncu --set full --clock-control none -k regex:conv_tc_pair -s 2 -c 1 -o /tmp/p_$1 -f python tools/prof_conv.py 4 $1 $2 > /tmp/p.log 2>&1
- ncu -i /tmp/p_$1.ncu-rep --page raw --csv > gpurun_out/prof_convpair_row_$1_r2.raw.csv 2>/dev/null
+timeout 400 python -m pytest tests/test_gpu_conv_rg.py tests/test_gpu_conv.py tests/test_gpu_backward.py tests/test_gpu_rows_f.py tests/test_gpu_graph.py tests/test_gpu_edge_cases.py -m gpu -q -x > gpurun_out/pytest_flat.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/pytest_flat.log
+rm -f gpurun_out/convvd_flat_ab.jsonl
+for f in 1 0 1 0; do
+ echo "{\"CPLXK_COMBINE_FLAT\": $f}" >> gpurun_out/convvd_flat_ab.jsonl
+ CPLXK_COMBINE_FLAT=$f timeout 200 python tools/convvd_probe.py 2>&1 | head -2 >> gpurun_out/convvd_flat_ab.jsonl
 done
-ls -la gpurun_out/*.raw.csv | tail -3
+cat gpurun_out/convvd_flat_ab.jsonl
