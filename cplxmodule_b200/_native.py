@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("CPLXK_LIB") or os.path.join(_HERE, "csrc", "libcplxk.
 F32, BF16 = 0, 1
 MATH_AUTO, MATH_TENSOR, MATH_SIMT, MATH_TENSOR_TF32 = 0, 1, 2, 3
 NOISE_INJECT, NOISE_PHILOX_TORCH, NOISE_PHILOX_FAST = 0, 1, 2
-ERR_UNSUPPORTED = -5
+ERR_UNSUPPORTED, ERR_WORKSPACE = -5, -6
 KL_REAL_VD, KL_REAL_ARD, KL_CPLX_VD, KL_CPLX_ARD = 0, 1, 2, 3
 KL_CPLX_VD_APPROX, KL_CPLX_VD_SCALEFREE = 4, 5        # nn/relevance/extensions/complex.py
 

@@ -278,9 +278,11 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
         y_re = y_im = None
         y_re, y_im, _ = _conv2d_raw(xr, xi, wr, wi, br, bi, None, None, None, nv.NOISE_INJECT, geom, groups)
         E = ops._eltwise(ops.TR_EXP, l2)
-        q = ops._eltwise(ops.TR_ABS2, xr, xi) if cplx else ops._eltwise(ops.TR_SQR, xr)
-        s2, _, _ = _conv2d_raw(q, None, E, None, None, None, None, None, None, nv.NOISE_INJECT, geom, groups)
-        del q
+        s2 = _variance_conv2d(xr, xi, E, geom, groups) if cplx else None
+        if s2 is None:
+            q = ops._eltwise(ops.TR_ABS2, xr, xi) if cplx else ops._eltwise(ops.TR_SQR, xr)
+            s2, _, _ = _conv2d_raw(q, None, E, None, None, None, None, None, None, nv.NOISE_INJECT, geom, groups)
+            del q
         with nv.device_guard(dev):
             nv.check(nv.lib().cplxk_vd_combine(
                 nv.ptr(y_re), nv.ptr(y_im), nv.ptr(s2), nv.ptr(er), nv.ptr(ei), mode, seed, offset,
@@ -318,6 +320,35 @@ def _conv2d_raw(x_re, x_im, w_re, w_im, b_re, b_im, ls2, eps_re, eps_im, noise, 
     if mode != nv.NOISE_INJECT:
         nv.philox_advance(gen, offset, inc)
     return y_re, y_im, {"philox": (seed, offset, threads), "eps_re": er, "eps_im": ei}
+
+
+def _variance_conv2d(x_re, x_im, E, geom, groups):
+    """s2 = conv(|x_re + i x_im|^2, E) in ONE C-ABI call: the real-plane tensor-core kernel whose
+    transposing pre-pass squares the input on the way (no |x|^2 plane is written or re-read;
+    ``cplxk_conv2d_fwd_g`` with an imaginary input plane but real weights and output).  Returns None
+    where that form is not available (geometry / alignment), the caller then forms |x|^2 itself.
+    Reference: ``F.conv(abs(input)**2, exp(log_sigma2))``, nn/relevance/complex/base.py:100-117."""
+    stride, padding, dilation = geom
+    dev, dt = x_re.device, E.dtype
+    B, C, H, W = x_re.shape
+    O, _, kh, kw = E.shape
+    Ho, Wo = _out_hw(x_re, E, geom)
+    if ops._MATH[ops.get_math_mode()] == nv.MATH_SIMT or min(B, O, Ho, Wo) <= 0:
+        return None
+    code = nv.dtype_code(dt)
+    ws_bytes = nv.lib().cplxk_conv2d_workspace_bytes_g(B, C, H, W, O, kh, kw, groups, 0, code, 0)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    s2 = torch.empty((B, O, Ho, Wo), dtype=dt, device=dev)
+    with nv.device_guard(dev):
+        rc = nv.lib().cplxk_conv2d_fwd_g(
+            nv.ptr(x_re), nv.ptr(x_im), nv.ptr(E), None, None, None, None, None, None, nv.NOISE_INJECT,
+            0, 0, 0, nv.ptr(s2), None, B, C, H, W, O, kh, kw, stride[0], stride[1], padding[0],
+            padding[1], dilation[0], dilation[1], groups, code, nv.MATH_TENSOR, 0, nv.ptr(ws), ws_bytes,
+            nv.stream_ptr(dev))
+    if rc in (nv.ERR_UNSUPPORTED, nv.ERR_WORKSPACE):
+        return None
+    nv.check(rc)
+    return s2
 
 
 def _out_hw(x, w, geom):

@@ -279,16 +279,15 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 vd_combine_torch_flat_kernel(T* __restrict__ y_re, T* __restrict__ y_im, const T* __restrict__ s2,
                              int64_t MN, uint64_t calls, NoiseParams np) {
+  // grid: x over torch's Tn generator threads, y (strided) over the Philox calls -- no division
   const uint32_t Tn = np.threads;
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Tn) return;
   const PhiloxKey key{np.seed_lo, np.seed_hi};
-  const uint64_t total = static_cast<uint64_t>(Tn) * calls;
   const uint64_t n2 = 2u * static_cast<uint64_t>(MN);
-  for (uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
-       t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    const uint64_t c = t / Tn;
-    const uint32_t idx = static_cast<uint32_t>(t - c * Tn);
+  for (uint64_t c = blockIdx.y; c < calls; c += gridDim.y) {
     const uint64_t l0 = idx + static_cast<uint64_t>(Tn) * 4u * c;
-    if (l0 >= n2) continue;
+    if (l0 >= n2) return;
     const uint64_t ctr = np.ctr_base + c;
     const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), idx, 0u), key);
     const float2 a = _curand_box_muller(r.x, r.y), b = _curand_box_muller(r.z, r.w);
@@ -648,8 +647,8 @@ extern "C" int cplxk_vd_combine(void* y_re, void* y_im, const void* s2, const vo
       const uint64_t q0 = static_cast<uint64_t>(numel) / Tn;
       if (cplx && knobs().combine_flat) {
         const uint64_t calls2 = (2u * static_cast<uint64_t>(numel) + 4 * Tn - 1) / (4 * Tn);
-        vd_combine_torch_flat_kernel<T><<<ew_grid(static_cast<int64_t>(Tn * calls2)), 256, 0, st>>>(
-            yr, yi, v, numel, calls2, np);
+        const dim3 fg(static_cast<unsigned>((Tn + 255) / 256), static_cast<unsigned>(calls2 < 65535 ? calls2 : 65535));
+        vd_combine_torch_flat_kernel<T><<<fg, 256, 0, st>>>(yr, yi, v, numel, calls2, np);
       } else {
         const int grid = ew_grid(static_cast<int64_t>(Tn * calls));
         if (cplx) vd_combine_torch_kernel<T, true><<<grid, 256, 0, st>>>(yr, yi, v, numel, r0, q0, calls, np);

@@ -218,10 +218,14 @@ extern "C" int cplxk_conv2d_fwd_g(const void* x_re, const void* x_im, const void
   if (B == 0 || O == 0) return CPLXK_OK;     // empty batch / layer (pointers may be null)
   if (!x_re || !w_re || !y_re) return CPLXK_ERR_BADARG;
   if (groups < 1 || groups > 0x7fffffff || C % groups || O % groups) return CPLXK_ERR_BADARG;
-  const bool cplx = x_im != nullptr;
+  // x_im with REAL weights and output: the real convolution of |x_re + i x_im|^2 (variance operand of
+  // a complex variational layer; squared inside the transposing pre-pass, tensor-core path only)
+  const bool abs2 = x_im != nullptr && w_im == nullptr && y_im == nullptr;
+  const bool cplx = x_im != nullptr && !abs2;
   if (cplx != (w_im != nullptr) || cplx != (y_im != nullptr)) return CPLXK_ERR_BADARG;
   if (b_re && cplx && !b_im) return CPLXK_ERR_BADARG;
   const bool vd = log_sigma2 != nullptr;
+  if (abs2 && (vd || channels_last || !aligned16(x_im))) return CPLXK_ERR_UNSUPPORTED;
   if (vd) {
     if (noise < CPLXK_NOISE_INJECT || noise > CPLXK_NOISE_PHILOX_FAST) return CPLXK_ERR_BADARG;
     if (noise == CPLXK_NOISE_INJECT && (!eps_re || (cplx && !eps_im))) return CPLXK_ERR_BADARG;
@@ -271,8 +275,9 @@ extern "C" int cplxk_conv2d_fwd_g(const void* x_re, const void* x_im, const void
     te.nhwc = channels_last ? 1 : 0;
     te.f16_ok = math != CPLXK_MATH_TENSOR_TF32;
     return conv_tc_dispatch(dtype, vd, channels_last != 0, x_re, x_im, w_re, w_im, log_sigma2, workspace, B, C, H, W, O,
-                            g.Ho, g.Wo, g.kh, g.kw, g.sh, g.sw, g.ph, g.pw, g.dh, g.dw, te, st, ng);
+                            g.Ho, g.Wo, g.kh, g.kw, g.sh, g.sw, g.ph, g.pw, g.dh, g.dw, te, st, ng, abs2);
   }
+  if (abs2) return CPLXK_ERR_UNSUPPORTED;
   // the exact-fp32 CUDA-core kernel covers one group per launch: the caller loops
   if (ng > 1) return CPLXK_ERR_UNSUPPORTED;
 #define CPLXK_CONV_CASE(T)                                                                  \

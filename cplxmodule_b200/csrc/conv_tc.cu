@@ -85,7 +85,7 @@ conv_nhwc_kernel(const T* __restrict__ x_re, const T* __restrict__ x_im, T* __re
 __global__ void __launch_bounds__(256)
 conv_nhwc_bf16_v8_kernel(const __nv_bfloat16* __restrict__ x_re, const __nv_bfloat16* __restrict__ x_im,
                          __nv_bfloat16* __restrict__ o_re, __nv_bfloat16* __restrict__ o_im, int C,
-                         int Cp, int H, int W) {
+                         int Cp, int H, int W, bool abs2 = false) {
   __shared__ __nv_bfloat16 s_re[64][66], s_im[64][66];
   const int tid = threadIdx.x;
   const int w0 = blockIdx.z * 64, c0 = blockIdx.y * 64;
@@ -105,8 +105,16 @@ conv_nhwc_bf16_v8_kernel(const __nv_bfloat16* __restrict__ x_re, const __nv_bflo
     }
     const __nv_bfloat16* pr = reinterpret_cast<const __nv_bfloat16*>(&vr);
     const __nv_bfloat16* pi = reinterpret_cast<const __nv_bfloat16*>(&vi);
+    if (abs2) {      // variance operand |x|^2 = x_re^2 + x_im^2 of a complex input (o_im == nullptr)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s_re[cl][8 * q + j] = pr[j], s_im[cl][8 * q + j] = pi[j];
+      for (int j = 0; j < 8; ++j) {
+        const float a = __bfloat162float(pr[j]), c2 = __bfloat162float(pi[j]);
+        s_re[cl][8 * q + j] = __float2bfloat16_rn(fmaf(a, a, c2 * c2));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_re[cl][8 * q + j] = pr[j], s_im[cl][8 * q + j] = pi[j];
+    }
   }
   __syncthreads();
   const int tx = tid & 31, ty = tid >> 5;
@@ -130,7 +138,8 @@ conv_nhwc_bf16_v8_kernel(const __nv_bfloat16* __restrict__ x_re, const __nv_bflo
 // (real planes).  W % 4 == 0, 16-byte aligned planes, Cp % 2 == 0.
 __global__ void __launch_bounds__(256)
 conv_nhwc_f32_v4_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im,
-                        float* __restrict__ o_re, float* __restrict__ o_im, int C, int Cp, int H, int W) {
+                        float* __restrict__ o_re, float* __restrict__ o_im, int C, int Cp, int H, int W,
+                        bool abs2 = false) {
   __shared__ float s_re[64][65], s_im[64][65];
   const int tid = threadIdx.x;
   const int w0 = blockIdx.z * 64, c0 = blockIdx.y * 64;
@@ -146,6 +155,10 @@ conv_nhwc_f32_v4_kernel(const float* __restrict__ x_re, const float* __restrict_
       const int64_t off = ((b * C + c) * H + h) * W + w;
       vr = __ldg(reinterpret_cast<const float4*>(x_re + off));
       if (x_im) vi = __ldg(reinterpret_cast<const float4*>(x_im + off));
+    }
+    if (abs2) {      // variance operand |x|^2 of a complex input (o_im == nullptr)
+      vr.x = fmaf(vr.x, vr.x, vi.x * vi.x), vr.y = fmaf(vr.y, vr.y, vi.y * vi.y);
+      vr.z = fmaf(vr.z, vr.z, vi.z * vi.z), vr.w = fmaf(vr.w, vr.w, vi.w * vi.w);
     }
     s_re[cl][4 * q] = vr.x, s_re[cl][4 * q + 1] = vr.y, s_re[cl][4 * q + 2] = vr.z, s_re[cl][4 * q + 3] = vr.w;
     s_im[cl][4 * q] = vi.x, s_im[cl][4 * q + 1] = vi.y, s_im[cl][4 * q + 2] = vi.z, s_im[cl][4 * q + 3] = vi.w;
@@ -1864,7 +1877,7 @@ static int launch_conv_tc(const void* x_re, const void* x_im, const void* w_re, 
 template <typename T, bool kVD, bool kReal>
 static int launch_conv_rg(const void* x_re, const void* x_im, const void* w_re, const void* w_im,
                           const void* ls2, void* workspace, const ConvTcGeom& g, const ConvTcEpi& ep,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool abs2 = false) {
   using C = ConvCfg<T, kVD, kReal>;
   if (ep.nhwc) return CPLXK_ERR_UNSUPPORTED;
   const size_t es = sizeof(T);
@@ -1892,7 +1905,7 @@ static int launch_conv_rg(const void* x_re, const void* x_im, const void* w_re, 
               static_cast<unsigned>((g.W + 63) / 64));
       conv_nhwc_bf16_v8_kernel<<<t8, 256, 0, st>>>(static_cast<const T*>(x_re), static_cast<const T*>(x_im),
                                                    a_re, a_im, static_cast<int>(g.C), g.Cp,
-                                                   static_cast<int>(g.H), static_cast<int>(g.W));
+                                                   static_cast<int>(g.H), static_cast<int>(g.W), abs2);
       done = true;
     }
   }
@@ -1903,10 +1916,11 @@ static int launch_conv_rg(const void* x_re, const void* x_im, const void* w_re, 
               static_cast<unsigned>((g.W + 63) / 64));
       conv_nhwc_f32_v4_kernel<<<t4, 256, 0, st>>>(static_cast<const float*>(x_re), static_cast<const float*>(x_im),
                                                   a_re, a_im, static_cast<int>(g.C), g.Cp,
-                                                  static_cast<int>(g.H), static_cast<int>(g.W));
+                                                  static_cast<int>(g.H), static_cast<int>(g.W), abs2);
       done = true;
     }
   }
+  if (abs2 && !done) return CPLXK_ERR_UNSUPPORTED;    // |x|^2 is formed by the 16-byte-load transposers only
   if (!done)
     conv_nhwc_kernel<T, kVD><<<tg, 256, 0, st>>>(static_cast<const T*>(x_re), static_cast<const T*>(x_im),
                                                  a_re, a_im, a_q, static_cast<int>(g.C), g.Cp,
@@ -1956,17 +1970,18 @@ int conv_tc_dispatch(int dtype, bool vd, bool nhwc, const void* x_re, const void
                      const void* w_im, const void* ls2, void* workspace, int64_t B, int64_t C,
                      int64_t H, int64_t W, int64_t O, int64_t Ho, int64_t Wo, int kh, int kw, int sh,
                      int sw, int ph, int pw, int dh, int dw, const ConvTcEpi& ep_in, cudaStream_t st,
-                     int groups) {
+                     int groups, bool abs2) {
   ConvTcEpi ep = ep_in;
   ep.nhwc = nhwc ? 1 : 0;
-  const bool real = x_im == nullptr;
+  const bool real = x_im == nullptr || abs2;      // abs2: real conv of |x_re + i x_im|^2
+  if (abs2 && (vd || nhwc)) return CPLXK_ERR_UNSUPPORTED;
   ConvTcGeom g{};
   g.B = B, g.C = C, g.H = H, g.W = W, g.O = O, g.Ho = Ho, g.Wo = Wo;
   g.kh = kh, g.kw = kw, g.sh = sh, g.sw = sw, g.ph = ph, g.pw = pw, g.dh = dh, g.dw = dw;
   conv_tc_plan(g, dtype, groups, real);
 #define CPLXK_RG(T)                                                                                       \
   if (real && vd) return launch_conv_rg<T, true, true>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st);   \
-  if (real) return launch_conv_rg<T, false, true>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st);        \
+  if (real) return launch_conv_rg<T, false, true>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st, abs2);  \
   if (g.groups > 1 && vd) return launch_conv_rg<T, true, false>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st); \
   if (g.groups > 1) return launch_conv_rg<T, false, false>(x_re, x_im, w_re, w_im, ls2, workspace, g, ep, st);
   if (dtype == CPLXK_F32) {

@@ -43,11 +43,12 @@ size_t conv_tc_workspace_bytes(int dtype, bool vd, int64_t B, int64_t C, int64_t
                                int64_t O, int64_t kh, int64_t kw, int groups = 1, bool real = false);
 bool conv_tc_supported(int dtype, int64_t B, int64_t C, int64_t H, int64_t W, int64_t O, int64_t Ho,
                        int64_t Wo, int kh, int kw, int sh, int sw, int groups = 1, bool real = false);
-// x_im == nullptr: real planes (w_im, y_im, b_im, eps_im unused)
+// x_im == nullptr: real planes (w_im, y_im, b_im, eps_im unused); abs2: real conv of |x_re + i x_im|^2
+// (the variance operand of a complex variational layer, squared inside the transposing pre-pass)
 int conv_tc_dispatch(int dtype, bool vd, bool nhwc, const void* x_re, const void* x_im, const void* w_re,
                      const void* w_im, const void* ls2, void* workspace, int64_t B, int64_t C,
                      int64_t H, int64_t W, int64_t O, int64_t Ho, int64_t Wo, int kh, int kw, int sh,
                      int sw, int ph, int pw, int dh, int dw, const ConvTcEpi& ep, cudaStream_t st,
-                     int groups = 1);
+                     int groups = 1, bool abs2 = false);
 
 }  // namespace cplxk

@@ -327,6 +327,11 @@ int cplxk_log_alpha(const void* w_re, const void* w_im, const void* log_sigma2,
  *     Without a workspace, or for geometries outside the TMA box limits, the exact-fp32
  *     CUDA-core kernel runs (groups == 1 only: CPLXK_ERR_UNSUPPORTED otherwise, the caller
  *     then issues one call per group).
+ *   Variance operand of the complex variational layers (F.conv(abs(input)**2, exp(log_sigma2)),
+ *   complex/base.py:100-117): x_im given with w_im == y_im == NULL is the REAL convolution of
+ *   |x_re + i x_im|^2 with w_re -- the square is formed inside the transposing pre-pass, no
+ *   |x|^2 plane is written.  Tensor-core path only (workspace of the real-plane size, NCHW planes
+ *   with W % 8 == 0 (bf16) / W % 4 == 0 (fp32), not variational): CPLXK_ERR_UNSUPPORTED otherwise.
  */
 size_t cplxk_conv2d_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t O,
                                     int64_t kh, int64_t kw, int dtype, int variational);

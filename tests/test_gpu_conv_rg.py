@@ -256,3 +256,35 @@ def test_conv_vd_modes_agree_with_oracle_and_each_other(mode, cplx_, dt):
         want = (orc.real_conv2d_vd(c64(x), c64(w), c64(b), c64(m.log_sigma2), c64(eps.to(dt)), (1, 2), 1, 1, 1),)
     for a, r in zip(planes(out), want):
         assert rel_err(f32(a), r) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_variance_conv_squares_the_input_in_the_prepass(dtype):
+    """s2 = conv(|x|^2, exp(log_sigma2)) of the complex variational layers in ONE call: the real-plane
+    kernel's transposing pre-pass forms x_re^2 + x_im^2 (cplxk_conv2d_fwd_g with x_im but real weights
+    and output) -- against float64 F.conv2d, against the two-step form, and the fall-back (None) for a
+    width the 16-byte-load transposers cannot take.  Reference: complex/base.py:100-117."""
+    from cplxmodule_b200 import conv_ops
+    torch.manual_seed(3)
+    B, C, H, W, O = 3, 32, 11, 136, 40
+    xr, xi = torch.randn(B, C, H, W, device=DEV).to(dtype), torch.randn(B, C, H, W, device=DEV).to(dtype)
+    E = torch.rand(O, C, 3, 3, device=DEV).to(dtype)
+    geom = ((1, 1), (1, 1), (1, 1))
+    s2 = conv_ops._variance_conv2d(xr, xi, E, geom, 1)
+    assert s2 is not None and s2.shape == (B, O, H, W)
+    c = lambda t: t.detach().double().cpu()
+    want = F.conv2d(c(xr) ** 2 + c(xi) ** 2, c(E), padding=1)
+    tol = 1e-3 if dtype == torch.float32 else 1e-2
+    assert rel_err(s2.float(), want) < tol
+    q = (xr.float() ** 2 + xi.float() ** 2).to(dtype)
+    two_step, _, _ = conv_ops._conv2d_raw(q, None, E, None, None, None, None, None, None, 0, geom, 1)
+    assert rel_err(s2.float(), two_step.float().cpu()) < tol
+    # groups, stride, a narrow image (several rows per tile)
+    xr2, xi2 = xr[:, :, :, :40].contiguous(), xi[:, :, :, :40].contiguous()
+    Eg = torch.rand(O, C // 2, 3, 3, device=DEV).to(dtype)
+    geom2 = ((2, 1), (0, 1), (1, 1))
+    s2g = conv_ops._variance_conv2d(xr2, xi2, Eg, geom2, 2)
+    want = F.conv2d(c(xr2) ** 2 + c(xi2) ** 2, c(Eg), stride=(2, 1), padding=(0, 1), groups=2)
+    assert s2g is not None and rel_err(s2g.float(), want) < tol
+    # W % 4 != 0: not available, the caller forms |x|^2 itself
+    assert conv_ops._variance_conv2d(xr[..., :37].contiguous(), xi[..., :37].contiguous(), E, geom, 1) is None
