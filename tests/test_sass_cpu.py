@@ -82,3 +82,16 @@ def test_real_and_grouped_conv_variants_are_built(sass):
 def test_guard_and_fingerprint_kernels_exist(sass):
     assert any("kl_guard_kernel" in k for k in sass), "kl_guard_kernel missing"
     assert any("vd_grad_s2_torch_kernel" in k for k in sass), "vd_grad_s2_torch_kernel missing"
+
+
+def test_pair_conv_kernel_variants_are_built(sass):
+    """conv_tc_pair_kernel<T, half operands, row mode, real planes>: complex bf16 / tf32 / scaled-fp16
+    and real bf16 / tf32, each with per-tap and per-row activation loads -- ten cta_group::2 kernels;
+    a row-mode instantiation issues its taps from one loaded tile (no extra TMA opcode per tap)."""
+    names = kernels_of(sass, "conv_tc_pair_kernel")
+    assert len(names) == 10, sorted(names)
+    row = [k for k in names if re.search(r"Lb[01]ELb1ELb[01]EEEv", k)]
+    real = [k for k in names if re.search(r"Lb[01]ELb[01]ELb1EEEv", k)]
+    assert len(row) == 5 and len(real) == 4, (row, real)
+    assert any("vd_combine_torch_flat_kernel" in k for k in sass), "flat noise kernel missing"
+    assert sum("conv_nhwc_f16_v4_kernel" in k for k in sass) == 3, "optimistic / fix-up conversion kernels"
