@@ -19,6 +19,7 @@ Legs of the default run (rank 0 prints them all in the one line):
   cpu_baseline       one full step of the reference's own CPU path on the host cores
   torch_eager_gpu    the UNMODIFIED reference executed on this GPU through torch eager
   extra.config5      CplxLinearARD 8192x8192 on 8192 rows per GPU (BASELINE.json configs[4])
+  extra.config4      CplxConv2d 64->64 3x3 on 256x64x128x128, fp32 NCHW and bf16 channels-last (configs[3])
 `--impl reference` times the unmodified reference (baseline/_ref) on the host cores, every step
 the FULL headline step.
 """
@@ -728,6 +729,14 @@ def run_ours(args, rank, local_rank, world):
         }
         torch.cuda.empty_cache()
 
+    if args.config == 3 and not args.no_extra and args.dtype == "f32" and world == 1:
+        # BASELINE.json configs[3]: CplxConv2d 64 -> 64, 3x3, 256 x 64 x 128 x 128 on one GPU
+        try:
+            extra["config4"] = conv_config4_leg(dev)
+        except Exception as exc:  # noqa: BLE001 -- an extra line, never the headline
+            extra["config4"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+        torch.cuda.empty_cache()
+
     eager = None
     if world == 1 and not args.no_eager and rank == 0:
         try:
@@ -888,6 +897,48 @@ def run_ours(args, rank, local_rank, world):
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def conv_config4_leg(dev, iters=10, warm=3):
+    """BASELINE.json configs[3] (CplxConv2d 64 -> 64 ch, 3x3, 128x128 input, batch 256): fp32 NCHW planes
+    (torch's default layout; per-image scaled fp16 operands) and bf16 channels-last, CUDA events, warm;
+    image 0 of the fp32 result against the float64 oracle.  1.199 TFLOP, 4.23 GB (fp32) per call."""
+    from cplxmodule_b200 import cplx as cx
+    from cplxmodule_b200.nn import CplxConv2d
+    from oracle import cplx_oracle as orc
+    torch.manual_seed(4)
+    flops = 8.0 * 256 * 64 * 126 * 126 * 64 * 9
+    out = {"workload": "CplxConv2d 64->64 3x3 on 256x64x128x128 (BASELINE.json configs[3])",
+           "algorithmic_tflop": flops / 1e12}
+    with torch.no_grad():
+        conv = CplxConv2d(64, 64, 3).to(dev)
+        z = cx.randn(256, 64, 128, 128, device=dev)
+        for tag, c, inp in (("fp32_nchw", conv, z), ("bf16_channels_last", None, None)):
+            if c is None:
+                c = conv.to(torch.bfloat16)
+                inp = cx.Cplx(z.real.to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
+                              z.imag.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+            for _ in range(warm):
+                y = c(inp)
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                y = c(inp)
+            b.record()
+            torch.cuda.synchronize(dev)
+            ms = a.elapsed_time(b) / iters
+            out[tag] = {"ms": ms, "tflops": flops / (ms / 1e3) / 1e12, "images_per_s": 256 / (ms / 1e3)}
+            if tag == "fp32_nchw":
+                cpu = lambda t: t.detach().double().cpu()
+                want = orc.cplx_conv2d(cpu(z.real[:1]), cpu(z.imag[:1]), cpu(conv.weight.real), cpu(conv.weight.imag),
+                                       cpu(conv.bias.real), cpu(conv.bias.imag))
+                err = max(float((cpu(y.real[:1]) - want[0]).abs().max() / want[0].abs().max()),
+                          float((cpu(y.imag[:1]) - want[1]).abs().max() / want[1].abs().max()))
+                out[tag]["rel_err_image0_vs_oracle"] = err
+                out[tag]["tol"] = 1e-3
+            del y
+    return out
 
 
 def main():
