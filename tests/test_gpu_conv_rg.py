@@ -288,3 +288,21 @@ def test_variance_conv_squares_the_input_in_the_prepass(dtype):
     assert s2g is not None and rel_err(s2g.float(), want) < tol
     # W % 4 != 0: not available, the caller forms |x|^2 itself
     assert conv_ops._variance_conv2d(xr[..., :37].contiguous(), xi[..., :37].contiguous(), E, geom, 1) is None
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("O,W", [(8, 140), (40, 140), (64, 200), (64, 30), (24, 30), (72, 140)])
+def test_real_conv_pair_kernel_channel_blocks(O, W, dtype, tensor_only):
+    """Ungrouped real planes on the CTA-pair kernel (128-channel n-blocks: layers with fewer output
+    channels multiply zero-padded weight rows and store only their own channels; 72 -> one block, the
+    second half mostly padding): wide images (one output row per tile: row mode) and narrow ones
+    (several rows per tile), bias, vs float64 F.conv2d."""
+    torch.manual_seed(O + W)
+    B, C, H = 3, 24, 9
+    x = torch.randn(B, C, H, W, device=DEV).to(dtype)
+    w = (torch.randn(O, C, 3, 3, device=DEV) / 8).to(dtype)
+    b = torch.randn(O, device=DEV).to(dtype)
+    y = conv_ops.real_convnd(2, x, w, b, padding=1)
+    want = F.conv2d(c64(x), c64(w), c64(b), padding=1)
+    assert y.shape == want.shape
+    assert rel_err(y.float(), want) < (1e-3 if dtype == torch.float32 else 1e-2)
