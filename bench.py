@@ -903,6 +903,7 @@ def conv_config4_leg(dev, iters=10, warm=3):
     """BASELINE.json configs[3] (CplxConv2d 64 -> 64 ch, 3x3, 128x128 input, batch 256): fp32 NCHW planes
     (torch's default layout; per-image scaled fp16 operands) and bf16 channels-last, CUDA events, warm;
     image 0 of the fp32 result against the float64 oracle.  1.199 TFLOP, 4.23 GB (fp32) per call."""
+    import torch
     from cplxmodule_b200 import cplx as cx
     from cplxmodule_b200.nn import CplxConv2d
     from oracle import cplx_oracle as orc

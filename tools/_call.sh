@@ -1,7 +1,5 @@
-timeout 400 python -m pytest tests/test_gpu_conv_rg.py tests/test_gpu_conv.py tests/test_gpu_backward.py -m gpu -q -x > gpurun_out/pytest_narrow.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/pytest_narrow.log
-rm -f gpurun_out/conv_real_narrow_ab.jsonl
-for nr in 1 0 1 0; do
- CPLXK_CONV_REAL_NARROW=$nr timeout 200 python tools/conv_real_ab.py >> gpurun_out/conv_real_narrow_ab.jsonl 2>gpurun_out/conv_real_narrow_ab.err
-done
-cat gpurun_out/conv_real_narrow_ab.jsonl | cut -c60-
-timeout 200 python tools/convvd_probe.py 2>&1 | head -4
+timeout 600 python -m pytest tests -m gpu -q > gpurun_out/pytest_final3.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_final3.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 300 python tools/config_bench.py > gpurun_out/configs_r2c.log 2>&1; echo "cfg rc=$?"
+timeout 400 python bench.py > gpurun_out/bench_final3.json 2> gpurun_out/bench_final3.err; echo "bench rc=$?"; python -c "
+import json;d=json.loads(open('gpurun_out/bench_final3.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['roofline']['frac'],d['e2e']['value'],d['parity']['ok'],json.dumps(d['extra'].get('config4')))"
