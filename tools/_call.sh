@@ -1,5 +1,5 @@
-timeout 600 python -m pytest tests -m gpu -q > gpurun_out/pytest_final3.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_final3.log
-timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 300 python tools/config_bench.py > gpurun_out/configs_r2c.log 2>&1; echo "cfg rc=$?"
-timeout 400 python bench.py > gpurun_out/bench_final3.json 2> gpurun_out/bench_final3.err; echo "bench rc=$?"; python -c "
-import json;d=json.loads(open('gpurun_out/bench_final3.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['roofline']['frac'],d['e2e']['value'],d['parity']['ok'],json.dumps(d['extra'].get('config4')))"
+timeout 200 ncu --set full --clock-control none -k regex:conv_tc_pair -s 2 -c 1 -o /tmp/p_real -f python tools/prof_real_conv.py 4 bf16 > /tmp/p.log 2>&1
+ncu -i /tmp/p_real.ncu-rep --page raw --csv > gpurun_out/prof_convpair_real_bf16_r2.raw.csv 2>/dev/null
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/conv_real_launches_r2.csv python tools/prof_real_conv.py 4 bf16 > /dev/null 2>&1
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/conv_launches_r2b.csv python tools/prof_conv.py 3 f32 nchw > /dev/null 2>&1
+ls -la gpurun_out/*.csv | tail -4
