@@ -1588,6 +1588,84 @@ static ConvSide* conv_side_stream() {
   return &s;
 }
 
+// Pre-pass (HBM bound) and GEMM (tensor bound) of an NCHW convolution over CHUNKS of images: the
+// pre-pass of chunk c + 1 runs on the caller's stream while the GEMM of chunk c runs on the
+// device's high-priority side stream (fork / join through events; nothing synchronises with the
+// host).  prepass(b0, nb, stream) / gemm(b0, nb, stream) work on images [b0, b0 + nb).  Chunks hold
+// >= 2 waves of pixel-tile pairs each, at most 16 (knob CPLXK_CONV_OVERLAP, default 4); a stream
+// that is being captured into a graph, or a small batch, keeps the simple serial form.
+template <typename Pre, typename Gemm>
+static int conv_run_chunked(const ConvTcGeom& g, cudaStream_t st, Pre&& prepass, Gemm&& gemm) {
+  int sms = 148, rc;
+  if ((rc = current_device_sm_count(&sms))) return rc;
+  const int64_t tiles_img = static_cast<int64_t>(g.tiles_h) * g.tiles_w;
+  int64_t per = (2 * static_cast<int64_t>(sms) + tiles_img - 1) / tiles_img;   // images per chunk, lower bound
+  int64_t nchunk = knobs().conv_overlap > 0 ? knobs().conv_overlap : 0;
+  if (nchunk > 16) nchunk = 16;
+  if (nchunk * per > g.B) nchunk = g.B / per;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (nchunk >= 2 && cudaStreamIsCapturing(st, &cap) != cudaSuccess) {
+    (void)cudaGetLastError();          // cannot tell: keep the serial form
+    cap = cudaStreamCaptureStatusActive;
+  }
+  ConvSide* side = (nchunk >= 2 && cap == cudaStreamCaptureStatusNone) ? conv_side_stream() : nullptr;
+  if (!side) {
+    if ((rc = prepass(0, g.B, st))) return rc;
+    return gemm(0, g.B, st);
+  }
+  std::lock_guard<std::mutex> lock(side->mu);
+  const int64_t nb = (g.B + nchunk - 1) / nchunk;
+  int64_t c = 0;
+#ifdef CPLXK_CONV_TRACE_BUILD      // side builds: begin / end of every chunk's pre-pass and GEMM on stderr
+  static cudaEvent_t tr[4][16];
+  static bool tr_ok = false;
+  if (!tr_ok) {
+    for (auto& row : tr)
+      for (auto& e : row) cudaEventCreate(&e);
+    tr_ok = true;
+  }
+#endif
+  for (int64_t b0 = 0; b0 < g.B; ++c, b0 += nb) {
+    const int64_t n = b0 + nb <= g.B ? nb : g.B - b0;
+#ifdef CPLXK_CONV_TRACE_BUILD
+    cudaEventRecord(tr[0][c], st);
+#endif
+    if ((rc = prepass(b0, n, st))) break;
+#ifdef CPLXK_CONV_TRACE_BUILD
+    cudaEventRecord(tr[1][c], st);
+#endif
+    if (cudaEventRecord(side->done[c], st) != cudaSuccess ||
+        cudaStreamWaitEvent(side->stream, side->done[c], 0) != cudaSuccess) {
+      rc = CPLXK_ERR_CUDA;
+      break;
+    }
+#ifdef CPLXK_CONV_TRACE_BUILD
+    cudaEventRecord(tr[2][c], side->stream);
+#endif
+    if ((rc = gemm(b0, n, side->stream))) break;
+#ifdef CPLXK_CONV_TRACE_BUILD
+    cudaEventRecord(tr[3][c], side->stream);
+#endif
+  }
+#ifdef CPLXK_CONV_TRACE_BUILD
+  if (rc == CPLXK_OK && std::getenv("CPLXK_CONV_TRACE")) {
+    cudaStreamSynchronize(side->stream);
+    cudaStreamSynchronize(st);
+    for (int64_t i = 0; i < c; ++i) {
+      float t[4];
+      for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tr[0][0], tr[k][i]);
+      std::fprintf(stderr, "conv_trace chunk %d: prepass %.3f .. %.3f ms, gemm %.3f .. %.3f ms\n",
+                   static_cast<int>(i), t[0], t[1], t[2], t[3]);
+    }
+  }
+#endif
+  // join (also on the error paths: the caller's stream never runs ahead of the side stream)
+  if (cudaEventRecord(side->join, side->stream) != cudaSuccess ||
+      cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess)
+    return CPLXK_ERR_CUDA;
+  return rc;
+}
+
 // fp32 NCHW planes on fp16 operands: transposing pre-pass (optimistic per-image scale, see
 // f16_image_scale_exp) -> weights with per-output-channel scales -> CTA-pair kernel on kind::f16.
 // The pre-pass is HBM bound and the GEMM tensor bound, so large batches run in CHUNKS of images:
@@ -1691,76 +1769,7 @@ static int launch_conv_f16(const void* x_re, const void* x_im, const void* w_re,
       g.Op, static_cast<int>(g.C), g.Cp, g.tOg, g.tCg, g.kh * g.kw);
   CPLXK_CUDA_TRY(cudaGetLastError());
 
-  // chunks of >= 2 waves of pixel-tile pairs each, at most 16; none while the stream is being captured
-  // (a captured graph keeps the simple serial form)
-  int sms = 148;
-  if ((rc = current_device_sm_count(&sms))) return rc;
-  const int64_t tiles_img = static_cast<int64_t>(g.tiles_h) * g.tiles_w;
-  int64_t per = (2 * static_cast<int64_t>(sms) + tiles_img - 1) / tiles_img;   // images per chunk, lower bound
-  int64_t nchunk = knobs().conv_overlap > 0 ? knobs().conv_overlap : 0;
-  if (nchunk > 16) nchunk = 16;
-  if (nchunk * per > g.B) nchunk = g.B / per;
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  if (nchunk >= 2 && cudaStreamIsCapturing(st, &cap) != cudaSuccess) {
-    (void)cudaGetLastError();          // cannot tell: keep the serial form
-    cap = cudaStreamCaptureStatusActive;
-  }
-  ConvSide* side = (nchunk >= 2 && cap == cudaStreamCaptureStatusNone) ? conv_side_stream() : nullptr;
-  if (!side) {
-    if ((rc = prepass(0, g.B, st))) return rc;
-    return gemm(0, g.B, st);
-  }
-  std::lock_guard<std::mutex> lock(side->mu);
-  const int64_t nb = (g.B + nchunk - 1) / nchunk;
-  int64_t c = 0;
-#ifdef CPLXK_CONV_TRACE_BUILD      // side builds: begin / end of every chunk's pre-pass and GEMM on stderr
-  static cudaEvent_t tr[4][16];
-  static bool tr_ok = false;
-  if (!tr_ok) {
-    for (auto& row : tr)
-      for (auto& e : row) cudaEventCreate(&e);
-    tr_ok = true;
-  }
-#endif
-  for (int64_t b0 = 0; b0 < g.B; ++c, b0 += nb) {
-    const int64_t n = b0 + nb <= g.B ? nb : g.B - b0;
-#ifdef CPLXK_CONV_TRACE_BUILD
-    cudaEventRecord(tr[0][c], st);
-#endif
-    if ((rc = prepass(b0, n, st))) break;
-#ifdef CPLXK_CONV_TRACE_BUILD
-    cudaEventRecord(tr[1][c], st);
-#endif
-    if (cudaEventRecord(side->done[c], st) != cudaSuccess ||
-        cudaStreamWaitEvent(side->stream, side->done[c], 0) != cudaSuccess) {
-      rc = CPLXK_ERR_CUDA;
-      break;
-    }
-#ifdef CPLXK_CONV_TRACE_BUILD
-    cudaEventRecord(tr[2][c], side->stream);
-#endif
-    if ((rc = gemm(b0, n, side->stream))) break;
-#ifdef CPLXK_CONV_TRACE_BUILD
-    cudaEventRecord(tr[3][c], side->stream);
-#endif
-  }
-#ifdef CPLXK_CONV_TRACE_BUILD
-  if (rc == CPLXK_OK && std::getenv("CPLXK_CONV_TRACE")) {
-    cudaStreamSynchronize(side->stream);
-    cudaStreamSynchronize(st);
-    for (int64_t i = 0; i < c; ++i) {
-      float t[4];
-      for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tr[0][0], tr[k][i]);
-      std::fprintf(stderr, "conv_trace chunk %d: prepass %.3f .. %.3f ms, gemm %.3f .. %.3f ms\n",
-                   static_cast<int>(i), t[0], t[1], t[2], t[3]);
-    }
-  }
-#endif
-  // join (also on the error paths: the caller's stream never runs ahead of the side stream)
-  if (cudaEventRecord(side->join, side->stream) != cudaSuccess ||
-      cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess)
-    return CPLXK_ERR_CUDA;
-  return rc;
+  return conv_run_chunked(g, st, prepass, gemm);
 }
 
 template <typename T, bool kVD>
@@ -1896,6 +1905,61 @@ static int launch_conv_rg(const void* x_re, const void* x_im, const void* w_re, 
   dim3 tg(static_cast<unsigned>(g.B * g.H), static_cast<unsigned>((g.Cp + 31) / 32),
           static_cast<unsigned>((g.W + 31) / 32));
   if (tg.y > 65535u || tg.z > 65535u || g.B * g.H > 0x7fffffff) return CPLXK_ERR_UNSUPPORTED;
+  if constexpr (kReal && !kVD) {
+    // ungrouped real planes: the persistent CTA-pair kernel (ConvPairCfg<.., kReal>; row mode for
+    // wide images) -- the one-tile-per-CTA kernel below pulls 32 KB per 256 MMA cycles through L2,
+    // twice what an SM can ingest -- with the transposing pre-pass and the GEMM over image chunks
+    // (conv_run_chunked)
+    const int64_t pix_tiles = g.B * g.tiles_h * g.tiles_w;
+    if (g.groups == 1 && knobs().conv_real_pair && knobs().conv_persistent && knobs().conv_pair &&
+        pix_tiles >= 2) {
+      const bool al = (reinterpret_cast<uintptr_t>(x_re) & 15u) == 0 &&
+                      (!x_im || (reinterpret_cast<uintptr_t>(x_im) & 15u) == 0) && g.Cp % 2 == 0;
+      const bool fast = al && (std::is_same<T, float>::value ? g.W % 4 == 0 : g.W % 8 == 0);
+      if (abs2 && !fast) return CPLXK_ERR_UNSUPPORTED;    // |x|^2 is formed by the 16-byte-load transposers only
+      const int64_t wtotal = static_cast<int64_t>(g.kh) * g.kw * g.Op * g.Cgp;
+      conv_wprep_kernel<T, kVD><<<static_cast<unsigned>(wtotal / 256 + 1 > 1184 ? 1184 : wtotal / 256 + 1), 256, 0, st>>>(
+          static_cast<const T*>(w_re), static_cast<const T*>(w_im), static_cast<const T*>(ls2), u, v, e,
+          g.Og, g.Ogp, g.Op, g.Cg, g.Cgp, g.tOg, g.tCg, g.kh * g.kw);
+      CPLXK_CUDA_TRY(cudaGetLastError());
+      CUtensorMap tm_w;
+      int rc;
+      if ((rc = make_w_map<T>(&tm_w, u, g))) return rc;
+      const int64_t img_in = g.C * g.H * g.W, img_a = g.H * g.W * g.Cp, img_out = g.O * g.Ho * g.Wo;
+      const int Ci = static_cast<int>(g.C), Hi = static_cast<int>(g.H), Wi = static_cast<int>(g.W);
+      auto prepass = [&](int64_t b0, int64_t nb, cudaStream_t cs) -> int {
+        const T* pr = static_cast<const T*>(x_re) + b0 * img_in;
+        const T* pi = x_im ? static_cast<const T*>(x_im) + b0 * img_in : nullptr;
+        T* or_ = a_re + b0 * img_a;
+        if (fast) {
+          const dim3 tf(static_cast<unsigned>(nb * g.H), static_cast<unsigned>((g.Cp + 63) / 64),
+                        static_cast<unsigned>((g.W + 63) / 64));
+          if constexpr (std::is_same<T, float>::value)
+            conv_nhwc_f32_v4_kernel<<<tf, 256, 0, cs>>>(pr, pi, or_, static_cast<float*>(nullptr), Ci, g.Cp, Hi, Wi, abs2);
+          else
+            conv_nhwc_bf16_v8_kernel<<<tf, 256, 0, cs>>>(pr, pi, or_, static_cast<__nv_bfloat16*>(nullptr), Ci, g.Cp, Hi, Wi, abs2);
+        } else {
+          const dim3 tgc(static_cast<unsigned>(nb * g.H), tg.y, tg.z);
+          conv_nhwc_kernel<T, kVD><<<tgc, 256, 0, cs>>>(pr, pi, or_, static_cast<T*>(nullptr), static_cast<T*>(nullptr),
+                                                        Ci, g.Cp, Hi, Wi);
+        }
+        CPLXK_CUDA_TRY(cudaGetLastError());
+        return CPLXK_OK;
+      };
+      const int halo = conv_row_halo(g);
+      auto gemm = [&](int64_t b0, int64_t nb, cudaStream_t gs) -> int {
+        ConvTcGeom gc = g;
+        gc.B = nb;
+        CUtensorMap tm_x;
+        int r;
+        if ((r = make_act_map<T>(&tm_x, a_re + b0 * img_a, gc, false, halo))) return r;
+        ConvTcEpi ec = ep;
+        ec.y_re = static_cast<T*>(ep.y_re) + b0 * img_out;
+        return launch_conv_pair<T, false, true>(tm_x, tm_x, tm_w, tm_w, gc, ec, nb * gc.tiles_h * gc.tiles_w * gc.tiles_n, gs);
+      };
+      return conv_run_chunked(g, st, prepass, gemm);
+    }
+  }
   bool done = false;
   if constexpr (std::is_same<T, __nv_bfloat16>::value && !kVD) {
     // 16-byte loads, 128-byte channel rows (the complex layers' fast transposer; x_im may be null)
@@ -1934,18 +1998,6 @@ static int launch_conv_rg(const void* x_re, const void* x_im, const void* w_re, 
 
   CUtensorMap tm_xr, tm_xi, tm_q, tm_u, tm_v, tm_e;
   int rc;
-  if constexpr (kReal && !kVD) {
-    // ungrouped real planes: the persistent CTA-pair kernel (ConvPairCfg<.., kReal>; row mode for
-    // wide images) -- the one-tile-per-CTA kernel below pulls 32 KB per 256 MMA cycles through L2,
-    // twice what an SM can ingest
-    const int64_t pix_tiles = g.B * g.tiles_h * g.tiles_w;
-    if (g.groups == 1 && knobs().conv_real_pair && knobs().conv_persistent && knobs().conv_pair &&
-        pix_tiles >= 2) {
-      if ((rc = make_act_map<T>(&tm_xr, a_re, g, false, conv_row_halo(g)))) return rc;
-      if ((rc = make_w_map<T>(&tm_u, u, g))) return rc;
-      return launch_conv_pair<T, false, true>(tm_xr, tm_xr, tm_u, tm_u, g, ep, pix_tiles * g.tiles_n, st);
-    }
-  }
   if ((rc = make_act_map<T>(&tm_xr, a_re, g))) return rc;
   if ((rc = make_w_map<T>(&tm_u, u, g))) return rc;
   tm_xi = tm_xr, tm_v = tm_u, tm_q = tm_xr, tm_e = tm_u;

@@ -38,11 +38,13 @@ def main():
             for dt, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
                 if "--fp32-nchw" in sys.argv and tag != "fp32":
                     continue
+                if "--bf16-nchw" in sys.argv and tag != "bf16":
+                    continue
                 convd, zd = conv.to(dt), z.to(dt)
                 zcl = cplx.Cplx(zd.real.contiguous(memory_format=torch.channels_last),
                                 zd.imag.contiguous(memory_format=torch.channels_last))
                 for name, inp in (("nchw", zd), ("nhwc", zcl)):
-                    if "--fp32-nchw" in sys.argv and name != "nchw":
+                    if ("--fp32-nchw" in sys.argv or "--bf16-nchw" in sys.argv) and name != "nchw":
                         continue
                     ms = timeit(lambda: convd(inp))
                     print(json.dumps(dict(lib=os.path.basename(lib), amax_pass=os.environ.get("CPLXK_CONV_AMAX_PASS", "0"), row=os.environ.get("CPLXK_CONV_ROW", "1"), overlap=os.environ.get("CPLXK_CONV_OVERLAP", "8"),

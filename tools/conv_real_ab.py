@@ -26,7 +26,7 @@ def timeit(fn, iters=10, warm=3):
 
 
 torch.manual_seed(0)
-knobs = {k: os.environ.get(k, "1") for k in ("CPLXK_CONV_REAL_PAIR", "CPLXK_CONV_ROW")}
+knobs = {k: os.environ.get(k, "1") for k in ("CPLXK_CONV_REAL_PAIR", "CPLXK_CONV_OVERLAP", "CPLXK_CONV_ROW")}
 with torch.no_grad():
     x = torch.randn(256, 64, 128, 128, device="cuda")
     w = torch.randn(64, 64, 3, 3, device="cuda") / 24
