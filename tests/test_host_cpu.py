@@ -240,3 +240,34 @@ def test_fused_kl_cache_bookkeeping_and_shard_requests():
     assert cache.take((w, ls2)) is None
     cache.put((w, ls2), {"kind": 0, "sum": s})
     assert cache.take((torch.nn.Parameter(w.detach().clone()), ls2)) is None   # other tensor
+
+
+def test_conv_abi_argument_contract_without_gpu():
+    """cplxk_conv2d_fwd_g rejects inconsistent plane sets BEFORE any CUDA call (include/cplxk.h): complex
+    input needs complex weights and output; an imaginary input plane with REAL weights and output is
+    the variance-operand form (real conv of |x|^2, complex/base.py:100-117) and exists on the
+    tensor-core path only -- no workspace / channels-last / variational -> CPLXK_ERR_UNSUPPORTED."""
+    lib = _native.lib()
+    buf = (ctypes.c_float * 64)()                       # never dereferenced: every call below is refused
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    geom = (1, 4, 8, 8, 4, 3, 3, 1, 1, 0, 0, 1, 1, 1)   # B C H W O kh kw sh sw ph pw dh dw groups
+
+    def call(x_im, w_im, y_im, ls2=None, channels_last=0, workspace=None, ws_bytes=0, math=_native.MATH_AUTO,
+             geometry=geom):
+        return lib.cplxk_conv2d_fwd_g(p, x_im, p, w_im, None, None, ls2, None, None, _native.NOISE_INJECT, 0, 0, 0,
+                                      p, y_im, *geometry, _native.F32, math, channels_last, workspace, ws_bytes, None)
+
+    assert call(p, p, None) == -1                       # complex input and weights, real output
+    assert call(p, None, p) == -1                       # complex output from real weights
+    assert call(None, p, None) == -1                    # real input, complex weights
+    assert call(p, None, None) == _native.ERR_UNSUPPORTED                 # variance form without a workspace
+    assert call(p, None, None, channels_last=1, workspace=p, ws_bytes=1 << 20) == _native.ERR_UNSUPPORTED
+    assert call(p, None, None, ls2=p, workspace=p, ws_bytes=1 << 20) == _native.ERR_UNSUPPORTED
+    assert call(p, None, None, math=_native.MATH_SIMT) == _native.ERR_UNSUPPORTED
+    bad = list(geom); bad[5] = 0                        # kh = 0
+    assert call(p, p, p, geometry=tuple(bad)) == -1
+    bad = list(geom); bad[13] = 3                       # C % groups != 0
+    assert call(p, p, p, geometry=tuple(bad)) == -1
+    empty = list(geom); empty[0] = 0                    # empty batch: nothing to do, no pointer is looked at
+    assert lib.cplxk_conv2d_fwd_g(None, None, None, None, None, None, None, None, None, 0, 0, 0, 0, None, None,
+                                  *empty, _native.F32, 0, 0, None, 0, None) == 0
